@@ -1,0 +1,139 @@
+/*
+ * smslu.h -- C ABI of libsmslu.so: B200-native sparse LU refactorization + triangular solves,
+ * the drop-in for the hot path of johnomotani/SharedMemSparseLU.jl.
+ *
+ * The reference has no FFI of its own; its boundary is the Julia API in
+ * /root/reference/src/SharedMemSparseLU.jl (cited below as src:N).  Each entry point names the
+ * reference interface it replaces; the Julia shim that `ccall`s these is
+ * sharedmemsparselu.jl_b200/julia/SharedMemSparseLU.jl and is reproduced in INTEGRATION.md.
+ *
+ * Conventions
+ *  - every function returns int: 0 = OK, negative = SMSLU_E_*; no exceptions, no exit().
+ *  - the caller owns every array it passes; nothing is retained after the call returns.
+ *    The handle owns all device memory and streams until smslu_destroy.
+ *  - indices at the ABI are int64 with an explicit index_base (Julia passes 1).
+ *  - value/vector pointers (nzval, Rs, x, b) may be HOST or DEVICE pointers; the library
+ *    asks the CUDA runtime which.  Host arrays are staged through pinned buffers.
+ *  - a handle is NOT thread-safe (the reference's F.wrk is shared state too, src:52, src:318);
+ *    distinct handles are independent.  Calls are synchronous on return.
+ *  - there is no CPU fallback: numeric calls fail with SMSLU_E_CUDA when no sm_100 GPU is usable.
+ */
+#ifndef SMSLU_H
+#define SMSLU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMSLU_OK 0
+#define SMSLU_E_DIM (-1)      /* -> Julia DimensionMismatch (src:288-290)                        */
+#define SMSLU_E_PIVOT (-2)    /* zero / non-finite pivot under the static pivot order -> SingularException */
+#define SMSLU_E_PATTERN (-3)  /* malformed CSC, or values do not match the analysed pattern -> ArgumentError */
+#define SMSLU_E_ARG (-4)      /* bad argument / wrong call order                                 */
+#define SMSLU_E_CUDA (-5)     /* CUDA runtime error or no usable device                           */
+#define SMSLU_E_OOM (-6)
+#define SMSLU_E_INTERNAL (-7)
+
+#define SMSLU_ORD_AUTO 0      /* ND_GRID when the grid hint matches n, else ND_GRAPH              */
+#define SMSLU_ORD_NATURAL 1
+#define SMSLU_ORD_GIVEN 2     /* use the (p,q) handed to smslu_analyze (e.g. UMFPACK's, from the Julia host) */
+#define SMSLU_ORD_ND_GRAPH 3  /* level-structure nested dissection on graph(A+A')                 */
+#define SMSLU_ORD_ND_GRID 4   /* geometric nested dissection, needs grid[]                         */
+
+#define SMSLU_SCALE_NONE 0
+#define SMSLU_SCALE_SUM 1     /* UMFPACK default: Rs[i] = 1/sum_j|a_ij| (what lu(A) at src:74 applies) */
+
+typedef struct smslu_handle_s* smslu_handle_t;
+
+typedef struct smslu_options {
+    int32_t ordering;        /* SMSLU_ORD_*                                                   */
+    int32_t grid[3];         /* nx, ny, nz with idx = i + nx*(j + ny*k); 0 = unknown          */
+    int32_t nd_leaf;         /* stop dissecting below this many vertices                       */
+    int32_t relax;           /* relaxed supernode amalgamation on/off                          */
+    int32_t max_width;       /* pivot-block width of a front (<= 32)                           */
+    int32_t scaling;         /* SMSLU_SCALE_*, used when smslu_refactor gets Rs == NULL        */
+    int32_t device;          /* CUDA device ordinal; -1 = current device                       */
+    int32_t use_graph;       /* replay the level schedule through CUDA graphs                  */
+    int32_t reserved[8];
+} smslu_options_t;
+
+typedef struct smslu_stats {
+    int64_t n, nnz_a;
+    int64_t nnz_l_exact, nnz_u_exact;   /* structural nnz incl. L's unit diagonal                */
+    int64_t nnz_l_stored, nnz_u_stored; /* entries held by the supernodal panels per factor      */
+    int64_t n_supernodes, n_levels, max_front, max_pivot_block, max_children, sum_rows;
+    int64_t lu_pool_doubles, cb_pool_doubles;
+    double flops_exact, flops_stored;   /* refactorization flops                                  */
+    double ms_analyze, ms_upload;
+    double ms_refactor, ms_solve;       /* device time of the last call (CUDA events)             */
+    double ms_refactor_h2d, ms_solve_h2d, ms_solve_d2h;
+    int64_t launches_refactor, launches_solve;  /* kernels launched by the last call             */
+    int64_t n_refactor, n_solve;        /* calls so far                                           */
+    int64_t bad_pivot_col;              /* permuted column of the first bad pivot, or -1          */
+    int64_t reserved[8];
+} smslu_stats_t;
+
+/* Fill *opts with defaults.  */
+int smslu_options_default(smslu_options_t* opts);
+
+/* Start of `ParallelSparseLU(A::SparseMatrixCSC{Float64,Int64}, chunk_size)` (src:64): take the
+ * pattern of A (colptr[n+1], rowval[nnz]).  Host-only; does not touch the GPU. */
+int smslu_create(smslu_handle_t* h, int64_t n, const int64_t* colptr, const int64_t* rowval,
+                 int32_t index_base, const smslu_options_t* opts);
+
+/* Symbolic half of `lu(A)` (src:74).  p, q: row/column permutations with
+ * L*U == (Rs .* A)[p,q] (src:307), index_base-based, only read when ordering == SMSLU_ORD_GIVEN;
+ * pass NULL for the native orderings.  Host-only.  The layout is uploaded on first numeric call. */
+int smslu_analyze(smslu_handle_t h, const int64_t* p, const int64_t* q);
+
+/* Numeric half of `lu(A)` (src:74) and all of `lu!(F, A)` (src:245-279) for a fixed pattern:
+ * nzval[nnz] in the order of the pattern given to smslu_create.  Rs: row multipliers indexed by
+ * original row (as UMFPACK's `.Rs`, src:263), or NULL to use opts.scaling. */
+int smslu_refactor(smslu_handle_t h, const double* nzval, const double* Rs);
+
+/* `ldiv!(x, F, b)` (src:286-342): x = A \ b; b is not modified.  nrhs = 1 is the reference
+ * signature; nrhs > 1 solves column-major blocks with leading dimensions ldx, ldb.
+ * nx / nb are the lengths of x and b per column (checked against n: SMSLU_E_DIM, src:288-290). */
+int smslu_solve(smslu_handle_t h, double* x, int64_t nx, const double* b, int64_t nb,
+                int64_t nrhs, int64_t ldx, int64_t ldb);
+
+/* `lsolve!(F, x)` (src:349-367) and `rsolve!(F, x)` (src:374-392): in place, in the permuted and
+ * scaled index space, x <- L^{-1} x  and  x <- U^{-1} x. */
+int smslu_lsolve(smslu_handle_t h, double* x, int64_t nx, int64_t nrhs, int64_t ld);
+int smslu_rsolve(smslu_handle_t h, double* x, int64_t nx, int64_t nrhs, int64_t ld);
+
+/* Fields `F.L F.U F.p F.q F.Rs` (src:47-51): CSC, rows sorted, L with explicit unit diagonal,
+ * exact structural pattern (relaxation padding removed).  Any pointer may be NULL. */
+int smslu_get_nnz(smslu_handle_t h, int64_t* nnz_l, int64_t* nnz_u);
+int smslu_get_factors(smslu_handle_t h, int64_t* l_colptr, int64_t* l_rowval, double* l_nzval,
+                      int64_t* u_colptr, int64_t* u_rowval, double* u_nzval,
+                      int64_t* p, int64_t* q, double* Rs, int32_t index_base);
+
+/* Diagnostics (no reference counterpart). */
+int smslu_get_stats(smslu_handle_t h, smslu_stats_t* stats);
+const char* smslu_last_error(smslu_handle_t h);
+/* Symbolic layout read-back for tests: any pointer may be NULL.  sn_start[nsn+1], rows_ptr[nsn+1],
+ * rows[sum_rows], sn_parent[nsn], sn_level[nsn], etree_parent[n], colcount[n]. */
+int smslu_get_symbolic(smslu_handle_t h, int64_t* sn_start, int64_t* rows_ptr, int64_t* rows,
+                       int64_t* sn_parent, int64_t* sn_level, int64_t* etree_parent, int64_t* colcount);
+
+/* `cleanup_ParallelSparseLU!(F)` (exported but undefined in the reference, src:31). */
+int smslu_destroy(smslu_handle_t h);
+
+/* `allocate_shared` (exported but undefined in the reference, src:31): name kept, no-op. */
+int smslu_allocate_shared(void);
+
+/* Page-locked host buffers for x / b / nzval so host<->device copies run at full PCIe speed
+ * (optional: any host pointer is accepted by the numeric calls). */
+int smslu_host_alloc(void** ptr, int64_t bytes);
+int smslu_host_free(void* ptr);
+
+/* Library/ABI version: major*10000 + minor*100 + patch. */
+int smslu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMSLU_H */

@@ -1,0 +1,569 @@
+// C ABI of libsmslu.so (include/smslu.h): handle, upload of the symbolic layout, level schedules,
+// and the numeric entry points.  No CPU fallback: numeric calls need a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/smslu.h"
+#include "kernels.cuh"
+#include "symbolic.hpp"
+
+using namespace smslu;
+
+namespace {
+
+enum LaunchKind { L_ZERO = 0, L_EXTEND, L_SMALL, L_PANEL, L_GEMM, L_FWD, L_BWD };
+
+struct Launch {
+    int kind;
+    int64_t off;
+    int ntasks;
+    int fmax;
+};
+
+double now_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+struct smslu_handle_s {
+    int n = 0;
+    int index_base = 0;
+    int64_t annz = 0;
+    std::vector<int64_t> Ap, Ai;   // 0-based pattern as given by the caller
+    smslu_options_t opt{};
+    Symbolic S;
+    bool analyzed = false, uploaded = false, factored = false;
+    std::string err;
+    smslu_stats_t st{};
+
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    std::vector<void*> dev_allocs;
+    DevCtx cx{};
+    int64_t* d_a_dst = nullptr;
+    int* d_a_row = nullptr;
+    int64_t *d_rowptr = nullptr, *d_rowidx = nullptr;
+    int *d_p = nullptr, *d_q = nullptr;
+    double *d_Rs = nullptr, *d_aval = nullptr, *d_w = nullptr, *d_z = nullptr, *d_xb = nullptr;
+    int4* d_tasks = nullptr;
+    std::vector<Launch> fac, fwd, bwd;
+
+    std::vector<int64_t> ex_ptr;   // exact structure, built lazily for get_factors
+    std::vector<int> ex_idx;
+    bool have_exact = false;
+};
+
+namespace {
+
+int fail(smslu_handle_t h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(h, e_ == cudaErrorMemoryAllocation ? SMSLU_E_OOM : SMSLU_E_CUDA,          \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                      \
+    } while (0)
+
+template <class T>
+int dev_alloc(smslu_handle_t h, T** p, size_t count) {
+    *p = nullptr;
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    cudaError_t e = cudaMalloc((void**)p, bytes);
+    if (e != cudaSuccess) return fail(h, SMSLU_E_OOM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    h->dev_allocs.push_back(*p);
+    return 0;
+}
+template <class T>
+int dev_upload(smslu_handle_t h, T** p, const std::vector<T>& v) {
+    int rc = dev_alloc(h, p, v.size());
+    if (rc) return rc;
+    if (!v.empty()) CU(cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+bool is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// ---------------------------------------------------------------- schedules
+void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
+    const Symbolic& S = h->S;
+    const int small_max = front_small_limit();
+    auto K = [&](int s) { return S.sn_start[s + 1] - S.sn_start[s]; };
+    auto R = [&](int s) { return (int64_t)(S.rows_ptr[s + 1] - S.rows_ptr[s]); };
+    auto NC = [&](int s) { return S.child_ptr[s + 1] - S.child_ptr[s]; };
+    auto push = [&](std::vector<Launch>& v, int kind, int64_t off, int fmax) {
+        int nt = (int)((int64_t)tasks.size() - off);
+        if (nt > 0) v.push_back(Launch{kind, off, nt, fmax});
+    };
+    h->fac.clear(); h->fwd.clear(); h->bwd.clear();
+    for (int l = 0; l < S.nlevels; ++l) {
+        const int* sn = S.level_sn.data() + S.level_ptr[l];
+        const int cnt = S.level_ptr[l + 1] - S.level_ptr[l];
+        int maxch = 0;
+        // zero the contribution blocks that children will be added into
+        int64_t off = (int64_t)tasks.size();
+        for (int t = 0; t < cnt; ++t) {
+            int s = sn[t];
+            maxch = std::max(maxch, NC(s));
+            if (NC(s) == 0 || R(s) == 0) continue;
+            int64_t tiles = (R(s) * R(s) + ZERO_TILE - 1) / ZERO_TILE;
+            for (int64_t i = 0; i < tiles; ++i) tasks.push_back(make_int4(s, (int)i, 0, 0));
+        }
+        push(h->fac, L_ZERO, off, 0);
+        // extend-add, one launch per child slot
+        for (int slot = 0; slot < maxch; ++slot) {
+            off = (int64_t)tasks.size();
+            for (int t = 0; t < cnt; ++t) {
+                int s = sn[t];
+                if (NC(s) <= slot) continue;
+                int c = S.child_idx[S.child_ptr[s] + slot];
+                int64_t rc = R(c);
+                if (rc == 0) continue;
+                int ncols = (int)std::max<int64_t>(1, std::min<int64_t>(rc, 4096 / rc));
+                for (int64_t b0 = 0; b0 < rc; b0 += ncols)
+                    tasks.push_back(make_int4(c, (int)b0, (int)std::min<int64_t>(ncols, rc - b0), 0));
+            }
+            push(h->fac, L_EXTEND, off, 0);
+        }
+        // fused small fronts by shared-memory class
+        const int classes[3] = {32, 64, small_max};
+        int lo = 0;
+        for (int ci = 0; ci < 3; ++ci) {
+            off = (int64_t)tasks.size();
+            for (int t = 0; t < cnt; ++t) {
+                int s = sn[t];
+                int64_t f = K(s) + R(s);
+                if (f > lo && f <= classes[ci]) tasks.push_back(make_int4(s, NC(s) > 0 ? 1 : 0, 0, 0));
+            }
+            push(h->fac, L_SMALL, off, classes[ci]);
+            lo = classes[ci];
+        }
+        // big fronts: panel then Schur update
+        off = (int64_t)tasks.size();
+        for (int t = 0; t < cnt; ++t) {
+            int s = sn[t];
+            int64_t r = R(s);
+            if (K(s) + r <= small_max) continue;
+            int nt = (int)((r + PANEL_ROWS - 1) / PANEL_ROWS);
+            for (int i = 0; i < 2 * nt; ++i) tasks.push_back(make_int4(s, i, nt, 2 * nt));
+        }
+        push(h->fac, L_PANEL, off, 0);
+        off = (int64_t)tasks.size();
+        for (int t = 0; t < cnt; ++t) {
+            int s = sn[t];
+            int64_t r = R(s);
+            if (K(s) + r <= small_max) continue;
+            int nt = (int)((r + GEMM_TILE - 1) / GEMM_TILE);
+            for (int j = 0; j < nt; ++j)
+                for (int i = 0; i < nt; ++i) tasks.push_back(make_int4(s, i, j, NC(s) > 0 ? 1 : 0));
+        }
+        push(h->fac, L_GEMM, off, 0);
+        // forward solve level
+        off = (int64_t)tasks.size();
+        for (int t = 0; t < cnt; ++t) {
+            int s = sn[t];
+            int nt = (int)std::max<int64_t>(1, (R(s) + FWD_ROWS - 1) / FWD_ROWS);
+            for (int i = 0; i < nt; ++i) tasks.push_back(make_int4(s, i, 0, 0));
+        }
+        push(h->fwd, L_FWD, off, 0);
+    }
+    for (int l = S.nlevels - 1; l >= 0; --l) {
+        int64_t off = (int64_t)tasks.size();
+        for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) tasks.push_back(make_int4(S.level_sn[t], 0, 0, 0));
+        push(h->bwd, L_BWD, off, 0);
+    }
+}
+
+int ensure_uploaded(smslu_handle_t h) {
+    if (h->uploaded) { CU(cudaSetDevice(h->device)); return 0; }
+    if (!h->analyzed) return fail(h, SMSLU_E_ARG, "smslu_analyze has not been called");
+    double t0 = now_ms();
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(h, SMSLU_E_CUDA, std::string("no usable CUDA device (no CPU fallback exists): ") + cudaGetErrorString(e));
+    if (h->opt.device >= 0) h->device = h->opt.device;
+    else CU(cudaGetDevice(&h->device));
+    CU(cudaSetDevice(h->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, h->device));
+    if (prop.major < 10) return fail(h, SMSLU_E_CUDA, "device is not sm_100 class; this library is built for sm_100a only");
+    CU(kernels_init());
+    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&h->ev0)); CU(cudaEventCreate(&h->ev1));
+    CU(cudaEventCreate(&h->ev2)); CU(cudaEventCreate(&h->ev3));
+    const Symbolic& S = h->S;
+    const int n = S.n;
+    int rc;
+    int *d_sn_start, *d_rows, *d_rel, *d_sn_parent, *d_child_ptr, *d_child_idx;
+    int64_t *d_rows_ptr, *d_Loff, *d_Uoff, *d_CBoff;
+    if ((rc = dev_upload(h, &d_sn_start, S.sn_start))) return rc;
+    if ((rc = dev_upload(h, &d_rows_ptr, S.rows_ptr))) return rc;
+    if ((rc = dev_upload(h, &d_rows, S.rows))) return rc;
+    if ((rc = dev_upload(h, &d_rel, S.rel))) return rc;
+    if ((rc = dev_upload(h, &d_Loff, S.Loff))) return rc;
+    if ((rc = dev_upload(h, &d_Uoff, S.Uoff))) return rc;
+    if ((rc = dev_upload(h, &d_CBoff, S.CBoff))) return rc;
+    if ((rc = dev_upload(h, &d_sn_parent, S.sn_parent))) return rc;
+    if ((rc = dev_upload(h, &d_child_ptr, S.child_ptr))) return rc;
+    if ((rc = dev_upload(h, &d_child_idx, S.child_idx))) return rc;
+    if ((rc = dev_upload(h, &h->d_a_dst, S.a_dst))) return rc;
+    if ((rc = dev_upload(h, &h->d_p, S.p))) return rc;
+    if ((rc = dev_upload(h, &h->d_q, S.q))) return rc;
+    {   // row index of every nonzero (for the scaling) and a row-major view of the pattern
+        std::vector<int> arow(h->annz);
+        std::vector<int64_t> rowptr(n + 1, 0), rowidx(h->annz);
+        for (int64_t t = 0; t < h->annz; ++t) { arow[t] = (int)h->Ai[t]; ++rowptr[h->Ai[t] + 1]; }
+        for (int i = 0; i < n; ++i) rowptr[i + 1] += rowptr[i];
+        std::vector<int64_t> w(rowptr.begin(), rowptr.end() - 1);
+        for (int c = 0; c < n; ++c)
+            for (int64_t t = h->Ap[c]; t < h->Ap[c + 1]; ++t) rowidx[w[h->Ai[t]]++] = t;
+        if ((rc = dev_upload(h, &h->d_a_row, arow))) return rc;
+        if ((rc = dev_upload(h, &h->d_rowptr, rowptr))) return rc;
+        if ((rc = dev_upload(h, &h->d_rowidx, rowidx))) return rc;
+    }
+    double *d_lu, *d_cb, *d_upd;
+    int *d_counters, *d_flag;
+    if ((rc = dev_alloc(h, &d_lu, (size_t)S.lu_size))) return rc;
+    if ((rc = dev_alloc(h, &d_cb, (size_t)S.cb_size))) return rc;
+    if ((rc = dev_alloc(h, &d_upd, (size_t)S.sum_r))) return rc;
+    if ((rc = dev_alloc(h, &d_counters, (size_t)S.nsn))) return rc;
+    if ((rc = dev_alloc(h, &d_flag, 1))) return rc;
+    if ((rc = dev_alloc(h, &h->d_Rs, (size_t)n))) return rc;
+    if ((rc = dev_alloc(h, &h->d_aval, (size_t)h->annz))) return rc;
+    if ((rc = dev_alloc(h, &h->d_w, (size_t)n))) return rc;
+    if ((rc = dev_alloc(h, &h->d_z, (size_t)n))) return rc;
+    if ((rc = dev_alloc(h, &h->d_xb, (size_t)n))) return rc;
+    {
+        std::vector<double> ones(n, 1.0);
+        CU(cudaMemcpy(h->d_Rs, ones.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+    }
+    std::vector<int4> tasks;
+    build_schedules(h, tasks);
+    if ((rc = dev_upload(h, &h->d_tasks, tasks))) return rc;
+    DevCtx& cx = h->cx;
+    cx.sn_start = d_sn_start; cx.rows_ptr = d_rows_ptr; cx.rows = d_rows; cx.rel = d_rel;
+    cx.Loff = d_Loff; cx.Uoff = d_Uoff; cx.CBoff = d_CBoff; cx.sn_parent = d_sn_parent;
+    cx.child_ptr = d_child_ptr; cx.child_idx = d_child_idx;
+    cx.lu = d_lu; cx.cb = d_cb; cx.upd = d_upd; cx.counters = d_counters; cx.flag = d_flag;
+    CU(cudaDeviceSynchronize());
+    h->uploaded = true;
+    h->st.ms_upload = now_ms() - t0;
+    return 0;
+}
+
+int run_schedule(smslu_handle_t h, const std::vector<Launch>& sched, const double* win, double* zx) {
+    for (const Launch& L : sched) {
+        const int4* tk = h->d_tasks + L.off;
+        switch (L.kind) {
+            case L_ZERO: launch_zero_cb(h->stream, h->cx, tk, L.ntasks); break;
+            case L_EXTEND: launch_extend_add(h->stream, h->cx, tk, L.ntasks); break;
+            case L_SMALL: launch_front_small(h->stream, h->cx, tk, L.ntasks, L.fmax); break;
+            case L_PANEL: launch_panel(h->stream, h->cx, tk, L.ntasks); break;
+            case L_GEMM: launch_gemm_cb(h->stream, h->cx, tk, L.ntasks); break;
+            case L_FWD: launch_fwd(h->stream, h->cx, tk, L.ntasks, win, zx); break;
+            case L_BWD: launch_bwd(h->stream, h->cx, tk, L.ntasks, zx); break;
+        }
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int smslu_version(void) { return 100; }
+int smslu_allocate_shared(void) { return 0; }
+
+int smslu_host_alloc(void** ptr, int64_t bytes) {
+    if (!ptr || bytes < 0) return SMSLU_E_ARG;
+    cudaError_t e = cudaMallocHost(ptr, (size_t)std::max<int64_t>(bytes, 1));
+    if (e != cudaSuccess) { *ptr = nullptr; cudaGetLastError(); return e == cudaErrorMemoryAllocation ? SMSLU_E_OOM : SMSLU_E_CUDA; }
+    return 0;
+}
+int smslu_host_free(void* ptr) {
+    if (!ptr) return 0;
+    return cudaFreeHost(ptr) == cudaSuccess ? 0 : SMSLU_E_CUDA;
+}
+
+int smslu_options_default(smslu_options_t* o) {
+    if (!o) return SMSLU_E_ARG;
+    memset(o, 0, sizeof(*o));
+    o->ordering = SMSLU_ORD_AUTO;
+    o->nd_leaf = 48;
+    o->relax = 1;
+    o->max_width = KMAX;
+    o->scaling = SMSLU_SCALE_SUM;
+    o->device = -1;
+    o->use_graph = 0;
+    return 0;
+}
+
+int smslu_create(smslu_handle_t* hp, int64_t n, const int64_t* colptr, const int64_t* rowval,
+                 int32_t index_base, const smslu_options_t* opts) {
+    if (!hp) return SMSLU_E_ARG;
+    *hp = nullptr;
+    if (!colptr || !rowval || n <= 0 || n > INT_MAX - 1 || (index_base != 0 && index_base != 1)) return SMSLU_E_ARG;
+    smslu_handle_t h = new (std::nothrow) smslu_handle_s();
+    if (!h) return SMSLU_E_OOM;
+    if (opts) h->opt = *opts; else smslu_options_default(&h->opt);
+    if (h->opt.max_width <= 0 || h->opt.max_width > KMAX) h->opt.max_width = KMAX;
+    h->n = (int)n;
+    h->index_base = index_base;
+    h->annz = colptr[n] - index_base;
+    if (h->annz < 0) { delete h; return SMSLU_E_PATTERN; }
+    h->Ap.resize(n + 1);
+    h->Ai.resize(h->annz);
+    for (int64_t c = 0; c <= n; ++c) h->Ap[c] = colptr[c] - index_base;
+    for (int64_t t = 0; t < h->annz; ++t) h->Ai[t] = rowval[t] - index_base;
+    h->st.n = n;
+    h->st.nnz_a = h->annz;
+    h->st.bad_pivot_col = -1;
+    *hp = h;
+    return 0;
+}
+
+int smslu_analyze(smslu_handle_t h, const int64_t* p, const int64_t* q) {
+    if (!h) return SMSLU_E_ARG;
+    if (h->uploaded) return fail(h, SMSLU_E_ARG, "pattern already uploaded; create a new handle to re-analyse");
+    double t0 = now_ms();
+    SymOptions o;
+    o.ordering = h->opt.ordering;
+    for (int d = 0; d < 3; ++d) o.grid[d] = h->opt.grid[d];
+    if (h->opt.nd_leaf > 0) o.nd_leaf = h->opt.nd_leaf;
+    o.relax = h->opt.relax;
+    o.max_width = h->opt.max_width;
+    std::vector<int> pp, qq;
+    if (o.ordering == ORD_GIVEN) {
+        if (!p || !q) return fail(h, SMSLU_E_ARG, "ordering GIVEN needs p and q");
+        pp.resize(h->n); qq.resize(h->n);
+        const int64_t base = h->index_base;   // p, q use the index base of the pattern
+        for (int i = 0; i < h->n; ++i) { pp[i] = (int)(p[i] - base); qq[i] = (int)(q[i] - base); }
+    }
+    int rc = analyze(h->n, h->Ap.data(), h->Ai.data(), pp.empty() ? nullptr : pp.data(),
+                     qq.empty() ? nullptr : qq.data(), o, h->S, h->err);
+    if (rc) return rc;
+    h->analyzed = true;
+    h->have_exact = false;
+    const Symbolic& S = h->S;
+    smslu_stats_t& st = h->st;
+    st.nnz_l_exact = st.nnz_u_exact = S.nnzL_exact;
+    st.nnz_l_stored = st.nnz_u_stored = S.nnzL_stored;
+    st.n_supernodes = S.nsn; st.n_levels = S.nlevels; st.max_front = S.max_front;
+    st.max_pivot_block = S.max_k; st.max_children = S.max_children; st.sum_rows = S.sum_r;
+    st.lu_pool_doubles = S.lu_size; st.cb_pool_doubles = S.cb_size;
+    st.flops_exact = S.flops_exact; st.flops_stored = S.flops_stored;
+    st.ms_analyze = now_ms() - t0;
+    return 0;
+}
+
+int smslu_refactor(smslu_handle_t h, const double* nzval, const double* Rs) {
+    if (!h || !nzval) return SMSLU_E_ARG;
+    int rc = ensure_uploaded(h);
+    if (rc) return rc;
+    const Symbolic& S = h->S;
+    h->factored = false;
+    CU(cudaEventRecord(h->ev0, h->stream));
+    const double* av = nzval;
+    if (!is_device_ptr(nzval)) {
+        CU(cudaMemcpyAsync(h->d_aval, nzval, sizeof(double) * h->annz, cudaMemcpyHostToDevice, h->stream));
+        av = h->d_aval;
+    }
+    if (Rs) {
+        CU(cudaMemcpyAsync(h->d_Rs, Rs, sizeof(double) * h->n, cudaMemcpyDefault, h->stream));
+    }
+    CU(cudaEventRecord(h->ev1, h->stream));
+    if (!Rs) {
+        if (h->opt.scaling == SMSLU_SCALE_SUM) launch_rowscale(h->stream, h->n, h->d_rowptr, h->d_rowidx, av, h->d_Rs);
+        else {
+            std::vector<double> ones(h->n, 1.0);
+            CU(cudaMemcpyAsync(h->d_Rs, ones.data(), sizeof(double) * h->n, cudaMemcpyHostToDevice, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+        }
+    }
+    const int clean = INT_MAX;
+    CU(cudaMemcpyAsync(h->cx.flag, &clean, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemsetAsync(h->cx.counters, 0, sizeof(int) * std::max(S.nsn, 1), h->stream));
+    CU(cudaMemsetAsync(h->cx.lu, 0, sizeof(double) * S.lu_size, h->stream));
+    launch_scatter(h->stream, h->annz, h->d_a_dst, h->d_a_row, h->d_Rs, av, h->cx.lu);
+    rc = run_schedule(h, h->fac, nullptr, nullptr);
+    if (rc) return rc;
+    CU(cudaEventRecord(h->ev2, h->stream));
+    int flag = 0;
+    CU(cudaMemcpyAsync(&flag, h->cx.flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1)); h->st.ms_refactor_h2d = ms;
+    CU(cudaEventElapsedTime(&ms, h->ev1, h->ev2)); h->st.ms_refactor = ms;
+    h->st.launches_refactor = (int64_t)h->fac.size() + 1 + ((!Rs && h->opt.scaling == SMSLU_SCALE_SUM) ? 1 : 0);
+    h->st.n_refactor++;
+    if (flag != INT_MAX) {
+        h->st.bad_pivot_col = flag;
+        char buf[160];
+        snprintf(buf, sizeof buf, "zero or non-finite pivot at permuted column %d under the static pivot order", flag);
+        return fail(h, SMSLU_E_PIVOT, buf);
+    }
+    h->st.bad_pivot_col = -1;
+    h->factored = true;
+    return 0;
+}
+
+static int check_vec(smslu_handle_t h, int64_t len, int64_t nrhs, int64_t ld, const char* what) {
+    if (len != h->n) return fail(h, SMSLU_E_DIM, std::string("`") + what + "` does not have same size as F");
+    if (nrhs < 1 || (nrhs > 1 && ld < h->n)) return fail(h, SMSLU_E_ARG, "bad nrhs / leading dimension");
+    return 0;
+}
+
+int smslu_solve(smslu_handle_t h, double* x, int64_t nx, const double* b, int64_t nb,
+                int64_t nrhs, int64_t ldx, int64_t ldb) {
+    if (!h || !x || !b) return SMSLU_E_ARG;
+    int rc;
+    if ((rc = check_vec(h, nx, nrhs, ldx, "x"))) return rc;
+    if ((rc = check_vec(h, nb, nrhs, ldb, "b"))) return rc;
+    if (!h->factored) return fail(h, SMSLU_E_ARG, "no valid factorization (call smslu_refactor)");
+    if ((rc = ensure_uploaded(h))) return rc;
+    const int n = h->n;
+    const bool xdev = is_device_ptr(x), bdev = is_device_ptr(b);
+    float h2d = 0, dev = 0, d2h = 0, ms;
+    for (int64_t c = 0; c < nrhs; ++c) {
+        const double* bc = b + c * ldb;
+        double* xc = x + c * ldx;
+        CU(cudaEventRecord(h->ev0, h->stream));
+        if (!bdev) { CU(cudaMemcpyAsync(h->d_xb, bc, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream)); bc = h->d_xb; }
+        CU(cudaEventRecord(h->ev1, h->stream));
+        launch_permute_scale(h->stream, n, h->d_p, h->d_Rs, bc, h->d_w);
+        if ((rc = run_schedule(h, h->fwd, h->d_w, h->d_z))) return rc;
+        if ((rc = run_schedule(h, h->bwd, nullptr, h->d_z))) return rc;
+        launch_unpermute(h->stream, n, h->d_q, h->d_z, xdev ? xc : h->d_xb);
+        CU(cudaEventRecord(h->ev2, h->stream));
+        if (!xdev) CU(cudaMemcpyAsync(xc, h->d_xb, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaEventRecord(h->ev3, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1)); h2d += ms;
+        CU(cudaEventElapsedTime(&ms, h->ev1, h->ev2)); dev += ms;
+        CU(cudaEventElapsedTime(&ms, h->ev2, h->ev3)); d2h += ms;
+    }
+    h->st.ms_solve_h2d = h2d; h->st.ms_solve = dev; h->st.ms_solve_d2h = d2h;
+    h->st.launches_solve = nrhs * ((int64_t)h->fwd.size() + (int64_t)h->bwd.size() + 2);
+    h->st.n_solve++;
+    return 0;
+}
+
+static int tri_solve(smslu_handle_t h, double* x, int64_t nx, int64_t nrhs, int64_t ld, bool lower) {
+    if (!h || !x) return SMSLU_E_ARG;
+    int rc;
+    if ((rc = check_vec(h, nx, nrhs, ld, "x"))) return rc;
+    if (!h->factored) return fail(h, SMSLU_E_ARG, "no valid factorization (call smslu_refactor)");
+    if ((rc = ensure_uploaded(h))) return rc;
+    const int n = h->n;
+    for (int64_t c = 0; c < nrhs; ++c) {
+        double* xc = x + c * ld;
+        if (lower) {
+            CU(cudaMemcpyAsync(h->d_w, xc, sizeof(double) * n, cudaMemcpyDefault, h->stream));
+            if ((rc = run_schedule(h, h->fwd, h->d_w, h->d_z))) return rc;
+        } else {
+            CU(cudaMemcpyAsync(h->d_z, xc, sizeof(double) * n, cudaMemcpyDefault, h->stream));
+            if ((rc = run_schedule(h, h->bwd, nullptr, h->d_z))) return rc;
+        }
+        CU(cudaMemcpyAsync(xc, h->d_z, sizeof(double) * n, cudaMemcpyDefault, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
+int smslu_lsolve(smslu_handle_t h, double* x, int64_t nx, int64_t nrhs, int64_t ld) { return tri_solve(h, x, nx, nrhs, ld, true); }
+int smslu_rsolve(smslu_handle_t h, double* x, int64_t nx, int64_t nrhs, int64_t ld) { return tri_solve(h, x, nx, nrhs, ld, false); }
+
+int smslu_get_nnz(smslu_handle_t h, int64_t* nnz_l, int64_t* nnz_u) {
+    if (!h || !h->analyzed) return SMSLU_E_ARG;
+    if (nnz_l) *nnz_l = h->S.nnzL_exact;
+    if (nnz_u) *nnz_u = h->S.nnzL_exact;
+    return 0;
+}
+
+int smslu_get_factors(smslu_handle_t h, int64_t* lp, int64_t* li, double* lx, int64_t* up, int64_t* ui,
+                      double* ux, int64_t* p, int64_t* q, double* Rs, int32_t index_base) {
+    if (!h || !h->analyzed) return SMSLU_E_ARG;
+    if (index_base != 0 && index_base != 1) return SMSLU_E_ARG;
+    const Symbolic& S = h->S;
+    if (p) for (int i = 0; i < S.n; ++i) p[i] = S.p[i] + index_base;
+    if (q) for (int i = 0; i < S.n; ++i) q[i] = S.q[i] + index_base;
+    const bool want_vals = lx || ux || Rs;
+    if (want_vals && !h->factored) return fail(h, SMSLU_E_ARG, "no valid factorization (call smslu_refactor)");
+    if (Rs) {
+        CU(cudaSetDevice(h->device));
+        CU(cudaMemcpy(Rs, h->d_Rs, sizeof(double) * S.n, cudaMemcpyDeviceToHost));
+    }
+    if (!(lp || li || lx || up || ui || ux)) return 0;
+    if (!h->have_exact) {
+        exact_structure(S, h->Ap.data(), h->Ai.data(), h->ex_ptr, h->ex_idx);
+        h->have_exact = true;
+    }
+    std::vector<double> lu;
+    if (lx || ux) {
+        CU(cudaSetDevice(h->device));
+        lu.resize((size_t)S.lu_size);
+        CU(cudaMemcpy(lu.data(), h->cx.lu, sizeof(double) * S.lu_size, cudaMemcpyDeviceToHost));
+    }
+    export_factors(S, h->ex_ptr, h->ex_idx, lu.empty() ? nullptr : lu.data(), index_base, lp, li,
+                   lu.empty() ? nullptr : lx, up, ui, lu.empty() ? nullptr : ux);
+    return 0;
+}
+
+int smslu_get_stats(smslu_handle_t h, smslu_stats_t* st) {
+    if (!h || !st) return SMSLU_E_ARG;
+    *st = h->st;
+    return 0;
+}
+
+const char* smslu_last_error(smslu_handle_t h) { return h ? h->err.c_str() : "null handle"; }
+
+int smslu_get_symbolic(smslu_handle_t h, int64_t* sn_start, int64_t* rows_ptr, int64_t* rows,
+                       int64_t* sn_parent, int64_t* sn_level, int64_t* etree_parent, int64_t* colcount) {
+    if (!h || !h->analyzed) return SMSLU_E_ARG;
+    const Symbolic& S = h->S;
+    if (sn_start) for (int s = 0; s <= S.nsn; ++s) sn_start[s] = S.sn_start[s];
+    if (rows_ptr) for (int s = 0; s <= S.nsn; ++s) rows_ptr[s] = S.rows_ptr[s];
+    if (rows) for (size_t t = 0; t < S.rows.size(); ++t) rows[t] = S.rows[t];
+    if (sn_parent) for (int s = 0; s < S.nsn; ++s) sn_parent[s] = S.sn_parent[s];
+    if (sn_level) for (int s = 0; s < S.nsn; ++s) sn_level[s] = S.sn_level[s];
+    if (etree_parent) for (int j = 0; j < S.n; ++j) etree_parent[j] = S.parent[j];
+    if (colcount) for (int j = 0; j < S.n; ++j) colcount[j] = S.colcount[j];
+    return 0;
+}
+
+int smslu_destroy(smslu_handle_t h) {
+    if (!h) return 0;
+    if (h->uploaded || h->stream) {
+        cudaSetDevice(h->device);
+        if (h->stream) cudaStreamSynchronize(h->stream);
+        for (void* p : h->dev_allocs) cudaFree(p);
+        if (h->ev0) cudaEventDestroy(h->ev0);
+        if (h->ev1) cudaEventDestroy(h->ev1);
+        if (h->ev2) cudaEventDestroy(h->ev2);
+        if (h->ev3) cudaEventDestroy(h->ev3);
+        if (h->stream) cudaStreamDestroy(h->stream);
+    }
+    delete h;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,389 @@
+// sm_100a kernels, see kernels.cuh for the data layout.  FP64 throughout.
+#include "kernels.cuh"
+
+#include <math.h>
+
+namespace smslu {
+
+namespace {
+
+struct Front {
+    int c0, k;
+    int64_t r, f;
+    double* P;
+    double* T;
+    double* C;
+};
+
+__device__ __forceinline__ Front load_front(const DevCtx& cx, int s) {
+    Front F;
+    F.c0 = cx.sn_start[s];
+    F.k = cx.sn_start[s + 1] - F.c0;
+    F.r = cx.rows_ptr[s + 1] - cx.rows_ptr[s];
+    F.f = F.k + F.r;
+    F.P = cx.lu + cx.Loff[s];
+    F.T = cx.lu + cx.Uoff[s];
+    F.C = cx.cb + cx.CBoff[s];
+    return F;
+}
+
+__device__ __forceinline__ bool bad_pivot(double p) { return !(fabs(p) > 0.0) || !isfinite(p); }
+
+// ------------------------------------------------------------------ row scaling (UMFPACK "SUM")
+__global__ void k_rowscale(int n, const int64_t* __restrict__ rowptr, const int64_t* __restrict__ rowidx,
+                           const double* __restrict__ av, double* __restrict__ Rs) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int64_t t = rowptr[i]; t < rowptr[i + 1]; ++t) s += fabs(av[rowidx[t]]);   // ascending column
+    Rs[i] = s > 0.0 ? 1.0 / s : 1.0;
+}
+
+// ------------------------------------------------------------------ A -> panels
+__global__ void k_scatter(int64_t nnz, const int64_t* __restrict__ dst, const int* __restrict__ arow,
+                          const double* __restrict__ Rs, const double* __restrict__ av, double* __restrict__ lu) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nnz; t += stride)
+        lu[dst[t]] = Rs[arow[t]] * av[t];
+}
+
+// ------------------------------------------------------------------ zero contribution blocks
+// task: x = supernode, y = tile
+__global__ void __launch_bounds__(256) k_zero_cb(DevCtx cx, const int4* __restrict__ tasks) {
+    int4 tk = tasks[blockIdx.x];
+    int64_t r = cx.rows_ptr[tk.x + 1] - cx.rows_ptr[tk.x];
+    int64_t tot = r * r;
+    double* C = cx.cb + cx.CBoff[tk.x];
+    int64_t lo = (int64_t)tk.y * ZERO_TILE, hi = lo + ZERO_TILE;
+    if (hi > tot) hi = tot;
+    for (int64_t e = lo + threadIdx.x; e < hi; e += 256) C[e] = 0.0;
+}
+
+// ------------------------------------------------------------------ extend-add child CB into parent
+// task: x = child supernode, y = first child-CB column, z = number of columns.
+// Within one launch every parent receives from at most one child => no write conflicts and a
+// fixed summation order (children are applied slot by slot, in ascending child order).
+__global__ void __launch_bounds__(256) k_extend_add(DevCtx cx, const int4* __restrict__ tasks) {
+    int4 tk = tasks[blockIdx.x];
+    const int c = tk.x;
+    const int64_t rc = cx.rows_ptr[c + 1] - cx.rows_ptr[c];
+    const int* __restrict__ rel = cx.rel + cx.rows_ptr[c];
+    const double* __restrict__ Cc = cx.cb + cx.CBoff[c];
+    const Front F = load_front(cx, cx.sn_parent[c]);
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    for (int b = tk.y + ty; b < tk.y + tk.z; b += 4) {
+        const int rb = rel[b];
+        const double* __restrict__ src = Cc + (int64_t)b * rc;
+        if (rb < F.k) {
+            double* dst = F.P + (int64_t)rb * F.f;
+            for (int a = tx; a < rc; a += 64) dst[rel[a]] += src[a];
+        } else {
+            double* dstC = F.C + (int64_t)(rb - F.k) * F.r - F.k;
+            double* dstT = F.T + (rb - F.k);
+            for (int a = tx; a < rc; a += 64) {
+                const int ra = rel[a];
+                if (ra < F.k) dstT[(int64_t)ra * F.r] += src[a];
+                else dstC[ra] += src[a];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ fused small front
+// One CTA holds the whole f x f front in shared memory: assemble, eliminate the k pivots, write
+// the panels and the contribution block back.  task: x = supernode, y = has assembled CB.
+__global__ void k_front_small(DevCtx cx, const int4* __restrict__ tasks) {
+    extern __shared__ double sm[];
+    int4 tk = tasks[blockIdx.x];
+    const Front F = load_front(cx, tk.x);
+    const int f = (int)F.f, k = F.k, r = (int)F.r;
+    const int ld = f | 1;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int e = tid; e < f * k; e += nt) { int i = e % f, j = e / f; sm[i + j * ld] = F.P[e]; }
+    for (int e = tid; e < r * k; e += nt) { int a = e % r, i = e / r; sm[i + (k + a) * ld] = F.T[e]; }
+    if (tk.y) {
+        for (int e = tid; e < r * r; e += nt) { int a = e % r, b = e / r; sm[(k + a) + (k + b) * ld] = F.C[e]; }
+    } else {
+        for (int e = tid; e < r * r; e += nt) { int a = e % r, b = e / r; sm[(k + a) + (k + b) * ld] = 0.0; }
+    }
+    __syncthreads();
+    const int tx = tid & 31, ty = tid >> 5, ny = nt >> 5;
+    for (int j = 0; j < k; ++j) {
+        const double piv = sm[j + j * ld];
+        if (tid == 0 && bad_pivot(piv)) atomicMin(cx.flag, F.c0 + j);
+        for (int i = j + 1 + tid; i < f; i += nt) sm[i + j * ld] /= piv;
+        __syncthreads();
+        for (int c = j + 1 + ty; c < f; c += ny) {
+            const double u = sm[j + c * ld];
+            for (int i = j + 1 + tx; i < f; i += 32) sm[i + c * ld] -= sm[i + j * ld] * u;
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < f * k; e += nt) { int i = e % f, j = e / f; F.P[e] = sm[i + j * ld]; }
+    for (int e = tid; e < r * k; e += nt) { int a = e % r, i = e / r; F.T[e] = sm[i + (k + a) * ld]; }
+    for (int e = tid; e < r * r; e += nt) { int a = e % r, b = e / r; F.C[e] = sm[(k + a) + (k + b) * ld]; }
+}
+
+// ------------------------------------------------------------------ panel: pivot-block LU + TRSMs
+// task: x = supernode, y = tile, z = number of L21 tiles (nt), w = total CTAs of this front.
+// Tiles [0,nt) solve 128 rows of L21 against U11, tiles [nt,2nt) solve 128 rows of U12' against
+// L11'.  Every CTA factors the (<=32x32) pivot block redundantly in shared memory; the CTA that
+// is last to have READ the unfactored block writes the factored one back (no CTA ever waits).
+__global__ void __launch_bounds__(PANEL_ROWS) k_panel(DevCtx cx, const int4* __restrict__ tasks) {
+    __shared__ double D[KMAX][KMAX + 1];
+    __shared__ int s_last;
+    int4 tk = tasks[blockIdx.x];
+    const Front F = load_front(cx, tk.x);
+    const int k = F.k, tid = threadIdx.x;
+    for (int e = tid; e < k * k; e += PANEL_ROWS) { int i = e % k, j = e / k; D[i][j] = F.P[i + (int64_t)j * F.f]; }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        int old = atomicAdd(cx.counters + tk.x, 1);
+        s_last = ((old + 1) % tk.w) == 0;
+    }
+    const int tx = tid & 31, ty = tid >> 5;
+    for (int j = 0; j < k; ++j) {
+        const double piv = D[j][j];
+        if (tid == 0 && bad_pivot(piv)) atomicMin(cx.flag, F.c0 + j);
+        if (tid > j && tid < k) D[tid][j] /= piv;
+        __syncthreads();
+        for (int c = j + 1 + ty; c < k; c += PANEL_ROWS / 32) {
+            const int i = j + 1 + tx;
+            if (i < k) D[i][c] -= D[i][j] * D[j][c];
+        }
+        __syncthreads();
+    }
+    if (s_last)
+        for (int e = tid; e < k * k; e += PANEL_ROWS) { int i = e % k, j = e / k; F.P[i + (int64_t)j * F.f] = D[i][j]; }
+    const int nt = tk.z;
+    double x[KMAX];
+    if (tk.y < nt) {   // L21 row: x <- x * U11^{-1}
+        const int64_t row = (int64_t)tk.y * PANEL_ROWS + tid;
+        if (row >= F.r) return;
+        double* src = F.P + F.k + row;
+#pragma unroll
+        for (int c = 0; c < KMAX; ++c) x[c] = c < k ? src[(int64_t)c * F.f] : 0.0;
+#pragma unroll
+        for (int c = 0; c < KMAX; ++c) {
+            if (c >= k) break;
+            double v = x[c];
+#pragma unroll
+            for (int p = 0; p < c; ++p) v -= x[p] * D[p][c];
+            x[c] = v / D[c][c];
+        }
+#pragma unroll
+        for (int c = 0; c < KMAX; ++c) if (c < k) src[(int64_t)c * F.f] = x[c];
+    } else {           // U12' row: x <- x * L11^{-T} (unit diagonal)
+        const int64_t row = (int64_t)(tk.y - nt) * PANEL_ROWS + tid;
+        if (row >= F.r) return;
+        double* src = F.T + row;
+#pragma unroll
+        for (int c = 0; c < KMAX; ++c) x[c] = c < k ? src[(int64_t)c * F.r] : 0.0;
+#pragma unroll
+        for (int c = 0; c < KMAX; ++c) {
+            if (c >= k) break;
+            double v = x[c];
+#pragma unroll
+            for (int p = 0; p < c; ++p) v -= x[p] * D[c][p];
+            x[c] = v;
+        }
+#pragma unroll
+        for (int c = 0; c < KMAX; ++c) if (c < k) src[(int64_t)c * F.r] = x[c];
+    }
+}
+
+// ------------------------------------------------------------------ Schur update of the CB
+// C (r x r) = beta*C - L21 (r x k) * U12 (k x r), U12 held transposed.  64x64 tile per CTA,
+// 4x4 per thread, whole K (<= 32) staged in shared memory once.
+// task: x = supernode, y = tile row, z = tile col, w = beta (1: CB was assembled, 0: overwrite)
+__global__ void __launch_bounds__(256) k_gemm_cb(DevCtx cx, const int4* __restrict__ tasks) {
+    __shared__ double As[KMAX][GEMM_TILE];
+    __shared__ double Bs[KMAX][GEMM_TILE];
+    int4 tk = tasks[blockIdx.x];
+    const Front F = load_front(cx, tk.x);
+    const int k = F.k, tid = threadIdx.x;
+    const int64_t m0 = (int64_t)tk.y * GEMM_TILE, n0 = (int64_t)tk.z * GEMM_TILE;
+    const double* __restrict__ A = F.P + F.k;
+    const double* __restrict__ B = F.T;
+    for (int e = tid; e < GEMM_TILE * k; e += 256) {
+        int a = e & (GEMM_TILE - 1), p = e >> 6;
+        int64_t ra = m0 + a, rb = n0 + a;
+        As[p][a] = ra < F.r ? A[ra + (int64_t)p * F.f] : 0.0;
+        Bs[p][a] = rb < F.r ? B[rb + (int64_t)p * F.r] : 0.0;
+    }
+    __syncthreads();
+    const int tx = tid & 15, ty = tid >> 4;
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    for (int p = 0; p < k; ++p) {
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { a[i] = As[p][tx + 16 * i]; b[i] = Bs[p][ty + 16 * i]; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int64_t col = n0 + ty + 16 * j;
+        if (col >= F.r) continue;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t row = m0 + tx + 16 * i;
+            if (row >= F.r) continue;
+            double* cp = F.C + row + col * F.r;
+            *cp = (tk.w ? *cp : 0.0) - acc[i][j];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ solves
+__global__ void k_permute_scale(int n, const int* __restrict__ p, const double* __restrict__ Rs,
+                                const double* __restrict__ b, double* __restrict__ w) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { int pi = p[i]; w[i] = Rs[pi] * b[pi]; }
+}
+__global__ void k_unpermute(int n, const int* __restrict__ q, const double* __restrict__ w, double* __restrict__ x) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[q[i]] = w[i];
+}
+
+// Forward substitution for one level.  task: x = supernode, y = row tile of the update vector.
+// y_s = L11^{-1} (w[cols] + children contributions); upd_s = children contributions - L21 y_s.
+// Every tile recomputes y_s (k <= 32); tile 0 stores it.  Children are gathered one at a time,
+// ascending, so the summation order is fixed.
+__global__ void __launch_bounds__(FWD_ROWS) k_fwd(DevCtx cx, const int4* __restrict__ tasks,
+                                                  const double* __restrict__ win, double* __restrict__ zout) {
+    __shared__ double ys[KMAX];
+    __shared__ double acc[FWD_ROWS];
+    int4 tk = tasks[blockIdx.x];
+    const int s = tk.x;
+    const Front F = load_front(cx, s);
+    const int k = F.k, tid = threadIdx.x;
+    const int64_t lo = (int64_t)tk.y * FWD_ROWS;            // first update row of this tile
+    if (tid < KMAX) ys[tid] = tid < k ? win[F.c0 + tid] : 0.0;
+    acc[tid] = 0.0;
+    __syncthreads();
+    for (int ci = cx.child_ptr[s]; ci < cx.child_ptr[s + 1]; ++ci) {
+        const int c = cx.child_idx[ci];
+        const int64_t rc = cx.rows_ptr[c + 1] - cx.rows_ptr[c];
+        const int* __restrict__ rel = cx.rel + cx.rows_ptr[c];
+        const double* __restrict__ uc = cx.upd + cx.rows_ptr[c];
+        for (int64_t a = tid; a < rc; a += FWD_ROWS) {
+            const int64_t ra = rel[a];
+            if (ra < k) ys[ra] += uc[a];
+            else if (ra - k >= lo && ra - k < lo + FWD_ROWS) acc[ra - k - lo] += uc[a];
+        }
+        __syncthreads();
+    }
+    if (tid < 32) {   // unit lower triangular solve with L11, one lane per row
+        double y = tid < k ? ys[tid] : 0.0;
+        for (int j = 0; j < k; ++j) {
+            const double yj = __shfl_sync(0xffffffffu, y, j);
+            if (tid > j && tid < k) y -= F.P[tid + (int64_t)j * F.f] * yj;
+        }
+        if (tid < k) {
+            ys[tid] = y;
+            if (tk.y == 0) zout[F.c0 + tid] = y;
+        }
+    }
+    __syncthreads();
+    const int64_t row = lo + tid;
+    if (row < F.r) {
+        double v = acc[tid];
+        const double* __restrict__ src = F.P + F.k + row;
+        for (int j = 0; j < k; ++j) v -= src[(int64_t)j * F.f] * ys[j];
+        cx.upd[cx.rows_ptr[s] + row] = v;
+    }
+}
+
+// Backward substitution for one level.  task: x = supernode.  One CTA per supernode:
+// x[cols] = U11^{-1} (x[cols] - U12 x[rows]).
+__global__ void __launch_bounds__(256) k_bwd(DevCtx cx, const int4* __restrict__ tasks, double* __restrict__ x) {
+    __shared__ double part[KMAX];
+    int4 tk = tasks[blockIdx.x];
+    const int s = tk.x;
+    const Front F = load_front(cx, s);
+    const int k = F.k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int* __restrict__ rows = cx.rows + cx.rows_ptr[s];
+    for (int i = warp; i < k; i += 8) {
+        const double* __restrict__ col = F.T + (int64_t)i * F.r;
+        double v = 0.0;
+        for (int64_t a = lane; a < F.r; a += 32) v += col[a] * x[rows[a]];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) part[i] = v;
+    }
+    __syncthreads();
+    if (tid < 32) {
+        double v = tid < k ? x[F.c0 + tid] - part[tid] : 0.0;
+        for (int j = k - 1; j >= 0; --j) {
+            double xj = 0.0;
+            if (tid == j) xj = v / F.P[j + (int64_t)j * F.f];
+            xj = __shfl_sync(0xffffffffu, xj, j);
+            if (tid == j) v = xj;
+            if (tid < j) v -= F.P[tid + (int64_t)j * F.f] * xj;
+        }
+        if (tid < k) x[F.c0 + tid] = v;
+    }
+}
+
+constexpr int SMALL_F_MAX = 96;
+
+}  // namespace
+
+int front_small_limit() { return SMALL_F_MAX; }
+
+cudaError_t kernels_init() {
+    int ld = SMALL_F_MAX | 1;
+    return cudaFuncSetAttribute(k_front_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(sizeof(double) * ld * SMALL_F_MAX));
+}
+
+void launch_rowscale(cudaStream_t st, int n, const int64_t* rowptr, const int64_t* rowidx, const double* av, double* Rs) {
+    k_rowscale<<<(n + 255) / 256, 256, 0, st>>>(n, rowptr, rowidx, av, Rs);
+}
+void launch_scatter(cudaStream_t st, int64_t nnz, const int64_t* dst, const int* arow, const double* Rs,
+                    const double* av, double* lu) {
+    int64_t blocks = (nnz + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    k_scatter<<<(int)blocks, 256, 0, st>>>(nnz, dst, arow, Rs, av, lu);
+}
+void launch_zero_cb(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks) {
+    if (ntasks > 0) k_zero_cb<<<ntasks, 256, 0, st>>>(cx, tasks);
+}
+void launch_extend_add(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks) {
+    if (ntasks > 0) k_extend_add<<<ntasks, 256, 0, st>>>(cx, tasks);
+}
+void launch_front_small(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int fmax) {
+    if (ntasks <= 0) return;
+    int threads = fmax <= 32 ? 64 : (fmax <= 64 ? 128 : 256);
+    size_t smem = sizeof(double) * (size_t)(fmax | 1) * fmax;
+    k_front_small<<<ntasks, threads, smem, st>>>(cx, tasks);
+}
+void launch_panel(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks) {
+    if (ntasks > 0) k_panel<<<ntasks, PANEL_ROWS, 0, st>>>(cx, tasks);
+}
+void launch_gemm_cb(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks) {
+    if (ntasks > 0) k_gemm_cb<<<ntasks, 256, 0, st>>>(cx, tasks);
+}
+void launch_permute_scale(cudaStream_t st, int n, const int* p, const double* Rs, const double* b, double* w) {
+    k_permute_scale<<<(n + 255) / 256, 256, 0, st>>>(n, p, Rs, b, w);
+}
+void launch_unpermute(cudaStream_t st, int n, const int* q, const double* w, double* x) {
+    k_unpermute<<<(n + 255) / 256, 256, 0, st>>>(n, q, w, x);
+}
+void launch_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const double* win, double* zout) {
+    if (ntasks > 0) k_fwd<<<ntasks, FWD_ROWS, 0, st>>>(cx, tasks, win, zout);
+}
+void launch_bwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, double* x) {
+    if (ntasks > 0) k_bwd<<<ntasks, 256, 0, st>>>(cx, tasks, x);
+}
+
+}  // namespace smslu

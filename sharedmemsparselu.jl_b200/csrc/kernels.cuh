@@ -1,0 +1,61 @@
+// Hand-written sm_100a kernels for the numeric hot path: multifrontal supernodal LU
+// refactorization (what UMFPACK does inside `lu!`, reference src/SharedMemSparseLU.jl:247) and
+// the level-scheduled supernodal triangular solves (reference lsolve!/rsolve!, src:349-392).
+//
+// Data layout in HBM (built once by symbolic.cpp):
+//   per supernode s with k pivot columns, r off-diagonal rows, f = k + r:
+//     P_s = lu + Loff[s] : f x k column-major (ld f).  Rows [0,k) are the pivot block (after
+//           factorization: L11 strictly below the diagonal, U11 on/above); rows [k,f) are L21.
+//     T_s = lu + Uoff[s] : r x k column-major (ld r) = U12 transposed.
+//     C_s = cb + CBoff[s]: r x r column-major contribution block (temporary).
+//   rows[rows_ptr[s] ..] : the r global (permuted) row indices, ascending.
+//   rel [rows_ptr[s] ..] : index of each of those rows inside the PARENT's front.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace smslu {
+
+constexpr int KMAX = 32;          // widest pivot block of a front (symbolic chains wider supernodes)
+constexpr int PANEL_ROWS = 128;   // rows of L21 / U12' handled by one panel CTA
+constexpr int GEMM_TILE = 64;
+constexpr int FWD_ROWS = 256;
+constexpr int ZERO_TILE = 8192;
+
+struct DevCtx {
+    const int* sn_start;
+    const int64_t* rows_ptr;
+    const int* rows;
+    const int* rel;
+    const int64_t* Loff;
+    const int64_t* Uoff;
+    const int64_t* CBoff;
+    const int* sn_parent;
+    const int* child_ptr;
+    const int* child_idx;
+    double* lu;
+    double* cb;
+    double* upd;        // forward-solve update vectors, sum_r doubles
+    int* counters;      // one per supernode, used by the panel kernel
+    int* flag;          // first bad pivot column (atomicMin), INT_MAX when clean
+};
+
+// ---- refactorization
+void launch_rowscale(cudaStream_t st, int n, const int64_t* rowptr, const int64_t* rowidx, const double* av, double* Rs);
+void launch_scatter(cudaStream_t st, int64_t nnz, const int64_t* dst, const int* arow, const double* Rs,
+                    const double* av, double* lu);
+void launch_zero_cb(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks);
+void launch_extend_add(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks);
+void launch_front_small(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int fmax);
+void launch_panel(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks);
+void launch_gemm_cb(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks);
+int front_small_limit();   // largest front the fused shared-memory kernel takes
+cudaError_t kernels_init();
+
+// ---- solves
+void launch_permute_scale(cudaStream_t st, int n, const int* p, const double* Rs, const double* b, double* w);
+void launch_unpermute(cudaStream_t st, int n, const int* q, const double* w, double* x);
+void launch_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const double* win, double* zout);
+void launch_bwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, double* x);
+
+}  // namespace smslu

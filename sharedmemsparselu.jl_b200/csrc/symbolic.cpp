@@ -1,0 +1,767 @@
+// Host-side symbolic analysis (see symbolic.hpp).  Plain C++17, no device code: testable on CPU.
+#include "symbolic.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <numeric>
+
+#include "../../include/smslu.h"
+
+namespace smslu {
+namespace {
+
+struct Graph {
+    int n = 0;
+    std::vector<int64_t> xadj;
+    std::vector<int> adj;   // sorted, unique, no self loops
+};
+
+// Graph of pattern(B + B') for B = A[p,q]; rinv/cinv map original row/col -> permuted index.
+Graph build_sym_graph(int n, const int64_t* Ap, const int64_t* Ai, const int* rinv, const int* cinv) {
+    Graph G;
+    G.n = n;
+    std::vector<int64_t> cnt(n + 1, 0);
+    for (int c = 0; c < n; ++c)
+        for (int64_t t = Ap[c]; t < Ap[c + 1]; ++t) {
+            int i = rinv[Ai[t]], j = cinv[c];
+            if (i == j) continue;
+            ++cnt[i + 1];
+            ++cnt[j + 1];
+        }
+    for (int i = 0; i < n; ++i) cnt[i + 1] += cnt[i];
+    std::vector<int> tmp(cnt[n]);
+    std::vector<int64_t> w(cnt.begin(), cnt.end() - 1);
+    for (int c = 0; c < n; ++c)
+        for (int64_t t = Ap[c]; t < Ap[c + 1]; ++t) {
+            int i = rinv[Ai[t]], j = cinv[c];
+            if (i == j) continue;
+            tmp[w[i]++] = j;
+            tmp[w[j]++] = i;
+        }
+    G.xadj.assign(n + 1, 0);
+    int64_t out = 0;
+    for (int i = 0; i < n; ++i) {
+        std::sort(tmp.begin() + cnt[i], tmp.begin() + cnt[i + 1]);
+        int64_t b = out;
+        for (int64_t t = cnt[i]; t < cnt[i + 1]; ++t)
+            if (out == b || tmp[out - 1] != tmp[t]) tmp[out++] = tmp[t];
+        G.xadj[i + 1] = out;
+    }
+    tmp.resize(out);
+    G.adj.swap(tmp);
+    return G;
+}
+
+// new vertex k is old vertex perm[k]
+Graph relabel(const Graph& G, const std::vector<int>& perm) {
+    int n = G.n;
+    std::vector<int> inv(n);
+    for (int k = 0; k < n; ++k) inv[perm[k]] = k;
+    Graph H;
+    H.n = n;
+    H.xadj.assign(n + 1, 0);
+    for (int k = 0; k < n; ++k) H.xadj[k + 1] = H.xadj[k] + (G.xadj[perm[k] + 1] - G.xadj[perm[k]]);
+    H.adj.resize(G.adj.size());
+    for (int k = 0; k < n; ++k) {
+        int v = perm[k];
+        int64_t o = H.xadj[k];
+        for (int64_t t = G.xadj[v]; t < G.xadj[v + 1]; ++t) H.adj[o++] = inv[G.adj[t]];
+        std::sort(H.adj.begin() + H.xadj[k], H.adj.begin() + H.xadj[k + 1]);
+    }
+    return H;
+}
+
+// ------------------------------------------------------------------ geometric nested dissection
+void nd_grid(const int dims[3], int leaf, std::vector<int>& order) {
+    const int nx = dims[0], ny = std::max(dims[1], 1), nz = std::max(dims[2], 1);
+    order.resize((size_t)nx * ny * nz);
+    struct Box { int lo[3], hi[3]; int64_t pos; };
+    std::vector<Box> st;
+    st.push_back(Box{{0, 0, 0}, {nx, ny, nz}, 0});
+    auto emit = [&](const int lo[3], const int hi[3], int64_t pos) {
+        for (int k = lo[2]; k < hi[2]; ++k)
+            for (int j = lo[1]; j < hi[1]; ++j)
+                for (int i = lo[0]; i < hi[0]; ++i) order[pos++] = i + nx * (j + ny * k);
+        return pos;
+    };
+    while (!st.empty()) {
+        Box b = st.back();
+        st.pop_back();
+        int64_t ext[3] = {b.hi[0] - b.lo[0], b.hi[1] - b.lo[1], b.hi[2] - b.lo[2]};
+        int64_t vol = ext[0] * ext[1] * ext[2];
+        int d = 0;
+        for (int a = 1; a < 3; ++a) if (ext[a] > ext[d]) d = a;
+        if (vol <= leaf || ext[d] < 3) { emit(b.lo, b.hi, b.pos); continue; }
+        int mid = b.lo[d] + (int)(ext[d] / 2);
+        Box L = b, R = b, Sp = b;
+        L.hi[d] = mid;
+        R.lo[d] = mid + 1;
+        Sp.lo[d] = mid; Sp.hi[d] = mid + 1;
+        int64_t vl = vol / ext[d] * (mid - b.lo[d]), vr = vol / ext[d] * (b.hi[d] - mid - 1);
+        L.pos = b.pos;
+        R.pos = b.pos + vl;
+        emit(Sp.lo, Sp.hi, b.pos + vl + vr);
+        st.push_back(L);
+        st.push_back(R);
+    }
+}
+
+// ------------------------------------------------------------------ graph nested dissection
+// George-style automatic nested dissection: the separator is a (trimmed) level set of a
+// rooted level structure started at a pseudo-peripheral vertex, chosen near the median.
+class GraphND {
+  public:
+    GraphND(const Graph& G, const SymOptions& o) : G_(G), opt_(o), region_(G.n, -1), level_(G.n, -1) {}
+
+    void run(std::vector<int>& order) {
+        const int n = G_.n;
+        order.assign(n, -1);
+        // dense vertices go last (they would wreck every level structure)
+        double thr = std::max(16.0, opt_.dense_factor * std::sqrt((double)n));
+        std::vector<int> normal, dense;
+        for (int v = 0; v < n; ++v)
+            ((double)(G_.xadj[v + 1] - G_.xadj[v]) > thr ? dense : normal).push_back(v);
+        if (normal.empty()) { std::iota(order.begin(), order.end(), 0); return; }
+        int64_t pos_dense = (int64_t)normal.size();
+        for (int v : dense) order[pos_dense++] = v;   // region_ stays -1 => invisible to BFS
+        struct Item { std::vector<int> verts; int64_t pos; };
+        std::vector<Item> st;
+        st.push_back(Item{std::move(normal), 0});
+        int next_region = 0;
+        std::vector<int> queue;
+        while (!st.empty()) {
+            Item it = std::move(st.back());
+            st.pop_back();
+            const int rid = next_region++;
+            for (int v : it.verts) region_[v] = rid;
+            // ---- connected components
+            std::vector<std::vector<int>> comps;
+            for (int v : it.verts) level_[v] = -1;
+            for (int v : it.verts) {
+                if (level_[v] != -1) continue;
+                comps.emplace_back();
+                bfs(v, rid, comps.back());
+            }
+            if (comps.size() > 1) {
+                int64_t pos = it.pos;
+                for (auto& c : comps) {
+                    int64_t sz = (int64_t)c.size();
+                    st.push_back(Item{std::move(c), pos});
+                    pos += sz;
+                }
+                continue;
+            }
+            std::vector<int>& comp = comps[0];
+            const int m = (int)comp.size();
+            if (m <= opt_.nd_leaf) {   // leaf: Cuthill-McKee style order from a peripheral vertex
+                int root = pseudo_peripheral(comp, rid);
+                std::vector<int> ord;
+                for (int v : comp) level_[v] = -1;
+                bfs(root, rid, ord);
+                for (int k = 0; k < m; ++k) order[it.pos + k] = ord[k];
+                continue;
+            }
+            int root = pseudo_peripheral(comp, rid);
+            std::vector<int> ord;
+            for (int v : comp) level_[v] = -1;
+            bfs(root, rid, ord);
+            int nlev = level_[ord.back()] + 1;
+            if (nlev < 3) {   // clique-like: no useful separator
+                for (int k = 0; k < m; ++k) order[it.pos + k] = ord[k];
+                continue;
+            }
+            std::vector<int> lcount(nlev, 0);
+            for (int v : ord) ++lcount[level_[v]];
+            // candidate separator levels: both sides keep >= 25% of the vertices; among those the
+            // narrowest level wins (penalised by imbalance).  Fallback: the median level.
+            int best = -1, median = -1; double best_score = 1e300; int64_t cum = 0;
+            for (int l = 0; l < nlev; ++l) {
+                int64_t before = cum; cum += lcount[l];
+                if (median < 0 && 2 * cum >= m) median = l;
+                if (l == 0 || l == nlev - 1) continue;
+                double fb = (double)before / m, fa = (double)(m - cum) / m;
+                if (fb < 0.25 || fa < 0.25) continue;
+                double score = (double)lcount[l] * (1.0 + std::fabs(fb - fa));
+                if (score < best_score) { best_score = score; best = l; }
+            }
+            if (best < 0) best = std::min(std::max(median, 1), nlev - 2);
+            std::vector<int> A, B, Sv;
+            for (int v : ord) {
+                int l = level_[v];
+                if (l < best) A.push_back(v);
+                else if (l > best) B.push_back(v);
+                else {
+                    bool touches_after = false;
+                    for (int64_t t = G_.xadj[v]; t < G_.xadj[v + 1] && !touches_after; ++t) {
+                        int u = G_.adj[t];
+                        if (region_[u] == rid && level_[u] == best + 1) touches_after = true;
+                    }
+                    (touches_after ? Sv : A).push_back(v);
+                }
+            }
+            if (Sv.empty() || A.empty() || B.empty()) {
+                for (int k = 0; k < m; ++k) order[it.pos + k] = ord[k];
+                continue;
+            }
+            int64_t pa = it.pos, pb = pa + (int64_t)A.size(), ps = pb + (int64_t)B.size();
+            for (size_t k = 0; k < Sv.size(); ++k) { order[ps + (int64_t)k] = Sv[k]; region_[Sv[k]] = -2; }
+            st.push_back(Item{std::move(A), pa});
+            st.push_back(Item{std::move(B), pb});
+        }
+    }
+
+  private:
+    // BFS inside region rid from root over vertices with level_ == -1; appends visit order.
+    void bfs(int root, int rid, std::vector<int>& out) {
+        size_t head = out.size();
+        level_[root] = 0;
+        out.push_back(root);
+        while (head < out.size()) {
+            int v = out[head++];
+            for (int64_t t = G_.xadj[v]; t < G_.xadj[v + 1]; ++t) {
+                int u = G_.adj[t];
+                if (region_[u] != rid || level_[u] != -1) continue;
+                level_[u] = level_[v] + 1;
+                out.push_back(u);
+            }
+        }
+    }
+    int pseudo_peripheral(const std::vector<int>& comp, int rid) {
+        int root = comp[0];
+        int64_t bestdeg = INT64_MAX;
+        for (int v : comp) {
+            int64_t d = G_.xadj[v + 1] - G_.xadj[v];
+            if (d < bestdeg) { bestdeg = d; root = v; }
+        }
+        int depth = -1;
+        std::vector<int> ord;
+        for (int iter = 0; iter < 4; ++iter) {
+            for (int v : comp) level_[v] = -1;
+            ord.clear();
+            bfs(root, rid, ord);
+            int d = level_[ord.back()];
+            if (d <= depth) break;
+            depth = d;
+            // smallest-degree vertex of the last level
+            int cand = ord.back(); int64_t cd = INT64_MAX;
+            for (size_t k = ord.size(); k-- > 0 && level_[ord[k]] == d;) {
+                int64_t dg = G_.xadj[ord[k] + 1] - G_.xadj[ord[k]];
+                if (dg < cd) { cd = dg; cand = ord[k]; }
+            }
+            root = cand;
+        }
+        return root;
+    }
+    const Graph& G_;
+    const SymOptions& opt_;
+    std::vector<int> region_, level_;
+};
+
+// ------------------------------------------------------------------ elimination tree etc.
+void etree(const Graph& G, std::vector<int>& parent) {
+    int n = G.n;
+    parent.assign(n, -1);
+    std::vector<int> anc(n, -1);
+    for (int j = 0; j < n; ++j)
+        for (int64_t t = G.xadj[j]; t < G.xadj[j + 1]; ++t) {
+            int r = G.adj[t];
+            if (r >= j) break;
+            while (anc[r] != -1 && anc[r] != j) { int nx = anc[r]; anc[r] = j; r = nx; }
+            if (anc[r] == -1) { anc[r] = j; parent[r] = j; }
+        }
+}
+
+void postorder(const std::vector<int>& parent, std::vector<int>& post) {
+    int n = (int)parent.size();
+    std::vector<int> head(n, -1), next(n, -1);
+    for (int j = n - 1; j >= 0; --j)
+        if (parent[j] != -1) { next[j] = head[parent[j]]; head[parent[j]] = j; }
+    post.clear();
+    post.reserve(n);
+    std::vector<int> st;
+    for (int r = 0; r < n; ++r) {
+        if (parent[r] != -1) continue;
+        st.push_back(r);
+        while (!st.empty()) {
+            int v = st.back();
+            int c = head[v];
+            if (c == -1) { post.push_back(v); st.pop_back(); }
+            else { head[v] = next[c]; st.push_back(c); }
+        }
+    }
+}
+
+// Column counts of the Cholesky-like factor of a postordered symmetric pattern
+// (skeleton-matrix / least-common-ancestor method of Gilbert, Ng and Peyton).
+void column_counts(const Graph& G, const std::vector<int>& parent, std::vector<int>& cc) {
+    int n = G.n;
+    std::vector<int> size(n, 1), first(n), maxfirst(n, -1), prevleaf(n, -1), anc(n);
+    std::vector<int64_t> delta(n);
+    for (int j = 0; j < n; ++j) if (parent[j] != -1) size[parent[j]] += size[j];
+    for (int j = 0; j < n; ++j) { first[j] = j - size[j] + 1; delta[j] = (size[j] == 1) ? 1 : 0; anc[j] = j; }
+    for (int j = 0; j < n; ++j) {
+        if (parent[j] != -1) --delta[parent[j]];
+        for (int64_t t = G.xadj[j]; t < G.xadj[j + 1]; ++t) {
+            int i = G.adj[t];
+            if (i <= j || first[j] <= maxfirst[i]) continue;
+            maxfirst[i] = first[j];
+            int jprev = prevleaf[i];
+            prevleaf[i] = j;
+            ++delta[j];
+            if (jprev != -1) {
+                int qn = jprev;
+                while (qn != anc[qn]) qn = anc[qn];
+                for (int s = jprev; s != qn;) { int sp = anc[s]; anc[s] = qn; s = sp; }
+                --delta[qn];
+            }
+        }
+        if (parent[j] != -1) anc[j] = parent[j];
+    }
+    cc.resize(n);
+    std::vector<int64_t> acc(delta);
+    for (int j = 0; j < n; ++j) if (parent[j] != -1) acc[parent[j]] += acc[j];
+    for (int j = 0; j < n; ++j) cc[j] = (int)acc[j];
+}
+
+// best-fit allocator over a growing arena, used to plan contribution-block lifetimes
+class Arena {
+  public:
+    int64_t alloc(int64_t len) {
+        if (len == 0) return 0;
+        auto it = by_size_.lower_bound(len);
+        if (it != by_size_.end()) {
+            int64_t sz = it->first, off = it->second;
+            by_size_.erase(it);
+            by_off_.erase(off);
+            if (sz > len) insert_free(off + len, sz - len);
+            return off;
+        }
+        // extend the arena; reuse a trailing free block if there is one
+        if (!by_off_.empty()) {
+            auto last = std::prev(by_off_.end());
+            if (last->first + last->second == top_) {
+                int64_t off = last->first, sz = last->second;
+                erase_free(off, sz);
+                top_ = off + len;
+                return off;
+            }
+        }
+        int64_t off = top_;
+        top_ += len;
+        return off;
+    }
+    void release(int64_t off, int64_t len) {
+        if (len == 0) return;
+        auto nx = by_off_.lower_bound(off);
+        if (nx != by_off_.end() && off + len == nx->first) {
+            int64_t nsz = nx->second, noff = nx->first;
+            erase_free(noff, nsz);
+            len += nsz;
+        }
+        auto pv = by_off_.lower_bound(off);
+        if (pv != by_off_.begin()) {
+            --pv;
+            if (pv->first + pv->second == off) {
+                int64_t poff = pv->first, psz = pv->second;
+                erase_free(poff, psz);
+                off = poff;
+                len += psz;
+            }
+        }
+        insert_free(off, len);
+    }
+    int64_t top() const { return top_; }
+
+  private:
+    void insert_free(int64_t off, int64_t len) { by_off_[off] = len; by_size_.emplace(len, off); }
+    void erase_free(int64_t off, int64_t len) {
+        by_off_.erase(off);
+        auto rng = by_size_.equal_range(len);
+        for (auto it = rng.first; it != rng.second; ++it)
+            if (it->second == off) { by_size_.erase(it); break; }
+    }
+    std::map<int64_t, int64_t> by_off_;
+    std::multimap<int64_t, int64_t> by_size_;
+    int64_t top_ = 0;
+};
+
+inline int64_t align2(int64_t x) { return (x + 1) & ~(int64_t)1; }
+
+}  // namespace
+
+int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const int* q_in,
+            const SymOptions& opt, Symbolic& S, std::string& err) {
+    S = Symbolic();
+    S.n = n;
+    if (n <= 0) { err = "matrix must have at least one row"; return SMSLU_E_DIM; }
+    S.annz = Ap[n];
+    for (int c = 0; c < n; ++c) {
+        if (Ap[c + 1] < Ap[c]) { err = "colptr is not monotone"; return SMSLU_E_PATTERN; }
+        for (int64_t t = Ap[c]; t < Ap[c + 1]; ++t)
+            if (Ai[t] < 0 || Ai[t] >= n) { err = "row index out of range"; return SMSLU_E_PATTERN; }
+    }
+    // ---------------------------------------------------------------- 1. initial ordering
+    std::vector<int> p0(n), q0(n);
+    int ordering = opt.ordering;
+    if (ordering == ORD_AUTO) {
+        int64_t g = (int64_t)opt.grid[0] * std::max(opt.grid[1], 1) * std::max(opt.grid[2], 1);
+        ordering = (opt.grid[0] > 0 && g == n) ? ORD_ND_GRID : ORD_ND_GRAPH;
+    }
+    if (ordering == ORD_GIVEN) {
+        if (!p_in || !q_in) { err = "ordering GIVEN needs p and q"; return SMSLU_E_ARG; }
+        std::vector<char> seenp(n, 0), seenq(n, 0);
+        for (int k = 0; k < n; ++k) {
+            if (p_in[k] < 0 || p_in[k] >= n || q_in[k] < 0 || q_in[k] >= n || seenp[p_in[k]] || seenq[q_in[k]]) {
+                err = "p/q is not a permutation";
+                return SMSLU_E_ARG;
+            }
+            seenp[p_in[k]] = seenq[q_in[k]] = 1;
+            p0[k] = p_in[k];
+            q0[k] = q_in[k];
+        }
+    } else if (ordering == ORD_NATURAL) {
+        std::iota(p0.begin(), p0.end(), 0);
+        q0 = p0;
+    } else if (ordering == ORD_ND_GRID) {
+        int64_t g = (int64_t)opt.grid[0] * std::max(opt.grid[1], 1) * std::max(opt.grid[2], 1);
+        if (opt.grid[0] <= 0 || g != n) { err = "grid hint does not match n"; return SMSLU_E_ARG; }
+        nd_grid(opt.grid, std::max(opt.nd_leaf, 1), p0);
+        q0 = p0;
+    } else if (ordering == ORD_ND_GRAPH) {
+        std::vector<int> id(n);
+        std::iota(id.begin(), id.end(), 0);
+        Graph G0 = build_sym_graph(n, Ap, Ai, id.data(), id.data());
+        GraphND nd(G0, opt);
+        nd.run(p0);
+        q0 = p0;
+    } else { err = "unknown ordering"; return SMSLU_E_ARG; }
+
+    // ---------------------------------------------------------------- 2. etree + postorder
+    std::vector<int> rinv(n), cinv(n);
+    for (int k = 0; k < n; ++k) { rinv[p0[k]] = k; cinv[q0[k]] = k; }
+    Graph G1 = build_sym_graph(n, Ap, Ai, rinv.data(), cinv.data());
+    std::vector<int> par1, post;
+    etree(G1, par1);
+    postorder(par1, post);
+    S.p.resize(n);
+    S.q.resize(n);
+    std::vector<int> ipost(n);
+    for (int k = 0; k < n; ++k) { S.p[k] = p0[post[k]]; S.q[k] = q0[post[k]]; ipost[post[k]] = k; }
+    Graph G = relabel(G1, post);
+    G1 = Graph();
+    S.parent.resize(n);
+    for (int k = 0; k < n; ++k) S.parent[k] = par1[post[k]] == -1 ? -1 : ipost[par1[post[k]]];
+    for (int k = 0; k < n; ++k) { rinv[S.p[k]] = k; cinv[S.q[k]] = k; }
+    const std::vector<int>& parent = S.parent;
+
+    // ---------------------------------------------------------------- 3. column counts
+    column_counts(G, parent, S.colcount);
+    const std::vector<int>& cc = S.colcount;
+    S.nnzL_exact = 0;
+    S.flops_exact = 0;
+    for (int j = 0; j < n; ++j) {
+        S.nnzL_exact += cc[j];
+        double c = cc[j] - 1;
+        S.flops_exact += c * (2.0 * c + 1.0);
+    }
+
+    // ---------------------------------------------------------------- 4. supernodes
+    std::vector<int> fs_start;   // fundamental (maximal) supernodes
+    const int W = std::max(1, opt.max_width);
+    for (int j = 0; j < n; ++j)   // wide supernodes become chains of <= W-column fronts
+        if (j == 0 || !(parent[j - 1] == j && cc[j] == cc[j - 1] - 1) || j - fs_start.back() >= W)
+            fs_start.push_back(j);
+    int nfs = (int)fs_start.size();
+    fs_start.push_back(n);
+    std::vector<int> gfirst(nfs);
+    std::vector<double> tru(nfs);
+    std::vector<char> dead(nfs, 0);
+    std::vector<int> col2fs(n);
+    for (int s = 0; s < nfs; ++s)
+        for (int j = fs_start[s]; j < fs_start[s + 1]; ++j) col2fs[j] = s;
+    for (int s = 0; s < nfs; ++s) {
+        gfirst[s] = fs_start[s];
+        double t = 0;
+        for (int j = fs_start[s]; j < fs_start[s + 1]; ++j) t += cc[j];
+        tru[s] = t;
+        if (!opt.relax) continue;
+        const int last = fs_start[s + 1] - 1;
+        const double rs = cc[last] - 1;
+        for (;;) {
+            int c = gfirst[s] - 1;
+            if (c < 0) break;
+            int pc = parent[c];
+            if (pc < gfirst[s] || pc > last) break;   // the group ending at c is not a child
+            int tgrp = col2fs[c];
+            double kt = c - gfirst[tgrp] + 1, ks = last - gfirst[s] + 1;
+            double kn = kt + ks;
+            if (kn > W) break;
+            double stored = kn * (kn + 1) / 2 + kn * rs;
+            double frac = 1.0 - (tru[tgrp] + tru[s]) / stored;
+            double lim = kn <= opt.relax_k1 ? opt.relax_f1 : (kn <= opt.relax_k2 ? opt.relax_f2 : opt.relax_f3);
+            if (!(kn <= opt.relax_always || frac <= lim)) break;
+            gfirst[s] = gfirst[tgrp];
+            tru[s] += tru[tgrp];
+            dead[tgrp] = 1;
+        }
+    }
+    S.sn_start.clear();
+    for (int s = 0; s < nfs; ++s) if (!dead[s]) S.sn_start.push_back(gfirst[s]);
+    S.nsn = (int)S.sn_start.size();
+    S.sn_start.push_back(n);
+    const int nsn = S.nsn;
+    S.col2sn.resize(n);
+    for (int s = 0; s < nsn; ++s)
+        for (int j = S.sn_start[s]; j < S.sn_start[s + 1]; ++j) S.col2sn[j] = s;
+    S.sn_parent.assign(nsn, -1);
+    for (int s = 0; s < nsn; ++s) {
+        int pl = parent[S.sn_start[s + 1] - 1];
+        S.sn_parent[s] = pl == -1 ? -1 : S.col2sn[pl];
+    }
+    S.child_ptr.assign(nsn + 1, 0);
+    for (int s = 0; s < nsn; ++s) if (S.sn_parent[s] != -1) ++S.child_ptr[S.sn_parent[s] + 1];
+    for (int s = 0; s < nsn; ++s) S.child_ptr[s + 1] += S.child_ptr[s];
+    S.child_idx.resize(S.child_ptr[nsn]);
+    {
+        std::vector<int> w(S.child_ptr.begin(), S.child_ptr.end() - 1);
+        for (int s = 0; s < nsn; ++s) if (S.sn_parent[s] != -1) S.child_idx[w[S.sn_parent[s]]++] = s;
+    }
+    S.max_children = 0;
+    for (int s = 0; s < nsn; ++s) S.max_children = std::max(S.max_children, S.child_ptr[s + 1] - S.child_ptr[s]);
+
+    // ---------------------------------------------------------------- 5. supernodal row structure
+    S.rows_ptr.assign(nsn + 1, 0);
+    S.rows.clear();
+    {
+        std::vector<int> marker(n, -1), list;
+        for (int s = 0; s < nsn; ++s) {
+            const int c0 = S.sn_start[s], last = S.sn_start[s + 1] - 1;
+            list.clear();
+            for (int j = c0; j <= last; ++j)
+                for (int64_t t = G.xadj[j + 1]; t-- > G.xadj[j];) {
+                    int i = G.adj[t];
+                    if (i <= last) break;
+                    if (marker[i] != s) { marker[i] = s; list.push_back(i); }
+                }
+            for (int t = S.child_ptr[s]; t < S.child_ptr[s + 1]; ++t) {
+                int c = S.child_idx[t];
+                for (int64_t u = S.rows_ptr[c + 1]; u-- > S.rows_ptr[c];) {
+                    int i = S.rows[u];
+                    if (i <= last) break;
+                    if (marker[i] != s) { marker[i] = s; list.push_back(i); }
+                }
+            }
+            std::sort(list.begin(), list.end());
+            if ((int)list.size() != cc[last] - 1) {
+                err = "internal: supernode row count disagrees with column count";
+                return SMSLU_E_INTERNAL;
+            }
+            S.rows.insert(S.rows.end(), list.begin(), list.end());
+            S.rows_ptr[s + 1] = (int64_t)S.rows.size();
+        }
+    }
+    // ---------------------------------------------------------------- 6. child -> parent index maps
+    S.rel.assign(S.rows.size(), -1);
+    for (int c = 0; c < nsn; ++c) {
+        int s = S.sn_parent[c];
+        if (s == -1) {
+            if (S.rows_ptr[c + 1] != S.rows_ptr[c]) { err = "internal: root supernode with rows"; return SMSLU_E_INTERNAL; }
+            continue;
+        }
+        const int pc0 = S.sn_start[s], plast = S.sn_start[s + 1] - 1, pk = plast - pc0 + 1;
+        int64_t u = S.rows_ptr[s];
+        for (int64_t t = S.rows_ptr[c]; t < S.rows_ptr[c + 1]; ++t) {
+            int i = S.rows[t];
+            if (i <= plast) { S.rel[t] = i - pc0; continue; }
+            while (u < S.rows_ptr[s + 1] && S.rows[u] < i) ++u;
+            if (u == S.rows_ptr[s + 1] || S.rows[u] != i) { err = "internal: child row missing in parent"; return SMSLU_E_INTERNAL; }
+            S.rel[t] = pk + (int)(u - S.rows_ptr[s]);
+        }
+    }
+    // ---------------------------------------------------------------- 7. levels
+    S.sn_level.assign(nsn, 0);
+    S.nlevels = 0;
+    for (int s = 0; s < nsn; ++s) {
+        if (S.sn_parent[s] != -1) S.sn_level[S.sn_parent[s]] = std::max(S.sn_level[S.sn_parent[s]], S.sn_level[s] + 1);
+        S.nlevels = std::max(S.nlevels, S.sn_level[s] + 1);
+    }
+    S.level_ptr.assign(S.nlevels + 1, 0);
+    for (int s = 0; s < nsn; ++s) ++S.level_ptr[S.sn_level[s] + 1];
+    for (int l = 0; l < S.nlevels; ++l) S.level_ptr[l + 1] += S.level_ptr[l];
+    S.level_sn.resize(nsn);
+    {
+        std::vector<int> w(S.level_ptr.begin(), S.level_ptr.end() - 1);
+        for (int s = 0; s < nsn; ++s) S.level_sn[w[S.sn_level[s]]++] = s;
+    }
+    // ---------------------------------------------------------------- 8. storage plan
+    S.Loff.resize(nsn);
+    S.Uoff.resize(nsn);
+    S.CBoff.assign(nsn, 0);
+    int64_t off = 0;
+    S.nnzL_stored = 0;
+    S.flops_stored = 0;
+    S.sum_r = (int64_t)S.rows.size();
+    for (int s = 0; s < nsn; ++s) {
+        int64_t k = S.sn_start[s + 1] - S.sn_start[s], r = S.rows_ptr[s + 1] - S.rows_ptr[s], f = k + r;
+        S.Loff[s] = off; off = align2(off + f * k);
+        S.Uoff[s] = off; off = align2(off + r * k);
+        S.nnzL_stored += k * (k + 1) / 2 + k * r;
+        S.max_front = std::max<int>(S.max_front, (int)f);
+        S.max_k = std::max<int>(S.max_k, (int)k);
+        double kd = (double)k, rd = (double)r;
+        S.flops_stored += 2.0 * kd * kd * kd / 3.0 + 2.0 * kd * kd * rd + 2.0 * kd * rd * rd;
+    }
+    S.lu_size = off;
+    {
+        Arena arena;
+        for (int l = 0; l < S.nlevels; ++l) {
+            for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) {
+                int s = S.level_sn[t];
+                int64_t r = S.rows_ptr[s + 1] - S.rows_ptr[s];
+                S.CBoff[s] = arena.alloc(align2(r * r));
+            }
+            for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) {
+                int s = S.level_sn[t];
+                for (int u = S.child_ptr[s]; u < S.child_ptr[s + 1]; ++u) {
+                    int c = S.child_idx[u];
+                    int64_t r = S.rows_ptr[c + 1] - S.rows_ptr[c];
+                    arena.release(S.CBoff[c], align2(r * r));
+                }
+            }
+        }
+        S.cb_size = arena.top();
+    }
+    // ---------------------------------------------------------------- 9. A -> factor scatter map
+    S.a_dst.resize(S.annz);
+    for (int c = 0; c < n; ++c) {
+        const int j = cinv[c];
+        for (int64_t t = Ap[c]; t < Ap[c + 1]; ++t) {
+            const int i = rinv[Ai[t]];
+            const int s = S.col2sn[std::min(i, j)];
+            const int c0 = S.sn_start[s], last = S.sn_start[s + 1] - 1;
+            const int64_t k = last - c0 + 1, r = S.rows_ptr[s + 1] - S.rows_ptr[s], f = k + r;
+            const int* rb = S.rows.data() + S.rows_ptr[s];
+            if (j <= last) {   // lands in the L panel (diagonal block included)
+                int64_t lr;
+                if (i <= last) lr = i - c0;
+                else {
+                    const int* it = std::lower_bound(rb, rb + r, i);
+                    if (it == rb + r || *it != i) { err = "internal: A entry outside L structure"; return SMSLU_E_INTERNAL; }
+                    lr = k + (it - rb);
+                }
+                S.a_dst[t] = S.Loff[s] + (int64_t)(j - c0) * f + lr;
+            } else {           // row in the pivot block, column beyond: U panel (stored transposed)
+                const int* it = std::lower_bound(rb, rb + r, j);
+                if (it == rb + r || *it != j) { err = "internal: A entry outside U structure"; return SMSLU_E_INTERNAL; }
+                S.a_dst[t] = S.Uoff[s] + (int64_t)(i - c0) * r + (it - rb);
+            }
+        }
+    }
+    return 0;
+}
+
+void exact_structure(const Symbolic& S, const int64_t* Ap, const int64_t* Ai,
+                     std::vector<int64_t>& ptr, std::vector<int>& idx) {
+    const int n = S.n;
+    std::vector<int> rinv(n), cinv(n);
+    for (int k = 0; k < n; ++k) { rinv[S.p[k]] = k; cinv[S.q[k]] = k; }
+    Graph G = build_sym_graph(n, Ap, Ai, rinv.data(), cinv.data());
+    std::vector<int> head(n, -1), next(n, -1);
+    for (int j = n - 1; j >= 0; --j)
+        if (S.parent[j] != -1) { next[j] = head[S.parent[j]]; head[S.parent[j]] = j; }
+    ptr.assign(n + 1, 0);
+    for (int j = 0; j < n; ++j) ptr[j + 1] = ptr[j] + S.colcount[j] - 1;
+    idx.resize(ptr[n]);
+    std::vector<int> marker(n, -1);
+    for (int j = 0; j < n; ++j) {
+        int64_t o = ptr[j];
+        for (int64_t t = G.xadj[j]; t < G.xadj[j + 1]; ++t) {
+            int i = G.adj[t];
+            if (i > j && marker[i] != j) { marker[i] = j; idx[o++] = i; }
+        }
+        for (int c = head[j]; c != -1; c = next[c])
+            for (int64_t t = ptr[c]; t < ptr[c + 1]; ++t) {
+                int i = idx[t];
+                if (i > j && marker[i] != j) { marker[i] = j; idx[o++] = i; }
+            }
+        std::sort(idx.begin() + ptr[j], idx.begin() + o);
+    }
+}
+
+}  // namespace smslu
+
+namespace smslu {
+
+void export_factors(const Symbolic& S, const std::vector<int64_t>& ptr, const std::vector<int>& idx,
+                    const double* lu, int64_t base, int64_t* Lp, int64_t* Li, double* Lx,
+                    int64_t* Up, int64_t* Ui, double* Ux) {
+    const int n = S.n;
+    // position of row i inside the front of supernode s
+    auto front_pos = [&](int s, int i) -> int64_t {
+        const int c0 = S.sn_start[s], last = S.sn_start[s + 1] - 1;
+        if (i <= last) return i - c0;
+        const int* rb = S.rows.data() + S.rows_ptr[s];
+        const int64_t r = S.rows_ptr[s + 1] - S.rows_ptr[s];
+        return (last - c0 + 1) + (std::lower_bound(rb, rb + r, i) - rb);
+    };
+    // ---- L: column j = unit diagonal + exact structure below it
+    if (Lp) {
+        Lp[0] = base;
+        for (int j = 0; j < n; ++j) Lp[j + 1] = Lp[j] + 1 + (ptr[j + 1] - ptr[j]);
+    }
+    if (Li || Lx) {
+        int64_t w = 0;
+        for (int j = 0; j < n; ++j) {
+            const int s = S.col2sn[j];
+            const int c0 = S.sn_start[s];
+            const int64_t k = S.sn_start[s + 1] - c0, f = k + (S.rows_ptr[s + 1] - S.rows_ptr[s]);
+            const double* col = lu + S.Loff[s] + (int64_t)(j - c0) * f;
+            if (Li) Li[w] = j + base;
+            if (Lx) Lx[w] = 1.0;
+            ++w;
+            for (int64_t t = ptr[j]; t < ptr[j + 1]; ++t, ++w) {
+                if (Li) Li[w] = idx[t] + base;
+                if (Lx) Lx[w] = col[front_pos(s, idx[t])];
+            }
+        }
+    }
+    // ---- U: row i of U has the structure of column i of L; emit by columns with sorted rows
+    if (Up || Ui || Ux) {
+        std::vector<int64_t> cnt(n + 1, 0);
+        for (int i = 0; i < n; ++i) {
+            ++cnt[i + 1];   // diagonal
+            for (int64_t t = ptr[i]; t < ptr[i + 1]; ++t) ++cnt[idx[t] + 1];
+        }
+        for (int j = 0; j < n; ++j) cnt[j + 1] += cnt[j];
+        if (Up) for (int j = 0; j <= n; ++j) Up[j] = cnt[j] + base;
+        if (Ui || Ux) {
+            std::vector<int64_t> w(cnt.begin(), cnt.end() - 1);
+            for (int i = 0; i < n; ++i) {   // ascending i => rows sorted inside every column
+                const int s = S.col2sn[i];
+                const int c0 = S.sn_start[s], last = S.sn_start[s + 1] - 1;
+                const int64_t k = last - c0 + 1, r = S.rows_ptr[s + 1] - S.rows_ptr[s], f = k + r;
+                const double* P = lu + S.Loff[s];
+                const double* T = lu + S.Uoff[s];
+                // strictly-upper entries of row i: columns idx[t] > i
+                for (int64_t t = ptr[i]; t < ptr[i + 1]; ++t) {
+                    const int j = idx[t];
+                    double v;
+                    if (j <= last) v = P[(int64_t)(j - c0) * f + (i - c0)];
+                    else v = T[(int64_t)(i - c0) * r + (front_pos(s, j) - k)];
+                    // column j receives rows in ascending order, but the diagonal of column j must
+                    // come last: it is written when i == j below, after all smaller rows
+                    int64_t o = w[j]++;
+                    if (Ui) Ui[o] = i + base;
+                    if (Ux) Ux[o] = v;
+                }
+                int64_t o = w[i]++;   // all rows < i of column i were emitted in earlier iterations
+                if (Ui) Ui[o] = i + base;
+                if (Ux) Ux[o] = P[(int64_t)(i - c0) * f + (i - c0)];
+            }
+        }
+    }
+}
+
+}  // namespace smslu

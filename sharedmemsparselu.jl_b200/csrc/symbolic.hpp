@@ -1,0 +1,85 @@
+// Host-side symbolic analysis: done once per sparsity pattern, result uploaded once.
+//
+// Replaces the symbolic half of UMFPACK that the reference enters through `lu(A)`
+// (reference src/SharedMemSparseLU.jl:74) and the reference's own solve "layout" step
+// (get_chunking_parameters, src:101-149): instead of dense column chunks over the row
+// envelope it produces a supernodal multifrontal layout -- fill-reducing ordering,
+// elimination tree, supernodes, per-supernode row lists, child->parent index maps,
+// the A->factor scatter map, storage offsets and the level schedule.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace smslu {
+
+enum Ordering { ORD_AUTO = 0, ORD_NATURAL = 1, ORD_GIVEN = 2, ORD_ND_GRAPH = 3, ORD_ND_GRID = 4 };
+
+struct SymOptions {
+    int ordering = ORD_AUTO;
+    int grid[3] = {0, 0, 0};      // nx, ny, nz hint for ORD_ND_GRID (idx = i + nx*(j + ny*k))
+    int nd_leaf = 48;             // stop dissecting below this many vertices
+    int max_width = 32;           // pivot-block width of a front; wider supernodes are chained
+    int relax = 1;                // relaxed supernode amalgamation on/off
+    int relax_always = 4;         // merged width <= this: always merge
+    int relax_k1 = 16;            // width <= k1: allow zero fraction relax_f1
+    int relax_k2 = 48;            // width <= k2: allow zero fraction relax_f2, else relax_f3
+    double relax_f1 = 0.5, relax_f2 = 0.15, relax_f3 = 0.05;
+    int dense_factor = 10;        // vertices with degree > dense_factor*sqrt(n) are ordered last
+};
+
+struct Symbolic {
+    int n = 0;
+    int64_t annz = 0;
+    std::vector<int> p, q;            // B = (Rs .* A)[p, q], 0-based, postordered
+    std::vector<int> parent;          // column elimination tree of pattern(B + B')
+    std::vector<int> colcount;        // exact |struct(L(:,j))| incl. diagonal
+
+    int nsn = 0;
+    std::vector<int> sn_start;        // nsn+1 column boundaries
+    std::vector<int> col2sn;          // n
+    std::vector<int64_t> rows_ptr;    // nsn+1
+    std::vector<int> rows;            // off-diagonal-block row indices, sorted, permuted numbering
+    std::vector<int> rel;             // same shape as rows: local index in the PARENT's front
+    std::vector<int> sn_parent;       // -1 for roots
+    std::vector<int> child_ptr, child_idx;   // children in ascending order
+    std::vector<int> sn_level;        // 0 = leaves
+    int nlevels = 0;
+    std::vector<int> level_ptr, level_sn;
+    int max_children = 0;
+
+    // factor storage (doubles): L panel f x k column-major (ld = f) holding the k x k diagonal
+    // block (L strictly below the diagonal, U on and above) on top of L21 (r x k);
+    // U panel r x k column-major (ld = r) holding U12 transposed.
+    std::vector<int64_t> Loff, Uoff;
+    int64_t lu_size = 0;
+    // contribution blocks r x r (ld = r), lifetime level(s)..level(parent(s))
+    std::vector<int64_t> CBoff;
+    int64_t cb_size = 0;
+    // for every nonzero of the caller's CSC, in the caller's order: offset into factor storage
+    std::vector<int64_t> a_dst;
+
+    int64_t nnzL_exact = 0;           // incl. unit diagonal; nnz(U) is the same number
+    int64_t nnzL_stored = 0;          // k(k+1)/2 + k*r summed (what the panels hold per factor)
+    double flops_exact = 0, flops_stored = 0;
+    int max_front = 0, max_k = 0;
+    int64_t sum_r = 0;
+};
+
+// Ap/Ai: CSC pattern, 0-based.  p_in/q_in: only for ORD_GIVEN (0-based, B = A[p,q]).
+// Returns 0 or a negative SMSLU_E_* code with a message in err.
+int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const int* q_in,
+            const SymOptions& opt, Symbolic& S, std::string& err);
+
+// Exact (unrelaxed) structure of L by columns, strictly below the diagonal, permuted numbering.
+// By symmetry of the pattern this is also the structure of the rows of U right of the diagonal.
+void exact_structure(const Symbolic& S, const int64_t* Ap, const int64_t* Ai,
+                     std::vector<int64_t>& ptr, std::vector<int>& idx);
+
+// Gather F.L / F.U (CSC, sorted rows, exact pattern, L with explicit unit diagonal) out of a host
+// copy of the factor storage.  colptr arrays have n+1 entries; any output may be null.
+void export_factors(const Symbolic& S, const std::vector<int64_t>& ptr, const std::vector<int>& idx,
+                    const double* lu, int64_t base, int64_t* Lp, int64_t* Li, double* Lx,
+                    int64_t* Up, int64_t* Ui, double* Ux);
+
+}  // namespace smslu

@@ -1,0 +1,147 @@
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def _have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+HAVE_GPU = _have_gpu()
+
+
+def pytest_collection_modifyitems(config, items):
+    if HAVE_GPU:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this container")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def smslu():
+    """The product package (builds libsmslu.so on demand)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_smslu_build", os.path.join(ROOT, "sharedmemsparselu.jl_b200", "build.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    b.build()
+    import smslu as m
+    return m
+
+
+@pytest.fixture(scope="session")
+def W(smslu):
+    from sharedmemsparselu_jl_b200 import workloads
+    return workloads
+
+
+@pytest.fixture(scope="session")
+def O():
+    from oracle import oracle
+    oracle.build()
+    return oracle
+
+
+class HostExec:
+    """ctypes wrapper of tests/hostexec.cpp (CPU walk over the device data structures)."""
+
+    def __init__(self):
+        src = [os.path.join(ROOT, "tests", "hostexec.cpp"),
+               os.path.join(ROOT, "sharedmemsparselu.jl_b200", "csrc", "symbolic.cpp")]
+        hdr = os.path.join(ROOT, "sharedmemsparselu.jl_b200", "csrc", "symbolic.hpp")
+        out = os.path.join(ROOT, "tests", "_build", "libhostexec.so")
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in src + [hdr]):
+            tmp = out + ".%d.tmp" % os.getpid()
+            subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-o", tmp] + src)
+            os.replace(tmp, out)
+        L = C.CDLL(out)
+        i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+        f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+        L.hx_create.restype = C.c_void_p
+        L.hx_create.argtypes = [C.c_longlong, i64p, i64p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                C.c_void_p, C.c_void_p]
+        L.hx_info.argtypes = [C.c_void_p, i64p, f64p]
+        L.hx_perm.argtypes = [C.c_void_p, i64p, i64p]
+        L.hx_factor.restype = C.c_longlong
+        L.hx_factor.argtypes = [C.c_void_p, f64p, C.c_void_p]
+        L.hx_solve.argtypes = [C.c_void_p, f64p, f64p]
+        L.hx_lsolve.argtypes = [C.c_void_p, f64p]
+        L.hx_rsolve.argtypes = [C.c_void_p, f64p]
+        L.hx_get_factors.argtypes = [C.c_void_p, i64p, i64p, f64p, i64p, i64p, f64p]
+        L.hx_free.argtypes = [C.c_void_p]
+        self.L = L
+
+    def run(self, A, ordering=0, grid=None, leaf=0, relax=1, maxw=0, p=None, q=None, Rs=None, factor=True):
+        import scipy.sparse as sp
+        A = sp.csc_matrix(A); A.sort_indices()
+        n = A.shape[0]
+        Ap = A.indptr.astype(np.int64); Ai = A.indices.astype(np.int64); Ax = A.data.astype(np.float64)
+        g = None if grid is None else np.array(list(grid) + [1] * (3 - len(grid)), dtype=np.int32)
+        pp = None if p is None else np.ascontiguousarray(p, np.int64)
+        qq = None if q is None else np.ascontiguousarray(q, np.int64)
+        h = self.L.hx_create(n, Ap, Ai, ordering, None if g is None else g.ctypes.data_as(C.c_void_p), leaf,
+                             relax, maxw, None if pp is None else pp.ctypes.data_as(C.c_void_p),
+                             None if qq is None else qq.ctypes.data_as(C.c_void_p))
+        assert h, "hx_create failed"
+        try:
+            info = np.zeros(16, np.int64); fl = np.zeros(2)
+            self.L.hx_info(h, info, fl)
+            keys = ("n", "nsn", "nlevels", "lu_size", "cb_size", "nnzL_exact", "nnzL_stored", "sum_r",
+                    "max_front", "max_k", "max_children")
+            out = dict(zip(keys, (int(v) for v in info)))
+            out["flops_exact"], out["flops_stored"] = float(fl[0]), float(fl[1])
+            po = np.zeros(n, np.int64); qo = np.zeros(n, np.int64)
+            self.L.hx_perm(h, po, qo)
+            out["p"], out["q"] = po, qo
+            if factor:
+                rs = None if Rs is None else np.ascontiguousarray(Rs, np.float64)
+                out["bad"] = int(self.L.hx_factor(h, Ax, None if rs is None else rs.ctypes.data_as(C.c_void_p)))
+                nl = out["nnzL_exact"]
+                Lp = np.zeros(n + 1, np.int64); Li = np.zeros(nl, np.int64); Lx = np.zeros(nl)
+                Up = np.zeros(n + 1, np.int64); Ui = np.zeros(nl, np.int64); Ux = np.zeros(nl)
+                self.L.hx_get_factors(h, Lp, Li, Lx, Up, Ui, Ux)
+                out.update(Lp=Lp, Li=Li, Lx=Lx, Up=Up, Ui=Ui, Ux=Ux)
+
+                def solve(b):
+                    x = np.zeros(n)
+                    self.L.hx_solve(h, np.ascontiguousarray(b, np.float64), x)
+                    return x
+                b = np.cos(np.arange(n) * 0.37) + 1.5
+                out["b"], out["x"] = b, solve(b)
+                y = b.copy(); self.L.hx_lsolve(h, y); out["lsolve_b"] = y
+                z = b.copy(); self.L.hx_rsolve(h, z); out["rsolve_b"] = z
+            return out
+        finally:
+            self.L.hx_free(h)
+
+
+@pytest.fixture(scope="session")
+def hostexec():
+    return HostExec()
+
+
+def relerr(a, b):
+    """max |a-b| / max(|b|, tiny) elementwise -- the 'relative' in 'L/U entries within 1e-12 relative'."""
+    a = np.asarray(a); b = np.asarray(b)
+    if a.size == 0:
+        return 0.0
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))

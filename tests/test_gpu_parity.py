@@ -1,0 +1,242 @@
+"""GPU: parity of the CUDA path (through the C ABI) with the CPU oracle, on the same inputs.
+
+Bar (BASELINE.json north_star): bit-exact symbolic structure, permutations and pivots; L/U entries
+within 1e-12 relative; solve residual no worse than the oracle's; lsolve!/rsolve!/ldiv! at the
+reference's own tolerances (test/runtests.jl:25-26: 1e-12, 1e-10 for dense / rsolve)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import relerr
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1.0e-12
+DENSE_TOL = 1.0e-10
+
+
+def isapprox(x, y, tol):
+    return np.linalg.norm(x - y) <= max(tol, tol * max(np.linalg.norm(x), np.linalg.norm(y)))
+
+
+def residual(A, x, b):
+    return np.linalg.norm(A @ x - b) / np.linalg.norm(b)
+
+
+CASES = {
+    "n1": lambda W: (sp.csc_matrix(np.array([[2.5]])), {}),
+    "diag7": lambda W: (sp.identity(7, format="csc") * 3.0, {}),
+    "lap2d_10": lambda W: (W.laplacian_2d(10), {}),
+    "lap2d_37x23": lambda W: (W.laplacian_2d(37, 23), {}),
+    "lap2d_37x23_grid": lambda W: (W.laplacian_2d(37, 23), dict(ordering="nd_grid", grid=(37, 23))),
+    "lap2d_64_norelax": lambda W: (W.laplacian_2d(64), dict(relax=False)),
+    "lap2d_64_w8": lambda W: (W.laplacian_2d(64), dict(max_width=8)),
+    "lap2d_100_config1": lambda W: (W.laplacian_2d(100), {}),          # BASELINE configs[0]
+    "lap2d_200": lambda W: (W.laplacian_2d(200), {}),
+    "lap3d_12": lambda W: (W.laplacian_3d(12), {}),
+    "lap3d_20": lambda W: (W.laplacian_3d(20), {}),
+    "natural_15": lambda W: (W.laplacian_2d(15), dict(ordering="natural")),
+    "fe_50_shifted": lambda W: (sp.csc_matrix(W.fe_test_matrix(50, seed=3) + 5 * sp.identity(201)), {}),
+    "dense_40_dd": lambda W: (sp.csc_matrix(W.dense_random(40, seed=2) + 40 * sp.identity(40)), {}),
+    "dense_150_dd": lambda W: (sp.csc_matrix(W.dense_random(150, seed=4) + 150 * sp.identity(150)), {}),
+    "block_border_small": lambda W: (W.block_border(nblocks=4, nel=5, ngr=5, border=8), {}),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_factor_and_solve_match_oracle(smslu, O, W, name):
+    A, kw = CASES[name](W)
+    n = A.shape[0]
+    F = smslu.ParallelSparseLU(A, **kw)
+    p, q, Rs = F.p, F.q, F.Rs
+    # permutations valid; row scaling bit-identical to the oracle's (same summation order)
+    assert np.array_equal(np.sort(p), np.arange(n)) and np.array_equal(np.sort(q), np.arange(n))
+    assert np.array_equal(Rs, O.row_scale_sum(A))
+    ref = O.OracleLU(A, p=p, q=q, Rs=Rs)
+    assert ref.bad_col == -1
+    L, U = F.L, F.U
+    # bit-exact structure
+    assert np.array_equal(L.indptr, ref.Lp) and np.array_equal(L.indices, ref.Li)
+    assert np.array_equal(U.indptr, ref.Up) and np.array_equal(U.indices, ref.Ui)
+    # entries within 1e-12 relative
+    assert relerr(L.data, ref.Lx) < 1e-12
+    assert relerr(U.data, ref.Ux) < 1e-12
+    # contract L*U == (Rs .* A)[p,q]  (src:307)
+    B = (sp.diags(Rs) @ A).tocsr()[p][:, q]
+    assert abs(L @ U - B).max() < 1e-13 * max(1.0, abs(B).max())
+    # lsolve! / rsolve! / ldiv!  (test:51,70,86,104,163)
+    b = W.rhs(n, 47)
+    x = b.copy(); smslu.lsolve_(F, x)
+    assert isapprox(x, ref.lsolve(b), TOL)
+    x = b.copy(); smslu.rsolve_(F, x)
+    assert isapprox(x, ref.usolve(b), DENSE_TOL)
+    x = np.empty(n); b0 = b.copy()
+    assert smslu.ldiv_(x, F, b) is x
+    assert np.array_equal(b, b0)                                   # b untouched (src:320-321)
+    xo = ref.solve(b)
+    assert isapprox(x, xo, TOL if n < 5000 else 1e-11)
+    assert residual(A, x, b) <= max(4 * residual(A, xo, b), 1e-15)
+    # new right-hand side (test:166-169)
+    b2 = W.rhs(n, 48)
+    smslu.ldiv_(x, F, b2)
+    assert isapprox(x, ref.solve(b2), TOL if n < 5000 else 1e-11)
+    smslu.cleanup_ParallelSparseLU_(F)
+
+
+@pytest.mark.parametrize("name", ["lap2d_37x23", "lap3d_12", "fe_50_shifted", "lap2d_200"])
+def test_refactor_with_new_values(smslu, O, W, name):
+    """lu!(F, A) with the same pattern and new values (src:245-279, test:171-186), repeatedly."""
+    A, kw = CASES[name](W)
+    n = A.shape[0]
+    F = smslu.ParallelSparseLU(A, **kw)
+    p, q = F.p.copy(), F.q.copy()
+    for k in range(1, 4):
+        A2 = A.copy()
+        A2.data = A.data * (1.0 + 0.05 * k * W.splitmix64(900 + k, A.nnz))
+        A2 = sp.csc_matrix(A2 + k * 1e-3 * sp.identity(n))
+        assert smslu.lu_(F, A2) is None
+        assert np.array_equal(F.p, p) and np.array_equal(F.q, q)     # static pivot order
+        ref = O.OracleLU(A2, p=p, q=q, Rs=F.Rs)
+        assert np.array_equal(F.L.indices, ref.Li)
+        assert relerr(F.L.data, ref.Lx) < 1e-12 and relerr(F.U.data, ref.Ux) < 1e-12
+        b = W.rhs(n, 60 + k)
+        x = np.empty(n)
+        smslu.ldiv_(x, F, b)
+        assert isapprox(x, ref.solve(b), TOL if n < 5000 else 1e-11)
+    F.close()
+
+
+@pytest.mark.parametrize("nel", [1, 2, 3, 7, 20, 64, 200])
+def test_reference_sparse_testsets_with_given_pivots(smslu, O, W, nel):
+    """The reference's 'lsolve!/rsolve!/sparse matrix' testsets (test:55-106, 148-188) on its
+    test_matrix fixture, with (p, q, Rs) handed in as the Julia shim hands in UMFPACK's."""
+    A = W.fe_test_matrix(nel, seed=nel)
+    n = A.shape[0]
+    piv = O.OracleLU(A, Rs=O.row_scale_sum(A))      # stand-in for UMFPACK's pivot search
+    F = smslu.ParallelSparseLU(A, p=piv.p, q=piv.q, Rs=piv.Rs)
+    ref = O.OracleLU(A, p=F.p, q=F.q, Rs=piv.Rs)
+    b = W.rhs(n, 5)
+    x = b.copy(); smslu.lsolve_(F, x)
+    assert isapprox(x, ref.lsolve(b), TOL)
+    x = b.copy(); smslu.rsolve_(F, x)
+    assert isapprox(x, ref.usolve(b), DENSE_TOL)
+    x = np.empty(n); smslu.ldiv_(x, F, b)
+    assert isapprox(x, ref.solve(b), TOL * 10)
+    assert isapprox(x, np.linalg.solve(A.toarray(), b), 1e-9)
+    F.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 8, 9, 33, 100, 200])
+def test_reference_dense_testsets_with_given_pivots(smslu, O, W, n):
+    """'lsolve!/rsolve!/dense matrix' testsets (test:38-53, 74-88, 108-146) on rand(n,n)."""
+    A = W.dense_random(n, seed=1000 + n)
+    piv = O.OracleLU(A, Rs=O.row_scale_sum(A), diag_tol=2.0)     # classical partial pivoting
+    F = smslu.ParallelSparseLU(A, p=piv.p, q=piv.q, Rs=piv.Rs)
+    ref = O.OracleLU(A, p=F.p, q=F.q, Rs=piv.Rs)
+    assert relerr(F.L.data, ref.Lx) < 1e-9 and relerr(F.U.data, ref.Ux) < 1e-9
+    b = W.rhs(n, 6)
+    x = b.copy(); smslu.lsolve_(F, x)
+    assert isapprox(x, ref.lsolve(b), TOL * 10)
+    x = b.copy(); smslu.rsolve_(F, x)
+    assert isapprox(x, ref.usolve(b), DENSE_TOL)
+    x = np.empty(n); smslu.ldiv_(x, F, b)
+    assert isapprox(x, np.linalg.solve(A.toarray(), b), DENSE_TOL * 10)
+    F.close()
+
+
+def test_errors(smslu, W):
+    A = W.laplacian_2d(6)
+    n = A.shape[0]
+    F = smslu.ParallelSparseLU(A)
+    with pytest.raises(smslu.DimensionMismatch):                    # src:289-290
+        smslu.ldiv_(np.empty(n + 1), F, np.ones(n))
+    with pytest.raises(smslu.DimensionMismatch):
+        smslu.ldiv_(np.empty(n), F, np.ones(n - 1))
+    with pytest.raises(smslu.SmsluError):                           # different pattern
+        smslu.lu_(F, W.laplacian_2d(6, 6, 0.0)[:, ::-1].tocsc())
+    S = sp.csc_matrix(np.array([[1.0, 2.0], [2.0, 4.0]]))
+    with pytest.raises(smslu.SingularException):
+        smslu.ParallelSparseLU(S, ordering="natural", scaling="none")
+    F.close()
+
+
+def test_device_resident_vectors(smslu, W):
+    import torch
+    A = W.laplacian_2d(40)
+    n = A.shape[0]
+    F = smslu.ParallelSparseLU(A)
+    b = W.rhs(n, 3)
+    xh = np.empty(n); smslu.ldiv_(xh, F, b)
+    bd = torch.from_numpy(b).cuda(); xd = torch.empty(n, dtype=torch.float64, device="cuda")
+    smslu.ldiv_(xd, F, bd)
+    torch.cuda.synchronize()
+    assert np.array_equal(xd.cpu().numpy(), xh)                     # deterministic, same bits
+    vd = torch.from_numpy(np.ascontiguousarray(A.data)).cuda()
+    smslu.lu_(F, vd)                                                # device-resident nzval
+    smslu.ldiv_(xd, F, bd)
+    torch.cuda.synchronize()
+    assert np.array_equal(xd.cpu().numpy(), xh)
+    xp = smslu.pinned_empty(n); bp = smslu.pinned_empty(n); bp[:] = b
+    smslu.ldiv_(xp, F, bp)
+    assert np.array_equal(np.asarray(xp), xh)
+    F.close()
+
+
+def test_multiple_rhs(smslu, O, W):
+    A = W.laplacian_3d(10)
+    n = A.shape[0]
+    F = smslu.ParallelSparseLU(A)
+    B = W.rhs(n, 47, nrhs=5)
+    X = np.empty((n, 5), order="F")
+    smslu.ldiv_(X, F, B)
+    for r in range(5):
+        x = np.empty(n); smslu.ldiv_(x, F, np.ascontiguousarray(B[:, r]))
+        assert np.array_equal(X[:, r], x)
+        assert residual(A, X[:, r], B[:, r]) < 1e-14
+    F.close()
+
+
+def test_bitwise_reproducible(smslu, W):
+    A = W.laplacian_2d(150)
+    n = A.shape[0]
+    b = W.rhs(n, 1)
+    outs = []
+    for _ in range(2):
+        F = smslu.ParallelSparseLU(A)
+        x = np.empty(n); smslu.ldiv_(x, F, b)
+        outs.append((x.copy(), F.L.data.copy()))
+        smslu.lu_(F, A); smslu.ldiv_(x, F, b)
+        outs.append((x.copy(), F.L.data.copy()))
+        F.close()
+    for x, l in outs[1:]:
+        assert np.array_equal(x, outs[0][0]) and np.array_equal(l, outs[0][1])
+
+
+@pytest.mark.parametrize("cfg", ["config2_lap2d_1024", "config5_lap3d_48"])
+def test_full_size_properties(smslu, W, cfg):
+    """BASELINE full sizes, where the oracle would take minutes: size-independent properties."""
+    A = W.laplacian_2d(1024) if cfg.startswith("config2") else W.laplacian_3d(48)
+    n = A.shape[0]
+    F = smslu.ParallelSparseLU(A)
+    st = F.stats()
+    assert st["bad_pivot_col"] == -1
+    x0 = W.rhs(n, 5) - 0.5
+    b = A @ x0
+    x = np.empty(n); smslu.ldiv_(x, F, b)
+    assert residual(A, x, b) < 1e-13                                 # residual
+    assert np.linalg.norm(x - x0) / np.linalg.norm(x0) < 1e-9        # round trip A*x0 -> x0
+    b2 = W.rhs(n, 6)
+    x2 = np.empty(n); smslu.ldiv_(x2, F, b2)
+    x3 = np.empty(n); smslu.ldiv_(x3, F, 2.0 * b + b2)               # linearity
+    assert np.linalg.norm(x3 - (2.0 * x + x2)) / np.linalg.norm(x3) < 1e-12
+    y = b2.copy(); smslu.lsolve_(F, y); smslu.rsolve_(F, y)          # ldiv! == unperm(rsolve(lsolve(perm)))
+    w = (F.Rs * b2)[F.p]
+    smslu.lsolve_(F, w); smslu.rsolve_(F, w)
+    xx = np.empty(n); xx[F.q] = w
+    assert np.array_equal(xx, x2)
+    # refactor with shifted values (config 2: A + k*1e-3*I), pattern fixed
+    A2 = sp.csc_matrix(A + 1e-3 * sp.identity(n)); A2.sort_indices()
+    smslu.lu_(F, A2)
+    smslu.ldiv_(x, F, b)
+    assert residual(A2, x, b) < 1e-13
+    F.close()
