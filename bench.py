@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py -- LU refactorize+solve per second (Laplacian, Float64) on N B200s.
+
+One "step" = one numeric refactorization (`lu!`, new values, fixed pattern) followed by one
+`ldiv!` with a fresh right-hand side, through libsmslu.so.  N=1 workload = BASELINE.json
+configs[1]: 2D 5-point Laplacian 1024x1024 (n = 1 048 576), refactor input k = A + k*1e-3*I,
+b from splitmix64(47+k).
+
+  value      : steps/s with nzval, b, x resident in HBM (stream-ordered calls, CUDA events on the
+               launching stream, max over ranks)
+  e2e        : same metric through the synchronous host API with pinned HOST buffers: H2D of nzval
+               and b and D2H of x inside the timed region
+  roofline   : the dominant kernel of the step (per-launch CUDA-event timing inside the library)
+  cpu_baseline / --impl reference : the CPU oracle port (oracle/ref_lu.c) on a bounded sample
+
+N>1 (torchrun): this round every rank factorizes its own copy ("replicas", weak scaling); the
+partitioned multi-GPU factorization with a Schur-complement exchange is described in DESIGN.md.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "lu_refactorize_plus_solve_per_sec"
+UNIT = "refactor+solve/s"
+
+
+# ----------------------------------------------------------------------------------------------
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measure_fp64_peak(torch):
+    """DGEMM throughput of this GPU (cuBLAS through torch.matmul), used only as the roofline
+    denominator for the FP64 GEMM kernel -- MEASURED_PEAKS.json has no FP64 entry."""
+    n = 6144
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    torch.matmul(a, b)
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(3):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def workload(grid):
+    from sharedmemsparselu_jl_b200 import workloads as W
+    A = W.laplacian_2d(grid)
+    return A, W
+
+
+def algorithmic_work(F, A):
+    """Algorithmic bytes / flops per kernel kind for one step (DESIGN.md 'Kernels')."""
+    import numpy as np
+    st = F.stats()
+    sym = F.symbolic()
+    k = np.diff(sym["sn_start"]).astype(np.float64)
+    r = np.diff(sym["rows_ptr"]).astype(np.float64)
+    f = k + r
+    big = f > 96
+    n, nnzL = float(A.shape[0]), float(st["nnz_l_exact"])
+    work = {
+        # FP64 flops of the Schur update of the big fronts: C(r x r) -= L21(r x k) U12(k x r)
+        "gemm_cb": {"flops": float(np.sum(2.0 * k[big] * r[big] * r[big])),
+                    "bytes": float(np.sum(8.0 * (2 * r[big] * r[big] + 2 * r[big] * k[big])))},
+        # fused small fronts: read+write panels and CB once, partial LU flops
+        "front_small": {"flops": float(np.sum((2.0 / 3) * k[~big] ** 3 + 2 * k[~big] ** 2 * r[~big] + 2 * k[~big] * r[~big] ** 2)),
+                        "bytes": float(np.sum(16.0 * (k[~big] * f[~big] + k[~big] * r[~big] + r[~big] ** 2)))},
+        "panel": {"flops": float(np.sum(2.0 * k[big] ** 2 * r[big])),
+                  "bytes": float(np.sum(16.0 * (2 * r[big] * k[big])))},
+        # extend-add: read every child CB once, read-modify-write the parent entries
+        "extend_add": {"flops": float(np.sum(r * r)), "bytes": float(np.sum(24.0 * r * r))},
+        "zero_cb": {"flops": 0.0, "bytes": float(np.sum(8.0 * r * r))},
+        "scatter": {"flops": float(A.nnz), "bytes": 8.0 * st["lu_pool_doubles"] + 28.0 * A.nnz},
+        # one solve, nrhs = 1: 12*(nnz(L)-n+nnz(U)) + 8n*(2+1) + 8n   (SURVEY 8d), split evenly
+        "fwd": {"flops": 2.0 * (nnzL - n), "bytes": 12.0 * (nnzL - n) + 16.0 * n},
+        "bwd": {"flops": 2.0 * nnzL, "bytes": 12.0 * nnzL + 16.0 * n},
+    }
+    return work, st
+
+
+def cpu_oracle_sample(sample_grid, full_flops):
+    """Oracle port timed on a smaller grid of the same stencil, scaled by the flop ratio."""
+    import numpy as np
+    import smslu
+    from sharedmemsparselu_jl_b200 import _SymbolicOnly, workloads as W
+    from oracle import oracle as O
+    As = W.laplacian_2d(sample_grid)
+    ns = As.shape[0]
+    S = _SymbolicOnly(As)                       # same ordering code as the GPU path (host only)
+    p, q = S.p.copy(), S.q.copy()
+    fl = S.stats()["flops_exact"]
+    S.close()
+    Rs = O.row_scale_sum(As)
+    t0 = time.perf_counter()
+    Fo = O.OracleLU(As, p=p, q=q, Rs=Rs)
+    t1 = time.perf_counter()
+    x = Fo.solve(W.rhs(ns, 47))
+    t2 = time.perf_counter()
+    scale = full_flops / fl
+    t_full = (t1 - t0) * scale + (t2 - t1) * scale ** 0.5
+    return {"value": 1.0 / t_full, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "oracle/ref_lu.c left-looking LU + CSC solves on a %dx%d grid of the same stencil with the "
+                      "GPU path's ordering (%.2f s factor, %.3f s solve), factor time scaled by the flop ratio %.1f"
+                      % (sample_grid, sample_grid, t1 - t0, t2 - t1, scale),
+            "sample_seconds": t2 - t0}
+
+
+def superlu_standin(A, W):
+    """SciPy SuperLU (single thread) on the FULL workload: a stand-in for the UMFPACK the reference
+    calls (src:74, 247); reported for context next to the oracle port."""
+    import numpy as np
+    import scipy.sparse.linalg as spla
+    t0 = time.perf_counter()
+    lu = spla.splu(A, permc_spec="MMD_AT_PLUS_A", diag_pivot_thresh=0.0, options=dict(SymmetricMode=True))
+    t1 = time.perf_counter()
+    lu.solve(W.rhs(A.shape[0], 47))
+    t2 = time.perf_counter()
+    return {"value": 1.0 / (t2 - t0), "unit": UNIT, "cores": 1, "factor_s": t1 - t0, "solve_s": t2 - t1,
+            "what": "scipy.sparse.linalg.splu(MMD_AT_PLUS_A)+solve, full size, stand-in for UMFPACK (not the reference)"}
+
+
+# ----------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """--impl reference: the CPU port of the path (the reference is Julia+UMFPACK and cannot run
+    here: no oracle/_ref), on the host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    import __graft_entry__ as ge
+    ge.build()
+    from sharedmemsparselu_jl_b200 import _SymbolicOnly
+    A, W = workload(args.grid)
+    S = _SymbolicOnly(A)
+    full_flops = S.stats()["flops_exact"]
+    S.close()
+    vals = []
+    for _ in range(args.warmup + args.steps if args.steps <= 2 else 1 + min(args.steps, 2)):
+        vals.append(cpu_oracle_sample(args.sample_grid, full_flops))
+    best = max(v["value"] for v in vals[-max(1, min(args.steps, 2)):])
+    cb = dict(vals[-1]); cb["value"] = best
+    out = {"impl": "reference", "metric": METRIC, "value": best, "unit": UNIT, "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / best, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "2D 5-point Laplacian %dx%d refactorize+solve (BASELINE configs[1])" % (args.grid, args.grid)},
+           "cpu_baseline": cb,
+           "e2e": {"value": best, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import scipy.sparse as sp
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if dist:
+        dist.barrier()
+    import smslu
+    A, W = workload(args.grid)
+    n, nnz = A.shape[0], A.nnz
+    K, Wu = args.steps, args.warmup
+    NV = 4                                                 # distinct value sets cycled through the steps
+    diag_pos = np.flatnonzero(A.indices == np.repeat(np.arange(n), np.diff(A.indptr)))
+    def values(k):
+        v = A.data.copy(); v[diag_pos] += k * 1e-3; return v
+    t_setup = time.perf_counter()
+    F = smslu.ParallelSparseLU(A, device=local_rank)
+    t_setup = time.perf_counter() - t_setup
+    work, st0 = algorithmic_work(F, A)
+    launches_per_step = None
+
+    # ---- kernel-only leg: everything resident in HBM, stream-ordered, CUDA events --------------
+    stream = torch.cuda.current_stream()
+    F.set_stream(stream)
+    vals_d = [torch.from_numpy(values(k)).cuda() for k in range(NV)]
+    b_d = [torch.from_numpy(W.rhs(n, 47 + k)).cuda() for k in range(NV)]
+    x_d = torch.empty(n, dtype=torch.float64, device="cuda")
+    for k in range(Wu):
+        F.refactor_async(vals_d[k % NV]); F.solve_async(x_d, b_d[k % NV])
+    F.sync()
+    sampler = ClockSampler(local_rank); sampler.start()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for k in range(K):
+        F.refactor_async(vals_d[k % NV]); F.solve_async(x_d, b_d[k % NV])
+    e1.record(stream)
+    F.sync()
+    torch.cuda.synchronize()
+    wall_dev = time.perf_counter() - t0
+    if dist:
+        dist.barrier()
+    ms_dev = e0.elapsed_time(e1)
+    st = F.stats()
+    launches_per_step = st["launches_refactor"] + st["launches_solve"]
+    xk = x_d.cpu().numpy()
+    Ak = sp.csc_matrix(A + ((K - 1) % NV) * 1e-3 * sp.identity(n))
+    bk = W.rhs(n, 47 + (K - 1) % NV)
+    residual = float(np.linalg.norm(Ak @ xk - bk) / np.linalg.norm(bk))
+
+    # ---- end-to-end leg: synchronous host API, pinned host buffers ----------------------------
+    vals_h = []
+    for k in range(NV):
+        v = smslu.pinned_empty(nnz); v[:] = values(k); vals_h.append(v)
+    b_h = []
+    for k in range(NV):
+        b = smslu.pinned_empty(n); b[:] = W.rhs(n, 47 + k); b_h.append(b)
+    x_h = smslu.pinned_empty(n)
+    for k in range(Wu):
+        smslu.lu_(F, vals_h[k % NV]); smslu.ldiv_(x_h, F, b_h[k % NV])
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e2 = torch.cuda.Event(enable_timing=True); e3 = torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    t0 = time.perf_counter()
+    for k in range(K):
+        smslu.lu_(F, vals_h[k % NV]); smslu.ldiv_(x_h, F, b_h[k % NV])
+    e3.record(stream)
+    torch.cuda.synchronize()
+    wall_e2e = time.perf_counter() - t0
+    ms_e2e = max(e2.elapsed_time(e3), wall_e2e * 1e3)
+    clocks = sampler.stop()
+    res_e2e = float(np.linalg.norm(Ak @ np.asarray(x_h) - bk) / np.linalg.norm(bk))
+
+    # ---- per-kernel timing (one profiled step, after the timed regions) -----------------------
+    F.set_profile(True)
+    for k in range(3):
+        F.refactor_async(vals_d[k % NV]); F.solve_async(x_d, b_d[k % NV]); F.sync()
+    sp_ = F.stats()
+    F.set_profile(False)
+    ms_kernel = {k: v / 3.0 for k, v in sp_["ms_kernel"].items()}
+    launches_kernel = {k: v // 3 for k, v in sp_["launches_kernel"].items()}
+
+    # ---- reduce over ranks --------------------------------------------------------------------
+    if dist:
+        t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        F.close()
+        if dist:
+            dist.destroy_process_group()
+        return
+    hbm_gbs, peak_src = load_peaks()
+    fp64_peak = measure_fp64_peak(torch)
+    value = world * K / (ms_dev * 1e-3)
+    e2e_value = world * K / (ms_e2e * 1e-3)
+    step_ms_prof = sum(ms_kernel.values())
+    dom = max((k for k in ms_kernel if k in work), key=lambda k: ms_kernel[k])
+    kinds = {}
+    for kname, w in work.items():
+        ms = ms_kernel.get(kname, 0.0)
+        if ms <= 0:
+            continue
+        kinds[kname] = {"ms": round(ms, 4), "launches": int(launches_kernel.get(kname, 0)),
+                        "share": round(ms / step_ms_prof, 4),
+                        "GB/s": round(w["bytes"] / (ms * 1e-3) / 1e9, 1),
+                        "TFLOP/s": round(w["flops"] / (ms * 1e-3) / 1e12, 3)}
+    if dom == "gemm_cb":   # FP64 contraction: bound by the FP64 pipe (DFMA/DMMA), not bf16 tensor peak
+        ach = work[dom]["flops"] / (ms_kernel[dom] * 1e-3) / 1e12
+        roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": ach / fp64_peak, "traffic": None,
+                "peak_source": "FP64 DGEMM (torch.matmul f64 6144^3) measured in this run; MEASURED_PEAKS.json has no FP64 entry"}
+    else:
+        ach = work[dom]["bytes"] / (ms_kernel[dom] * 1e-3) / 1e9
+        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_gbs, "unit": "GB/s",
+                "frac": ach / hbm_gbs, "traffic": None, "peak_source": peak_src}
+    roof["kernel_ms_per_step"] = ms_kernel[dom]
+    roof["share_of_step"] = ms_kernel[dom] / step_ms_prof
+    solve_ms = ms_kernel.get("fwd", 0) + ms_kernel.get("bwd", 0) + ms_kernel.get("permute_scale", 0) + ms_kernel.get("unpermute", 0)
+    solve_bytes = work["fwd"]["bytes"] + work["bwd"]["bytes"]
+    refac_ms = step_ms_prof - solve_ms
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wu,
+        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "2D 5-point Laplacian %dx%d (n=%d, nnz=%d) refactorize+solve, BASELINE configs[1]" % (args.grid, args.grid, n, nnz),
+                   "values": "A + k*1e-3*I, %d value sets cycled; b = splitmix64(47+k)" % NV,
+                   "ordering": "nd_graph", "nnz_L": int(st0["nnz_l_exact"]), "flops_refactor": st0["flops_exact"],
+                   "cache": "factor storage %.0f MB per step exceeds the 126 MB L2 (no explicit flush)" % (8e-6 * st0["lu_pool_doubles"]),
+                   "parallelism": "1 GPU" if world == 1 else "replicas: one independent factorization per GPU"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * (nnz + n), "d2h_bytes_per_step": 8 * n,
+                "ms_per_step": ms_e2e / K, "residual": res_e2e},
+        "gpu_launches": int(launches_per_step * K),
+        "clocks": clocks,
+        "roofline": roof,
+        "kernels": kinds,
+        "phases": {"refactor_ms": refac_ms, "solve_ms": solve_ms,
+                   "refactor_TFLOPs": st0["flops_exact"] / (refac_ms * 1e-3) / 1e12,
+                   "solve_GBs": solve_bytes / (solve_ms * 1e-3) / 1e9, "solve_frac_hbm": solve_bytes / (solve_ms * 1e-3) / 1e9 / hbm_gbs},
+        "residual": residual, "setup_s": t_setup,
+        "host_overhead": {"wall_ms_per_step_kernel_leg": wall_dev * 1e3 / K},
+    }
+    if not args.no_cpu:
+        out["cpu_baseline"] = cpu_oracle_sample(args.sample_grid, st0["flops_exact"])
+        if args.superlu:
+            out["cpu_superlu_standin"] = superlu_standin(A, W)
+    F.close()
+    print(json.dumps(out), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, default=1024, help="2D grid edge (default: BASELINE configs[1])")
+    ap.add_argument("--sample-grid", type=int, default=448, help="grid edge of the bounded CPU sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--superlu", action="store_true", help="also time SciPy SuperLU on the full workload")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

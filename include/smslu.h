@@ -72,8 +72,23 @@ typedef struct smslu_stats {
     int64_t launches_refactor, launches_solve;  /* kernels launched by the last call             */
     int64_t n_refactor, n_solve;        /* calls so far                                           */
     int64_t bad_pivot_col;              /* permuted column of the first bad pivot, or -1          */
+    double ms_kernel[16];               /* smslu_set_profile(h,1): device ms per kernel kind, summed */
+    int64_t launches_kernel[16];        /*   and launches per kernel kind (index = SMSLU_K_*)     */
     int64_t reserved[8];
 } smslu_stats_t;
+
+/* kernel kinds for ms_kernel / launches_kernel */
+#define SMSLU_K_ROWSCALE 0
+#define SMSLU_K_SCATTER 1    /* memset of the factor storage + scatter of A */
+#define SMSLU_K_ZERO 2
+#define SMSLU_K_EXTEND 3
+#define SMSLU_K_SMALL 4
+#define SMSLU_K_PANEL 5
+#define SMSLU_K_GEMM 6
+#define SMSLU_K_PERMUTE 7
+#define SMSLU_K_FWD 8
+#define SMSLU_K_BWD 9
+#define SMSLU_K_UNPERMUTE 10
 
 /* Fill *opts with defaults.  */
 int smslu_options_default(smslu_options_t* opts);
@@ -98,6 +113,17 @@ int smslu_refactor(smslu_handle_t h, const double* nzval, const double* Rs);
  * nx / nb are the lengths of x and b per column (checked against n: SMSLU_E_DIM, src:288-290). */
 int smslu_solve(smslu_handle_t h, double* x, int64_t nx, const double* b, int64_t nb,
                 int64_t nrhs, int64_t ldx, int64_t ldb);
+
+/* Stream-ordered variants for callers that keep everything on the device (CUDA.jl arrays, the
+ * benchmark's kernel-only leg): DEVICE pointers only, work is enqueued on the handle's stream and
+ * the call returns without synchronizing.  smslu_sync waits and reports a deferred pivot failure.
+ * smslu_set_stream makes the handle use the caller's cudaStream_t (so the caller's events bracket
+ * the work); smslu_set_profile turns per-launch event timing on (stats.ms_kernel). */
+int smslu_refactor_async(smslu_handle_t h, const double* nzval_dev, const double* Rs_dev);
+int smslu_solve_async(smslu_handle_t h, double* x_dev, const double* b_dev);
+int smslu_sync(smslu_handle_t h);
+int smslu_set_stream(smslu_handle_t h, void* cuda_stream);
+int smslu_set_profile(smslu_handle_t h, int32_t on);
 
 /* `lsolve!(F, x)` (src:349-367) and `rsolve!(F, x)` (src:374-392): in place, in the permuted and
  * scaled index space, x <- L^{-1} x  and  x <- U^{-1} x. */

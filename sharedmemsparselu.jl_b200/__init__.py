@@ -197,6 +197,25 @@ class ParallelSparseLU:
     def Rs(self):
         return self._factors()["Rs"]
 
+    # -- stream-ordered device-only variants (kernel-only timing, CUDA-array callers) -------------
+    def set_stream(self, cuda_stream):
+        """Run all of this handle's work on the caller's stream (int / torch.cuda.Stream)."""
+        ptr = getattr(cuda_stream, "cuda_stream", cuda_stream)
+        _capi.check(self._h, _capi.lib().smslu_set_stream(self._h, C.c_void_p(int(ptr))))
+
+    def set_profile(self, on=True):
+        _capi.check(self._h, _capi.lib().smslu_set_profile(self._h, 1 if on else 0))
+
+    def refactor_async(self, nzval_dev, Rs_dev=None):
+        self._cache = {}
+        _capi.check(self._h, _capi.lib().smslu_refactor_async(self._h, _ptr(nzval_dev), _ptr(Rs_dev)))
+
+    def solve_async(self, x_dev, b_dev):
+        _capi.check(self._h, _capi.lib().smslu_solve_async(self._h, _ptr(x_dev), _ptr(b_dev)))
+
+    def sync(self):
+        _capi.check(self._h, _capi.lib().smslu_sync(self._h))
+
     def stats(self):
         st = _capi.Stats()
         _capi.check(self._h, _capi.lib().smslu_get_stats(self._h, C.byref(st)))

@@ -17,8 +17,11 @@ EXPORTS = [
     "smslu_options_default", "smslu_create", "smslu_analyze", "smslu_refactor", "smslu_solve",
     "smslu_lsolve", "smslu_rsolve", "smslu_get_nnz", "smslu_get_factors", "smslu_get_stats",
     "smslu_last_error", "smslu_get_symbolic", "smslu_destroy", "smslu_allocate_shared",
-    "smslu_host_alloc", "smslu_host_free", "smslu_version",
+    "smslu_host_alloc", "smslu_host_free", "smslu_version", "smslu_refactor_async",
+    "smslu_solve_async", "smslu_sync", "smslu_set_stream", "smslu_set_profile",
 ]
+KERNEL_KINDS = ["rowscale", "scatter", "zero_cb", "extend_add", "front_small", "panel", "gemm_cb",
+                "permute_scale", "fwd", "bwd", "unpermute"]
 
 
 class Options(C.Structure):
@@ -35,10 +38,13 @@ class Stats(C.Structure):
             "flops_exact", "flops_stored", "ms_analyze", "ms_upload", "ms_refactor", "ms_solve",
             "ms_refactor_h2d", "ms_solve_h2d", "ms_solve_d2h")] + [(k, C.c_int64) for k in (
                 "launches_refactor", "launches_solve", "n_refactor", "n_solve", "bad_pivot_col")] + [
-        ("reserved", C.c_int64 * 8)]
+        ("ms_kernel", C.c_double * 16), ("launches_kernel", C.c_int64 * 16), ("reserved", C.c_int64 * 8)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k not in ("reserved", "ms_kernel", "launches_kernel")}
+        d["ms_kernel"] = {k: self.ms_kernel[i] for i, k in enumerate(KERNEL_KINDS)}
+        d["launches_kernel"] = {k: self.launches_kernel[i] for i, k in enumerate(KERNEL_KINDS)}
+        return d
 
 
 class SmsluError(RuntimeError):
@@ -84,6 +90,11 @@ def lib():
         L.smslu_destroy.argtypes = [vp]
         L.smslu_host_alloc.argtypes = [C.POINTER(vp), i64]
         L.smslu_host_free.argtypes = [vp]
+        L.smslu_refactor_async.argtypes = [vp, dp, dp]
+        L.smslu_solve_async.argtypes = [vp, dp, dp]
+        L.smslu_sync.argtypes = [vp]
+        L.smslu_set_stream.argtypes = [vp, vp]
+        L.smslu_set_profile.argtypes = [vp, i32]
         for name in EXPORTS:
             if name != "smslu_last_error":
                 getattr(L, name).restype = C.c_int

@@ -18,7 +18,8 @@ using namespace smslu;
 
 namespace {
 
-enum LaunchKind { L_ZERO = 0, L_EXTEND, L_SMALL, L_PANEL, L_GEMM, L_FWD, L_BWD };
+enum LaunchKind { L_ZERO = SMSLU_K_ZERO, L_EXTEND = SMSLU_K_EXTEND, L_SMALL = SMSLU_K_SMALL, L_PANEL = SMSLU_K_PANEL,
+                  L_GEMM = SMSLU_K_GEMM, L_FWD = SMSLU_K_FWD, L_BWD = SMSLU_K_BWD };
 
 struct Launch {
     int kind;
@@ -57,6 +58,16 @@ struct smslu_handle_s {
     double *d_Rs = nullptr, *d_aval = nullptr, *d_w = nullptr, *d_z = nullptr, *d_xb = nullptr;
     int4* d_tasks = nullptr;
     std::vector<Launch> fac, fwd, bwd;
+
+    bool own_stream = true;
+    cudaStream_t user_stream = nullptr;
+    bool have_user_stream = false;
+    bool profile = false;
+    std::vector<cudaEvent_t> pev;          // event pool for per-launch profiling
+    std::vector<int> pev_kind;             // kind of the launch between pev[2i], pev[2i+1]
+    size_t pev_used = 0;
+    bool pending_refactor = false;         // an async refactor has not been checked yet
+    int* h_flag = nullptr;                 // pinned
 
     std::vector<int64_t> ex_ptr;   // exact structure, built lazily for get_factors
     std::vector<int> ex_idx;
@@ -206,7 +217,9 @@ int ensure_uploaded(smslu_handle_t h) {
     CU(cudaGetDeviceProperties(&prop, h->device));
     if (prop.major < 10) return fail(h, SMSLU_E_CUDA, "device is not sm_100 class; this library is built for sm_100a only");
     CU(kernels_init());
-    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    if (h->have_user_stream) { h->stream = h->user_stream; h->own_stream = false; }
+    else CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CU(cudaMallocHost((void**)&h->h_flag, sizeof(int)));
     CU(cudaEventCreate(&h->ev0)); CU(cudaEventCreate(&h->ev1));
     CU(cudaEventCreate(&h->ev2)); CU(cudaEventCreate(&h->ev3));
     const Symbolic& S = h->S;
@@ -269,9 +282,40 @@ int ensure_uploaded(smslu_handle_t h) {
     return 0;
 }
 
+// ---- optional per-launch timing (smslu_set_profile): events around every launch, summed by kind
+int prof_begin(smslu_handle_t h, int kind) {
+    if (!h->profile) return 0;
+    if (h->pev_used + 2 > h->pev.size()) {
+        for (int i = 0; i < 256; ++i) { cudaEvent_t e; CU(cudaEventCreate(&e)); h->pev.push_back(e); }
+    }
+    h->pev_kind.push_back(kind);
+    CU(cudaEventRecord(h->pev[h->pev_used++], h->stream));
+    return 0;
+}
+int prof_end(smslu_handle_t h) {
+    if (!h->profile) return 0;
+    CU(cudaEventRecord(h->pev[h->pev_used++], h->stream));
+    return 0;
+}
+int prof_collect(smslu_handle_t h) {   // stream must be synchronized
+    if (!h->profile) return 0;
+    for (size_t i = 0; i + 1 < h->pev_used; i += 2) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, h->pev[i], h->pev[i + 1]));
+        int k = h->pev_kind[i / 2];
+        h->st.ms_kernel[k] += ms;
+        h->st.launches_kernel[k] += 1;
+    }
+    h->pev_used = 0;
+    h->pev_kind.clear();
+    return 0;
+}
+
 int run_schedule(smslu_handle_t h, const std::vector<Launch>& sched, const double* win, double* zx) {
+    int rc;
     for (const Launch& L : sched) {
         const int4* tk = h->d_tasks + L.off;
+        if ((rc = prof_begin(h, L.kind))) return rc;
         switch (L.kind) {
             case L_ZERO: launch_zero_cb(h->stream, h->cx, tk, L.ntasks); break;
             case L_EXTEND: launch_extend_add(h->stream, h->cx, tk, L.ntasks); break;
@@ -281,8 +325,62 @@ int run_schedule(smslu_handle_t h, const std::vector<Launch>& sched, const doubl
             case L_FWD: launch_fwd(h->stream, h->cx, tk, L.ntasks, win, zx); break;
             case L_BWD: launch_bwd(h->stream, h->cx, tk, L.ntasks, zx); break;
         }
+        if ((rc = prof_end(h))) return rc;
     }
     CU(cudaGetLastError());
+    return 0;
+}
+
+// Enqueue one numeric refactorization on h->stream; av / Rs are DEVICE pointers (Rs may be null).
+int enqueue_refactor(smslu_handle_t h, const double* av, bool rs_given) {
+    const Symbolic& S = h->S;
+    int rc;
+    if (!rs_given && h->opt.scaling == SMSLU_SCALE_SUM) {
+        if ((rc = prof_begin(h, SMSLU_K_ROWSCALE))) return rc;
+        launch_rowscale(h->stream, h->n, h->d_rowptr, h->d_rowidx, av, h->d_Rs);
+        if ((rc = prof_end(h))) return rc;
+    }
+    if ((rc = prof_begin(h, SMSLU_K_SCATTER))) return rc;
+    CU(cudaMemsetAsync(h->cx.flag, 0x7f, sizeof(int), h->stream));   // 0x7f7f7f7f = clean
+    CU(cudaMemsetAsync(h->cx.counters, 0, sizeof(int) * std::max(S.nsn, 1), h->stream));
+    CU(cudaMemsetAsync(h->cx.lu, 0, sizeof(double) * S.lu_size, h->stream));
+    launch_scatter(h->stream, h->annz, h->d_a_dst, h->d_a_row, h->d_Rs, av, h->cx.lu);
+    if ((rc = prof_end(h))) return rc;
+    if ((rc = run_schedule(h, h->fac, nullptr, nullptr))) return rc;
+    CU(cudaMemcpyAsync(h->h_flag, h->cx.flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    h->pending_refactor = true;
+    return 0;
+}
+
+constexpr int FLAG_CLEAN = 0x7f7f7f7f;
+
+// After the stream has been synchronized: turn the device pivot flag into a status.
+int finish_refactor(smslu_handle_t h) {
+    h->pending_refactor = false;
+    h->st.n_refactor++;
+    const int flag = *h->h_flag;
+    if (flag != FLAG_CLEAN) {
+        h->factored = false;
+        h->st.bad_pivot_col = flag;
+        char buf[160];
+        snprintf(buf, sizeof buf, "zero or non-finite pivot at permuted column %d under the static pivot order", flag);
+        return fail(h, SMSLU_E_PIVOT, buf);
+    }
+    h->st.bad_pivot_col = -1;
+    h->factored = true;
+    return 0;
+}
+
+int enqueue_solve(smslu_handle_t h, double* xdev, const double* bdev) {
+    int rc;
+    if ((rc = prof_begin(h, SMSLU_K_PERMUTE))) return rc;
+    launch_permute_scale(h->stream, h->n, h->d_p, h->d_Rs, bdev, h->d_w);
+    if ((rc = prof_end(h))) return rc;
+    if ((rc = run_schedule(h, h->fwd, h->d_w, h->d_z))) return rc;
+    if ((rc = run_schedule(h, h->bwd, nullptr, h->d_z))) return rc;
+    if ((rc = prof_begin(h, SMSLU_K_UNPERMUTE))) return rc;
+    launch_unpermute(h->stream, h->n, h->d_q, h->d_z, xdev);
+    if ((rc = prof_end(h))) return rc;
     return 0;
 }
 
@@ -379,7 +477,6 @@ int smslu_refactor(smslu_handle_t h, const double* nzval, const double* Rs) {
     if (!h || !nzval) return SMSLU_E_ARG;
     int rc = ensure_uploaded(h);
     if (rc) return rc;
-    const Symbolic& S = h->S;
     h->factored = false;
     CU(cudaEventRecord(h->ev0, h->stream));
     const double* av = nzval;
@@ -387,42 +484,75 @@ int smslu_refactor(smslu_handle_t h, const double* nzval, const double* Rs) {
         CU(cudaMemcpyAsync(h->d_aval, nzval, sizeof(double) * h->annz, cudaMemcpyHostToDevice, h->stream));
         av = h->d_aval;
     }
-    if (Rs) {
-        CU(cudaMemcpyAsync(h->d_Rs, Rs, sizeof(double) * h->n, cudaMemcpyDefault, h->stream));
+    if (Rs) CU(cudaMemcpyAsync(h->d_Rs, Rs, sizeof(double) * h->n, cudaMemcpyDefault, h->stream));
+    else if (h->opt.scaling != SMSLU_SCALE_SUM) {
+        std::vector<double> ones(h->n, 1.0);
+        CU(cudaMemcpyAsync(h->d_Rs, ones.data(), sizeof(double) * h->n, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
     }
     CU(cudaEventRecord(h->ev1, h->stream));
-    if (!Rs) {
-        if (h->opt.scaling == SMSLU_SCALE_SUM) launch_rowscale(h->stream, h->n, h->d_rowptr, h->d_rowidx, av, h->d_Rs);
-        else {
-            std::vector<double> ones(h->n, 1.0);
-            CU(cudaMemcpyAsync(h->d_Rs, ones.data(), sizeof(double) * h->n, cudaMemcpyHostToDevice, h->stream));
-            CU(cudaStreamSynchronize(h->stream));
-        }
-    }
-    const int clean = INT_MAX;
-    CU(cudaMemcpyAsync(h->cx.flag, &clean, sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemsetAsync(h->cx.counters, 0, sizeof(int) * std::max(S.nsn, 1), h->stream));
-    CU(cudaMemsetAsync(h->cx.lu, 0, sizeof(double) * S.lu_size, h->stream));
-    launch_scatter(h->stream, h->annz, h->d_a_dst, h->d_a_row, h->d_Rs, av, h->cx.lu);
-    rc = run_schedule(h, h->fac, nullptr, nullptr);
-    if (rc) return rc;
+    if ((rc = enqueue_refactor(h, av, Rs != nullptr))) return rc;
     CU(cudaEventRecord(h->ev2, h->stream));
-    int flag = 0;
-    CU(cudaMemcpyAsync(&flag, h->cx.flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1)); h->st.ms_refactor_h2d = ms;
     CU(cudaEventElapsedTime(&ms, h->ev1, h->ev2)); h->st.ms_refactor = ms;
     h->st.launches_refactor = (int64_t)h->fac.size() + 1 + ((!Rs && h->opt.scaling == SMSLU_SCALE_SUM) ? 1 : 0);
-    h->st.n_refactor++;
-    if (flag != INT_MAX) {
-        h->st.bad_pivot_col = flag;
-        char buf[160];
-        snprintf(buf, sizeof buf, "zero or non-finite pivot at permuted column %d under the static pivot order", flag);
-        return fail(h, SMSLU_E_PIVOT, buf);
+    if ((rc = prof_collect(h))) return rc;
+    return finish_refactor(h);
+}
+
+int smslu_refactor_async(smslu_handle_t h, const double* nzval_dev, const double* Rs_dev) {
+    if (!h || !nzval_dev) return SMSLU_E_ARG;
+    int rc = ensure_uploaded(h);
+    if (rc) return rc;
+    if (!is_device_ptr(nzval_dev) || (Rs_dev && !is_device_ptr(Rs_dev)))
+        return fail(h, SMSLU_E_ARG, "smslu_refactor_async needs device pointers");
+    if (Rs_dev) CU(cudaMemcpyAsync(h->d_Rs, Rs_dev, sizeof(double) * h->n, cudaMemcpyDeviceToDevice, h->stream));
+    else if (h->opt.scaling != SMSLU_SCALE_SUM) return fail(h, SMSLU_E_ARG, "async refactor needs Rs or SUM scaling");
+    h->st.launches_refactor = (int64_t)h->fac.size() + 1 + ((!Rs_dev) ? 1 : 0);
+    return enqueue_refactor(h, nzval_dev, Rs_dev != nullptr);
+}
+
+int smslu_solve_async(smslu_handle_t h, double* x_dev, const double* b_dev) {
+    if (!h || !x_dev || !b_dev) return SMSLU_E_ARG;
+    if (!h->uploaded) return fail(h, SMSLU_E_ARG, "no factorization has been enqueued");
+    if (!h->factored && !h->pending_refactor) return fail(h, SMSLU_E_ARG, "no valid factorization (call smslu_refactor)");
+    if (!is_device_ptr(x_dev) || !is_device_ptr(b_dev)) return fail(h, SMSLU_E_ARG, "smslu_solve_async needs device pointers");
+    CU(cudaSetDevice(h->device));
+    h->st.launches_solve = (int64_t)h->fwd.size() + (int64_t)h->bwd.size() + 2;
+    return enqueue_solve(h, x_dev, b_dev);
+}
+
+int smslu_sync(smslu_handle_t h) {
+    if (!h) return SMSLU_E_ARG;
+    if (!h->uploaded) return 0;
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    int rc;
+    if ((rc = prof_collect(h))) return rc;
+    if (h->pending_refactor) return finish_refactor(h);
+    return 0;
+}
+
+int smslu_set_stream(smslu_handle_t h, void* stream) {
+    if (!h) return SMSLU_E_ARG;
+    if (h->uploaded) {
+        CU(cudaSetDevice(h->device));
+        CU(cudaStreamSynchronize(h->stream));
+        if (h->own_stream) cudaStreamDestroy(h->stream);
+        h->stream = (cudaStream_t)stream;
+        h->own_stream = false;
     }
-    h->st.bad_pivot_col = -1;
-    h->factored = true;
+    h->user_stream = (cudaStream_t)stream;
+    h->have_user_stream = true;
+    return 0;
+}
+
+int smslu_set_profile(smslu_handle_t h, int32_t on) {
+    if (!h) return SMSLU_E_ARG;
+    h->profile = on != 0;
+    if (on) { memset(h->st.ms_kernel, 0, sizeof h->st.ms_kernel); memset(h->st.launches_kernel, 0, sizeof h->st.launches_kernel); }
     return 0;
 }
 
@@ -438,6 +568,7 @@ int smslu_solve(smslu_handle_t h, double* x, int64_t nx, const double* b, int64_
     int rc;
     if ((rc = check_vec(h, nx, nrhs, ldx, "x"))) return rc;
     if ((rc = check_vec(h, nb, nrhs, ldb, "b"))) return rc;
+    if (h->pending_refactor && (rc = smslu_sync(h))) return rc;
     if (!h->factored) return fail(h, SMSLU_E_ARG, "no valid factorization (call smslu_refactor)");
     if ((rc = ensure_uploaded(h))) return rc;
     const int n = h->n;
@@ -449,10 +580,7 @@ int smslu_solve(smslu_handle_t h, double* x, int64_t nx, const double* b, int64_
         CU(cudaEventRecord(h->ev0, h->stream));
         if (!bdev) { CU(cudaMemcpyAsync(h->d_xb, bc, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream)); bc = h->d_xb; }
         CU(cudaEventRecord(h->ev1, h->stream));
-        launch_permute_scale(h->stream, n, h->d_p, h->d_Rs, bc, h->d_w);
-        if ((rc = run_schedule(h, h->fwd, h->d_w, h->d_z))) return rc;
-        if ((rc = run_schedule(h, h->bwd, nullptr, h->d_z))) return rc;
-        launch_unpermute(h->stream, n, h->d_q, h->d_z, xdev ? xc : h->d_xb);
+        if ((rc = enqueue_solve(h, xdev ? xc : h->d_xb, bc))) return rc;
         CU(cudaEventRecord(h->ev2, h->stream));
         if (!xdev) CU(cudaMemcpyAsync(xc, h->d_xb, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaEventRecord(h->ev3, h->stream));
@@ -464,7 +592,7 @@ int smslu_solve(smslu_handle_t h, double* x, int64_t nx, const double* b, int64_
     h->st.ms_solve_h2d = h2d; h->st.ms_solve = dev; h->st.ms_solve_d2h = d2h;
     h->st.launches_solve = nrhs * ((int64_t)h->fwd.size() + (int64_t)h->bwd.size() + 2);
     h->st.n_solve++;
-    return 0;
+    return prof_collect(h);
 }
 
 static int tri_solve(smslu_handle_t h, double* x, int64_t nx, int64_t nrhs, int64_t ld, bool lower) {
@@ -560,7 +688,9 @@ int smslu_destroy(smslu_handle_t h) {
         if (h->ev1) cudaEventDestroy(h->ev1);
         if (h->ev2) cudaEventDestroy(h->ev2);
         if (h->ev3) cudaEventDestroy(h->ev3);
-        if (h->stream) cudaStreamDestroy(h->stream);
+        for (cudaEvent_t e : h->pev) cudaEventDestroy(e);
+        if (h->h_flag) cudaFreeHost(h->h_flag);
+        if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
     }
     delete h;
     return 0;

@@ -145,3 +145,17 @@ def relerr(a, b):
     if a.size == 0:
         return 0.0
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+
+
+def relerr_csc(data, ref, indptr, floor=1e-2):
+    """Entry-wise relative error of CSC values, with |ref_ij| floored at `floor` * (largest |entry| of
+    its column): entries that are the residue of cancellation are compared against the column scale."""
+    data = np.asarray(data); ref = np.asarray(ref)
+    if data.size == 0:
+        return 0.0
+    counts = np.diff(indptr)
+    col = np.repeat(np.arange(counts.size), counts)
+    cmax = np.zeros(counts.size)
+    np.maximum.at(cmax, col, np.abs(ref))
+    denom = np.maximum(np.abs(ref), floor * cmax[col])
+    return float(np.max(np.abs(data - ref) / np.maximum(denom, 1e-300)))

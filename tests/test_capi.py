@@ -30,7 +30,7 @@ def test_header_symbols_exported(smslu):
 def test_struct_sizes_match_header(smslu):
     from sharedmemsparselu_jl_b200 import _capi
     assert C.sizeof(_capi.Options) == 4 * (1 + 3 + 6 + 8)
-    assert C.sizeof(_capi.Stats) == 8 * (14 + 9 + 5 + 8)
+    assert C.sizeof(_capi.Stats) == 8 * (14 + 9 + 5 + 16 + 16 + 8)
 
 
 def test_create_rejects_bad_input(smslu):
