@@ -92,6 +92,22 @@ def row_scale_sum(A) -> np.ndarray:
     return Rs
 
 
+def csc_lsolve(L, b):
+    """`L \\ b` for a lower-triangular CSC matrix with its diagonal stored (test/runtests.jl:51,70)."""
+    n, Lp, Li, Lx = _csc(L)
+    x = np.array(b, np.float64, copy=True)
+    lib().oracle_csc_lsolve(n, Lp, Li, Lx, x)
+    return x
+
+
+def csc_usolve(U, b):
+    """`U \\ b` for an upper-triangular CSC matrix (test/runtests.jl:86,104)."""
+    n, Up, Ui, Ux = _csc(U)
+    x = np.array(b, np.float64, copy=True)
+    lib().oracle_csc_usolve(n, Up, Ui, Ux, x)
+    return x
+
+
 class OracleLU:
     """L*U == (Rs .* A)[p, q] (0-based p, q), restating the contract at reference src:305-316.
 

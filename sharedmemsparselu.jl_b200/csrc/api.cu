@@ -58,6 +58,7 @@ struct smslu_handle_s {
     double *d_Rs = nullptr, *d_aval = nullptr, *d_w = nullptr, *d_z = nullptr, *d_xb = nullptr;
     int4* d_tasks = nullptr;
     std::vector<Launch> fac, fwd, bwd;
+    int64_t bpart_slots = 0;
 
     bool own_stream = true;
     cudaStream_t user_stream = nullptr;
@@ -128,17 +129,22 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
         const int* sn = S.level_sn.data() + S.level_ptr[l];
         const int cnt = S.level_ptr[l + 1] - S.level_ptr[l];
         int maxch = 0;
-        // zero the contribution blocks that children will be added into
+        // Zero the contribution blocks that receive '+=' contributions.  Extend-add children add
+        // at this level; a direct child adds one level earlier, so its parent is zeroed there.
         int64_t off = (int64_t)tasks.size();
+        auto zero_tasks = [&](int s) {
+            int64_t tiles = (R(s) * R(s) + ZERO_TILE - 1) / ZERO_TILE;
+            for (int64_t i = 0; i < tiles; ++i) tasks.push_back(make_int4(s, (int)i, 0, 0));
+        };
         for (int t = 0; t < cnt; ++t) {
             int s = sn[t];
             maxch = std::max(maxch, NC(s));
-            if (NC(s) == 0 || R(s) == 0) continue;
-            int64_t tiles = (R(s) * R(s) + ZERO_TILE - 1) / ZERO_TILE;
-            for (int64_t i = 0; i < tiles; ++i) tasks.push_back(make_int4(s, (int)i, 0, 0));
+            const bool fed_directly = NC(s) == 1 && S.direct[S.child_idx[S.child_ptr[s]]];
+            if (NC(s) > 0 && R(s) > 0 && !fed_directly) zero_tasks(s);
+            if (S.direct[s] && !S.cb_assigned[S.sn_parent[s]] && R(S.sn_parent[s]) > 0) zero_tasks(S.sn_parent[s]);
         }
         push(h->fac, L_ZERO, off, 0);
-        // extend-add, one launch per child slot
+        // extend-add, one launch per child slot (children that write directly are skipped)
         for (int slot = 0; slot < maxch; ++slot) {
             off = (int64_t)tasks.size();
             for (int t = 0; t < cnt; ++t) {
@@ -146,7 +152,7 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
                 if (NC(s) <= slot) continue;
                 int c = S.child_idx[S.child_ptr[s] + slot];
                 int64_t rc = R(c);
-                if (rc == 0) continue;
+                if (rc == 0 || S.direct[c]) continue;
                 int ncols = (int)std::max<int64_t>(1, std::min<int64_t>(rc, 4096 / rc));
                 for (int64_t b0 = 0; b0 < rc; b0 += ncols)
                     tasks.push_back(make_int4(c, (int)b0, (int)std::min<int64_t>(ncols, rc - b0), 0));
@@ -183,7 +189,11 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
             if (K(s) + r <= small_max) continue;
             int nt = (int)((r + GEMM_TILE - 1) / GEMM_TILE);
             for (int j = 0; j < nt; ++j)
-                for (int i = 0; i < nt; ++i) tasks.push_back(make_int4(s, i, j, NC(s) > 0 ? 1 : 0));
+                for (int i = 0; i < nt; ++i) {
+                    int flags = (NC(s) > 0 ? 1 : 0) | (S.direct[s] ? 2 : 0) |
+                                (S.direct[s] && S.cb_assigned[S.sn_parent[s]] ? 4 : 0);
+                    tasks.push_back(make_int4(s, i, j, flags));
+                }
         }
         push(h->fac, L_GEMM, off, 0);
         // forward solve level
@@ -195,11 +205,18 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
         }
         push(h->fwd, L_FWD, off, 0);
     }
+    int64_t slots = 0;
     for (int l = S.nlevels - 1; l >= 0; --l) {
         int64_t off = (int64_t)tasks.size();
-        for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) tasks.push_back(make_int4(S.level_sn[t], 0, 0, 0));
+        for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) {
+            int s = S.level_sn[t];
+            int nt = (int)std::max<int64_t>(1, (R(s) + BWD_ROWS - 1) / BWD_ROWS);
+            for (int i = 0; i < nt; ++i) tasks.push_back(make_int4(s, i, nt, (int)slots));
+            if (nt > 1) slots += nt;
+        }
         push(h->bwd, L_BWD, off, 0);
     }
+    h->bpart_slots = slots;
 }
 
 int ensure_uploaded(smslu_handle_t h) {
@@ -271,11 +288,16 @@ int ensure_uploaded(smslu_handle_t h) {
     std::vector<int4> tasks;
     build_schedules(h, tasks);
     if ((rc = dev_upload(h, &h->d_tasks, tasks))) return rc;
+    double* d_bpart; int* d_counters2;
+    if ((rc = dev_alloc(h, &d_bpart, (size_t)h->bpart_slots * KMAX))) return rc;
+    if ((rc = dev_alloc(h, &d_counters2, (size_t)S.nsn))) return rc;
+    CU(cudaMemset(d_counters2, 0, sizeof(int) * std::max(S.nsn, 1)));
     DevCtx& cx = h->cx;
     cx.sn_start = d_sn_start; cx.rows_ptr = d_rows_ptr; cx.rows = d_rows; cx.rel = d_rel;
     cx.Loff = d_Loff; cx.Uoff = d_Uoff; cx.CBoff = d_CBoff; cx.sn_parent = d_sn_parent;
     cx.child_ptr = d_child_ptr; cx.child_idx = d_child_idx;
     cx.lu = d_lu; cx.cb = d_cb; cx.upd = d_upd; cx.counters = d_counters; cx.flag = d_flag;
+    cx.bpart = d_bpart; cx.counters2 = d_counters2;
     CU(cudaDeviceSynchronize());
     h->uploaded = true;
     h->st.ms_upload = now_ms() - t0;
@@ -449,6 +471,7 @@ int smslu_analyze(smslu_handle_t h, const int64_t* p, const int64_t* q) {
     if (h->opt.nd_leaf > 0) o.nd_leaf = h->opt.nd_leaf;
     o.relax = h->opt.relax;
     o.max_width = h->opt.max_width;
+    o.small_front_max = front_small_limit();
     std::vector<int> pp, qq;
     if (o.ordering == ORD_GIVEN) {
         if (!p || !q) return fail(h, SMSLU_E_ARG, "ordering GIVEN needs p and q");

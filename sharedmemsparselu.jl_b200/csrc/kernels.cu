@@ -194,9 +194,14 @@ __global__ void __launch_bounds__(PANEL_ROWS) k_panel(DevCtx cx, const int4* __r
 }
 
 // ------------------------------------------------------------------ Schur update of the CB
-// C (r x r) = beta*C - L21 (r x k) * U12 (k x r), U12 held transposed.  64x64 tile per CTA,
+// V (r x r) = beta*C - L21 (r x k) * U12 (k x r), U12 held transposed.  64x64 tile per CTA,
 // 4x4 per thread, whole K (<= 32) staged in shared memory once.
-// task: x = supernode, y = tile row, z = tile col, w = beta (1: CB was assembled, 0: overwrite)
+// task: x = supernode, y = tile row, z = tile col, w = flags:
+//   bit0 beta   : C holds assembled contributions (else it is taken as zero)
+//   bit1 direct : V is written straight into the parent's front through the rel map (this front
+//                 is its parent's only child, so nobody else writes there): panel entries +=,
+//   bit2 assign : ... and the parent's contribution-block entries are assigned (=) instead of +=.
+//   without bit1 V overwrites C in place.
 __global__ void __launch_bounds__(256) k_gemm_cb(DevCtx cx, const int4* __restrict__ tasks) {
     __shared__ double As[KMAX][GEMM_TILE];
     __shared__ double Bs[KMAX][GEMM_TILE];
@@ -206,6 +211,19 @@ __global__ void __launch_bounds__(256) k_gemm_cb(DevCtx cx, const int4* __restri
     const int64_t m0 = (int64_t)tk.y * GEMM_TILE, n0 = (int64_t)tk.z * GEMM_TILE;
     const double* __restrict__ A = F.P + F.k;
     const double* __restrict__ B = F.T;
+    const int tx = tid & 15, ty = tid >> 4;
+    const bool beta = tk.w & 1, direct = tk.w & 2, assign = tk.w & 4;
+    double acc[4][4];
+    // issue the C loads first so they are in flight while the operand tiles are staged
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int64_t col = n0 + ty + 16 * j;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t row = m0 + tx + 16 * i;
+            acc[i][j] = (beta && row < F.r && col < F.r) ? F.C[row + col * F.r] : 0.0;
+        }
+    }
     for (int e = tid; e < GEMM_TILE * k; e += 256) {
         int a = e & (GEMM_TILE - 1), p = e >> 6;
         int64_t ra = m0 + a, rb = n0 + a;
@@ -213,12 +231,6 @@ __global__ void __launch_bounds__(256) k_gemm_cb(DevCtx cx, const int4* __restri
         Bs[p][a] = rb < F.r ? B[rb + (int64_t)p * F.r] : 0.0;
     }
     __syncthreads();
-    const int tx = tid & 15, ty = tid >> 4;
-    double acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
     for (int p = 0; p < k; ++p) {
         double a[4], b[4];
 #pragma unroll
@@ -226,18 +238,45 @@ __global__ void __launch_bounds__(256) k_gemm_cb(DevCtx cx, const int4* __restri
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+            for (int j = 0; j < 4; ++j) acc[i][j] -= a[i] * b[j];
+    }
+    if (!direct) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t col = n0 + ty + 16 * j;
+            if (col >= F.r) continue;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int64_t row = m0 + tx + 16 * i;
+                if (row < F.r) F.C[row + col * F.r] = acc[i][j];
+            }
+        }
+        return;
+    }
+    const Front Q = load_front(cx, cx.sn_parent[tk.x]);
+    const int* __restrict__ rel = cx.rel + cx.rows_ptr[tk.x];
+    int64_t prow[4], pcol[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t row = m0 + tx + 16 * i, col = n0 + ty + 16 * i;
+        prow[i] = row < F.r ? rel[row] : -1;
+        pcol[i] = col < F.r ? rel[col] : -1;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const int64_t col = n0 + ty + 16 * j;
-        if (col >= F.r) continue;
+        const int64_t pb = pcol[j];
+        if (pb < 0) continue;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int64_t row = m0 + tx + 16 * i;
-            if (row >= F.r) continue;
-            double* cp = F.C + row + col * F.r;
-            *cp = (tk.w ? *cp : 0.0) - acc[i][j];
+            const int64_t pa = prow[i];
+            if (pa < 0) continue;
+            const double v = acc[i][j];
+            if (pb < Q.k) Q.P[pa + pb * Q.f] += v;
+            else if (pa < Q.k) Q.T[(pb - Q.k) + pa * Q.r] += v;
+            else {
+                double* d = Q.C + (pa - Q.k) + (pb - Q.k) * Q.r;
+                *d = assign ? v : *d + v;
+            }
         }
     }
 }
@@ -256,9 +295,11 @@ __global__ void k_unpermute(int n, const int* __restrict__ q, const double* __re
 // Forward substitution for one level.  task: x = supernode, y = row tile of the update vector.
 // y_s = L11^{-1} (w[cols] + children contributions); upd_s = children contributions - L21 y_s.
 // Every tile recomputes y_s (k <= 32); tile 0 stores it.  Children are gathered one at a time,
-// ascending, so the summation order is fixed.
+// ascending, so the summation order is fixed.  L11 is staged in shared memory up front so the
+// 32-step substitution never waits on global memory.
 __global__ void __launch_bounds__(FWD_ROWS) k_fwd(DevCtx cx, const int4* __restrict__ tasks,
                                                   const double* __restrict__ win, double* __restrict__ zout) {
+    __shared__ double Ls[KMAX][KMAX + 1];
     __shared__ double ys[KMAX];
     __shared__ double acc[FWD_ROWS];
     int4 tk = tasks[blockIdx.x];
@@ -266,6 +307,7 @@ __global__ void __launch_bounds__(FWD_ROWS) k_fwd(DevCtx cx, const int4* __restr
     const Front F = load_front(cx, s);
     const int k = F.k, tid = threadIdx.x;
     const int64_t lo = (int64_t)tk.y * FWD_ROWS;            // first update row of this tile
+    for (int e = tid; e < k * k; e += FWD_ROWS) { int i = e % k, j = e / k; Ls[i][j] = F.P[i + (int64_t)j * F.f]; }
     if (tid < KMAX) ys[tid] = tid < k ? win[F.c0 + tid] : 0.0;
     acc[tid] = 0.0;
     __syncthreads();
@@ -285,7 +327,7 @@ __global__ void __launch_bounds__(FWD_ROWS) k_fwd(DevCtx cx, const int4* __restr
         double y = tid < k ? ys[tid] : 0.0;
         for (int j = 0; j < k; ++j) {
             const double yj = __shfl_sync(0xffffffffu, y, j);
-            if (tid > j && tid < k) y -= F.P[tid + (int64_t)j * F.f] * yj;
+            if (tid > j && tid < k) y -= Ls[tid][j] * yj;
         }
         if (tid < k) {
             ys[tid] = y;
@@ -297,37 +339,68 @@ __global__ void __launch_bounds__(FWD_ROWS) k_fwd(DevCtx cx, const int4* __restr
     if (row < F.r) {
         double v = acc[tid];
         const double* __restrict__ src = F.P + F.k + row;
+#pragma unroll 8
         for (int j = 0; j < k; ++j) v -= src[(int64_t)j * F.f] * ys[j];
         cx.upd[cx.rows_ptr[s] + row] = v;
     }
 }
 
-// Backward substitution for one level.  task: x = supernode.  One CTA per supernode:
-// x[cols] = U11^{-1} (x[cols] - U12 x[rows]).
-__global__ void __launch_bounds__(256) k_bwd(DevCtx cx, const int4* __restrict__ tasks, double* __restrict__ x) {
+// Backward substitution for one level.  task: x = supernode, y = row tile, z = tiles of this
+// supernode, w = slot of its partial sums in cx.bpart.   x[cols] = U11^{-1} (x[cols] - U12 x[rows]).
+// Each CTA reduces BWD_ROWS rows of U12' against the gathered x; with several tiles the partial
+// k-vectors go to scratch and the CTA that arrives last adds them in tile order (fixed summation
+// order, nobody waits) and finishes the 32x32 back substitution.
+__global__ void __launch_bounds__(BWD_ROWS) k_bwd(DevCtx cx, const int4* __restrict__ tasks, double* __restrict__ x) {
+    __shared__ double Us[KMAX][KMAX + 1];
+    __shared__ double xs[BWD_ROWS];
     __shared__ double part[KMAX];
+    __shared__ int s_last;
     int4 tk = tasks[blockIdx.x];
-    const int s = tk.x;
+    const int s = tk.x, ntiles = tk.z;
     const Front F = load_front(cx, s);
     const int k = F.k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int* __restrict__ rows = cx.rows + cx.rows_ptr[s];
-    for (int i = warp; i < k; i += 8) {
-        const double* __restrict__ col = F.T + (int64_t)i * F.r;
+    const int64_t lo = (int64_t)tk.y * BWD_ROWS;
+    const int cnt = (int)(F.r - lo < BWD_ROWS ? F.r - lo : BWD_ROWS);
+    const int* __restrict__ rows = cx.rows + cx.rows_ptr[s] + lo;
+    if (tid < cnt) xs[tid] = x[rows[tid]];
+    for (int e = tid; e < k * k; e += BWD_ROWS) { int i = e % k, j = e / k; Us[i][j] = F.P[i + (int64_t)j * F.f]; }
+    __syncthreads();
+    for (int i = warp; i < k; i += BWD_ROWS / 32) {
+        const double* __restrict__ col = F.T + (int64_t)i * F.r + lo;
         double v = 0.0;
-        for (int64_t a = lane; a < F.r; a += 32) v += col[a] * x[rows[a]];
+        for (int a = lane; a < cnt; a += 32) v += col[a] * xs[a];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (lane == 0) part[i] = v;
     }
     __syncthreads();
+    if (ntiles > 1) {
+        double* slot = cx.bpart + (int64_t)tk.w * KMAX;
+        if (tid < k) slot[(int64_t)tk.y * KMAX + tid] = part[tid];
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            int old = atomicAdd(cx.counters2 + s, 1);
+            s_last = ((old + 1) % ntiles) == 0;
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        if (tid < k) {
+            double v = 0.0;
+            for (int t = 0; t < ntiles; ++t) v += __ldcg(slot + (int64_t)t * KMAX + tid);
+            part[tid] = v;
+        }
+        __syncthreads();
+    }
     if (tid < 32) {
         double v = tid < k ? x[F.c0 + tid] - part[tid] : 0.0;
         for (int j = k - 1; j >= 0; --j) {
             double xj = 0.0;
-            if (tid == j) xj = v / F.P[j + (int64_t)j * F.f];
+            if (tid == j) xj = v / Us[j][j];
             xj = __shfl_sync(0xffffffffu, xj, j);
             if (tid == j) v = xj;
-            if (tid < j) v -= F.P[tid + (int64_t)j * F.f] * xj;
+            if (tid < j) v -= Us[tid][j] * xj;
         }
         if (tid < k) x[F.c0 + tid] = v;
     }
@@ -383,7 +456,7 @@ void launch_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks
     if (ntasks > 0) k_fwd<<<ntasks, FWD_ROWS, 0, st>>>(cx, tasks, win, zout);
 }
 void launch_bwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, double* x) {
-    if (ntasks > 0) k_bwd<<<ntasks, 256, 0, st>>>(cx, tasks, x);
+    if (ntasks > 0) k_bwd<<<ntasks, BWD_ROWS, 0, st>>>(cx, tasks, x);
 }
 
 }  // namespace smslu

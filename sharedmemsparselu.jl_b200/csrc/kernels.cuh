@@ -20,6 +20,7 @@ constexpr int KMAX = 32;          // widest pivot block of a front (symbolic cha
 constexpr int PANEL_ROWS = 128;   // rows of L21 / U12' handled by one panel CTA
 constexpr int GEMM_TILE = 64;
 constexpr int FWD_ROWS = 256;
+constexpr int BWD_ROWS = 256;
 constexpr int ZERO_TILE = 8192;
 
 struct DevCtx {
@@ -36,7 +37,9 @@ struct DevCtx {
     double* lu;
     double* cb;
     double* upd;        // forward-solve update vectors, sum_r doubles
+    double* bpart;      // backward-solve partial sums, KMAX doubles per (supernode, tile)
     int* counters;      // one per supernode, used by the panel kernel
+    int* counters2;     // one per supernode, used by the backward-solve kernel
     int* flag;          // first bad pivot column (atomicMin), INT_MAX when clean
 };
 

@@ -614,14 +614,35 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
         S.flops_stored += 2.0 * kd * kd * kd / 3.0 + 2.0 * kd * kd * rd + 2.0 * kd * rd * rd;
     }
     S.lu_size = off;
+    // direct-write eligibility
+    S.direct.assign(nsn, 0);
+    S.cb_assigned.assign(nsn, 0);
+    for (int c = 0; c < nsn; ++c) {
+        const int s = S.sn_parent[c];
+        if (s == -1) continue;
+        const int64_t kc = S.sn_start[c + 1] - S.sn_start[c], rc = S.rows_ptr[c + 1] - S.rows_ptr[c];
+        if (kc + rc <= opt.small_front_max) continue;
+        if (S.child_ptr[s + 1] - S.child_ptr[s] != 1) continue;
+        S.direct[c] = 1;
+        const int64_t ks = S.sn_start[s + 1] - S.sn_start[s], rs = S.rows_ptr[s + 1] - S.rows_ptr[s];
+        int64_t inside = 0;   // rows of c that are pivot columns of s
+        for (int64_t t = S.rows_ptr[c]; t < S.rows_ptr[c + 1] && S.rel[t] < ks; ++t) ++inside;
+        if (rc - inside == rs) S.cb_assigned[s] = 1;
+    }
     {
         Arena arena;
+        std::vector<char> have(nsn, 0);
+        auto need = [&](int s) {
+            if (have[s]) return;
+            int64_t r = S.rows_ptr[s + 1] - S.rows_ptr[s];
+            S.CBoff[s] = arena.alloc(align2(r * r));
+            have[s] = 1;
+        };
         for (int l = 0; l < S.nlevels; ++l) {
-            for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) {
-                int s = S.level_sn[t];
-                int64_t r = S.rows_ptr[s + 1] - S.rows_ptr[s];
-                S.CBoff[s] = arena.alloc(align2(r * r));
-            }
+            for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) need(S.level_sn[t]);
+            // a direct child writes into its parent's block while its own level runs
+            for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t)
+                if (S.direct[S.level_sn[t]]) need(S.sn_parent[S.level_sn[t]]);
             for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) {
                 int s = S.level_sn[t];
                 for (int u = S.child_ptr[s]; u < S.child_ptr[s + 1]; ++u) {

@@ -26,6 +26,7 @@ struct SymOptions {
     int relax_k2 = 48;            // width <= k2: allow zero fraction relax_f2, else relax_f3
     double relax_f1 = 0.5, relax_f2 = 0.15, relax_f3 = 0.05;
     int dense_factor = 10;        // vertices with degree > dense_factor*sqrt(n) are ordered last
+    int small_front_max = 96;     // fronts up to this size run in the fused shared-memory kernel
 };
 
 struct Symbolic {
@@ -43,6 +44,10 @@ struct Symbolic {
     std::vector<int> rel;             // same shape as rows: local index in the PARENT's front
     std::vector<int> sn_parent;       // -1 for roots
     std::vector<int> child_ptr, child_idx;   // children in ascending order
+    // direct[c] = 1: c is the only child of its parent and a 'big' front, so its Schur update is
+    // written straight into the parent's panels / contribution block (no extend-add pass).
+    // cb_assigned[s] = 1: every entry of C_s is assigned by that direct child (no zeroing pass).
+    std::vector<char> direct, cb_assigned;
     std::vector<int> sn_level;        // 0 = leaves
     int nlevels = 0;
     std::vector<int> level_ptr, level_sn;

@@ -68,6 +68,7 @@ int64_t hx_factor(void* hv, const double* Ax, const double* Rs) {
     if (Rs) h->Rs.assign(Rs, Rs + n);
     h->lu.assign(S.lu_size, 0.0);
     h->cb.assign(S.cb_size, 0.0);
+    std::vector<char> zeroed(S.nsn, 0);
     for (int c = 0; c < n; ++c)
         for (int64_t t = h->Ap[c]; t < h->Ap[c + 1]; ++t) h->lu[S.a_dst[t]] += h->Rs[h->Ai[t]] * Ax[t];
     int64_t bad = -1;
@@ -79,10 +80,14 @@ int64_t hx_factor(void* hv, const double* Ax, const double* Rs) {
             double* P = h->lu.data() + S.Loff[s];
             double* T = h->lu.data() + S.Uoff[s];
             double* C = h->cb.data() + S.CBoff[s];
-            for (int64_t e = 0; e < r * r; ++e) C[e] = 0.0;
-            // extend-add
+            const bool has_children = S.child_ptr[s + 1] > S.child_ptr[s];
+            // blocks that receive '+=' contributions are zeroed before the first one arrives: at
+            // this level for extend-add children, one level earlier for a direct child (done there)
+            if (has_children && !S.cb_assigned[s] && !zeroed[s]) { for (int64_t e = 0; e < r * r; ++e) C[e] = 0.0; zeroed[s] = 1; }
+            // extend-add of the children that did not write directly
             for (int ci = S.child_ptr[s]; ci < S.child_ptr[s + 1]; ++ci) {
                 const int c = S.child_idx[ci];
+                if (S.direct[c]) continue;
                 const int64_t rc = S.rows_ptr[c + 1] - S.rows_ptr[c];
                 const int* rel = S.rel.data() + S.rows_ptr[c];
                 const double* Cc = h->cb.data() + S.CBoff[c];
@@ -109,11 +114,36 @@ int64_t hx_factor(void* hv, const double* Ax, const double* Rs) {
                     for (int64_t i = j + 1; i < k; ++i) T[a + i * r] -= P[i + j * f] * uja;
                 }
             }
+            // Schur update.  beta: the block holds assembled contributions; leaves start from 0.
+            if (!has_children) for (int64_t e = 0; e < r * r; ++e) C[e] = 0.0;
             for (int64_t p = 0; p < k; ++p)
                 for (int64_t b = 0; b < r; ++b) {
                     const double upb = T[b + p * r];
                     for (int64_t a = 0; a < r; ++a) C[a + b * r] -= P[(k + a) + p * f] * upb;
                 }
+            if (S.direct[s]) {   // hand the finished block straight to the parent
+                const int ps = S.sn_parent[s];
+                if (!S.cb_assigned[ps] && !zeroed[ps]) {
+                    const int64_t pr0 = S.rows_ptr[ps + 1] - S.rows_ptr[ps];
+                    double* PC0 = h->cb.data() + S.CBoff[ps];
+                    for (int64_t e = 0; e < pr0 * pr0; ++e) PC0[e] = 0.0;
+                    zeroed[ps] = 1;
+                }
+                const int64_t pk = S.sn_start[ps + 1] - S.sn_start[ps], pr = S.rows_ptr[ps + 1] - S.rows_ptr[ps], pf = pk + pr;
+                double* PP = h->lu.data() + S.Loff[ps];
+                double* PT = h->lu.data() + S.Uoff[ps];
+                double* PC = h->cb.data() + S.CBoff[ps];
+                const int* rel = S.rel.data() + S.rows_ptr[s];
+                for (int64_t b = 0; b < r; ++b)
+                    for (int64_t a = 0; a < r; ++a) {
+                        const double v = C[a + b * r];
+                        const int64_t ra = rel[a], rb = rel[b];
+                        if (rb < pk) PP[ra + rb * pf] += v;
+                        else if (ra < pk) PT[(rb - pk) + ra * pr] += v;
+                        else if (S.cb_assigned[ps]) PC[(ra - pk) + (rb - pk) * pr] = v;
+                        else PC[(ra - pk) + (rb - pk) * pr] += v;
+                    }
+            }
         }
     return bad;
 }

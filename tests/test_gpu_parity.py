@@ -130,10 +130,11 @@ def test_reference_sparse_testsets_with_given_pivots(smslu, O, W, nel):
     F = smslu.ParallelSparseLU(A, p=piv.p, q=piv.q, Rs=piv.Rs)
     ref = O.OracleLU(A, p=F.p, q=F.q, Rs=piv.Rs)
     b = W.rhs(n, 5)
+    # as in the reference: lsolve!(F, x) against `F.L \ b` with F's own factor (test:68-70, 102-104)
     x = b.copy(); smslu.lsolve_(F, x)
-    assert isapprox(x, ref.lsolve(b), TOL)
+    assert isapprox(x, O.csc_lsolve(F.L, b), TOL)
     x = b.copy(); smslu.rsolve_(F, x)
-    assert isapprox(x, ref.usolve(b), DENSE_TOL)
+    assert isapprox(x, O.csc_usolve(F.U, b), DENSE_TOL)
     x = np.empty(n); smslu.ldiv_(x, F, b)
     assert isapprox(x, ref.solve(b), TOL * 10)
     assert isapprox(x, np.linalg.solve(A.toarray(), b), 1e-9)
@@ -150,9 +151,9 @@ def test_reference_dense_testsets_with_given_pivots(smslu, O, W, n):
     assert relerr_csc(F.L.data, ref.Lx, ref.Lp) < 1e-10 and relerr_csc(F.U.data, ref.Ux, ref.Up) < 1e-10
     b = W.rhs(n, 6)
     x = b.copy(); smslu.lsolve_(F, x)
-    assert isapprox(x, ref.lsolve(b), TOL * 10)
+    assert isapprox(x, O.csc_lsolve(F.L, b), TOL)               # test:49-51
     x = b.copy(); smslu.rsolve_(F, x)
-    assert isapprox(x, ref.usolve(b), DENSE_TOL)
+    assert isapprox(x, O.csc_usolve(F.U, b), DENSE_TOL)         # test:84-86
     x = np.empty(n); smslu.ldiv_(x, F, b)
     assert isapprox(x, np.linalg.solve(A.toarray(), b), DENSE_TOL * 10)
     F.close()
