@@ -89,108 +89,170 @@ __global__ void __launch_bounds__(256) k_extend_add(DevCtx cx, const int4* __res
     }
 }
 
+// ------------------------------------------------------------------ warp-level 32x32 LU
+// One warp factors a k x k (k <= 32) block held one row per lane in registers, in the given
+// (static) pivot order: on exit lane i holds row i of the packed factors (L strictly below the
+// diagonal, U on and above).  No shared memory, no block barriers; the pivot row travels by
+// shuffles.  Entries with row or column >= k must be zero on entry.
+__device__ __forceinline__ void warp_lu32(double (&a)[KMAX], int lane, int k, int c0, int* flag) {
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) {
+        if (j >= k) break;
+        const double piv = __shfl_sync(0xffffffffu, a[j], j);
+        if (lane == 0 && bad_pivot(piv)) atomicMin(flag, c0 + j);
+        double l = 0.0;
+        if (lane > j) { l = a[j] / piv; a[j] = l; }
+#pragma unroll
+        for (int c = j + 1; c < KMAX; ++c) {
+            const double u = __shfl_sync(0xffffffffu, a[c], j);
+            if (lane > j) a[c] -= l * u;
+        }
+    }
+}
+
+// Row of L21 against U11 (x <- x U11^{-1}) or row of U12' against L11' (x <- x L11^{-T}, unit
+// diagonal); D holds the packed factors of the pivot block in shared memory.
+__device__ __forceinline__ void trsm_row_upper(double (&x)[KMAX], const double (*D)[KMAX + 1], int k) {
+#pragma unroll
+    for (int c = 0; c < KMAX; ++c) {
+        if (c >= k) break;
+        double v = x[c];
+#pragma unroll
+        for (int p = 0; p < c; ++p) v -= x[p] * D[p][c];
+        x[c] = v / D[c][c];
+    }
+}
+__device__ __forceinline__ void trsm_row_lower_t(double (&x)[KMAX], const double (*D)[KMAX + 1], int k) {
+#pragma unroll
+    for (int c = 0; c < KMAX; ++c) {
+        if (c >= k) break;
+        double v = x[c];
+#pragma unroll
+        for (int p = 0; p < c; ++p) v -= x[p] * D[c][p];
+        x[c] = v;
+    }
+}
+
 // ------------------------------------------------------------------ fused small front
-// One CTA holds the whole f x f front in shared memory: assemble, eliminate the k pivots, write
-// the panels and the contribution block back.  task: x = supernode, y = has assembled CB.
-__global__ void k_front_small(DevCtx cx, const int4* __restrict__ tasks) {
+// One CTA does a whole front with f <= SMALL_F_MAX: warp 0 factors the pivot block in registers
+// (warp_lu32) while the other warps stage L21 and U12' in shared memory; then every thread solves
+// rows of the two panels against the pivot block, and the CTA forms the contribution block
+// C = beta*C - L21 U12 from shared memory (4x4 micro-tiles) and streams it to HBM.
+// task: x = supernode, y = beta (the block holds assembled child contributions).
+// dynamic shared memory: 2 * KMAX * rp doubles, rp = r rounded up to 4 (+4 padding).
+__global__ void __launch_bounds__(128) k_front_small(DevCtx cx, const int4* __restrict__ tasks) {
     extern __shared__ double sm[];
+    __shared__ double D[KMAX][KMAX + 1];
     int4 tk = tasks[blockIdx.x];
     const Front F = load_front(cx, tk.x);
-    const int f = (int)F.f, k = F.k, r = (int)F.r;
-    const int ld = f | 1;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    for (int e = tid; e < f * k; e += nt) { int i = e % f, j = e / f; sm[i + j * ld] = F.P[e]; }
-    for (int e = tid; e < r * k; e += nt) { int a = e % r, i = e / r; sm[i + (k + a) * ld] = F.T[e]; }
-    if (tk.y) {
-        for (int e = tid; e < r * r; e += nt) { int a = e % r, b = e / r; sm[(k + a) + (k + b) * ld] = F.C[e]; }
+    const int k = F.k, r = (int)F.r, f = (int)F.f;
+    const int rp = ((r + 3) & ~3) + 4;
+    double* Ls = sm;                  // Ls[c * rp + a] = L21[a][c]
+    double* Ts = sm + KMAX * rp;      // Ts[c * rp + b] = U12[c][b]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (warp == 0) {
+        double a[KMAX];
+#pragma unroll
+        for (int c = 0; c < KMAX; ++c) a[c] = (lane < k && c < k) ? F.P[lane + (int64_t)c * f] : 0.0;
+        warp_lu32(a, lane, k, F.c0, cx.flag);
+#pragma unroll
+        for (int c = 0; c < KMAX; ++c) {
+            D[lane][c] = a[c];
+            if (lane < k && c < k) F.P[lane + (int64_t)c * f] = a[c];
+        }
     } else {
-        for (int e = tid; e < r * r; e += nt) { int a = e % r, b = e / r; sm[(k + a) + (k + b) * ld] = 0.0; }
+        for (int c = warp - 1; c < k; c += 3) {
+            const double* __restrict__ pl = F.P + k + (int64_t)c * f;
+            const double* __restrict__ pt = F.T + (int64_t)c * r;
+            for (int a = lane; a < r; a += 32) { Ls[c * rp + a] = pl[a]; Ts[c * rp + a] = pt[a]; }
+        }
     }
     __syncthreads();
-    const int tx = tid & 31, ty = tid >> 5, ny = nt >> 5;
-    for (int j = 0; j < k; ++j) {
-        const double piv = sm[j + j * ld];
-        if (tid == 0 && bad_pivot(piv)) atomicMin(cx.flag, F.c0 + j);
-        for (int i = j + 1 + tid; i < f; i += nt) sm[i + j * ld] /= piv;
-        __syncthreads();
-        for (int c = j + 1 + ty; c < f; c += ny) {
-            const double u = sm[j + c * ld];
-            for (int i = j + 1 + tx; i < f; i += 32) sm[i + c * ld] -= sm[i + j * ld] * u;
-        }
-        __syncthreads();
+    for (int t = tid; t < 2 * r; t += 128) {   // row solves: first the r rows of L21, then of U12'
+        double x[KMAX];
+        const bool lower = t < r;
+        const int a = lower ? t : t - r;
+        double* row = (lower ? Ls : Ts) + a;
+#pragma unroll
+        for (int c = 0; c < KMAX; ++c) x[c] = c < k ? row[c * rp] : 0.0;
+        if (lower) trsm_row_upper(x, D, k); else trsm_row_lower_t(x, D, k);
+        double* g = lower ? F.P + k + a : F.T + a;
+        const int64_t ldg = lower ? f : r;
+#pragma unroll
+        for (int c = 0; c < KMAX; ++c) if (c < k) { row[c * rp] = x[c]; g[(int64_t)c * ldg] = x[c]; }
     }
-    for (int e = tid; e < f * k; e += nt) { int i = e % f, j = e / f; F.P[e] = sm[i + j * ld]; }
-    for (int e = tid; e < r * k; e += nt) { int a = e % r, i = e / r; F.T[e] = sm[i + (k + a) * ld]; }
-    for (int e = tid; e < r * r; e += nt) { int a = e % r, b = e / r; F.C[e] = sm[(k + a) + (k + b) * ld]; }
+    __syncthreads();
+    const int nt4 = (r + 3) >> 2;
+    for (int t = tid; t < nt4 * nt4; t += 128) {
+        const int a0 = (t % nt4) * 4, b0 = (t / nt4) * 4;
+        double acc[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                acc[i][j] = (tk.y && a0 + i < r && b0 + j < r) ? F.C[(a0 + i) + (int64_t)(b0 + j) * r] : 0.0;
+        for (int c = 0; c < k; ++c) {
+            const double2 l01 = *reinterpret_cast<const double2*>(Ls + c * rp + a0);
+            const double2 l23 = *reinterpret_cast<const double2*>(Ls + c * rp + a0 + 2);
+            const double2 u01 = *reinterpret_cast<const double2*>(Ts + c * rp + b0);
+            const double2 u23 = *reinterpret_cast<const double2*>(Ts + c * rp + b0 + 2);
+            const double l[4] = {l01.x, l01.y, l23.x, l23.y}, u[4] = {u01.x, u01.y, u23.x, u23.y};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[i][j] -= l[i] * u[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (a0 + i < r && b0 + j < r) F.C[(a0 + i) + (int64_t)(b0 + j) * r] = acc[i][j];
+    }
 }
 
 // ------------------------------------------------------------------ panel: pivot-block LU + TRSMs
 // task: x = supernode, y = tile, z = number of L21 tiles (nt), w = total CTAs of this front.
 // Tiles [0,nt) solve 128 rows of L21 against U11, tiles [nt,2nt) solve 128 rows of U12' against
-// L11'.  Every CTA factors the (<=32x32) pivot block redundantly in shared memory; the CTA that
-// is last to have READ the unfactored block writes the factored one back (no CTA ever waits).
+// L11'.  Every CTA factors the (<=32x32) pivot block redundantly (warp 0, in registers) while the
+// other warps already fetch their rows; the CTA that is last to have READ the unfactored block
+// writes the factored one back (no CTA ever waits on another).
 __global__ void __launch_bounds__(PANEL_ROWS) k_panel(DevCtx cx, const int4* __restrict__ tasks) {
     __shared__ double D[KMAX][KMAX + 1];
     __shared__ int s_last;
     int4 tk = tasks[blockIdx.x];
     const Front F = load_front(cx, tk.x);
-    const int k = F.k, tid = threadIdx.x;
-    for (int e = tid; e < k * k; e += PANEL_ROWS) { int i = e % k, j = e / k; D[i][j] = F.P[i + (int64_t)j * F.f]; }
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        int old = atomicAdd(cx.counters + tk.x, 1);
-        s_last = ((old + 1) % tk.w) == 0;
-    }
-    const int tx = tid & 31, ty = tid >> 5;
-    for (int j = 0; j < k; ++j) {
-        const double piv = D[j][j];
-        if (tid == 0 && bad_pivot(piv)) atomicMin(cx.flag, F.c0 + j);
-        if (tid > j && tid < k) D[tid][j] /= piv;
-        __syncthreads();
-        for (int c = j + 1 + ty; c < k; c += PANEL_ROWS / 32) {
-            const int i = j + 1 + tx;
-            if (i < k) D[i][c] -= D[i][j] * D[j][c];
-        }
-        __syncthreads();
-    }
-    if (s_last)
-        for (int e = tid; e < k * k; e += PANEL_ROWS) { int i = e % k, j = e / k; F.P[i + (int64_t)j * F.f] = D[i][j]; }
+    const int k = F.k, tid = threadIdx.x, lane = tid & 31;
     const int nt = tk.z;
+    const bool lower = tk.y < nt;
+    const int64_t row = (int64_t)(lower ? tk.y : tk.y - nt) * PANEL_ROWS + tid;
+    double* src = lower ? F.P + F.k + row : F.T + row;
+    const int64_t ld = lower ? F.f : F.r;
     double x[KMAX];
-    if (tk.y < nt) {   // L21 row: x <- x * U11^{-1}
-        const int64_t row = (int64_t)tk.y * PANEL_ROWS + tid;
-        if (row >= F.r) return;
-        double* src = F.P + F.k + row;
+    if (tid < 32) {
+        double a[KMAX];
 #pragma unroll
-        for (int c = 0; c < KMAX; ++c) x[c] = c < k ? src[(int64_t)c * F.f] : 0.0;
+        for (int c = 0; c < KMAX; ++c) a[c] = (lane < k && c < k) ? F.P[lane + (int64_t)c * F.f] : 0.0;
 #pragma unroll
-        for (int c = 0; c < KMAX; ++c) {
-            if (c >= k) break;
-            double v = x[c];
+        for (int c = 0; c < KMAX; ++c) x[c] = (c < k && row < F.r) ? src[(int64_t)c * ld] : 0.0;
+        warp_lu32(a, lane, k, F.c0, cx.flag);
 #pragma unroll
-            for (int p = 0; p < c; ++p) v -= x[p] * D[p][c];
-            x[c] = v / D[c][c];
+        for (int c = 0; c < KMAX; ++c) D[lane][c] = a[c];
+        if (lane == 0) {   // this CTA's reads of the unfactored block are complete
+            __threadfence();
+            int old = atomicAdd(cx.counters + tk.x, 1);
+            s_last = ((old + 1) % tk.w) == 0;
         }
+    } else {
 #pragma unroll
-        for (int c = 0; c < KMAX; ++c) if (c < k) src[(int64_t)c * F.f] = x[c];
-    } else {           // U12' row: x <- x * L11^{-T} (unit diagonal)
-        const int64_t row = (int64_t)(tk.y - nt) * PANEL_ROWS + tid;
-        if (row >= F.r) return;
-        double* src = F.T + row;
-#pragma unroll
-        for (int c = 0; c < KMAX; ++c) x[c] = c < k ? src[(int64_t)c * F.r] : 0.0;
-#pragma unroll
-        for (int c = 0; c < KMAX; ++c) {
-            if (c >= k) break;
-            double v = x[c];
-#pragma unroll
-            for (int p = 0; p < c; ++p) v -= x[p] * D[c][p];
-            x[c] = v;
-        }
-#pragma unroll
-        for (int c = 0; c < KMAX; ++c) if (c < k) src[(int64_t)c * F.r] = x[c];
+        for (int c = 0; c < KMAX; ++c) x[c] = (c < k && row < F.r) ? src[(int64_t)c * ld] : 0.0;
     }
+    __syncthreads();
+    if (s_last)
+        for (int e = tid; e < KMAX * k; e += PANEL_ROWS) { int i = e & 31, j = e >> 5; if (i < k) F.P[i + (int64_t)j * F.f] = D[i][j]; }
+    if (row >= F.r) return;
+    if (lower) trsm_row_upper(x, D, k); else trsm_row_lower_t(x, D, k);
+#pragma unroll
+    for (int c = 0; c < KMAX; ++c) if (c < k) src[(int64_t)c * ld] = x[c];
 }
 
 // ------------------------------------------------------------------ Schur update of the CB
@@ -412,10 +474,10 @@ constexpr int SMALL_F_MAX = 96;
 
 int front_small_limit() { return SMALL_F_MAX; }
 
+static size_t small_smem(int rmax) { return sizeof(double) * 2 * KMAX * (size_t)(((rmax + 3) & ~3) + 4); }
+
 cudaError_t kernels_init() {
-    int ld = SMALL_F_MAX | 1;
-    return cudaFuncSetAttribute(k_front_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)(sizeof(double) * ld * SMALL_F_MAX));
+    return cudaFuncSetAttribute(k_front_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem(SMALL_F_MAX));
 }
 
 void launch_rowscale(cudaStream_t st, int n, const int64_t* rowptr, const int64_t* rowidx, const double* av, double* Rs) {
@@ -436,9 +498,7 @@ void launch_extend_add(cudaStream_t st, const DevCtx& cx, const int4* tasks, int
 }
 void launch_front_small(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int fmax) {
     if (ntasks <= 0) return;
-    int threads = fmax <= 32 ? 64 : (fmax <= 64 ? 128 : 256);
-    size_t smem = sizeof(double) * (size_t)(fmax | 1) * fmax;
-    k_front_small<<<ntasks, threads, smem, st>>>(cx, tasks);
+    k_front_small<<<ntasks, 128, small_smem(fmax), st>>>(cx, tasks);   // fmax bounds r of the class
 }
 void launch_panel(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks) {
     if (ntasks > 0) k_panel<<<ntasks, PANEL_ROWS, 0, st>>>(cx, tasks);
