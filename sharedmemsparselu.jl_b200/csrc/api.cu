@@ -58,7 +58,7 @@ struct smslu_handle_s {
     double *d_Rs = nullptr, *d_aval = nullptr, *d_w = nullptr, *d_z = nullptr, *d_xb = nullptr;
     int4* d_tasks = nullptr;
     std::vector<Launch> fac, fwd, bwd;
-    int64_t bpart_slots = 0;
+    int64_t bpart_slots = 0, ncounters = 0;
 
     bool own_stream = true;
     cudaStream_t user_stream = nullptr;
@@ -120,6 +120,8 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
     auto K = [&](int s) { return S.sn_start[s + 1] - S.sn_start[s]; };
     auto R = [&](int s) { return (int64_t)(S.rows_ptr[s + 1] - S.rows_ptr[s]); };
     auto NC = [&](int s) { return S.child_ptr[s + 1] - S.child_ptr[s]; };
+    auto SMALL = [&](int s) { return K(s) <= NB && K(s) + R(s) <= small_max; };
+    int64_t ncounters = 0;
     auto push = [&](std::vector<Launch>& v, int kind, int64_t off, int fmax) {
         int nt = (int)((int64_t)tasks.size() - off);
         if (nt > 0) v.push_back(Launch{kind, off, nt, fmax});
@@ -167,26 +169,40 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
             for (int t = 0; t < cnt; ++t) {
                 int s = sn[t];
                 int64_t f = K(s) + R(s);
-                if (f > lo && f <= classes[ci]) tasks.push_back(make_int4(s, NC(s) > 0 ? 1 : 0, 0, 0));
+                if (SMALL(s) && f > lo && f <= classes[ci]) tasks.push_back(make_int4(s, NC(s) > 0 ? 1 : 0, 0, 0));
             }
             push(h->fac, L_SMALL, off, classes[ci]);
             lo = classes[ci];
         }
-        // big fronts: panel then Schur update
-        off = (int64_t)tasks.size();
-        for (int t = 0; t < cnt; ++t) {
-            int s = sn[t];
-            int64_t r = R(s);
-            if (K(s) + r <= small_max) continue;
-            int nt = (int)((r + PANEL_ROWS - 1) / PANEL_ROWS);
-            for (int i = 0; i < 2 * nt; ++i) tasks.push_back(make_int4(s, i, nt, 2 * nt));
+        // big fronts: left-looking panel steps (one launch per 32 pivot columns), then Schur update
+        int max_blk = 0;
+        for (int t = 0; t < cnt; ++t) if (!SMALL(sn[t])) max_blk = std::max(max_blk, (K(sn[t]) + NB - 1) / NB);
+        for (int g = 0; g < max_blk; ++g) {
+            off = (int64_t)tasks.size();
+            for (int t = 0; t < cnt; ++t) {
+                int s = sn[t];
+                if (SMALL(s)) continue;
+                const int k = K(s), nblk = (k + NB - 1) / NB;
+                if (g >= nblk) continue;
+                const int64_t r = R(s), f = k + r;
+                const int j1 = std::min(k, (g + 1) * NB);
+                int tl = (int)((f - j1 + PANEL_ROWS - 1) / PANEL_ROWS);      // rows below the diagonal block
+                const int tt = (int)((r + PANEL_ROWS - 1) / PANEL_ROWS);     // rows of U12'
+                const int ti = (k - j1 + PANEL_ROWS - 1) / PANEL_ROWS;       // columns right of it
+                if (tl + tt + ti == 0) tl = 1;                               // someone has to factor D_gg
+                const int total = tl + tt + ti;
+                const int cidx = (int)ncounters++;
+                for (int i = 0; i < tl; ++i) tasks.push_back(make_int4(s, g | (0 << 4) | (total << 8), i, cidx));
+                for (int i = 0; i < tt; ++i) tasks.push_back(make_int4(s, g | (1 << 4) | (total << 8), i, cidx));
+                for (int i = 0; i < ti; ++i) tasks.push_back(make_int4(s, g | (2 << 4) | (total << 8), i, cidx));
+            }
+            push(h->fac, L_PANEL, off, g);
         }
-        push(h->fac, L_PANEL, off, 0);
         off = (int64_t)tasks.size();
         for (int t = 0; t < cnt; ++t) {
             int s = sn[t];
             int64_t r = R(s);
-            if (K(s) + r <= small_max) continue;
+            if (SMALL(s)) continue;
             int nt = (int)((r + GEMM_TILE - 1) / GEMM_TILE);
             for (int j = 0; j < nt; ++j)
                 for (int i = 0; i < nt; ++i) {
@@ -217,6 +233,7 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
         push(h->bwd, L_BWD, off, 0);
     }
     h->bpart_slots = slots;
+    h->ncounters = ncounters;
 }
 
 int ensure_uploaded(smslu_handle_t h) {
@@ -274,7 +291,6 @@ int ensure_uploaded(smslu_handle_t h) {
     if ((rc = dev_alloc(h, &d_lu, (size_t)S.lu_size))) return rc;
     if ((rc = dev_alloc(h, &d_cb, (size_t)S.cb_size))) return rc;
     if ((rc = dev_alloc(h, &d_upd, (size_t)S.sum_r))) return rc;
-    if ((rc = dev_alloc(h, &d_counters, (size_t)S.nsn))) return rc;
     if ((rc = dev_alloc(h, &d_flag, 1))) return rc;
     if ((rc = dev_alloc(h, &h->d_Rs, (size_t)n))) return rc;
     if ((rc = dev_alloc(h, &h->d_aval, (size_t)h->annz))) return rc;
@@ -289,6 +305,7 @@ int ensure_uploaded(smslu_handle_t h) {
     build_schedules(h, tasks);
     if ((rc = dev_upload(h, &h->d_tasks, tasks))) return rc;
     double* d_bpart; int* d_counters2;
+    if ((rc = dev_alloc(h, &d_counters, (size_t)h->ncounters))) return rc;
     if ((rc = dev_alloc(h, &d_bpart, (size_t)h->bpart_slots * KMAX))) return rc;
     if ((rc = dev_alloc(h, &d_counters2, (size_t)S.nsn))) return rc;
     CU(cudaMemset(d_counters2, 0, sizeof(int) * std::max(S.nsn, 1)));
@@ -342,7 +359,7 @@ int run_schedule(smslu_handle_t h, const std::vector<Launch>& sched, const doubl
             case L_ZERO: launch_zero_cb(h->stream, h->cx, tk, L.ntasks); break;
             case L_EXTEND: launch_extend_add(h->stream, h->cx, tk, L.ntasks); break;
             case L_SMALL: launch_front_small(h->stream, h->cx, tk, L.ntasks, L.fmax); break;
-            case L_PANEL: launch_panel(h->stream, h->cx, tk, L.ntasks); break;
+            case L_PANEL: launch_panel(h->stream, h->cx, tk, L.ntasks, L.fmax); break;
             case L_GEMM: launch_gemm_cb(h->stream, h->cx, tk, L.ntasks); break;
             case L_FWD: launch_fwd(h->stream, h->cx, tk, L.ntasks, win, zx); break;
             case L_BWD: launch_bwd(h->stream, h->cx, tk, L.ntasks, zx); break;
@@ -364,7 +381,7 @@ int enqueue_refactor(smslu_handle_t h, const double* av, bool rs_given) {
     }
     if ((rc = prof_begin(h, SMSLU_K_SCATTER))) return rc;
     CU(cudaMemsetAsync(h->cx.flag, 0x7f, sizeof(int), h->stream));   // 0x7f7f7f7f = clean
-    CU(cudaMemsetAsync(h->cx.counters, 0, sizeof(int) * std::max(S.nsn, 1), h->stream));
+    CU(cudaMemsetAsync(h->cx.counters, 0, sizeof(int) * std::max<int64_t>(h->ncounters, 1), h->stream));
     CU(cudaMemsetAsync(h->cx.lu, 0, sizeof(double) * S.lu_size, h->stream));
     launch_scatter(h->stream, h->annz, h->d_a_dst, h->d_a_row, h->d_Rs, av, h->cx.lu);
     if ((rc = prof_end(h))) return rc;
@@ -472,6 +489,8 @@ int smslu_analyze(smslu_handle_t h, const int64_t* p, const int64_t* q) {
     o.relax = h->opt.relax;
     o.max_width = h->opt.max_width;
     o.small_front_max = front_small_limit();
+    o.small_k_max = NB;
+    o.relax_width = NB;
     std::vector<int> pp, qq;
     if (o.ordering == ORD_GIVEN) {
         if (!p || !q) return fail(h, SMSLU_E_ARG, "ordering GIVEN needs p and q");

@@ -89,101 +89,97 @@ __global__ void __launch_bounds__(256) k_extend_add(DevCtx cx, const int4* __res
     }
 }
 
-// ------------------------------------------------------------------ warp-level 32x32 LU
-// One warp factors a k x k (k <= 32) block held one row per lane in registers, in the given
-// (static) pivot order: on exit lane i holds row i of the packed factors (L strictly below the
-// diagonal, U on and above).  No shared memory, no block barriers; the pivot row travels by
-// shuffles.  Entries with row or column >= k must be zero on entry.
-__device__ __forceinline__ void warp_lu32(double (&a)[KMAX], int lane, int k, int c0, int* flag) {
-#pragma unroll
-    for (int j = 0; j < KMAX; ++j) {
-        if (j >= k) break;
-        const double piv = __shfl_sync(0xffffffffu, a[j], j);
-        if (lane == 0 && bad_pivot(piv)) atomicMin(flag, c0 + j);
+// ------------------------------------------------------------------ dense building blocks
+// LU of a w x w (w <= 32) block held in shared memory, static pivot order, all PANEL threads.
+// One barrier per elimination step: every thread reads the pivot and its own row's entry of
+// column j, divides, and updates its share of the row; the multiplier is stored after the
+// barrier (column j is never read again).  rd[j] receives 1/pivot for the row solves.
+__device__ __forceinline__ void block_lu(double (*D)[NB + 1], double* rd, int w, int c0, int* flag) {
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    for (int j = 0; j < w; ++j) {
+        const double piv = D[j][j];
+        const int i = j + 1 + tx;
         double l = 0.0;
-        if (lane > j) { l = a[j] / piv; a[j] = l; }
-#pragma unroll
-        for (int c = j + 1; c < KMAX; ++c) {
-            const double u = __shfl_sync(0xffffffffu, a[c], j);
-            if (lane > j) a[c] -= l * u;
+        if (i < w) {
+            l = D[i][j] / piv;
+            for (int c = j + 1 + ty; c < w; c += PANEL_ROWS / 32) D[i][c] -= l * D[j][c];
         }
+        if (tid == 0) {
+            if (bad_pivot(piv)) atomicMin(flag, c0 + j);
+            rd[j] = 1.0 / piv;
+        }
+        __syncthreads();
+        if (ty == 0 && i < w) D[i][j] = l;
     }
+    __syncthreads();
 }
 
-// Row of L21 against U11 (x <- x U11^{-1}) or row of U12' against L11' (x <- x L11^{-T}, unit
-// diagonal); D holds the packed factors of the pivot block in shared memory.
-__device__ __forceinline__ void trsm_row_upper(double (&x)[KMAX], const double (*D)[KMAX + 1], int k) {
+// Row solves against the factored pivot block, written column-oriented (right-looking) so that the
+// dependent chain is one multiply-add per column instead of an inner product:
+//   upper:   x <- x U^{-1}   (U non-unit; rd = reciprocals of its diagonal)
+//   lower_t: x <- x L^{-T}   (L unit lower)
+__device__ __forceinline__ void trsm_row_upper(double (&x)[NB], const double (*D)[NB + 1], const double* rd, int w) {
 #pragma unroll
-    for (int c = 0; c < KMAX; ++c) {
-        if (c >= k) break;
-        double v = x[c];
+    for (int p = 0; p < NB; ++p) {
+        if (p >= w) break;
+        const double xp = x[p] * rd[p];
+        x[p] = xp;
 #pragma unroll
-        for (int p = 0; p < c; ++p) v -= x[p] * D[p][c];
-        x[c] = v / D[c][c];
+        for (int c = p + 1; c < NB; ++c) x[c] -= xp * D[p][c];
     }
 }
-__device__ __forceinline__ void trsm_row_lower_t(double (&x)[KMAX], const double (*D)[KMAX + 1], int k) {
+__device__ __forceinline__ void trsm_row_lower_t(double (&x)[NB], const double (*D)[NB + 1], int w) {
 #pragma unroll
-    for (int c = 0; c < KMAX; ++c) {
-        if (c >= k) break;
-        double v = x[c];
+    for (int p = 0; p < NB; ++p) {
+        if (p >= w) break;
+        const double xp = x[p];
 #pragma unroll
-        for (int p = 0; p < c; ++p) v -= x[p] * D[c][p];
-        x[c] = v;
+        for (int c = p + 1; c < NB; ++c) x[c] -= xp * D[c][p];
     }
 }
 
 // ------------------------------------------------------------------ fused small front
-// One CTA does a whole front with f <= SMALL_F_MAX: warp 0 factors the pivot block in registers
-// (warp_lu32) while the other warps stage L21 and U12' in shared memory; then every thread solves
-// rows of the two panels against the pivot block, and the CTA forms the contribution block
-// C = beta*C - L21 U12 from shared memory (4x4 micro-tiles) and streams it to HBM.
+// One CTA does a whole front with k <= 32 and f <= SMALL_F_MAX: stage the pivot block, L21 and
+// U12' in shared memory, factor the pivot block (block_lu), solve the rows of both panels, then
+// form the contribution block C = beta*C - L21 U12 from shared memory (4x4 micro-tiles).
 // task: x = supernode, y = beta (the block holds assembled child contributions).
-// dynamic shared memory: 2 * KMAX * rp doubles, rp = r rounded up to 4 (+4 padding).
-__global__ void __launch_bounds__(128) k_front_small(DevCtx cx, const int4* __restrict__ tasks) {
+// dynamic shared memory: 2 * NB * rp doubles, rp = r rounded up to 4 (+4 padding).
+__global__ void __launch_bounds__(PANEL_ROWS) k_front_small(DevCtx cx, const int4* __restrict__ tasks) {
     extern __shared__ double sm[];
-    __shared__ double D[KMAX][KMAX + 1];
+    __shared__ double D[NB][NB + 1];
+    __shared__ double rd[NB];
     int4 tk = tasks[blockIdx.x];
     const Front F = load_front(cx, tk.x);
     const int k = F.k, r = (int)F.r, f = (int)F.f;
     const int rp = ((r + 3) & ~3) + 4;
-    double* Ls = sm;                  // Ls[c * rp + a] = L21[a][c]
-    double* Ts = sm + KMAX * rp;      // Ts[c * rp + b] = U12[c][b]
+    double* Ls = sm;                // Ls[c * rp + a] = L21[a][c]
+    double* Ts = sm + NB * rp;      // Ts[c * rp + b] = U12[c][b]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (warp == 0) {
-        double a[KMAX];
-#pragma unroll
-        for (int c = 0; c < KMAX; ++c) a[c] = (lane < k && c < k) ? F.P[lane + (int64_t)c * f] : 0.0;
-        warp_lu32(a, lane, k, F.c0, cx.flag);
-#pragma unroll
-        for (int c = 0; c < KMAX; ++c) {
-            D[lane][c] = a[c];
-            if (lane < k && c < k) F.P[lane + (int64_t)c * f] = a[c];
-        }
-    } else {
-        for (int c = warp - 1; c < k; c += 3) {
-            const double* __restrict__ pl = F.P + k + (int64_t)c * f;
-            const double* __restrict__ pt = F.T + (int64_t)c * r;
-            for (int a = lane; a < r; a += 32) { Ls[c * rp + a] = pl[a]; Ts[c * rp + a] = pt[a]; }
-        }
+    for (int c = warp; c < k; c += PANEL_ROWS / 32) {
+        const double* __restrict__ pc = F.P + (int64_t)c * f;
+        const double* __restrict__ pt = F.T + (int64_t)c * r;
+        if (lane < k) D[lane][c] = pc[lane];
+        for (int a = lane; a < r; a += 32) { Ls[c * rp + a] = pc[k + a]; Ts[c * rp + a] = pt[a]; }
     }
     __syncthreads();
-    for (int t = tid; t < 2 * r; t += 128) {   // row solves: first the r rows of L21, then of U12'
-        double x[KMAX];
+    block_lu(D, rd, k, F.c0, cx.flag);
+    for (int e = tid; e < k * NB; e += PANEL_ROWS) { int i = e & 31, c = e >> 5; if (i < k) F.P[i + (int64_t)c * f] = D[i][c]; }
+    for (int t = tid; t < 2 * r; t += PANEL_ROWS) {   // row solves: the r rows of L21, then of U12'
+        double x[NB];
         const bool lower = t < r;
         const int a = lower ? t : t - r;
         double* row = (lower ? Ls : Ts) + a;
 #pragma unroll
-        for (int c = 0; c < KMAX; ++c) x[c] = c < k ? row[c * rp] : 0.0;
-        if (lower) trsm_row_upper(x, D, k); else trsm_row_lower_t(x, D, k);
+        for (int c = 0; c < NB; ++c) x[c] = c < k ? row[c * rp] : 0.0;
+        if (lower) trsm_row_upper(x, D, rd, k); else trsm_row_lower_t(x, D, k);
         double* g = lower ? F.P + k + a : F.T + a;
         const int64_t ldg = lower ? f : r;
 #pragma unroll
-        for (int c = 0; c < KMAX; ++c) if (c < k) { row[c * rp] = x[c]; g[(int64_t)c * ldg] = x[c]; }
+        for (int c = 0; c < NB; ++c) if (c < k) { row[c * rp] = x[c]; g[(int64_t)c * ldg] = x[c]; }
     }
     __syncthreads();
     const int nt4 = (r + 3) >> 2;
-    for (int t = tid; t < nt4 * nt4; t += 128) {
+    for (int t = tid; t < nt4 * nt4; t += PANEL_ROWS) {
         const int a0 = (t % nt4) * 4, b0 = (t / nt4) * 4;
         double acc[4][4];
 #pragma unroll
@@ -210,54 +206,89 @@ __global__ void __launch_bounds__(128) k_front_small(DevCtx cx, const int4* __re
     }
 }
 
-// ------------------------------------------------------------------ panel: pivot-block LU + TRSMs
-// task: x = supernode, y = tile, z = number of L21 tiles (nt), w = total CTAs of this front.
-// Tiles [0,nt) solve 128 rows of L21 against U11, tiles [nt,2nt) solve 128 rows of U12' against
-// L11'.  Every CTA factors the (<=32x32) pivot block redundantly (warp 0, in registers) while the
-// other warps already fetch their rows; the CTA that is last to have READ the unfactored block
-// writes the factored one back (no CTA ever waits on another).
+// ------------------------------------------------------------------ panel step of a big front
+// A front with k (<= KW) pivot columns is factored in ceil(k/32) left-looking panel steps, one
+// launch each.  Step g owns pivot columns [j0, j1) = [32g, min(k, 32g+32)):
+//   kind 0 (L): 128 rows of P below the diagonal block (the rest of the pivot block and L21):
+//               row <- (row[j0:j1] - row[0:j0] * U[0:j0, j0:j1]) * U_gg^{-1}
+//   kind 1 (T): 128 rows of U12' :  row <- (row[j0:j1] - row[0:j0] * L[j0:j1, 0:j0]') * L_gg^{-T}
+//   kind 2 (I): 128 columns of the pivot block right of the diagonal block (U inside the block),
+//               same arithmetic as kind 1 on P[j0:j1, c].
+// Every CTA first brings the diagonal block up to date (D_gg -= L[g,0:g] U[0:g,g]) and factors it,
+// redundantly; the CTA that is last to have read the raw block stores the factors (nobody waits).
+// task: x = supernode, y = g | kind << 4 | (CTAs of this step of this front) << 8, z = tile,
+//       w = index of the step's arrival counter.
+// dynamic shared memory: 2 * j0 * (NB+1) doubles (the two coefficient blocks).
 __global__ void __launch_bounds__(PANEL_ROWS) k_panel(DevCtx cx, const int4* __restrict__ tasks) {
-    __shared__ double D[KMAX][KMAX + 1];
+    extern __shared__ double coef[];
+    __shared__ double D[NB][NB + 1];
+    __shared__ double rd[NB];
     __shared__ int s_last;
     int4 tk = tasks[blockIdx.x];
     const Front F = load_front(cx, tk.x);
-    const int k = F.k, tid = threadIdx.x, lane = tid & 31;
-    const int nt = tk.z;
-    const bool lower = tk.y < nt;
-    const int64_t row = (int64_t)(lower ? tk.y : tk.y - nt) * PANEL_ROWS + tid;
-    double* src = lower ? F.P + F.k + row : F.T + row;
-    const int64_t ld = lower ? F.f : F.r;
-    double x[KMAX];
-    if (tid < 32) {
-        double a[KMAX];
+    const int g = tk.y & 15, kind = (tk.y >> 4) & 15, total = tk.y >> 8;
+    const int k = F.k, j0 = g * NB, w = (k - j0 < NB) ? k - j0 : NB, j1 = j0 + w;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* Uc = coef;                       // Uc[m * (NB+1) + c] = U[m, j0 + c],  m < j0
+    double* Lc = coef + j0 * (NB + 1);       // Lc[m * (NB+1) + i] = L[j0 + i, m],  m < j0
+    for (int c = warp; c < w; c += PANEL_ROWS / 32) {
+        const double* __restrict__ pc = F.P + (int64_t)(j0 + c) * F.f;
+        for (int m = lane; m < j0; m += 32) Uc[m * (NB + 1) + c] = pc[m];
+        if (lane < w) D[lane][c] = pc[j0 + lane];
+    }
+    for (int m = warp; m < j0; m += PANEL_ROWS / 32)
+        if (lane < w) Lc[m * (NB + 1) + lane] = F.P[(j0 + lane) + (int64_t)m * F.f];
+    __syncthreads();
+    if (tid == 0) {   // this CTA's reads of the raw diagonal block are complete
+        __threadfence();
+        int old = atomicAdd(cx.counters + tk.w, 1);
+        s_last = ((old + 1) % total) == 0;
+    }
+    // ---- this thread's row (or column), brought up to date with the earlier blocks
+    const int64_t idx = (int64_t)tk.z * PANEL_ROWS + tid;
+    double* base; int64_t stride; const double* cf; bool active;
+    if (kind == 0) { active = j1 + idx < F.f; base = F.P + j1 + idx; stride = F.f; cf = Uc; }
+    else if (kind == 1) { active = idx < F.r; base = F.T + idx; stride = F.r; cf = Lc; }
+    else { active = j1 + idx < k; base = F.P + (j1 + idx) * F.f; stride = 1; cf = Lc; }
+    double x[NB];
 #pragma unroll
-        for (int c = 0; c < KMAX; ++c) a[c] = (lane < k && c < k) ? F.P[lane + (int64_t)c * F.f] : 0.0;
+    for (int c = 0; c < NB; ++c) x[c] = (active && c < w) ? base[(int64_t)(j0 + c) * stride] : 0.0;
+    if (active)
+        for (int m = 0; m < j0; ++m) {
+            const double v = base[(int64_t)m * stride];
+            const double* __restrict__ cm = cf + m * (NB + 1);
 #pragma unroll
-        for (int c = 0; c < KMAX; ++c) x[c] = (c < k && row < F.r) ? src[(int64_t)c * ld] : 0.0;
-        warp_lu32(a, lane, k, F.c0, cx.flag);
-#pragma unroll
-        for (int c = 0; c < KMAX; ++c) D[lane][c] = a[c];
-        if (lane == 0) {   // this CTA's reads of the unfactored block are complete
-            __threadfence();
-            int old = atomicAdd(cx.counters + tk.x, 1);
-            s_last = ((old + 1) % tk.w) == 0;
+            for (int c = 0; c < NB; ++c) x[c] -= v * cm[c];
         }
-    } else {
+    // ---- diagonal block: D_gg -= L[g, 0:j0] U[0:j0, g]  (lane = row, warp = 8 columns), then LU
+    if (j0 > 0) {
+        double acc[8];
 #pragma unroll
-        for (int c = 0; c < KMAX; ++c) x[c] = (c < k && row < F.r) ? src[(int64_t)c * ld] : 0.0;
+        for (int u = 0; u < 8; ++u) acc[u] = 0.0;
+        for (int m = 0; m < j0; ++m) {
+            const double li = Lc[m * (NB + 1) + lane];
+            const double* __restrict__ um = Uc + m * (NB + 1) + warp * 8;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc[u] += li * um[u];
+        }
+        if (lane < w) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) if (warp * 8 + u < w) D[lane][warp * 8 + u] -= acc[u];
+        }
     }
     __syncthreads();
+    block_lu(D, rd, w, F.c0 + j0, cx.flag);
     if (s_last)
-        for (int e = tid; e < KMAX * k; e += PANEL_ROWS) { int i = e & 31, j = e >> 5; if (i < k) F.P[i + (int64_t)j * F.f] = D[i][j]; }
-    if (row >= F.r) return;
-    if (lower) trsm_row_upper(x, D, k); else trsm_row_lower_t(x, D, k);
+        for (int e = tid; e < w * NB; e += PANEL_ROWS) { int i = e & 31, c = e >> 5; if (i < w) F.P[(j0 + i) + (int64_t)(j0 + c) * F.f] = D[i][c]; }
+    if (!active) return;
+    if (kind == 0) trsm_row_upper(x, D, rd, w); else trsm_row_lower_t(x, D, w);
 #pragma unroll
-    for (int c = 0; c < KMAX; ++c) if (c < k) src[(int64_t)c * ld] = x[c];
+    for (int c = 0; c < NB; ++c) if (c < w) base[(int64_t)(j0 + c) * stride] = x[c];
 }
 
 // ------------------------------------------------------------------ Schur update of the CB
-// V (r x r) = beta*C - L21 (r x k) * U12 (k x r), U12 held transposed.  64x64 tile per CTA,
-// 4x4 per thread, whole K (<= 32) staged in shared memory once.
+// V (r x r) = beta*C - L21 (r x k) * U12 (k x r), U12 held transposed, k <= KW.  64x64 tile per
+// CTA, 4x4 per thread, K staged through shared memory in chunks of 32.
 // task: x = supernode, y = tile row, z = tile col, w = flags:
 //   bit0 beta   : C holds assembled contributions (else it is taken as zero)
 //   bit1 direct : V is written straight into the parent's front through the rel map (this front
@@ -265,8 +296,8 @@ __global__ void __launch_bounds__(PANEL_ROWS) k_panel(DevCtx cx, const int4* __r
 //   bit2 assign : ... and the parent's contribution-block entries are assigned (=) instead of +=.
 //   without bit1 V overwrites C in place.
 __global__ void __launch_bounds__(256) k_gemm_cb(DevCtx cx, const int4* __restrict__ tasks) {
-    __shared__ double As[KMAX][GEMM_TILE];
-    __shared__ double Bs[KMAX][GEMM_TILE];
+    __shared__ double As[NB][GEMM_TILE];
+    __shared__ double Bs[NB][GEMM_TILE];
     int4 tk = tasks[blockIdx.x];
     const Front F = load_front(cx, tk.x);
     const int k = F.k, tid = threadIdx.x;
@@ -286,21 +317,25 @@ __global__ void __launch_bounds__(256) k_gemm_cb(DevCtx cx, const int4* __restri
             acc[i][j] = (beta && row < F.r && col < F.r) ? F.C[row + col * F.r] : 0.0;
         }
     }
-    for (int e = tid; e < GEMM_TILE * k; e += 256) {
-        int a = e & (GEMM_TILE - 1), p = e >> 6;
-        int64_t ra = m0 + a, rb = n0 + a;
-        As[p][a] = ra < F.r ? A[ra + (int64_t)p * F.f] : 0.0;
-        Bs[p][a] = rb < F.r ? B[rb + (int64_t)p * F.r] : 0.0;
-    }
-    __syncthreads();
-    for (int p = 0; p < k; ++p) {
-        double a[4], b[4];
+    for (int kc = 0; kc < k; kc += NB) {
+        const int kw = (k - kc < NB) ? k - kc : NB;
+        if (kc) __syncthreads();
+        for (int e = tid; e < GEMM_TILE * kw; e += 256) {
+            int a = e & (GEMM_TILE - 1), p = e >> 6;
+            int64_t ra = m0 + a, rb = n0 + a;
+            As[p][a] = ra < F.r ? A[ra + (int64_t)(kc + p) * F.f] : 0.0;
+            Bs[p][a] = rb < F.r ? B[rb + (int64_t)(kc + p) * F.r] : 0.0;
+        }
+        __syncthreads();
+        for (int p = 0; p < kw; ++p) {
+            double a[4], b[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { a[i] = As[p][tx + 16 * i]; b[i] = Bs[p][ty + 16 * i]; }
+            for (int i = 0; i < 4; ++i) { a[i] = As[p][tx + 16 * i]; b[i] = Bs[p][ty + 16 * i]; }
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] -= a[i] * b[j];
+                for (int j = 0; j < 4; ++j) acc[i][j] -= a[i] * b[j];
+        }
     }
     if (!direct) {
 #pragma unroll
@@ -356,21 +391,21 @@ __global__ void k_unpermute(int n, const int* __restrict__ q, const double* __re
 
 // Forward substitution for one level.  task: x = supernode, y = row tile of the update vector.
 // y_s = L11^{-1} (w[cols] + children contributions); upd_s = children contributions - L21 y_s.
-// Every tile recomputes y_s (k <= 32); tile 0 stores it.  Children are gathered one at a time,
-// ascending, so the summation order is fixed.  L11 is staged in shared memory up front so the
-// 32-step substitution never waits on global memory.
+// Every tile recomputes y_s; tile 0 stores it.  Children are gathered one at a time, ascending,
+// so the summation order is fixed.  L11 (k <= KW) is applied 32 columns at a time: the diagonal
+// block is staged in shared memory and solved by one warp with shuffles, then the rest of y_s is
+// updated by the block column below it.
 __global__ void __launch_bounds__(FWD_ROWS) k_fwd(DevCtx cx, const int4* __restrict__ tasks,
                                                   const double* __restrict__ win, double* __restrict__ zout) {
-    __shared__ double Ls[KMAX][KMAX + 1];
-    __shared__ double ys[KMAX];
+    __shared__ double Lg[NB][NB + 1];
+    __shared__ double ys[KW];
     __shared__ double acc[FWD_ROWS];
     int4 tk = tasks[blockIdx.x];
     const int s = tk.x;
     const Front F = load_front(cx, s);
     const int k = F.k, tid = threadIdx.x;
     const int64_t lo = (int64_t)tk.y * FWD_ROWS;            // first update row of this tile
-    for (int e = tid; e < k * k; e += FWD_ROWS) { int i = e % k, j = e / k; Ls[i][j] = F.P[i + (int64_t)j * F.f]; }
-    if (tid < KMAX) ys[tid] = tid < k ? win[F.c0 + tid] : 0.0;
+    if (tid < KW) ys[tid] = tid < k ? win[F.c0 + tid] : 0.0;
     acc[tid] = 0.0;
     __syncthreads();
     for (int ci = cx.child_ptr[s]; ci < cx.child_ptr[s + 1]; ++ci) {
@@ -385,18 +420,29 @@ __global__ void __launch_bounds__(FWD_ROWS) k_fwd(DevCtx cx, const int4* __restr
         }
         __syncthreads();
     }
-    if (tid < 32) {   // unit lower triangular solve with L11, one lane per row
-        double y = tid < k ? ys[tid] : 0.0;
-        for (int j = 0; j < k; ++j) {
-            const double yj = __shfl_sync(0xffffffffu, y, j);
-            if (tid > j && tid < k) y -= Ls[tid][j] * yj;
+    for (int j0 = 0; j0 < k; j0 += NB) {
+        const int w = (k - j0 < NB) ? k - j0 : NB, j1 = j0 + w;
+        for (int e = tid; e < w * NB; e += FWD_ROWS) { int i = e & 31, c = e >> 5; if (i < w) Lg[i][c] = F.P[(j0 + i) + (int64_t)(j0 + c) * F.f]; }
+        __syncthreads();
+        if (tid < 32) {   // unit lower triangular solve with the diagonal block, one lane per row
+            double y = tid < w ? ys[j0 + tid] : 0.0;
+            for (int j = 0; j < w; ++j) {
+                const double yj = __shfl_sync(0xffffffffu, y, j);
+                if (tid > j && tid < w) y -= Lg[tid][j] * yj;
+            }
+            if (tid < w) ys[j0 + tid] = y;
         }
-        if (tid < k) {
-            ys[tid] = y;
-            if (tk.y == 0) zout[F.c0 + tid] = y;
+        __syncthreads();
+        if (j1 + tid < k) {   // rest of the pivot block
+            const double* __restrict__ src = F.P + (j1 + tid) + (int64_t)j0 * F.f;
+            double v = ys[j1 + tid];
+#pragma unroll 8
+            for (int c = 0; c < w; ++c) v -= src[(int64_t)c * F.f] * ys[j0 + c];
+            ys[j1 + tid] = v;
         }
+        __syncthreads();
     }
-    __syncthreads();
+    if (tk.y == 0 && tid < k) zout[F.c0 + tid] = ys[tid];
     const int64_t row = lo + tid;
     if (row < F.r) {
         double v = acc[tid];
@@ -411,11 +457,11 @@ __global__ void __launch_bounds__(FWD_ROWS) k_fwd(DevCtx cx, const int4* __restr
 // supernode, w = slot of its partial sums in cx.bpart.   x[cols] = U11^{-1} (x[cols] - U12 x[rows]).
 // Each CTA reduces BWD_ROWS rows of U12' against the gathered x; with several tiles the partial
 // k-vectors go to scratch and the CTA that arrives last adds them in tile order (fixed summation
-// order, nobody waits) and finishes the 32x32 back substitution.
+// order, nobody waits) and finishes the back substitution, 32 columns at a time.
 __global__ void __launch_bounds__(BWD_ROWS) k_bwd(DevCtx cx, const int4* __restrict__ tasks, double* __restrict__ x) {
-    __shared__ double Us[KMAX][KMAX + 1];
+    __shared__ double Ug[NB][NB + 1];
     __shared__ double xs[BWD_ROWS];
-    __shared__ double part[KMAX];
+    __shared__ double part[KW];
     __shared__ int s_last;
     int4 tk = tasks[blockIdx.x];
     const int s = tk.x, ntiles = tk.z;
@@ -425,7 +471,6 @@ __global__ void __launch_bounds__(BWD_ROWS) k_bwd(DevCtx cx, const int4* __restr
     const int cnt = (int)(F.r - lo < BWD_ROWS ? F.r - lo : BWD_ROWS);
     const int* __restrict__ rows = cx.rows + cx.rows_ptr[s] + lo;
     if (tid < cnt) xs[tid] = x[rows[tid]];
-    for (int e = tid; e < k * k; e += BWD_ROWS) { int i = e % k, j = e / k; Us[i][j] = F.P[i + (int64_t)j * F.f]; }
     __syncthreads();
     for (int i = warp; i < k; i += BWD_ROWS / 32) {
         const double* __restrict__ col = F.T + (int64_t)i * F.r + lo;
@@ -437,8 +482,8 @@ __global__ void __launch_bounds__(BWD_ROWS) k_bwd(DevCtx cx, const int4* __restr
     }
     __syncthreads();
     if (ntiles > 1) {
-        double* slot = cx.bpart + (int64_t)tk.w * KMAX;
-        if (tid < k) slot[(int64_t)tk.y * KMAX + tid] = part[tid];
+        double* slot = cx.bpart + (int64_t)tk.w * KW;
+        if (tid < k) slot[(int64_t)tk.y * KW + tid] = part[tid];
         __threadfence();
         __syncthreads();
         if (tid == 0) {
@@ -450,22 +495,40 @@ __global__ void __launch_bounds__(BWD_ROWS) k_bwd(DevCtx cx, const int4* __restr
         __threadfence();
         if (tid < k) {
             double v = 0.0;
-            for (int t = 0; t < ntiles; ++t) v += __ldcg(slot + (int64_t)t * KMAX + tid);
+            for (int t = 0; t < ntiles; ++t) v += __ldcg(slot + (int64_t)t * KW + tid);
             part[tid] = v;
         }
         __syncthreads();
     }
-    if (tid < 32) {
-        double v = tid < k ? x[F.c0 + tid] - part[tid] : 0.0;
-        for (int j = k - 1; j >= 0; --j) {
-            double xj = 0.0;
-            if (tid == j) xj = v / Us[j][j];
-            xj = __shfl_sync(0xffffffffu, xj, j);
-            if (tid == j) v = xj;
-            if (tid < j) v -= Us[tid][j] * xj;
+    if (tid < k) part[tid] = x[F.c0 + tid] - part[tid];     // right-hand side of U11 x = ...
+    __syncthreads();
+    const int nblk = (k + NB - 1) / NB;
+    for (int g = nblk - 1; g >= 0; --g) {
+        const int j0 = g * NB, w = (k - j0 < NB) ? k - j0 : NB;
+        for (int e = tid; e < w * NB; e += BWD_ROWS) { int i = e & 31, c = e >> 5; if (i < w) Ug[i][c] = F.P[(j0 + i) + (int64_t)(j0 + c) * F.f]; }
+        __syncthreads();
+        if (tid < 32) {
+            double v = tid < w ? part[j0 + tid] : 0.0;
+            for (int j = w - 1; j >= 0; --j) {
+                double xj = 0.0;
+                if (tid == j) xj = v / Ug[j][j];
+                xj = __shfl_sync(0xffffffffu, xj, j);
+                if (tid == j) v = xj;
+                if (tid < j) v -= Ug[tid][j] * xj;
+            }
+            if (tid < w) part[j0 + tid] = v;
         }
-        if (tid < k) x[F.c0 + tid] = v;
+        __syncthreads();
+        if (tid < j0) {   // columns of U above the diagonal block
+            const double* __restrict__ src = F.P + tid + (int64_t)j0 * F.f;
+            double v = part[tid];
+#pragma unroll 8
+            for (int c = 0; c < w; ++c) v -= src[(int64_t)c * F.f] * part[j0 + c];
+            part[tid] = v;
+        }
+        __syncthreads();
     }
+    if (tid < k) x[F.c0 + tid] = part[tid];
 }
 
 constexpr int SMALL_F_MAX = 96;
@@ -474,10 +537,14 @@ constexpr int SMALL_F_MAX = 96;
 
 int front_small_limit() { return SMALL_F_MAX; }
 
-static size_t small_smem(int rmax) { return sizeof(double) * 2 * KMAX * (size_t)(((rmax + 3) & ~3) + 4); }
+static size_t small_smem(int rmax) { return sizeof(double) * 2 * NB * (size_t)(((rmax + 3) & ~3) + 4); }
+
+static size_t panel_smem(int j0) { return sizeof(double) * 2 * (size_t)j0 * (NB + 1); }
 
 cudaError_t kernels_init() {
-    return cudaFuncSetAttribute(k_front_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem(SMALL_F_MAX));
+    cudaError_t e = cudaFuncSetAttribute(k_front_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem(SMALL_F_MAX));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem(KW - NB));
 }
 
 void launch_rowscale(cudaStream_t st, int n, const int64_t* rowptr, const int64_t* rowidx, const double* av, double* Rs) {
@@ -498,10 +565,10 @@ void launch_extend_add(cudaStream_t st, const DevCtx& cx, const int4* tasks, int
 }
 void launch_front_small(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int fmax) {
     if (ntasks <= 0) return;
-    k_front_small<<<ntasks, 128, small_smem(fmax), st>>>(cx, tasks);   // fmax bounds r of the class
+    k_front_small<<<ntasks, PANEL_ROWS, small_smem(fmax), st>>>(cx, tasks);   // fmax bounds r of the class
 }
-void launch_panel(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks) {
-    if (ntasks > 0) k_panel<<<ntasks, PANEL_ROWS, 0, st>>>(cx, tasks);
+void launch_panel(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int g) {
+    if (ntasks > 0) k_panel<<<ntasks, PANEL_ROWS, panel_smem(g * NB), st>>>(cx, tasks);
 }
 void launch_gemm_cb(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks) {
     if (ntasks > 0) k_gemm_cb<<<ntasks, 256, 0, st>>>(cx, tasks);

@@ -16,7 +16,9 @@
 
 namespace smslu {
 
-constexpr int KMAX = 32;          // widest pivot block of a front (symbolic chains wider supernodes)
+constexpr int NB = 32;            // panel block: pivot columns eliminated per panel step
+constexpr int KW = 128;           // widest pivot block of a front (symbolic chains wider supernodes)
+constexpr int KMAX = KW;
 constexpr int PANEL_ROWS = 128;   // rows of L21 / U12' handled by one panel CTA
 constexpr int GEMM_TILE = 64;
 constexpr int FWD_ROWS = 256;
@@ -38,7 +40,7 @@ struct DevCtx {
     double* cb;
     double* upd;        // forward-solve update vectors, sum_r doubles
     double* bpart;      // backward-solve partial sums, KMAX doubles per (supernode, tile)
-    int* counters;      // one per supernode, used by the panel kernel
+    int* counters;      // one per (big front, panel step), used by the panel kernel
     int* counters2;     // one per supernode, used by the backward-solve kernel
     int* flag;          // first bad pivot column (atomicMin), INT_MAX when clean
 };
@@ -50,7 +52,7 @@ void launch_scatter(cudaStream_t st, int64_t nnz, const int64_t* dst, const int*
 void launch_zero_cb(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks);
 void launch_extend_add(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks);
 void launch_front_small(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int fmax);
-void launch_panel(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks);
+void launch_panel(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int g);
 void launch_gemm_cb(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks);
 int front_small_limit();   // largest front the fused shared-memory kernel takes
 cudaError_t kernels_init();

@@ -497,7 +497,7 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
             int tgrp = col2fs[c];
             double kt = c - gfirst[tgrp] + 1, ks = last - gfirst[s] + 1;
             double kn = kt + ks;
-            if (kn > W) break;
+            if (kn > std::min(W, opt.relax_width)) break;
             double stored = kn * (kn + 1) / 2 + kn * rs;
             double frac = 1.0 - (tru[tgrp] + tru[s]) / stored;
             double lim = kn <= opt.relax_k1 ? opt.relax_f1 : (kn <= opt.relax_k2 ? opt.relax_f2 : opt.relax_f3);
@@ -621,7 +621,7 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
         const int s = S.sn_parent[c];
         if (s == -1) continue;
         const int64_t kc = S.sn_start[c + 1] - S.sn_start[c], rc = S.rows_ptr[c + 1] - S.rows_ptr[c];
-        if (kc + rc <= opt.small_front_max) continue;
+        if (kc + rc <= opt.small_front_max && kc <= opt.small_k_max) continue;   // fused small-front kernel
         if (S.child_ptr[s + 1] - S.child_ptr[s] != 1) continue;
         S.direct[c] = 1;
         const int64_t ks = S.sn_start[s + 1] - S.sn_start[s], rs = S.rows_ptr[s + 1] - S.rows_ptr[s];

@@ -19,7 +19,9 @@ struct SymOptions {
     int ordering = ORD_AUTO;
     int grid[3] = {0, 0, 0};      // nx, ny, nz hint for ORD_ND_GRID (idx = i + nx*(j + ny*k))
     int nd_leaf = 48;             // stop dissecting below this many vertices
-    int max_width = 32;           // pivot-block width of a front; wider supernodes are chained
+    int max_width = 128;          // pivot-block width of a front; wider supernodes are chained
+    int relax_width = 32;         // relaxed amalgamation never builds a pivot block wider than this
+    int small_k_max = 32;         // ... and the fused kernel only takes pivot blocks up to this wide
     int relax = 1;                // relaxed supernode amalgamation on/off
     int relax_always = 4;         // merged width <= this: always merge
     int relax_k1 = 16;            // width <= k1: allow zero fraction relax_f1
