@@ -212,26 +212,36 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
                 }
         }
         push(h->fac, L_GEMM, off, 0);
-        // forward solve level
-        off = (int64_t)tasks.size();
-        for (int t = 0; t < cnt; ++t) {
-            int s = sn[t];
-            int nt = (int)std::max<int64_t>(1, (R(s) + FWD_ROWS - 1) / FWD_ROWS);
-            for (int i = 0; i < nt; ++i) tasks.push_back(make_int4(s, i, 0, 0));
+        // forward solve level: narrow (k <= 32) and wide fronts go to separate launches because
+        // the kernel stages the whole pivot block in shared memory (8 KB vs up to 129 KB)
+        for (int cls = 0; cls < 2; ++cls) {
+            off = (int64_t)tasks.size();
+            int kmax = 0;
+            for (int t = 0; t < cnt; ++t) {
+                int s = sn[t];
+                if ((K(s) > NB) != (cls == 1)) continue;
+                kmax = std::max(kmax, K(s));
+                int nt = (int)std::max<int64_t>(1, (R(s) + FWD_ROWS - 1) / FWD_ROWS);
+                for (int i = 0; i < nt; ++i) tasks.push_back(make_int4(s, i, 0, 0));
+            }
+            push(h->fwd, L_FWD, off, kmax);
         }
-        push(h->fwd, L_FWD, off, 0);
     }
     int64_t slots = 0;
-    for (int l = S.nlevels - 1; l >= 0; --l) {
-        int64_t off = (int64_t)tasks.size();
-        for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) {
-            int s = S.level_sn[t];
-            int nt = (int)std::max<int64_t>(1, (R(s) + BWD_ROWS - 1) / BWD_ROWS);
-            for (int i = 0; i < nt; ++i) tasks.push_back(make_int4(s, i, nt, (int)slots));
-            if (nt > 1) slots += nt;
+    for (int l = S.nlevels - 1; l >= 0; --l)
+        for (int cls = 0; cls < 2; ++cls) {
+            int64_t off = (int64_t)tasks.size();
+            int kmax = 0;
+            for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) {
+                int s = S.level_sn[t];
+                if ((K(s) > NB) != (cls == 1)) continue;
+                kmax = std::max(kmax, K(s));
+                int nt = (int)std::max<int64_t>(1, (R(s) + BWD_ROWS - 1) / BWD_ROWS);
+                for (int i = 0; i < nt; ++i) tasks.push_back(make_int4(s, i, nt, (int)slots));
+                if (nt > 1) slots += nt;
+            }
+            push(h->bwd, L_BWD, off, kmax);
         }
-        push(h->bwd, L_BWD, off, 0);
-    }
     h->bpart_slots = slots;
     h->ncounters = ncounters;
 }
@@ -361,8 +371,8 @@ int run_schedule(smslu_handle_t h, const std::vector<Launch>& sched, const doubl
             case L_SMALL: launch_front_small(h->stream, h->cx, tk, L.ntasks, L.fmax); break;
             case L_PANEL: launch_panel(h->stream, h->cx, tk, L.ntasks, L.fmax); break;
             case L_GEMM: launch_gemm_cb(h->stream, h->cx, tk, L.ntasks); break;
-            case L_FWD: launch_fwd(h->stream, h->cx, tk, L.ntasks, win, zx); break;
-            case L_BWD: launch_bwd(h->stream, h->cx, tk, L.ntasks, zx); break;
+            case L_FWD: launch_fwd(h->stream, h->cx, tk, L.ntasks, L.fmax, win, zx); break;
+            case L_BWD: launch_bwd(h->stream, h->cx, tk, L.ntasks, L.fmax, zx); break;
         }
         if ((rc = prof_end(h))) return rc;
     }

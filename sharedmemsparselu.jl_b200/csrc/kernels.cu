@@ -231,13 +231,40 @@ __global__ void __launch_bounds__(PANEL_ROWS) k_panel(DevCtx cx, const int4* __r
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* Uc = coef;                       // Uc[m * (NB+1) + c] = U[m, j0 + c],  m < j0
     double* Lc = coef + j0 * (NB + 1);       // Lc[m * (NB+1) + i] = L[j0 + i, m],  m < j0
-    for (int c = warp; c < w; c += PANEL_ROWS / 32) {
-        const double* __restrict__ pc = F.P + (int64_t)(j0 + c) * F.f;
-        for (int m = lane; m < j0; m += 32) Uc[m * (NB + 1) + c] = pc[m];
-        if (lane < w) D[lane][c] = pc[j0 + lane];
+    // stage D_gg and the two coefficient blocks; loads are issued in batches of 8 per thread so
+    // that their latencies overlap (these CTAs run almost alone on the machine)
+    {
+        const double* __restrict__ Pg = F.P;
+        double t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {   // D_gg: 32 x 32 = 8 per thread
+            const int e = u * PANEL_ROWS + tid, i = e & 31, c = e >> 5;
+            t[u] = (i < w && c < w) ? Pg[(j0 + i) + (int64_t)(j0 + c) * F.f] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int e = u * PANEL_ROWS + tid; D[e & 31][e >> 5] = t[u]; }
+        for (int it = 0; it < 8 * g; it += 8) {   // Lc: j0 x 32 elements, (m, i) -> L[j0+i, m]
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = (it + u) * PANEL_ROWS + tid, i = e & 31, m = e >> 5;
+                t[u] = i < w ? Pg[(j0 + i) + (int64_t)m * F.f] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int e = (it + u) * PANEL_ROWS + tid; Lc[(e >> 5) * (NB + 1) + (e & 31)] = t[u]; }
+        }
+        for (int it = 0; it < 8 * g; it += 8) {   // Uc: 32 columns x j0 rows, (m, c) -> U[m, j0+c]
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = (it + u) * PANEL_ROWS + tid, q = e >> 5, c = q / g, m = (q - c * g) * 32 + (e & 31);
+                t[u] = c < w ? Pg[m + (int64_t)(j0 + c) * F.f] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = (it + u) * PANEL_ROWS + tid, q = e >> 5, c = q / g, m = (q - c * g) * 32 + (e & 31);
+                Uc[m * (NB + 1) + c] = t[u];
+            }
+        }
     }
-    for (int m = warp; m < j0; m += PANEL_ROWS / 32)
-        if (lane < w) Lc[m * (NB + 1) + lane] = F.P[(j0 + lane) + (int64_t)m * F.f];
     __syncthreads();
     if (tid == 0) {   // this CTA's reads of the raw diagonal block are complete
         __threadfence();
@@ -253,13 +280,31 @@ __global__ void __launch_bounds__(PANEL_ROWS) k_panel(DevCtx cx, const int4* __r
     double x[NB];
 #pragma unroll
     for (int c = 0; c < NB; ++c) x[c] = (active && c < w) ? base[(int64_t)(j0 + c) * stride] : 0.0;
-    if (active)
-        for (int m = 0; m < j0; ++m) {
-            const double v = base[(int64_t)m * stride];
-            const double* __restrict__ cm = cf + m * (NB + 1);
+    if (active && j0 > 0) {   // j0 is a multiple of 32; two batches of 16 loads in flight per thread
+        double va[16], vb[16];
 #pragma unroll
-            for (int c = 0; c < NB; ++c) x[c] -= v * cm[c];
+        for (int u = 0; u < 16; ++u) va[u] = base[(int64_t)u * stride];
+        for (int m0 = 0; m0 < j0; m0 += 32) {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) vb[u] = base[(int64_t)(m0 + 16 + u) * stride];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const double* __restrict__ cm = cf + (m0 + u) * (NB + 1);
+#pragma unroll
+                for (int c = 0; c < NB; ++c) x[c] -= va[u] * cm[c];
+            }
+            if (m0 + 32 < j0) {
+#pragma unroll
+                for (int u = 0; u < 16; ++u) va[u] = base[(int64_t)(m0 + 32 + u) * stride];
+            }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const double* __restrict__ cm = cf + (m0 + 16 + u) * (NB + 1);
+#pragma unroll
+                for (int c = 0; c < NB; ++c) x[c] -= vb[u] * cm[c];
+            }
         }
+    }
     // ---- diagonal block: D_gg -= L[g, 0:j0] U[0:j0, g]  (lane = row, warp = 8 columns), then LU
     if (j0 > 0) {
         double acc[8];
@@ -389,96 +434,155 @@ __global__ void k_unpermute(int n, const int* __restrict__ q, const double* __re
     if (i < n) x[q[i]] = w[i];
 }
 
+// Stage the k x k pivot block of a front (top of P, ld f) into shared memory Dk[i + c * ldk],
+// kp = k rounded up to 32; loads are issued 16 per thread at a time so their latencies overlap.
+__device__ __forceinline__ void stage_pivot_block(const Front& F, double* Dk, int ldk, int nthreads) {
+    const int k = F.k, nblk = (k + NB - 1) / NB, total = nblk * NB * k;   // (i in [0,kp), c in [0,k))
+    const int tid = threadIdx.x;
+    for (int e0 = 0; e0 < total; e0 += 16 * nthreads) {
+        double t[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int e = e0 + u * nthreads + tid, q = e >> 5, c = q / nblk, i = (q - c * nblk) * 32 + (e & 31);
+            t[u] = (e < total && i < k) ? F.P[i + (int64_t)c * F.f] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int e = e0 + u * nthreads + tid, q = e >> 5, c = q / nblk, i = (q - c * nblk) * 32 + (e & 31);
+            if (e < total) Dk[i + c * ldk] = t[u];
+        }
+    }
+}
+
 // Forward substitution for one level.  task: x = supernode, y = row tile of the update vector.
 // y_s = L11^{-1} (w[cols] + children contributions); upd_s = children contributions - L21 y_s.
 // Every tile recomputes y_s; tile 0 stores it.  Children are gathered one at a time, ascending,
-// so the summation order is fixed.  L11 (k <= KW) is applied 32 columns at a time: the diagonal
-// block is staged in shared memory and solved by one warp with shuffles, then the rest of y_s is
-// updated by the block column below it.
-__global__ void __launch_bounds__(FWD_ROWS) k_fwd(DevCtx cx, const int4* __restrict__ tasks,
-                                                  const double* __restrict__ win, double* __restrict__ zout) {
-    __shared__ double Lg[NB][NB + 1];
+// so the summation order is fixed.  The whole pivot block is staged in shared memory first; L11 is
+// then applied 32 columns at a time (one warp solves the diagonal block with shuffles, all threads
+// update the rest).  The tile's FWD_ROWS rows of L21 are reduced by 4 threads per row (k/4 columns
+// each, combined in a fixed order).
+// dynamic shared memory: kp * (kp + 1) doubles.
+__global__ void __launch_bounds__(SOLVE_THREADS) k_fwd(DevCtx cx, const int4* __restrict__ tasks,
+                                                       const double* __restrict__ win, double* __restrict__ zout) {
+    extern __shared__ double Dk[];
     __shared__ double ys[KW];
     __shared__ double acc[FWD_ROWS];
+    __shared__ double red[4][FWD_ROWS];
     int4 tk = tasks[blockIdx.x];
     const int s = tk.x;
     const Front F = load_front(cx, s);
-    const int k = F.k, tid = threadIdx.x;
+    const int k = F.k, tid = threadIdx.x, kp = ((k + NB - 1) / NB) * NB, ldk = kp + 1;
     const int64_t lo = (int64_t)tk.y * FWD_ROWS;            // first update row of this tile
+    stage_pivot_block(F, Dk, ldk, SOLVE_THREADS);
     if (tid < KW) ys[tid] = tid < k ? win[F.c0 + tid] : 0.0;
-    acc[tid] = 0.0;
+    if (tid < FWD_ROWS) acc[tid] = 0.0;
     __syncthreads();
     for (int ci = cx.child_ptr[s]; ci < cx.child_ptr[s + 1]; ++ci) {
         const int c = cx.child_idx[ci];
         const int64_t rc = cx.rows_ptr[c + 1] - cx.rows_ptr[c];
         const int* __restrict__ rel = cx.rel + cx.rows_ptr[c];
         const double* __restrict__ uc = cx.upd + cx.rows_ptr[c];
-        for (int64_t a = tid; a < rc; a += FWD_ROWS) {
-            const int64_t ra = rel[a];
-            if (ra < k) ys[ra] += uc[a];
-            else if (ra - k >= lo && ra - k < lo + FWD_ROWS) acc[ra - k - lo] += uc[a];
+        for (int64_t a0 = 0; a0 < rc; a0 += 4 * SOLVE_THREADS) {
+            int64_t ra[4]; double uv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t a = a0 + u * SOLVE_THREADS + tid;
+                ra[u] = a < rc ? rel[a] : -1;
+                uv[u] = a < rc ? uc[a] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (ra[u] < 0) continue;
+                if (ra[u] < k) ys[ra[u]] += uv[u];
+                else if (ra[u] - k >= lo && ra[u] - k < lo + FWD_ROWS) acc[ra[u] - k - lo] += uv[u];
+            }
         }
         __syncthreads();
     }
     for (int j0 = 0; j0 < k; j0 += NB) {
         const int w = (k - j0 < NB) ? k - j0 : NB, j1 = j0 + w;
-        for (int e = tid; e < w * NB; e += FWD_ROWS) { int i = e & 31, c = e >> 5; if (i < w) Lg[i][c] = F.P[(j0 + i) + (int64_t)(j0 + c) * F.f]; }
-        __syncthreads();
         if (tid < 32) {   // unit lower triangular solve with the diagonal block, one lane per row
             double y = tid < w ? ys[j0 + tid] : 0.0;
             for (int j = 0; j < w; ++j) {
                 const double yj = __shfl_sync(0xffffffffu, y, j);
-                if (tid > j && tid < w) y -= Lg[tid][j] * yj;
+                if (tid > j && tid < w) y -= Dk[(j0 + tid) + (j0 + j) * ldk] * yj;
             }
             if (tid < w) ys[j0 + tid] = y;
         }
         __syncthreads();
         if (j1 + tid < k) {   // rest of the pivot block
-            const double* __restrict__ src = F.P + (j1 + tid) + (int64_t)j0 * F.f;
             double v = ys[j1 + tid];
-#pragma unroll 8
-            for (int c = 0; c < w; ++c) v -= src[(int64_t)c * F.f] * ys[j0 + c];
+            for (int c = 0; c < w; ++c) v -= Dk[(j1 + tid) + (j0 + c) * ldk] * ys[j0 + c];
             ys[j1 + tid] = v;
         }
         __syncthreads();
     }
     if (tk.y == 0 && tid < k) zout[F.c0 + tid] = ys[tid];
-    const int64_t row = lo + tid;
-    if (row < F.r) {
-        double v = acc[tid];
-        const double* __restrict__ src = F.P + F.k + row;
-#pragma unroll 8
-        for (int j = 0; j < k; ++j) v -= src[(int64_t)j * F.f] * ys[j];
-        cx.upd[cx.rows_ptr[s] + row] = v;
+    {   // rows of L21: thread (row, quarter) sums kp/4 columns
+        const int rloc = tid & (FWD_ROWS - 1), q = tid / FWD_ROWS, kq = kp / 4;
+        const int64_t row = lo + rloc;
+        double v = 0.0;
+        if (row < F.r) {
+            const double* __restrict__ src = F.P + F.k + row + (int64_t)(q * kq) * F.f;
+            const int jn = (k - q * kq < kq) ? k - q * kq : kq;     // may be <= 0 for the last quarters
+            int j = 0;
+            for (; j + 8 <= jn; j += 8) {
+                double l[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) l[u] = src[(int64_t)(j + u) * F.f];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v += l[u] * ys[q * kq + j + u];
+            }
+            for (; j < jn; ++j) v += src[(int64_t)j * F.f] * ys[q * kq + j];
+        }
+        red[q][rloc] = v;
+        __syncthreads();
+        if (q == 0 && row < F.r)
+            cx.upd[cx.rows_ptr[s] + row] = acc[rloc] - (((red[0][rloc] + red[1][rloc]) + red[2][rloc]) + red[3][rloc]);
     }
 }
 
 // Backward substitution for one level.  task: x = supernode, y = row tile, z = tiles of this
 // supernode, w = slot of its partial sums in cx.bpart.   x[cols] = U11^{-1} (x[cols] - U12 x[rows]).
-// Each CTA reduces BWD_ROWS rows of U12' against the gathered x; with several tiles the partial
-// k-vectors go to scratch and the CTA that arrives last adds them in tile order (fixed summation
-// order, nobody waits) and finishes the back substitution, 32 columns at a time.
-__global__ void __launch_bounds__(BWD_ROWS) k_bwd(DevCtx cx, const int4* __restrict__ tasks, double* __restrict__ x) {
-    __shared__ double Ug[NB][NB + 1];
+// Each CTA reduces BWD_ROWS rows of U12' against the gathered x (a warp takes 4 columns at a time
+// so 32 loads per lane are in flight); with several tiles the partial k-vectors go to scratch and
+// the CTA that arrives last adds them in tile order (fixed summation order, nobody waits) and
+// finishes the back substitution from the pivot block staged in shared memory.
+// dynamic shared memory: kp * (kp + 1) doubles.
+__global__ void __launch_bounds__(SOLVE_THREADS) k_bwd(DevCtx cx, const int4* __restrict__ tasks, double* __restrict__ x) {
+    extern __shared__ double Dk[];
     __shared__ double xs[BWD_ROWS];
     __shared__ double part[KW];
     __shared__ int s_last;
     int4 tk = tasks[blockIdx.x];
     const int s = tk.x, ntiles = tk.z;
     const Front F = load_front(cx, s);
-    const int k = F.k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k = F.k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, kp = ((k + NB - 1) / NB) * NB, ldk = kp + 1;
     const int64_t lo = (int64_t)tk.y * BWD_ROWS;
     const int cnt = (int)(F.r - lo < BWD_ROWS ? F.r - lo : BWD_ROWS);
     const int* __restrict__ rows = cx.rows + cx.rows_ptr[s] + lo;
-    if (tid < cnt) xs[tid] = x[rows[tid]];
+    xs[tid] = tid < cnt ? x[rows[tid]] : 0.0;          // BWD_ROWS == SOLVE_THREADS
+    stage_pivot_block(F, Dk, ldk, SOLVE_THREADS);
     __syncthreads();
-    for (int i = warp; i < k; i += BWD_ROWS / 32) {
-        const double* __restrict__ col = F.T + (int64_t)i * F.r + lo;
-        double v = 0.0;
-        for (int a = lane; a < cnt; a += 32) v += col[a] * xs[a];
+    for (int i0 = warp * 4; i0 < k; i0 += (SOLVE_THREADS / 32) * 4) {
+        double v[4] = {0.0, 0.0, 0.0, 0.0};
+        double t[4][BWD_ROWS / 32];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) part[i] = v;
+        for (int u = 0; u < 4; ++u) {
+            const double* __restrict__ col = F.T + (int64_t)(i0 + u) * F.r + lo;
+#pragma unroll
+            for (int a = 0; a < BWD_ROWS / 32; ++a) t[u][a] = (i0 + u < k && lane + 32 * a < cnt) ? col[lane + 32 * a] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int a = 0; a < BWD_ROWS / 32; ++a) v[u] += t[u][a] * xs[(lane + 32 * a) & (BWD_ROWS - 1)];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[u] += __shfl_xor_sync(0xffffffffu, v[u], o);
+            if (lane == 0 && i0 + u < k) part[i0 + u] = v[u];
+        }
     }
     __syncthreads();
     if (ntiles > 1) {
@@ -502,28 +606,24 @@ __global__ void __launch_bounds__(BWD_ROWS) k_bwd(DevCtx cx, const int4* __restr
     }
     if (tid < k) part[tid] = x[F.c0 + tid] - part[tid];     // right-hand side of U11 x = ...
     __syncthreads();
-    const int nblk = (k + NB - 1) / NB;
+    const int nblk = kp / NB;
     for (int g = nblk - 1; g >= 0; --g) {
         const int j0 = g * NB, w = (k - j0 < NB) ? k - j0 : NB;
-        for (int e = tid; e < w * NB; e += BWD_ROWS) { int i = e & 31, c = e >> 5; if (i < w) Ug[i][c] = F.P[(j0 + i) + (int64_t)(j0 + c) * F.f]; }
-        __syncthreads();
         if (tid < 32) {
             double v = tid < w ? part[j0 + tid] : 0.0;
             for (int j = w - 1; j >= 0; --j) {
                 double xj = 0.0;
-                if (tid == j) xj = v / Ug[j][j];
+                if (tid == j) xj = v / Dk[(j0 + j) + (j0 + j) * ldk];
                 xj = __shfl_sync(0xffffffffu, xj, j);
                 if (tid == j) v = xj;
-                if (tid < j) v -= Ug[tid][j] * xj;
+                if (tid < j) v -= Dk[(j0 + tid) + (j0 + j) * ldk] * xj;
             }
             if (tid < w) part[j0 + tid] = v;
         }
         __syncthreads();
         if (tid < j0) {   // columns of U above the diagonal block
-            const double* __restrict__ src = F.P + tid + (int64_t)j0 * F.f;
             double v = part[tid];
-#pragma unroll 8
-            for (int c = 0; c < w; ++c) v -= src[(int64_t)c * F.f] * part[j0 + c];
+            for (int c = 0; c < w; ++c) v -= Dk[tid + (j0 + c) * ldk] * part[j0 + c];
             part[tid] = v;
         }
         __syncthreads();
@@ -540,11 +640,16 @@ int front_small_limit() { return SMALL_F_MAX; }
 static size_t small_smem(int rmax) { return sizeof(double) * 2 * NB * (size_t)(((rmax + 3) & ~3) + 4); }
 
 static size_t panel_smem(int j0) { return sizeof(double) * 2 * (size_t)j0 * (NB + 1); }
+static size_t solve_smem(int kmax) { size_t kp = (size_t)((kmax + NB - 1) / NB) * NB; return sizeof(double) * kp * (kp + 1); }
 
 cudaError_t kernels_init() {
     cudaError_t e = cudaFuncSetAttribute(k_front_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem(SMALL_F_MAX));
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem(KW - NB));
+    e = cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem(KW - NB));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem(KW));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem(KW));
 }
 
 void launch_rowscale(cudaStream_t st, int n, const int64_t* rowptr, const int64_t* rowidx, const double* av, double* Rs) {
@@ -579,11 +684,11 @@ void launch_permute_scale(cudaStream_t st, int n, const int* p, const double* Rs
 void launch_unpermute(cudaStream_t st, int n, const int* q, const double* w, double* x) {
     k_unpermute<<<(n + 255) / 256, 256, 0, st>>>(n, q, w, x);
 }
-void launch_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const double* win, double* zout) {
-    if (ntasks > 0) k_fwd<<<ntasks, FWD_ROWS, 0, st>>>(cx, tasks, win, zout);
+void launch_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int kmax, const double* win, double* zout) {
+    if (ntasks > 0) k_fwd<<<ntasks, SOLVE_THREADS, solve_smem(kmax), st>>>(cx, tasks, win, zout);
 }
-void launch_bwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, double* x) {
-    if (ntasks > 0) k_bwd<<<ntasks, BWD_ROWS, 0, st>>>(cx, tasks, x);
+void launch_bwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int kmax, double* x) {
+    if (ntasks > 0) k_bwd<<<ntasks, SOLVE_THREADS, solve_smem(kmax), st>>>(cx, tasks, x);
 }
 
 }  // namespace smslu

@@ -21,8 +21,9 @@ constexpr int KW = 128;           // widest pivot block of a front (symbolic cha
 constexpr int KMAX = KW;
 constexpr int PANEL_ROWS = 128;   // rows of L21 / U12' handled by one panel CTA
 constexpr int GEMM_TILE = 64;
-constexpr int FWD_ROWS = 256;
-constexpr int BWD_ROWS = 256;
+constexpr int SOLVE_THREADS = 256;
+constexpr int FWD_ROWS = 64;      // update rows per forward CTA (4 threads per row)
+constexpr int BWD_ROWS = 256;     // rows of U12' per backward CTA
 constexpr int ZERO_TILE = 8192;
 
 struct DevCtx {
@@ -60,7 +61,7 @@ cudaError_t kernels_init();
 // ---- solves
 void launch_permute_scale(cudaStream_t st, int n, const int* p, const double* Rs, const double* b, double* w);
 void launch_unpermute(cudaStream_t st, int n, const int* q, const double* w, double* x);
-void launch_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const double* win, double* zout);
-void launch_bwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, double* x);
+void launch_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int kmax, const double* win, double* zout);
+void launch_bwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int kmax, double* x);
 
 }  // namespace smslu
