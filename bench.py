@@ -121,24 +121,35 @@ def algorithmic_work(F, A):
     k = np.diff(sym["sn_start"]).astype(np.float64)
     r = np.diff(sym["rows_ptr"]).astype(np.float64)
     f = k + r
-    big = f > 96
+    small = (k <= 32) & (f <= 96)          # fronts handled by the shared-memory kernels
+    big = ~small
     n, nnzL = float(A.shape[0]), float(st["nnz_l_exact"])
+    # one solve (nrhs=1) moves 12*(nnz(L)-n) [fwd] + 12*nnz(U) [bwd] + 16n each of vectors;
+    # split between the small- and big-front kernels by their share of the stored panel entries.
+    ent_f = k * (k - 1) / 2 + k * r
+    ent_b = k * (k + 1) / 2 + k * r
+    Bf, Bb = 12.0 * (nnzL - n) + 16.0 * n, 12.0 * nnzL + 16.0 * n
+    sf, sb = float(ent_f[small].sum() / ent_f.sum()), float(ent_b[small].sum() / ent_b.sum())
+    lu_small = float(np.sum(k[small] * f[small] + k[small] * r[small]))
+    a_small = float(A.nnz) * lu_small / float(np.sum(k * f + k * r))   # approximate split of nnz(A)
     work = {
         # FP64 flops of the Schur update of the big fronts: C(r x r) -= L21(r x k) U12(k x r)
         "gemm_cb": {"flops": float(np.sum(2.0 * k[big] * r[big] * r[big])),
                     "bytes": float(np.sum(8.0 * (2 * r[big] * r[big] + 2 * r[big] * k[big])))},
-        # fused small fronts: read+write panels and CB once, partial LU flops
-        "front_small": {"flops": float(np.sum((2.0 / 3) * k[~big] ** 3 + 2 * k[~big] ** 2 * r[~big] + 2 * k[~big] * r[~big] ** 2)),
-                        "bytes": float(np.sum(16.0 * (k[~big] * f[~big] + k[~big] * r[~big] + r[~big] ** 2)))},
-        "panel": {"flops": float(np.sum(2.0 * k[big] ** 2 * r[big])),
-                  "bytes": float(np.sum(16.0 * (2 * r[big] * k[big])))},
-        # extend-add: read every child CB once, read-modify-write the parent entries
+        # small fronts: pull A entries (20 B each) and the children's blocks, write panels and CB once
+        "front_small": {"flops": float(np.sum((2.0 / 3) * k[small] ** 3 + 2 * k[small] ** 2 * r[small] + 2 * k[small] * r[small] ** 2)),
+                        "bytes": 8.0 * lu_small + 20.0 * a_small + float(np.sum(16.0 * r[small] ** 2))},
+        "panel": {"flops": float(np.sum((2.0 / 3) * k[big] ** 3 + 2.0 * k[big] ** 2 * r[big])),
+                  "bytes": float(np.sum(16.0 * (k[big] * f[big] + r[big] * k[big])))},
+        # extend-add into big parents: read every child CB once, read-modify-write the parent entries
         "extend_add": {"flops": float(np.sum(r * r)), "bytes": float(np.sum(24.0 * r * r))},
-        "zero_cb": {"flops": 0.0, "bytes": float(np.sum(8.0 * r * r))},
-        "scatter": {"flops": float(A.nnz), "bytes": 8.0 * st["lu_pool_doubles"] + 28.0 * A.nnz},
-        # one solve, nrhs = 1: 12*(nnz(L)-n+nnz(U)) + 8n*(2+1) + 8n   (SURVEY 8d), split evenly
-        "fwd": {"flops": 2.0 * (nnzL - n), "bytes": 12.0 * (nnzL - n) + 16.0 * n},
-        "bwd": {"flops": 2.0 * nnzL, "bytes": 12.0 * nnzL + 16.0 * n},
+        "zero_cb": {"flops": 0.0, "bytes": float(np.sum(8.0 * r[big] * r[big]))},
+        "scatter": {"flops": float(A.nnz) - a_small,
+                    "bytes": 8.0 * float(np.sum(k[big] * f[big] + k[big] * r[big])) + 28.0 * (float(A.nnz) - a_small)},
+        "fwd": {"flops": 2.0 * (nnzL - n) * (1 - sf), "bytes": Bf * (1 - sf)},
+        "bwd": {"flops": 2.0 * nnzL * (1 - sb), "bytes": Bb * (1 - sb)},
+        "fwd_small": {"flops": 2.0 * (nnzL - n) * sf, "bytes": Bf * sf},
+        "bwd_small": {"flops": 2.0 * nnzL * sb, "bytes": Bb * sb},
     }
     return work, st
 
@@ -344,8 +355,8 @@ def run_ours(args, rank, world, local_rank):
                 "frac": ach / hbm_gbs, "traffic": None, "peak_source": peak_src}
     roof["kernel_ms_per_step"] = ms_kernel[dom]
     roof["share_of_step"] = ms_kernel[dom] / step_ms_prof
-    solve_ms = ms_kernel.get("fwd", 0) + ms_kernel.get("bwd", 0) + ms_kernel.get("permute_scale", 0) + ms_kernel.get("unpermute", 0)
-    solve_bytes = work["fwd"]["bytes"] + work["bwd"]["bytes"]
+    solve_ms = sum(ms_kernel.get(kk, 0) for kk in ("fwd", "bwd", "fwd_small", "bwd_small", "permute_scale", "unpermute"))
+    solve_bytes = sum(work[kk]["bytes"] for kk in ("fwd", "bwd", "fwd_small", "bwd_small"))
     refac_ms = step_ms_prof - solve_ms
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wu,

@@ -79,16 +79,18 @@ typedef struct smslu_stats {
 
 /* kernel kinds for ms_kernel / launches_kernel */
 #define SMSLU_K_ROWSCALE 0
-#define SMSLU_K_SCATTER 1    /* memset of the factor storage + scatter of A */
+#define SMSLU_K_SCATTER 1    /* zero-fill of the big fronts' panels + scatter of their entries of A */
 #define SMSLU_K_ZERO 2
 #define SMSLU_K_EXTEND 3
-#define SMSLU_K_SMALL 4
+#define SMSLU_K_SMALL 4      /* fronts assembled, factored and stored from shared memory */
 #define SMSLU_K_PANEL 5
 #define SMSLU_K_GEMM 6
 #define SMSLU_K_PERMUTE 7
 #define SMSLU_K_FWD 8
 #define SMSLU_K_BWD 9
 #define SMSLU_K_UNPERMUTE 10
+#define SMSLU_K_FWD_SMALL 11 /* warp-per-front solve kernels of the shared-memory-sized fronts */
+#define SMSLU_K_BWD_SMALL 12
 
 /* Fill *opts with defaults.  */
 int smslu_options_default(smslu_options_t* opts);

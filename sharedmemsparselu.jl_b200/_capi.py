@@ -21,7 +21,7 @@ EXPORTS = [
     "smslu_solve_async", "smslu_sync", "smslu_set_stream", "smslu_set_profile",
 ]
 KERNEL_KINDS = ["rowscale", "scatter", "zero_cb", "extend_add", "front_small", "panel", "gemm_cb",
-                "permute_scale", "fwd", "bwd", "unpermute"]
+                "permute_scale", "fwd", "bwd", "unpermute", "fwd_small", "bwd_small"]
 
 
 class Options(C.Structure):

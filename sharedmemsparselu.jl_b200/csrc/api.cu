@@ -19,7 +19,8 @@ using namespace smslu;
 namespace {
 
 enum LaunchKind { L_ZERO = SMSLU_K_ZERO, L_EXTEND = SMSLU_K_EXTEND, L_SMALL = SMSLU_K_SMALL, L_PANEL = SMSLU_K_PANEL,
-                  L_GEMM = SMSLU_K_GEMM, L_FWD = SMSLU_K_FWD, L_BWD = SMSLU_K_BWD };
+                  L_GEMM = SMSLU_K_GEMM, L_FWD = SMSLU_K_FWD, L_BWD = SMSLU_K_BWD,
+                  L_FWD_SMALL = SMSLU_K_FWD_SMALL, L_BWD_SMALL = SMSLU_K_BWD_SMALL };
 
 struct Launch {
     int kind;
@@ -51,8 +52,10 @@ struct smslu_handle_s {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     std::vector<void*> dev_allocs;
     DevCtx cx{};
-    int64_t* d_a_dst = nullptr;
-    int* d_a_row = nullptr;
+    int64_t* d_big_dst = nullptr;        // entries of A that land in big fronts: offset into lu,
+    const int *d_big_row = nullptr, *d_big_src = nullptr;   // original row, index into nzval
+    int64_t nnz_big = 0;
+    const double* cur_av = nullptr;      // device nzval of the refactorization being enqueued
     int64_t *d_rowptr = nullptr, *d_rowidx = nullptr;
     int *d_p = nullptr, *d_q = nullptr;
     double *d_Rs = nullptr, *d_aval = nullptr, *d_w = nullptr, *d_z = nullptr, *d_xb = nullptr;
@@ -142,7 +145,7 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
             int s = sn[t];
             maxch = std::max(maxch, NC(s));
             const bool fed_directly = NC(s) == 1 && S.direct[S.child_idx[S.child_ptr[s]]];
-            if (NC(s) > 0 && R(s) > 0 && !fed_directly) zero_tasks(s);
+            if (NC(s) > 0 && R(s) > 0 && !fed_directly && !SMALL(s)) zero_tasks(s);
             if (S.direct[s] && !S.cb_assigned[S.sn_parent[s]] && R(S.sn_parent[s]) > 0) zero_tasks(S.sn_parent[s]);
         }
         push(h->fac, L_ZERO, off, 0);
@@ -151,7 +154,7 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
             off = (int64_t)tasks.size();
             for (int t = 0; t < cnt; ++t) {
                 int s = sn[t];
-                if (NC(s) <= slot) continue;
+                if (NC(s) <= slot || SMALL(s)) continue;          // small parents pull their children
                 int c = S.child_idx[S.child_ptr[s] + slot];
                 int64_t rc = R(c);
                 if (rc == 0 || S.direct[c]) continue;
@@ -169,7 +172,7 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
             for (int t = 0; t < cnt; ++t) {
                 int s = sn[t];
                 int64_t f = K(s) + R(s);
-                if (SMALL(s) && f > lo && f <= classes[ci]) tasks.push_back(make_int4(s, NC(s) > 0 ? 1 : 0, 0, 0));
+                if (SMALL(s) && f > lo && f <= classes[ci]) tasks.push_back(make_int4(s, 0, 0, 0));
             }
             push(h->fac, L_SMALL, off, classes[ci]);
             lo = classes[ci];
@@ -214,12 +217,15 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
         push(h->fac, L_GEMM, off, 0);
         // forward solve level: narrow (k <= 32) and wide fronts go to separate launches because
         // the kernel stages the whole pivot block in shared memory (8 KB vs up to 129 KB)
+        off = (int64_t)tasks.size();
+        for (int t = 0; t < cnt; ++t) if (SMALL(sn[t])) tasks.push_back(make_int4(sn[t], 0, 0, 0));
+        push(h->fwd, L_FWD_SMALL, off, 0);
         for (int cls = 0; cls < 2; ++cls) {
             off = (int64_t)tasks.size();
             int kmax = 0;
             for (int t = 0; t < cnt; ++t) {
                 int s = sn[t];
-                if ((K(s) > NB) != (cls == 1)) continue;
+                if (SMALL(s) || (K(s) > NB) != (cls == 1)) continue;
                 kmax = std::max(kmax, K(s));
                 int nt = (int)std::max<int64_t>(1, (R(s) + FWD_ROWS - 1) / FWD_ROWS);
                 for (int i = 0; i < nt; ++i) tasks.push_back(make_int4(s, i, 0, 0));
@@ -228,13 +234,17 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
         }
     }
     int64_t slots = 0;
-    for (int l = S.nlevels - 1; l >= 0; --l)
+    for (int l = S.nlevels - 1; l >= 0; --l) {
+        int64_t off0 = (int64_t)tasks.size();
+        for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t)
+            if (SMALL(S.level_sn[t])) tasks.push_back(make_int4(S.level_sn[t], 0, 0, 0));
+        push(h->bwd, L_BWD_SMALL, off0, 0);
         for (int cls = 0; cls < 2; ++cls) {
             int64_t off = (int64_t)tasks.size();
             int kmax = 0;
             for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) {
                 int s = S.level_sn[t];
-                if ((K(s) > NB) != (cls == 1)) continue;
+                if (SMALL(s) || (K(s) > NB) != (cls == 1)) continue;
                 kmax = std::max(kmax, K(s));
                 int nt = (int)std::max<int64_t>(1, (R(s) + BWD_ROWS - 1) / BWD_ROWS);
                 for (int i = 0; i < nt; ++i) tasks.push_back(make_int4(s, i, nt, (int)slots));
@@ -242,6 +252,7 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
             }
             push(h->bwd, L_BWD, off, kmax);
         }
+    }
     h->bpart_slots = slots;
     h->ncounters = ncounters;
 }
@@ -281,27 +292,57 @@ int ensure_uploaded(smslu_handle_t h) {
     if ((rc = dev_upload(h, &d_sn_parent, S.sn_parent))) return rc;
     if ((rc = dev_upload(h, &d_child_ptr, S.child_ptr))) return rc;
     if ((rc = dev_upload(h, &d_child_idx, S.child_idx))) return rc;
-    if ((rc = dev_upload(h, &h->d_a_dst, S.a_dst))) return rc;
     if ((rc = dev_upload(h, &h->d_p, S.p))) return rc;
     if ((rc = dev_upload(h, &h->d_q, S.q))) return rc;
     {   // row index of every nonzero (for the scaling) and a row-major view of the pattern
-        std::vector<int> arow(h->annz);
         std::vector<int64_t> rowptr(n + 1, 0), rowidx(h->annz);
-        for (int64_t t = 0; t < h->annz; ++t) { arow[t] = (int)h->Ai[t]; ++rowptr[h->Ai[t] + 1]; }
+        for (int64_t t = 0; t < h->annz; ++t) ++rowptr[h->Ai[t] + 1];
         for (int i = 0; i < n; ++i) rowptr[i + 1] += rowptr[i];
         std::vector<int64_t> w(rowptr.begin(), rowptr.end() - 1);
         for (int c = 0; c < n; ++c)
             for (int64_t t = h->Ap[c]; t < h->Ap[c + 1]; ++t) rowidx[w[h->Ai[t]]++] = t;
-        if ((rc = dev_upload(h, &h->d_a_row, arow))) return rc;
         if ((rc = dev_upload(h, &h->d_rowptr, rowptr))) return rc;
         if ((rc = dev_upload(h, &h->d_rowidx, rowidx))) return rc;
     }
-    double *d_lu, *d_cb, *d_upd;
+    int *d_a_ptr, *d_a_src, *d_a_row, *d_a_pos;
+    {   // entries of A grouped by the small front that pulls them; the big fronts' entries follow
+        const int nsn = S.nsn;
+        if (h->annz > INT_MAX) return fail(h, SMSLU_E_ARG, "more than 2^31-1 nonzeros");
+        auto small = [&](int s) {
+            const int64_t k = S.sn_start[s + 1] - S.sn_start[s], r = S.rows_ptr[s + 1] - S.rows_ptr[s];
+            return k <= NB && k + r <= front_small_limit();
+        };
+        std::vector<int> a_ptr(nsn + 1, 0);
+        for (int64_t t = 0; t < h->annz; ++t) if (small(S.a_sn[t])) ++a_ptr[S.a_sn[t] + 1];
+        for (int s = 0; s < nsn; ++s) a_ptr[s + 1] += a_ptr[s];
+        const int nsmall = a_ptr[nsn];
+        std::vector<int> a_src(h->annz), a_row(h->annz), a_pos(nsmall), w(a_ptr.begin(), a_ptr.end() - 1);
+        std::vector<int64_t> dst_big(h->annz - nsmall);
+        int64_t nb = 0;
+        for (int64_t t = 0; t < h->annz; ++t) {
+            const int s = S.a_sn[t];
+            int64_t o;
+            if (small(s)) { o = w[s]++; a_pos[o] = S.a_loc[t]; }
+            else { o = nsmall + nb; dst_big[nb++] = S.a_dst[t]; }
+            a_src[o] = (int)t;
+            a_row[o] = (int)h->Ai[t];
+        }
+        if ((rc = dev_upload(h, &d_a_ptr, a_ptr))) return rc;
+        if ((rc = dev_upload(h, &d_a_src, a_src))) return rc;
+        if ((rc = dev_upload(h, &d_a_row, a_row))) return rc;
+        if ((rc = dev_upload(h, &d_a_pos, a_pos))) return rc;
+        if ((rc = dev_upload(h, &h->d_big_dst, dst_big))) return rc;
+        h->d_big_src = d_a_src + nsmall;
+        h->d_big_row = d_a_row + nsmall;
+        h->nnz_big = nb;
+    }
+    double *d_lu, *d_cb, *d_upd, *d_dinv;
     int *d_counters, *d_flag;
     if ((rc = dev_alloc(h, &d_lu, (size_t)S.lu_size))) return rc;
     if ((rc = dev_alloc(h, &d_cb, (size_t)S.cb_size))) return rc;
     if ((rc = dev_alloc(h, &d_upd, (size_t)S.sum_r))) return rc;
     if ((rc = dev_alloc(h, &d_flag, 1))) return rc;
+    if ((rc = dev_alloc(h, &d_dinv, (size_t)n))) return rc;
     if ((rc = dev_alloc(h, &h->d_Rs, (size_t)n))) return rc;
     if ((rc = dev_alloc(h, &h->d_aval, (size_t)h->annz))) return rc;
     if ((rc = dev_alloc(h, &h->d_w, (size_t)n))) return rc;
@@ -324,7 +365,8 @@ int ensure_uploaded(smslu_handle_t h) {
     cx.Loff = d_Loff; cx.Uoff = d_Uoff; cx.CBoff = d_CBoff; cx.sn_parent = d_sn_parent;
     cx.child_ptr = d_child_ptr; cx.child_idx = d_child_idx;
     cx.lu = d_lu; cx.cb = d_cb; cx.upd = d_upd; cx.counters = d_counters; cx.flag = d_flag;
-    cx.bpart = d_bpart; cx.counters2 = d_counters2;
+    cx.bpart = d_bpart; cx.counters2 = d_counters2; cx.dinv = d_dinv;
+    cx.a_ptr = d_a_ptr; cx.a_src = d_a_src; cx.a_row = d_a_row; cx.a_pos = d_a_pos;
     CU(cudaDeviceSynchronize());
     h->uploaded = true;
     h->st.ms_upload = now_ms() - t0;
@@ -368,7 +410,9 @@ int run_schedule(smslu_handle_t h, const std::vector<Launch>& sched, const doubl
         switch (L.kind) {
             case L_ZERO: launch_zero_cb(h->stream, h->cx, tk, L.ntasks); break;
             case L_EXTEND: launch_extend_add(h->stream, h->cx, tk, L.ntasks); break;
-            case L_SMALL: launch_front_small(h->stream, h->cx, tk, L.ntasks, L.fmax); break;
+            case L_SMALL: launch_front_small(h->stream, h->cx, tk, L.ntasks, L.fmax, h->cur_av, h->d_Rs); break;
+            case L_FWD_SMALL: launch_small_fwd(h->stream, h->cx, tk, L.ntasks, win, zx); break;
+            case L_BWD_SMALL: launch_small_bwd(h->stream, h->cx, tk, L.ntasks, zx); break;
             case L_PANEL: launch_panel(h->stream, h->cx, tk, L.ntasks, L.fmax); break;
             case L_GEMM: launch_gemm_cb(h->stream, h->cx, tk, L.ntasks); break;
             case L_FWD: launch_fwd(h->stream, h->cx, tk, L.ntasks, L.fmax, win, zx); break;
@@ -392,8 +436,9 @@ int enqueue_refactor(smslu_handle_t h, const double* av, bool rs_given) {
     if ((rc = prof_begin(h, SMSLU_K_SCATTER))) return rc;
     CU(cudaMemsetAsync(h->cx.flag, 0x7f, sizeof(int), h->stream));   // 0x7f7f7f7f = clean
     CU(cudaMemsetAsync(h->cx.counters, 0, sizeof(int) * std::max<int64_t>(h->ncounters, 1), h->stream));
-    CU(cudaMemsetAsync(h->cx.lu, 0, sizeof(double) * S.lu_size, h->stream));
-    launch_scatter(h->stream, h->annz, h->d_a_dst, h->d_a_row, h->d_Rs, av, h->cx.lu);
+    if (S.lu_big_size > 0) CU(cudaMemsetAsync(h->cx.lu, 0, sizeof(double) * S.lu_big_size, h->stream));
+    launch_scatter(h->stream, h->nnz_big, h->d_big_dst, h->d_big_row, h->d_big_src, h->d_Rs, av, h->cx.lu);
+    h->cur_av = av;
     if ((rc = prof_end(h))) return rc;
     if ((rc = run_schedule(h, h->fac, nullptr, nullptr))) return rc;
     CU(cudaMemcpyAsync(h->h_flag, h->cx.flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));

@@ -29,6 +29,9 @@ __device__ __forceinline__ Front load_front(const DevCtx& cx, int s) {
 
 __device__ __forceinline__ bool bad_pivot(double p) { return !(fabs(p) > 0.0) || !isfinite(p); }
 
+constexpr int SMALL_F_MAX = 96;   // largest front handled by the shared-memory kernels (with k <= NB)
+__host__ __device__ constexpr int small_group_doubles(int fmax) { return fmax * (fmax | 1) + NB; }
+
 // ------------------------------------------------------------------ row scaling (UMFPACK "SUM")
 __global__ void k_rowscale(int n, const int64_t* __restrict__ rowptr, const int64_t* __restrict__ rowidx,
                            const double* __restrict__ av, double* __restrict__ Rs) {
@@ -40,11 +43,13 @@ __global__ void k_rowscale(int n, const int64_t* __restrict__ rowptr, const int6
 }
 
 // ------------------------------------------------------------------ A -> panels
+// (entries of the big fronts only; the small fronts pull theirs inside k_small_factor)
 __global__ void k_scatter(int64_t nnz, const int64_t* __restrict__ dst, const int* __restrict__ arow,
-                          const double* __restrict__ Rs, const double* __restrict__ av, double* __restrict__ lu) {
+                          const int* __restrict__ asrc, const double* __restrict__ Rs,
+                          const double* __restrict__ av, double* __restrict__ lu) {
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nnz; t += stride)
-        lu[dst[t]] = Rs[arow[t]] * av[t];
+        lu[dst[t]] = Rs[arow[t]] * av[asrc[t]];
 }
 
 // ------------------------------------------------------------------ zero contribution blocks
@@ -139,71 +144,97 @@ __device__ __forceinline__ void trsm_row_lower_t(double (&x)[NB], const double (
 }
 
 // ------------------------------------------------------------------ fused small front
-// One CTA does a whole front with k <= 32 and f <= SMALL_F_MAX: stage the pivot block, L21 and
-// U12' in shared memory, factor the pivot block (block_lu), solve the rows of both panels, then
-// form the contribution block C = beta*C - L21 U12 from shared memory (4x4 micro-tiles).
-// task: x = supernode, y = beta (the block holds assembled child contributions).
-// dynamic shared memory: 2 * NB * rp doubles, rp = r rounded up to 4 (+4 padding).
-__global__ void __launch_bounds__(PANEL_ROWS) k_front_small(DevCtx cx, const int4* __restrict__ tasks) {
+// A front with k <= 32 pivots and f <= SMALL_F_MAX rows is assembled, factored and stored by one
+// group of RW*CH threads entirely in shared memory ("pull" assembly):
+//   Fs (f x f, column-major, odd leading dimension) = 0
+//   Fs += the entries of Rs .* A that land in this front      (per-front lists a_ptr/a_src/a_row/a_pos)
+//   Fs += contribution blocks of the children, child by child in ascending order (rel maps)
+//   right-looking elimination of the k pivots, one barrier per pivot: thread (i, h) owns row i and
+//   the columns c = j+1+h (mod CH); multipliers are formed as a_ij * (1/u_jj) on the fly and
+//   column j is left unscaled until the final copy-out, so no thread ever reads what another
+//   thread writes inside a step.  1/u_jj is produced by the thread that finishes u_jj.
+//   copy-out: P (f x k), T = U12' (r x k), C (r x r), dinv (reciprocal pivots for the solves).
+// Factor storage is written exactly once and never read here; nothing has to be zero-filled.
+// RW = row slots (>= f), CH = column interleave, FPC = fronts per CTA (FPC > 1 only with one warp
+// per front, where the barriers are __syncwarp).
+// task: x = supernode.
+template <int RW, int CH, int FPC>
+__global__ void __launch_bounds__(RW * CH * FPC) k_small_factor(DevCtx cx, const int4* __restrict__ tasks, int ntasks,
+                                                                 int fmax, const double* __restrict__ av,
+                                                                 const double* __restrict__ Rs) {
     extern __shared__ double sm[];
-    __shared__ double D[NB][NB + 1];
-    __shared__ double rd[NB];
-    int4 tk = tasks[blockIdx.x];
-    const Front F = load_front(cx, tk.x);
-    const int k = F.k, r = (int)F.r, f = (int)F.f;
-    const int rp = ((r + 3) & ~3) + 4;
-    double* Ls = sm;                // Ls[c * rp + a] = L21[a][c]
-    double* Ts = sm + NB * rp;      // Ts[c * rp + b] = U12[c][b]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int c = warp; c < k; c += PANEL_ROWS / 32) {
-        const double* __restrict__ pc = F.P + (int64_t)c * f;
-        const double* __restrict__ pt = F.T + (int64_t)c * r;
-        if (lane < k) D[lane][c] = pc[lane];
-        for (int a = lane; a < r; a += 32) { Ls[c * rp + a] = pc[k + a]; Ts[c * rp + a] = pt[a]; }
+    constexpr int NT = RW * CH;
+    static_assert(NT % 32 == 0 && (FPC == 1 || NT == 32), "group layout");
+    const int grp = threadIdx.x / NT, tid = threadIdx.x % NT, lane = tid & 31, wrp = tid >> 5;
+    const int ti = blockIdx.x * FPC + grp;
+    if (ti >= ntasks) return;                                 // FPC > 1: a whole warp leaves
+    auto sync = [&]() { if (NT == 32) __syncwarp(); else __syncthreads(); };
+    const int s = tasks[ti].x;
+    const Front F = load_front(cx, s);
+    const int k = F.k, r = (int)F.r, f = (int)F.f, ld = f | 1;
+    double* Fs = sm + (size_t)grp * (small_group_doubles(fmax));
+    double* rd = Fs + (size_t)fmax * (fmax | 1);
+    for (int e = tid; e < f * ld; e += NT) Fs[e] = 0.0;
+    sync();
+    for (int e = cx.a_ptr[s] + tid; e < cx.a_ptr[s + 1]; e += NT) {
+        const int pos = cx.a_pos[e];
+        Fs[(pos & 0xffff) + (pos >> 16) * ld] = Rs[cx.a_row[e]] * av[cx.a_src[e]];
     }
-    __syncthreads();
-    block_lu(D, rd, k, F.c0, cx.flag);
-    for (int e = tid; e < k * NB; e += PANEL_ROWS) { int i = e & 31, c = e >> 5; if (i < k) F.P[i + (int64_t)c * f] = D[i][c]; }
-    for (int t = tid; t < 2 * r; t += PANEL_ROWS) {   // row solves: the r rows of L21, then of U12'
-        double x[NB];
-        const bool lower = t < r;
-        const int a = lower ? t : t - r;
-        double* row = (lower ? Ls : Ts) + a;
-#pragma unroll
-        for (int c = 0; c < NB; ++c) x[c] = c < k ? row[c * rp] : 0.0;
-        if (lower) trsm_row_upper(x, D, rd, k); else trsm_row_lower_t(x, D, k);
-        double* g = lower ? F.P + k + a : F.T + a;
-        const int64_t ldg = lower ? f : r;
-#pragma unroll
-        for (int c = 0; c < NB; ++c) if (c < k) { row[c * rp] = x[c]; g[(int64_t)c * ldg] = x[c]; }
-    }
-    __syncthreads();
-    const int nt4 = (r + 3) >> 2;
-    for (int t = tid; t < nt4 * nt4; t += PANEL_ROWS) {
-        const int a0 = (t % nt4) * 4, b0 = (t / nt4) * 4;
-        double acc[4][4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                acc[i][j] = (tk.y && a0 + i < r && b0 + j < r) ? F.C[(a0 + i) + (int64_t)(b0 + j) * r] : 0.0;
-        for (int c = 0; c < k; ++c) {
-            const double2 l01 = *reinterpret_cast<const double2*>(Ls + c * rp + a0);
-            const double2 l23 = *reinterpret_cast<const double2*>(Ls + c * rp + a0 + 2);
-            const double2 u01 = *reinterpret_cast<const double2*>(Ts + c * rp + b0);
-            const double2 u23 = *reinterpret_cast<const double2*>(Ts + c * rp + b0 + 2);
-            const double l[4] = {l01.x, l01.y, l23.x, l23.y}, u[4] = {u01.x, u01.y, u23.x, u23.y};
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[i][j] -= l[i] * u[j];
+    sync();
+    for (int ci = cx.child_ptr[s]; ci < cx.child_ptr[s + 1]; ++ci) {
+        const int c = cx.child_idx[ci];
+        const int rc = (int)(cx.rows_ptr[c + 1] - cx.rows_ptr[c]);
+        const int* __restrict__ rel = cx.rel + cx.rows_ptr[c];
+        const double* __restrict__ Cc = cx.cb + cx.CBoff[c];
+        for (int b = wrp; b < rc; b += NT / 32) {
+            const int pb = rel[b] * ld;
+            for (int a = lane; a < rc; a += 32) Fs[rel[a] + pb] += Cc[a + (int64_t)b * rc];
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (a0 + i < r && b0 + j < r) F.C[(a0 + i) + (int64_t)(b0 + j) * r] = acc[i][j];
+        sync();
     }
+    if (tid == 0) {
+        const double piv = Fs[0];
+        if (bad_pivot(piv)) atomicMin(cx.flag, F.c0);
+        rd[0] = 1.0 / piv;
+    }
+    sync();
+    {
+        const int i = tid % RW, h = tid / RW;
+        double* row = Fs + i;
+        for (int j = 0; j < k; ++j) {
+            if (i > j && i < f) {
+                const double l = row[j * ld] * rd[j];
+                const double* uj = Fs + j;
+                int c = j + 1 + h;
+                if (h == 0) {                                 // column j+1 holds the next pivot
+                    const double v = row[c * ld] - l * uj[c * ld];
+                    row[c * ld] = v;
+                    if (i == c && c < k) {
+                        if (bad_pivot(v)) atomicMin(cx.flag, F.c0 + c);
+                        rd[c] = 1.0 / v;
+                    }
+                    c += CH;
+                }
+#pragma unroll 4
+                for (; c < f; c += CH) row[c * ld] -= l * uj[c * ld];
+            }
+            sync();
+        }
+    }
+    for (int c = wrp; c < k; c += NT / 32) {                  // P: pivot block on top of L21
+        const double rc = rd[c];
+        double* __restrict__ dst = F.P + (int64_t)c * f;
+        for (int i = lane; i < f; i += 32) { const double v = Fs[i + c * ld]; dst[i] = i > c ? v * rc : v; }
+    }
+    for (int c = wrp; c < k; c += NT / 32) {                  // T = U12 transposed
+        double* __restrict__ dst = F.T + (int64_t)c * r;
+        for (int b = lane; b < r; b += 32) dst[b] = Fs[c + (k + b) * ld];
+    }
+    for (int b = wrp; b < r; b += NT / 32) {                  // contribution block for the parent
+        double* __restrict__ dst = F.C + (int64_t)b * r;
+        for (int a = lane; a < r; a += 32) dst[a] = Fs[(k + a) + (k + b) * ld];
+    }
+    if (tid < k) cx.dinv[F.c0 + tid] = rd[tid];
 }
 
 // ------------------------------------------------------------------ panel step of a big front
@@ -323,8 +354,10 @@ __global__ void __launch_bounds__(PANEL_ROWS) k_panel(DevCtx cx, const int4* __r
     }
     __syncthreads();
     block_lu(D, rd, w, F.c0 + j0, cx.flag);
-    if (s_last)
+    if (s_last) {
         for (int e = tid; e < w * NB; e += PANEL_ROWS) { int i = e & 31, c = e >> 5; if (i < w) F.P[(j0 + i) + (int64_t)(j0 + c) * F.f] = D[i][c]; }
+        if (tid < w) cx.dinv[F.c0 + j0 + tid] = rd[tid];
+    }
     if (!active) return;
     if (kind == 0) trsm_row_upper(x, D, rd, w); else trsm_row_lower_t(x, D, w);
 #pragma unroll
@@ -611,9 +644,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_bwd(DevCtx cx, const int4* __
         const int j0 = g * NB, w = (k - j0 < NB) ? k - j0 : NB;
         if (tid < 32) {
             double v = tid < w ? part[j0 + tid] : 0.0;
+            const double d = tid < w ? cx.dinv[F.c0 + j0 + tid] : 0.0;
             for (int j = w - 1; j >= 0; --j) {
                 double xj = 0.0;
-                if (tid == j) xj = v / Dk[(j0 + j) + (j0 + j) * ldk];
+                if (tid == j) xj = v * d;
                 xj = __shfl_sync(0xffffffffu, xj, j);
                 if (tid == j) v = xj;
                 if (tid < j) v -= Dk[(j0 + tid) + (j0 + j) * ldk] * xj;
@@ -631,19 +665,97 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_bwd(DevCtx cx, const int4* __
     if (tid < k) x[F.c0 + tid] = part[tid];
 }
 
-constexpr int SMALL_F_MAX = 96;
+// ------------------------------------------------------------------ solves, small fronts
+// One warp per front (k <= 32, f <= SMALL_F_MAX), FPC fronts per CTA, no block-wide barriers.
+// Forward: v = [w[cols]; 0] + children's update vectors (gathered through rel, child by child),
+// then column-oriented substitution: for j < k: y_j = v_j (broadcast by shuffle), v_i -= L_ij y_j
+// for all i > j -- rows of L11 and of L21 alike, each column of P read once, coalesced.
+template <int FPC>
+__global__ void __launch_bounds__(32 * FPC) k_small_fwd(DevCtx cx, const int4* __restrict__ tasks, int ntasks,
+                                                        const double* __restrict__ win, double* __restrict__ zout) {
+    __shared__ double vs[FPC][SMALL_F_MAX];
+    const int grp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ti = blockIdx.x * FPC + grp;
+    if (ti >= ntasks) return;
+    const int s = tasks[ti].x;
+    const Front F = load_front(cx, s);
+    const int k = F.k, f = (int)F.f;
+    double* v = vs[grp];
+    for (int i = lane; i < f; i += 32) v[i] = i < k ? win[F.c0 + i] : 0.0;
+    __syncwarp();
+    for (int ci = cx.child_ptr[s]; ci < cx.child_ptr[s + 1]; ++ci) {
+        const int c = cx.child_idx[ci];
+        const int rc = (int)(cx.rows_ptr[c + 1] - cx.rows_ptr[c]);
+        const int* __restrict__ rel = cx.rel + cx.rows_ptr[c];
+        const double* __restrict__ uc = cx.upd + cx.rows_ptr[c];
+        for (int a = lane; a < rc; a += 32) v[rel[a]] += uc[a];
+        __syncwarp();
+    }
+    const bool h0 = lane < f, h1 = lane + 32 < f, h2 = lane + 64 < f;
+    double v0 = h0 ? v[lane] : 0.0, v1 = h1 ? v[lane + 32] : 0.0, v2 = h2 ? v[lane + 64] : 0.0;
+    const double* __restrict__ col = F.P + lane;
+#pragma unroll 4
+    for (int j = 0; j < k; ++j, col += f) {
+        const double l0 = (h0 && lane > j) ? col[0] : 0.0, l1 = h1 ? col[32] : 0.0, l2 = h2 ? col[64] : 0.0;
+        const double yj = __shfl_sync(0xffffffffu, v0, j);
+        v0 -= l0 * yj; v1 -= l1 * yj; v2 -= l2 * yj;
+    }
+    if (lane < k) zout[F.c0 + lane] = v0;
+    double* __restrict__ us = cx.upd + cx.rows_ptr[s] - k;
+    if (h0 && lane >= k) us[lane] = v0;
+    if (h1) us[lane + 32] = v1;                                // k <= 32 <= lane + 32
+    if (h2) us[lane + 64] = v2;
+}
+
+// Backward: lane c owns pivot row c.  t_c = sum_b U12[c][b] x[rows[b]] is a plain loop over b (the
+// r x k block is a few KB and stays in L1, so the strided reads cost nothing in HBM traffic and no
+// reduction is needed); then column-oriented back substitution with U11 and the stored 1/u_jj.
+template <int FPC>
+__global__ void __launch_bounds__(32 * FPC) k_small_bwd(DevCtx cx, const int4* __restrict__ tasks, int ntasks,
+                                                        double* __restrict__ x) {
+    __shared__ double xs[FPC][SMALL_F_MAX];
+    const int grp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ti = blockIdx.x * FPC + grp;
+    if (ti >= ntasks) return;
+    const int s = tasks[ti].x;
+    const Front F = load_front(cx, s);
+    const int k = F.k, r = (int)F.r, f = (int)F.f;
+    double* xr = xs[grp];
+    const int* __restrict__ rows = cx.rows + cx.rows_ptr[s];
+    for (int b = lane; b < r; b += 32) xr[b] = x[rows[b]];
+    __syncwarp();
+    const bool act = lane < k;
+    double t = 0.0;
+    {
+        const double* __restrict__ tc = F.T + (int64_t)(act ? lane : 0) * r;
+#pragma unroll 4
+        for (int b = 0; b < r; ++b) t += tc[b] * xr[b];
+    }
+    double v = act ? x[F.c0 + lane] - t : 0.0;
+    const double d = act ? cx.dinv[F.c0 + lane] : 0.0;
+    const double* __restrict__ col = F.P + lane + (int64_t)(k - 1) * f;
+#pragma unroll 4
+    for (int j = k - 1; j >= 0; --j, col -= f) {
+        const double u = lane < j ? col[0] : 0.0;
+        const double xj = __shfl_sync(0xffffffffu, v * d, j);
+        v = lane == j ? xj : v - u * xj;
+    }
+    if (act) x[F.c0 + lane] = v;
+}
 
 }  // namespace
 
 int front_small_limit() { return SMALL_F_MAX; }
 
-static size_t small_smem(int rmax) { return sizeof(double) * 2 * NB * (size_t)(((rmax + 3) & ~3) + 4); }
+constexpr int SMALL_FPC32 = 4;     // fronts per CTA in the one-warp class of k_small_factor
+constexpr int SOLVE_FPC = 8;       // fronts per CTA in the small solve kernels
 
 static size_t panel_smem(int j0) { return sizeof(double) * 2 * (size_t)j0 * (NB + 1); }
 static size_t solve_smem(int kmax) { size_t kp = (size_t)((kmax + NB - 1) / NB) * NB; return sizeof(double) * kp * (kp + 1); }
 
 cudaError_t kernels_init() {
-    cudaError_t e = cudaFuncSetAttribute(k_front_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem(SMALL_F_MAX));
+    cudaError_t e = cudaFuncSetAttribute(k_small_factor<96, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(sizeof(double) * small_group_doubles(96)));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem(KW - NB));
     if (e != cudaSuccess) return e;
@@ -655,12 +767,12 @@ cudaError_t kernels_init() {
 void launch_rowscale(cudaStream_t st, int n, const int64_t* rowptr, const int64_t* rowidx, const double* av, double* Rs) {
     k_rowscale<<<(n + 255) / 256, 256, 0, st>>>(n, rowptr, rowidx, av, Rs);
 }
-void launch_scatter(cudaStream_t st, int64_t nnz, const int64_t* dst, const int* arow, const double* Rs,
-                    const double* av, double* lu) {
+void launch_scatter(cudaStream_t st, int64_t nnz, const int64_t* dst, const int* arow, const int* asrc,
+                    const double* Rs, const double* av, double* lu) {
+    if (nnz <= 0) return;
     int64_t blocks = (nnz + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    if (blocks < 1) blocks = 1;
-    k_scatter<<<(int)blocks, 256, 0, st>>>(nnz, dst, arow, Rs, av, lu);
+    k_scatter<<<(int)blocks, 256, 0, st>>>(nnz, dst, arow, asrc, Rs, av, lu);
 }
 void launch_zero_cb(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks) {
     if (ntasks > 0) k_zero_cb<<<ntasks, 256, 0, st>>>(cx, tasks);
@@ -668,9 +780,22 @@ void launch_zero_cb(cudaStream_t st, const DevCtx& cx, const int4* tasks, int nt
 void launch_extend_add(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks) {
     if (ntasks > 0) k_extend_add<<<ntasks, 256, 0, st>>>(cx, tasks);
 }
-void launch_front_small(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int fmax) {
+void launch_front_small(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int fmax,
+                        const double* av, const double* Rs) {
     if (ntasks <= 0) return;
-    k_front_small<<<ntasks, PANEL_ROWS, small_smem(fmax), st>>>(cx, tasks);   // fmax bounds r of the class
+    if (fmax <= 32)
+        k_small_factor<32, 1, SMALL_FPC32><<<(ntasks + SMALL_FPC32 - 1) / SMALL_FPC32, 32 * SMALL_FPC32,
+                                            sizeof(double) * small_group_doubles(32) * SMALL_FPC32, st>>>(cx, tasks, ntasks, 32, av, Rs);
+    else if (fmax <= 64)
+        k_small_factor<64, 2, 1><<<ntasks, 128, sizeof(double) * small_group_doubles(64), st>>>(cx, tasks, ntasks, 64, av, Rs);
+    else
+        k_small_factor<96, 3, 1><<<ntasks, 288, sizeof(double) * small_group_doubles(96), st>>>(cx, tasks, ntasks, 96, av, Rs);
+}
+void launch_small_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const double* win, double* zout) {
+    if (ntasks > 0) k_small_fwd<SOLVE_FPC><<<(ntasks + SOLVE_FPC - 1) / SOLVE_FPC, 32 * SOLVE_FPC, 0, st>>>(cx, tasks, ntasks, win, zout);
+}
+void launch_small_bwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, double* x) {
+    if (ntasks > 0) k_small_bwd<SOLVE_FPC><<<(ntasks + SOLVE_FPC - 1) / SOLVE_FPC, 32 * SOLVE_FPC, 0, st>>>(cx, tasks, ntasks, x);
 }
 void launch_panel(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int g) {
     if (ntasks > 0) k_panel<<<ntasks, PANEL_ROWS, panel_smem(g * NB), st>>>(cx, tasks);

@@ -44,15 +44,24 @@ struct DevCtx {
     int* counters;      // one per (big front, panel step), used by the panel kernel
     int* counters2;     // one per supernode, used by the backward-solve kernel
     int* flag;          // first bad pivot column (atomicMin), INT_MAX when clean
+    double* dinv;       // 1 / u_jj by permuted column, written by the factor kernels
+    // entries of A grouped by the small front that pulls them (k_small_factor)
+    const int* a_ptr;   // nsn+1 (empty range for big fronts)
+    const int* a_src;   // index into the caller's nzval
+    const int* a_row;   // original row (for Rs)
+    const int* a_pos;   // row | col << 16 inside the front
 };
 
 // ---- refactorization
 void launch_rowscale(cudaStream_t st, int n, const int64_t* rowptr, const int64_t* rowidx, const double* av, double* Rs);
-void launch_scatter(cudaStream_t st, int64_t nnz, const int64_t* dst, const int* arow, const double* Rs,
-                    const double* av, double* lu);
+void launch_scatter(cudaStream_t st, int64_t nnz, const int64_t* dst, const int* arow, const int* asrc,
+                    const double* Rs, const double* av, double* lu);
 void launch_zero_cb(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks);
 void launch_extend_add(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks);
-void launch_front_small(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int fmax);
+void launch_front_small(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int fmax,
+                        const double* av, const double* Rs);
+void launch_small_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const double* win, double* zout);
+void launch_small_bwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, double* x);
 void launch_panel(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int g);
 void launch_gemm_cb(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks);
 int front_small_limit();   // largest front the fused shared-memory kernel takes

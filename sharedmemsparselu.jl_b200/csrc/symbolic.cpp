@@ -599,19 +599,29 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
     S.Loff.resize(nsn);
     S.Uoff.resize(nsn);
     S.CBoff.assign(nsn, 0);
-    int64_t off = 0;
     S.nnzL_stored = 0;
     S.flops_stored = 0;
     S.sum_r = (int64_t)S.rows.size();
-    for (int s = 0; s < nsn; ++s) {
-        int64_t k = S.sn_start[s + 1] - S.sn_start[s], r = S.rows_ptr[s + 1] - S.rows_ptr[s], f = k + r;
-        S.Loff[s] = off; off = align2(off + f * k);
-        S.Uoff[s] = off; off = align2(off + r * k);
-        S.nnzL_stored += k * (k + 1) / 2 + k * r;
-        S.max_front = std::max<int>(S.max_front, (int)f);
-        S.max_k = std::max<int>(S.max_k, (int)k);
-        double kd = (double)k, rd = (double)r;
-        S.flops_stored += 2.0 * kd * kd * kd / 3.0 + 2.0 * kd * kd * rd + 2.0 * kd * rd * rd;
+    auto is_small = [&](int s) {
+        const int64_t k = S.sn_start[s + 1] - S.sn_start[s], r = S.rows_ptr[s + 1] - S.rows_ptr[s];
+        return k <= opt.small_k_max && k + r <= opt.small_front_max;
+    };
+    // Big fronts first: their panels are zero-filled and scattered into in HBM at the start of every
+    // refactorization; the small fronts behind them are assembled in shared memory and written once.
+    int64_t off = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int s = 0; s < nsn; ++s) {
+            if (is_small(s) != (pass == 1)) continue;
+            int64_t k = S.sn_start[s + 1] - S.sn_start[s], r = S.rows_ptr[s + 1] - S.rows_ptr[s], f = k + r;
+            S.Loff[s] = off; off = align2(off + f * k);
+            S.Uoff[s] = off; off = align2(off + r * k);
+            S.nnzL_stored += k * (k + 1) / 2 + k * r;
+            S.max_front = std::max<int>(S.max_front, (int)f);
+            S.max_k = std::max<int>(S.max_k, (int)k);
+            double kd = (double)k, rd = (double)r;
+            S.flops_stored += 2.0 * kd * kd * kd / 3.0 + 2.0 * kd * kd * rd + 2.0 * kd * rd * rd;
+        }
+        if (pass == 0) S.lu_big_size = off;
     }
     S.lu_size = off;
     // direct-write eligibility
@@ -621,7 +631,7 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
         const int s = S.sn_parent[c];
         if (s == -1) continue;
         const int64_t kc = S.sn_start[c + 1] - S.sn_start[c], rc = S.rows_ptr[c + 1] - S.rows_ptr[c];
-        if (kc + rc <= opt.small_front_max && kc <= opt.small_k_max) continue;   // fused small-front kernel
+        if (is_small(c) || is_small(s)) continue;   // small fronts are assembled in shared memory
         if (S.child_ptr[s + 1] - S.child_ptr[s] != 1) continue;
         S.direct[c] = 1;
         const int64_t ks = S.sn_start[s + 1] - S.sn_start[s], rs = S.rows_ptr[s + 1] - S.rows_ptr[s];
@@ -656,6 +666,8 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
     }
     // ---------------------------------------------------------------- 9. A -> factor scatter map
     S.a_dst.resize(S.annz);
+    S.a_sn.resize(S.annz);
+    S.a_loc.resize(S.annz);
     for (int c = 0; c < n; ++c) {
         const int j = cinv[c];
         for (int64_t t = Ap[c]; t < Ap[c + 1]; ++t) {
@@ -673,10 +685,14 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
                     lr = k + (it - rb);
                 }
                 S.a_dst[t] = S.Loff[s] + (int64_t)(j - c0) * f + lr;
+                S.a_sn[t] = s;
+                S.a_loc[t] = f < 65536 ? (int)(lr | ((int64_t)(j - c0) << 16)) : 0;
             } else {           // row in the pivot block, column beyond: U panel (stored transposed)
                 const int* it = std::lower_bound(rb, rb + r, j);
                 if (it == rb + r || *it != j) { err = "internal: A entry outside U structure"; return SMSLU_E_INTERNAL; }
                 S.a_dst[t] = S.Uoff[s] + (int64_t)(i - c0) * r + (it - rb);
+                S.a_sn[t] = s;
+                S.a_loc[t] = f < 65536 ? (int)((i - c0) | ((k + (it - rb)) << 16)) : 0;
             }
         }
     }

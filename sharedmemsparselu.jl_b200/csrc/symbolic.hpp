@@ -60,11 +60,15 @@ struct Symbolic {
     // U panel r x k column-major (ld = r) holding U12 transposed.
     std::vector<int64_t> Loff, Uoff;
     int64_t lu_size = 0;
+    int64_t lu_big_size = 0;          // [0, lu_big_size) holds the big fronts, the small ones follow
     // contribution blocks r x r (ld = r), lifetime level(s)..level(parent(s))
     std::vector<int64_t> CBoff;
     int64_t cb_size = 0;
     // for every nonzero of the caller's CSC, in the caller's order: offset into factor storage
     std::vector<int64_t> a_dst;
+    // ... the front it lands in, and its position inside that front: row | col << 16 of the f x f
+    // frontal matrix [pivot block, U12; L21, contribution block] (0 when f >= 65536)
+    std::vector<int> a_sn, a_loc;
 
     int64_t nnzL_exact = 0;           // incl. unit diagonal; nnz(U) is the same number
     int64_t nnzL_stored = 0;          // k(k+1)/2 + k*r summed (what the panels hold per factor)
