@@ -13,8 +13,10 @@ b from splitmix64(47+k).
   roofline   : the dominant kernel of the step (per-launch CUDA-event timing inside the library)
   cpu_baseline / --impl reference : the CPU oracle port (oracle/ref_lu.c) on a bounded sample
 
-N>1 (torchrun): this round every rank factorizes its own copy ("replicas", weak scaling); the
-partitioned multi-GPU factorization with a Schur-complement exchange is described in DESIGN.md.
+N>1 (torchrun): ONE factorization partitioned over the GPUs (strong scaling): every rank factors the
+subtrees it owns, the contributions to the top of the elimination tree (the coupling Schur complement)
+are summed with ncclAllReduce inside libsmslu.so, the top is factored by every rank.  `--replicas`
+runs one independent factorization per GPU instead (weak scaling).
 """
 import argparse
 import json
@@ -148,6 +150,7 @@ def algorithmic_work(F, A):
                     "bytes": 8.0 * float(np.sum(k[big] * f[big] + k[big] * r[big])) + 28.0 * (float(A.nnz) - a_small)},
         "fwd": {"flops": 2.0 * (nnzL - n) * (1 - sf), "bytes": Bf * (1 - sf)},
         "bwd": {"flops": 2.0 * nnzL * (1 - sb), "bytes": Bb * (1 - sb)},
+        "allreduce": {"flops": 0.0, "bytes": 8.0 * (st["allreduce_doubles_refactor"] + st["allreduce_doubles_solve"])},
         "fwd_small": {"flops": 2.0 * (nnzL - n) * sf, "bytes": Bf * sf},
         "bwd_small": {"flops": 2.0 * nnzL * sb, "bytes": Bb * sb},
     }
@@ -248,7 +251,16 @@ def run_ours(args, rank, world, local_rank):
     def values(k):
         v = A.data.copy(); v[diag_pos] += k * 1e-3; return v
     t_setup = time.perf_counter()
-    F = smslu.ParallelSparseLU(A, device=local_rank)
+    if world > 1 and not args.replicas:
+        # one factorization partitioned over the GPUs: per-rank subtrees, NCCL all-reduce of the coupling
+        # Schur-complement contributions inside libsmslu.so, replicated top (DESIGN.md "Multi-GPU")
+        ids = [smslu.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, 0)
+        F = smslu.ParallelSparseLU(A, device=local_rank, nranks=world, rank=rank, comm_id=ids[0])
+        jobs = 1
+    else:
+        F = smslu.ParallelSparseLU(A, device=local_rank)
+        jobs = world
     t_setup = time.perf_counter() - t_setup
     work, st0 = algorithmic_work(F, A)
     launches_per_step = None
@@ -331,8 +343,8 @@ def run_ours(args, rank, world, local_rank):
         return
     hbm_gbs, peak_src = load_peaks()
     fp64_peak = measure_fp64_peak(torch)
-    value = world * K / (ms_dev * 1e-3)
-    e2e_value = world * K / (ms_e2e * 1e-3)
+    value = jobs * K / (ms_dev * 1e-3)
+    e2e_value = jobs * K / (ms_e2e * 1e-3)
     step_ms_prof = sum(ms_kernel.values())
     dom = max((k for k in ms_kernel if k in work), key=lambda k: ms_kernel[k])
     kinds = {}
@@ -360,13 +372,19 @@ def run_ours(args, rank, world, local_rank):
     refac_ms = step_ms_prof - solve_ms
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wu,
-        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak" if jobs == world else "strong",
+        "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "2D 5-point Laplacian %dx%d (n=%d, nnz=%d) refactorize+solve, BASELINE configs[1]" % (args.grid, args.grid, n, nnz),
                    "values": "A + k*1e-3*I, %d value sets cycled; b = splitmix64(47+k)" % NV,
                    "ordering": "nd_graph", "nnz_L": int(st0["nnz_l_exact"]), "flops_refactor": st0["flops_exact"],
                    "cache": "factor storage %.0f MB per step exceeds the 126 MB L2 (no explicit flush)" % (8e-6 * st0["lu_pool_doubles"]),
-                   "parallelism": "1 GPU" if world == 1 else "replicas: one independent factorization per GPU"},
+                   "parallelism": "1 GPU" if world == 1 else (
+                       "replicas: one independent factorization per GPU" if jobs == world else
+                       "one factorization partitioned over %d GPUs: per-rank subtrees + NCCL all-reduce of the coupling "
+                       "Schur complement (%d top supernodes replicated, %.1f MB all-reduced per refactor, %.1f MB per solve)"
+                       % (world, st0["n_top_supernodes"], 8e-6 * st0["allreduce_doubles_refactor"],
+                          8e-6 * st0["allreduce_doubles_solve"]))},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * (nnz + n), "d2h_bytes_per_step": 8 * n,
                 "ms_per_step": ms_e2e / K, "residual": res_e2e},
         "gpu_launches": int(launches_per_step * K),
@@ -399,6 +417,7 @@ def main():
     ap.add_argument("--sample-grid", type=int, default=448, help="grid edge of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--superlu", action="store_true", help="also time SciPy SuperLU on the full workload")
+    ap.add_argument("--replicas", action="store_true", help="N>1: independent factorization per GPU instead of one partitioned factorization")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -35,6 +35,7 @@ extern "C" {
 #define SMSLU_E_CUDA (-5)     /* CUDA runtime error or no usable device                           */
 #define SMSLU_E_OOM (-6)
 #define SMSLU_E_INTERNAL (-7)
+#define SMSLU_E_NCCL (-8)
 
 #define SMSLU_ORD_AUTO 0      /* ND_GRID when the grid hint matches n, else ND_GRAPH              */
 #define SMSLU_ORD_NATURAL 1
@@ -56,7 +57,9 @@ typedef struct smslu_options {
     int32_t scaling;         /* SMSLU_SCALE_*, used when smslu_refactor gets Rs == NULL        */
     int32_t device;          /* CUDA device ordinal; -1 = current device                       */
     int32_t use_graph;       /* replay the level schedule through CUDA graphs                  */
-    int32_t reserved[8];
+    int32_t nranks;          /* GPUs (= processes) the elimination tree is partitioned over; 0/1 = one GPU */
+    int32_t rank;            /* this process' rank in [0, nranks)                                */
+    int32_t reserved[6];
 } smslu_options_t;
 
 typedef struct smslu_stats {
@@ -74,7 +77,11 @@ typedef struct smslu_stats {
     int64_t bad_pivot_col;              /* permuted column of the first bad pivot, or -1          */
     double ms_kernel[16];               /* smslu_set_profile(h,1): device ms per kernel kind, summed */
     int64_t launches_kernel[16];        /*   and launches per kernel kind (index = SMSLU_K_*)     */
-    int64_t reserved[8];
+    int64_t n_top_supernodes;           /* partition: supernodes factored redundantly by every rank      */
+    int64_t n_local_supernodes;         /*   supernodes owned by this rank                                */
+    int64_t allreduce_doubles_refactor; /*   doubles summed across ranks per refactorization / per solve  */
+    int64_t allreduce_doubles_solve;
+    int64_t reserved[4];
 } smslu_stats_t;
 
 /* kernel kinds for ms_kernel / launches_kernel */
@@ -91,6 +98,7 @@ typedef struct smslu_stats {
 #define SMSLU_K_UNPERMUTE 10
 #define SMSLU_K_FWD_SMALL 11 /* warp-per-front solve kernels of the shared-memory-sized fronts */
 #define SMSLU_K_BWD_SMALL 12
+#define SMSLU_K_ALLREDUCE 13 /* NCCL all-reduces of a partitioned handle (+ the small kernels around them) */
 
 /* Fill *opts with defaults.  */
 int smslu_options_default(smslu_options_t* opts);
@@ -138,6 +146,17 @@ int smslu_get_nnz(smslu_handle_t h, int64_t* nnz_l, int64_t* nnz_u);
 int smslu_get_factors(smslu_handle_t h, int64_t* l_colptr, int64_t* l_rowval, double* l_nzval,
                       int64_t* u_colptr, int64_t* u_rowval, double* u_nzval,
                       int64_t* p, int64_t* q, double* Rs, int32_t index_base);
+
+/* Multi-GPU, one process per GPU (no reference counterpart: its MPI dependency is declared but never
+ * used, Project.toml:8).  Every rank creates a handle for the SAME pattern with options.nranks /
+ * options.rank set; smslu_analyze partitions the elimination tree into per-rank subtrees plus a top part
+ * that every rank factors after the subtrees' Schur-complement contributions have been summed with
+ * ncclAllReduce over NVLink.  Rank 0 calls smslu_comm_unique_id and hands the 128 bytes to the other
+ * ranks (MPI.Bcast, torch.distributed.broadcast, ...); then every rank calls smslu_comm_init
+ * (collective).  After that smslu_refactor* / smslu_solve* are collective calls: every rank passes the
+ * full nzval / b and receives the full x. */
+int smslu_comm_unique_id(void* id, int64_t nbytes);
+int smslu_comm_init(smslu_handle_t h, const void* id, int64_t nbytes);
 
 /* Diagnostics (no reference counterpart). */
 int smslu_get_stats(smslu_handle_t h, smslu_stats_t* stats);

@@ -21,7 +21,18 @@ from . import _capi
 from ._capi import DimensionMismatch, SingularException, SmsluError  # noqa: F401
 
 __all__ = ["ParallelSparseLU", "lu_", "ldiv_", "lsolve_", "rsolve_", "cleanup_ParallelSparseLU_",
-           "allocate_shared", "pinned_empty", "DimensionMismatch", "SingularException", "SmsluError"]
+           "allocate_shared", "pinned_empty", "comm_unique_id", "DimensionMismatch", "SingularException",
+           "SmsluError"]
+
+
+def comm_unique_id() -> bytes:
+    """128-byte NCCL id made on rank 0; broadcast it to the other ranks (torch.distributed, MPI, ...)
+    and pass it to every rank's ``ParallelSparseLU(..., nranks=N, rank=r, comm_id=id)``."""
+    buf = C.create_string_buffer(128)
+    rc = _capi.lib().smslu_comm_unique_id(buf, 128)
+    if rc != 0:
+        raise _capi.SmsluError(rc, "smslu_comm_unique_id failed")
+    return buf.raw
 
 
 def _ptr(a):
@@ -94,10 +105,14 @@ class ParallelSparseLU:
     "nd_graph", "nd_grid"), ``grid`` (nx, ny, nz), ``p``/``q``/``Rs`` to reproduce a given
     factorization contract ``L*U == (Rs .* A)[p, q]`` (what the Julia shim passes from
     UMFPACK's ``lu(A)``), ``scaling`` ("sum" = UMFPACK's default row scaling, "none").
+    Multi-GPU (one process per GPU): ``nranks``, ``rank`` and the 128-byte ``comm_id`` from
+    ``comm_unique_id()`` of rank 0; every call is then collective, every rank passes the full
+    ``A`` / ``b`` and receives the full ``x``; ``F.L`` / ``F.U`` hold this rank's share of the values.
     """
 
     def __init__(self, A, chunk_size=None, *, ordering="auto", grid=None, p=None, q=None, Rs=None,
-                 scaling="sum", nd_leaf=None, relax=True, max_width=None, device=None):
+                 scaling="sum", nd_leaf=None, relax=True, max_width=None, device=None,
+                 nranks=1, rank=0, comm_id=None):
         import scipy.sparse as sp
         if not sp.isspmatrix_csc(A):
             raise TypeError("A must be a scipy.sparse.csc_matrix (SparseMatrixCSC)")
@@ -127,6 +142,8 @@ class ParallelSparseLU:
         opts.scaling = _capi.SCALE[scaling]
         if device is not None:
             opts.device = int(device)
+        opts.nranks, opts.rank = int(nranks), int(rank)
+        self.nranks, self.rank = int(nranks), int(rank)
         self._h = C.c_void_p()
         rc = L.smslu_create(C.byref(self._h), self.n, _ptr(self._colptr), _ptr(self._rowval), 0, C.byref(opts))
         if rc != 0:
@@ -134,6 +151,8 @@ class ParallelSparseLU:
         pp = None if p is None else np.ascontiguousarray(p, dtype=np.int64)
         qq = None if q is None else np.ascontiguousarray(q, dtype=np.int64)
         _capi.check(self._h, L.smslu_analyze(self._h, _ptr(pp), _ptr(qq)))
+        if self.nranks > 1 and comm_id is not None:      # collective: every rank of the partition
+            _capi.check(self._h, L.smslu_comm_init(self._h, C.c_char_p(bytes(comm_id)), len(comm_id)))
         self._Rs_given = None if Rs is None else np.ascontiguousarray(Rs, dtype=np.float64)
         self._cache = {}
         self._numeric(A)

@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsmslu.so")
 
-OK, E_DIM, E_PIVOT, E_PATTERN, E_ARG, E_CUDA, E_OOM, E_INTERNAL = 0, -1, -2, -3, -4, -5, -6, -7
+OK, E_DIM, E_PIVOT, E_PATTERN, E_ARG, E_CUDA, E_OOM, E_INTERNAL, E_NCCL = 0, -1, -2, -3, -4, -5, -6, -7, -8
 ORD = {"auto": 0, "natural": 1, "given": 2, "nd_graph": 3, "nd_grid": 4}
 SCALE = {"none": 0, "sum": 1}
 
@@ -19,15 +19,17 @@ EXPORTS = [
     "smslu_last_error", "smslu_get_symbolic", "smslu_destroy", "smslu_allocate_shared",
     "smslu_host_alloc", "smslu_host_free", "smslu_version", "smslu_refactor_async",
     "smslu_solve_async", "smslu_sync", "smslu_set_stream", "smslu_set_profile",
+    "smslu_comm_unique_id", "smslu_comm_init",
 ]
 KERNEL_KINDS = ["rowscale", "scatter", "zero_cb", "extend_add", "front_small", "panel", "gemm_cb",
-                "permute_scale", "fwd", "bwd", "unpermute", "fwd_small", "bwd_small"]
+                "permute_scale", "fwd", "bwd", "unpermute", "fwd_small", "bwd_small", "allreduce"]
 
 
 class Options(C.Structure):
     _fields_ = [("ordering", C.c_int32), ("grid", C.c_int32 * 3), ("nd_leaf", C.c_int32),
                 ("relax", C.c_int32), ("max_width", C.c_int32), ("scaling", C.c_int32),
-                ("device", C.c_int32), ("use_graph", C.c_int32), ("reserved", C.c_int32 * 8)]
+                ("device", C.c_int32), ("use_graph", C.c_int32), ("nranks", C.c_int32), ("rank", C.c_int32),
+                ("reserved", C.c_int32 * 6)]
 
 
 class Stats(C.Structure):
@@ -38,7 +40,9 @@ class Stats(C.Structure):
             "flops_exact", "flops_stored", "ms_analyze", "ms_upload", "ms_refactor", "ms_solve",
             "ms_refactor_h2d", "ms_solve_h2d", "ms_solve_d2h")] + [(k, C.c_int64) for k in (
                 "launches_refactor", "launches_solve", "n_refactor", "n_solve", "bad_pivot_col")] + [
-        ("ms_kernel", C.c_double * 16), ("launches_kernel", C.c_int64 * 16), ("reserved", C.c_int64 * 8)]
+        ("ms_kernel", C.c_double * 16), ("launches_kernel", C.c_int64 * 16)] + [(k, C.c_int64) for k in (
+            "n_top_supernodes", "n_local_supernodes", "allreduce_doubles_refactor", "allreduce_doubles_solve")] + [
+        ("reserved", C.c_int64 * 4)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k not in ("reserved", "ms_kernel", "launches_kernel")}
@@ -95,6 +99,8 @@ def lib():
         L.smslu_sync.argtypes = [vp]
         L.smslu_set_stream.argtypes = [vp, vp]
         L.smslu_set_profile.argtypes = [vp, i32]
+        L.smslu_comm_unique_id.argtypes = [vp, i64]
+        L.smslu_comm_init.argtypes = [vp, vp, i64]
         for name in EXPORTS:
             if name != "smslu_last_error":
                 getattr(L, name).restype = C.c_int

@@ -34,7 +34,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     tmp = LIB + ".%d.tmp" % os.getpid()
     cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + \
-          [os.path.join(CSRC, s) for s in SOURCES]
+          [os.path.join(CSRC, s) for s in SOURCES] + ["-lnccl"]
     subprocess.check_call(cmd)
     os.replace(tmp, LIB)
     return LIB

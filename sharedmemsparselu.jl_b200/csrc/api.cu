@@ -1,6 +1,7 @@
 // C ABI of libsmslu.so (include/smslu.h): handle, upload of the symbolic layout, level schedules,
 // and the numeric entry points.  No CPU fallback: numeric calls need a CUDA device.
 #include <cuda_runtime.h>
+#include <nccl.h>
 
 #include <algorithm>
 #include <chrono>
@@ -60,7 +61,15 @@ struct smslu_handle_s {
     int *d_p = nullptr, *d_q = nullptr;
     double *d_Rs = nullptr, *d_aval = nullptr, *d_w = nullptr, *d_z = nullptr, *d_xb = nullptr;
     int4* d_tasks = nullptr;
-    std::vector<Launch> fac, fwd, bwd;
+    std::vector<Launch> fac, fwd, bwd;               // this rank's supernodes (everything when nranks == 1)
+    std::vector<Launch> fac_top, fwd_top, bwd_top;   // top of the tree, replicated on every rank
+    int rank = 0, nranks = 1;
+    ncclComm_t comm = nullptr;
+    int4* d_vtasks = nullptr;            // interface fronts: x = front, y = virtual child, z..w = range in d_vlist
+    int* d_vlist = nullptr;              // this rank's subtree roots below each interface front
+    int nvtasks = 0;
+    int64_t vupd_off = 0, vupd_len = 0;  // region of cx.upd holding the virtual children's vectors
+    int* d_colowner = nullptr;           // owner of every permuted column (-1 = top)
     int64_t bpart_slots = 0, ncounters = 0;
 
     bool own_stream = true;
@@ -93,6 +102,12 @@ int fail(smslu_handle_t h, int code, const std::string& msg) {
                         std::string(#call) + ": " + cudaGetErrorString(e_));                      \
     } while (0)
 
+#define NCCLCHK(call)                                                                                 \
+    do {                                                                                          \
+        ncclResult_t r_ = (call);                                                                 \
+        if (r_ != ncclSuccess) return fail(h, SMSLU_E_NCCL, std::string(#call) + ": " + ncclGetErrorString(r_)); \
+    } while (0)
+
 template <class T>
 int dev_alloc(smslu_handle_t h, T** p, size_t count) {
     *p = nullptr;
@@ -117,140 +132,157 @@ bool is_device_ptr(const void* p) {
 }
 
 // ---------------------------------------------------------------- schedules
+// Launch lists are built once per pattern.  With a partition (nranks > 1) a rank runs
+//   phase A: the supernodes it owns, level by level (their contributions into top fronts included),
+//   all-reduce of the top panels and interface contribution blocks,
+//   phase B: the top of the tree, level by level, identically on every rank.
+// phase 0 = this rank's supernodes, phase 1 = top supernodes (owner -1).
 void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
     const Symbolic& S = h->S;
-    const int small_max = front_small_limit();
+    const int rank = h->rank;
     auto K = [&](int s) { return S.sn_start[s + 1] - S.sn_start[s]; };
     auto R = [&](int s) { return (int64_t)(S.rows_ptr[s + 1] - S.rows_ptr[s]); };
     auto NC = [&](int s) { return S.child_ptr[s + 1] - S.child_ptr[s]; };
-    auto SMALL = [&](int s) { return K(s) <= NB && K(s) + R(s) <= small_max; };
-    int64_t ncounters = 0;
+    auto SMALL = [&](int s) { return S.small[s] != 0; };
+    int64_t ncounters = 0, slots = 0;
     auto push = [&](std::vector<Launch>& v, int kind, int64_t off, int fmax) {
         int nt = (int)((int64_t)tasks.size() - off);
         if (nt > 0) v.push_back(Launch{kind, off, nt, fmax});
     };
-    h->fac.clear(); h->fwd.clear(); h->bwd.clear();
-    for (int l = 0; l < S.nlevels; ++l) {
-        const int* sn = S.level_sn.data() + S.level_ptr[l];
-        const int cnt = S.level_ptr[l + 1] - S.level_ptr[l];
-        int maxch = 0;
-        // Zero the contribution blocks that receive '+=' contributions.  Extend-add children add
-        // at this level; a direct child adds one level earlier, so its parent is zeroed there.
-        int64_t off = (int64_t)tasks.size();
-        auto zero_tasks = [&](int s) {
-            int64_t tiles = (R(s) * R(s) + ZERO_TILE - 1) / ZERO_TILE;
-            for (int64_t i = 0; i < tiles; ++i) tasks.push_back(make_int4(s, (int)i, 0, 0));
-        };
-        for (int t = 0; t < cnt; ++t) {
-            int s = sn[t];
-            maxch = std::max(maxch, NC(s));
-            const bool fed_directly = NC(s) == 1 && S.direct[S.child_idx[S.child_ptr[s]]];
-            if (NC(s) > 0 && R(s) > 0 && !fed_directly && !SMALL(s)) zero_tasks(s);
-            if (S.direct[s] && !S.cb_assigned[S.sn_parent[s]] && R(S.sn_parent[s]) > 0) zero_tasks(S.sn_parent[s]);
-        }
-        push(h->fac, L_ZERO, off, 0);
-        // extend-add, one launch per child slot (children that write directly are skipped)
-        for (int slot = 0; slot < maxch; ++slot) {
-            off = (int64_t)tasks.size();
-            for (int t = 0; t < cnt; ++t) {
-                int s = sn[t];
-                if (NC(s) <= slot || SMALL(s)) continue;          // small parents pull their children
-                int c = S.child_idx[S.child_ptr[s] + slot];
-                int64_t rc = R(c);
-                if (rc == 0 || S.direct[c]) continue;
-                int ncols = (int)std::max<int64_t>(1, std::min<int64_t>(rc, 4096 / rc));
-                for (int64_t b0 = 0; b0 < rc; b0 += ncols)
-                    tasks.push_back(make_int4(c, (int)b0, (int)std::min<int64_t>(ncols, rc - b0), 0));
-            }
-            push(h->fac, L_EXTEND, off, 0);
-        }
-        // fused small fronts by shared-memory class
-        const int classes[3] = {32, 64, small_max};
-        int lo = 0;
-        for (int ci = 0; ci < 3; ++ci) {
-            off = (int64_t)tasks.size();
-            for (int t = 0; t < cnt; ++t) {
-                int s = sn[t];
-                int64_t f = K(s) + R(s);
-                if (SMALL(s) && f > lo && f <= classes[ci]) tasks.push_back(make_int4(s, 0, 0, 0));
-            }
-            push(h->fac, L_SMALL, off, classes[ci]);
-            lo = classes[ci];
-        }
-        // big fronts: left-looking panel steps (one launch per 32 pivot columns), then Schur update
-        int max_blk = 0;
-        for (int t = 0; t < cnt; ++t) if (!SMALL(sn[t])) max_blk = std::max(max_blk, (K(sn[t]) + NB - 1) / NB);
-        for (int g = 0; g < max_blk; ++g) {
-            off = (int64_t)tasks.size();
-            for (int t = 0; t < cnt; ++t) {
-                int s = sn[t];
-                if (SMALL(s)) continue;
-                const int k = K(s), nblk = (k + NB - 1) / NB;
-                if (g >= nblk) continue;
-                const int64_t r = R(s), f = k + r;
-                const int j1 = std::min(k, (g + 1) * NB);
-                int tl = (int)((f - j1 + PANEL_ROWS - 1) / PANEL_ROWS);      // rows below the diagonal block
-                const int tt = (int)((r + PANEL_ROWS - 1) / PANEL_ROWS);     // rows of U12'
-                const int ti = (k - j1 + PANEL_ROWS - 1) / PANEL_ROWS;       // columns right of it
-                if (tl + tt + ti == 0) tl = 1;                               // someone has to factor D_gg
-                const int total = tl + tt + ti;
-                const int cidx = (int)ncounters++;
-                for (int i = 0; i < tl; ++i) tasks.push_back(make_int4(s, g | (0 << 4) | (total << 8), i, cidx));
-                for (int i = 0; i < tt; ++i) tasks.push_back(make_int4(s, g | (1 << 4) | (total << 8), i, cidx));
-                for (int i = 0; i < ti; ++i) tasks.push_back(make_int4(s, g | (2 << 4) | (total << 8), i, cidx));
-            }
-            push(h->fac, L_PANEL, off, g);
-        }
-        off = (int64_t)tasks.size();
-        for (int t = 0; t < cnt; ++t) {
-            int s = sn[t];
-            int64_t r = R(s);
-            if (SMALL(s)) continue;
-            int nt = (int)((r + GEMM_TILE - 1) / GEMM_TILE);
-            for (int j = 0; j < nt; ++j)
-                for (int i = 0; i < nt; ++i) {
-                    int flags = (NC(s) > 0 ? 1 : 0) | (S.direct[s] ? 2 : 0) |
-                                (S.direct[s] && S.cb_assigned[S.sn_parent[s]] ? 4 : 0);
-                    tasks.push_back(make_int4(s, i, j, flags));
-                }
-        }
-        push(h->fac, L_GEMM, off, 0);
-        // forward solve level: narrow (k <= 32) and wide fronts go to separate launches because
-        // the kernel stages the whole pivot block in shared memory (8 KB vs up to 129 KB)
-        off = (int64_t)tasks.size();
-        for (int t = 0; t < cnt; ++t) if (SMALL(sn[t])) tasks.push_back(make_int4(sn[t], 0, 0, 0));
-        push(h->fwd, L_FWD_SMALL, off, 0);
-        for (int cls = 0; cls < 2; ++cls) {
-            off = (int64_t)tasks.size();
-            int kmax = 0;
-            for (int t = 0; t < cnt; ++t) {
-                int s = sn[t];
-                if (SMALL(s) || (K(s) > NB) != (cls == 1)) continue;
-                kmax = std::max(kmax, K(s));
-                int nt = (int)std::max<int64_t>(1, (R(s) + FWD_ROWS - 1) / FWD_ROWS);
-                for (int i = 0; i < nt; ++i) tasks.push_back(make_int4(s, i, 0, 0));
-            }
-            push(h->fwd, L_FWD, off, kmax);
-        }
-    }
-    int64_t slots = 0;
-    for (int l = S.nlevels - 1; l >= 0; --l) {
-        int64_t off0 = (int64_t)tasks.size();
-        for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t)
-            if (SMALL(S.level_sn[t])) tasks.push_back(make_int4(S.level_sn[t], 0, 0, 0));
-        push(h->bwd, L_BWD_SMALL, off0, 0);
-        for (int cls = 0; cls < 2; ++cls) {
+    for (int ph = 0; ph < 2; ++ph) {
+        std::vector<Launch>& fac = ph == 0 ? h->fac : h->fac_top;
+        std::vector<Launch>& fwd = ph == 0 ? h->fwd : h->fwd_top;
+        std::vector<Launch>& bwd = ph == 0 ? h->bwd : h->bwd_top;
+        fac.clear(); fwd.clear(); bwd.clear();
+        const int mine = ph == 0 ? rank : -1;
+        auto IN = [&](int s) { return S.owner[s] == mine; };
+        for (int l = 0; l < S.nlevels; ++l) {
+            const int* sn = S.level_sn.data() + S.level_ptr[l];
+            const int cnt = S.level_ptr[l + 1] - S.level_ptr[l];
+            int maxch = 0;
+            // Zero the contribution blocks that receive '+=' contributions.  Extend-add children add
+            // at this level; a direct child adds one level earlier, so its parent is zeroed there.
+            // Interface blocks are zero-filled once, before phase A, and arrive here all-reduced.
             int64_t off = (int64_t)tasks.size();
-            int kmax = 0;
-            for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) {
-                int s = S.level_sn[t];
-                if (SMALL(s) || (K(s) > NB) != (cls == 1)) continue;
-                kmax = std::max(kmax, K(s));
-                int nt = (int)std::max<int64_t>(1, (R(s) + BWD_ROWS - 1) / BWD_ROWS);
-                for (int i = 0; i < nt; ++i) tasks.push_back(make_int4(s, i, nt, (int)slots));
-                if (nt > 1) slots += nt;
+            auto zero_tasks = [&](int s) {
+                int64_t tiles = (R(s) * R(s) + ZERO_TILE - 1) / ZERO_TILE;
+                for (int64_t i = 0; i < tiles; ++i) tasks.push_back(make_int4(s, (int)i, 0, 0));
+            };
+            for (int t = 0; t < cnt; ++t) {
+                int s = sn[t];
+                // a top parent receives this rank's subtree contributions during phase A
+                if (IN(s) || (ph == 0 && S.owner[s] == -1)) maxch = std::max(maxch, NC(s));
+                if (!IN(s)) continue;
+                const bool fed_directly = NC(s) == 1 && S.direct[S.child_idx[S.child_ptr[s]]];
+                if (NC(s) > 0 && R(s) > 0 && !fed_directly && !SMALL(s) && !S.iface[s]) zero_tasks(s);
+                if (S.direct[s] && !S.cb_assigned[S.sn_parent[s]] && R(S.sn_parent[s]) > 0) zero_tasks(S.sn_parent[s]);
             }
-            push(h->bwd, L_BWD, off, kmax);
+            push(fac, L_ZERO, off, 0);
+            // extend-add, one launch per child slot (children that write directly are skipped)
+            for (int slot = 0; slot < maxch; ++slot) {
+                off = (int64_t)tasks.size();
+                for (int t = 0; t < cnt; ++t) {
+                    int s = sn[t];
+                    if (NC(s) <= slot || SMALL(s)) continue;          // small parents pull their children
+                    if (!(IN(s) || (ph == 0 && S.owner[s] == -1))) continue;
+                    int c = S.child_idx[S.child_ptr[s] + slot];
+                    if (!IN(c)) continue;                             // phase A: this rank's children; B: top children
+                    int64_t rc = R(c);
+                    if (rc == 0 || S.direct[c]) continue;
+                    int ncols = (int)std::max<int64_t>(1, std::min<int64_t>(rc, 4096 / rc));
+                    for (int64_t b0 = 0; b0 < rc; b0 += ncols)
+                        tasks.push_back(make_int4(c, (int)b0, (int)std::min<int64_t>(ncols, rc - b0), 0));
+                }
+                push(fac, L_EXTEND, off, 0);
+            }
+            // small fronts by shared-memory class
+            const int classes[3] = {32, 64, front_small_limit()};
+            int lo = 0;
+            for (int ci = 0; ci < 3; ++ci) {
+                off = (int64_t)tasks.size();
+                for (int t = 0; t < cnt; ++t) {
+                    int s = sn[t];
+                    int64_t f = K(s) + R(s);
+                    if (IN(s) && SMALL(s) && f > lo && f <= classes[ci]) tasks.push_back(make_int4(s, 0, 0, 0));
+                }
+                push(fac, L_SMALL, off, classes[ci]);
+                lo = classes[ci];
+            }
+            // big fronts: left-looking panel steps (one launch per 32 pivot columns), then Schur update
+            int max_blk = 0;
+            for (int t = 0; t < cnt; ++t) if (IN(sn[t]) && !SMALL(sn[t])) max_blk = std::max(max_blk, (K(sn[t]) + NB - 1) / NB);
+            for (int g = 0; g < max_blk; ++g) {
+                off = (int64_t)tasks.size();
+                for (int t = 0; t < cnt; ++t) {
+                    int s = sn[t];
+                    if (!IN(s) || SMALL(s)) continue;
+                    const int k = K(s), nblk = (k + NB - 1) / NB;
+                    if (g >= nblk) continue;
+                    const int64_t r = R(s), f = k + r;
+                    const int j1 = std::min(k, (g + 1) * NB);
+                    int tl = (int)((f - j1 + PANEL_ROWS - 1) / PANEL_ROWS);      // rows below the diagonal block
+                    const int tt = (int)((r + PANEL_ROWS - 1) / PANEL_ROWS);     // rows of U12'
+                    const int ti = (k - j1 + PANEL_ROWS - 1) / PANEL_ROWS;       // columns right of it
+                    if (tl + tt + ti == 0) tl = 1;                               // someone has to factor D_gg
+                    const int total = tl + tt + ti;
+                    const int cidx = (int)ncounters++;
+                    for (int i = 0; i < tl; ++i) tasks.push_back(make_int4(s, g | (0 << 4) | (total << 8), i, cidx));
+                    for (int i = 0; i < tt; ++i) tasks.push_back(make_int4(s, g | (1 << 4) | (total << 8), i, cidx));
+                    for (int i = 0; i < ti; ++i) tasks.push_back(make_int4(s, g | (2 << 4) | (total << 8), i, cidx));
+                }
+                push(fac, L_PANEL, off, g);
+            }
+            off = (int64_t)tasks.size();
+            for (int t = 0; t < cnt; ++t) {
+                int s = sn[t];
+                int64_t r = R(s);
+                if (!IN(s) || SMALL(s)) continue;
+                int nt = (int)((r + GEMM_TILE - 1) / GEMM_TILE);
+                for (int j = 0; j < nt; ++j)
+                    for (int i = 0; i < nt; ++i) {
+                        int flags = (NC(s) > 0 ? 1 : 0) | (S.direct[s] ? 2 : 0) |
+                                    (S.direct[s] && S.cb_assigned[S.sn_parent[s]] ? 4 : 0);
+                        tasks.push_back(make_int4(s, i, j, flags));
+                    }
+            }
+            push(fac, L_GEMM, off, 0);
+            // forward solve level: warp-per-front kernel for the small fronts; narrow (k <= 32) and
+            // wide big fronts go to separate launches because the kernel stages the whole pivot block
+            // in shared memory (8 KB vs up to 129 KB)
+            off = (int64_t)tasks.size();
+            for (int t = 0; t < cnt; ++t) if (IN(sn[t]) && SMALL(sn[t])) tasks.push_back(make_int4(sn[t], 0, 0, 0));
+            push(fwd, L_FWD_SMALL, off, 0);
+            for (int cls = 0; cls < 2; ++cls) {
+                off = (int64_t)tasks.size();
+                int kmax = 0;
+                for (int t = 0; t < cnt; ++t) {
+                    int s = sn[t];
+                    if (!IN(s) || SMALL(s) || (K(s) > NB) != (cls == 1)) continue;
+                    kmax = std::max(kmax, K(s));
+                    int nt = (int)std::max<int64_t>(1, (R(s) + FWD_ROWS - 1) / FWD_ROWS);
+                    for (int i = 0; i < nt; ++i) tasks.push_back(make_int4(s, i, 0, 0));
+                }
+                push(fwd, L_FWD, off, kmax);
+            }
+        }
+        for (int l = S.nlevels - 1; l >= 0; --l) {
+            int64_t off0 = (int64_t)tasks.size();
+            for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t)
+                if (IN(S.level_sn[t]) && SMALL(S.level_sn[t])) tasks.push_back(make_int4(S.level_sn[t], 0, 0, 0));
+            push(bwd, L_BWD_SMALL, off0, 0);
+            for (int cls = 0; cls < 2; ++cls) {
+                int64_t off = (int64_t)tasks.size();
+                int kmax = 0;
+                for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) {
+                    int s = S.level_sn[t];
+                    if (!IN(s) || SMALL(s) || (K(s) > NB) != (cls == 1)) continue;
+                    kmax = std::max(kmax, K(s));
+                    int nt = (int)std::max<int64_t>(1, (R(s) + BWD_ROWS - 1) / BWD_ROWS);
+                    for (int i = 0; i < nt; ++i) tasks.push_back(make_int4(s, i, nt, (int)slots));
+                    if (nt > 1) slots += nt;
+                }
+                push(bwd, L_BWD, off, kmax);
+            }
         }
     }
     h->bpart_slots = slots;
@@ -260,6 +292,7 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
 int ensure_uploaded(smslu_handle_t h) {
     if (h->uploaded) { CU(cudaSetDevice(h->device)); return 0; }
     if (!h->analyzed) return fail(h, SMSLU_E_ARG, "smslu_analyze has not been called");
+    if (h->nranks > 1 && !h->comm) return fail(h, SMSLU_E_ARG, "partitioned handle: call smslu_comm_init on every rank first");
     double t0 = now_ms();
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -282,16 +315,53 @@ int ensure_uploaded(smslu_handle_t h) {
     int rc;
     int *d_sn_start, *d_rows, *d_rel, *d_sn_parent, *d_child_ptr, *d_child_idx;
     int64_t *d_rows_ptr, *d_Loff, *d_Uoff, *d_CBoff;
+    // Device copies of the tree.  With a partition every interface front gets one extra "virtual
+    // child" whose update vector is the all-reduced sum of the forward-solve contributions of the
+    // subtrees below the cut (rel = identity over the parent's front); it replaces those subtree
+    // roots in the parent's child list, so the solve kernels need no special case.
+    std::vector<int64_t> rows_ptr_d(S.rows_ptr);
+    std::vector<int> rows_d(S.rows), rel_d(S.rel), child_ptr_d(S.child_ptr), child_idx_d(S.child_idx);
+    h->vupd_off = S.sum_r; h->vupd_len = 0; h->nvtasks = 0;
+    if (S.nranks > 1) {
+        std::vector<int4> vtasks;
+        std::vector<int> vlist;
+        child_ptr_d.assign(S.nsn + 1, 0);
+        child_idx_d.clear();
+        int nv = 0;
+        for (int s2 = 0; s2 < S.nsn; ++s2) {
+            if (S.iface[s2]) {
+                const int v = S.nsn + nv++;
+                const int64_t f = (S.sn_start[s2 + 1] - S.sn_start[s2]) + (S.rows_ptr[s2 + 1] - S.rows_ptr[s2]);
+                for (int64_t i = 0; i < f; ++i) { rows_d.push_back(0); rel_d.push_back((int)i); }
+                rows_ptr_d.push_back((int64_t)rows_d.size());
+                child_idx_d.push_back(v);
+                const int l0 = (int)vlist.size();
+                for (int u = S.child_ptr[s2]; u < S.child_ptr[s2 + 1]; ++u)
+                    if (S.owner[S.child_idx[u]] == h->rank) vlist.push_back(S.child_idx[u]);
+                vtasks.push_back(make_int4(s2, v, l0, (int)vlist.size()));
+            }
+            for (int u = S.child_ptr[s2]; u < S.child_ptr[s2 + 1]; ++u)
+                if (!S.iface[s2] || S.owner[S.child_idx[u]] == -1) child_idx_d.push_back(S.child_idx[u]);
+            child_ptr_d[s2 + 1] = (int)child_idx_d.size();
+        }
+        h->vupd_len = (int64_t)rows_d.size() - S.sum_r;
+        h->nvtasks = (int)vtasks.size();
+        if ((rc = dev_upload(h, &h->d_vtasks, vtasks))) return rc;
+        if ((rc = dev_upload(h, &h->d_vlist, vlist))) return rc;
+        std::vector<int> colowner(n);
+        for (int j = 0; j < n; ++j) colowner[j] = S.owner[S.col2sn[j]];
+        if ((rc = dev_upload(h, &h->d_colowner, colowner))) return rc;
+    }
     if ((rc = dev_upload(h, &d_sn_start, S.sn_start))) return rc;
-    if ((rc = dev_upload(h, &d_rows_ptr, S.rows_ptr))) return rc;
-    if ((rc = dev_upload(h, &d_rows, S.rows))) return rc;
-    if ((rc = dev_upload(h, &d_rel, S.rel))) return rc;
+    if ((rc = dev_upload(h, &d_rows_ptr, rows_ptr_d))) return rc;
+    if ((rc = dev_upload(h, &d_rows, rows_d))) return rc;
+    if ((rc = dev_upload(h, &d_rel, rel_d))) return rc;
     if ((rc = dev_upload(h, &d_Loff, S.Loff))) return rc;
     if ((rc = dev_upload(h, &d_Uoff, S.Uoff))) return rc;
     if ((rc = dev_upload(h, &d_CBoff, S.CBoff))) return rc;
     if ((rc = dev_upload(h, &d_sn_parent, S.sn_parent))) return rc;
-    if ((rc = dev_upload(h, &d_child_ptr, S.child_ptr))) return rc;
-    if ((rc = dev_upload(h, &d_child_idx, S.child_idx))) return rc;
+    if ((rc = dev_upload(h, &d_child_ptr, child_ptr_d))) return rc;
+    if ((rc = dev_upload(h, &d_child_idx, child_idx_d))) return rc;
     if ((rc = dev_upload(h, &h->d_p, S.p))) return rc;
     if ((rc = dev_upload(h, &h->d_q, S.q))) return rc;
     {   // row index of every nonzero (for the scaling) and a row-major view of the pattern
@@ -308,22 +378,22 @@ int ensure_uploaded(smslu_handle_t h) {
     {   // entries of A grouped by the small front that pulls them; the big fronts' entries follow
         const int nsn = S.nsn;
         if (h->annz > INT_MAX) return fail(h, SMSLU_E_ARG, "more than 2^31-1 nonzeros");
-        auto small = [&](int s) {
-            const int64_t k = S.sn_start[s + 1] - S.sn_start[s], r = S.rows_ptr[s + 1] - S.rows_ptr[s];
-            return k <= NB && k + r <= front_small_limit();
-        };
+        // this rank assembles the entries of its own fronts; rank 0 also those of the top fronts
+        auto small = [&](int s) { return S.small[s] != 0 && S.owner[s] == h->rank; };
+        auto mine = [&](int s) { return S.owner[s] == h->rank || (S.owner[s] == -1 && h->rank == 0); };
         std::vector<int> a_ptr(nsn + 1, 0);
         for (int64_t t = 0; t < h->annz; ++t) if (small(S.a_sn[t])) ++a_ptr[S.a_sn[t] + 1];
         for (int s = 0; s < nsn; ++s) a_ptr[s + 1] += a_ptr[s];
         const int nsmall = a_ptr[nsn];
         std::vector<int> a_src(h->annz), a_row(h->annz), a_pos(nsmall), w(a_ptr.begin(), a_ptr.end() - 1);
-        std::vector<int64_t> dst_big(h->annz - nsmall);
+        std::vector<int64_t> dst_big(h->annz - nsmall);     // upper bound; nb entries are used
         int64_t nb = 0;
         for (int64_t t = 0; t < h->annz; ++t) {
             const int s = S.a_sn[t];
             int64_t o;
             if (small(s)) { o = w[s]++; a_pos[o] = S.a_loc[t]; }
-            else { o = nsmall + nb; dst_big[nb++] = S.a_dst[t]; }
+            else if (mine(s)) { o = nsmall + nb; dst_big[nb++] = S.a_dst[t]; }
+            else continue;
             a_src[o] = (int)t;
             a_row[o] = (int)h->Ai[t];
         }
@@ -340,7 +410,7 @@ int ensure_uploaded(smslu_handle_t h) {
     int *d_counters, *d_flag;
     if ((rc = dev_alloc(h, &d_lu, (size_t)S.lu_size))) return rc;
     if ((rc = dev_alloc(h, &d_cb, (size_t)S.cb_size))) return rc;
-    if ((rc = dev_alloc(h, &d_upd, (size_t)S.sum_r))) return rc;
+    if ((rc = dev_alloc(h, &d_upd, (size_t)(S.sum_r + h->vupd_len)))) return rc;
     if ((rc = dev_alloc(h, &d_flag, 1))) return rc;
     if ((rc = dev_alloc(h, &d_dinv, (size_t)n))) return rc;
     if ((rc = dev_alloc(h, &h->d_Rs, (size_t)n))) return rc;
@@ -436,11 +506,26 @@ int enqueue_refactor(smslu_handle_t h, const double* av, bool rs_given) {
     if ((rc = prof_begin(h, SMSLU_K_SCATTER))) return rc;
     CU(cudaMemsetAsync(h->cx.flag, 0x7f, sizeof(int), h->stream));   // 0x7f7f7f7f = clean
     CU(cudaMemsetAsync(h->cx.counters, 0, sizeof(int) * std::max<int64_t>(h->ncounters, 1), h->stream));
-    if (S.lu_big_size > 0) CU(cudaMemsetAsync(h->cx.lu, 0, sizeof(double) * S.lu_big_size, h->stream));
+    if (S.lu_top_size > 0) CU(cudaMemsetAsync(h->cx.lu, 0, sizeof(double) * S.lu_top_size, h->stream));
+    if (S.lu_big_end[h->rank] > S.lu_big_begin[h->rank])
+        CU(cudaMemsetAsync(h->cx.lu + S.lu_big_begin[h->rank], 0,
+                           sizeof(double) * (S.lu_big_end[h->rank] - S.lu_big_begin[h->rank]), h->stream));
+    if (S.cb_iface_size > 0) CU(cudaMemsetAsync(h->cx.cb, 0, sizeof(double) * S.cb_iface_size, h->stream));
     launch_scatter(h->stream, h->nnz_big, h->d_big_dst, h->d_big_row, h->d_big_src, h->d_Rs, av, h->cx.lu);
     h->cur_av = av;
     if ((rc = prof_end(h))) return rc;
     if ((rc = run_schedule(h, h->fac, nullptr, nullptr))) return rc;
+    if (h->nranks > 1) {
+        // sum the subtrees' contributions to the top of the tree over NVLink, then factor the top
+        if ((rc = prof_begin(h, SMSLU_K_ALLREDUCE))) return rc;
+        NCCLCHK(ncclGroupStart());
+        if (S.lu_top_size > 0) NCCLCHK(ncclAllReduce(h->cx.lu, h->cx.lu, (size_t)S.lu_top_size, ncclDouble, ncclSum, h->comm, h->stream));
+        if (S.cb_iface_size > 0) NCCLCHK(ncclAllReduce(h->cx.cb, h->cx.cb, (size_t)S.cb_iface_size, ncclDouble, ncclSum, h->comm, h->stream));
+        NCCLCHK(ncclGroupEnd());
+        if ((rc = prof_end(h))) return rc;
+        if ((rc = run_schedule(h, h->fac_top, nullptr, nullptr))) return rc;
+        NCCLCHK(ncclAllReduce(h->cx.flag, h->cx.flag, 1, ncclInt, ncclMin, h->comm, h->stream));
+    }
     CU(cudaMemcpyAsync(h->h_flag, h->cx.flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     h->pending_refactor = true;
     return 0;
@@ -465,13 +550,40 @@ int finish_refactor(smslu_handle_t h) {
     return 0;
 }
 
+// Partitioned forward solve across the cut: sum this rank's subtree contributions per interface front
+// into the virtual children's vectors, all-reduce them, then run the top of the tree.
+int enqueue_top_forward(smslu_handle_t h) {
+    int rc;
+    if ((rc = prof_begin(h, SMSLU_K_ALLREDUCE))) return rc;
+    launch_vgather(h->stream, h->cx, h->d_vtasks, h->nvtasks, h->d_vlist);
+    if (h->vupd_len > 0)
+        NCCLCHK(ncclAllReduce(h->cx.upd + h->vupd_off, h->cx.upd + h->vupd_off, (size_t)h->vupd_len, ncclDouble, ncclSum, h->comm, h->stream));
+    if ((rc = prof_end(h))) return rc;
+    return run_schedule(h, h->fwd_top, h->d_w, h->d_z);
+}
+
+// Every rank holds the solution on its own columns and on the top columns; zero the rest (rank 0
+// keeps the top) and sum over ranks so that every rank ends with the full vector.
+int enqueue_gather_solution(smslu_handle_t h) {
+    int rc;
+    if ((rc = prof_begin(h, SMSLU_K_ALLREDUCE))) return rc;
+    launch_mask_owned(h->stream, h->n, h->d_colowner, h->rank, h->d_z);
+    NCCLCHK(ncclAllReduce(h->d_z, h->d_z, (size_t)h->n, ncclDouble, ncclSum, h->comm, h->stream));
+    return prof_end(h);
+}
+
 int enqueue_solve(smslu_handle_t h, double* xdev, const double* bdev) {
     int rc;
     if ((rc = prof_begin(h, SMSLU_K_PERMUTE))) return rc;
     launch_permute_scale(h->stream, h->n, h->d_p, h->d_Rs, bdev, h->d_w);
     if ((rc = prof_end(h))) return rc;
     if ((rc = run_schedule(h, h->fwd, h->d_w, h->d_z))) return rc;
+    if (h->nranks > 1) {
+        if ((rc = enqueue_top_forward(h))) return rc;
+        if ((rc = run_schedule(h, h->bwd_top, nullptr, h->d_z))) return rc;
+    }
     if ((rc = run_schedule(h, h->bwd, nullptr, h->d_z))) return rc;
+    if (h->nranks > 1 && (rc = enqueue_gather_solution(h))) return rc;
     if ((rc = prof_begin(h, SMSLU_K_UNPERMUTE))) return rc;
     launch_unpermute(h->stream, h->n, h->d_q, h->d_z, xdev);
     if ((rc = prof_end(h))) return rc;
@@ -518,6 +630,9 @@ int smslu_create(smslu_handle_t* hp, int64_t n, const int64_t* colptr, const int
     if (!h) return SMSLU_E_OOM;
     if (opts) h->opt = *opts; else smslu_options_default(&h->opt);
     if (h->opt.max_width <= 0 || h->opt.max_width > KMAX) h->opt.max_width = KMAX;
+    h->nranks = std::max(1, (int)h->opt.nranks);
+    h->rank = h->nranks > 1 ? (int)h->opt.rank : 0;
+    if (h->rank < 0 || h->rank >= h->nranks) { delete h; return SMSLU_E_ARG; }
     h->n = (int)n;
     h->index_base = index_base;
     h->annz = colptr[n] - index_base;
@@ -546,6 +661,7 @@ int smslu_analyze(smslu_handle_t h, const int64_t* p, const int64_t* q) {
     o.small_front_max = front_small_limit();
     o.small_k_max = NB;
     o.relax_width = NB;
+    o.nranks = h->nranks;
     std::vector<int> pp, qq;
     if (o.ordering == ORD_GIVEN) {
         if (!p || !q) return fail(h, SMSLU_E_ARG, "ordering GIVEN needs p and q");
@@ -566,7 +682,38 @@ int smslu_analyze(smslu_handle_t h, const int64_t* p, const int64_t* q) {
     st.max_pivot_block = S.max_k; st.max_children = S.max_children; st.sum_rows = S.sum_r;
     st.lu_pool_doubles = S.lu_size; st.cb_pool_doubles = S.cb_size;
     st.flops_exact = S.flops_exact; st.flops_stored = S.flops_stored;
+    st.n_top_supernodes = st.n_local_supernodes = 0;
+    for (int s2 = 0; s2 < S.nsn; ++s2) {
+        if (S.owner[s2] == -1) ++st.n_top_supernodes;
+        if (S.owner[s2] == h->rank) ++st.n_local_supernodes;
+    }
+    int64_t vlen = 0;
+    for (int s2 = 0; s2 < S.nsn; ++s2)
+        if (S.iface[s2]) vlen += (S.sn_start[s2 + 1] - S.sn_start[s2]) + (S.rows_ptr[s2 + 1] - S.rows_ptr[s2]);
+    st.allreduce_doubles_refactor = h->nranks > 1 ? S.lu_top_size + S.cb_iface_size : 0;
+    st.allreduce_doubles_solve = h->nranks > 1 ? vlen + S.n : 0;
     st.ms_analyze = now_ms() - t0;
+    return 0;
+}
+
+int smslu_comm_unique_id(void* id, int64_t nbytes) {
+    if (!id || nbytes < (int64_t)sizeof(ncclUniqueId)) return SMSLU_E_ARG;
+    ncclUniqueId u;
+    if (ncclGetUniqueId(&u) != ncclSuccess) return SMSLU_E_NCCL;
+    memcpy(id, &u, sizeof(u));
+    return 0;
+}
+
+int smslu_comm_init(smslu_handle_t h, const void* id, int64_t nbytes) {
+    if (!h || !id || nbytes < (int64_t)sizeof(ncclUniqueId)) return SMSLU_E_ARG;
+    if (h->nranks <= 1) return 0;
+    if (h->comm) return fail(h, SMSLU_E_ARG, "communicator already initialised");
+    if (h->opt.device >= 0) h->device = h->opt.device;
+    else CU(cudaGetDevice(&h->device));
+    CU(cudaSetDevice(h->device));
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof(u));
+    NCCLCHK(ncclCommInitRank(&h->comm, h->nranks, u, h->rank));
     return 0;
 }
 
@@ -704,10 +851,13 @@ static int tri_solve(smslu_handle_t h, double* x, int64_t nx, int64_t nrhs, int6
         if (lower) {
             CU(cudaMemcpyAsync(h->d_w, xc, sizeof(double) * n, cudaMemcpyDefault, h->stream));
             if ((rc = run_schedule(h, h->fwd, h->d_w, h->d_z))) return rc;
+            if (h->nranks > 1 && (rc = enqueue_top_forward(h))) return rc;
         } else {
             CU(cudaMemcpyAsync(h->d_z, xc, sizeof(double) * n, cudaMemcpyDefault, h->stream));
+            if (h->nranks > 1 && (rc = run_schedule(h, h->bwd_top, nullptr, h->d_z))) return rc;
             if ((rc = run_schedule(h, h->bwd, nullptr, h->d_z))) return rc;
         }
+        if (h->nranks > 1 && (rc = enqueue_gather_solution(h))) return rc;
         CU(cudaMemcpyAsync(xc, h->d_z, sizeof(double) * n, cudaMemcpyDefault, h->stream));
         CU(cudaStreamSynchronize(h->stream));
     }
@@ -748,8 +898,24 @@ int smslu_get_factors(smslu_handle_t h, int64_t* lp, int64_t* li, double* lx, in
         lu.resize((size_t)S.lu_size);
         CU(cudaMemcpy(lu.data(), h->cx.lu, sizeof(double) * S.lu_size, cudaMemcpyDeviceToHost));
     }
+    std::vector<char> col_mine;
+    if (h->nranks > 1) {
+        // this rank's share: its own supernodes, plus the (replicated) top on rank 0; zero elsewhere, so
+        // that the value arrays summed over the ranks are F.L and F.U
+        col_mine.assign(S.n, 0);
+        for (int s2 = 0; s2 < S.nsn; ++s2) {
+            const bool mine = S.owner[s2] == h->rank || (S.owner[s2] == -1 && h->rank == 0);
+            const int64_t k = S.sn_start[s2 + 1] - S.sn_start[s2], r = S.rows_ptr[s2 + 1] - S.rows_ptr[s2];
+            if (mine) { for (int j = S.sn_start[s2]; j < S.sn_start[s2 + 1]; ++j) col_mine[j] = 1; continue; }
+            if (!lu.empty()) {
+                std::fill(lu.begin() + S.Loff[s2], lu.begin() + S.Loff[s2] + (k + r) * k, 0.0);
+                std::fill(lu.begin() + S.Uoff[s2], lu.begin() + S.Uoff[s2] + r * k, 0.0);
+            }
+        }
+    }
     export_factors(S, h->ex_ptr, h->ex_idx, lu.empty() ? nullptr : lu.data(), index_base, lp, li,
-                   lu.empty() ? nullptr : lx, up, ui, lu.empty() ? nullptr : ux);
+                   lu.empty() ? nullptr : lx, up, ui, lu.empty() ? nullptr : ux,
+                   col_mine.empty() ? nullptr : col_mine.data());
     return 0;
 }
 
@@ -777,6 +943,7 @@ int smslu_get_symbolic(smslu_handle_t h, int64_t* sn_start, int64_t* rows_ptr, i
 
 int smslu_destroy(smslu_handle_t h) {
     if (!h) return 0;
+    if (h->comm) { cudaSetDevice(h->device); ncclCommDestroy(h->comm); h->comm = nullptr; }
     if (h->uploaded || h->stream) {
         cudaSetDevice(h->device);
         if (h->stream) cudaStreamSynchronize(h->stream);

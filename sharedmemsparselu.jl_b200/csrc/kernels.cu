@@ -665,6 +665,33 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_bwd(DevCtx cx, const int4* __
     if (tid < k) x[F.c0 + tid] = part[tid];
 }
 
+// ------------------------------------------------------------------ partitioned solves
+// One CTA per interface front: sum the update vectors of this rank's subtree roots below it into the
+// front's virtual child (rel = identity), root by root in ascending order.
+// task: x = interface front, y = virtual child, [z, w) = range in vlist.
+__global__ void __launch_bounds__(256) k_vgather(DevCtx cx, const int4* __restrict__ tasks, const int* __restrict__ vlist) {
+    const int4 tk = tasks[blockIdx.x];
+    double* __restrict__ v = cx.upd + cx.rows_ptr[tk.y];
+    const int64_t fs = cx.rows_ptr[tk.y + 1] - cx.rows_ptr[tk.y];
+    for (int64_t i = threadIdx.x; i < fs; i += 256) v[i] = 0.0;
+    __syncthreads();
+    for (int ci = tk.z; ci < tk.w; ++ci) {
+        const int c = vlist[ci];
+        const int64_t rc = cx.rows_ptr[c + 1] - cx.rows_ptr[c];
+        const int* __restrict__ rel = cx.rel + cx.rows_ptr[c];
+        const double* __restrict__ uc = cx.upd + cx.rows_ptr[c];
+        for (int64_t a = threadIdx.x; a < rc; a += 256) v[rel[a]] += uc[a];
+        __syncthreads();
+    }
+}
+// keep the entries this rank is responsible for (its own columns; the top columns on rank 0)
+__global__ void k_mask_owned(int n, const int* __restrict__ colowner, int rank, double* __restrict__ z) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int o = colowner[i];
+    if (!(o == rank || (o == -1 && rank == 0))) z[i] = 0.0;
+}
+
 // ------------------------------------------------------------------ solves, small fronts
 // One warp per front (k <= 32, f <= SMALL_F_MAX), FPC fronts per CTA, no block-wide barriers.
 // Forward: v = [w[cols]; 0] + children's update vectors (gathered through rel, child by child),
@@ -790,6 +817,12 @@ void launch_front_small(cudaStream_t st, const DevCtx& cx, const int4* tasks, in
         k_small_factor<64, 2, 1><<<ntasks, 128, sizeof(double) * small_group_doubles(64), st>>>(cx, tasks, ntasks, 64, av, Rs);
     else
         k_small_factor<96, 3, 1><<<ntasks, 288, sizeof(double) * small_group_doubles(96), st>>>(cx, tasks, ntasks, 96, av, Rs);
+}
+void launch_vgather(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const int* vlist) {
+    if (ntasks > 0) k_vgather<<<ntasks, 256, 0, st>>>(cx, tasks, vlist);
+}
+void launch_mask_owned(cudaStream_t st, int n, const int* colowner, int rank, double* z) {
+    k_mask_owned<<<(n + 255) / 256, 256, 0, st>>>(n, colowner, rank, z);
 }
 void launch_small_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const double* win, double* zout) {
     if (ntasks > 0) k_small_fwd<SOLVE_FPC><<<(ntasks + SOLVE_FPC - 1) / SOLVE_FPC, 32 * SOLVE_FPC, 0, st>>>(cx, tasks, ntasks, win, zout);

@@ -60,6 +60,8 @@ void launch_zero_cb(cudaStream_t st, const DevCtx& cx, const int4* tasks, int nt
 void launch_extend_add(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks);
 void launch_front_small(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int fmax,
                         const double* av, const double* Rs);
+void launch_vgather(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const int* vlist);
+void launch_mask_owned(cudaStream_t st, int n, const int* colowner, int rank, double* z);
 void launch_small_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const double* win, double* zout);
 void launch_small_bwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, double* x);
 void launch_panel(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int g);

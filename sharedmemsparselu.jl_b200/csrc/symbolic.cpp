@@ -595,6 +595,66 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
         std::vector<int> w(S.level_ptr.begin(), S.level_ptr.end() - 1);
         for (int s = 0; s < nsn; ++s) S.level_sn[w[S.sn_level[s]]++] = s;
     }
+    // ---------------------------------------------------------------- 7b. partition over GPUs
+    // owner[s] = rank that factors supernode s, or -1 for the "top" of the tree, which every rank
+    // factors redundantly after the contributions of the subtrees have been summed (all-reduce).
+    // Greedy: start from the roots, repeatedly move the heaviest remaining subtree root into the top
+    // set and replace it by its children; keep the cut with the smallest  top work + heaviest rank.
+    const int NR = std::max(1, opt.nranks);
+    S.nranks = NR;
+    S.owner.assign(nsn, 0);
+    S.iface.assign(nsn, 0);
+    if (NR > 1) {
+        std::vector<double> wsub(nsn, 0.0), wself(nsn);
+        for (int s = 0; s < nsn; ++s) {
+            const double kd = S.sn_start[s + 1] - S.sn_start[s], rd = (double)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
+            wself[s] = 2.0 * kd * kd * kd / 3.0 + 2.0 * kd * kd * rd + 2.0 * kd * rd * rd + 1.0e5;
+        }
+        for (int s = 0; s < nsn; ++s) {          // children precede parents (postorder)
+            wsub[s] += wself[s];
+            if (S.sn_parent[s] != -1) wsub[S.sn_parent[s]] += wsub[s];
+        }
+        auto lpt = [&](const std::vector<int>& q, std::vector<int>* assign) {
+            std::vector<int> ord(q.size());
+            std::iota(ord.begin(), ord.end(), 0);
+            std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return wsub[q[a]] > wsub[q[b]]; });
+            std::vector<double> load(NR, 0.0);
+            if (assign) assign->assign(q.size(), 0);
+            for (int t : ord) {
+                int best = 0;
+                for (int g = 1; g < NR; ++g) if (load[g] < load[best]) best = g;
+                load[best] += wsub[q[t]];
+                if (assign) (*assign)[t] = best;
+            }
+            return *std::max_element(load.begin(), load.end());
+        };
+        std::vector<int> q, best_q;
+        std::vector<char> is_top(nsn, 0), best_top;
+        for (int s = 0; s < nsn; ++s) if (S.sn_parent[s] == -1) q.push_back(s);
+        double top_w = 0.0, best_cost = top_w + lpt(q, nullptr);
+        best_q = q; best_top = is_top;
+        for (int it = 0; it < 96 * NR && !q.empty(); ++it) {
+            int hi = -1;
+            for (size_t t = 0; t < q.size(); ++t)
+                if (S.child_ptr[q[t] + 1] > S.child_ptr[q[t]] && (hi < 0 || wsub[q[t]] > wsub[q[hi]])) hi = (int)t;
+            if (hi < 0) break;
+            const int s = q[hi];
+            q.erase(q.begin() + hi);
+            is_top[s] = 1;
+            top_w += wself[s];
+            for (int u = S.child_ptr[s]; u < S.child_ptr[s + 1]; ++u) q.push_back(S.child_idx[u]);
+            const double cost = top_w + lpt(q, nullptr);
+            if (cost < best_cost) { best_cost = cost; best_q = q; best_top = is_top; }
+        }
+        std::vector<int> assign;
+        lpt(best_q, &assign);
+        for (int s = 0; s < nsn; ++s) S.owner[s] = best_top[s] ? -1 : -2;
+        for (size_t t = 0; t < best_q.size(); ++t) S.owner[best_q[t]] = assign[t];
+        for (int s = nsn - 1; s >= 0; --s)       // parents precede children in this sweep
+            if (S.owner[s] == -2) S.owner[s] = S.owner[S.sn_parent[s]];
+        for (int s = 0; s < nsn; ++s)
+            if (S.owner[s] >= 0 && S.sn_parent[s] != -1 && S.owner[S.sn_parent[s]] == -1) S.iface[S.sn_parent[s]] = 1;
+    }
     // ---------------------------------------------------------------- 8. storage plan
     S.Loff.resize(nsn);
     S.Uoff.resize(nsn);
@@ -602,16 +662,23 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
     S.nnzL_stored = 0;
     S.flops_stored = 0;
     S.sum_r = (int64_t)S.rows.size();
-    auto is_small = [&](int s) {
+    S.small.assign(nsn, 0);
+    for (int s = 0; s < nsn; ++s) {
         const int64_t k = S.sn_start[s + 1] - S.sn_start[s], r = S.rows_ptr[s + 1] - S.rows_ptr[s];
-        return k <= opt.small_k_max && k + r <= opt.small_front_max;
-    };
-    // Big fronts first: their panels are zero-filled and scattered into in HBM at the start of every
-    // refactorization; the small fronts behind them are assembled in shared memory and written once.
+        S.small[s] = S.owner[s] >= 0 && k <= opt.small_k_max && k + r <= opt.small_front_max;
+    }
+    auto is_small = [&](int s) { return S.small[s] != 0; };
+    // Pool order: top fronts (summed across ranks in one all-reduce), then per rank its big fronts
+    // (zero-filled and scattered into in HBM at the start of every refactorization), then per rank
+    // its small fronts (assembled in shared memory, written exactly once, never zero-filled).
     int64_t off = 0;
-    for (int pass = 0; pass < 2; ++pass) {
+    S.lu_big_begin.assign(NR, 0); S.lu_big_end.assign(NR, 0);
+    for (int pass = 0; pass < 1 + 2 * NR; ++pass) {
+        const int want_owner = pass == 0 ? -1 : (pass - 1) % NR;
+        const bool want_small = pass > NR;
+        if (pass >= 1 && pass <= NR) S.lu_big_begin[want_owner] = off;
         for (int s = 0; s < nsn; ++s) {
-            if (is_small(s) != (pass == 1)) continue;
+            if (S.owner[s] != want_owner || (pass > 0 && is_small(s) != want_small)) continue;
             int64_t k = S.sn_start[s + 1] - S.sn_start[s], r = S.rows_ptr[s + 1] - S.rows_ptr[s], f = k + r;
             S.Loff[s] = off; off = align2(off + f * k);
             S.Uoff[s] = off; off = align2(off + r * k);
@@ -621,7 +688,9 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
             double kd = (double)k, rd = (double)r;
             S.flops_stored += 2.0 * kd * kd * kd / 3.0 + 2.0 * kd * kd * rd + 2.0 * kd * rd * rd;
         }
-        if (pass == 0) S.lu_big_size = off;
+        if (pass == 0) S.lu_top_size = off;
+        if (pass >= 1 && pass <= NR) S.lu_big_end[want_owner] = off;
+        if (pass == NR) S.lu_big_size = off;
     }
     S.lu_size = off;
     // direct-write eligibility
@@ -630,8 +699,9 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
     for (int c = 0; c < nsn; ++c) {
         const int s = S.sn_parent[c];
         if (s == -1) continue;
-        const int64_t kc = S.sn_start[c + 1] - S.sn_start[c], rc = S.rows_ptr[c + 1] - S.rows_ptr[c];
+        const int64_t rc = S.rows_ptr[c + 1] - S.rows_ptr[c];
         if (is_small(c) || is_small(s)) continue;   // small fronts are assembled in shared memory
+        if (S.owner[c] != S.owner[s]) continue;     // contributions that cross the partition are summed by all-reduce
         if (S.child_ptr[s + 1] - S.child_ptr[s] != 1) continue;
         S.direct[c] = 1;
         const int64_t ks = S.sn_start[s + 1] - S.sn_start[s], rs = S.rows_ptr[s + 1] - S.rows_ptr[s];
@@ -640,12 +710,23 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
         if (rc - inside == rs) S.cb_assigned[s] = 1;
     }
     {
-        Arena arena;
+        // contribution blocks of the interface fronts (top fronts with children below the cut) live in a
+        // permanent, contiguous region at the start of the pool: they are zero-filled at the start of a
+        // refactorization, receive the subtrees' contributions and are all-reduced in one call.
+        int64_t ioff = 0;
         std::vector<char> have(nsn, 0);
+        for (int s = 0; s < nsn; ++s)
+            if (S.iface[s]) {
+                int64_t r = S.rows_ptr[s + 1] - S.rows_ptr[s];
+                S.CBoff[s] = ioff; ioff += align2(r * r);
+                have[s] = 1;
+            }
+        S.cb_iface_size = ioff;
+        Arena arena;
         auto need = [&](int s) {
             if (have[s]) return;
             int64_t r = S.rows_ptr[s + 1] - S.rows_ptr[s];
-            S.CBoff[s] = arena.alloc(align2(r * r));
+            S.CBoff[s] = ioff + arena.alloc(align2(r * r));
             have[s] = 1;
         };
         for (int l = 0; l < S.nlevels; ++l) {
@@ -657,12 +738,13 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
                 int s = S.level_sn[t];
                 for (int u = S.child_ptr[s]; u < S.child_ptr[s + 1]; ++u) {
                     int c = S.child_idx[u];
+                    if (S.iface[c]) continue;
                     int64_t r = S.rows_ptr[c + 1] - S.rows_ptr[c];
-                    arena.release(S.CBoff[c], align2(r * r));
+                    arena.release(S.CBoff[c] - ioff, align2(r * r));
                 }
             }
         }
-        S.cb_size = arena.top();
+        S.cb_size = ioff + arena.top();
     }
     // ---------------------------------------------------------------- 9. A -> factor scatter map
     S.a_dst.resize(S.annz);
@@ -733,7 +815,7 @@ namespace smslu {
 
 void export_factors(const Symbolic& S, const std::vector<int64_t>& ptr, const std::vector<int>& idx,
                     const double* lu, int64_t base, int64_t* Lp, int64_t* Li, double* Lx,
-                    int64_t* Up, int64_t* Ui, double* Ux) {
+                    int64_t* Up, int64_t* Ui, double* Ux, const char* col_mine) {
     const int n = S.n;
     // position of row i inside the front of supernode s
     auto front_pos = [&](int s, int i) -> int64_t {
@@ -756,7 +838,7 @@ void export_factors(const Symbolic& S, const std::vector<int64_t>& ptr, const st
             const int64_t k = S.sn_start[s + 1] - c0, f = k + (S.rows_ptr[s + 1] - S.rows_ptr[s]);
             const double* col = lu + S.Loff[s] + (int64_t)(j - c0) * f;
             if (Li) Li[w] = j + base;
-            if (Lx) Lx[w] = 1.0;
+            if (Lx) Lx[w] = (!col_mine || col_mine[j]) ? 1.0 : 0.0;
             ++w;
             for (int64_t t = ptr[j]; t < ptr[j + 1]; ++t, ++w) {
                 if (Li) Li[w] = idx[t] + base;

@@ -29,6 +29,7 @@ struct SymOptions {
     double relax_f1 = 0.5, relax_f2 = 0.15, relax_f3 = 0.05;
     int dense_factor = 10;        // vertices with degree > dense_factor*sqrt(n) are ordered last
     int small_front_max = 96;     // fronts up to this size run in the fused shared-memory kernel
+    int nranks = 1;               // GPUs the tree is partitioned over (one process per GPU)
 };
 
 struct Symbolic {
@@ -60,7 +61,15 @@ struct Symbolic {
     // U panel r x k column-major (ld = r) holding U12 transposed.
     std::vector<int64_t> Loff, Uoff;
     int64_t lu_size = 0;
-    int64_t lu_big_size = 0;          // [0, lu_big_size) holds the big fronts, the small ones follow
+    int64_t lu_big_size = 0;          // [0, lu_big_size) holds the top and big fronts, the small ones follow
+    // partition over nranks GPUs (nranks == 1: everything is owned by rank 0, no top set)
+    int nranks = 1;
+    std::vector<int> owner;           // rank that factors the supernode; -1 = top of the tree (replicated)
+    std::vector<char> iface;          // top front that receives contributions from below the cut
+    std::vector<char> small;          // handled by the shared-memory kernels (never a top front)
+    int64_t lu_top_size = 0;          // [0, lu_top_size): panels of the top fronts (all-reduced)
+    std::vector<int64_t> lu_big_begin, lu_big_end;   // per rank: its big fronts' panels
+    int64_t cb_iface_size = 0;        // [0, cb_iface_size): contribution blocks of the interface fronts
     // contribution blocks r x r (ld = r), lifetime level(s)..level(parent(s))
     std::vector<int64_t> CBoff;
     int64_t cb_size = 0;
@@ -89,8 +98,9 @@ void exact_structure(const Symbolic& S, const int64_t* Ap, const int64_t* Ai,
 
 // Gather F.L / F.U (CSC, sorted rows, exact pattern, L with explicit unit diagonal) out of a host
 // copy of the factor storage.  colptr arrays have n+1 entries; any output may be null.
+// col_mine (optional, per permuted column): L's unit diagonal is emitted as 0 where it is 0.
 void export_factors(const Symbolic& S, const std::vector<int64_t>& ptr, const std::vector<int>& idx,
                     const double* lu, int64_t base, int64_t* Lp, int64_t* Li, double* Lx,
-                    int64_t* Up, int64_t* Ui, double* Ux);
+                    int64_t* Up, int64_t* Ui, double* Ux, const char* col_mine = nullptr);
 
 }  // namespace smslu

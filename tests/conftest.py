@@ -79,6 +79,18 @@ class HostExec:
         L.hx_create.restype = C.c_void_p
         L.hx_create.argtypes = [C.c_longlong, i64p, i64p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                 C.c_void_p, C.c_void_p]
+        L.hx_create2.restype = C.c_void_p
+        L.hx_create2.argtypes = L.hx_create.argtypes + [C.c_int]
+        L.hx_owner.argtypes = [C.c_void_p, i64p]
+        L.hx_buffer.restype = C.c_void_p
+        L.hx_buffer.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_longlong)]
+        L.hx_factor_phase.restype = C.c_longlong
+        L.hx_factor_phase.argtypes = [C.c_void_p, f64p, C.c_void_p, C.c_int, C.c_int]
+        L.hx_lsolve_phase.argtypes = [C.c_void_p, f64p, C.c_int, C.c_int]
+        L.hx_rsolve_phase.argtypes = [C.c_void_p, f64p, C.c_int, C.c_int]
+        L.hx_mask_owned.argtypes = [C.c_void_p, f64p, C.c_int]
+        L.hx_permute_scale.argtypes = [C.c_void_p, f64p, f64p]
+        L.hx_unpermute.argtypes = [C.c_void_p, f64p, f64p]
         L.hx_info.argtypes = [C.c_void_p, i64p, f64p]
         L.hx_perm.argtypes = [C.c_void_p, i64p, i64p]
         L.hx_factor.restype = C.c_longlong
@@ -106,7 +118,7 @@ class HostExec:
             info = np.zeros(16, np.int64); fl = np.zeros(2)
             self.L.hx_info(h, info, fl)
             keys = ("n", "nsn", "nlevels", "lu_size", "cb_size", "nnzL_exact", "nnzL_stored", "sum_r",
-                    "max_front", "max_k", "max_children")
+                    "max_front", "max_k", "max_children", "nranks", "lu_top_size", "cb_iface_size", "vbuf_len", "ntop")
             out = dict(zip(keys, (int(v) for v in info)))
             out["flops_exact"], out["flops_stored"] = float(fl[0]), float(fl[1])
             po = np.zeros(n, np.int64); qo = np.zeros(n, np.int64)
@@ -132,6 +144,67 @@ class HostExec:
             return out
         finally:
             self.L.hx_free(h)
+
+
+class PartitionedWalk:
+    """One rank's view of the partitioned factorization / solve, walked on the CPU (tests/hostexec.cpp).
+    `allreduce(array)` must sum a float64 numpy array in place over the ranks (gloo in the tests)."""
+
+    def __init__(self, hx, A, nranks, rank, allreduce, **kw):
+        import scipy.sparse as sp
+        A = sp.csc_matrix(A); A.sort_indices()
+        self.L, self.rank, self.nranks, self.allreduce = hx.L, rank, nranks, allreduce
+        self.n = n = A.shape[0]
+        self.Ap = A.indptr.astype(np.int64); self.Ai = A.indices.astype(np.int64)
+        self.h = self.L.hx_create2(n, self.Ap, self.Ai, kw.get("ordering", 0), None, kw.get("leaf", 0), 1,
+                                   kw.get("maxw", 0), None, None, nranks)
+        assert self.h
+        info = np.zeros(16, np.int64); fl = np.zeros(2)
+        self.L.hx_info(self.h, info, fl)
+        self.info = dict(zip(("n", "nsn", "nlevels", "lu_size", "cb_size", "nnzL_exact", "nnzL_stored", "sum_r",
+                              "max_front", "max_k", "max_children", "nranks", "lu_top_size", "cb_iface_size",
+                              "vbuf_len", "ntop"), (int(v) for v in info)))
+        self.owner = np.zeros(self.info["nsn"], np.int64)
+        self.L.hx_owner(self.h, self.owner)
+        self.p = np.zeros(n, np.int64); self.q = np.zeros(n, np.int64)
+        self.L.hx_perm(self.h, self.p, self.q)
+
+    def _view(self, which, count):
+        ln = C.c_longlong()
+        ptr = self.L.hx_buffer(self.h, which, C.byref(ln))
+        assert count <= ln.value
+        if count == 0:
+            return np.zeros(0)
+        return np.ctypeslib.as_array((C.c_double * count).from_address(ptr))
+
+    def factor(self, Ax, Rs):
+        Ax = np.ascontiguousarray(Ax, np.float64); Rs = np.ascontiguousarray(Rs, np.float64)
+        self.L.hx_factor_phase(self.h, Ax, Rs.ctypes.data_as(C.c_void_p), self.rank, 0)
+        if self.nranks > 1:
+            self.allreduce(self._view(0, self.info["lu_top_size"]))      # panels of the top fronts
+            self.allreduce(self._view(1, self.info["cb_iface_size"]))    # interface contribution blocks
+            return int(self.L.hx_factor_phase(self.h, Ax, Rs.ctypes.data_as(C.c_void_p), self.rank, 1))
+        return 0
+
+    def solve(self, b):
+        n = self.n
+        w = np.zeros(n); x = np.zeros(n)
+        self.L.hx_permute_scale(self.h, np.ascontiguousarray(b, np.float64), w)
+        self.L.hx_lsolve_phase(self.h, w, self.rank, 0)
+        if self.nranks > 1:
+            self.allreduce(self._view(2, self.info["vbuf_len"]))
+            self.L.hx_lsolve_phase(self.h, w, self.rank, 1)
+            self.L.hx_rsolve_phase(self.h, w, self.rank, 1)
+        self.L.hx_rsolve_phase(self.h, w, self.rank, 0)
+        if self.nranks > 1:
+            self.L.hx_mask_owned(self.h, w, self.rank)
+            self.allreduce(w)
+        self.L.hx_unpermute(self.h, w, x)
+        return x
+
+    def close(self):
+        if self.h:
+            self.L.hx_free(self.h); self.h = None
 
 
 @pytest.fixture(scope="session")

@@ -17,14 +17,17 @@ using namespace smslu;
 struct HX {
     Symbolic S;
     std::vector<int64_t> Ap, Ai;
-    std::vector<double> lu, cb, Rs, upd;
+    std::vector<double> lu, cb, Rs, upd, vbuf;
+    std::vector<char> zeroed;
+    std::vector<int64_t> voff;      // per supernode: offset of its slice of vbuf (interface fronts), else -1
+    int64_t bad = -1;
     std::string err;
 };
 
 extern "C" {
 
-void* hx_create(int64_t n, const int64_t* Ap, const int64_t* Ai, int ordering, const int* grid,
-                int nd_leaf, int relax, int max_width, const int64_t* p, const int64_t* q) {
+void* hx_create2(int64_t n, const int64_t* Ap, const int64_t* Ai, int ordering, const int* grid,
+                 int nd_leaf, int relax, int max_width, const int64_t* p, const int64_t* q, int nranks) {
     HX* h = new HX();
     h->Ap.assign(Ap, Ap + n + 1);
     h->Ai.assign(Ai, Ai + Ap[n]);
@@ -34,20 +37,37 @@ void* hx_create(int64_t n, const int64_t* Ap, const int64_t* Ai, int ordering, c
     if (nd_leaf > 0) o.nd_leaf = nd_leaf;
     o.relax = relax;
     if (max_width > 0) o.max_width = max_width;
+    o.nranks = nranks > 0 ? nranks : 1;
     std::vector<int> pp, qq;
     if (p && q) { pp.assign(p, p + n); qq.assign(q, q + n); }
     int rc = analyze((int)n, Ap, Ai, pp.empty() ? nullptr : pp.data(), qq.empty() ? nullptr : qq.data(), o, h->S, h->err);
     if (rc != 0) { fprintf(stderr, "hx_create: %s\n", h->err.c_str()); delete h; return nullptr; }
+    const Symbolic& S = h->S;
+    h->voff.assign(S.nsn, -1);
+    int64_t v = 0;
+    for (int s = 0; s < S.nsn; ++s)
+        if (S.iface[s]) { h->voff[s] = v; v += (S.sn_start[s + 1] - S.sn_start[s]) + (S.rows_ptr[s + 1] - S.rows_ptr[s]); }
+    h->vbuf.assign(v, 0.0);
     return h;
+}
+
+void* hx_create(int64_t n, const int64_t* Ap, const int64_t* Ai, int ordering, const int* grid,
+                int nd_leaf, int relax, int max_width, const int64_t* p, const int64_t* q) {
+    return hx_create2(n, Ap, Ai, ordering, grid, nd_leaf, relax, max_width, p, q, 1);
 }
 
 void hx_free(void* hv) { delete (HX*)hv; }
 
-// info: n, nsn, nlevels, lu_size, cb_size, nnzL_exact, nnzL_stored, sum_r, max_front, max_k, max_children
+// info: n, nsn, nlevels, lu_size, cb_size, nnzL_exact, nnzL_stored, sum_r, max_front, max_k, max_children,
+//       nranks, lu_top_size, cb_iface_size, vbuf length, number of top supernodes
 void hx_info(void* hv, int64_t* out, double* flops) {
-    const Symbolic& S = ((HX*)hv)->S;
+    HX* h = (HX*)hv;
+    const Symbolic& S = h->S;
+    int64_t ntop = 0;
+    for (int s = 0; s < S.nsn; ++s) ntop += S.owner[s] == -1;
     int64_t v[] = {S.n, S.nsn, S.nlevels, S.lu_size, S.cb_size, S.nnzL_exact, S.nnzL_stored,
-                   S.sum_r, S.max_front, S.max_k, S.max_children};
+                   S.sum_r, S.max_front, S.max_k, S.max_children,
+                   S.nranks, S.lu_top_size, S.cb_iface_size, (int64_t)h->vbuf.size(), ntop};
     memcpy(out, v, sizeof(v));
     flops[0] = S.flops_exact;
     flops[1] = S.flops_stored;
@@ -58,23 +78,50 @@ void hx_perm(void* hv, int64_t* p, int64_t* q) {
     for (int k = 0; k < S.n; ++k) { p[k] = S.p[k]; q[k] = S.q[k]; }
 }
 
-// Numeric multifrontal factorization, level by level, children in ascending order.
-// Returns the permuted column of the first zero/non-finite pivot, or -1.
-int64_t hx_factor(void* hv, const double* Ax, const double* Rs) {
+void hx_owner(void* hv, int64_t* owner) {
+    const Symbolic& S = ((HX*)hv)->S;
+    for (int s = 0; s < S.nsn; ++s) owner[s] = S.owner[s];
+}
+
+// raw views for the exchange steps of the partitioned walk: 0 = factor pool, 1 = contribution pool,
+// 2 = forward-solve interface vectors
+double* hx_buffer(void* hv, int which, int64_t* len) {
+    HX* h = (HX*)hv;
+    std::vector<double>& v = which == 0 ? h->lu : which == 1 ? h->cb : h->vbuf;
+    *len = (int64_t)v.size();
+    return v.data();
+}
+
+// One phase of the numeric multifrontal factorization as rank `rank` of the partition runs it:
+// phase 0 = the supernodes the rank owns (plus their contributions into top fronts), phase 1 = the
+// top of the tree (after the caller has summed lu[0:lu_top_size] and cb[0:cb_iface_size] over ranks).
+// With nranks == 1 phase 0 is the whole factorization.  Children in ascending order.
+// Returns the permuted column of the first zero/non-finite pivot met so far, or -1.
+int64_t hx_factor_phase(void* hv, const double* Ax, const double* Rs, int rank, int phase) {
     HX* h = (HX*)hv;
     const Symbolic& S = h->S;
     const int n = S.n;
-    h->Rs.assign(n, 1.0);
-    if (Rs) h->Rs.assign(Rs, Rs + n);
-    h->lu.assign(S.lu_size, 0.0);
-    h->cb.assign(S.cb_size, 0.0);
-    std::vector<char> zeroed(S.nsn, 0);
-    for (int c = 0; c < n; ++c)
-        for (int64_t t = h->Ap[c]; t < h->Ap[c + 1]; ++t) h->lu[S.a_dst[t]] += h->Rs[h->Ai[t]] * Ax[t];
-    int64_t bad = -1;
+    const int mine = phase == 0 ? rank : -1;
+    if (phase == 0) {
+        h->Rs.assign(n, 1.0);
+        if (Rs) h->Rs.assign(Rs, Rs + n);
+        h->lu.assign(S.lu_size, 0.0);
+        h->cb.assign(S.cb_size, 0.0);
+        h->zeroed.assign(S.nsn, 0);
+        h->bad = -1;
+        for (int c = 0; c < n; ++c)
+            for (int64_t t = h->Ap[c]; t < h->Ap[c + 1]; ++t) {
+                const int o = S.owner[S.a_sn[t]];
+                if (o == rank || (o == -1 && rank == 0)) h->lu[S.a_dst[t]] += h->Rs[h->Ai[t]] * Ax[t];
+            }
+    }
+    int64_t& bad = h->bad;
+    std::vector<char>& zeroed = h->zeroed;
     for (int l = 0; l < S.nlevels; ++l)
         for (int u = S.level_ptr[l]; u < S.level_ptr[l + 1]; ++u) {
             const int s = S.level_sn[u];
+            const bool own = S.owner[s] == mine;
+            if (!own && !(phase == 0 && S.owner[s] == -1)) continue;
             const int c0 = S.sn_start[s];
             const int64_t k = S.sn_start[s + 1] - c0, r = S.rows_ptr[s + 1] - S.rows_ptr[s], f = k + r;
             double* P = h->lu.data() + S.Loff[s];
@@ -82,12 +129,13 @@ int64_t hx_factor(void* hv, const double* Ax, const double* Rs) {
             double* C = h->cb.data() + S.CBoff[s];
             const bool has_children = S.child_ptr[s + 1] > S.child_ptr[s];
             // blocks that receive '+=' contributions are zeroed before the first one arrives: at
-            // this level for extend-add children, one level earlier for a direct child (done there)
-            if (has_children && !S.cb_assigned[s] && !zeroed[s]) { for (int64_t e = 0; e < r * r; ++e) C[e] = 0.0; zeroed[s] = 1; }
+            // this level for extend-add children, one level earlier for a direct child (done there);
+            // interface blocks were zeroed with the pool and arrive summed over the ranks
+            if (own && has_children && !S.cb_assigned[s] && !zeroed[s] && !S.iface[s]) { for (int64_t e = 0; e < r * r; ++e) C[e] = 0.0; zeroed[s] = 1; }
             // extend-add of the children that did not write directly
             for (int ci = S.child_ptr[s]; ci < S.child_ptr[s + 1]; ++ci) {
                 const int c = S.child_idx[ci];
-                if (S.direct[c]) continue;
+                if (S.direct[c] || S.owner[c] != mine) continue;
                 const int64_t rc = S.rows_ptr[c + 1] - S.rows_ptr[c];
                 const int* rel = S.rel.data() + S.rows_ptr[c];
                 const double* Cc = h->cb.data() + S.CBoff[c];
@@ -100,6 +148,7 @@ int64_t hx_factor(void* hv, const double* Ax, const double* Rs) {
                         else C[(ra - k) + (rb - k) * r] += v;
                     }
             }
+            if (!own) continue;
             // dense partial factorization of the front
             for (int64_t j = 0; j < k; ++j) {
                 const double piv = P[j + j * f];
@@ -148,19 +197,32 @@ int64_t hx_factor(void* hv, const double* Ax, const double* Rs) {
     return bad;
 }
 
-void hx_lsolve(void* hv, double* x) {
+int64_t hx_factor(void* hv, const double* Ax, const double* Rs) { return hx_factor_phase(hv, Ax, Rs, 0, 0); }
+
+// Forward substitution, one phase (see hx_factor_phase).  Phase 0 also sums the update vectors of the
+// rank's subtree roots into vbuf (one dense slice per interface front); the caller sums vbuf over the
+// ranks before phase 1, where an interface front takes that slice instead of its children below the cut.
+void hx_lsolve_phase(void* hv, double* x, int rank, int phase) {
     HX* h = (HX*)hv;
     const Symbolic& S = h->S;
-    h->upd.assign(S.sum_r, 0.0);
+    const int mine = phase == 0 ? rank : -1;
+    if (phase == 0) { h->upd.assign(S.sum_r, 0.0); std::fill(h->vbuf.begin(), h->vbuf.end(), 0.0); }
     for (int l = 0; l < S.nlevels; ++l)
         for (int u = S.level_ptr[l]; u < S.level_ptr[l + 1]; ++u) {
             const int s = S.level_sn[u];
+            if (S.owner[s] != mine) continue;
             const int c0 = S.sn_start[s];
             const int64_t k = S.sn_start[s + 1] - c0, r = S.rows_ptr[s + 1] - S.rows_ptr[s], f = k + r;
             const double* P = h->lu.data() + S.Loff[s];
             double* us = h->upd.data() + S.rows_ptr[s];
+            if (S.iface[s]) {
+                const double* vb = h->vbuf.data() + h->voff[s];
+                for (int64_t i = 0; i < k; ++i) x[c0 + i] += vb[i];
+                for (int64_t a = 0; a < r; ++a) us[a] += vb[k + a];
+            }
             for (int ci = S.child_ptr[s]; ci < S.child_ptr[s + 1]; ++ci) {
                 const int c = S.child_idx[ci];
+                if (S.owner[c] != mine) continue;
                 const int64_t rc = S.rows_ptr[c + 1] - S.rows_ptr[c];
                 const int* rel = S.rel.data() + S.rows_ptr[c];
                 const double* uc = h->upd.data() + S.rows_ptr[c];
@@ -174,15 +236,26 @@ void hx_lsolve(void* hv, double* x) {
                 for (int64_t i = j + 1; i < k; ++i) x[c0 + i] -= P[i + j * f] * xj;
                 for (int64_t a = 0; a < r; ++a) us[a] -= P[(k + a) + j * f] * xj;
             }
+            const int ps = S.sn_parent[s];
+            if (phase == 0 && ps != -1 && S.owner[ps] == -1) {      // subtree root: hand over across the cut
+                double* vb = h->vbuf.data() + h->voff[ps];
+                const int* rel = S.rel.data() + S.rows_ptr[s];
+                for (int64_t a = 0; a < r; ++a) vb[rel[a]] += us[a];
+            }
         }
 }
 
-void hx_rsolve(void* hv, double* x) {
+void hx_lsolve(void* hv, double* x) { hx_lsolve_phase(hv, x, 0, 0); }
+
+// Backward substitution, one phase: phase 1 (top) runs first, then phase 0 (the rank's subtrees).
+void hx_rsolve_phase(void* hv, double* x, int rank, int phase) {
     HX* h = (HX*)hv;
     const Symbolic& S = h->S;
+    const int mine = phase == 0 ? rank : -1;
     for (int l = S.nlevels - 1; l >= 0; --l)
         for (int u = S.level_ptr[l]; u < S.level_ptr[l + 1]; ++u) {
             const int s = S.level_sn[u];
+            if (S.owner[s] != mine) continue;
             const int c0 = S.sn_start[s];
             const int64_t k = S.sn_start[s + 1] - c0, r = S.rows_ptr[s + 1] - S.rows_ptr[s], f = k + r;
             const double* P = h->lu.data() + S.Loff[s];
@@ -195,6 +268,26 @@ void hx_rsolve(void* hv, double* x) {
                 x[c0 + i] = acc / P[i + i * f];
             }
         }
+}
+
+void hx_rsolve(void* hv, double* x) { hx_rsolve_phase(hv, x, 0, 0); }
+
+// zero the entries of a permuted-space vector this rank is not responsible for
+void hx_mask_owned(void* hv, double* z, int rank) {
+    const Symbolic& S = ((HX*)hv)->S;
+    for (int j = 0; j < S.n; ++j) {
+        const int o = S.owner[S.col2sn[j]];
+        if (!(o == rank || (o == -1 && rank == 0))) z[j] = 0.0;
+    }
+}
+
+void hx_permute_scale(void* hv, const double* b, double* w) {
+    HX* h = (HX*)hv;
+    for (int i = 0; i < h->S.n; ++i) w[i] = h->Rs[h->S.p[i]] * b[h->S.p[i]];
+}
+void hx_unpermute(void* hv, const double* w, double* x) {
+    HX* h = (HX*)hv;
+    for (int i = 0; i < h->S.n; ++i) x[h->S.q[i]] = w[i];
 }
 
 void hx_solve(void* hv, const double* b, double* x) {
