@@ -159,7 +159,6 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
         for (int l = 0; l < S.nlevels; ++l) {
             const int* sn = S.level_sn.data() + S.level_ptr[l];
             const int cnt = S.level_ptr[l + 1] - S.level_ptr[l];
-            int maxch = 0;
             // Zero the contribution blocks that receive '+=' contributions.  Extend-add children add
             // at this level; a direct child adds one level earlier, so its parent is zeroed there.
             // Interface blocks are zero-filled once, before phase A, and arrive here all-reduced.
@@ -170,31 +169,31 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
             };
             for (int t = 0; t < cnt; ++t) {
                 int s = sn[t];
-                // a top parent receives this rank's subtree contributions during phase A
-                if (IN(s) || (ph == 0 && S.owner[s] == -1)) maxch = std::max(maxch, NC(s));
                 if (!IN(s)) continue;
-                const bool fed_directly = NC(s) == 1 && S.direct[S.child_idx[S.child_ptr[s]]];
-                if (NC(s) > 0 && R(s) > 0 && !fed_directly && !SMALL(s) && !S.iface[s]) zero_tasks(s);
                 if (S.direct[s] && !S.cb_assigned[S.sn_parent[s]] && R(S.sn_parent[s]) > 0) zero_tasks(S.sn_parent[s]);
             }
             push(fac, L_ZERO, off, 0);
-            // extend-add, one launch per child slot (children that write directly are skipped)
-            for (int slot = 0; slot < maxch; ++slot) {
-                off = (int64_t)tasks.size();
-                for (int t = 0; t < cnt; ++t) {
-                    int s = sn[t];
-                    if (NC(s) <= slot || SMALL(s)) continue;          // small parents pull their children
-                    if (!(IN(s) || (ph == 0 && S.owner[s] == -1))) continue;
-                    int c = S.child_idx[S.child_ptr[s] + slot];
-                    if (!IN(c)) continue;                             // phase A: this rank's children; B: top children
-                    int64_t rc = R(c);
-                    if (rc == 0 || S.direct[c]) continue;
-                    int ncols = (int)std::max<int64_t>(1, std::min<int64_t>(rc, 4096 / rc));
-                    for (int64_t b0 = 0; b0 < rc; b0 += ncols)
-                        tasks.push_back(make_int4(c, (int)b0, (int)std::min<int64_t>(ncols, rc - b0), 0));
+            // assembly of the children's contribution blocks into big parents: one launch, the CTA that
+            // owns a range of destination columns also zero-fills its part of the parent's block.
+            // In phase A a top parent receives this rank's subtree contributions here as well.
+            off = (int64_t)tasks.size();
+            for (int t = 0; t < cnt; ++t) {
+                int s = sn[t];
+                if (SMALL(s) || NC(s) == 0) continue;                 // small parents pull their children
+                if (!(IN(s) || (ph == 0 && S.owner[s] == -1))) continue;
+                bool any = false;
+                for (int u = S.child_ptr[s]; u < S.child_ptr[s + 1]; ++u) {
+                    const int c = S.child_idx[u];
+                    if (IN(c) && !S.direct[c] && R(c) > 0) any = true;
                 }
-                push(fac, L_EXTEND, off, 0);
+                if (!any) continue;
+                const bool zero = IN(s) && R(s) > 0 && !S.iface[s];
+                const int64_t f = K(s) + R(s);
+                for (int64_t pb0 = 0; pb0 < f; pb0 += ASM_COLS)
+                    tasks.push_back(make_int4(s, (int)pb0, (int)std::min<int64_t>(ASM_COLS, f - pb0),
+                                              (zero ? 1 : 0) | ((mine + 1) << 1)));
             }
+            push(fac, L_EXTEND, off, 0);
             // small fronts by shared-memory class
             const int classes[3] = {32, 64, front_small_limit()};
             int lo = 0;
@@ -360,6 +359,10 @@ int ensure_uploaded(smslu_handle_t h) {
     if ((rc = dev_upload(h, &d_Uoff, S.Uoff))) return rc;
     if ((rc = dev_upload(h, &d_CBoff, S.CBoff))) return rc;
     if ((rc = dev_upload(h, &d_sn_parent, S.sn_parent))) return rc;
+    int *d_asm_child_ptr, *d_asm_child_idx, *d_owner;
+    if ((rc = dev_upload(h, &d_asm_child_ptr, S.child_ptr))) return rc;
+    if ((rc = dev_upload(h, &d_asm_child_idx, S.child_idx))) return rc;
+    if ((rc = dev_upload(h, &d_owner, S.owner))) return rc;
     if ((rc = dev_upload(h, &d_child_ptr, child_ptr_d))) return rc;
     if ((rc = dev_upload(h, &d_child_idx, child_idx_d))) return rc;
     if ((rc = dev_upload(h, &h->d_p, S.p))) return rc;
@@ -436,6 +439,7 @@ int ensure_uploaded(smslu_handle_t h) {
     cx.child_ptr = d_child_ptr; cx.child_idx = d_child_idx;
     cx.lu = d_lu; cx.cb = d_cb; cx.upd = d_upd; cx.counters = d_counters; cx.flag = d_flag;
     cx.bpart = d_bpart; cx.counters2 = d_counters2; cx.dinv = d_dinv;
+    cx.asm_child_ptr = d_asm_child_ptr; cx.asm_child_idx = d_asm_child_idx; cx.owner = d_owner;
     cx.a_ptr = d_a_ptr; cx.a_src = d_a_src; cx.a_row = d_a_row; cx.a_pos = d_a_pos;
     CU(cudaDeviceSynchronize());
     h->uploaded = true;
@@ -479,7 +483,7 @@ int run_schedule(smslu_handle_t h, const std::vector<Launch>& sched, const doubl
         if ((rc = prof_begin(h, L.kind))) return rc;
         switch (L.kind) {
             case L_ZERO: launch_zero_cb(h->stream, h->cx, tk, L.ntasks); break;
-            case L_EXTEND: launch_extend_add(h->stream, h->cx, tk, L.ntasks); break;
+            case L_EXTEND: launch_assemble(h->stream, h->cx, tk, L.ntasks); break;
             case L_SMALL: launch_front_small(h->stream, h->cx, tk, L.ntasks, L.fmax, h->cur_av, h->d_Rs); break;
             case L_FWD_SMALL: launch_small_fwd(h->stream, h->cx, tk, L.ntasks, win, zx); break;
             case L_BWD_SMALL: launch_small_bwd(h->stream, h->cx, tk, L.ntasks, zx); break;

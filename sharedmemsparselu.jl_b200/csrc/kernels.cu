@@ -64,82 +64,54 @@ __global__ void __launch_bounds__(256) k_zero_cb(DevCtx cx, const int4* __restri
     for (int64_t e = lo + threadIdx.x; e < hi; e += 256) C[e] = 0.0;
 }
 
-// ------------------------------------------------------------------ extend-add child CB into parent
-// task: x = child supernode, y = first child-CB column, z = number of columns.
-// Within one launch every parent receives from at most one child => no write conflicts and a
-// fixed summation order (children are applied slot by slot, in ascending child order).
-__global__ void __launch_bounds__(256) k_extend_add(DevCtx cx, const int4* __restrict__ tasks) {
-    int4 tk = tasks[blockIdx.x];
-    const int c = tk.x;
-    const int64_t rc = cx.rows_ptr[c + 1] - cx.rows_ptr[c];
-    const int* __restrict__ rel = cx.rel + cx.rows_ptr[c];
-    const double* __restrict__ Cc = cx.cb + cx.CBoff[c];
-    const Front F = load_front(cx, cx.sn_parent[c]);
-    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
-    for (int b = tk.y + ty; b < tk.y + tk.z; b += 4) {
-        const int rb = rel[b];
-        const double* __restrict__ src = Cc + (int64_t)b * rc;
-        if (rb < F.k) {
-            double* dst = F.P + (int64_t)rb * F.f;
-            for (int a = tx; a < rc; a += 64) dst[rel[a]] += src[a];
-        } else {
-            double* dstC = F.C + (int64_t)(rb - F.k) * F.r - F.k;
-            double* dstT = F.T + (rb - F.k);
-            for (int a = tx; a < rc; a += 64) {
-                const int ra = rel[a];
-                if (ra < F.k) dstT[(int64_t)ra * F.r] += src[a];
-                else dstC[ra] += src[a];
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------ dense building blocks
-// LU of a w x w (w <= 32) block held in shared memory, static pivot order, all PANEL threads.
-// One barrier per elimination step: every thread reads the pivot and its own row's entry of
-// column j, divides, and updates its share of the row; the multiplier is stored after the
-// barrier (column j is never read again).  rd[j] receives 1/pivot for the row solves.
-__device__ __forceinline__ void block_lu(double (*D)[NB + 1], double* rd, int w, int c0, int* flag) {
-    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-    for (int j = 0; j < w; ++j) {
-        const double piv = D[j][j];
-        const int i = j + 1 + tx;
-        double l = 0.0;
-        if (i < w) {
-            l = D[i][j] / piv;
-            for (int c = j + 1 + ty; c < w; c += PANEL_ROWS / 32) D[i][c] -= l * D[j][c];
-        }
-        if (tid == 0) {
-            if (bad_pivot(piv)) atomicMin(flag, c0 + j);
-            rd[j] = 1.0 / piv;
+// ------------------------------------------------------------------ assemble children into a big parent
+// One CTA owns ASM_COLS destination columns [pb0, pb0 + ncols) of the parent's front and pulls every
+// qualifying child's contribution block into them, child by child in ascending order (fixed summation
+// order, no atomics, one launch per level).  Destination column pb < k lands in P(:, pb); pb >= k lands
+// in row pb-k of U12' (rows pa < k) and in column pb-k of the contribution block (rows pa >= k), which the
+// CTA zero-fills first when asked to.  rel is ascending, so a child's columns that fall into the CTA's
+// range are found by binary search.
+// task: x = parent, y = pb0, z = ncols, w = (zero ? 1 : 0) | (owner filter + 1) << 1.
+__global__ void __launch_bounds__(256) k_assemble(DevCtx cx, const int4* __restrict__ tasks) {
+    const int4 tk = tasks[blockIdx.x];
+    const int s = tk.x, pb0 = tk.y, pb1 = tk.y + tk.z, filt = (tk.w >> 1) - 1;
+    const Front F = load_front(cx, s);
+    const int k = F.k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tk.w & 1) {
+        const int c_lo = pb0 > k ? pb0 - k : 0, c_hi = pb1 - k;      // contribution-block columns owned here
+        if (c_hi > c_lo) {
+            double* __restrict__ z = F.C + (int64_t)c_lo * F.r;
+            const int64_t cnt = (int64_t)(c_hi - c_lo) * F.r;
+            for (int64_t e = tid; e < cnt; e += 256) z[e] = 0.0;
         }
         __syncthreads();
-        if (ty == 0 && i < w) D[i][j] = l;
     }
-    __syncthreads();
-}
-
-// Row solves against the factored pivot block, written column-oriented (right-looking) so that the
-// dependent chain is one multiply-add per column instead of an inner product:
-//   upper:   x <- x U^{-1}   (U non-unit; rd = reciprocals of its diagonal)
-//   lower_t: x <- x L^{-T}   (L unit lower)
-__device__ __forceinline__ void trsm_row_upper(double (&x)[NB], const double (*D)[NB + 1], const double* rd, int w) {
-#pragma unroll
-    for (int p = 0; p < NB; ++p) {
-        if (p >= w) break;
-        const double xp = x[p] * rd[p];
-        x[p] = xp;
-#pragma unroll
-        for (int c = p + 1; c < NB; ++c) x[c] -= xp * D[p][c];
-    }
-}
-__device__ __forceinline__ void trsm_row_lower_t(double (&x)[NB], const double (*D)[NB + 1], int w) {
-#pragma unroll
-    for (int p = 0; p < NB; ++p) {
-        if (p >= w) break;
-        const double xp = x[p];
-#pragma unroll
-        for (int c = p + 1; c < NB; ++c) x[c] -= xp * D[c][p];
+    for (int ci = cx.asm_child_ptr[s]; ci < cx.asm_child_ptr[s + 1]; ++ci) {
+        const int c = cx.asm_child_idx[ci];
+        if (cx.owner[c] != filt) continue;
+        const int rc = (int)(cx.rows_ptr[c + 1] - cx.rows_ptr[c]);
+        const int* __restrict__ rel = cx.rel + cx.rows_ptr[c];
+        int lo = 0, hi = rc;                       // first b with rel[b] >= pb0
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (rel[mid] < pb0) lo = mid + 1; else hi = mid; }
+        const double* __restrict__ Cc = cx.cb + cx.CBoff[c];
+        for (int b = lo + warp; b < rc; b += 8) {
+            const int pb = rel[b];
+            if (pb >= pb1) break;
+            const double* __restrict__ src = Cc + (int64_t)b * rc;
+            if (pb < k) {
+                double* __restrict__ dst = F.P + (int64_t)pb * F.f;
+                for (int a = lane; a < rc; a += 32) dst[rel[a]] += src[a];
+            } else {
+                double* __restrict__ dstC = F.C + (int64_t)(pb - k) * F.r - k;
+                double* __restrict__ dstT = F.T + (pb - k);
+                for (int a = lane; a < rc; a += 32) {
+                    const int pa = rel[a];
+                    if (pa < k) dstT[(int64_t)pa * F.r] += src[a];
+                    else dstC[pa] += src[a];
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -237,6 +209,14 @@ __global__ void __launch_bounds__(RW * CH * FPC) k_small_factor(DevCtx cx, const
     if (tid < k) cx.dinv[F.c0 + tid] = rd[tid];
 }
 
+// ------------------------------------------------------------------ FP64 tensor-core tile
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    // D(8x8) = A(8x4, row) * B(4x8, col) + C on the FP64 tensor pipe (SASS: DMMA.8x8x4).
+    // lane l holds A[l/4][l%4], B[l%4][l/4], C[l/4][2*(l%4)], C[l/4][2*(l%4)+1].
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
 // ------------------------------------------------------------------ panel step of a big front
 // A front with k (<= KW) pivot columns is factored in ceil(k/32) left-looking panel steps, one
 // launch each.  Step g owns pivot columns [j0, j1) = [32g, min(k, 32g+32)):
@@ -245,54 +225,68 @@ __global__ void __launch_bounds__(RW * CH * FPC) k_small_factor(DevCtx cx, const
 //   kind 1 (T): 128 rows of U12' :  row <- (row[j0:j1] - row[0:j0] * L[j0:j1, 0:j0]') * L_gg^{-T}
 //   kind 2 (I): 128 columns of the pivot block right of the diagonal block (U inside the block),
 //               same arithmetic as kind 1 on P[j0:j1, c].
-// Every CTA first brings the diagonal block up to date (D_gg -= L[g,0:g] U[0:g,g]) and factors it,
-// redundantly; the CTA that is last to have read the raw block stores the factors (nobody waits).
+// CTA = 4 row warps + 1 pivot warp, working concurrently between two barriers:
+//   row warps  : the left-looking update of their 32 rows x 32 columns on the FP64 tensor pipe (DMMA
+//                m8n8k4, 4 x 4 accumulator tiles per warp, A fragments straight from global memory with
+//                one k-step of prefetch, B fragments from the staged coefficient block), then the tile is
+//                transposed through shared memory so that every thread holds one row in registers;
+//   pivot warp : D_gg -= L[g, 0:j0] U[0:j0, g] (DMMA), then the 32 x 32 LU with one row per lane, all 32
+//                columns in registers, pivot row broadcast by shuffles, reciprocal pivots -- no barriers.
+//   after the second barrier the row threads solve against the factored block (registers, 128-bit
+//   shared-memory loads of the factor rows) and store their 32 values.
+// Every CTA factors the diagonal block redundantly; the CTA that is last to have read the raw block
+// stores the factors and the reciprocal pivots (nobody waits).
 // task: x = supernode, y = g | kind << 4 | (CTAs of this step of this front) << 8, z = tile,
 //       w = index of the step's arrival counter.
-// dynamic shared memory: 2 * j0 * (NB+1) doubles (the two coefficient blocks).
-__global__ void __launch_bounds__(PANEL_ROWS) k_panel(DevCtx cx, const int4* __restrict__ tasks) {
-    extern __shared__ double coef[];
-    __shared__ double D[NB][NB + 1];
+// dynamic shared memory: (2 * j0 + 128) * CLD doubles (two coefficient blocks + transposition buffers).
+constexpr int PANEL_THREADS = PANEL_ROWS + 32;
+constexpr int CLD = NB + 2;           // even row stride: 128-bit aligned pairs
+
+__global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* __restrict__ tasks) {
+    extern __shared__ __align__(16) double dsm[];
+    __shared__ __align__(16) double D[NB][CLD];     // diagonal block, D[i][c]
+    __shared__ __align__(16) double W[NB][CLD];     // W[p][c] = U[p][c] (kind 0) or L[c][p] (kinds 1, 2)
     __shared__ double rd[NB];
     __shared__ int s_last;
     int4 tk = tasks[blockIdx.x];
     const Front F = load_front(cx, tk.x);
     const int g = tk.y & 15, kind = (tk.y >> 4) & 15, total = tk.y >> 8;
     const int k = F.k, j0 = g * NB, w = (k - j0 < NB) ? k - j0 : NB, j1 = j0 + w;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double* Uc = coef;                       // Uc[m * (NB+1) + c] = U[m, j0 + c],  m < j0
-    double* Lc = coef + j0 * (NB + 1);       // Lc[m * (NB+1) + i] = L[j0 + i, m],  m < j0
-    // stage D_gg and the two coefficient blocks; loads are issued in batches of 8 per thread so
-    // that their latencies overlap (these CTAs run almost alone on the machine)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, fr = lane >> 2, fc = lane & 3;
+    double* Uc = dsm;                               // Uc[m * CLD + c] = U[m, j0 + c],  m < j0
+    double* Lc = dsm + j0 * CLD;                    // Lc[m * CLD + i] = L[j0 + i, m],  m < j0
+    double* Xs = dsm + 2 * j0 * CLD;                // Xs[warp][32][CLD]
+    // ---- stage D_gg and the two coefficient blocks, 8 loads in flight per thread
     {
         const double* __restrict__ Pg = F.P;
         double t[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {   // D_gg: 32 x 32 = 8 per thread
-            const int e = u * PANEL_ROWS + tid, i = e & 31, c = e >> 5;
-            t[u] = (i < w && c < w) ? Pg[(j0 + i) + (int64_t)(j0 + c) * F.f] : 0.0;
+        for (int u = 0; u < 8; ++u) {
+            const int e = u * PANEL_THREADS + tid, i = e & 31, c = e >> 5;
+            t[u] = (e < NB * NB && i < w && c < w) ? Pg[(j0 + i) + (int64_t)(j0 + c) * F.f] : 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { const int e = u * PANEL_ROWS + tid; D[e & 31][e >> 5] = t[u]; }
-        for (int it = 0; it < 8 * g; it += 8) {   // Lc: j0 x 32 elements, (m, i) -> L[j0+i, m]
+        for (int u = 0; u < 8; ++u) { const int e = u * PANEL_THREADS + tid; if (e < NB * NB) D[e & 31][e >> 5] = t[u]; }
+        const int tot = j0 * NB;
+        for (int e0 = 0; e0 < tot; e0 += 8 * PANEL_THREADS) {          // Lc: (m, i) -> L[j0+i, m]
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const int e = (it + u) * PANEL_ROWS + tid, i = e & 31, m = e >> 5;
-                t[u] = i < w ? Pg[(j0 + i) + (int64_t)m * F.f] : 0.0;
+                const int e = e0 + u * PANEL_THREADS + tid, i = e & 31, m = e >> 5;
+                t[u] = (e < tot && i < w) ? Pg[(j0 + i) + (int64_t)m * F.f] : 0.0;
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) { const int e = (it + u) * PANEL_ROWS + tid; Lc[(e >> 5) * (NB + 1) + (e & 31)] = t[u]; }
+            for (int u = 0; u < 8; ++u) { const int e = e0 + u * PANEL_THREADS + tid; if (e < tot) Lc[(e >> 5) * CLD + (e & 31)] = t[u]; }
         }
-        for (int it = 0; it < 8 * g; it += 8) {   // Uc: 32 columns x j0 rows, (m, c) -> U[m, j0+c]
+        for (int e0 = 0; e0 < tot; e0 += 8 * PANEL_THREADS) {          // Uc: (m, c) -> U[m, j0+c]
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const int e = (it + u) * PANEL_ROWS + tid, q = e >> 5, c = q / g, m = (q - c * g) * 32 + (e & 31);
-                t[u] = c < w ? Pg[m + (int64_t)(j0 + c) * F.f] : 0.0;
+                const int e = e0 + u * PANEL_THREADS + tid, q = e >> 5, c = q / g, m = (q - c * g) * 32 + (e & 31);
+                t[u] = (e < tot && c < w) ? Pg[m + (int64_t)(j0 + c) * F.f] : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const int e = (it + u) * PANEL_ROWS + tid, q = e >> 5, c = q / g, m = (q - c * g) * 32 + (e & 31);
-                Uc[m * (NB + 1) + c] = t[u];
+                const int e = e0 + u * PANEL_THREADS + tid, q = e >> 5, c = q / g, m = (q - c * g) * 32 + (e & 31);
+                if (e < tot) Uc[m * CLD + c] = t[u];
             }
         }
     }
@@ -302,158 +296,247 @@ __global__ void __launch_bounds__(PANEL_ROWS) k_panel(DevCtx cx, const int4* __r
         int old = atomicAdd(cx.counters + tk.w, 1);
         s_last = ((old + 1) % total) == 0;
     }
-    // ---- this thread's row (or column), brought up to date with the earlier blocks
-    const int64_t idx = (int64_t)tk.z * PANEL_ROWS + tid;
-    double* base; int64_t stride; const double* cf; bool active;
-    if (kind == 0) { active = j1 + idx < F.f; base = F.P + j1 + idx; stride = F.f; cf = Uc; }
-    else if (kind == 1) { active = idx < F.r; base = F.T + idx; stride = F.r; cf = Lc; }
-    else { active = j1 + idx < k; base = F.P + (j1 + idx) * F.f; stride = 1; cf = Lc; }
-    double x[NB];
+    double x[NB];                                   // row warps: one row; pivot warp: row `lane` of the block
+    double* base = nullptr; int64_t stride = 1; bool active = false;
+    if (warp < 4) {
+        // ---- row warps: left-looking update of 32 rows x 32 columns
+        const double* cf = kind == 0 ? Uc : Lc;
+        const int64_t idx0 = (int64_t)tk.z * PANEL_ROWS + warp * 32;
+        auto row_ptr = [&](int64_t idx, double*& b, bool& act) {
+            if (kind == 0) { act = j1 + idx < F.f; b = F.P + j1 + idx; }
+            else if (kind == 1) { act = idx < F.r; b = F.T + idx; }
+            else { act = j1 + idx < k; b = F.P + (j1 + idx) * F.f; }
+        };
+        stride = kind == 0 ? F.f : (kind == 1 ? F.r : 1);
+        double acc[4][4][2];
+        const double* fb[4]; bool fa[4];
 #pragma unroll
-    for (int c = 0; c < NB; ++c) x[c] = (active && c < w) ? base[(int64_t)(j0 + c) * stride] : 0.0;
-    if (active && j0 > 0) {   // j0 is a multiple of 32; two batches of 16 loads in flight per thread
-        double va[16], vb[16];
+        for (int i = 0; i < 4; ++i) { double* b; row_ptr(idx0 + 8 * i + fr, b, fa[i]); fb[i] = b; }
 #pragma unroll
-        for (int u = 0; u < 16; ++u) va[u] = base[(int64_t)u * stride];
-        for (int m0 = 0; m0 < j0; m0 += 32) {
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int u = 0; u < 16; ++u) vb[u] = base[(int64_t)(m0 + 16 + u) * stride];
+            for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                const double* __restrict__ cm = cf + (m0 + u) * (NB + 1);
+                for (int e = 0; e < 2; ++e) {
+                    const int c = 8 * j + 2 * fc + e;
+                    acc[i][j][e] = (fa[i] && c < w) ? fb[i][(int64_t)(j0 + c) * stride] : 0.0;
+                }
+        if (j0 > 0) {
+            double an[4], bn[4];
 #pragma unroll
-                for (int c = 0; c < NB; ++c) x[c] -= va[u] * cm[c];
-            }
-            if (m0 + 32 < j0) {
+            for (int i = 0; i < 4; ++i) an[i] = fa[i] ? -fb[i][(int64_t)fc * stride] : 0.0;
 #pragma unroll
-                for (int u = 0; u < 16; ++u) va[u] = base[(int64_t)(m0 + 32 + u) * stride];
-            }
+            for (int j = 0; j < 4; ++j) bn[j] = cf[fc * CLD + 8 * j + fr];
+            for (int m0 = 0; m0 < j0; m0 += 4) {
+                double a[4], b[4];
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                const double* __restrict__ cm = cf + (m0 + 16 + u) * (NB + 1);
+                for (int i = 0; i < 4; ++i) { a[i] = an[i]; b[i] = bn[i]; }
+                if (m0 + 4 < j0) {
 #pragma unroll
-                for (int c = 0; c < NB; ++c) x[c] -= vb[u] * cm[c];
+                    for (int i = 0; i < 4; ++i) an[i] = fa[i] ? -fb[i][(int64_t)(m0 + 4 + fc) * stride] : 0.0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) bn[j] = cf[(m0 + 4 + fc) * CLD + 8 * j + fr];
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
             }
         }
-    }
-    // ---- diagonal block: D_gg -= L[g, 0:j0] U[0:j0, g]  (lane = row, warp = 8 columns), then LU
-    if (j0 > 0) {
-        double acc[8];
+        double* xs = Xs + warp * 32 * CLD;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) acc[u] = 0.0;
-        for (int m = 0; m < j0; ++m) {
-            const double li = Lc[m * (NB + 1) + lane];
-            const double* __restrict__ um = Uc + m * (NB + 1) + warp * 8;
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int u = 0; u < 8; ++u) acc[u] += li * um[u];
+            for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<double2*>(xs + (8 * i + fr) * CLD + 8 * j + 2 * fc) = make_double2(acc[i][j][0], acc[i][j][1]);
+        __syncwarp();
+#pragma unroll
+        for (int c2 = 0; c2 < NB / 2; ++c2) {
+            const double2 v = *reinterpret_cast<const double2*>(xs + lane * CLD + 2 * c2);
+            x[2 * c2] = v.x; x[2 * c2 + 1] = v.y;
         }
-        if (lane < w) {
+        row_ptr(idx0 + lane, base, active);
+    } else {
+        // ---- pivot warp: bring the diagonal block up to date, then factor it in registers
+        if (j0 > 0) {
+            double acc[4][4][2];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) if (warp * 8 + u < w) D[lane][warp * 8 + u] -= acc[u];
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double2 v = *reinterpret_cast<const double2*>(&D[8 * i + fr][8 * j + 2 * fc]);
+                    acc[i][j][0] = v.x; acc[i][j][1] = v.y;
+                }
+            for (int m0 = 0; m0 < j0; m0 += 4) {
+                double a[4], b[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = -Lc[(m0 + fc) * CLD + 8 * i + fr];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) b[j] = Uc[(m0 + fc) * CLD + 8 * j + fr];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<double2*>(&D[8 * i + fr][8 * j + 2 * fc]) = make_double2(acc[i][j][0], acc[i][j][1]);
+            __syncwarp();
+        }
+#pragma unroll
+        for (int c2 = 0; c2 < NB / 2; ++c2) {
+            const double2 v = *reinterpret_cast<const double2*>(&D[lane][2 * c2]);
+            x[2 * c2] = v.x; x[2 * c2 + 1] = v.y;
+        }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            if (j >= w) break;
+            const double piv = __shfl_sync(0xffffffffu, x[j], j);
+            const double rinv = 1.0 / piv;
+            const double l = lane > j ? x[j] * rinv : 0.0;
+            if (lane > j) x[j] = l;
+            if (lane == j) {
+                if (bad_pivot(piv)) atomicMin(cx.flag, F.c0 + j0 + j);
+                rd[j] = rinv;
+            }
+#pragma unroll
+            for (int c = j + 1; c < NB; ++c) x[c] -= l * __shfl_sync(0xffffffffu, x[c], j);
+        }
+        if (kind == 0) {                           // W[p][c] = U[p][c]: lane p stores its row
+#pragma unroll
+            for (int c2 = 0; c2 < NB / 2; ++c2) *reinterpret_cast<double2*>(&W[lane][2 * c2]) = make_double2(x[2 * c2], x[2 * c2 + 1]);
+        } else {                                   // W[p][c] = L[c][p]: lane c stores column c
+#pragma unroll
+            for (int p = 0; p < NB; ++p) W[p][lane] = x[p];
         }
     }
     __syncthreads();
-    block_lu(D, rd, w, F.c0 + j0, cx.flag);
-    if (s_last) {
-        for (int e = tid; e < w * NB; e += PANEL_ROWS) { int i = e & 31, c = e >> 5; if (i < w) F.P[(j0 + i) + (int64_t)(j0 + c) * F.f] = D[i][c]; }
-        if (tid < w) cx.dinv[F.c0 + j0 + tid] = rd[tid];
+    if (warp == 4) {
+        // the CTA that read the raw block last stores the factors (column by column: lanes = rows)
+        if (s_last && lane < w) {
+            double* __restrict__ dst = F.P + (j0 + lane) + (int64_t)j0 * F.f;
+#pragma unroll
+            for (int c = 0; c < NB; ++c) if (c < w) dst[(int64_t)c * F.f] = x[c];
+            cx.dinv[F.c0 + j0 + lane] = rd[lane];
+        }
+        return;
     }
     if (!active) return;
-    if (kind == 0) trsm_row_upper(x, D, rd, w); else trsm_row_lower_t(x, D, w);
+    // ---- solve the row against the factored block
+#pragma unroll
+    for (int p = 0; p < NB; ++p) {
+        if (p >= w) break;
+        const double xp = kind == 0 ? x[p] * rd[p] : x[p];
+        x[p] = xp;
+        const double2* __restrict__ wr = reinterpret_cast<const double2*>(&W[p][0]);
+#pragma unroll
+        for (int c2 = (p + 1) / 2; c2 < NB / 2; ++c2) {
+            const double2 wv = wr[c2];
+            if (2 * c2 > p) x[2 * c2] -= xp * wv.x;
+            x[2 * c2 + 1] -= xp * wv.y;
+        }
+    }
 #pragma unroll
     for (int c = 0; c < NB; ++c) if (c < w) base[(int64_t)(j0 + c) * stride] = x[c];
 }
 
 // ------------------------------------------------------------------ Schur update of the CB
 // V (r x r) = beta*C - L21 (r x k) * U12 (k x r), U12 held transposed, k <= KW.  64x64 tile per
-// CTA, 4x4 per thread, K staged through shared memory in chunks of 32.
+// CTA; each of the 8 warps owns 32 x 16 of it as 4 x 2 DMMA (m8n8k4) accumulator tiles; K is staged
+// through shared memory in chunks of 32 (L21 negated on the way in, so the MMA accumulates C - L21 U12).
 // task: x = supernode, y = tile row, z = tile col, w = flags:
 //   bit0 beta   : C holds assembled contributions (else it is taken as zero)
 //   bit1 direct : V is written straight into the parent's front through the rel map (this front
 //                 is its parent's only child, so nobody else writes there): panel entries +=,
 //   bit2 assign : ... and the parent's contribution-block entries are assigned (=) instead of +=.
 //   without bit1 V overwrites C in place.
+constexpr int GEMM_LDS = GEMM_TILE + 4;   // row stride = 4 (mod 16) doubles: fragment loads are conflict-free
+
 __global__ void __launch_bounds__(256) k_gemm_cb(DevCtx cx, const int4* __restrict__ tasks) {
-    __shared__ double As[NB][GEMM_TILE];
-    __shared__ double Bs[NB][GEMM_TILE];
+    __shared__ double As[NB][GEMM_LDS];   // As[p][m] = -L21[m0 + m][kc + p]
+    __shared__ double Bs[NB][GEMM_LDS];   // Bs[p][n] =  U12[kc + p][n0 + n]
     int4 tk = tasks[blockIdx.x];
     const Front F = load_front(cx, tk.x);
-    const int k = F.k, tid = threadIdx.x;
+    const int k = F.k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t m0 = (int64_t)tk.y * GEMM_TILE, n0 = (int64_t)tk.z * GEMM_TILE;
     const double* __restrict__ A = F.P + F.k;
     const double* __restrict__ B = F.T;
-    const int tx = tid & 15, ty = tid >> 4;
     const bool beta = tk.w & 1, direct = tk.w & 2, assign = tk.w & 4;
-    double acc[4][4];
+    // warp tile: 32 rows x 16 columns = 4 x 2 DMMA tiles; 8 warps cover 64 x 64
+    const int wm = (warp & 1) * 32, wn = (warp >> 1) * 16;
+    const int fr = lane >> 2, fc = lane & 3;            // fragment row / k (A), n / k (B), row / column pair (C)
+    double acc[4][2][2];
     // issue the C loads first so they are in flight while the operand tiles are staged
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int64_t col = n0 + ty + 16 * j;
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int64_t row = m0 + tx + 16 * i;
-            acc[i][j] = (beta && row < F.r && col < F.r) ? F.C[row + col * F.r] : 0.0;
-        }
-    }
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int64_t row = m0 + wm + 8 * i + fr, col = n0 + wn + 8 * j + 2 * fc + e;
+                acc[i][j][e] = (beta && row < F.r && col < F.r) ? F.C[row + col * F.r] : 0.0;
+            }
     for (int kc = 0; kc < k; kc += NB) {
         const int kw = (k - kc < NB) ? k - kc : NB;
         if (kc) __syncthreads();
-        for (int e = tid; e < GEMM_TILE * kw; e += 256) {
-            int a = e & (GEMM_TILE - 1), p = e >> 6;
-            int64_t ra = m0 + a, rb = n0 + a;
-            As[p][a] = ra < F.r ? A[ra + (int64_t)(kc + p) * F.f] : 0.0;
-            Bs[p][a] = rb < F.r ? B[rb + (int64_t)(kc + p) * F.r] : 0.0;
+        for (int e = tid; e < GEMM_TILE * NB; e += 256) {
+            const int a = e & (GEMM_TILE - 1), p = e >> 6;
+            const int64_t ra = m0 + a, rb = n0 + a;
+            As[p][a] = (p < kw && ra < F.r) ? -A[ra + (int64_t)(kc + p) * F.f] : 0.0;
+            Bs[p][a] = (p < kw && rb < F.r) ? B[rb + (int64_t)(kc + p) * F.r] : 0.0;
         }
         __syncthreads();
-        for (int p = 0; p < kw; ++p) {
-            double a[4], b[4];
+        const int ksteps = (kw + 3) >> 2;
+        for (int ks = 0; ks < ksteps; ++ks) {
+            const int p = 4 * ks + fc;
+            double a[4], b[2];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { a[i] = As[p][tx + 16 * i]; b[i] = Bs[p][ty + 16 * i]; }
+            for (int i = 0; i < 4; ++i) a[i] = As[p][wm + 8 * i + fr];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) b[j] = Bs[p][wn + 8 * j + fr];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] -= a[i] * b[j];
+                for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
     }
     if (!direct) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int64_t col = n0 + ty + 16 * j;
-            if (col >= F.r) continue;
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int64_t row = m0 + tx + 16 * i;
-                if (row < F.r) F.C[row + col * F.r] = acc[i][j];
-            }
-        }
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int64_t row = m0 + wm + 8 * i + fr, col = n0 + wn + 8 * j + 2 * fc + e;
+                    if (row < F.r && col < F.r) F.C[row + col * F.r] = acc[i][j][e];
+                }
         return;
     }
     const Front Q = load_front(cx, cx.sn_parent[tk.x]);
     const int* __restrict__ rel = cx.rel + cx.rows_ptr[tk.x];
-    int64_t prow[4], pcol[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int64_t row = m0 + tx + 16 * i, col = n0 + ty + 16 * i;
-        prow[i] = row < F.r ? rel[row] : -1;
-        pcol[i] = col < F.r ? rel[col] : -1;
-    }
+    for (int j = 0; j < 2; ++j)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int64_t pb = pcol[j];
-        if (pb < 0) continue;
+        for (int e = 0; e < 2; ++e) {
+            const int64_t col = n0 + wn + 8 * j + 2 * fc + e;
+            if (col >= F.r) continue;
+            const int64_t pb = rel[col];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int64_t pa = prow[i];
-            if (pa < 0) continue;
-            const double v = acc[i][j];
-            if (pb < Q.k) Q.P[pa + pb * Q.f] += v;
-            else if (pa < Q.k) Q.T[(pb - Q.k) + pa * Q.r] += v;
-            else {
-                double* d = Q.C + (pa - Q.k) + (pb - Q.k) * Q.r;
-                *d = assign ? v : *d + v;
+            for (int i = 0; i < 4; ++i) {
+                const int64_t row = m0 + wm + 8 * i + fr;
+                if (row >= F.r) continue;
+                const int64_t pa = rel[row];
+                const double v = acc[i][j][e];
+                if (pb < Q.k) Q.P[pa + pb * Q.f] += v;
+                else if (pa < Q.k) Q.T[(pb - Q.k) + pa * Q.r] += v;
+                else {
+                    double* d = Q.C + (pa - Q.k) + (pb - Q.k) * Q.r;
+                    *d = assign ? v : *d + v;
+                }
             }
         }
-    }
 }
 
 // ------------------------------------------------------------------ solves
@@ -777,7 +860,7 @@ int front_small_limit() { return SMALL_F_MAX; }
 constexpr int SMALL_FPC32 = 4;     // fronts per CTA in the one-warp class of k_small_factor
 constexpr int SOLVE_FPC = 8;       // fronts per CTA in the small solve kernels
 
-static size_t panel_smem(int j0) { return sizeof(double) * 2 * (size_t)j0 * (NB + 1); }
+static size_t panel_smem(int j0) { return sizeof(double) * (2 * (size_t)j0 + PANEL_ROWS) * CLD; }
 static size_t solve_smem(int kmax) { size_t kp = (size_t)((kmax + NB - 1) / NB) * NB; return sizeof(double) * kp * (kp + 1); }
 
 cudaError_t kernels_init() {
@@ -804,8 +887,8 @@ void launch_scatter(cudaStream_t st, int64_t nnz, const int64_t* dst, const int*
 void launch_zero_cb(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks) {
     if (ntasks > 0) k_zero_cb<<<ntasks, 256, 0, st>>>(cx, tasks);
 }
-void launch_extend_add(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks) {
-    if (ntasks > 0) k_extend_add<<<ntasks, 256, 0, st>>>(cx, tasks);
+void launch_assemble(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks) {
+    if (ntasks > 0) k_assemble<<<ntasks, 256, 0, st>>>(cx, tasks);
 }
 void launch_front_small(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int fmax,
                         const double* av, const double* Rs) {
@@ -831,7 +914,7 @@ void launch_small_bwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int 
     if (ntasks > 0) k_small_bwd<SOLVE_FPC><<<(ntasks + SOLVE_FPC - 1) / SOLVE_FPC, 32 * SOLVE_FPC, 0, st>>>(cx, tasks, ntasks, x);
 }
 void launch_panel(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int g) {
-    if (ntasks > 0) k_panel<<<ntasks, PANEL_ROWS, panel_smem(g * NB), st>>>(cx, tasks);
+    if (ntasks > 0) k_panel<<<ntasks, PANEL_THREADS, panel_smem(g * NB), st>>>(cx, tasks);
 }
 void launch_gemm_cb(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks) {
     if (ntasks > 0) k_gemm_cb<<<ntasks, 256, 0, st>>>(cx, tasks);

@@ -25,6 +25,7 @@ constexpr int SOLVE_THREADS = 256;
 constexpr int FWD_ROWS = 64;      // update rows per forward CTA (4 threads per row)
 constexpr int BWD_ROWS = 256;     // rows of U12' per backward CTA
 constexpr int ZERO_TILE = 8192;
+constexpr int ASM_COLS = 16;      // destination columns of a parent front per assembly CTA
 
 struct DevCtx {
     const int* sn_start;
@@ -50,6 +51,11 @@ struct DevCtx {
     const int* a_src;   // index into the caller's nzval
     const int* a_row;   // original row (for Rs)
     const int* a_pos;   // row | col << 16 inside the front
+    // the real child lists (child_ptr/child_idx may hold virtual children, see api.cu) and the owner
+    // of every supernode (-1 = top), for the assembly kernel
+    const int* asm_child_ptr;
+    const int* asm_child_idx;
+    const int* owner;
 };
 
 // ---- refactorization
@@ -57,7 +63,7 @@ void launch_rowscale(cudaStream_t st, int n, const int64_t* rowptr, const int64_
 void launch_scatter(cudaStream_t st, int64_t nnz, const int64_t* dst, const int* arow, const int* asrc,
                     const double* Rs, const double* av, double* lu);
 void launch_zero_cb(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks);
-void launch_extend_add(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks);
+void launch_assemble(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks);
 void launch_front_small(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int fmax,
                         const double* av, const double* Rs);
 void launch_vgather(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const int* vlist);
