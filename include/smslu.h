@@ -177,6 +177,10 @@ int smslu_allocate_shared(void);
 int smslu_host_alloc(void** ptr, int64_t bytes);
 int smslu_host_free(void* ptr);
 
+/* Developer aid: phase timestamps (clock64) of the most recent panel kernel, 32 slots; returns the
+ * number of slots filled -- 0 unless the library was built with SMSLU_TRACE=1. */
+int smslu_debug_trace(int64_t* out32);
+
 /* Library/ABI version: major*10000 + minor*100 + patch. */
 int smslu_version(void);
 

@@ -77,6 +77,68 @@ __global__ void luB(const double* A, double* out, long long* cyc, int reps) {
 #pragma unroll
     for (int c = 0; c < K; ++c) out[lane + c * K] = a[c];
 }
+// LU-B2/B3: as LU-B, but the reciprocal of the next pivot is started as soon as column j+1 is up to date,
+// so that its latency overlaps the rest of the step (B3: __drcp_rn instead of 1.0/x).
+template <int RCPK>
+__global__ void luB2(const double* A, double* out, long long* cyc, int reps) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    long long tot = 0;
+    double a[K];
+    if (tid >= 32) return;
+    for (int r = 0; r < reps; ++r) {
+#pragma unroll
+        for (int c = 0; c < K; ++c) a[c] = A[lane + c * K] + r * 1e-9;
+        __syncwarp();
+        long long t0 = clock64();
+        double piv = __shfl_sync(0xffffffffu, a[0], 0);
+        double rinv = RCPK ? __drcp_rn(piv) : 1.0 / piv;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const double l = lane > j ? a[j] * rinv : 0.0;
+            if (lane > j) a[j] = l;
+            if (j + 1 < K) {
+                a[j + 1] -= l * __shfl_sync(0xffffffffu, a[j + 1], j);
+                piv = __shfl_sync(0xffffffffu, a[j + 1], j + 1);
+                rinv = RCPK ? __drcp_rn(piv) : 1.0 / piv;
+            }
+#pragma unroll
+            for (int c = j + 2; c < K; ++c) a[c] -= l * __shfl_sync(0xffffffffu, a[c], j);
+        }
+        tot += clock64() - t0;
+    }
+    if (tid == 0) *cyc = tot / reps;
+#pragma unroll
+    for (int c = 0; c < K; ++c) out[lane + c * K] = a[c];
+}
+// LU-D: lane = COLUMN, all 32 rows in registers: the multipliers of step j live in lane j and are broadcast
+// by shuffles, the pivot-row element is the lane's own register.
+__global__ void luD(const double* A, double* out, long long* cyc, int reps) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    long long tot = 0;
+    double a[K];      // a[i] = D[i][lane]
+    if (tid >= 32) return;
+    for (int r = 0; r < reps; ++r) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) a[i] = A[i + lane * K] + r * 1e-9;
+        __syncwarp();
+        long long t0 = clock64();
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const double rinv = 1.0 / a[j];                 // only lane j's value is used
+            const double u = lane > j ? a[j] : 0.0;         // pivot row element of this column
+#pragma unroll
+            for (int i = j + 1; i < K; ++i) {
+                const double l = __shfl_sync(0xffffffffu, a[i] * rinv, j);
+                if (lane == j) a[i] = l;
+                a[i] -= l * u;
+            }
+        }
+        tot += clock64() - t0;
+    }
+    if (tid == 0) *cyc = tot / reps;
+#pragma unroll
+    for (int i = 0; i < K; ++i) out[i + lane * K] = a[i];
+}
 // LU-C: as LU-A but the whole block lives in shared memory D[i][CLD]; thread (lane = row, warp = 8 columns)
 // reads the pivot row with 128-bit loads; one barrier per step, reciprocal produced one step ahead.
 __global__ void luC(const double* A, double* out, long long* cyc, int reps) {
@@ -244,6 +306,9 @@ int main() {
         luA<<<1, 128>>>(A, out, cyc, reps); rep("LU-A 4 warps, register strips, 1 barrier/step", true);
         luB<<<1, 128>>>(A, out, cyc, reps); rep("LU-B 1 warp, registers + shuffles, unrolled", true);
         luC<<<1, 128>>>(A, out, cyc, reps); rep("LU-C 4 warps, smem block + register strips", true);
+        luB2<0><<<1, 128>>>(A, out, cyc, reps); rep("LU-B2 1 warp, early reciprocal (1.0/x)", true);
+        luB2<1><<<1, 128>>>(A, out, cyc, reps); rep("LU-B3 1 warp, early reciprocal (__drcp_rn)", true);
+        luD<<<1, 128>>>(A, out, cyc, reps); rep("LU-D 1 warp, lane = column", true);
         trsmT<<<1, 128>>>(A, X, cyc, reps); rep("TRSM-T registers, 128-bit factor loads", false);
         updU1<<<1, 128, 96 * CLD * 8>>>(Rg, X, cyc, reps, 96); rep("UPD-U1 j0=96 thread=row, 128-bit coef loads", false);
         updU2<<<1, 128, 96 * CLD * 8>>>(Rg, X, cyc, reps, 96); rep("UPD-U2 j0=96 DMMA", false);

@@ -19,7 +19,7 @@ EXPORTS = [
     "smslu_last_error", "smslu_get_symbolic", "smslu_destroy", "smslu_allocate_shared",
     "smslu_host_alloc", "smslu_host_free", "smslu_version", "smslu_refactor_async",
     "smslu_solve_async", "smslu_sync", "smslu_set_stream", "smslu_set_profile",
-    "smslu_comm_unique_id", "smslu_comm_init",
+    "smslu_comm_unique_id", "smslu_comm_init", "smslu_debug_trace",
 ]
 KERNEL_KINDS = ["rowscale", "scatter", "zero_cb", "extend_add", "front_small", "panel", "gemm_cb",
                 "permute_scale", "fwd", "bwd", "unpermute", "fwd_small", "bwd_small", "allreduce"]
@@ -99,6 +99,7 @@ def lib():
         L.smslu_sync.argtypes = [vp]
         L.smslu_set_stream.argtypes = [vp, vp]
         L.smslu_set_profile.argtypes = [vp, i32]
+        L.smslu_debug_trace.argtypes = [vp]
         L.smslu_comm_unique_id.argtypes = [vp, i64]
         L.smslu_comm_init.argtypes = [vp, vp, i64]
         for name in EXPORTS:

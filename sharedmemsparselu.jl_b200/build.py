@@ -33,7 +33,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
     tmp = LIB + ".%d.tmp" % os.getpid()
-    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + \
+    trace = ["-DSMSLU_TRACE"] if os.environ.get("SMSLU_TRACE") == "1" else []
+    cmd = [nvcc()] + NVCC_FLAGS + trace + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + \
           [os.path.join(CSRC, s) for s in SOURCES] + ["-lnccl"]
     subprocess.check_call(cmd)
     os.replace(tmp, LIB)

@@ -211,25 +211,35 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
             int max_blk = 0;
             for (int t = 0; t < cnt; ++t) if (IN(sn[t]) && !SMALL(sn[t])) max_blk = std::max(max_blk, (K(sn[t]) + NB - 1) / NB);
             for (int g = 0; g < max_blk; ++g) {
-                off = (int64_t)tasks.size();
-                for (int t = 0; t < cnt; ++t) {
-                    int s = sn[t];
-                    if (!IN(s) || SMALL(s)) continue;
-                    const int k = K(s), nblk = (k + NB - 1) / NB;
-                    if (g >= nblk) continue;
-                    const int64_t r = R(s), f = k + r;
-                    const int j1 = std::min(k, (g + 1) * NB);
-                    int tl = (int)((f - j1 + PANEL_ROWS - 1) / PANEL_ROWS);      // rows below the diagonal block
-                    const int tt = (int)((r + PANEL_ROWS - 1) / PANEL_ROWS);     // rows of U12'
-                    const int ti = (k - j1 + PANEL_ROWS - 1) / PANEL_ROWS;       // columns right of it
-                    if (tl + tt + ti == 0) tl = 1;                               // someone has to factor D_gg
-                    const int total = tl + tt + ti;
-                    const int cidx = (int)ncounters++;
-                    for (int i = 0; i < tl; ++i) tasks.push_back(make_int4(s, g | (0 << 4) | (total << 8), i, cidx));
-                    for (int i = 0; i < tt; ++i) tasks.push_back(make_int4(s, g | (1 << 4) | (total << 8), i, cidx));
-                    for (int i = 0; i < ti; ++i) tasks.push_back(make_int4(s, g | (2 << 4) | (total << 8), i, cidx));
+                // rows per CTA: 128 when that already gives the machine enough CTAs, else 32
+                int rows = PANEL_ROWS;
+                for (int attempt = 0; attempt < 2; ++attempt) {
+                    off = (int64_t)tasks.size();
+                    const int64_t nc0 = ncounters;
+                    for (int t = 0; t < cnt; ++t) {
+                        int s = sn[t];
+                        if (!IN(s) || SMALL(s)) continue;
+                        const int k = K(s), nblk = (k + NB - 1) / NB;
+                        if (g >= nblk) continue;
+                        const int64_t r = R(s), f = k + r;
+                        const int j1 = std::min(k, (g + 1) * NB);
+                        int tl = (int)((f - j1 + rows - 1) / rows);      // rows below the diagonal block
+                        const int tt = (int)((r + rows - 1) / rows);     // rows of U12'
+                        const int ti = (k - j1 + rows - 1) / rows;       // columns right of it
+                        if (tl + tt + ti == 0) tl = 1;                   // someone has to factor D_gg
+                        const int total = tl + tt + ti;
+                        const int cidx = (int)ncounters++;
+                        for (int i = 0; i < tl; ++i) tasks.push_back(make_int4(s, g | (0 << 4) | (total << 8), i, cidx));
+                        for (int i = 0; i < tt; ++i) tasks.push_back(make_int4(s, g | (1 << 4) | (total << 8), i, cidx));
+                        for (int i = 0; i < ti; ++i) tasks.push_back(make_int4(s, g | (2 << 4) | (total << 8), i, cidx));
+                    }
+                    if (attempt == 0 && (int64_t)tasks.size() - off < 120 && (int64_t)tasks.size() > off) {
+                        tasks.resize(off); ncounters = nc0; rows = PANEL_ROWS_TOP;     // redo with small CTAs
+                        continue;
+                    }
+                    break;
                 }
-                push(fac, L_PANEL, off, g);
+                push(fac, L_PANEL, off, g | (rows << 8));
             }
             off = (int64_t)tasks.size();
             for (int t = 0; t < cnt; ++t) {
@@ -487,7 +497,7 @@ int run_schedule(smslu_handle_t h, const std::vector<Launch>& sched, const doubl
             case L_SMALL: launch_front_small(h->stream, h->cx, tk, L.ntasks, L.fmax, h->cur_av, h->d_Rs); break;
             case L_FWD_SMALL: launch_small_fwd(h->stream, h->cx, tk, L.ntasks, win, zx); break;
             case L_BWD_SMALL: launch_small_bwd(h->stream, h->cx, tk, L.ntasks, zx); break;
-            case L_PANEL: launch_panel(h->stream, h->cx, tk, L.ntasks, L.fmax); break;
+            case L_PANEL: launch_panel(h->stream, h->cx, tk, L.ntasks, L.fmax & 255, L.fmax >> 8); break;
             case L_GEMM: launch_gemm_cb(h->stream, h->cx, tk, L.ntasks); break;
             case L_FWD: launch_fwd(h->stream, h->cx, tk, L.ntasks, L.fmax, win, zx); break;
             case L_BWD: launch_bwd(h->stream, h->cx, tk, L.ntasks, L.fmax, zx); break;
@@ -599,6 +609,7 @@ int enqueue_solve(smslu_handle_t h, double* xdev, const double* bdev) {
 extern "C" {
 
 int smslu_version(void) { return 100; }
+int smslu_debug_trace(int64_t* out32) { return out32 ? debug_read_trace((long long*)out32) : SMSLU_E_ARG; }
 int smslu_allocate_shared(void) { return 0; }
 
 int smslu_host_alloc(void** ptr, int64_t bytes) {

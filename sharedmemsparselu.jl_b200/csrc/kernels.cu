@@ -5,6 +5,16 @@
 
 namespace smslu {
 
+// Optional phase timestamps (build with SMSLU_TRACE=1): CTA 0 of the most recent k_panel launch records
+// clock64() at its phase boundaries; slots 0-7 = row warp 0, 8-15 = pivot warp.
+#ifdef SMSLU_TRACE
+__device__ long long g_trace[32];
+#define TRACE(i) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && ((threadIdx.x >> 5) == 0 || (threadIdx.x >> 5) == 4)) \
+        g_trace[(i) + ((threadIdx.x >> 5) == 4 ? 8 : 0)] = clock64(); } while (0)
+#else
+#define TRACE(i) do {} while (0)
+#endif
+
 namespace {
 
 struct Front {
@@ -220,190 +230,156 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // ------------------------------------------------------------------ panel step of a big front
 // A front with k (<= KW) pivot columns is factored in ceil(k/32) left-looking panel steps, one
 // launch each.  Step g owns pivot columns [j0, j1) = [32g, min(k, 32g+32)):
-//   kind 0 (L): 128 rows of P below the diagonal block (the rest of the pivot block and L21):
+//   kind 0 (L): ROWS rows of P below the diagonal block (the rest of the pivot block and L21):
 //               row <- (row[j0:j1] - row[0:j0] * U[0:j0, j0:j1]) * U_gg^{-1}
-//   kind 1 (T): 128 rows of U12' :  row <- (row[j0:j1] - row[0:j0] * L[j0:j1, 0:j0]') * L_gg^{-T}
-//   kind 2 (I): 128 columns of the pivot block right of the diagonal block (U inside the block),
+//   kind 1 (T): ROWS rows of U12' :  row <- (row[j0:j1] - row[0:j0] * L[j0:j1, 0:j0]') * L_gg^{-T}
+//   kind 2 (I): ROWS columns of the pivot block right of the diagonal block (U inside the block),
 //               same arithmetic as kind 1 on P[j0:j1, c].
-// CTA = 4 row warps + 1 pivot warp, working concurrently between two barriers:
-//   row warps  : the left-looking update of their 32 rows x 32 columns on the FP64 tensor pipe (DMMA
-//                m8n8k4, 4 x 4 accumulator tiles per warp, A fragments straight from global memory with
-//                one k-step of prefetch, B fragments from the staged coefficient block), then the tile is
-//                transposed through shared memory so that every thread holds one row in registers;
-//   pivot warp : D_gg -= L[g, 0:j0] U[0:j0, g] (DMMA), then the 32 x 32 LU with one row per lane, all 32
-//                columns in registers, pivot row broadcast by shuffles, reciprocal pivots -- no barriers.
-//   after the second barrier the row threads solve against the factored block (registers, 128-bit
-//   shared-memory loads of the factor rows) and store their 32 values.
-// Every CTA factors the diagonal block redundantly; the CTA that is last to have read the raw block
-// stores the factors and the reciprocal pivots (nobody waits).
+// One CTA = 16 warps, four phases separated by barriers:
+//   S  stage D_gg and the two j0 x 32 coefficient blocks in shared memory with cp.async (every element
+//      is in flight at once; out-of-range elements are zero-filled by the copy itself);
+//   U  left-looking update on the FP64 tensor pipe (DMMA m8n8k4): the ROWS x 32 row block and the
+//      32 x 32 diagonal block are cut into pieces of 8 rows x 16 columns that the warps take round-robin
+//      (one warp can issue a DMMA only every ~45 cycles, so latency needs many warps, not big tiles);
+//      A fragments of the row strips come straight from global memory (one k-step of prefetch);
+//   L  warp 0 factors the diagonal block: one row per lane, all 32 columns in registers, pivot row by
+//      shuffles, reciprocal pivots; it then publishes the factor rows (W) and, if this CTA was the last
+//      of the step to have read the raw block, stores the block and the reciprocal pivots (nobody waits);
+//   T  thread = row: solve against the factored block from registers (128-bit loads of W) and store.
+// ROWS = 128 when a level has enough fronts to fill the machine, 32 near the top of the tree where the
+// latency of a single CTA is what matters.
 // task: x = supernode, y = g | kind << 4 | (CTAs of this step of this front) << 8, z = tile,
 //       w = index of the step's arrival counter.
-// dynamic shared memory: (2 * j0 + 128) * CLD doubles (two coefficient blocks + transposition buffers).
-constexpr int PANEL_THREADS = PANEL_ROWS + 32;
+// dynamic shared memory: (2 * j0 + ROWS) * CLD doubles.
+constexpr int PANEL_THREADS = 512;
 constexpr int CLD = NB + 2;           // even row stride: 128-bit aligned pairs
 
+__device__ __forceinline__ void cp_async8(double* dst_smem, const double* src, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    const int nbytes = valid ? 8 : 0;                 // src-size 0: the 8 bytes are zero-filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(nbytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int ROWS>
 __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* __restrict__ tasks) {
     extern __shared__ __align__(16) double dsm[];
     __shared__ __align__(16) double D[NB][CLD];     // diagonal block, D[i][c]
     __shared__ __align__(16) double W[NB][CLD];     // W[p][c] = U[p][c] (kind 0) or L[c][p] (kinds 1, 2)
     __shared__ double rd[NB];
-    __shared__ int s_last;
+    TRACE(0);
     int4 tk = tasks[blockIdx.x];
     const Front F = load_front(cx, tk.x);
     const int g = tk.y & 15, kind = (tk.y >> 4) & 15, total = tk.y >> 8;
     const int k = F.k, j0 = g * NB, w = (k - j0 < NB) ? k - j0 : NB, j1 = j0 + w;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, fr = lane >> 2, fc = lane & 3;
+    TRACE(1);
     double* Uc = dsm;                               // Uc[m * CLD + c] = U[m, j0 + c],  m < j0
     double* Lc = dsm + j0 * CLD;                    // Lc[m * CLD + i] = L[j0 + i, m],  m < j0
-    double* Xs = dsm + 2 * j0 * CLD;                // Xs[warp][32][CLD]
-    // ---- stage D_gg and the two coefficient blocks, 8 loads in flight per thread
+    double* Xs = dsm + 2 * j0 * CLD;                // Xs[row][CLD]: updated rows, one per thread in phase T
+    // ---- S: stage D_gg and the coefficient blocks
     {
         const double* __restrict__ Pg = F.P;
-        double t[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int e = u * PANEL_THREADS + tid, i = e & 31, c = e >> 5;
-            t[u] = (e < NB * NB && i < w && c < w) ? Pg[(j0 + i) + (int64_t)(j0 + c) * F.f] : 0.0;
+        constexpr int NW = PANEL_THREADS / 32;
+        {
+            const bool ok = lane < w;
+            for (int c = warp; c < NB; c += NW)                           // D[i][c], lanes = rows
+                cp_async8(&D[lane][c], Pg + ((ok && c < w) ? (j0 + lane) + (int64_t)(j0 + c) * F.f : 0), ok && c < w);
+            for (int m = warp; m < j0; m += NW)                           // Lc[m][i] = L[j0+i, m], lanes = rows
+                cp_async8(Lc + m * CLD + lane, Pg + (ok ? (j0 + lane) + (int64_t)m * F.f : 0), ok);
         }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) { const int e = u * PANEL_THREADS + tid; if (e < NB * NB) D[e & 31][e >> 5] = t[u]; }
-        const int tot = j0 * NB;
-        for (int e0 = 0; e0 < tot; e0 += 8 * PANEL_THREADS) {          // Lc: (m, i) -> L[j0+i, m]
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int e = e0 + u * PANEL_THREADS + tid, i = e & 31, m = e >> 5;
-                t[u] = (e < tot && i < w) ? Pg[(j0 + i) + (int64_t)m * F.f] : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) { const int e = e0 + u * PANEL_THREADS + tid; if (e < tot) Lc[(e >> 5) * CLD + (e & 31)] = t[u]; }
+        for (int c = warp; c < NB; c += NW) {                             // Uc[m][c] = U[m, j0+c], lanes = m
+            const bool ok = c < w;
+            const double* __restrict__ src = Pg + (ok ? (int64_t)(j0 + c) * F.f : 0);
+            for (int m = lane; m < j0; m += 32) cp_async8(Uc + m * CLD + c, src + (ok ? m : 0), ok);
         }
-        for (int e0 = 0; e0 < tot; e0 += 8 * PANEL_THREADS) {          // Uc: (m, c) -> U[m, j0+c]
+        cp_async_wait_all();
+    }
+    __syncthreads();
+    TRACE(2);
+    // ---- U: left-looking update, strips of 8 rows x 32 columns (4 DMMA tiles) round-robin over the warps
+    const int64_t stride = kind == 0 ? F.f : (kind == 1 ? F.r : 1);
+    auto row_ptr = [&](int64_t idx, double*& b, bool& act) {
+        if (kind == 0) { act = j1 + idx < F.f; b = F.P + j1 + idx; }
+        else if (kind == 1) { act = idx < F.r; b = F.T + idx; }
+        else { act = j1 + idx < k; b = F.P + (j1 + idx) * F.f; }
+    };
+    const double* cf = kind == 0 ? Uc : Lc;
+    constexpr int NPIECE = (ROWS / 8 + 4) * 2;      // pieces of 8 rows x 16 columns (2 DMMA tiles)
+    for (int pc = warp; pc < NPIECE; pc += PANEL_THREADS / 32) {
+        const int st = pc >> 1, ch = (pc & 1) * 16;
+        double acc[2][2];
+        if (st < ROWS / 8) {                        // a piece of the row block
+            double* fb; bool fa;
+            row_ptr((int64_t)tk.z * ROWS + st * 8 + fr, fb, fa);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int e = e0 + u * PANEL_THREADS + tid, q = e >> 5, c = q / g, m = (q - c * g) * 32 + (e & 31);
-                t[u] = (e < tot && c < w) ? Pg[m + (int64_t)(j0 + c) * F.f] : 0.0;
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int c = ch + 8 * j + 2 * fc + e;
+                    acc[j][e] = (fa && c < w) ? fb[(int64_t)(j0 + c) * stride] : 0.0;
+                }
+            if (j0 > 0) {
+                double an = fa ? -fb[(int64_t)fc * stride] : 0.0;
+                double an2 = (fa && j0 > 4) ? -fb[(int64_t)(4 + fc) * stride] : 0.0;
+                for (int m0 = 0; m0 < j0; m0 += 4) {
+                    const double a = an;
+                    an = an2;
+                    if (m0 + 8 < j0) an2 = fa ? -fb[(int64_t)(m0 + 8 + fc) * stride] : 0.0;
+                    const double* __restrict__ cm = cf + (m0 + fc) * CLD + ch + fr;
+                    dmma884(acc[0][0], acc[0][1], a, cm[0]);
+                    dmma884(acc[1][0], acc[1][1], a, cm[8]);
+                }
+            }
+            double* xs = Xs + (st * 8 + fr) * CLD + ch + 2 * fc;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) *reinterpret_cast<double2*>(xs + 8 * j) = make_double2(acc[j][0], acc[j][1]);
+        } else if (j0 > 0) {                        // a piece of the diagonal block: D -= L[g, 0:j0] U[0:j0, g]
+            const int i0 = (st - ROWS / 8) * 8;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const double2 v = *reinterpret_cast<const double2*>(&D[i0 + fr][ch + 8 * j + 2 * fc]);
+                acc[j][0] = v.x; acc[j][1] = v.y;
+            }
+            for (int m0 = 0; m0 < j0; m0 += 4) {
+                const double a = -Lc[(m0 + fc) * CLD + i0 + fr];
+                const double* __restrict__ cm = Uc + (m0 + fc) * CLD + ch + fr;
+                dmma884(acc[0][0], acc[0][1], a, cm[0]);
+                dmma884(acc[1][0], acc[1][1], a, cm[8]);
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int e = e0 + u * PANEL_THREADS + tid, q = e >> 5, c = q / g, m = (q - c * g) * 32 + (e & 31);
-                if (e < tot) Uc[m * CLD + c] = t[u];
-            }
+            for (int j = 0; j < 2; ++j)
+                *reinterpret_cast<double2*>(&D[i0 + fr][ch + 8 * j + 2 * fc]) = make_double2(acc[j][0], acc[j][1]);
         }
     }
     __syncthreads();
-    if (tid == 0) {   // this CTA's reads of the raw diagonal block are complete
-        __threadfence();
-        int old = atomicAdd(cx.counters + tk.w, 1);
-        s_last = ((old + 1) % total) == 0;
-    }
-    double x[NB];                                   // row warps: one row; pivot warp: row `lane` of the block
-    double* base = nullptr; int64_t stride = 1; bool active = false;
-    if (warp < 4) {
-        // ---- row warps: left-looking update of 32 rows x 32 columns
-        const double* cf = kind == 0 ? Uc : Lc;
-        const int64_t idx0 = (int64_t)tk.z * PANEL_ROWS + warp * 32;
-        auto row_ptr = [&](int64_t idx, double*& b, bool& act) {
-            if (kind == 0) { act = j1 + idx < F.f; b = F.P + j1 + idx; }
-            else if (kind == 1) { act = idx < F.r; b = F.T + idx; }
-            else { act = j1 + idx < k; b = F.P + (j1 + idx) * F.f; }
-        };
-        stride = kind == 0 ? F.f : (kind == 1 ? F.r : 1);
-        double acc[4][4][2];
-        const double* fb[4]; bool fa[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { double* b; row_ptr(idx0 + 8 * i + fr, b, fa[i]); fb[i] = b; }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int c = 8 * j + 2 * fc + e;
-                    acc[i][j][e] = (fa[i] && c < w) ? fb[i][(int64_t)(j0 + c) * stride] : 0.0;
-                }
-        if (j0 > 0) {
-            double an[4], bn[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) an[i] = fa[i] ? -fb[i][(int64_t)fc * stride] : 0.0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) bn[j] = cf[fc * CLD + 8 * j + fr];
-            for (int m0 = 0; m0 < j0; m0 += 4) {
-                double a[4], b[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { a[i] = an[i]; b[i] = bn[i]; }
-                if (m0 + 4 < j0) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) an[i] = fa[i] ? -fb[i][(int64_t)(m0 + 4 + fc) * stride] : 0.0;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) bn[j] = cf[(m0 + 4 + fc) * CLD + 8 * j + fr];
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-            }
-        }
-        double* xs = Xs + warp * 32 * CLD;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                *reinterpret_cast<double2*>(xs + (8 * i + fr) * CLD + 8 * j + 2 * fc) = make_double2(acc[i][j][0], acc[i][j][1]);
-        __syncwarp();
-#pragma unroll
-        for (int c2 = 0; c2 < NB / 2; ++c2) {
-            const double2 v = *reinterpret_cast<const double2*>(xs + lane * CLD + 2 * c2);
-            x[2 * c2] = v.x; x[2 * c2 + 1] = v.y;
-        }
-        row_ptr(idx0 + lane, base, active);
-    } else {
-        // ---- pivot warp: bring the diagonal block up to date, then factor it in registers
-        if (j0 > 0) {
-            double acc[4][4][2];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const double2 v = *reinterpret_cast<const double2*>(&D[8 * i + fr][8 * j + 2 * fc]);
-                    acc[i][j][0] = v.x; acc[i][j][1] = v.y;
-                }
-            for (int m0 = 0; m0 < j0; m0 += 4) {
-                double a[4], b[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) a[i] = -Lc[(m0 + fc) * CLD + 8 * i + fr];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) b[j] = Uc[(m0 + fc) * CLD + 8 * j + fr];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    *reinterpret_cast<double2*>(&D[8 * i + fr][8 * j + 2 * fc]) = make_double2(acc[i][j][0], acc[i][j][1]);
-            __syncwarp();
-        }
+    TRACE(3);
+    double x[NB];
+    // ---- L: warp 0 factors the diagonal block
+    if (warp == 0) {
 #pragma unroll
         for (int c2 = 0; c2 < NB / 2; ++c2) {
             const double2 v = *reinterpret_cast<const double2*>(&D[lane][2 * c2]);
             x[2 * c2] = v.x; x[2 * c2 + 1] = v.y;
         }
+        // a partial block (w < 32) is padded with the identity, so that all 32 steps run without a special case
+#pragma unroll
+        for (int c = 0; c < NB; ++c) x[c] = (lane >= w && c == lane) ? 1.0 : x[c];
+        double myr = 0.0;                          // 1 / u_jj of this lane's row
+        int bad = NB;                              // first bad pivot (uniform across the warp)
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
-            if (j >= w) break;
             const double piv = __shfl_sync(0xffffffffu, x[j], j);
             const double rinv = 1.0 / piv;
+            bad = (bad == NB && bad_pivot(piv)) ? j : bad;
+            myr = lane == j ? rinv : myr;
             const double l = lane > j ? x[j] * rinv : 0.0;
-            if (lane > j) x[j] = l;
-            if (lane == j) {
-                if (bad_pivot(piv)) atomicMin(cx.flag, F.c0 + j0 + j);
-                rd[j] = rinv;
-            }
+            x[j] = lane > j ? l : x[j];
 #pragma unroll
             for (int c = j + 1; c < NB; ++c) x[c] -= l * __shfl_sync(0xffffffffu, x[c], j);
         }
+        rd[lane] = myr;
+        if (lane == 0 && bad < w) atomicMin(cx.flag, F.c0 + j0 + bad);
         if (kind == 0) {                           // W[p][c] = U[p][c]: lane p stores its row
 #pragma unroll
             for (int c2 = 0; c2 < NB / 2; ++c2) *reinterpret_cast<double2*>(&W[lane][2 * c2]) = make_double2(x[2 * c2], x[2 * c2 + 1]);
@@ -412,19 +388,38 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
             for (int p = 0; p < NB; ++p) W[p][lane] = x[p];
         }
     }
+    TRACE(4);
     __syncthreads();
-    if (warp == 4) {
-        // the CTA that read the raw block last stores the factors (column by column: lanes = rows)
-        if (s_last && lane < w) {
+    TRACE(5);
+    if (warp == 0) {
+        // this CTA's reads of the raw diagonal block completed in phase S; the CTA that arrives last
+        // stores the factors (column by column: lanes = rows) and the reciprocal pivots
+        int last = 0;
+        if (lane == 0) {
+            __threadfence();
+            const int old = atomicAdd(cx.counters + tk.w, 1);
+            last = ((old + 1) % total) == 0;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last && lane < w) {
             double* __restrict__ dst = F.P + (j0 + lane) + (int64_t)j0 * F.f;
 #pragma unroll
             for (int c = 0; c < NB; ++c) if (c < w) dst[(int64_t)c * F.f] = x[c];
             cx.dinv[F.c0 + j0 + lane] = rd[lane];
         }
-        return;
     }
+    // ---- T: thread = row; warp 0 is busy storing the block, so the rows start at warp 1 when ROWS < 224
+    constexpr int T0 = ROWS <= PANEL_THREADS - 32 ? 32 : 0;
+    const int row = tid - T0;
+    if (row < 0 || row >= ROWS) return;
+    double* base; bool active;
+    row_ptr((int64_t)tk.z * ROWS + row, base, active);
     if (!active) return;
-    // ---- solve the row against the factored block
+#pragma unroll
+    for (int c2 = 0; c2 < NB / 2; ++c2) {
+        const double2 v = *reinterpret_cast<const double2*>(Xs + row * CLD + 2 * c2);
+        x[2 * c2] = v.x; x[2 * c2 + 1] = v.y;
+    }
 #pragma unroll
     for (int p = 0; p < NB; ++p) {
         if (p >= w) break;
@@ -438,6 +433,7 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
             x[2 * c2 + 1] -= xp * wv.y;
         }
     }
+    TRACE(6);
 #pragma unroll
     for (int c = 0; c < NB; ++c) if (c < w) base[(int64_t)(j0 + c) * stride] = x[c];
 }
@@ -857,17 +853,28 @@ __global__ void __launch_bounds__(32 * FPC) k_small_bwd(DevCtx cx, const int4* _
 
 int front_small_limit() { return SMALL_F_MAX; }
 
+int debug_read_trace(long long* out) {
+#ifdef SMSLU_TRACE
+    return cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 32) == cudaSuccess ? 32 : -1;
+#else
+    (void)out;
+    return 0;
+#endif
+}
+
 constexpr int SMALL_FPC32 = 4;     // fronts per CTA in the one-warp class of k_small_factor
 constexpr int SOLVE_FPC = 8;       // fronts per CTA in the small solve kernels
 
-static size_t panel_smem(int j0) { return sizeof(double) * (2 * (size_t)j0 + PANEL_ROWS) * CLD; }
+static size_t panel_smem(int j0, int rows) { return sizeof(double) * (2 * (size_t)j0 + rows) * CLD; }
 static size_t solve_smem(int kmax) { size_t kp = (size_t)((kmax + NB - 1) / NB) * NB; return sizeof(double) * kp * (kp + 1); }
 
 cudaError_t kernels_init() {
     cudaError_t e = cudaFuncSetAttribute(k_small_factor<96, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(sizeof(double) * small_group_doubles(96)));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem(KW - NB));
+    e = cudaFuncSetAttribute(k_panel<PANEL_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem(KW - NB, PANEL_ROWS));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_panel<PANEL_ROWS_TOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem(KW - NB, PANEL_ROWS_TOP));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem(KW));
     if (e != cudaSuccess) return e;
@@ -913,8 +920,10 @@ void launch_small_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int 
 void launch_small_bwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, double* x) {
     if (ntasks > 0) k_small_bwd<SOLVE_FPC><<<(ntasks + SOLVE_FPC - 1) / SOLVE_FPC, 32 * SOLVE_FPC, 0, st>>>(cx, tasks, ntasks, x);
 }
-void launch_panel(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int g) {
-    if (ntasks > 0) k_panel<<<ntasks, PANEL_THREADS, panel_smem(g * NB), st>>>(cx, tasks);
+void launch_panel(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int g, int rows) {
+    if (ntasks <= 0) return;
+    if (rows == PANEL_ROWS) k_panel<PANEL_ROWS><<<ntasks, PANEL_THREADS, panel_smem(g * NB, PANEL_ROWS), st>>>(cx, tasks);
+    else k_panel<PANEL_ROWS_TOP><<<ntasks, PANEL_THREADS, panel_smem(g * NB, PANEL_ROWS_TOP), st>>>(cx, tasks);
 }
 void launch_gemm_cb(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks) {
     if (ntasks > 0) k_gemm_cb<<<ntasks, 256, 0, st>>>(cx, tasks);

@@ -19,7 +19,8 @@ namespace smslu {
 constexpr int NB = 32;            // panel block: pivot columns eliminated per panel step
 constexpr int KW = 128;           // widest pivot block of a front (symbolic chains wider supernodes)
 constexpr int KMAX = KW;
-constexpr int PANEL_ROWS = 128;   // rows of L21 / U12' handled by one panel CTA
+constexpr int PANEL_ROWS = 128;   // rows of L21 / U12' handled by one panel CTA (levels with many fronts)
+constexpr int PANEL_ROWS_TOP = 32; // ... near the top of the tree, where one CTA's latency is what matters
 constexpr int GEMM_TILE = 64;
 constexpr int SOLVE_THREADS = 256;
 constexpr int FWD_ROWS = 64;      // update rows per forward CTA (4 threads per row)
@@ -70,10 +71,11 @@ void launch_vgather(cudaStream_t st, const DevCtx& cx, const int4* tasks, int nt
 void launch_mask_owned(cudaStream_t st, int n, const int* colowner, int rank, double* z);
 void launch_small_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const double* win, double* zout);
 void launch_small_bwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, double* x);
-void launch_panel(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int g);
+void launch_panel(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int g, int rows);
 void launch_gemm_cb(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks);
 int front_small_limit();   // largest front the fused shared-memory kernel takes
 cudaError_t kernels_init();
+int debug_read_trace(long long* out);   // 0 unless built with SMSLU_TRACE
 
 // ---- solves
 void launch_permute_scale(cudaStream_t st, int n, const int* p, const double* Rs, const double* b, double* w);
