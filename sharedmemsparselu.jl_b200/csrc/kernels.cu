@@ -235,7 +235,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 //   kind 1 (T): ROWS rows of U12' :  row <- (row[j0:j1] - row[0:j0] * L[j0:j1, 0:j0]') * L_gg^{-T}
 //   kind 2 (I): ROWS columns of the pivot block right of the diagonal block (U inside the block),
 //               same arithmetic as kind 1 on P[j0:j1, c].
-// One CTA = 16 warps, four phases separated by barriers:
+// One CTA = 8 warps, four phases separated by barriers:
 //   S  stage D_gg and the two j0 x 32 coefficient blocks in shared memory with cp.async (every element
 //      is in flight at once; out-of-range elements are zero-filled by the copy itself);
 //   U  left-looking update on the FP64 tensor pipe (DMMA m8n8k4): the ROWS x 32 row block and the
@@ -251,7 +251,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // task: x = supernode, y = g | kind << 4 | (CTAs of this step of this front) << 8, z = tile,
 //       w = index of the step's arrival counter.
 // dynamic shared memory: (2 * j0 + ROWS) * CLD doubles.
-constexpr int PANEL_THREADS = 512;
+constexpr int PANEL_THREADS = 256;
 constexpr int CLD = NB + 2;           // even row stride: 128-bit aligned pairs
 
 __device__ __forceinline__ void cp_async8(double* dst_smem, const double* src, bool valid) {
