@@ -61,6 +61,7 @@ struct smslu_handle_s {
     int *d_p = nullptr, *d_q = nullptr;
     double *d_Rs = nullptr, *d_aval = nullptr, *d_w = nullptr, *d_z = nullptr, *d_xb = nullptr;
     int4* d_tasks = nullptr;
+    std::vector<int> asm_meta;                       // (child, first column) pairs of the assembly tasks
     std::vector<Launch> fac, fwd, bwd;               // this rank's supernodes (everything when nranks == 1)
     std::vector<Launch> fac_top, fwd_top, bwd_top;   // top of the tree, replicated on every rank
     int rank = 0, nranks = 1;
@@ -181,23 +182,34 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
                 int s = sn[t];
                 if (SMALL(s) || NC(s) == 0) continue;                 // small parents pull their children
                 if (!(IN(s) || (ph == 0 && S.owner[s] == -1))) continue;
-                bool any = false;
+                std::vector<int> kids;
                 for (int u = S.child_ptr[s]; u < S.child_ptr[s + 1]; ++u) {
                     const int c = S.child_idx[u];
-                    if (IN(c) && !S.direct[c] && R(c) > 0) any = true;
+                    if (IN(c) && !S.direct[c] && R(c) > 0) kids.push_back(c);
                 }
-                if (!any) continue;
+                if (kids.empty()) continue;
                 const bool zero = IN(s) && R(s) > 0 && !S.iface[s];
                 const int64_t f = K(s) + R(s);
-                for (int64_t pb0 = 0; pb0 < f; pb0 += ASM_COLS)
-                    tasks.push_back(make_int4(s, (int)pb0, (int)std::min<int64_t>(ASM_COLS, f - pb0),
-                                              (zero ? 1 : 0) | ((mine + 1) << 1)));
+                for (int64_t pb0 = 0; pb0 < f; pb0 += ASM_COLS) {
+                    const int64_t moff = (int64_t)h->asm_meta.size();
+                    int np = 0;
+                    for (int c : kids) {            // first column of c whose parent position is >= pb0
+                        const int* rb = S.rel.data() + S.rows_ptr[c];
+                        const int* re = S.rel.data() + S.rows_ptr[c + 1];
+                        const int* it = std::lower_bound(rb, re, (int)pb0);
+                        if (it == re || *it >= pb0 + ASM_COLS) continue;       // nothing of c lands in this range
+                        h->asm_meta.push_back(c); h->asm_meta.push_back((int)(it - rb));
+                        ++np;
+                    }
+                    if (np == 0 && !zero) continue;
+                    tasks.push_back(make_int4(s, (int)pb0, (int)moff, (zero ? 1 : 0) | (np << 8)));
+                }
             }
             push(fac, L_EXTEND, off, 0);
             // small fronts by shared-memory class
-            const int classes[3] = {32, 64, front_small_limit()};
+            const int classes[5] = {32, 40, 48, 64, front_small_limit()};
             int lo = 0;
-            for (int ci = 0; ci < 3; ++ci) {
+            for (int ci = 0; ci < 5; ++ci) {
                 off = (int64_t)tasks.size();
                 for (int t = 0; t < cnt; ++t) {
                     int s = sn[t];
@@ -369,10 +381,6 @@ int ensure_uploaded(smslu_handle_t h) {
     if ((rc = dev_upload(h, &d_Uoff, S.Uoff))) return rc;
     if ((rc = dev_upload(h, &d_CBoff, S.CBoff))) return rc;
     if ((rc = dev_upload(h, &d_sn_parent, S.sn_parent))) return rc;
-    int *d_asm_child_ptr, *d_asm_child_idx, *d_owner;
-    if ((rc = dev_upload(h, &d_asm_child_ptr, S.child_ptr))) return rc;
-    if ((rc = dev_upload(h, &d_asm_child_idx, S.child_idx))) return rc;
-    if ((rc = dev_upload(h, &d_owner, S.owner))) return rc;
     if ((rc = dev_upload(h, &d_child_ptr, child_ptr_d))) return rc;
     if ((rc = dev_upload(h, &d_child_idx, child_idx_d))) return rc;
     if ((rc = dev_upload(h, &h->d_p, S.p))) return rc;
@@ -438,6 +446,9 @@ int ensure_uploaded(smslu_handle_t h) {
     std::vector<int4> tasks;
     build_schedules(h, tasks);
     if ((rc = dev_upload(h, &h->d_tasks, tasks))) return rc;
+    int* d_asm_meta;
+    if ((rc = dev_upload(h, &d_asm_meta, h->asm_meta))) return rc;
+    h->cx.asm_meta = d_asm_meta;
     double* d_bpart; int* d_counters2;
     if ((rc = dev_alloc(h, &d_counters, (size_t)h->ncounters))) return rc;
     if ((rc = dev_alloc(h, &d_bpart, (size_t)h->bpart_slots * KMAX))) return rc;
@@ -449,7 +460,6 @@ int ensure_uploaded(smslu_handle_t h) {
     cx.child_ptr = d_child_ptr; cx.child_idx = d_child_idx;
     cx.lu = d_lu; cx.cb = d_cb; cx.upd = d_upd; cx.counters = d_counters; cx.flag = d_flag;
     cx.bpart = d_bpart; cx.counters2 = d_counters2; cx.dinv = d_dinv;
-    cx.asm_child_ptr = d_asm_child_ptr; cx.asm_child_idx = d_asm_child_idx; cx.owner = d_owner;
     cx.a_ptr = d_a_ptr; cx.a_src = d_a_src; cx.a_row = d_a_row; cx.a_pos = d_a_pos;
     CU(cudaDeviceSynchronize());
     h->uploaded = true;

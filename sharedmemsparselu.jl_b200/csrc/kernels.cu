@@ -40,7 +40,8 @@ __device__ __forceinline__ Front load_front(const DevCtx& cx, int s) {
 __device__ __forceinline__ bool bad_pivot(double p) { return !(fabs(p) > 0.0) || !isfinite(p); }
 
 constexpr int SMALL_F_MAX = 96;   // largest front handled by the shared-memory kernels (with k <= NB)
-__host__ __device__ constexpr int small_group_doubles(int fmax) { return fmax * (fmax | 1) + NB; }
+__host__ __device__ constexpr int small_ld(int f) { return f + ((6 - (f & 3)) & 3); }   // smallest ld >= f with ld = 2 (mod 4)
+__host__ __device__ constexpr int small_group_doubles(int fmax) { return fmax * small_ld(fmax) + NB; }
 
 // ------------------------------------------------------------------ row scaling (UMFPACK "SUM")
 __global__ void k_rowscale(int n, const int64_t* __restrict__ rowptr, const int64_t* __restrict__ rowidx,
@@ -81,12 +82,16 @@ __global__ void __launch_bounds__(256) k_zero_cb(DevCtx cx, const int4* __restri
 // in row pb-k of U12' (rows pa < k) and in column pb-k of the contribution block (rows pa >= k), which the
 // CTA zero-fills first when asked to.  rel is ascending, so a child's columns that fall into the CTA's
 // range are found by binary search.
-// task: x = parent, y = pb0, z = ncols, w = (zero ? 1 : 0) | (owner filter + 1) << 1.
+// The host precomputes, per task, the list of (child, first child column that falls into the range):
+// the kernel's chain of dependent global loads is task -> child record -> rel -> data.
+// task: x = parent, y = pb0, z = offset of the task's (child, lo) pairs in asm_meta, w = zero flag | pairs << 8.
 __global__ void __launch_bounds__(256) k_assemble(DevCtx cx, const int4* __restrict__ tasks) {
     const int4 tk = tasks[blockIdx.x];
-    const int s = tk.x, pb0 = tk.y, pb1 = tk.y + tk.z, filt = (tk.w >> 1) - 1;
+    const int s = tk.x, pb0 = tk.y, nch = tk.w >> 8;
+    const int* __restrict__ meta = cx.asm_meta + tk.z;
     const Front F = load_front(cx, s);
     const int k = F.k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pb1 = pb0 + ASM_COLS < (int)F.f ? pb0 + ASM_COLS : (int)F.f;
     if (tk.w & 1) {
         const int c_lo = pb0 > k ? pb0 - k : 0, c_hi = pb1 - k;      // contribution-block columns owned here
         if (c_hi > c_lo) {
@@ -96,29 +101,37 @@ __global__ void __launch_bounds__(256) k_assemble(DevCtx cx, const int4* __restr
         }
         __syncthreads();
     }
-    for (int ci = cx.asm_child_ptr[s]; ci < cx.asm_child_ptr[s + 1]; ++ci) {
-        const int c = cx.asm_child_idx[ci];
-        if (cx.owner[c] != filt) continue;
+    for (int q = 0; q < nch; ++q) {
+        const int c = meta[2 * q], lo = meta[2 * q + 1];
         const int rc = (int)(cx.rows_ptr[c + 1] - cx.rows_ptr[c]);
         const int* __restrict__ rel = cx.rel + cx.rows_ptr[c];
-        int lo = 0, hi = rc;                       // first b with rel[b] >= pb0
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (rel[mid] < pb0) lo = mid + 1; else hi = mid; }
         const double* __restrict__ Cc = cx.cb + cx.CBoff[c];
         for (int b = lo + warp; b < rc; b += 8) {
             const int pb = rel[b];
             if (pb >= pb1) break;
             const double* __restrict__ src = Cc + (int64_t)b * rc;
-            if (pb < k) {
-                double* __restrict__ dst = F.P + (int64_t)pb * F.f;
-                for (int a = lane; a < rc; a += 32) dst[rel[a]] += src[a];
-            } else {
-                double* __restrict__ dstC = F.C + (int64_t)(pb - k) * F.r - k;
-                double* __restrict__ dstT = F.T + (pb - k);
-                for (int a = lane; a < rc; a += 32) {
-                    const int pa = rel[a];
-                    if (pa < k) dstT[(int64_t)pa * F.r] += src[a];
-                    else dstC[pa] += src[a];
+            // destination of row position pa: P(:, pb) for pb < k; else row pb-k of U12' when pa < k,
+            // column pb-k of the contribution block otherwise.  rel is strictly ascending, so the four
+            // read-modify-writes of a batch never alias: their loads are issued together.
+            double* __restrict__ dP = F.P + (int64_t)pb * F.f;
+            double* __restrict__ dC = F.C + (int64_t)(pb - k) * F.r - k;
+            double* __restrict__ dT = F.T + (pb - k);
+            for (int a0 = lane; a0 < rc; a0 += 128) {
+                double* d[4]; double v[4], o[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int a = a0 + 32 * u;
+                    d[u] = nullptr; v[u] = 0.0;
+                    if (a < rc) {
+                        const int pa = rel[a];
+                        v[u] = src[a];
+                        d[u] = pb < k ? dP + pa : (pa < k ? dT + (int64_t)pa * F.r : dC + pa);
+                    }
                 }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) o[u] = d[u] ? *d[u] : 0.0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) if (d[u]) *d[u] = o[u] + v[u];
             }
         }
         __syncthreads();
@@ -128,13 +141,14 @@ __global__ void __launch_bounds__(256) k_assemble(DevCtx cx, const int4* __restr
 // ------------------------------------------------------------------ fused small front
 // A front with k <= 32 pivots and f <= SMALL_F_MAX rows is assembled, factored and stored by one
 // group of RW*CH threads entirely in shared memory ("pull" assembly):
-//   Fs (f x f, column-major, odd leading dimension) = 0
+//   Fs (f x f, ROW-major, leading dimension ld = 2 mod 4 so that 128-bit row accesses of consecutive
+//   lanes are conflict-free) = 0
 //   Fs += the entries of Rs .* A that land in this front      (per-front lists a_ptr/a_src/a_row/a_pos)
 //   Fs += contribution blocks of the children, child by child in ascending order (rel maps)
-//   right-looking elimination of the k pivots, one barrier per pivot: thread (i, h) owns row i and
-//   the columns c = j+1+h (mod CH); multipliers are formed as a_ij * (1/u_jj) on the fly and
-//   column j is left unscaled until the final copy-out, so no thread ever reads what another
-//   thread writes inside a step.  1/u_jj is produced by the thread that finishes u_jj.
+//   right-looking elimination of the k pivots, one barrier per pivot: thread (i, h) owns row i and the
+//   column pairs p = (j+1)/2 + h (mod CH), updated with 128-bit loads/stores; multipliers are formed as
+//   a_ij * (1/u_jj) on the fly and column j is left unscaled until the final copy-out, so no thread ever
+//   reads what another thread writes inside a step.  1/u_jj is produced by the thread that finishes u_jj.
 //   copy-out: P (f x k), T = U12' (r x k), C (r x r), dinv (reciprocal pivots for the solves).
 // Factor storage is written exactly once and never read here; nothing has to be zero-filled.
 // RW = row slots (>= f), CH = column interleave, FPC = fronts per CTA (FPC > 1 only with one warp
@@ -144,7 +158,7 @@ template <int RW, int CH, int FPC>
 __global__ void __launch_bounds__(RW * CH * FPC) k_small_factor(DevCtx cx, const int4* __restrict__ tasks, int ntasks,
                                                                  int fmax, const double* __restrict__ av,
                                                                  const double* __restrict__ Rs) {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) double sm[];
     constexpr int NT = RW * CH;
     static_assert(NT % 32 == 0 && (FPC == 1 || NT == 32), "group layout");
     const int grp = threadIdx.x / NT, tid = threadIdx.x % NT, lane = tid & 31, wrp = tid >> 5;
@@ -153,14 +167,17 @@ __global__ void __launch_bounds__(RW * CH * FPC) k_small_factor(DevCtx cx, const
     auto sync = [&]() { if (NT == 32) __syncwarp(); else __syncthreads(); };
     const int s = tasks[ti].x;
     const Front F = load_front(cx, s);
-    const int k = F.k, r = (int)F.r, f = (int)F.f, ld = f | 1;
-    double* Fs = sm + (size_t)grp * (small_group_doubles(fmax));
-    double* rd = Fs + (size_t)fmax * (fmax | 1);
-    for (int e = tid; e < f * ld; e += NT) Fs[e] = 0.0;
+    const int k = F.k, r = (int)F.r, f = (int)F.f, ld = small_ld(f);
+    double* Fs = sm + (size_t)grp * small_group_doubles(fmax);
+    double* rd = Fs + (size_t)fmax * small_ld(fmax);
+    {
+        double2* z = reinterpret_cast<double2*>(Fs);
+        for (int e = tid; e < f * ld / 2; e += NT) z[e] = make_double2(0.0, 0.0);
+    }
     sync();
     for (int e = cx.a_ptr[s] + tid; e < cx.a_ptr[s + 1]; e += NT) {
         const int pos = cx.a_pos[e];
-        Fs[(pos & 0xffff) + (pos >> 16) * ld] = Rs[cx.a_row[e]] * av[cx.a_src[e]];
+        Fs[(pos & 0xffff) * ld + (pos >> 16)] = Rs[cx.a_row[e]] * av[cx.a_src[e]];
     }
     sync();
     for (int ci = cx.child_ptr[s]; ci < cx.child_ptr[s + 1]; ++ci) {
@@ -169,8 +186,8 @@ __global__ void __launch_bounds__(RW * CH * FPC) k_small_factor(DevCtx cx, const
         const int* __restrict__ rel = cx.rel + cx.rows_ptr[c];
         const double* __restrict__ Cc = cx.cb + cx.CBoff[c];
         for (int b = wrp; b < rc; b += NT / 32) {
-            const int pb = rel[b] * ld;
-            for (int a = lane; a < rc; a += 32) Fs[rel[a] + pb] += Cc[a + (int64_t)b * rc];
+            const int pb = rel[b];
+            for (int a = lane; a < rc; a += 32) Fs[rel[a] * ld + pb] += Cc[a + (int64_t)b * rc];
         }
         sync();
     }
@@ -181,24 +198,35 @@ __global__ void __launch_bounds__(RW * CH * FPC) k_small_factor(DevCtx cx, const
     }
     sync();
     {
-        const int i = tid % RW, h = tid / RW;
-        double* row = Fs + i;
+        const int i = tid % RW, h = tid / RW, npair = ld >> 1;
+        double* myrow = Fs + i * ld;
         for (int j = 0; j < k; ++j) {
             if (i > j && i < f) {
-                const double l = row[j * ld] * rd[j];
-                const double* uj = Fs + j;
-                int c = j + 1 + h;
-                if (h == 0) {                                 // column j+1 holds the next pivot
-                    const double v = row[c * ld] - l * uj[c * ld];
-                    row[c * ld] = v;
-                    if (i == c && c < k) {
-                        if (bad_pivot(v)) atomicMin(cx.flag, F.c0 + c);
-                        rd[c] = 1.0 / v;
+                const double l = myrow[j] * rd[j];
+                const double2* __restrict__ prow = reinterpret_cast<const double2*>(Fs + j * ld);
+                double2* __restrict__ mrow = reinterpret_cast<double2*>(myrow);
+                int p = ((j + 1) >> 1) + h;
+                if (h == 0) {                                 // the pair holding column j+1: the next pivot
+                    const double2 u = prow[p];
+                    double2 v = mrow[p];
+                    if (2 * p > j) v.x -= l * u.x;
+                    v.y -= l * u.y;
+                    mrow[p] = v;
+                    if (i == j + 1 && i < k) {
+                        const double piv = (j & 1) ? v.x : v.y;
+                        if (bad_pivot(piv)) atomicMin(cx.flag, F.c0 + i);
+                        rd[i] = 1.0 / piv;
                     }
-                    c += CH;
+                    p += CH;
                 }
-#pragma unroll 4
-                for (; c < f; c += CH) row[c * ld] -= l * uj[c * ld];
+#pragma unroll 2
+                for (; p < npair; p += CH) {
+                    const double2 u = prow[p];
+                    double2 v = mrow[p];
+                    v.x -= l * u.x;
+                    v.y -= l * u.y;
+                    mrow[p] = v;
+                }
             }
             sync();
         }
@@ -206,15 +234,15 @@ __global__ void __launch_bounds__(RW * CH * FPC) k_small_factor(DevCtx cx, const
     for (int c = wrp; c < k; c += NT / 32) {                  // P: pivot block on top of L21
         const double rc = rd[c];
         double* __restrict__ dst = F.P + (int64_t)c * f;
-        for (int i = lane; i < f; i += 32) { const double v = Fs[i + c * ld]; dst[i] = i > c ? v * rc : v; }
+        for (int i = lane; i < f; i += 32) { const double v = Fs[i * ld + c]; dst[i] = i > c ? v * rc : v; }
     }
     for (int c = wrp; c < k; c += NT / 32) {                  // T = U12 transposed
         double* __restrict__ dst = F.T + (int64_t)c * r;
-        for (int b = lane; b < r; b += 32) dst[b] = Fs[c + (k + b) * ld];
+        for (int b = lane; b < r; b += 32) dst[b] = Fs[c * ld + k + b];
     }
     for (int b = wrp; b < r; b += NT / 32) {                  // contribution block for the parent
         double* __restrict__ dst = F.C + (int64_t)b * r;
-        for (int a = lane; a < r; a += 32) dst[a] = Fs[(k + a) + (k + b) * ld];
+        for (int a = lane; a < r; a += 32) dst[a] = Fs[(k + a) * ld + k + b];
     }
     if (tid < k) cx.dinv[F.c0 + tid] = rd[tid];
 }
@@ -897,16 +925,19 @@ void launch_zero_cb(cudaStream_t st, const DevCtx& cx, const int4* tasks, int nt
 void launch_assemble(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks) {
     if (ntasks > 0) k_assemble<<<ntasks, 256, 0, st>>>(cx, tasks);
 }
+template <int RW, int CH, int FPC>
+static void launch_small_class(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int fmax,
+                               const double* av, const double* Rs) {
+    k_small_factor<RW, CH, FPC><<<(ntasks + FPC - 1) / FPC, RW * CH * FPC,
+                                  sizeof(double) * small_group_doubles(fmax) * FPC, st>>>(cx, tasks, ntasks, fmax, av, Rs);
+}
 void launch_front_small(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int fmax,
                         const double* av, const double* Rs) {
     if (ntasks <= 0) return;
-    if (fmax <= 32)
-        k_small_factor<32, 1, SMALL_FPC32><<<(ntasks + SMALL_FPC32 - 1) / SMALL_FPC32, 32 * SMALL_FPC32,
-                                            sizeof(double) * small_group_doubles(32) * SMALL_FPC32, st>>>(cx, tasks, ntasks, 32, av, Rs);
-    else if (fmax <= 64)
-        k_small_factor<64, 2, 1><<<ntasks, 128, sizeof(double) * small_group_doubles(64), st>>>(cx, tasks, ntasks, 64, av, Rs);
-    else
-        k_small_factor<96, 3, 1><<<ntasks, 288, sizeof(double) * small_group_doubles(96), st>>>(cx, tasks, ntasks, 96, av, Rs);
+    if (fmax <= 32) launch_small_class<32, 1, SMALL_FPC32>(st, cx, tasks, ntasks, fmax, av, Rs);
+    else if (fmax <= 48) launch_small_class<64, 1, 1>(st, cx, tasks, ntasks, fmax, av, Rs);
+    else if (fmax <= 64) launch_small_class<64, 2, 1>(st, cx, tasks, ntasks, fmax, av, Rs);
+    else launch_small_class<96, 3, 1>(st, cx, tasks, ntasks, fmax, av, Rs);
 }
 void launch_vgather(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const int* vlist) {
     if (ntasks > 0) k_vgather<<<ntasks, 256, 0, st>>>(cx, tasks, vlist);

@@ -26,7 +26,7 @@ constexpr int SOLVE_THREADS = 256;
 constexpr int FWD_ROWS = 64;      // update rows per forward CTA (4 threads per row)
 constexpr int BWD_ROWS = 256;     // rows of U12' per backward CTA
 constexpr int ZERO_TILE = 8192;
-constexpr int ASM_COLS = 16;      // destination columns of a parent front per assembly CTA
+constexpr int ASM_COLS = 8;       // destination columns of a parent front per assembly CTA
 
 struct DevCtx {
     const int* sn_start;
@@ -52,11 +52,8 @@ struct DevCtx {
     const int* a_src;   // index into the caller's nzval
     const int* a_row;   // original row (for Rs)
     const int* a_pos;   // row | col << 16 inside the front
-    // the real child lists (child_ptr/child_idx may hold virtual children, see api.cu) and the owner
-    // of every supernode (-1 = top), for the assembly kernel
-    const int* asm_child_ptr;
-    const int* asm_child_idx;
-    const int* owner;
+    // assembly kernel: per task, the (child, first column in range) pairs it pulls
+    const int* asm_meta;
 };
 
 // ---- refactorization
