@@ -247,6 +247,103 @@ __global__ void __launch_bounds__(RW * CH * FPC) k_small_factor(DevCtx cx, const
     if (tid < k) cx.dinv[F.c0 + tid] = rd[tid];
 }
 
+// ------------------------------------------------------------------ fused small front, rows in registers
+// Fronts with f <= NC (NC = 32, 40, 48, 64): one thread per row, ceil(NC/32) warps per front (FPC fronts
+// per CTA when that is one warp).  Assembly in shared memory as in k_small_factor (row-major, ld = NC + 2),
+// then every thread takes its row into registers (NC doubles) and the elimination runs without touching
+// the front in shared memory again: the owner of row j publishes its (final) row and 1/u_jj in a double-
+// buffered strip, every thread reads it back with broadcast 128-bit loads and updates its own registers.
+// L21 / the pivot block go to HBM straight from registers (threads = rows: coalesced); U12' and the
+// contribution block are transposed through the shared-memory copy of the front.
+__host__ __device__ constexpr int reg_group_doubles(int nc) { return nc * (nc + 2) + 2 * (nc + 4) + NB; }
+
+template <int NC, int FPC>
+__global__ void __launch_bounds__(((NC + 31) / 32) * 32 * FPC) k_small_factor_reg(DevCtx cx, const int4* __restrict__ tasks, int ntasks,
+                                                                                  const double* __restrict__ av,
+                                                                                  const double* __restrict__ Rs) {
+    extern __shared__ __align__(16) double sm[];
+    constexpr int NT = ((NC + 31) / 32) * 32, ld = NC + 2, SL = NC + 4;
+    static_assert(FPC == 1 || NT == 32, "several fronts per CTA only with one warp per front");
+    const int grp = threadIdx.x / NT, tid = threadIdx.x % NT;
+    const int ti = blockIdx.x * FPC + grp;
+    if (ti >= ntasks) return;
+    auto sync = [&]() { if (NT == 32) __syncwarp(); else __syncthreads(); };
+    const int s = tasks[ti].x;
+    const Front F = load_front(cx, s);
+    const int k = F.k, r = (int)F.r, f = (int)F.f;
+    double* Fs = sm + (size_t)grp * reg_group_doubles(NC);
+    double* strip = Fs + NC * ld;                     // strip[2][SL]: row j (NC values), 1/u_jj at [NC]
+    double* rd = strip + 2 * SL;
+    {
+        double2* z = reinterpret_cast<double2*>(Fs);
+        for (int e = tid; e < f * ld / 2; e += NT) z[e] = make_double2(0.0, 0.0);
+    }
+    sync();
+    for (int e = cx.a_ptr[s] + tid; e < cx.a_ptr[s + 1]; e += NT) {
+        const int pos = cx.a_pos[e];
+        Fs[(pos & 0xffff) * ld + (pos >> 16)] = Rs[cx.a_row[e]] * av[cx.a_src[e]];
+    }
+    sync();
+    for (int ci = cx.child_ptr[s]; ci < cx.child_ptr[s + 1]; ++ci) {
+        const int c = cx.child_idx[ci];
+        const int rc = (int)(cx.rows_ptr[c + 1] - cx.rows_ptr[c]);
+        const int* __restrict__ rel = cx.rel + cx.rows_ptr[c];
+        const double* __restrict__ Cc = cx.cb + cx.CBoff[c];
+        const int pa = tid < rc ? rel[tid] * ld : 0;              // rc <= f <= NC <= NT
+        for (int b = 0; b < rc; ++b) {
+            const int pb = rel[b];
+            if (tid < rc) Fs[pa + pb] += Cc[tid + b * rc];
+        }
+        sync();
+    }
+    double x[NC];                                     // row `tid` of the front (zero beyond f)
+#pragma unroll
+    for (int p = 0; p < NC / 2; ++p) {
+        const double2 v = tid < f ? *reinterpret_cast<const double2*>(Fs + tid * ld + 2 * p) : make_double2(0.0, 0.0);
+        x[2 * p] = v.x; x[2 * p + 1] = v.y;
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+        if (j >= k) break;
+        double* sj = strip + (j & 1) * SL;
+        if (tid == j) {
+            const double piv = x[j];
+            if (bad_pivot(piv)) atomicMin(cx.flag, F.c0 + j);
+            const double rinv = 1.0 / piv;
+            sj[NC] = rinv;
+            rd[j] = rinv;
+#pragma unroll
+            for (int p = (j + 1) / 2; p < NC / 2; ++p) *reinterpret_cast<double2*>(sj + 2 * p) = make_double2(x[2 * p], x[2 * p + 1]);
+        }
+        sync();
+        const double l = tid > j ? x[j] * sj[NC] : 0.0;
+        x[j] = tid > j ? l : x[j];
+#pragma unroll
+        for (int p = (j + 1) / 2; p < NC / 2; ++p) {
+            const double2 u = *reinterpret_cast<const double2*>(sj + 2 * p);
+            if (2 * p > j) x[2 * p] -= l * u.x;
+            x[2 * p + 1] -= l * u.y;
+        }
+    }
+    // pivot block on top of L21: column c of P, threads = rows (multipliers are already scaled)
+    if (tid < f) {
+        double* __restrict__ dst = F.P + tid;
+#pragma unroll
+        for (int c = 0; c < NB; ++c) if (c < k) dst[(int64_t)c * f] = x[c];
+    }
+    sync();
+    if (tid < f) {
+#pragma unroll
+        for (int p = 0; p < NC / 2; ++p) *reinterpret_cast<double2*>(Fs + tid * ld + 2 * p) = make_double2(x[2 * p], x[2 * p + 1]);
+    }
+    sync();
+    if (tid < r) {
+        for (int c = 0; c < k; ++c) F.T[tid + (int64_t)c * r] = Fs[c * ld + k + tid];          // T[b + c r] = U[c][k + b]
+        for (int b = 0; b < r; ++b) F.C[tid + (int64_t)b * r] = Fs[(k + tid) * ld + k + b];    // contribution block
+    }
+    if (tid < k) cx.dinv[F.c0 + tid] = rd[tid];
+}
+
 // ------------------------------------------------------------------ FP64 tensor-core tile
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     // D(8x8) = A(8x4, row) * B(4x8, col) + C on the FP64 tensor pipe (SASS: DMMA.8x8x4).
@@ -934,8 +1031,13 @@ static void launch_small_class(cudaStream_t st, const DevCtx& cx, const int4* ta
 void launch_front_small(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int fmax,
                         const double* av, const double* Rs) {
     if (ntasks <= 0) return;
-    if (fmax <= 32) launch_small_class<32, 1, SMALL_FPC32>(st, cx, tasks, ntasks, fmax, av, Rs);
-    else if (fmax <= 48) launch_small_class<64, 1, 1>(st, cx, tasks, ntasks, fmax, av, Rs);
+    if (fmax <= 32)
+        k_small_factor_reg<32, SMALL_FPC32><<<(ntasks + SMALL_FPC32 - 1) / SMALL_FPC32, 32 * SMALL_FPC32,
+                                             sizeof(double) * reg_group_doubles(32) * SMALL_FPC32, st>>>(cx, tasks, ntasks, av, Rs);
+    else if (fmax <= 40)
+        k_small_factor_reg<40, 1><<<ntasks, 64, sizeof(double) * reg_group_doubles(40), st>>>(cx, tasks, ntasks, av, Rs);
+    else if (fmax <= 48)
+        k_small_factor_reg<48, 1><<<ntasks, 64, sizeof(double) * reg_group_doubles(48), st>>>(cx, tasks, ntasks, av, Rs);
     else if (fmax <= 64) launch_small_class<64, 2, 1>(st, cx, tasks, ntasks, fmax, av, Rs);
     else launch_small_class<96, 3, 1>(st, cx, tasks, ntasks, fmax, av, Rs);
 }
