@@ -11,8 +11,10 @@ namespace smslu {
 __device__ long long g_trace[32];
 #define TRACE(i) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && ((threadIdx.x >> 5) == 0 || (threadIdx.x >> 5) == 4)) \
         g_trace[(i) + ((threadIdx.x >> 5) == 4 ? 8 : 0)] = clock64(); } while (0)
+#define TRACE2(i) do { if (blockIdx.x == 0 && threadIdx.x == 0 && gridDim.x == 1) g_trace[16 + (i)] = clock64(); } while (0)
 #else
 #define TRACE(i) do {} while (0)
+#define TRACE2(i) do {} while (0)
 #endif
 
 namespace {
@@ -671,46 +673,91 @@ __global__ void k_unpermute(int n, const int* __restrict__ q, const double* __re
     if (i < n) x[q[i]] = w[i];
 }
 
-// Stage the k x k pivot block of a front (top of P, ld f) into shared memory Dk[i + c * ldk],
-// kp = k rounded up to 32; loads are issued 16 per thread at a time so their latencies overlap.
-__device__ __forceinline__ void stage_pivot_block(const Front& F, double* Dk, int ldk, int nthreads) {
-    const int k = F.k, nblk = (k + NB - 1) / NB, total = nblk * NB * k;   // (i in [0,kp), c in [0,k))
-    const int tid = threadIdx.x;
-    for (int e0 = 0; e0 < total; e0 += 16 * nthreads) {
-        double t[16];
+// Triangular solves with the k x k pivot block (k <= KW = 128) of a big front, without staging the block:
+// thread t < 128 owns row t and keeps its current right-hand-side value in a register; the pivot block is
+// consumed 32 columns (block g) at a time, every thread loading its 32 coefficients of the block straight
+// from global memory into registers one block ahead (each entry of the pivot block is used exactly once).
+// Warp g owns the rows of diagonal block g: it runs the 32-step substitution with shuffles only (the
+// coefficients that do not apply are loaded as zeros, so the loop has no predicates); the warps on the far
+// side of the block then apply the block's solution values, published in shared memory, to their rows.
+__device__ __forceinline__ void diag_load_lower(double (&buf)[NB], const Front& F, int t, int g, int lane, int warp) {
+    const int j0 = g * NB;
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            const int e = e0 + u * nthreads + tid, q = e >> 5, c = q / nblk, i = (q - c * nblk) * 32 + (e & 31);
-            t[u] = (e < total && i < k) ? F.P[i + (int64_t)c * F.f] : 0.0;
+    for (int c = 0; c < NB; ++c)
+        buf[c] = (t < F.k && j0 + c < F.k && (warp > g || (warp == g && c < lane))) ? F.P[t + (int64_t)(j0 + c) * F.f] : 0.0;
+}
+__device__ __forceinline__ void diag_load_upper(double (&buf)[NB], const Front& F, int t, int g, int lane, int warp) {
+    const int j0 = g * NB;
+#pragma unroll
+    for (int c = 0; c < NB; ++c)
+        buf[c] = (t < F.k && j0 + c < F.k && (warp < g || (warp == g && c > lane))) ? F.P[t + (int64_t)(j0 + c) * F.f] : 0.0;
+}
+// y <- L11^{-1} y (unit lower).  ys: shared, KW doubles.  Threads t >= 128 only take part in the barriers.
+__device__ __forceinline__ double diag_solve_lower(const Front& F, double y, double* ys, int tid) {
+    const int lane = tid & 31, warp = tid >> 5, nblk = (F.k + NB - 1) / NB;
+    double cur[NB], nxt[NB];
+    if (tid < KW) diag_load_lower(cur, F, tid, 0, lane, warp);
+    for (int g = 0; g < nblk; ++g) {
+        if (tid < KW && g + 1 < nblk) diag_load_lower(nxt, F, tid, g + 1, lane, warp);
+        if (warp == g) {
+#pragma unroll
+            for (int j = 0; j < NB; ++j) y -= cur[j] * __shfl_sync(0xffffffffu, y, j);
+            ys[tid] = y;
+        }
+        __syncthreads();
+        if (tid < KW && warp > g) {
+            const double* __restrict__ yb = ys + g * NB;
+#pragma unroll
+            for (int c = 0; c < NB; ++c) y -= cur[c] * yb[c];
         }
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            const int e = e0 + u * nthreads + tid, q = e >> 5, c = q / nblk, i = (q - c * nblk) * 32 + (e & 31);
-            if (e < total) Dk[i + c * ldk] = t[u];
-        }
+        for (int c = 0; c < NB; ++c) cur[c] = nxt[c];
     }
+    return y;
+}
+// x <- U11^{-1} v (upper, d = 1 / u_tt).  xs: shared, KW doubles.
+__device__ __forceinline__ double diag_solve_upper(const Front& F, double v, double d, double* xs, int tid) {
+    const int lane = tid & 31, warp = tid >> 5, nblk = (F.k + NB - 1) / NB;
+    double cur[NB], nxt[NB];
+    if (tid < KW) diag_load_upper(cur, F, tid, nblk - 1, lane, warp);
+    for (int g = nblk - 1; g >= 0; --g) {
+        if (tid < KW && g > 0) diag_load_upper(nxt, F, tid, g - 1, lane, warp);
+        if (warp == g) {
+#pragma unroll
+            for (int j = NB - 1; j >= 0; --j) {
+                const double xj = __shfl_sync(0xffffffffu, v * d, j);
+                v = lane == j ? xj : v - cur[j] * xj;
+            }
+            xs[tid] = v;
+        }
+        __syncthreads();
+        if (tid < KW && warp < g) {
+            const double* __restrict__ xb = xs + g * NB;
+#pragma unroll
+            for (int c = 0; c < NB; ++c) v -= cur[c] * xb[c];
+        }
+#pragma unroll
+        for (int c = 0; c < NB; ++c) cur[c] = nxt[c];
+    }
+    return v;
 }
 
 // Forward substitution for one level.  task: x = supernode, y = row tile of the update vector.
 // y_s = L11^{-1} (w[cols] + children contributions); upd_s = children contributions - L21 y_s.
 // Every tile recomputes y_s; tile 0 stores it.  Children are gathered one at a time, ascending,
-// so the summation order is fixed.  The whole pivot block is staged in shared memory first; L11 is
-// then applied 32 columns at a time (one warp solves the diagonal block with shuffles, all threads
-// update the rest).  The tile's FWD_ROWS rows of L21 are reduced by 4 threads per row (k/4 columns
-// each, combined in a fixed order).
-// dynamic shared memory: kp * (kp + 1) doubles.
+// so the summation order is fixed.  L11 is applied by diag_solve_lower (coefficients straight from
+// global memory into registers).  The tile's FWD_ROWS rows of L21 are reduced by 4 threads per row
+// (k/4 columns each, combined in a fixed order).
 __global__ void __launch_bounds__(SOLVE_THREADS) k_fwd(DevCtx cx, const int4* __restrict__ tasks,
                                                        const double* __restrict__ win, double* __restrict__ zout) {
-    extern __shared__ double Dk[];
     __shared__ double ys[KW];
     __shared__ double acc[FWD_ROWS];
     __shared__ double red[4][FWD_ROWS];
     int4 tk = tasks[blockIdx.x];
     const int s = tk.x;
     const Front F = load_front(cx, s);
-    const int k = F.k, tid = threadIdx.x, kp = ((k + NB - 1) / NB) * NB, ldk = kp + 1;
+    const int k = F.k, tid = threadIdx.x, kp = ((k + NB - 1) / NB) * NB;
     const int64_t lo = (int64_t)tk.y * FWD_ROWS;            // first update row of this tile
-    stage_pivot_block(F, Dk, ldk, SOLVE_THREADS);
     if (tid < KW) ys[tid] = tid < k ? win[F.c0 + tid] : 0.0;
     if (tid < FWD_ROWS) acc[tid] = 0.0;
     __syncthreads();
@@ -736,22 +783,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_fwd(DevCtx cx, const int4* __
         }
         __syncthreads();
     }
-    for (int j0 = 0; j0 < k; j0 += NB) {
-        const int w = (k - j0 < NB) ? k - j0 : NB, j1 = j0 + w;
-        if (tid < 32) {   // unit lower triangular solve with the diagonal block, one lane per row
-            double y = tid < w ? ys[j0 + tid] : 0.0;
-            for (int j = 0; j < w; ++j) {
-                const double yj = __shfl_sync(0xffffffffu, y, j);
-                if (tid > j && tid < w) y -= Dk[(j0 + tid) + (j0 + j) * ldk] * yj;
-            }
-            if (tid < w) ys[j0 + tid] = y;
-        }
-        __syncthreads();
-        if (j1 + tid < k) {   // rest of the pivot block
-            double v = ys[j1 + tid];
-            for (int c = 0; c < w; ++c) v -= Dk[(j1 + tid) + (j0 + c) * ldk] * ys[j0 + c];
-            ys[j1 + tid] = v;
-        }
+    {
+        const double y0 = tid < k ? ys[tid] : 0.0;
+        __syncthreads();                                     // everybody has read its entry of ys
+        const double y = diag_solve_lower(F, y0, ys, tid);
+        (void)y;                                             // the solution is in ys (published block by block)
         __syncthreads();
     }
     if (tk.y == 0 && tid < k) zout[F.c0 + tid] = ys[tid];
@@ -784,23 +820,22 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_fwd(DevCtx cx, const int4* __
 // Each CTA reduces BWD_ROWS rows of U12' against the gathered x (a warp takes 4 columns at a time
 // so 32 loads per lane are in flight); with several tiles the partial k-vectors go to scratch and
 // the CTA that arrives last adds them in tile order (fixed summation order, nobody waits) and
-// finishes the back substitution from the pivot block staged in shared memory.
-// dynamic shared memory: kp * (kp + 1) doubles.
+// finishes the back substitution (diag_solve_upper: coefficients straight from global memory into registers).
 __global__ void __launch_bounds__(SOLVE_THREADS) k_bwd(DevCtx cx, const int4* __restrict__ tasks, double* __restrict__ x) {
-    extern __shared__ double Dk[];
     __shared__ double xs[BWD_ROWS];
     __shared__ double part[KW];
     __shared__ int s_last;
     int4 tk = tasks[blockIdx.x];
     const int s = tk.x, ntiles = tk.z;
     const Front F = load_front(cx, s);
-    const int k = F.k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, kp = ((k + NB - 1) / NB) * NB, ldk = kp + 1;
+    const int k = F.k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t lo = (int64_t)tk.y * BWD_ROWS;
     const int cnt = (int)(F.r - lo < BWD_ROWS ? F.r - lo : BWD_ROWS);
+    TRACE2(0);
     const int* __restrict__ rows = cx.rows + cx.rows_ptr[s] + lo;
     xs[tid] = tid < cnt ? x[rows[tid]] : 0.0;          // BWD_ROWS == SOLVE_THREADS
-    stage_pivot_block(F, Dk, ldk, SOLVE_THREADS);
     __syncthreads();
+    TRACE2(1);
     for (int i0 = warp * 4; i0 < k; i0 += (SOLVE_THREADS / 32) * 4) {
         double v[4] = {0.0, 0.0, 0.0, 0.0};
         double t[4][BWD_ROWS / 32];
@@ -822,6 +857,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_bwd(DevCtx cx, const int4* __
         }
     }
     __syncthreads();
+    TRACE2(2);
     if (ntiles > 1) {
         double* slot = cx.bpart + (int64_t)tk.w * KW;
         if (tid < k) slot[(int64_t)tk.y * KW + tid] = part[tid];
@@ -841,31 +877,15 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_bwd(DevCtx cx, const int4* __
         }
         __syncthreads();
     }
-    if (tid < k) part[tid] = x[F.c0 + tid] - part[tid];     // right-hand side of U11 x = ...
-    __syncthreads();
-    const int nblk = kp / NB;
-    for (int g = nblk - 1; g >= 0; --g) {
-        const int j0 = g * NB, w = (k - j0 < NB) ? k - j0 : NB;
-        if (tid < 32) {
-            double v = tid < w ? part[j0 + tid] : 0.0;
-            const double d = tid < w ? cx.dinv[F.c0 + j0 + tid] : 0.0;
-            for (int j = w - 1; j >= 0; --j) {
-                double xj = 0.0;
-                if (tid == j) xj = v * d;
-                xj = __shfl_sync(0xffffffffu, xj, j);
-                if (tid == j) v = xj;
-                if (tid < j) v -= Dk[(j0 + tid) + (j0 + j) * ldk] * xj;
-            }
-            if (tid < w) part[j0 + tid] = v;
-        }
-        __syncthreads();
-        if (tid < j0) {   // columns of U above the diagonal block
-            double v = part[tid];
-            for (int c = 0; c < w; ++c) v -= Dk[tid + (j0 + c) * ldk] * part[j0 + c];
-            part[tid] = v;
-        }
+    TRACE2(3);
+    {
+        const double v0 = tid < k ? x[F.c0 + tid] - part[tid] : 0.0;     // right-hand side of U11 x = ...
+        const double d = tid < k ? cx.dinv[F.c0 + tid] : 0.0;
+        __syncthreads();                                     // everybody has read its entry of part
+        diag_solve_upper(F, v0, d, part, tid);               // the solution is published in part
         __syncthreads();
     }
+    TRACE2(4);
     if (tid < k) x[F.c0 + tid] = part[tid];
 }
 
@@ -991,7 +1011,6 @@ constexpr int SMALL_FPC32 = 4;     // fronts per CTA in the one-warp class of k_
 constexpr int SOLVE_FPC = 8;       // fronts per CTA in the small solve kernels
 
 static size_t panel_smem(int j0, int rows) { return sizeof(double) * (2 * (size_t)j0 + rows) * CLD; }
-static size_t solve_smem(int kmax) { size_t kp = (size_t)((kmax + NB - 1) / NB) * NB; return sizeof(double) * kp * (kp + 1); }
 
 cudaError_t kernels_init() {
     cudaError_t e = cudaFuncSetAttribute(k_small_factor<96, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1001,9 +1020,7 @@ cudaError_t kernels_init() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_panel<PANEL_ROWS_TOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem(KW - NB, PANEL_ROWS_TOP));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem(KW));
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem(KW));
+    return cudaSuccess;
 }
 
 void launch_rowscale(cudaStream_t st, int n, const int64_t* rowptr, const int64_t* rowidx, const double* av, double* Rs) {
@@ -1068,10 +1085,10 @@ void launch_unpermute(cudaStream_t st, int n, const int* q, const double* w, dou
     k_unpermute<<<(n + 255) / 256, 256, 0, st>>>(n, q, w, x);
 }
 void launch_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int kmax, const double* win, double* zout) {
-    if (ntasks > 0) k_fwd<<<ntasks, SOLVE_THREADS, solve_smem(kmax), st>>>(cx, tasks, win, zout);
+    if (ntasks > 0) k_fwd<<<ntasks, SOLVE_THREADS, 0, st>>>(cx, tasks, win, zout);
 }
 void launch_bwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int kmax, double* x) {
-    if (ntasks > 0) k_bwd<<<ntasks, SOLVE_THREADS, solve_smem(kmax), st>>>(cx, tasks, x);
+    if (ntasks > 0) k_bwd<<<ntasks, SOLVE_THREADS, 0, st>>>(cx, tasks, x);
 }
 
 }  // namespace smslu
