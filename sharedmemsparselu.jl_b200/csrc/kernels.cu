@@ -578,8 +578,7 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
 constexpr int GEMM_LDS = GEMM_TILE + 4;   // row stride = 4 (mod 16) doubles: fragment loads are conflict-free
 
 __global__ void __launch_bounds__(256) k_gemm_cb(DevCtx cx, const int4* __restrict__ tasks) {
-    __shared__ double As[NB][GEMM_LDS];   // As[p][m] = -L21[m0 + m][kc + p]
-    __shared__ double Bs[NB][GEMM_LDS];   // Bs[p][n] =  U12[kc + p][n0 + n]
+    extern __shared__ __align__(16) double gsm[];         // 2 stages x (As[NB][GEMM_LDS] | Bs[NB][GEMM_LDS])
     int4 tk = tasks[blockIdx.x];
     const Front F = load_front(cx, tk.x);
     const int k = F.k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -590,8 +589,24 @@ __global__ void __launch_bounds__(256) k_gemm_cb(DevCtx cx, const int4* __restri
     // warp tile: 32 rows x 16 columns = 4 x 2 DMMA tiles; 8 warps cover 64 x 64
     const int wm = (warp & 1) * 32, wn = (warp >> 1) * 16;
     const int fr = lane >> 2, fc = lane & 3;            // fragment row / k (A), n / k (B), row / column pair (C)
+    // stage one K chunk (32 columns of L21, 32 rows of U12) with cp.async; rows beyond the block are zero-filled
+    auto stage = [&](int kc, int buf) {
+        double* As = gsm + buf * (2 * NB * GEMM_LDS);
+        double* Bs = As + NB * GEMM_LDS;
+        const int kw = (k - kc < NB) ? k - kc : NB;
+        const int a = tid & (GEMM_TILE - 1);
+        const int64_t ra = m0 + a, rb = n0 + a;
+        const bool oka = ra < F.r, okb = rb < F.r;
+        for (int p = tid >> 6; p < NB; p += 4) {
+            const bool in = p < kw;
+            cp_async8(As + p * GEMM_LDS + a, A + ((in && oka) ? ra + (int64_t)(kc + p) * F.f : 0), in && oka);
+            cp_async8(Bs + p * GEMM_LDS + a, B + ((in && okb) ? rb + (int64_t)(kc + p) * F.r : 0), in && okb);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage(0, 0);
     double acc[4][2][2];
-    // issue the C loads first so they are in flight while the operand tiles are staged
+    // the C loads are in flight while the operand tiles arrive
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -601,29 +616,32 @@ __global__ void __launch_bounds__(256) k_gemm_cb(DevCtx cx, const int4* __restri
                 const int64_t row = m0 + wm + 8 * i + fr, col = n0 + wn + 8 * j + 2 * fc + e;
                 acc[i][j][e] = (beta && row < F.r && col < F.r) ? F.C[row + col * F.r] : 0.0;
             }
-    for (int kc = 0; kc < k; kc += NB) {
-        const int kw = (k - kc < NB) ? k - kc : NB;
-        if (kc) __syncthreads();
-        for (int e = tid; e < GEMM_TILE * NB; e += 256) {
-            const int a = e & (GEMM_TILE - 1), p = e >> 6;
-            const int64_t ra = m0 + a, rb = n0 + a;
-            As[p][a] = (p < kw && ra < F.r) ? -A[ra + (int64_t)(kc + p) * F.f] : 0.0;
-            Bs[p][a] = (p < kw && rb < F.r) ? B[rb + (int64_t)(kc + p) * F.r] : 0.0;
+    int buf = 0;
+    for (int kc = 0; kc < k; kc += NB, buf ^= 1) {
+        if (kc + NB < k) {
+            stage(kc + NB, buf ^ 1);                     // next chunk into the other stage
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
+        const double* As = gsm + buf * (2 * NB * GEMM_LDS);
+        const double* Bs = As + NB * GEMM_LDS;
+        const int kw = (k - kc < NB) ? k - kc : NB;
         const int ksteps = (kw + 3) >> 2;
         for (int ks = 0; ks < ksteps; ++ks) {
             const int p = 4 * ks + fc;
             double a[4], b[2];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = As[p][wm + 8 * i + fr];
+            for (int i = 0; i < 4; ++i) a[i] = -As[p * GEMM_LDS + wm + 8 * i + fr];      // C - L21 U12
 #pragma unroll
-            for (int j = 0; j < 2; ++j) b[j] = Bs[p][wn + 8 * j + fr];
+            for (int j = 0; j < 2; ++j) b[j] = Bs[p * GEMM_LDS + wn + 8 * j + fr];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
+        __syncthreads();                                 // the stage is refilled two iterations from now
     }
     if (!direct) {
 #pragma unroll
@@ -1010,11 +1028,14 @@ int debug_read_trace(long long* out) {
 constexpr int SMALL_FPC32 = 4;     // fronts per CTA in the one-warp class of k_small_factor
 constexpr int SOLVE_FPC = 8;       // fronts per CTA in the small solve kernels
 
+static size_t gemm_smem() { return sizeof(double) * 2 * 2 * NB * GEMM_LDS; }
 static size_t panel_smem(int j0, int rows) { return sizeof(double) * (2 * (size_t)j0 + rows) * CLD; }
 
 cudaError_t kernels_init() {
     cudaError_t e = cudaFuncSetAttribute(k_small_factor<96, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(sizeof(double) * small_group_doubles(96)));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_gemm_cb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_panel<PANEL_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem(KW - NB, PANEL_ROWS));
     if (e != cudaSuccess) return e;
@@ -1076,7 +1097,7 @@ void launch_panel(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntas
     else k_panel<PANEL_ROWS_TOP><<<ntasks, PANEL_THREADS, panel_smem(g * NB, PANEL_ROWS_TOP), st>>>(cx, tasks);
 }
 void launch_gemm_cb(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks) {
-    if (ntasks > 0) k_gemm_cb<<<ntasks, 256, 0, st>>>(cx, tasks);
+    if (ntasks > 0) k_gemm_cb<<<ntasks, 256, gemm_smem(), st>>>(cx, tasks);
 }
 void launch_permute_scale(cudaStream_t st, int n, const int* p, const double* Rs, const double* b, double* w) {
     k_permute_scale<<<(n + 255) / 256, 256, 0, st>>>(n, p, Rs, b, w);
