@@ -384,6 +384,14 @@ def run_ours(args, rank, world, local_rank):
         ach = work[dom]["bytes"] / (ms_kernel[dom] * 1e-3) / 1e9
         roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_gbs, "unit": "GB/s",
                 "frac": ach / hbm_gbs, "traffic": None, "peak_source": peak_src}
+    try:   # DRAM traffic of that kernel from the committed ncu --set full capture (mean over the captured launches)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["kernels"].get(dom)
+        if tr:
+            roof["traffic"] = tr["dram_bytes_per_launch_mean"]
+            roof["traffic_source"] = "profiles/%s: mean dram read+write bytes over %d captured launches" % (tr["capture"], len(tr["launches"]))
+            roof["algorithmic_bytes_per_launch"] = work[dom]["bytes"] / max(1, launches_kernel.get(dom, 1))
+    except Exception:
+        pass
     roof["kernel_ms_per_step"] = ms_kernel[dom]
     roof["share_of_step"] = ms_kernel[dom] / step_ms_prof
     solve_ms = sum(ms_kernel.get(kk, 0) for kk in ("fwd", "bwd", "fwd_small", "bwd_small", "permute_scale", "unpermute"))
