@@ -1076,7 +1076,8 @@ void launch_front_small(cudaStream_t st, const DevCtx& cx, const int4* tasks, in
         k_small_factor_reg<40, 1><<<ntasks, 64, sizeof(double) * reg_group_doubles(40), st>>>(cx, tasks, ntasks, av, Rs);
     else if (fmax <= 48)
         k_small_factor_reg<48, 1><<<ntasks, 64, sizeof(double) * reg_group_doubles(48), st>>>(cx, tasks, ntasks, av, Rs);
-    else if (fmax <= 64) launch_small_class<64, 2, 1>(st, cx, tasks, ntasks, fmax, av, Rs);
+    else if (fmax <= 64)
+        k_small_factor_reg<64, 1><<<ntasks, 64, sizeof(double) * reg_group_doubles(64), st>>>(cx, tasks, ntasks, av, Rs);
     else launch_small_class<96, 3, 1>(st, cx, tasks, ntasks, fmax, av, Rs);
 }
 void launch_vgather(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const int* vlist) {
