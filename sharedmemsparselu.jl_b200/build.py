@@ -35,7 +35,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     tmp = LIB + ".%d.tmp" % os.getpid()
     trace = ["-DSMSLU_TRACE"] if os.environ.get("SMSLU_TRACE") == "1" else []
     cmd = [nvcc()] + NVCC_FLAGS + trace + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-lnccl"]
+          [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     subprocess.check_call(cmd)
     os.replace(tmp, LIB)
     return LIB

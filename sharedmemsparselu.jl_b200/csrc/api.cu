@@ -1,7 +1,8 @@
 // C ABI of libsmslu.so (include/smslu.h): handle, upload of the symbolic layout, level schedules,
 // and the numeric entry points.  No CPU fallback: numeric calls need a CUDA device.
 #include <cuda_runtime.h>
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h>     // types and prototypes only: the library is loaded lazily (see nccl_api below)
 
 #include <algorithm>
 #include <chrono>
@@ -18,6 +19,41 @@
 using namespace smslu;
 
 namespace {
+
+// NCCL is resolved with dlopen on first multi-GPU use instead of being a link-time dependency: a process
+// that never partitions a matrix never loads it, and a host that already carries its own NCCL (PyTorch
+// bundles one under the same soname) is not handed a second, possibly older, copy.
+struct NcclApi {
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    bool ok = false;
+};
+NcclApi& nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (lib) {
+            api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+            api.CommInitRank = (decltype(api.CommInitRank))dlsym(lib, "ncclCommInitRank");
+            api.CommDestroy = (decltype(api.CommDestroy))dlsym(lib, "ncclCommDestroy");
+            api.AllReduce = (decltype(api.AllReduce))dlsym(lib, "ncclAllReduce");
+            api.GroupStart = (decltype(api.GroupStart))dlsym(lib, "ncclGroupStart");
+            api.GroupEnd = (decltype(api.GroupEnd))dlsym(lib, "ncclGroupEnd");
+            api.GetErrorString = (decltype(api.GetErrorString))dlsym(lib, "ncclGetErrorString");
+            api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GroupStart &&
+                     api.GroupEnd && api.GetErrorString;
+        }
+    }
+    return api;
+}
 
 enum LaunchKind { L_ZERO = SMSLU_K_ZERO, L_EXTEND = SMSLU_K_EXTEND, L_SMALL = SMSLU_K_SMALL, L_PANEL = SMSLU_K_PANEL,
                   L_GEMM = SMSLU_K_GEMM, L_FWD = SMSLU_K_FWD, L_BWD = SMSLU_K_BWD,
@@ -106,7 +142,7 @@ int fail(smslu_handle_t h, int code, const std::string& msg) {
 #define NCCLCHK(call)                                                                                 \
     do {                                                                                          \
         ncclResult_t r_ = (call);                                                                 \
-        if (r_ != ncclSuccess) return fail(h, SMSLU_E_NCCL, std::string(#call) + ": " + ncclGetErrorString(r_)); \
+        if (r_ != ncclSuccess) return fail(h, SMSLU_E_NCCL, std::string(#call) + ": " + nccl_api().GetErrorString(r_)); \
     } while (0)
 
 template <class T>
@@ -431,14 +467,14 @@ int ensure_uploaded(smslu_handle_t h) {
     int *d_counters, *d_flag;
     if ((rc = dev_alloc(h, &d_lu, (size_t)S.lu_size))) return rc;
     if ((rc = dev_alloc(h, &d_cb, (size_t)S.cb_size))) return rc;
-    if ((rc = dev_alloc(h, &d_upd, (size_t)(S.sum_r + h->vupd_len)))) return rc;
+    if ((rc = dev_alloc(h, &d_upd, (size_t)(S.sum_r + h->vupd_len) * RB_MAX))) return rc;
     if ((rc = dev_alloc(h, &d_flag, 1))) return rc;
     if ((rc = dev_alloc(h, &d_dinv, (size_t)n))) return rc;
     if ((rc = dev_alloc(h, &h->d_Rs, (size_t)n))) return rc;
     if ((rc = dev_alloc(h, &h->d_aval, (size_t)h->annz))) return rc;
-    if ((rc = dev_alloc(h, &h->d_w, (size_t)n))) return rc;
-    if ((rc = dev_alloc(h, &h->d_z, (size_t)n))) return rc;
-    if ((rc = dev_alloc(h, &h->d_xb, (size_t)n))) return rc;
+    if ((rc = dev_alloc(h, &h->d_w, (size_t)n * RB_MAX))) return rc;
+    if ((rc = dev_alloc(h, &h->d_z, (size_t)n * RB_MAX))) return rc;
+    if ((rc = dev_alloc(h, &h->d_xb, (size_t)n * RB_MAX))) return rc;
     {
         std::vector<double> ones(n, 1.0);
         CU(cudaMemcpy(h->d_Rs, ones.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
@@ -451,7 +487,7 @@ int ensure_uploaded(smslu_handle_t h) {
     h->cx.asm_meta = d_asm_meta;
     double* d_bpart; int* d_counters2;
     if ((rc = dev_alloc(h, &d_counters, (size_t)h->ncounters))) return rc;
-    if ((rc = dev_alloc(h, &d_bpart, (size_t)h->bpart_slots * KMAX))) return rc;
+    if ((rc = dev_alloc(h, &d_bpart, (size_t)h->bpart_slots * KMAX * RB_MAX))) return rc;
     if ((rc = dev_alloc(h, &d_counters2, (size_t)S.nsn))) return rc;
     CU(cudaMemset(d_counters2, 0, sizeof(int) * std::max(S.nsn, 1)));
     DevCtx& cx = h->cx;
@@ -496,7 +532,7 @@ int prof_collect(smslu_handle_t h) {   // stream must be synchronized
     return 0;
 }
 
-int run_schedule(smslu_handle_t h, const std::vector<Launch>& sched, const double* win, double* zx) {
+int run_schedule(smslu_handle_t h, const std::vector<Launch>& sched, const double* win, double* zx, int rb = 1) {
     int rc;
     for (const Launch& L : sched) {
         const int4* tk = h->d_tasks + L.off;
@@ -505,12 +541,12 @@ int run_schedule(smslu_handle_t h, const std::vector<Launch>& sched, const doubl
             case L_ZERO: launch_zero_cb(h->stream, h->cx, tk, L.ntasks); break;
             case L_EXTEND: launch_assemble(h->stream, h->cx, tk, L.ntasks); break;
             case L_SMALL: launch_front_small(h->stream, h->cx, tk, L.ntasks, L.fmax, h->cur_av, h->d_Rs); break;
-            case L_FWD_SMALL: launch_small_fwd(h->stream, h->cx, tk, L.ntasks, win, zx); break;
-            case L_BWD_SMALL: launch_small_bwd(h->stream, h->cx, tk, L.ntasks, zx); break;
+            case L_FWD_SMALL: launch_small_fwd(h->stream, h->cx, tk, L.ntasks, win, zx, rb); break;
+            case L_BWD_SMALL: launch_small_bwd(h->stream, h->cx, tk, L.ntasks, zx, rb); break;
             case L_PANEL: launch_panel(h->stream, h->cx, tk, L.ntasks, L.fmax & 255, L.fmax >> 8); break;
             case L_GEMM: launch_gemm_cb(h->stream, h->cx, tk, L.ntasks); break;
-            case L_FWD: launch_fwd(h->stream, h->cx, tk, L.ntasks, L.fmax, win, zx); break;
-            case L_BWD: launch_bwd(h->stream, h->cx, tk, L.ntasks, L.fmax, zx); break;
+            case L_FWD: launch_fwd(h->stream, h->cx, tk, L.ntasks, win, zx, rb); break;
+            case L_BWD: launch_bwd(h->stream, h->cx, tk, L.ntasks, zx, rb); break;
         }
         if ((rc = prof_end(h))) return rc;
     }
@@ -542,13 +578,13 @@ int enqueue_refactor(smslu_handle_t h, const double* av, bool rs_given) {
     if (h->nranks > 1) {
         // sum the subtrees' contributions to the top of the tree over NVLink, then factor the top
         if ((rc = prof_begin(h, SMSLU_K_ALLREDUCE))) return rc;
-        NCCLCHK(ncclGroupStart());
-        if (S.lu_top_size > 0) NCCLCHK(ncclAllReduce(h->cx.lu, h->cx.lu, (size_t)S.lu_top_size, ncclDouble, ncclSum, h->comm, h->stream));
-        if (S.cb_iface_size > 0) NCCLCHK(ncclAllReduce(h->cx.cb, h->cx.cb, (size_t)S.cb_iface_size, ncclDouble, ncclSum, h->comm, h->stream));
-        NCCLCHK(ncclGroupEnd());
+        NCCLCHK(nccl_api().GroupStart());
+        if (S.lu_top_size > 0) NCCLCHK(nccl_api().AllReduce(h->cx.lu, h->cx.lu, (size_t)S.lu_top_size, ncclDouble, ncclSum, h->comm, h->stream));
+        if (S.cb_iface_size > 0) NCCLCHK(nccl_api().AllReduce(h->cx.cb, h->cx.cb, (size_t)S.cb_iface_size, ncclDouble, ncclSum, h->comm, h->stream));
+        NCCLCHK(nccl_api().GroupEnd());
         if ((rc = prof_end(h))) return rc;
         if ((rc = run_schedule(h, h->fac_top, nullptr, nullptr))) return rc;
-        NCCLCHK(ncclAllReduce(h->cx.flag, h->cx.flag, 1, ncclInt, ncclMin, h->comm, h->stream));
+        NCCLCHK(nccl_api().AllReduce(h->cx.flag, h->cx.flag, 1, ncclInt, ncclMin, h->comm, h->stream));
     }
     CU(cudaMemcpyAsync(h->h_flag, h->cx.flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     h->pending_refactor = true;
@@ -576,43 +612,46 @@ int finish_refactor(smslu_handle_t h) {
 
 // Partitioned forward solve across the cut: sum this rank's subtree contributions per interface front
 // into the virtual children's vectors, all-reduce them, then run the top of the tree.
-int enqueue_top_forward(smslu_handle_t h) {
+int enqueue_top_forward(smslu_handle_t h, int rb) {
     int rc;
     if ((rc = prof_begin(h, SMSLU_K_ALLREDUCE))) return rc;
-    launch_vgather(h->stream, h->cx, h->d_vtasks, h->nvtasks, h->d_vlist);
+    launch_vgather(h->stream, h->cx, h->d_vtasks, h->nvtasks, h->d_vlist, rb);
     if (h->vupd_len > 0)
-        NCCLCHK(ncclAllReduce(h->cx.upd + h->vupd_off, h->cx.upd + h->vupd_off, (size_t)h->vupd_len, ncclDouble, ncclSum, h->comm, h->stream));
+        NCCLCHK(nccl_api().AllReduce(h->cx.upd + h->vupd_off * rb, h->cx.upd + h->vupd_off * rb, (size_t)h->vupd_len * rb, ncclDouble, ncclSum, h->comm, h->stream));
     if ((rc = prof_end(h))) return rc;
-    return run_schedule(h, h->fwd_top, h->d_w, h->d_z);
+    return run_schedule(h, h->fwd_top, h->d_w, h->d_z, rb);
 }
 
 // Every rank holds the solution on its own columns and on the top columns; zero the rest (rank 0
 // keeps the top) and sum over ranks so that every rank ends with the full vector.
-int enqueue_gather_solution(smslu_handle_t h) {
+int enqueue_gather_solution(smslu_handle_t h, int rb) {
     int rc;
     if ((rc = prof_begin(h, SMSLU_K_ALLREDUCE))) return rc;
-    launch_mask_owned(h->stream, h->n, h->d_colowner, h->rank, h->d_z);
-    NCCLCHK(ncclAllReduce(h->d_z, h->d_z, (size_t)h->n, ncclDouble, ncclSum, h->comm, h->stream));
+    launch_mask_owned(h->stream, h->n, h->d_colowner, h->rank, h->d_z, rb);
+    NCCLCHK(nccl_api().AllReduce(h->d_z, h->d_z, (size_t)h->n * rb, ncclDouble, ncclSum, h->comm, h->stream));
     return prof_end(h);
 }
 
-int enqueue_solve(smslu_handle_t h, double* xdev, const double* bdev) {
+// rb right-hand sides (columns bdev + q * ldb) are swept together; rb is 1, 4 or 8.
+int enqueue_solve(smslu_handle_t h, double* xdev, int64_t ldx, const double* bdev, int64_t ldb, int rb) {
     int rc;
     if ((rc = prof_begin(h, SMSLU_K_PERMUTE))) return rc;
-    launch_permute_scale(h->stream, h->n, h->d_p, h->d_Rs, bdev, h->d_w);
+    launch_permute_scale(h->stream, h->n, h->d_p, h->d_Rs, bdev, ldb, h->d_w, rb);
     if ((rc = prof_end(h))) return rc;
-    if ((rc = run_schedule(h, h->fwd, h->d_w, h->d_z))) return rc;
+    if ((rc = run_schedule(h, h->fwd, h->d_w, h->d_z, rb))) return rc;
     if (h->nranks > 1) {
-        if ((rc = enqueue_top_forward(h))) return rc;
-        if ((rc = run_schedule(h, h->bwd_top, nullptr, h->d_z))) return rc;
+        if ((rc = enqueue_top_forward(h, rb))) return rc;
+        if ((rc = run_schedule(h, h->bwd_top, nullptr, h->d_z, rb))) return rc;
     }
-    if ((rc = run_schedule(h, h->bwd, nullptr, h->d_z))) return rc;
-    if (h->nranks > 1 && (rc = enqueue_gather_solution(h))) return rc;
+    if ((rc = run_schedule(h, h->bwd, nullptr, h->d_z, rb))) return rc;
+    if (h->nranks > 1 && (rc = enqueue_gather_solution(h, rb))) return rc;
     if ((rc = prof_begin(h, SMSLU_K_UNPERMUTE))) return rc;
-    launch_unpermute(h->stream, h->n, h->d_q, h->d_z, xdev);
+    launch_unpermute(h->stream, h->n, h->d_q, h->d_z, xdev, ldx, rb);
     if ((rc = prof_end(h))) return rc;
     return 0;
 }
+
+inline int chunk_rb(int64_t left) { return left >= 8 ? 8 : (left >= 4 ? 4 : 1); }
 
 }  // namespace
 
@@ -723,8 +762,9 @@ int smslu_analyze(smslu_handle_t h, const int64_t* p, const int64_t* q) {
 
 int smslu_comm_unique_id(void* id, int64_t nbytes) {
     if (!id || nbytes < (int64_t)sizeof(ncclUniqueId)) return SMSLU_E_ARG;
+    if (!nccl_api().ok) return SMSLU_E_NCCL;
     ncclUniqueId u;
-    if (ncclGetUniqueId(&u) != ncclSuccess) return SMSLU_E_NCCL;
+    if (nccl_api().GetUniqueId(&u) != ncclSuccess) return SMSLU_E_NCCL;
     memcpy(id, &u, sizeof(u));
     return 0;
 }
@@ -733,12 +773,13 @@ int smslu_comm_init(smslu_handle_t h, const void* id, int64_t nbytes) {
     if (!h || !id || nbytes < (int64_t)sizeof(ncclUniqueId)) return SMSLU_E_ARG;
     if (h->nranks <= 1) return 0;
     if (h->comm) return fail(h, SMSLU_E_ARG, "communicator already initialised");
+    if (!nccl_api().ok) return fail(h, SMSLU_E_NCCL, "libnccl.so.2 could not be loaded");
     if (h->opt.device >= 0) h->device = h->opt.device;
     else CU(cudaGetDevice(&h->device));
     CU(cudaSetDevice(h->device));
     ncclUniqueId u;
     memcpy(&u, id, sizeof(u));
-    NCCLCHK(ncclCommInitRank(&h->comm, h->nranks, u, h->rank));
+    NCCLCHK(nccl_api().CommInitRank(&h->comm, h->nranks, u, h->rank));
     return 0;
 }
 
@@ -790,7 +831,7 @@ int smslu_solve_async(smslu_handle_t h, double* x_dev, const double* b_dev) {
     if (!is_device_ptr(x_dev) || !is_device_ptr(b_dev)) return fail(h, SMSLU_E_ARG, "smslu_solve_async needs device pointers");
     CU(cudaSetDevice(h->device));
     h->st.launches_solve = (int64_t)h->fwd.size() + (int64_t)h->bwd.size() + 2;
-    return enqueue_solve(h, x_dev, b_dev);
+    return enqueue_solve(h, x_dev, h->n, b_dev, h->n, 1);
 }
 
 int smslu_sync(smslu_handle_t h) {
@@ -843,23 +884,32 @@ int smslu_solve(smslu_handle_t h, double* x, int64_t nx, const double* b, int64_
     const int n = h->n;
     const bool xdev = is_device_ptr(x), bdev = is_device_ptr(b);
     float h2d = 0, dev = 0, d2h = 0, ms;
-    for (int64_t c = 0; c < nrhs; ++c) {
+    int64_t nsweeps = 0;
+    for (int64_t c = 0; c < nrhs;) {
+        const int rb = chunk_rb(nrhs - c);               // 8, 4 or 1 right-hand sides per sweep
         const double* bc = b + c * ldb;
         double* xc = x + c * ldx;
+        int64_t lb = ldb, lx = ldx;
         CU(cudaEventRecord(h->ev0, h->stream));
-        if (!bdev) { CU(cudaMemcpyAsync(h->d_xb, bc, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream)); bc = h->d_xb; }
+        if (!bdev) {                                     // host columns -> contiguous device block, ld = n
+            CU(cudaMemcpy2DAsync(h->d_xb, sizeof(double) * n, bc, sizeof(double) * ldb, sizeof(double) * n, rb,
+                                 cudaMemcpyHostToDevice, h->stream));
+            bc = h->d_xb; lb = n;
+        }
         CU(cudaEventRecord(h->ev1, h->stream));
-        if ((rc = enqueue_solve(h, xdev ? xc : h->d_xb, bc))) return rc;
+        if ((rc = enqueue_solve(h, xdev ? xc : h->d_xb, xdev ? lx : n, bc, lb, rb))) return rc;
         CU(cudaEventRecord(h->ev2, h->stream));
-        if (!xdev) CU(cudaMemcpyAsync(xc, h->d_xb, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+        if (!xdev) CU(cudaMemcpy2DAsync(xc, sizeof(double) * ldx, h->d_xb, sizeof(double) * n, sizeof(double) * n, rb,
+                                        cudaMemcpyDeviceToHost, h->stream));
         CU(cudaEventRecord(h->ev3, h->stream));
         CU(cudaStreamSynchronize(h->stream));
         CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1)); h2d += ms;
         CU(cudaEventElapsedTime(&ms, h->ev1, h->ev2)); dev += ms;
         CU(cudaEventElapsedTime(&ms, h->ev2, h->ev3)); d2h += ms;
+        c += rb; ++nsweeps;
     }
     h->st.ms_solve_h2d = h2d; h->st.ms_solve = dev; h->st.ms_solve_d2h = d2h;
-    h->st.launches_solve = nrhs * ((int64_t)h->fwd.size() + (int64_t)h->bwd.size() + 2);
+    h->st.launches_solve = nsweeps * ((int64_t)h->fwd.size() + (int64_t)h->bwd.size() + 2);
     h->st.n_solve++;
     return prof_collect(h);
 }
@@ -871,20 +921,32 @@ static int tri_solve(smslu_handle_t h, double* x, int64_t nx, int64_t nrhs, int6
     if (!h->factored) return fail(h, SMSLU_E_ARG, "no valid factorization (call smslu_refactor)");
     if ((rc = ensure_uploaded(h))) return rc;
     const int n = h->n;
-    for (int64_t c = 0; c < nrhs; ++c) {
+    const bool dev = is_device_ptr(x);
+    for (int64_t c = 0; c < nrhs;) {
+        const int rb = chunk_rb(nrhs - c);
         double* xc = x + c * ld;
-        if (lower) {
-            CU(cudaMemcpyAsync(h->d_w, xc, sizeof(double) * n, cudaMemcpyDefault, h->stream));
-            if ((rc = run_schedule(h, h->fwd, h->d_w, h->d_z))) return rc;
-            if (h->nranks > 1 && (rc = enqueue_top_forward(h))) return rc;
-        } else {
-            CU(cudaMemcpyAsync(h->d_z, xc, sizeof(double) * n, cudaMemcpyDefault, h->stream));
-            if (h->nranks > 1 && (rc = run_schedule(h, h->bwd_top, nullptr, h->d_z))) return rc;
-            if ((rc = run_schedule(h, h->bwd, nullptr, h->d_z))) return rc;
+        const double* src = xc; int64_t lsrc = ld;
+        if (!dev) {
+            CU(cudaMemcpy2DAsync(h->d_xb, sizeof(double) * n, xc, sizeof(double) * ld, sizeof(double) * n, rb,
+                                 cudaMemcpyHostToDevice, h->stream));
+            src = h->d_xb; lsrc = n;
         }
-        if (h->nranks > 1 && (rc = enqueue_gather_solution(h))) return rc;
-        CU(cudaMemcpyAsync(xc, h->d_z, sizeof(double) * n, cudaMemcpyDefault, h->stream));
+        // interleave the block (identity permutation, no scaling), sweep, de-interleave
+        if (lower) {
+            launch_permute_scale(h->stream, n, nullptr, nullptr, src, lsrc, h->d_w, rb);
+            if ((rc = run_schedule(h, h->fwd, h->d_w, h->d_z, rb))) return rc;
+            if (h->nranks > 1 && (rc = enqueue_top_forward(h, rb))) return rc;
+        } else {
+            launch_permute_scale(h->stream, n, nullptr, nullptr, src, lsrc, h->d_z, rb);
+            if (h->nranks > 1 && (rc = run_schedule(h, h->bwd_top, nullptr, h->d_z, rb))) return rc;
+            if ((rc = run_schedule(h, h->bwd, nullptr, h->d_z, rb))) return rc;
+        }
+        if (h->nranks > 1 && (rc = enqueue_gather_solution(h, rb))) return rc;
+        launch_unpermute(h->stream, n, nullptr, h->d_z, dev ? xc : h->d_xb, dev ? ld : n, rb);
+        if (!dev) CU(cudaMemcpy2DAsync(xc, sizeof(double) * ld, h->d_xb, sizeof(double) * n, sizeof(double) * n, rb,
+                                       cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
+        c += rb;
     }
     return 0;
 }
@@ -968,7 +1030,7 @@ int smslu_get_symbolic(smslu_handle_t h, int64_t* sn_start, int64_t* rows_ptr, i
 
 int smslu_destroy(smslu_handle_t h) {
     if (!h) return 0;
-    if (h->comm) { cudaSetDevice(h->device); ncclCommDestroy(h->comm); h->comm = nullptr; }
+    if (h->comm) { cudaSetDevice(h->device); nccl_api().CommDestroy(h->comm); h->comm = nullptr; }
     if (h->uploaded || h->stream) {
         cudaSetDevice(h->device);
         if (h->stream) cudaStreamSynchronize(h->stream);

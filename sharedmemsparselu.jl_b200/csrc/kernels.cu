@@ -681,18 +681,30 @@ __global__ void __launch_bounds__(256) k_gemm_cb(DevCtx cx, const int4* __restri
 }
 
 // ------------------------------------------------------------------ solves
+// All solve kernels are templated on RB, the number of right-hand sides swept together (1, 4 or 8): the
+// work vectors are interleaved (entry i of right-hand side q at [i * RB + q]), so the factor entries are
+// read once per RB right-hand sides and every thread's RB values are contiguous.
+template <int RB>
 __global__ void k_permute_scale(int n, const int* __restrict__ p, const double* __restrict__ Rs,
-                                const double* __restrict__ b, double* __restrict__ w) {
+                                const double* __restrict__ b, int64_t ldb, double* __restrict__ w) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { int pi = p[i]; w[i] = Rs[pi] * b[pi]; }
+    if (i >= n) return;
+    const int pi = p ? p[i] : i;
+    const double sc = Rs ? Rs[pi] : 1.0;
+#pragma unroll
+    for (int q = 0; q < RB; ++q) w[(int64_t)i * RB + q] = sc * b[pi + q * ldb];
 }
-__global__ void k_unpermute(int n, const int* __restrict__ q, const double* __restrict__ w, double* __restrict__ x) {
+template <int RB>
+__global__ void k_unpermute(int n, const int* __restrict__ qv, const double* __restrict__ w, double* __restrict__ x, int64_t ldx) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) x[q[i]] = w[i];
+    if (i >= n) return;
+    const int qi = qv ? qv[i] : i;
+#pragma unroll
+    for (int q = 0; q < RB; ++q) x[qi + q * ldx] = w[(int64_t)i * RB + q];
 }
 
 // Triangular solves with the k x k pivot block (k <= KW = 128) of a big front, without staging the block:
-// thread t < 128 owns row t and keeps its current right-hand-side value in a register; the pivot block is
+// thread t < 128 owns row t and keeps its current right-hand-side values in registers; the pivot block is
 // consumed 32 columns (block g) at a time, every thread loading its 32 coefficients of the block straight
 // from global memory into registers one block ahead (each entry of the pivot block is used exactly once).
 // Warp g owns the rows of diagonal block g: it runs the 32-step substitution with shuffles only (the
@@ -710,8 +722,10 @@ __device__ __forceinline__ void diag_load_upper(double (&buf)[NB], const Front& 
     for (int c = 0; c < NB; ++c)
         buf[c] = (t < F.k && j0 + c < F.k && (warp < g || (warp == g && c > lane))) ? F.P[t + (int64_t)(j0 + c) * F.f] : 0.0;
 }
-// y <- L11^{-1} y (unit lower).  ys: shared, KW doubles.  Threads t >= 128 only take part in the barriers.
-__device__ __forceinline__ double diag_solve_lower(const Front& F, double y, double* ys, int tid) {
+// y <- L11^{-1} y (unit lower).  ys: shared, KW * RB doubles; the solution is left there.
+// Threads t >= KW only take part in the barriers.
+template <int RB>
+__device__ __forceinline__ void diag_solve_lower(const Front& F, double (&y)[RB], double* ys, int tid) {
     const int lane = tid & 31, warp = tid >> 5, nblk = (F.k + NB - 1) / NB;
     double cur[NB], nxt[NB];
     if (tid < KW) diag_load_lower(cur, F, tid, 0, lane, warp);
@@ -719,22 +733,27 @@ __device__ __forceinline__ double diag_solve_lower(const Front& F, double y, dou
         if (tid < KW && g + 1 < nblk) diag_load_lower(nxt, F, tid, g + 1, lane, warp);
         if (warp == g) {
 #pragma unroll
-            for (int j = 0; j < NB; ++j) y -= cur[j] * __shfl_sync(0xffffffffu, y, j);
-            ys[tid] = y;
+            for (int j = 0; j < NB; ++j)
+#pragma unroll
+                for (int q = 0; q < RB; ++q) y[q] -= cur[j] * __shfl_sync(0xffffffffu, y[q], j);
+#pragma unroll
+            for (int q = 0; q < RB; ++q) ys[tid * RB + q] = y[q];
         }
         __syncthreads();
         if (tid < KW && warp > g) {
-            const double* __restrict__ yb = ys + g * NB;
+            const double* __restrict__ yb = ys + g * NB * RB;
 #pragma unroll
-            for (int c = 0; c < NB; ++c) y -= cur[c] * yb[c];
+            for (int c = 0; c < NB; ++c)
+#pragma unroll
+                for (int q = 0; q < RB; ++q) y[q] -= cur[c] * yb[c * RB + q];
         }
 #pragma unroll
         for (int c = 0; c < NB; ++c) cur[c] = nxt[c];
     }
-    return y;
 }
-// x <- U11^{-1} v (upper, d = 1 / u_tt).  xs: shared, KW doubles.
-__device__ __forceinline__ double diag_solve_upper(const Front& F, double v, double d, double* xs, int tid) {
+// x <- U11^{-1} v (upper, d = 1 / u_tt).  xs: shared, KW * RB doubles; the solution is left there.
+template <int RB>
+__device__ __forceinline__ void diag_solve_upper(const Front& F, double (&v)[RB], double d, double* xs, int tid) {
     const int lane = tid & 31, warp = tid >> 5, nblk = (F.k + NB - 1) / NB;
     double cur[NB], nxt[NB];
     if (tid < KW) diag_load_upper(cur, F, tid, nblk - 1, lane, warp);
@@ -742,22 +761,26 @@ __device__ __forceinline__ double diag_solve_upper(const Front& F, double v, dou
         if (tid < KW && g > 0) diag_load_upper(nxt, F, tid, g - 1, lane, warp);
         if (warp == g) {
 #pragma unroll
-            for (int j = NB - 1; j >= 0; --j) {
-                const double xj = __shfl_sync(0xffffffffu, v * d, j);
-                v = lane == j ? xj : v - cur[j] * xj;
-            }
-            xs[tid] = v;
+            for (int j = NB - 1; j >= 0; --j)
+#pragma unroll
+                for (int q = 0; q < RB; ++q) {
+                    const double xj = __shfl_sync(0xffffffffu, v[q] * d, j);
+                    v[q] = lane == j ? xj : v[q] - cur[j] * xj;
+                }
+#pragma unroll
+            for (int q = 0; q < RB; ++q) xs[tid * RB + q] = v[q];
         }
         __syncthreads();
         if (tid < KW && warp < g) {
-            const double* __restrict__ xb = xs + g * NB;
+            const double* __restrict__ xb = xs + g * NB * RB;
 #pragma unroll
-            for (int c = 0; c < NB; ++c) v -= cur[c] * xb[c];
+            for (int c = 0; c < NB; ++c)
+#pragma unroll
+                for (int q = 0; q < RB; ++q) v[q] -= cur[c] * xb[c * RB + q];
         }
 #pragma unroll
         for (int c = 0; c < NB; ++c) cur[c] = nxt[c];
     }
-    return v;
 }
 
 // Forward substitution for one level.  task: x = supernode, y = row tile of the update vector.
@@ -766,70 +789,93 @@ __device__ __forceinline__ double diag_solve_upper(const Front& F, double v, dou
 // so the summation order is fixed.  L11 is applied by diag_solve_lower (coefficients straight from
 // global memory into registers).  The tile's FWD_ROWS rows of L21 are reduced by 4 threads per row
 // (k/4 columns each, combined in a fixed order).
+template <int RB>
 __global__ void __launch_bounds__(SOLVE_THREADS) k_fwd(DevCtx cx, const int4* __restrict__ tasks,
                                                        const double* __restrict__ win, double* __restrict__ zout) {
-    __shared__ double ys[KW];
-    __shared__ double acc[FWD_ROWS];
-    __shared__ double red[4][FWD_ROWS];
+    __shared__ double ys[KW * RB];
+    __shared__ double acc[FWD_ROWS * RB];
+    __shared__ double red[4][FWD_ROWS * RB];
     int4 tk = tasks[blockIdx.x];
     const int s = tk.x;
     const Front F = load_front(cx, s);
     const int k = F.k, tid = threadIdx.x, kp = ((k + NB - 1) / NB) * NB;
     const int64_t lo = (int64_t)tk.y * FWD_ROWS;            // first update row of this tile
-    if (tid < KW) ys[tid] = tid < k ? win[F.c0 + tid] : 0.0;
-    if (tid < FWD_ROWS) acc[tid] = 0.0;
+    for (int e = tid; e < KW * RB; e += SOLVE_THREADS) ys[e] = e < k * RB ? win[(int64_t)F.c0 * RB + e] : 0.0;
+    for (int e = tid; e < FWD_ROWS * RB; e += SOLVE_THREADS) acc[e] = 0.0;
     __syncthreads();
     for (int ci = cx.child_ptr[s]; ci < cx.child_ptr[s + 1]; ++ci) {
         const int c = cx.child_idx[ci];
         const int64_t rc = cx.rows_ptr[c + 1] - cx.rows_ptr[c];
         const int* __restrict__ rel = cx.rel + cx.rows_ptr[c];
-        const double* __restrict__ uc = cx.upd + cx.rows_ptr[c];
-        for (int64_t a0 = 0; a0 < rc; a0 += 4 * SOLVE_THREADS) {
-            int64_t ra[4]; double uv[4];
+        const double* __restrict__ uc = cx.upd + cx.rows_ptr[c] * RB;
+        constexpr int NBATCH = RB >= 4 ? 2 : 4;
+        for (int64_t a0 = 0; a0 < rc; a0 += NBATCH * SOLVE_THREADS) {
+            int64_t ra[NBATCH]; double uv[NBATCH][RB];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < NBATCH; ++u) {
                 const int64_t a = a0 + u * SOLVE_THREADS + tid;
                 ra[u] = a < rc ? rel[a] : -1;
-                uv[u] = a < rc ? uc[a] : 0.0;
+#pragma unroll
+                for (int q = 0; q < RB; ++q) uv[u][q] = a < rc ? uc[a * RB + q] : 0.0;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < NBATCH; ++u) {
                 if (ra[u] < 0) continue;
-                if (ra[u] < k) ys[ra[u]] += uv[u];
-                else if (ra[u] - k >= lo && ra[u] - k < lo + FWD_ROWS) acc[ra[u] - k - lo] += uv[u];
+                if (ra[u] < k) {
+#pragma unroll
+                    for (int q = 0; q < RB; ++q) ys[ra[u] * RB + q] += uv[u][q];
+                } else if (ra[u] - k >= lo && ra[u] - k < lo + FWD_ROWS) {
+#pragma unroll
+                    for (int q = 0; q < RB; ++q) acc[(ra[u] - k - lo) * RB + q] += uv[u][q];
+                }
             }
         }
         __syncthreads();
     }
     {
-        const double y0 = tid < k ? ys[tid] : 0.0;
-        __syncthreads();                                     // everybody has read its entry of ys
-        const double y = diag_solve_lower(F, y0, ys, tid);
-        (void)y;                                             // the solution is in ys (published block by block)
+        double y[RB];
+#pragma unroll
+        for (int q = 0; q < RB; ++q) y[q] = tid < k ? ys[tid * RB + q] : 0.0;
+        __syncthreads();                                     // everybody has read its entries of ys
+        diag_solve_lower<RB>(F, y, ys, tid);
         __syncthreads();
     }
-    if (tk.y == 0 && tid < k) zout[F.c0 + tid] = ys[tid];
+    if (tk.y == 0) for (int e = tid; e < k * RB; e += SOLVE_THREADS) zout[(int64_t)F.c0 * RB + e] = ys[e];
     {   // rows of L21: thread (row, quarter) sums kp/4 columns
-        const int rloc = tid & (FWD_ROWS - 1), q = tid / FWD_ROWS, kq = kp / 4;
+        const int rloc = tid & (FWD_ROWS - 1), qt = tid / FWD_ROWS, kq = kp / 4;
         const int64_t row = lo + rloc;
-        double v = 0.0;
+        double v[RB];
+#pragma unroll
+        for (int q = 0; q < RB; ++q) v[q] = 0.0;
         if (row < F.r) {
-            const double* __restrict__ src = F.P + F.k + row + (int64_t)(q * kq) * F.f;
-            const int jn = (k - q * kq < kq) ? k - q * kq : kq;     // may be <= 0 for the last quarters
+            const double* __restrict__ src = F.P + F.k + row + (int64_t)(qt * kq) * F.f;
+            const int jn = (k - qt * kq < kq) ? k - qt * kq : kq;     // may be <= 0 for the last quarters
             int j = 0;
             for (; j + 8 <= jn; j += 8) {
                 double l[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) l[u] = src[(int64_t)(j + u) * F.f];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v += l[u] * ys[q * kq + j + u];
+                for (int u = 0; u < 8; ++u)
+#pragma unroll
+                    for (int q = 0; q < RB; ++q) v[q] += l[u] * ys[(qt * kq + j + u) * RB + q];
             }
-            for (; j < jn; ++j) v += src[(int64_t)j * F.f] * ys[q * kq + j];
+            for (; j < jn; ++j) {
+                const double l = src[(int64_t)j * F.f];
+#pragma unroll
+                for (int q = 0; q < RB; ++q) v[q] += l * ys[(qt * kq + j) * RB + q];
+            }
         }
-        red[q][rloc] = v;
+#pragma unroll
+        for (int q = 0; q < RB; ++q) red[qt][rloc * RB + q] = v[q];
         __syncthreads();
-        if (q == 0 && row < F.r)
-            cx.upd[cx.rows_ptr[s] + row] = acc[rloc] - (((red[0][rloc] + red[1][rloc]) + red[2][rloc]) + red[3][rloc]);
+        if (qt == 0 && row < F.r) {
+#pragma unroll
+            for (int q = 0; q < RB; ++q) {
+                const int e = rloc * RB + q;
+                cx.upd[(cx.rows_ptr[s] + row) * RB + q] = acc[e] - (((red[0][e] + red[1][e]) + red[2][e]) + red[3][e]);
+            }
+        }
     }
 }
 
@@ -839,9 +885,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_fwd(DevCtx cx, const int4* __
 // so 32 loads per lane are in flight); with several tiles the partial k-vectors go to scratch and
 // the CTA that arrives last adds them in tile order (fixed summation order, nobody waits) and
 // finishes the back substitution (diag_solve_upper: coefficients straight from global memory into registers).
+template <int RB>
 __global__ void __launch_bounds__(SOLVE_THREADS) k_bwd(DevCtx cx, const int4* __restrict__ tasks, double* __restrict__ x) {
-    __shared__ double xs[BWD_ROWS];
-    __shared__ double part[KW];
+    __shared__ double xs[BWD_ROWS * RB];
+    __shared__ double part[KW * RB];
     __shared__ int s_last;
     int4 tk = tasks[blockIdx.x];
     const int s = tk.x, ntiles = tk.z;
@@ -849,13 +896,19 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_bwd(DevCtx cx, const int4* __
     const int k = F.k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t lo = (int64_t)tk.y * BWD_ROWS;
     const int cnt = (int)(F.r - lo < BWD_ROWS ? F.r - lo : BWD_ROWS);
-    TRACE2(0);
     const int* __restrict__ rows = cx.rows + cx.rows_ptr[s] + lo;
-    xs[tid] = tid < cnt ? x[rows[tid]] : 0.0;          // BWD_ROWS == SOLVE_THREADS
+    {
+        const int64_t xr = tid < cnt ? (int64_t)rows[tid] * RB : 0;     // BWD_ROWS == SOLVE_THREADS
+#pragma unroll
+        for (int q = 0; q < RB; ++q) xs[tid * RB + q] = tid < cnt ? x[xr + q] : 0.0;
+    }
     __syncthreads();
-    TRACE2(1);
     for (int i0 = warp * 4; i0 < k; i0 += (SOLVE_THREADS / 32) * 4) {
-        double v[4] = {0.0, 0.0, 0.0, 0.0};
+        double v[4][RB];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int q = 0; q < RB; ++q) v[u][q] = 0.0;
         double t[4][BWD_ROWS / 32];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -864,21 +917,26 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_bwd(DevCtx cx, const int4* __
             for (int a = 0; a < BWD_ROWS / 32; ++a) t[u][a] = (i0 + u < k && lane + 32 * a < cnt) ? col[lane + 32 * a] : 0.0;
         }
 #pragma unroll
+        for (int a = 0; a < BWD_ROWS / 32; ++a)
+#pragma unroll
+            for (int q = 0; q < RB; ++q) {
+                const double xv = xs[(lane + 32 * a) * RB + q];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u][q] += t[u][a] * xv;
+            }
+#pragma unroll
         for (int u = 0; u < 4; ++u)
 #pragma unroll
-            for (int a = 0; a < BWD_ROWS / 32; ++a) v[u] += t[u][a] * xs[(lane + 32 * a) & (BWD_ROWS - 1)];
+            for (int q = 0; q < RB; ++q) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v[u] += __shfl_xor_sync(0xffffffffu, v[u], o);
-            if (lane == 0 && i0 + u < k) part[i0 + u] = v[u];
-        }
+                for (int o = 16; o > 0; o >>= 1) v[u][q] += __shfl_xor_sync(0xffffffffu, v[u][q], o);
+                if (lane == 0 && i0 + u < k) part[(i0 + u) * RB + q] = v[u][q];
+            }
     }
     __syncthreads();
-    TRACE2(2);
     if (ntiles > 1) {
-        double* slot = cx.bpart + (int64_t)tk.w * KW;
-        if (tid < k) slot[(int64_t)tk.y * KW + tid] = part[tid];
+        double* slot = cx.bpart + (int64_t)tk.w * KW * RB;
+        for (int e = tid; e < k * RB; e += SOLVE_THREADS) slot[(int64_t)tk.y * KW * RB + e] = part[e];
         __threadfence();
         __syncthreads();
         if (tid == 0) {
@@ -888,50 +946,60 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_bwd(DevCtx cx, const int4* __
         __syncthreads();
         if (!s_last) return;
         __threadfence();
-        if (tid < k) {
+        for (int e = tid; e < k * RB; e += SOLVE_THREADS) {
             double v = 0.0;
-            for (int t = 0; t < ntiles; ++t) v += __ldcg(slot + (int64_t)t * KW + tid);
-            part[tid] = v;
+            for (int t = 0; t < ntiles; ++t) v += __ldcg(slot + (int64_t)t * KW * RB + e);
+            part[e] = v;
         }
         __syncthreads();
     }
-    TRACE2(3);
     {
-        const double v0 = tid < k ? x[F.c0 + tid] - part[tid] : 0.0;     // right-hand side of U11 x = ...
+        double v0[RB];
+        const int64_t xc = (int64_t)(F.c0 + tid) * RB;
+#pragma unroll
+        for (int q = 0; q < RB; ++q) v0[q] = tid < k ? x[xc + q] - part[tid * RB + q] : 0.0;     // right-hand side of U11 x = ...
         const double d = tid < k ? cx.dinv[F.c0 + tid] : 0.0;
-        __syncthreads();                                     // everybody has read its entry of part
-        diag_solve_upper(F, v0, d, part, tid);               // the solution is published in part
+        __syncthreads();                                     // everybody has read its entries of part
+        diag_solve_upper<RB>(F, v0, d, part, tid);           // the solution is published in part
         __syncthreads();
     }
-    TRACE2(4);
-    if (tid < k) x[F.c0 + tid] = part[tid];
+    for (int e = tid; e < k * RB; e += SOLVE_THREADS) x[(int64_t)F.c0 * RB + e] = part[e];
 }
 
 // ------------------------------------------------------------------ partitioned solves
 // One CTA per interface front: sum the update vectors of this rank's subtree roots below it into the
 // front's virtual child (rel = identity), root by root in ascending order.
 // task: x = interface front, y = virtual child, [z, w) = range in vlist.
+template <int RB>
 __global__ void __launch_bounds__(256) k_vgather(DevCtx cx, const int4* __restrict__ tasks, const int* __restrict__ vlist) {
     const int4 tk = tasks[blockIdx.x];
-    double* __restrict__ v = cx.upd + cx.rows_ptr[tk.y];
+    double* __restrict__ v = cx.upd + cx.rows_ptr[tk.y] * RB;
     const int64_t fs = cx.rows_ptr[tk.y + 1] - cx.rows_ptr[tk.y];
-    for (int64_t i = threadIdx.x; i < fs; i += 256) v[i] = 0.0;
+    for (int64_t i = threadIdx.x; i < fs * RB; i += 256) v[i] = 0.0;
     __syncthreads();
     for (int ci = tk.z; ci < tk.w; ++ci) {
         const int c = vlist[ci];
         const int64_t rc = cx.rows_ptr[c + 1] - cx.rows_ptr[c];
         const int* __restrict__ rel = cx.rel + cx.rows_ptr[c];
-        const double* __restrict__ uc = cx.upd + cx.rows_ptr[c];
-        for (int64_t a = threadIdx.x; a < rc; a += 256) v[rel[a]] += uc[a];
+        const double* __restrict__ uc = cx.upd + cx.rows_ptr[c] * RB;
+        for (int64_t a = threadIdx.x; a < rc; a += 256) {
+            const int64_t ra = (int64_t)rel[a] * RB;
+#pragma unroll
+            for (int q = 0; q < RB; ++q) v[ra + q] += uc[a * RB + q];
+        }
         __syncthreads();
     }
 }
 // keep the entries this rank is responsible for (its own columns; the top columns on rank 0)
+template <int RB>
 __global__ void k_mask_owned(int n, const int* __restrict__ colowner, int rank, double* __restrict__ z) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int o = colowner[i];
-    if (!(o == rank || (o == -1 && rank == 0))) z[i] = 0.0;
+    if (!(o == rank || (o == -1 && rank == 0))) {
+#pragma unroll
+        for (int q = 0; q < RB; ++q) z[(int64_t)i * RB + q] = 0.0;
+    }
 }
 
 // ------------------------------------------------------------------ solves, small fronts
@@ -939,10 +1007,10 @@ __global__ void k_mask_owned(int n, const int* __restrict__ colowner, int rank, 
 // Forward: v = [w[cols]; 0] + children's update vectors (gathered through rel, child by child),
 // then column-oriented substitution: for j < k: y_j = v_j (broadcast by shuffle), v_i -= L_ij y_j
 // for all i > j -- rows of L11 and of L21 alike, each column of P read once, coalesced.
-template <int FPC>
+template <int FPC, int RB>
 __global__ void __launch_bounds__(32 * FPC) k_small_fwd(DevCtx cx, const int4* __restrict__ tasks, int ntasks,
                                                         const double* __restrict__ win, double* __restrict__ zout) {
-    __shared__ double vs[FPC][SMALL_F_MAX];
+    __shared__ double vs[FPC][SMALL_F_MAX * RB];
     const int grp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ti = blockIdx.x * FPC + grp;
     if (ti >= ntasks) return;
@@ -950,39 +1018,55 @@ __global__ void __launch_bounds__(32 * FPC) k_small_fwd(DevCtx cx, const int4* _
     const Front F = load_front(cx, s);
     const int k = F.k, f = (int)F.f;
     double* v = vs[grp];
-    for (int i = lane; i < f; i += 32) v[i] = i < k ? win[F.c0 + i] : 0.0;
+    for (int e = lane; e < f * RB; e += 32) v[e] = e < k * RB ? win[(int64_t)F.c0 * RB + e] : 0.0;
     __syncwarp();
     for (int ci = cx.child_ptr[s]; ci < cx.child_ptr[s + 1]; ++ci) {
         const int c = cx.child_idx[ci];
         const int rc = (int)(cx.rows_ptr[c + 1] - cx.rows_ptr[c]);
         const int* __restrict__ rel = cx.rel + cx.rows_ptr[c];
-        const double* __restrict__ uc = cx.upd + cx.rows_ptr[c];
-        for (int a = lane; a < rc; a += 32) v[rel[a]] += uc[a];
+        const double* __restrict__ uc = cx.upd + cx.rows_ptr[c] * RB;
+        for (int a = lane; a < rc; a += 32) {
+            const int ra = rel[a] * RB;
+#pragma unroll
+            for (int q = 0; q < RB; ++q) v[ra + q] += uc[(int64_t)a * RB + q];
+        }
         __syncwarp();
     }
     const bool h0 = lane < f, h1 = lane + 32 < f, h2 = lane + 64 < f;
-    double v0 = h0 ? v[lane] : 0.0, v1 = h1 ? v[lane + 32] : 0.0, v2 = h2 ? v[lane + 64] : 0.0;
+    double v0[RB], v1[RB], v2[RB];
+#pragma unroll
+    for (int q = 0; q < RB; ++q) {
+        v0[q] = h0 ? v[lane * RB + q] : 0.0;
+        v1[q] = h1 ? v[(lane + 32) * RB + q] : 0.0;
+        v2[q] = h2 ? v[(lane + 64) * RB + q] : 0.0;
+    }
     const double* __restrict__ col = F.P + lane;
 #pragma unroll 4
     for (int j = 0; j < k; ++j, col += f) {
         const double l0 = (h0 && lane > j) ? col[0] : 0.0, l1 = h1 ? col[32] : 0.0, l2 = h2 ? col[64] : 0.0;
-        const double yj = __shfl_sync(0xffffffffu, v0, j);
-        v0 -= l0 * yj; v1 -= l1 * yj; v2 -= l2 * yj;
+#pragma unroll
+        for (int q = 0; q < RB; ++q) {
+            const double yj = __shfl_sync(0xffffffffu, v0[q], j);
+            v0[q] -= l0 * yj; v1[q] -= l1 * yj; v2[q] -= l2 * yj;
+        }
     }
-    if (lane < k) zout[F.c0 + lane] = v0;
-    double* __restrict__ us = cx.upd + cx.rows_ptr[s] - k;
-    if (h0 && lane >= k) us[lane] = v0;
-    if (h1) us[lane + 32] = v1;                                // k <= 32 <= lane + 32
-    if (h2) us[lane + 64] = v2;
+    double* __restrict__ us = cx.upd + (cx.rows_ptr[s] - k) * RB;
+#pragma unroll
+    for (int q = 0; q < RB; ++q) {
+        if (lane < k) zout[(int64_t)(F.c0 + lane) * RB + q] = v0[q];
+        if (h0 && lane >= k) us[lane * RB + q] = v0[q];
+        if (h1) us[(lane + 32) * RB + q] = v1[q];                  // k <= 32 <= lane + 32
+        if (h2) us[(lane + 64) * RB + q] = v2[q];
+    }
 }
 
 // Backward: lane c owns pivot row c.  t_c = sum_b U12[c][b] x[rows[b]] is a plain loop over b (the
 // r x k block is a few KB and stays in L1, so the strided reads cost nothing in HBM traffic and no
 // reduction is needed); then column-oriented back substitution with U11 and the stored 1/u_jj.
-template <int FPC>
+template <int FPC, int RB>
 __global__ void __launch_bounds__(32 * FPC) k_small_bwd(DevCtx cx, const int4* __restrict__ tasks, int ntasks,
                                                         double* __restrict__ x) {
-    __shared__ double xs[FPC][SMALL_F_MAX];
+    __shared__ double xs[FPC][SMALL_F_MAX * RB];
     const int grp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ti = blockIdx.x * FPC + grp;
     if (ti >= ntasks) return;
@@ -991,25 +1075,42 @@ __global__ void __launch_bounds__(32 * FPC) k_small_bwd(DevCtx cx, const int4* _
     const int k = F.k, r = (int)F.r, f = (int)F.f;
     double* xr = xs[grp];
     const int* __restrict__ rows = cx.rows + cx.rows_ptr[s];
-    for (int b = lane; b < r; b += 32) xr[b] = x[rows[b]];
+    for (int b = lane; b < r; b += 32) {
+        const int64_t xo = (int64_t)rows[b] * RB;
+#pragma unroll
+        for (int q = 0; q < RB; ++q) xr[b * RB + q] = x[xo + q];
+    }
     __syncwarp();
     const bool act = lane < k;
-    double t = 0.0;
+    double v[RB];
+#pragma unroll
+    for (int q = 0; q < RB; ++q) v[q] = 0.0;
     {
         const double* __restrict__ tc = F.T + (int64_t)(act ? lane : 0) * r;
 #pragma unroll 4
-        for (int b = 0; b < r; ++b) t += tc[b] * xr[b];
+        for (int b = 0; b < r; ++b) {
+            const double tv = tc[b];
+#pragma unroll
+            for (int q = 0; q < RB; ++q) v[q] += tv * xr[b * RB + q];
+        }
     }
-    double v = act ? x[F.c0 + lane] - t : 0.0;
+#pragma unroll
+    for (int q = 0; q < RB; ++q) v[q] = act ? x[(int64_t)(F.c0 + lane) * RB + q] - v[q] : 0.0;
     const double d = act ? cx.dinv[F.c0 + lane] : 0.0;
     const double* __restrict__ col = F.P + lane + (int64_t)(k - 1) * f;
 #pragma unroll 4
     for (int j = k - 1; j >= 0; --j, col -= f) {
         const double u = lane < j ? col[0] : 0.0;
-        const double xj = __shfl_sync(0xffffffffu, v * d, j);
-        v = lane == j ? xj : v - u * xj;
+#pragma unroll
+        for (int q = 0; q < RB; ++q) {
+            const double xj = __shfl_sync(0xffffffffu, v[q] * d, j);
+            v[q] = lane == j ? xj : v[q] - u * xj;
+        }
     }
-    if (act) x[F.c0 + lane] = v;
+    if (act) {
+#pragma unroll
+        for (int q = 0; q < RB; ++q) x[(int64_t)(F.c0 + lane) * RB + q] = v[q];
+    }
 }
 
 }  // namespace
@@ -1026,7 +1127,6 @@ int debug_read_trace(long long* out) {
 }
 
 constexpr int SMALL_FPC32 = 4;     // fronts per CTA in the one-warp class of k_small_factor
-constexpr int SOLVE_FPC = 8;       // fronts per CTA in the small solve kernels
 
 static size_t gemm_smem() { return sizeof(double) * 2 * 2 * NB * GEMM_LDS; }
 static size_t panel_smem(int j0, int rows) { return sizeof(double) * (2 * (size_t)j0 + rows) * CLD; }
@@ -1080,17 +1180,29 @@ void launch_front_small(cudaStream_t st, const DevCtx& cx, const int4* tasks, in
         k_small_factor_reg<64, 1><<<ntasks, 64, sizeof(double) * reg_group_doubles(64), st>>>(cx, tasks, ntasks, av, Rs);
     else launch_small_class<96, 3, 1>(st, cx, tasks, ntasks, fmax, av, Rs);
 }
-void launch_vgather(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const int* vlist) {
-    if (ntasks > 0) k_vgather<<<ntasks, 256, 0, st>>>(cx, tasks, vlist);
+#define RB_DISPATCH(rb, CALL) do { if ((rb) == 1) { CALL(1); } else if ((rb) == 4) { CALL(4); } else { CALL(8); } } while (0)
+void launch_vgather(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const int* vlist, int rb) {
+    if (ntasks <= 0) return;
+#define CALL(R) k_vgather<R><<<ntasks, 256, 0, st>>>(cx, tasks, vlist)
+    RB_DISPATCH(rb, CALL);
+#undef CALL
 }
-void launch_mask_owned(cudaStream_t st, int n, const int* colowner, int rank, double* z) {
-    k_mask_owned<<<(n + 255) / 256, 256, 0, st>>>(n, colowner, rank, z);
+void launch_mask_owned(cudaStream_t st, int n, const int* colowner, int rank, double* z, int rb) {
+#define CALL(R) k_mask_owned<R><<<(n + 255) / 256, 256, 0, st>>>(n, colowner, rank, z)
+    RB_DISPATCH(rb, CALL);
+#undef CALL
 }
-void launch_small_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const double* win, double* zout) {
-    if (ntasks > 0) k_small_fwd<SOLVE_FPC><<<(ntasks + SOLVE_FPC - 1) / SOLVE_FPC, 32 * SOLVE_FPC, 0, st>>>(cx, tasks, ntasks, win, zout);
+void launch_small_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const double* win, double* zout, int rb) {
+    if (ntasks <= 0) return;
+    if (rb == 1) k_small_fwd<8, 1><<<(ntasks + 7) / 8, 256, 0, st>>>(cx, tasks, ntasks, win, zout);
+    else if (rb == 4) k_small_fwd<4, 4><<<(ntasks + 3) / 4, 128, 0, st>>>(cx, tasks, ntasks, win, zout);
+    else k_small_fwd<2, 8><<<(ntasks + 1) / 2, 64, 0, st>>>(cx, tasks, ntasks, win, zout);
 }
-void launch_small_bwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, double* x) {
-    if (ntasks > 0) k_small_bwd<SOLVE_FPC><<<(ntasks + SOLVE_FPC - 1) / SOLVE_FPC, 32 * SOLVE_FPC, 0, st>>>(cx, tasks, ntasks, x);
+void launch_small_bwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, double* x, int rb) {
+    if (ntasks <= 0) return;
+    if (rb == 1) k_small_bwd<8, 1><<<(ntasks + 7) / 8, 256, 0, st>>>(cx, tasks, ntasks, x);
+    else if (rb == 4) k_small_bwd<4, 4><<<(ntasks + 3) / 4, 128, 0, st>>>(cx, tasks, ntasks, x);
+    else k_small_bwd<2, 8><<<(ntasks + 1) / 2, 64, 0, st>>>(cx, tasks, ntasks, x);
 }
 void launch_panel(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int g, int rows) {
     if (ntasks <= 0) return;
@@ -1100,17 +1212,27 @@ void launch_panel(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntas
 void launch_gemm_cb(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks) {
     if (ntasks > 0) k_gemm_cb<<<ntasks, 256, gemm_smem(), st>>>(cx, tasks);
 }
-void launch_permute_scale(cudaStream_t st, int n, const int* p, const double* Rs, const double* b, double* w) {
-    k_permute_scale<<<(n + 255) / 256, 256, 0, st>>>(n, p, Rs, b, w);
+void launch_permute_scale(cudaStream_t st, int n, const int* p, const double* Rs, const double* b, int64_t ldb, double* w, int rb) {
+#define CALL(R) k_permute_scale<R><<<(n + 255) / 256, 256, 0, st>>>(n, p, Rs, b, ldb, w)
+    RB_DISPATCH(rb, CALL);
+#undef CALL
 }
-void launch_unpermute(cudaStream_t st, int n, const int* q, const double* w, double* x) {
-    k_unpermute<<<(n + 255) / 256, 256, 0, st>>>(n, q, w, x);
+void launch_unpermute(cudaStream_t st, int n, const int* q, const double* w, double* x, int64_t ldx, int rb) {
+#define CALL(R) k_unpermute<R><<<(n + 255) / 256, 256, 0, st>>>(n, q, w, x, ldx)
+    RB_DISPATCH(rb, CALL);
+#undef CALL
 }
-void launch_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int kmax, const double* win, double* zout) {
-    if (ntasks > 0) k_fwd<<<ntasks, SOLVE_THREADS, 0, st>>>(cx, tasks, win, zout);
+void launch_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const double* win, double* zout, int rb) {
+    if (ntasks <= 0) return;
+#define CALL(R) k_fwd<R><<<ntasks, SOLVE_THREADS, 0, st>>>(cx, tasks, win, zout)
+    RB_DISPATCH(rb, CALL);
+#undef CALL
 }
-void launch_bwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int kmax, double* x) {
-    if (ntasks > 0) k_bwd<<<ntasks, SOLVE_THREADS, 0, st>>>(cx, tasks, x);
+void launch_bwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, double* x, int rb) {
+    if (ntasks <= 0) return;
+#define CALL(R) k_bwd<R><<<ntasks, SOLVE_THREADS, 0, st>>>(cx, tasks, x)
+    RB_DISPATCH(rb, CALL);
+#undef CALL
 }
 
 }  // namespace smslu

@@ -26,6 +26,7 @@ constexpr int SOLVE_THREADS = 256;
 constexpr int FWD_ROWS = 64;      // update rows per forward CTA (4 threads per row)
 constexpr int BWD_ROWS = 256;     // rows of U12' per backward CTA
 constexpr int ZERO_TILE = 8192;
+constexpr int RB_MAX = 8;         // most right-hand sides swept together by the solve kernels
 constexpr int ASM_COLS = 8;       // destination columns of a parent front per assembly CTA
 
 struct DevCtx {
@@ -64,10 +65,11 @@ void launch_zero_cb(cudaStream_t st, const DevCtx& cx, const int4* tasks, int nt
 void launch_assemble(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks);
 void launch_front_small(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int fmax,
                         const double* av, const double* Rs);
-void launch_vgather(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const int* vlist);
-void launch_mask_owned(cudaStream_t st, int n, const int* colowner, int rank, double* z);
-void launch_small_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const double* win, double* zout);
-void launch_small_bwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, double* x);
+// rb = right-hand sides swept together (1, 4 or 8); vectors are interleaved [i * rb + q]
+void launch_vgather(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const int* vlist, int rb);
+void launch_mask_owned(cudaStream_t st, int n, const int* colowner, int rank, double* z, int rb);
+void launch_small_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const double* win, double* zout, int rb);
+void launch_small_bwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, double* x, int rb);
 void launch_panel(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int g, int rows);
 void launch_gemm_cb(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks);
 int front_small_limit();   // largest front the fused shared-memory kernel takes
@@ -75,9 +77,9 @@ cudaError_t kernels_init();
 int debug_read_trace(long long* out);   // 0 unless built with SMSLU_TRACE
 
 // ---- solves
-void launch_permute_scale(cudaStream_t st, int n, const int* p, const double* Rs, const double* b, double* w);
-void launch_unpermute(cudaStream_t st, int n, const int* q, const double* w, double* x);
-void launch_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int kmax, const double* win, double* zout);
-void launch_bwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int kmax, double* x);
+void launch_permute_scale(cudaStream_t st, int n, const int* p, const double* Rs, const double* b, int64_t ldb, double* w, int rb);
+void launch_unpermute(cudaStream_t st, int n, const int* q, const double* w, double* x, int64_t ldx, int rb);
+void launch_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const double* win, double* zout, int rb);
+void launch_bwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, double* x, int rb);
 
 }  // namespace smslu

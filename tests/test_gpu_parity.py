@@ -197,17 +197,31 @@ def test_device_resident_vectors(smslu, W):
     F.close()
 
 
-def test_multiple_rhs(smslu, O, W):
-    A = W.laplacian_3d(10)
+@pytest.mark.parametrize("case,nrhs", [("lap3d_10", 5), ("lap2d_150", 13), ("lap3d_14", 21), ("block_border_small", 8)])
+def test_multiple_rhs(smslu, O, W, case, nrhs):
+    """Matrix right-hand sides (BASELINE config 5): the solve kernels sweep 8 / 4 / 1 columns at a time over
+    interleaved work vectors; every column must equal the single-vector ldiv!/lsolve!/rsolve! of that column."""
+    A = {"lap3d_10": lambda: W.laplacian_3d(10), "lap2d_150": lambda: W.laplacian_2d(150),
+         "lap3d_14": lambda: W.laplacian_3d(14),
+         "block_border_small": lambda: W.block_border(nblocks=4, nel=5, ngr=5, border=8)}[case]()
     n = A.shape[0]
     F = smslu.ParallelSparseLU(A)
-    B = W.rhs(n, 47, nrhs=5)
-    X = np.empty((n, 5), order="F")
+    B = W.rhs(n, 47, nrhs=nrhs)
+    X = np.empty((n, nrhs), order="F")
+    B0 = B.copy(order="F")
     smslu.ldiv_(X, F, B)
-    for r in range(5):
-        x = np.empty(n); smslu.ldiv_(x, F, np.ascontiguousarray(B[:, r]))
-        assert np.array_equal(X[:, r], x)
-        assert residual(A, X[:, r], B[:, r]) < 1e-14
+    assert np.array_equal(B, B0)
+    YL = B.copy(order="F"); smslu.lsolve_(F, YL)
+    YU = B.copy(order="F"); smslu.rsolve_(F, YU)
+    for r in range(nrhs):
+        bcol = np.ascontiguousarray(B[:, r])
+        x = np.empty(n); smslu.ldiv_(x, F, bcol)
+        assert np.linalg.norm(X[:, r] - x) <= 1e-14 * np.linalg.norm(x)
+        assert residual(A, X[:, r], B[:, r]) < 1e-12
+        y = bcol.copy(); smslu.lsolve_(F, y)
+        assert np.linalg.norm(YL[:, r] - y) <= 1e-14 * np.linalg.norm(y)
+        y = bcol.copy(); smslu.rsolve_(F, y)
+        assert np.linalg.norm(YU[:, r] - y) <= 1e-14 * np.linalg.norm(y)
     F.close()
 
 
