@@ -404,10 +404,27 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
     double* Uc = dsm;                               // Uc[m * CLD + c] = U[m, j0 + c],  m < j0
     double* Lc = dsm + j0 * CLD;                    // Lc[m * CLD + i] = L[j0 + i, m],  m < j0
     double* Xs = dsm + 2 * j0 * CLD;                // Xs[row][CLD]: updated rows, one per thread in phase T
+    // Latency variant (ROWS == 32): the CTA's 32 rows, columns [0, j1), are staged in shared memory as well
+    // (As[row][ALD], row stride = 4 mod 16: conflict-free A fragments), so that the update phase never waits
+    // on global memory.
+    constexpr bool STAGE_ROWS = ROWS == PANEL_ROWS_TOP;
+    constexpr int ALD = KW + 4;
+    double* As = Xs + ROWS * CLD;
+    const int64_t stride = kind == 0 ? F.f : (kind == 1 ? F.r : 1);
+    auto row_ptr = [&](int64_t idx, double*& b, bool& act) {
+        if (kind == 0) { act = j1 + idx < F.f; b = F.P + j1 + idx; }
+        else if (kind == 1) { act = idx < F.r; b = F.T + idx; }
+        else { act = j1 + idx < k; b = F.P + (j1 + idx) * F.f; }
+    };
     // ---- S: stage D_gg and the coefficient blocks
     {
         const double* __restrict__ Pg = F.P;
         constexpr int NW = PANEL_THREADS / 32;
+        if (STAGE_ROWS) {
+            double* rb; bool ra;
+            row_ptr((int64_t)tk.z * ROWS + lane, rb, ra);
+            for (int m = warp; m < j1; m += NW) cp_async8(As + lane * ALD + m, ra ? rb + (int64_t)m * stride : Pg, ra);
+        }
         {
             const bool ok = lane < w;
             for (int c = warp; c < NB; c += NW)                           // D[i][c], lanes = rows
@@ -424,19 +441,29 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
     }
     __syncthreads();
     TRACE(2);
-    // ---- U: left-looking update, strips of 8 rows x 32 columns (4 DMMA tiles) round-robin over the warps
-    const int64_t stride = kind == 0 ? F.f : (kind == 1 ? F.r : 1);
-    auto row_ptr = [&](int64_t idx, double*& b, bool& act) {
-        if (kind == 0) { act = j1 + idx < F.f; b = F.P + j1 + idx; }
-        else if (kind == 1) { act = idx < F.r; b = F.T + idx; }
-        else { act = j1 + idx < k; b = F.P + (j1 + idx) * F.f; }
-    };
+    // ---- U: left-looking update, pieces of 8 rows x 16 columns (2 DMMA tiles) round-robin over the warps
     const double* cf = kind == 0 ? Uc : Lc;
     constexpr int NPIECE = (ROWS / 8 + 4) * 2;      // pieces of 8 rows x 16 columns (2 DMMA tiles)
     for (int pc = warp; pc < NPIECE; pc += PANEL_THREADS / 32) {
         const int st = pc >> 1, ch = (pc & 1) * 16;
         double acc[2][2];
         if (st < ROWS / 8) {                        // a piece of the row block
+            if (STAGE_ROWS) {
+                const double* __restrict__ ar = As + (st * 8 + fr) * ALD;
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int c = ch + 8 * j + 2 * fc + e;
+                        acc[j][e] = c < w ? ar[j0 + c] : 0.0;
+                    }
+                for (int m0 = 0; m0 < j0; m0 += 4) {
+                    const double a = -ar[m0 + fc];
+                    const double* __restrict__ cm = cf + (m0 + fc) * CLD + ch + fr;
+                    dmma884(acc[0][0], acc[0][1], a, cm[0]);
+                    dmma884(acc[1][0], acc[1][1], a, cm[8]);
+                }
+            } else {
             double* fb; bool fa;
             row_ptr((int64_t)tk.z * ROWS + st * 8 + fr, fb, fa);
 #pragma unroll
@@ -457,6 +484,7 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
                     dmma884(acc[0][0], acc[0][1], a, cm[0]);
                     dmma884(acc[1][0], acc[1][1], a, cm[8]);
                 }
+            }
             }
             double* xs = Xs + (st * 8 + fr) * CLD + ch + 2 * fc;
 #pragma unroll
@@ -1129,7 +1157,9 @@ int debug_read_trace(long long* out) {
 constexpr int SMALL_FPC32 = 4;     // fronts per CTA in the one-warp class of k_small_factor
 
 static size_t gemm_smem() { return sizeof(double) * 2 * 2 * NB * GEMM_LDS; }
-static size_t panel_smem(int j0, int rows) { return sizeof(double) * (2 * (size_t)j0 + rows) * CLD; }
+static size_t panel_smem(int j0, int rows) {
+    return sizeof(double) * ((2 * (size_t)j0 + rows) * CLD + (rows == PANEL_ROWS_TOP ? (size_t)rows * (KW + 4) : 0));
+}
 
 cudaError_t kernels_init() {
     cudaError_t e = cudaFuncSetAttribute(k_small_factor<96, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
