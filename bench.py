@@ -374,6 +374,7 @@ def run_ours(args, rank, world, local_rank):
         kinds[kname] = {"ms": round(ms, 4), "launches": int(launches_kernel.get(kname, 0)),
                         "share": round(ms / step_ms_prof, 4),
                         "GB/s": round(w["bytes"] / (ms * 1e-3) / 1e9, 1),
+                        "frac_hbm": round(w["bytes"] / (ms * 1e-3) / 1e9 / hbm_gbs, 4),
                         "TFLOP/s": round(w["flops"] / (ms * 1e-3) / 1e12, 3)}
     if dom == "gemm_cb":   # FP64 contraction: bound by the FP64 pipe (DFMA/DMMA), not bf16 tensor peak
         ach = work[dom]["flops"] / (ms_kernel[dom] * 1e-3) / 1e12
