@@ -24,7 +24,7 @@
 #                                bit-identical to the reference's and L, U agree to rounding.
 module SharedMemSparseLU
 
-export ParallelSparseLU, cleanup_ParallelSparseLU!, allocate_shared
+export ParallelSparseLU, cleanup_ParallelSparseLU!, allocate_shared, comm_unique_id
 
 using LinearAlgebra
 using SparseArrays
@@ -48,7 +48,9 @@ struct SmsluOptions
     scaling::Int32
     device::Int32
     use_graph::Int32
-    reserved::NTuple{8,Int32}
+    nranks::Int32
+    rank::Int32
+    reserved::NTuple{6,Int32}
 end
 
 const ORDERINGS = Dict(:auto => 0, :natural => 1, :given => 2, :nd_graph => 3, :nd_grid => 4)
@@ -92,7 +94,9 @@ mutable struct ParallelSparseLU{Tf,Ti}
 
     function ParallelSparseLU(A::SparseMatrixCSC{Tf,Ti}, chunk_size=nothing;
                               pivots::Symbol=:native, ordering::Symbol=:auto,
-                              grid=nothing, device::Integer=-1) where {Tf<:Float64,Ti<:Int64}
+                              grid=nothing, device::Integer=-1,
+                              nranks::Integer=1, rank::Integer=0,
+                              comm_id::Union{Vector{UInt8},Nothing}=nothing) where {Tf<:Float64,Ti<:Int64}
         size(A, 1) == size(A, 2) || throw(DimensionMismatch("matrix is not square: $(size(A))"))
         chunk_size === nothing && (chunk_size = 8)                       # src:67-70
         chunk_size = min(chunk_size, A.n)                                # src:72
@@ -107,7 +111,7 @@ mutable struct ParallelSparseLU{Tf,Ti}
         g = grid === nothing ? (Int32(0), Int32(0), Int32(0)) :
             (Int32(grid[1]), Int32(length(grid) > 1 ? grid[2] : 1), Int32(length(grid) > 2 ? grid[3] : 1))
         o = SmsluOptions(Int32(ORDERINGS[ordering]), g, o.nd_leaf, o.relax, o.max_width, o.scaling,
-                         Int32(device), o.use_graph, o.reserved)
+                         Int32(device), o.use_graph, Int32(nranks), Int32(rank), o.reserved)
         h = Ref{Ptr{Cvoid}}(C_NULL)
         rc = ccall((:smslu_create, libsmslu), Cint,
                    (Ptr{Ptr{Cvoid}}, Int64, Ptr{Int64}, Ptr{Int64}, Int32, Ptr{SmsluOptions}),
@@ -117,9 +121,28 @@ mutable struct ParallelSparseLU{Tf,Ti}
         finalizer(cleanup_ParallelSparseLU!, F)
         check(F.handle, ccall((:smslu_analyze, libsmslu), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}),
                               F.handle, p === nothing ? C_NULL : p, q === nothing ? C_NULL : q))
+        if nranks > 1
+            # one process (MPI rank) per GPU: every rank analyses the same pattern; the 128-byte id comes from
+            # `comm_unique_id()` on rank 0, e.g.  id = MPI.bcast(rank == 0 ? comm_unique_id() : nothing, 0, comm)
+            comm_id === nothing && throw(ArgumentError("nranks > 1 needs comm_id (see comm_unique_id)"))
+            check(F.handle, ccall((:smslu_comm_init, libsmslu), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int64),
+                                  F.handle, comm_id, length(comm_id)))
+        end
         lu!(F, A)
         return F
     end
+end
+
+"""
+    comm_unique_id() -> Vector{UInt8}
+
+128-byte NCCL id for a multi-GPU `ParallelSparseLU`; call on rank 0 and broadcast to the other ranks.
+"""
+function comm_unique_id()
+    id = zeros(UInt8, 128)
+    rc = ccall((:smslu_comm_unique_id, libsmslu), Cint, (Ptr{UInt8}, Int64), id, 128)
+    rc == 0 || error("smslu_comm_unique_id failed with code $rc")
+    return id
 end
 
 """
@@ -235,7 +258,7 @@ allocate_shared(args...) = (ccall((:smslu_allocate_shared, libsmslu), Cint, ());
 
 # Diagnostics: nnz, supernodes, levels, per-phase device times of the last calls.
 function stats(F::ParallelSparseLU)
-    buf = zeros(UInt8, 8 * (14 + 9 + 5 + 16 + 16 + 8))
+    buf = zeros(UInt8, 8 * (14 + 9 + 5 + 16 + 16 + 8))     # sizeof(smslu_stats_t)
     check(F.handle, ccall((:smslu_get_stats, libsmslu), Cint, (Ptr{Cvoid}, Ptr{UInt8}), F.handle, buf))
     i64 = reinterpret(Int64, buf); f64 = reinterpret(Float64, buf)
     return (n=i64[1], nnz_a=i64[2], nnz_l=i64[3], nnz_u=i64[4], supernodes=i64[7], levels=i64[8],
