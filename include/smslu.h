@@ -53,10 +53,10 @@ typedef struct smslu_options {
     int32_t grid[3];         /* nx, ny, nz with idx = i + nx*(j + ny*k); 0 = unknown          */
     int32_t nd_leaf;         /* stop dissecting below this many vertices                       */
     int32_t relax;           /* relaxed supernode amalgamation on/off                          */
-    int32_t max_width;       /* pivot-block width of a front (<= 32)                           */
+    int32_t max_width;       /* pivot-block width of a front (<= 128); wider supernodes are chained */
     int32_t scaling;         /* SMSLU_SCALE_*, used when smslu_refactor gets Rs == NULL        */
     int32_t device;          /* CUDA device ordinal; -1 = current device                       */
-    int32_t use_graph;       /* replay the level schedule through CUDA graphs                  */
+    int32_t use_graph;       /* reserved (ignored): launch cost is hidden behind the kernels   */
     int32_t nranks;          /* GPUs (= processes) the elimination tree is partitioned over; 0/1 = one GPU */
     int32_t rank;            /* this process' rank in [0, nranks)                                */
     int32_t reserved[6];

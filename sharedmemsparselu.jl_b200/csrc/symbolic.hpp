@@ -48,7 +48,7 @@ struct Symbolic {
     std::vector<int> sn_parent;       // -1 for roots
     std::vector<int> child_ptr, child_idx;   // children in ascending order
     // direct[c] = 1: c is the only child of its parent and a 'big' front, so its Schur update is
-    // written straight into the parent's panels / contribution block (no extend-add pass).
+    // written straight into the parent's panels / contribution block (no assembly pass).
     // cb_assigned[s] = 1: every entry of C_s is assigned by that direct child (no zeroing pass).
     std::vector<char> direct, cb_assigned;
     std::vector<int> sn_level;        // 0 = leaves
