@@ -632,11 +632,11 @@ int enqueue_gather_solution(smslu_handle_t h, int rb) {
     return prof_end(h);
 }
 
-// rb right-hand sides (columns bdev + q * ldb) are swept together; rb is 1, 4 or 8.
-int enqueue_solve(smslu_handle_t h, double* xdev, int64_t ldx, const double* bdev, int64_t ldb, int rb) {
+// nv right-hand sides (columns bdev + q * ldb) are swept together in rb = 1, 4 or 8 slots (nv <= rb).
+int enqueue_solve(smslu_handle_t h, double* xdev, int64_t ldx, const double* bdev, int64_t ldb, int rb, int nv) {
     int rc;
     if ((rc = prof_begin(h, SMSLU_K_PERMUTE))) return rc;
-    launch_permute_scale(h->stream, h->n, h->d_p, h->d_Rs, bdev, ldb, h->d_w, rb);
+    launch_permute_scale(h->stream, h->n, h->d_p, h->d_Rs, bdev, ldb, h->d_w, rb, nv);
     if ((rc = prof_end(h))) return rc;
     if ((rc = run_schedule(h, h->fwd, h->d_w, h->d_z, rb))) return rc;
     if (h->nranks > 1) {
@@ -646,12 +646,13 @@ int enqueue_solve(smslu_handle_t h, double* xdev, int64_t ldx, const double* bde
     if ((rc = run_schedule(h, h->bwd, nullptr, h->d_z, rb))) return rc;
     if (h->nranks > 1 && (rc = enqueue_gather_solution(h, rb))) return rc;
     if ((rc = prof_begin(h, SMSLU_K_UNPERMUTE))) return rc;
-    launch_unpermute(h->stream, h->n, h->d_q, h->d_z, xdev, ldx, rb);
+    launch_unpermute(h->stream, h->n, h->d_q, h->d_z, xdev, ldx, rb, nv);
     if ((rc = prof_end(h))) return rc;
     return 0;
 }
 
-inline int chunk_rb(int64_t left) { return left >= 8 ? 8 : (left >= 4 ? 4 : 1); }
+// slots of the next sweep: a partly filled sweep of 4 or 8 beats several narrower ones
+inline int chunk_rb(int64_t left) { return left >= 5 ? 8 : (left >= 2 ? 4 : 1); }
 
 }  // namespace
 
@@ -831,7 +832,7 @@ int smslu_solve_async(smslu_handle_t h, double* x_dev, const double* b_dev) {
     if (!is_device_ptr(x_dev) || !is_device_ptr(b_dev)) return fail(h, SMSLU_E_ARG, "smslu_solve_async needs device pointers");
     CU(cudaSetDevice(h->device));
     h->st.launches_solve = (int64_t)h->fwd.size() + (int64_t)h->bwd.size() + 2;
-    return enqueue_solve(h, x_dev, h->n, b_dev, h->n, 1);
+    return enqueue_solve(h, x_dev, h->n, b_dev, h->n, 1, 1);
 }
 
 int smslu_sync(smslu_handle_t h) {
@@ -886,27 +887,28 @@ int smslu_solve(smslu_handle_t h, double* x, int64_t nx, const double* b, int64_
     float h2d = 0, dev = 0, d2h = 0, ms;
     int64_t nsweeps = 0;
     for (int64_t c = 0; c < nrhs;) {
-        const int rb = chunk_rb(nrhs - c);               // 8, 4 or 1 right-hand sides per sweep
+        const int rb = chunk_rb(nrhs - c);               // 8, 4 or 1 slots per sweep
+        const int nv = (int)std::min<int64_t>(rb, nrhs - c);
         const double* bc = b + c * ldb;
         double* xc = x + c * ldx;
         int64_t lb = ldb, lx = ldx;
         CU(cudaEventRecord(h->ev0, h->stream));
         if (!bdev) {                                     // host columns -> contiguous device block, ld = n
-            CU(cudaMemcpy2DAsync(h->d_xb, sizeof(double) * n, bc, sizeof(double) * ldb, sizeof(double) * n, rb,
+            CU(cudaMemcpy2DAsync(h->d_xb, sizeof(double) * n, bc, sizeof(double) * ldb, sizeof(double) * n, nv,
                                  cudaMemcpyHostToDevice, h->stream));
             bc = h->d_xb; lb = n;
         }
         CU(cudaEventRecord(h->ev1, h->stream));
-        if ((rc = enqueue_solve(h, xdev ? xc : h->d_xb, xdev ? lx : n, bc, lb, rb))) return rc;
+        if ((rc = enqueue_solve(h, xdev ? xc : h->d_xb, xdev ? lx : n, bc, lb, rb, nv))) return rc;
         CU(cudaEventRecord(h->ev2, h->stream));
-        if (!xdev) CU(cudaMemcpy2DAsync(xc, sizeof(double) * ldx, h->d_xb, sizeof(double) * n, sizeof(double) * n, rb,
+        if (!xdev) CU(cudaMemcpy2DAsync(xc, sizeof(double) * ldx, h->d_xb, sizeof(double) * n, sizeof(double) * n, nv,
                                         cudaMemcpyDeviceToHost, h->stream));
         CU(cudaEventRecord(h->ev3, h->stream));
         CU(cudaStreamSynchronize(h->stream));
         CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1)); h2d += ms;
         CU(cudaEventElapsedTime(&ms, h->ev1, h->ev2)); dev += ms;
         CU(cudaEventElapsedTime(&ms, h->ev2, h->ev3)); d2h += ms;
-        c += rb; ++nsweeps;
+        c += nv; ++nsweeps;
     }
     h->st.ms_solve_h2d = h2d; h->st.ms_solve = dev; h->st.ms_solve_d2h = d2h;
     h->st.launches_solve = nsweeps * ((int64_t)h->fwd.size() + (int64_t)h->bwd.size() + 2);
@@ -924,29 +926,30 @@ static int tri_solve(smslu_handle_t h, double* x, int64_t nx, int64_t nrhs, int6
     const bool dev = is_device_ptr(x);
     for (int64_t c = 0; c < nrhs;) {
         const int rb = chunk_rb(nrhs - c);
+        const int nv = (int)std::min<int64_t>(rb, nrhs - c);
         double* xc = x + c * ld;
         const double* src = xc; int64_t lsrc = ld;
         if (!dev) {
-            CU(cudaMemcpy2DAsync(h->d_xb, sizeof(double) * n, xc, sizeof(double) * ld, sizeof(double) * n, rb,
+            CU(cudaMemcpy2DAsync(h->d_xb, sizeof(double) * n, xc, sizeof(double) * ld, sizeof(double) * n, nv,
                                  cudaMemcpyHostToDevice, h->stream));
             src = h->d_xb; lsrc = n;
         }
         // interleave the block (identity permutation, no scaling), sweep, de-interleave
         if (lower) {
-            launch_permute_scale(h->stream, n, nullptr, nullptr, src, lsrc, h->d_w, rb);
+            launch_permute_scale(h->stream, n, nullptr, nullptr, src, lsrc, h->d_w, rb, nv);
             if ((rc = run_schedule(h, h->fwd, h->d_w, h->d_z, rb))) return rc;
             if (h->nranks > 1 && (rc = enqueue_top_forward(h, rb))) return rc;
         } else {
-            launch_permute_scale(h->stream, n, nullptr, nullptr, src, lsrc, h->d_z, rb);
+            launch_permute_scale(h->stream, n, nullptr, nullptr, src, lsrc, h->d_z, rb, nv);
             if (h->nranks > 1 && (rc = run_schedule(h, h->bwd_top, nullptr, h->d_z, rb))) return rc;
             if ((rc = run_schedule(h, h->bwd, nullptr, h->d_z, rb))) return rc;
         }
         if (h->nranks > 1 && (rc = enqueue_gather_solution(h, rb))) return rc;
-        launch_unpermute(h->stream, n, nullptr, h->d_z, dev ? xc : h->d_xb, dev ? ld : n, rb);
-        if (!dev) CU(cudaMemcpy2DAsync(xc, sizeof(double) * ld, h->d_xb, sizeof(double) * n, sizeof(double) * n, rb,
+        launch_unpermute(h->stream, n, nullptr, h->d_z, dev ? xc : h->d_xb, dev ? ld : n, rb, nv);
+        if (!dev) CU(cudaMemcpy2DAsync(xc, sizeof(double) * ld, h->d_xb, sizeof(double) * n, sizeof(double) * n, nv,
                                        cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
-        c += rb;
+        c += nv;
     }
     return 0;
 }

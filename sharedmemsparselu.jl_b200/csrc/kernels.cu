@@ -712,23 +712,24 @@ __global__ void __launch_bounds__(256) k_gemm_cb(DevCtx cx, const int4* __restri
 // All solve kernels are templated on RB, the number of right-hand sides swept together (1, 4 or 8): the
 // work vectors are interleaved (entry i of right-hand side q at [i * RB + q]), so the factor entries are
 // read once per RB right-hand sides and every thread's RB values are contiguous.
+// nv <= RB columns are real; the sweep's remaining slots are zero-filled on the way in and dropped on the way out
 template <int RB>
 __global__ void k_permute_scale(int n, const int* __restrict__ p, const double* __restrict__ Rs,
-                                const double* __restrict__ b, int64_t ldb, double* __restrict__ w) {
+                                const double* __restrict__ b, int64_t ldb, double* __restrict__ w, int nv) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int pi = p ? p[i] : i;
     const double sc = Rs ? Rs[pi] : 1.0;
 #pragma unroll
-    for (int q = 0; q < RB; ++q) w[(int64_t)i * RB + q] = sc * b[pi + q * ldb];
+    for (int q = 0; q < RB; ++q) w[(int64_t)i * RB + q] = q < nv ? sc * b[pi + q * ldb] : 0.0;
 }
 template <int RB>
-__global__ void k_unpermute(int n, const int* __restrict__ qv, const double* __restrict__ w, double* __restrict__ x, int64_t ldx) {
+__global__ void k_unpermute(int n, const int* __restrict__ qv, const double* __restrict__ w, double* __restrict__ x, int64_t ldx, int nv) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int qi = qv ? qv[i] : i;
 #pragma unroll
-    for (int q = 0; q < RB; ++q) x[qi + q * ldx] = w[(int64_t)i * RB + q];
+    for (int q = 0; q < RB; ++q) if (q < nv) x[qi + q * ldx] = w[(int64_t)i * RB + q];
 }
 
 // Triangular solves with the k x k pivot block (k <= KW = 128) of a big front, without staging the block:
@@ -1242,13 +1243,13 @@ void launch_panel(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntas
 void launch_gemm_cb(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks) {
     if (ntasks > 0) k_gemm_cb<<<ntasks, 256, gemm_smem(), st>>>(cx, tasks);
 }
-void launch_permute_scale(cudaStream_t st, int n, const int* p, const double* Rs, const double* b, int64_t ldb, double* w, int rb) {
-#define CALL(R) k_permute_scale<R><<<(n + 255) / 256, 256, 0, st>>>(n, p, Rs, b, ldb, w)
+void launch_permute_scale(cudaStream_t st, int n, const int* p, const double* Rs, const double* b, int64_t ldb, double* w, int rb, int nv) {
+#define CALL(R) k_permute_scale<R><<<(n + 255) / 256, 256, 0, st>>>(n, p, Rs, b, ldb, w, nv)
     RB_DISPATCH(rb, CALL);
 #undef CALL
 }
-void launch_unpermute(cudaStream_t st, int n, const int* q, const double* w, double* x, int64_t ldx, int rb) {
-#define CALL(R) k_unpermute<R><<<(n + 255) / 256, 256, 0, st>>>(n, q, w, x, ldx)
+void launch_unpermute(cudaStream_t st, int n, const int* q, const double* w, double* x, int64_t ldx, int rb, int nv) {
+#define CALL(R) k_unpermute<R><<<(n + 255) / 256, 256, 0, st>>>(n, q, w, x, ldx, nv)
     RB_DISPATCH(rb, CALL);
 #undef CALL
 }
