@@ -139,6 +139,62 @@ __global__ void luD(const double* A, double* out, long long* cyc, int reps) {
 #pragma unroll
     for (int i = 0; i < K; ++i) out[i + lane * K] = a[i];
 }
+// LU-K: the pivot-warp code of k_panel verbatim (row from shared memory, identity padding, branch-free bad-pivot
+// bookkeeping, factor rows written back to shared memory), warp 0 of a 256-thread CTA.
+__device__ __forceinline__ bool bad_pivot(double p) { return !(fabs(p) > 0.0) || !isfinite(p); }
+__global__ void luK(const double* A, double* out, long long* cyc, int reps, int kind, int w) {
+    __shared__ __align__(16) double D[K][CLD];
+    __shared__ __align__(16) double W[K][CLD];
+    __shared__ double rd[K];
+    __shared__ int flag;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    long long tot = 0;
+    double x[K];
+    for (int r = 0; r < reps; ++r) {
+        for (int e = tid; e < K * K; e += blockDim.x) D[e % K][e / K] = A[e] + r * 1e-9;
+        __syncthreads();
+        long long t0 = clock64();
+        if (warp == 0) {
+#pragma unroll
+            for (int c2 = 0; c2 < K / 2; ++c2) {
+                const double2 v = *reinterpret_cast<const double2*>(&D[lane][2 * c2]);
+                x[2 * c2] = v.x; x[2 * c2 + 1] = v.y;
+            }
+#pragma unroll
+            for (int c = 0; c < K; ++c) x[c] = (lane >= w && c == lane) ? 1.0 : x[c];
+            double myr = 0.0;
+            int bad = K;
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const double piv = __shfl_sync(0xffffffffu, x[j], j);
+                const double rinv = 1.0 / piv;
+                bad = (bad == K && bad_pivot(piv)) ? j : bad;
+                myr = lane == j ? rinv : myr;
+                const double l = lane > j ? x[j] * rinv : 0.0;
+                x[j] = lane > j ? l : x[j];
+#pragma unroll
+                for (int c = j + 1; c < K; ++c) x[c] -= l * __shfl_sync(0xffffffffu, x[c], j);
+            }
+            rd[lane] = myr;
+            if (lane == 0 && bad < w) atomicMin(&flag, bad);
+            if (kind == 0) {
+#pragma unroll
+                for (int c2 = 0; c2 < K / 2; ++c2) *reinterpret_cast<double2*>(&W[lane][2 * c2]) = make_double2(x[2 * c2], x[2 * c2 + 1]);
+            } else {
+#pragma unroll
+                for (int p = 0; p < K; ++p) W[p][lane] = x[p];
+            }
+        }
+        tot += clock64() - t0;
+        __syncthreads();
+    }
+    if (tid == 0) *cyc = tot / reps;
+    if (warp == 0) {
+#pragma unroll
+        for (int c = 0; c < K; ++c) out[lane + c * K] = x[c];
+    }
+    if (tid == 300) out[0] = W[1][1] + rd[1];
+}
 // LU-C: as LU-A but the whole block lives in shared memory D[i][CLD]; thread (lane = row, warp = 8 columns)
 // reads the pivot row with 128-bit loads; one barrier per step, reciprocal produced one step ahead.
 __global__ void luC(const double* A, double* out, long long* cyc, int reps) {
@@ -309,6 +365,9 @@ int main() {
         luB2<0><<<1, 128>>>(A, out, cyc, reps); rep("LU-B2 1 warp, early reciprocal (1.0/x)", true);
         luB2<1><<<1, 128>>>(A, out, cyc, reps); rep("LU-B3 1 warp, early reciprocal (__drcp_rn)", true);
         luD<<<1, 128>>>(A, out, cyc, reps); rep("LU-D 1 warp, lane = column", true);
+        luK<<<1, 256>>>(A, out, cyc, reps, 0, 32); rep("LU-K k_panel pivot warp verbatim, hot (100 reps)", true);
+        luK<<<1, 256>>>(A, out, cyc, 1, 0, 32); rep("LU-K k_panel pivot warp verbatim, single cold rep", false);
+        luB<<<1, 128>>>(A, out, cyc, 1); rep("LU-B single cold rep", false);
         trsmT<<<1, 128>>>(A, X, cyc, reps); rep("TRSM-T registers, 128-bit factor loads", false);
         updU1<<<1, 128, 96 * CLD * 8>>>(Rg, X, cyc, reps, 96); rep("UPD-U1 j0=96 thread=row, 128-bit coef loads", false);
         updU2<<<1, 128, 96 * CLD * 8>>>(Rg, X, cyc, reps, 96); rep("UPD-U2 j0=96 DMMA", false);

@@ -39,6 +39,12 @@ __device__ __forceinline__ Front load_front(const DevCtx& cx, int s) {
     return F;
 }
 
+// Programmatic dependent launch: every task kernel lets its successor start launching right away and reads its
+// own static metadata (task record, front geometry) before waiting for the predecessor's results, so the
+// successor's prologue overlaps the predecessor's tail.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ bool bad_pivot(double p) { return !(fabs(p) > 0.0) || !isfinite(p); }
 
 constexpr int SMALL_F_MAX = 96;   // largest front handled by the shared-memory kernels (with k <= NB)
@@ -68,10 +74,12 @@ __global__ void k_scatter(int64_t nnz, const int64_t* __restrict__ dst, const in
 // ------------------------------------------------------------------ zero contribution blocks
 // task: x = supernode, y = tile
 __global__ void __launch_bounds__(256) k_zero_cb(DevCtx cx, const int4* __restrict__ tasks) {
+    pdl_trigger();
     int4 tk = tasks[blockIdx.x];
     int64_t r = cx.rows_ptr[tk.x + 1] - cx.rows_ptr[tk.x];
     int64_t tot = r * r;
     double* C = cx.cb + cx.CBoff[tk.x];
+    pdl_wait();
     int64_t lo = (int64_t)tk.y * ZERO_TILE, hi = lo + ZERO_TILE;
     if (hi > tot) hi = tot;
     for (int64_t e = lo + threadIdx.x; e < hi; e += 256) C[e] = 0.0;
@@ -90,8 +98,10 @@ __global__ void __launch_bounds__(256) k_zero_cb(DevCtx cx, const int4* __restri
 __global__ void __launch_bounds__(256) k_assemble(DevCtx cx, const int4* __restrict__ tasks) {
     const int4 tk = tasks[blockIdx.x];
     const int s = tk.x, pb0 = tk.y, nch = tk.w >> 8;
+    pdl_trigger();
     const int* __restrict__ meta = cx.asm_meta + tk.z;
     const Front F = load_front(cx, s);
+    pdl_wait();
     const int k = F.k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int pb1 = pb0 + ASM_COLS < (int)F.f ? pb0 + ASM_COLS : (int)F.f;
     if (tk.w & 1) {
@@ -167,8 +177,10 @@ __global__ void __launch_bounds__(RW * CH * FPC) k_small_factor(DevCtx cx, const
     const int ti = blockIdx.x * FPC + grp;
     if (ti >= ntasks) return;                                 // FPC > 1: a whole warp leaves
     auto sync = [&]() { if (NT == 32) __syncwarp(); else __syncthreads(); };
+    pdl_trigger();
     const int s = tasks[ti].x;
     const Front F = load_front(cx, s);
+    pdl_wait();
     const int k = F.k, r = (int)F.r, f = (int)F.f, ld = small_ld(f);
     double* Fs = sm + (size_t)grp * small_group_doubles(fmax);
     double* rd = Fs + (size_t)fmax * small_ld(fmax);
@@ -270,8 +282,10 @@ __global__ void __launch_bounds__(((NC + 31) / 32) * 32 * FPC) k_small_factor_re
     const int ti = blockIdx.x * FPC + grp;
     if (ti >= ntasks) return;
     auto sync = [&]() { if (NT == 32) __syncwarp(); else __syncthreads(); };
+    pdl_trigger();
     const int s = tasks[ti].x;
     const Front F = load_front(cx, s);
+    pdl_wait();
     const int k = F.k, r = (int)F.r, f = (int)F.f;
     double* Fs = sm + (size_t)grp * reg_group_doubles(NC);
     double* strip = Fs + NC * ld;                     // strip[2][SL]: row j (NC values), 1/u_jj at [NC]
@@ -395,8 +409,10 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
     __shared__ __align__(16) double W[NB][CLD];     // W[p][c] = U[p][c] (kind 0) or L[c][p] (kinds 1, 2)
     __shared__ double rd[NB];
     TRACE(0);
+    pdl_trigger();
     int4 tk = tasks[blockIdx.x];
     const Front F = load_front(cx, tk.x);
+    pdl_wait();
     const int g = tk.y & 15, kind = (tk.y >> 4) & 15, total = tk.y >> 8;
     const int k = F.k, j0 = g * NB, w = (k - j0 < NB) ? k - j0 : NB, j1 = j0 + w;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, fr = lane >> 2, fc = lane & 3;
@@ -607,8 +623,10 @@ constexpr int GEMM_LDS = GEMM_TILE + 4;   // row stride = 4 (mod 16) doubles: fr
 
 __global__ void __launch_bounds__(256) k_gemm_cb(DevCtx cx, const int4* __restrict__ tasks) {
     extern __shared__ __align__(16) double gsm[];         // 2 stages x (As[NB][GEMM_LDS] | Bs[NB][GEMM_LDS])
+    pdl_trigger();
     int4 tk = tasks[blockIdx.x];
     const Front F = load_front(cx, tk.x);
+    pdl_wait();
     const int k = F.k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t m0 = (int64_t)tk.y * GEMM_TILE, n0 = (int64_t)tk.z * GEMM_TILE;
     const double* __restrict__ A = F.P + F.k;
@@ -824,9 +842,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_fwd(DevCtx cx, const int4* __
     __shared__ double ys[KW * RB];
     __shared__ double acc[FWD_ROWS * RB];
     __shared__ double red[4][FWD_ROWS * RB];
+    pdl_trigger();
     int4 tk = tasks[blockIdx.x];
     const int s = tk.x;
     const Front F = load_front(cx, s);
+    pdl_wait();
     const int k = F.k, tid = threadIdx.x, kp = ((k + NB - 1) / NB) * NB;
     const int64_t lo = (int64_t)tk.y * FWD_ROWS;            // first update row of this tile
     for (int e = tid; e < KW * RB; e += SOLVE_THREADS) ys[e] = e < k * RB ? win[(int64_t)F.c0 * RB + e] : 0.0;
@@ -919,9 +939,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_bwd(DevCtx cx, const int4* __
     __shared__ double xs[BWD_ROWS * RB];
     __shared__ double part[KW * RB];
     __shared__ int s_last;
+    pdl_trigger();
     int4 tk = tasks[blockIdx.x];
     const int s = tk.x, ntiles = tk.z;
     const Front F = load_front(cx, s);
+    pdl_wait();
     const int k = F.k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t lo = (int64_t)tk.y * BWD_ROWS;
     const int cnt = (int)(F.r - lo < BWD_ROWS ? F.r - lo : BWD_ROWS);
@@ -1043,8 +1065,10 @@ __global__ void __launch_bounds__(32 * FPC) k_small_fwd(DevCtx cx, const int4* _
     const int grp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ti = blockIdx.x * FPC + grp;
     if (ti >= ntasks) return;
+    pdl_trigger();
     const int s = tasks[ti].x;
     const Front F = load_front(cx, s);
+    pdl_wait();
     const int k = F.k, f = (int)F.f;
     double* v = vs[grp];
     for (int e = lane; e < f * RB; e += 32) v[e] = e < k * RB ? win[(int64_t)F.c0 * RB + e] : 0.0;
@@ -1099,8 +1123,10 @@ __global__ void __launch_bounds__(32 * FPC) k_small_bwd(DevCtx cx, const int4* _
     const int grp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ti = blockIdx.x * FPC + grp;
     if (ti >= ntasks) return;
+    pdl_trigger();
     const int s = tasks[ti].x;
     const Front F = load_front(cx, s);
+    pdl_wait();
     const int k = F.k, r = (int)F.r, f = (int)F.f;
     double* xr = xs[grp];
     const int* __restrict__ rows = cx.rows + cx.rows_ptr[s];
@@ -1162,6 +1188,18 @@ static size_t panel_smem(int j0, int rows) {
     return sizeof(double) * ((2 * (size_t)j0 + rows) * CLD + (rows == PANEL_ROWS_TOP ? (size_t)rows * (KW + 4) : 0));
 }
 
+// launch with programmatic stream serialization (see pdl_trigger / pdl_wait)
+template <class... KArgs, class... Args>
+static void launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 cudaError_t kernels_init() {
     cudaError_t e = cudaFuncSetAttribute(k_small_factor<96, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(sizeof(double) * small_group_doubles(96)));
@@ -1186,29 +1224,29 @@ void launch_scatter(cudaStream_t st, int64_t nnz, const int64_t* dst, const int*
     k_scatter<<<(int)blocks, 256, 0, st>>>(nnz, dst, arow, asrc, Rs, av, lu);
 }
 void launch_zero_cb(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks) {
-    if (ntasks > 0) k_zero_cb<<<ntasks, 256, 0, st>>>(cx, tasks);
+    if (ntasks > 0) launch_pdl(k_zero_cb, ntasks, 256, 0, st, cx, tasks);
 }
 void launch_assemble(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks) {
-    if (ntasks > 0) k_assemble<<<ntasks, 256, 0, st>>>(cx, tasks);
+    if (ntasks > 0) launch_pdl(k_assemble, ntasks, 256, 0, st, cx, tasks);
 }
 template <int RW, int CH, int FPC>
 static void launch_small_class(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int fmax,
                                const double* av, const double* Rs) {
-    k_small_factor<RW, CH, FPC><<<(ntasks + FPC - 1) / FPC, RW * CH * FPC,
-                                  sizeof(double) * small_group_doubles(fmax) * FPC, st>>>(cx, tasks, ntasks, fmax, av, Rs);
+    launch_pdl(k_small_factor<RW, CH, FPC>, (ntasks + FPC - 1) / FPC, RW * CH * FPC,
+               sizeof(double) * small_group_doubles(fmax) * FPC, st, cx, tasks, ntasks, fmax, av, Rs);
 }
 void launch_front_small(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int fmax,
                         const double* av, const double* Rs) {
     if (ntasks <= 0) return;
     if (fmax <= 32)
-        k_small_factor_reg<32, SMALL_FPC32><<<(ntasks + SMALL_FPC32 - 1) / SMALL_FPC32, 32 * SMALL_FPC32,
-                                             sizeof(double) * reg_group_doubles(32) * SMALL_FPC32, st>>>(cx, tasks, ntasks, av, Rs);
+        launch_pdl(k_small_factor_reg<32, SMALL_FPC32>, (ntasks + SMALL_FPC32 - 1) / SMALL_FPC32, 32 * SMALL_FPC32,
+                   sizeof(double) * reg_group_doubles(32) * SMALL_FPC32, st, cx, tasks, ntasks, av, Rs);
     else if (fmax <= 40)
-        k_small_factor_reg<40, 1><<<ntasks, 64, sizeof(double) * reg_group_doubles(40), st>>>(cx, tasks, ntasks, av, Rs);
+        launch_pdl(k_small_factor_reg<40, 1>, ntasks, 64, sizeof(double) * reg_group_doubles(40), st, cx, tasks, ntasks, av, Rs);
     else if (fmax <= 48)
-        k_small_factor_reg<48, 1><<<ntasks, 64, sizeof(double) * reg_group_doubles(48), st>>>(cx, tasks, ntasks, av, Rs);
+        launch_pdl(k_small_factor_reg<48, 1>, ntasks, 64, sizeof(double) * reg_group_doubles(48), st, cx, tasks, ntasks, av, Rs);
     else if (fmax <= 64)
-        k_small_factor_reg<64, 1><<<ntasks, 64, sizeof(double) * reg_group_doubles(64), st>>>(cx, tasks, ntasks, av, Rs);
+        launch_pdl(k_small_factor_reg<64, 1>, ntasks, 64, sizeof(double) * reg_group_doubles(64), st, cx, tasks, ntasks, av, Rs);
     else launch_small_class<96, 3, 1>(st, cx, tasks, ntasks, fmax, av, Rs);
 }
 #define RB_DISPATCH(rb, CALL) do { if ((rb) == 1) { CALL(1); } else if ((rb) == 4) { CALL(4); } else { CALL(8); } } while (0)
@@ -1225,23 +1263,23 @@ void launch_mask_owned(cudaStream_t st, int n, const int* colowner, int rank, do
 }
 void launch_small_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const double* win, double* zout, int rb) {
     if (ntasks <= 0) return;
-    if (rb == 1) k_small_fwd<8, 1><<<(ntasks + 7) / 8, 256, 0, st>>>(cx, tasks, ntasks, win, zout);
-    else if (rb == 4) k_small_fwd<4, 4><<<(ntasks + 3) / 4, 128, 0, st>>>(cx, tasks, ntasks, win, zout);
-    else k_small_fwd<2, 8><<<(ntasks + 1) / 2, 64, 0, st>>>(cx, tasks, ntasks, win, zout);
+    if (rb == 1) launch_pdl(k_small_fwd<8, 1>, (ntasks + 7) / 8, 256, 0, st, cx, tasks, ntasks, win, zout);
+    else if (rb == 4) launch_pdl(k_small_fwd<4, 4>, (ntasks + 3) / 4, 128, 0, st, cx, tasks, ntasks, win, zout);
+    else launch_pdl(k_small_fwd<2, 8>, (ntasks + 1) / 2, 64, 0, st, cx, tasks, ntasks, win, zout);
 }
 void launch_small_bwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, double* x, int rb) {
     if (ntasks <= 0) return;
-    if (rb == 1) k_small_bwd<8, 1><<<(ntasks + 7) / 8, 256, 0, st>>>(cx, tasks, ntasks, x);
-    else if (rb == 4) k_small_bwd<4, 4><<<(ntasks + 3) / 4, 128, 0, st>>>(cx, tasks, ntasks, x);
-    else k_small_bwd<2, 8><<<(ntasks + 1) / 2, 64, 0, st>>>(cx, tasks, ntasks, x);
+    if (rb == 1) launch_pdl(k_small_bwd<8, 1>, (ntasks + 7) / 8, 256, 0, st, cx, tasks, ntasks, x);
+    else if (rb == 4) launch_pdl(k_small_bwd<4, 4>, (ntasks + 3) / 4, 128, 0, st, cx, tasks, ntasks, x);
+    else launch_pdl(k_small_bwd<2, 8>, (ntasks + 1) / 2, 64, 0, st, cx, tasks, ntasks, x);
 }
 void launch_panel(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int g, int rows) {
     if (ntasks <= 0) return;
-    if (rows == PANEL_ROWS) k_panel<PANEL_ROWS><<<ntasks, PANEL_THREADS, panel_smem(g * NB, PANEL_ROWS), st>>>(cx, tasks);
-    else k_panel<PANEL_ROWS_TOP><<<ntasks, PANEL_THREADS, panel_smem(g * NB, PANEL_ROWS_TOP), st>>>(cx, tasks);
+    if (rows == PANEL_ROWS) launch_pdl(k_panel<PANEL_ROWS>, ntasks, PANEL_THREADS, panel_smem(g * NB, PANEL_ROWS), st, cx, tasks);
+    else launch_pdl(k_panel<PANEL_ROWS_TOP>, ntasks, PANEL_THREADS, panel_smem(g * NB, PANEL_ROWS_TOP), st, cx, tasks);
 }
 void launch_gemm_cb(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks) {
-    if (ntasks > 0) k_gemm_cb<<<ntasks, 256, gemm_smem(), st>>>(cx, tasks);
+    if (ntasks > 0) launch_pdl(k_gemm_cb, ntasks, 256, gemm_smem(), st, cx, tasks);
 }
 void launch_permute_scale(cudaStream_t st, int n, const int* p, const double* Rs, const double* b, int64_t ldb, double* w, int rb, int nv) {
 #define CALL(R) k_permute_scale<R><<<(n + 255) / 256, 256, 0, st>>>(n, p, Rs, b, ldb, w, nv)
@@ -1255,13 +1293,13 @@ void launch_unpermute(cudaStream_t st, int n, const int* q, const double* w, dou
 }
 void launch_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const double* win, double* zout, int rb) {
     if (ntasks <= 0) return;
-#define CALL(R) k_fwd<R><<<ntasks, SOLVE_THREADS, 0, st>>>(cx, tasks, win, zout)
+#define CALL(R) launch_pdl(k_fwd<R>, ntasks, SOLVE_THREADS, 0, st, cx, tasks, win, zout)
     RB_DISPATCH(rb, CALL);
 #undef CALL
 }
 void launch_bwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, double* x, int rb) {
     if (ntasks <= 0) return;
-#define CALL(R) k_bwd<R><<<ntasks, SOLVE_THREADS, 0, st>>>(cx, tasks, x)
+#define CALL(R) launch_pdl(k_bwd<R>, ntasks, SOLVE_THREADS, 0, st, cx, tasks, x)
     RB_DISPATCH(rb, CALL);
 #undef CALL
 }
