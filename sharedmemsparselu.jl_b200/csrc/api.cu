@@ -64,6 +64,8 @@ struct Launch {
     int64_t off;
     int ntasks;
     int fmax;
+    int level;     // launches of one level of one schedule are independent across the two lanes
+    int lane;      // 0 = big-front kernels (main stream), 1 = small-front kernels (auxiliary stream)
 };
 
 double now_ms() {
@@ -86,6 +88,8 @@ struct smslu_handle_s {
 
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t aux_stream = nullptr;       // small-front launches of levels that also have big fronts
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     std::vector<void*> dev_allocs;
     DevCtx cx{};
@@ -182,9 +186,11 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
     auto NC = [&](int s) { return S.child_ptr[s + 1] - S.child_ptr[s]; };
     auto SMALL = [&](int s) { return S.small[s] != 0; };
     int64_t ncounters = 0, slots = 0;
+    int cur_level = 0;
     auto push = [&](std::vector<Launch>& v, int kind, int64_t off, int fmax) {
         int nt = (int)((int64_t)tasks.size() - off);
-        if (nt > 0) v.push_back(Launch{kind, off, nt, fmax});
+        const int lane = (kind == L_SMALL || kind == L_FWD_SMALL || kind == L_BWD_SMALL) ? 1 : 0;
+        if (nt > 0) v.push_back(Launch{kind, off, nt, fmax, cur_level, lane});
     };
     for (int ph = 0; ph < 2; ++ph) {
         std::vector<Launch>& fac = ph == 0 ? h->fac : h->fac_top;
@@ -194,6 +200,7 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
         const int mine = ph == 0 ? rank : -1;
         auto IN = [&](int s) { return S.owner[s] == mine; };
         for (int l = 0; l < S.nlevels; ++l) {
+            cur_level = l;
             const int* sn = S.level_sn.data() + S.level_ptr[l];
             const int cnt = S.level_ptr[l + 1] - S.level_ptr[l];
             // Zero the contribution blocks that receive '+=' contributions.  Extend-add children add
@@ -323,6 +330,7 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
             }
         }
         for (int l = S.nlevels - 1; l >= 0; --l) {
+            cur_level = l;
             int64_t off0 = (int64_t)tasks.size();
             for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t)
                 if (IN(S.level_sn[t]) && SMALL(S.level_sn[t])) tasks.push_back(make_int4(S.level_sn[t], 0, 0, 0));
@@ -364,6 +372,9 @@ int ensure_uploaded(smslu_handle_t h) {
     CU(kernels_init());
     if (h->have_user_stream) { h->stream = h->user_stream; h->own_stream = false; }
     else CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     CU(cudaMallocHost((void**)&h->h_flag, sizeof(int)));
     CU(cudaEventCreate(&h->ev0)); CU(cudaEventCreate(&h->ev1));
     CU(cudaEventCreate(&h->ev2)); CU(cudaEventCreate(&h->ev3));
@@ -532,23 +543,47 @@ int prof_collect(smslu_handle_t h) {   // stream must be synchronized
     return 0;
 }
 
+int launch_one(smslu_handle_t h, cudaStream_t st, const Launch& L, const double* win, double* zx, int rb) {
+    const int4* tk = h->d_tasks + L.off;
+    switch (L.kind) {
+        case L_ZERO: launch_zero_cb(st, h->cx, tk, L.ntasks); break;
+        case L_EXTEND: launch_assemble(st, h->cx, tk, L.ntasks); break;
+        case L_SMALL: launch_front_small(st, h->cx, tk, L.ntasks, L.fmax, h->cur_av, h->d_Rs); break;
+        case L_FWD_SMALL: launch_small_fwd(st, h->cx, tk, L.ntasks, win, zx, rb); break;
+        case L_BWD_SMALL: launch_small_bwd(st, h->cx, tk, L.ntasks, zx, rb); break;
+        case L_PANEL: launch_panel(st, h->cx, tk, L.ntasks, L.fmax & 255, L.fmax >> 8); break;
+        case L_GEMM: launch_gemm_cb(st, h->cx, tk, L.ntasks); break;
+        case L_FWD: launch_fwd(st, h->cx, tk, L.ntasks, win, zx, rb); break;
+        case L_BWD: launch_bwd(st, h->cx, tk, L.ntasks, zx, rb); break;
+    }
+    return 0;
+}
+
+// Inside one level the small-front kernels and the big-front kernels touch disjoint fronts; where a level has
+// both, the small-front launches go to an auxiliary stream (fork / join with events) so that the two chains of
+// launches overlap.  Per-launch profiling keeps everything on one stream.
 int run_schedule(smslu_handle_t h, const std::vector<Launch>& sched, const double* win, double* zx, int rb = 1) {
     int rc;
-    for (const Launch& L : sched) {
-        const int4* tk = h->d_tasks + L.off;
-        if ((rc = prof_begin(h, L.kind))) return rc;
-        switch (L.kind) {
-            case L_ZERO: launch_zero_cb(h->stream, h->cx, tk, L.ntasks); break;
-            case L_EXTEND: launch_assemble(h->stream, h->cx, tk, L.ntasks); break;
-            case L_SMALL: launch_front_small(h->stream, h->cx, tk, L.ntasks, L.fmax, h->cur_av, h->d_Rs); break;
-            case L_FWD_SMALL: launch_small_fwd(h->stream, h->cx, tk, L.ntasks, win, zx, rb); break;
-            case L_BWD_SMALL: launch_small_bwd(h->stream, h->cx, tk, L.ntasks, zx, rb); break;
-            case L_PANEL: launch_panel(h->stream, h->cx, tk, L.ntasks, L.fmax & 255, L.fmax >> 8); break;
-            case L_GEMM: launch_gemm_cb(h->stream, h->cx, tk, L.ntasks); break;
-            case L_FWD: launch_fwd(h->stream, h->cx, tk, L.ntasks, win, zx, rb); break;
-            case L_BWD: launch_bwd(h->stream, h->cx, tk, L.ntasks, zx, rb); break;
+    for (size_t i = 0; i < sched.size();) {
+        size_t j = i;
+        bool lane0 = false, lane1 = false;
+        while (j < sched.size() && sched[j].level == sched[i].level) { (sched[j].lane ? lane1 : lane0) = true; ++j; }
+        const bool fork = lane0 && lane1 && !h->profile && h->aux_stream;
+        if (fork) {
+            CU(cudaEventRecord(h->ev_fork, h->stream));
+            CU(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
         }
-        if ((rc = prof_end(h))) return rc;
+        for (size_t t = i; t < j; ++t) {
+            const Launch& L = sched[t];
+            if ((rc = prof_begin(h, L.kind))) return rc;
+            launch_one(h, fork && L.lane ? h->aux_stream : h->stream, L, win, zx, rb);
+            if ((rc = prof_end(h))) return rc;
+        }
+        if (fork) {
+            CU(cudaEventRecord(h->ev_join, h->aux_stream));
+            CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+        }
+        i = j;
     }
     CU(cudaGetLastError());
     return 0;
@@ -1045,6 +1080,9 @@ int smslu_destroy(smslu_handle_t h) {
         for (cudaEvent_t e : h->pev) cudaEventDestroy(e);
         if (h->h_flag) cudaFreeHost(h->h_flag);
         if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
+        if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }
+        if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+        if (h->ev_join) cudaEventDestroy(h->ev_join);
     }
     delete h;
     return 0;
