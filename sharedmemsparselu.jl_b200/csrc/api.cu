@@ -59,13 +59,15 @@ enum LaunchKind { L_ZERO = SMSLU_K_ZERO, L_EXTEND = SMSLU_K_EXTEND, L_SMALL = SM
                   L_GEMM = SMSLU_K_GEMM, L_FWD = SMSLU_K_FWD, L_BWD = SMSLU_K_BWD,
                   L_FWD_SMALL = SMSLU_K_FWD_SMALL, L_BWD_SMALL = SMSLU_K_BWD_SMALL };
 
+constexpr int NLANES = 3;
+
 struct Launch {
     int kind;
     int64_t off;
     int ntasks;
     int fmax;
     int level;     // launches of one level of one schedule are independent across the two lanes
-    int lane;      // 0 = big-front kernels (main stream), 1 = small-front kernels (auxiliary stream)
+    int lane;      // 0 = big-front kernels (main stream), 1 / 2 = small-front kernels (auxiliary streams)
 };
 
 double now_ms() {
@@ -88,8 +90,8 @@ struct smslu_handle_s {
 
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t aux_stream = nullptr;       // small-front launches of levels that also have big fronts
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t aux_stream[2] = {nullptr, nullptr};   // small-front launches of a level (lanes 1, 2)
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     std::vector<void*> dev_allocs;
     DevCtx cx{};
@@ -189,7 +191,8 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
     int cur_level = 0;
     auto push = [&](std::vector<Launch>& v, int kind, int64_t off, int fmax) {
         int nt = (int)((int64_t)tasks.size() - off);
-        const int lane = (kind == L_SMALL || kind == L_FWD_SMALL || kind == L_BWD_SMALL) ? 1 : 0;
+        // small fronts: factor classes up to 40 rows on lane 1, the wider ones on lane 2; solves on lane 1
+        const int lane = kind == L_SMALL ? (fmax <= 40 ? 1 : 2) : ((kind == L_FWD_SMALL || kind == L_BWD_SMALL) ? 1 : 0);
         if (nt > 0) v.push_back(Launch{kind, off, nt, fmax, cur_level, lane});
     };
     for (int ph = 0; ph < 2; ++ph) {
@@ -372,9 +375,11 @@ int ensure_uploaded(smslu_handle_t h) {
     CU(kernels_init());
     if (h->have_user_stream) { h->stream = h->user_stream; h->own_stream = false; }
     else CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+    for (int a = 0; a < 2; ++a) {
+        CU(cudaStreamCreateWithFlags(&h->aux_stream[a], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&h->ev_join[a], cudaEventDisableTiming));
+    }
     CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     CU(cudaMallocHost((void**)&h->h_flag, sizeof(int)));
     CU(cudaEventCreate(&h->ev0)); CU(cudaEventCreate(&h->ev1));
     CU(cudaEventCreate(&h->ev2)); CU(cudaEventCreate(&h->ev3));
@@ -566,22 +571,27 @@ int run_schedule(smslu_handle_t h, const std::vector<Launch>& sched, const doubl
     int rc;
     for (size_t i = 0; i < sched.size();) {
         size_t j = i;
-        bool lane0 = false, lane1 = false;
-        while (j < sched.size() && sched[j].level == sched[i].level) { (sched[j].lane ? lane1 : lane0) = true; ++j; }
-        const bool fork = lane0 && lane1 && !h->profile && h->aux_stream;
+        bool used[NLANES] = {false, false, false};
+        while (j < sched.size() && sched[j].level == sched[i].level) { used[sched[j].lane] = true; ++j; }
+        const int nused = (int)used[0] + (int)used[1] + (int)used[2];
+        const bool fork = nused > 1 && !h->profile && h->aux_stream[0];
+        auto lane_stream = [&](int lane) { return (fork && lane > 0) ? h->aux_stream[lane - 1] : h->stream; };
         if (fork) {
             CU(cudaEventRecord(h->ev_fork, h->stream));
-            CU(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
+            for (int a = 1; a < NLANES; ++a) if (used[a]) CU(cudaStreamWaitEvent(h->aux_stream[a - 1], h->ev_fork, 0));
         }
         for (size_t t = i; t < j; ++t) {
             const Launch& L = sched[t];
             if ((rc = prof_begin(h, L.kind))) return rc;
-            launch_one(h, fork && L.lane ? h->aux_stream : h->stream, L, win, zx, rb);
+            launch_one(h, lane_stream(L.lane), L, win, zx, rb);
             if ((rc = prof_end(h))) return rc;
         }
         if (fork) {
-            CU(cudaEventRecord(h->ev_join, h->aux_stream));
-            CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+            for (int a = 1; a < NLANES; ++a)
+                if (used[a]) {
+                    CU(cudaEventRecord(h->ev_join[a - 1], h->aux_stream[a - 1]));
+                    CU(cudaStreamWaitEvent(h->stream, h->ev_join[a - 1], 0));
+                }
         }
         i = j;
     }
@@ -1080,9 +1090,11 @@ int smslu_destroy(smslu_handle_t h) {
         for (cudaEvent_t e : h->pev) cudaEventDestroy(e);
         if (h->h_flag) cudaFreeHost(h->h_flag);
         if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
-        if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }
+        for (int a = 0; a < 2; ++a) {
+            if (h->aux_stream[a]) { cudaStreamSynchronize(h->aux_stream[a]); cudaStreamDestroy(h->aux_stream[a]); }
+            if (h->ev_join[a]) cudaEventDestroy(h->ev_join[a]);
+        }
         if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-        if (h->ev_join) cudaEventDestroy(h->ev_join);
     }
     delete h;
     return 0;
