@@ -59,7 +59,7 @@ enum LaunchKind { L_ZERO = SMSLU_K_ZERO, L_EXTEND = SMSLU_K_EXTEND, L_SMALL = SM
                   L_GEMM = SMSLU_K_GEMM, L_FWD = SMSLU_K_FWD, L_BWD = SMSLU_K_BWD,
                   L_FWD_SMALL = SMSLU_K_FWD_SMALL, L_BWD_SMALL = SMSLU_K_BWD_SMALL };
 
-constexpr int NLANES = 3;
+constexpr int NLANES = 4;
 
 struct Launch {
     int kind;
@@ -90,8 +90,8 @@ struct smslu_handle_s {
 
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t aux_stream[2] = {nullptr, nullptr};   // small-front launches of a level (lanes 1, 2)
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    cudaStream_t aux_stream[NLANES - 1] = {nullptr, nullptr, nullptr};   // lanes 1..3 of a level
+    cudaEvent_t ev_fork = nullptr, ev_join[NLANES - 1] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     std::vector<void*> dev_allocs;
     DevCtx cx{};
@@ -188,11 +188,13 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
     auto NC = [&](int s) { return S.child_ptr[s + 1] - S.child_ptr[s]; };
     auto SMALL = [&](int s) { return S.small[s] != 0; };
     int64_t ncounters = 0, slots = 0;
-    int cur_level = 0;
+    int cur_level = 0, big_lane = 0;
     auto push = [&](std::vector<Launch>& v, int kind, int64_t off, int fmax) {
         int nt = (int)((int64_t)tasks.size() - off);
-        // small fronts: factor classes up to 40 rows on lane 1, the wider ones on lane 2; solves on lane 1
-        const int lane = kind == L_SMALL ? (fmax <= 40 ? 1 : 2) : ((kind == L_FWD_SMALL || kind == L_BWD_SMALL) ? 1 : 0);
+        // small fronts: factor classes up to 40 rows on lane 1, the wider ones on lane 2; solves on lane 1;
+        // big fronts of the factorization: lane 0 (wide pivot blocks) or lane 3 (at most 64 pivot columns)
+        const int lane = kind == L_SMALL ? (fmax <= 40 ? 1 : 2) : ((kind == L_FWD_SMALL || kind == L_BWD_SMALL) ? 1 :
+                         ((kind == L_ZERO || kind == L_EXTEND || kind == L_PANEL || kind == L_GEMM) ? big_lane : 0));
         if (nt > 0) v.push_back(Launch{kind, off, nt, fmax, cur_level, lane});
     };
     for (int ph = 0; ph < 2; ++ph) {
@@ -206,52 +208,7 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
             cur_level = l;
             const int* sn = S.level_sn.data() + S.level_ptr[l];
             const int cnt = S.level_ptr[l + 1] - S.level_ptr[l];
-            // Zero the contribution blocks that receive '+=' contributions.  Extend-add children add
-            // at this level; a direct child adds one level earlier, so its parent is zeroed there.
-            // Interface blocks are zero-filled once, before phase A, and arrive here all-reduced.
-            int64_t off = (int64_t)tasks.size();
-            auto zero_tasks = [&](int s) {
-                int64_t tiles = (R(s) * R(s) + ZERO_TILE - 1) / ZERO_TILE;
-                for (int64_t i = 0; i < tiles; ++i) tasks.push_back(make_int4(s, (int)i, 0, 0));
-            };
-            for (int t = 0; t < cnt; ++t) {
-                int s = sn[t];
-                if (!IN(s)) continue;
-                if (S.direct[s] && !S.cb_assigned[S.sn_parent[s]] && R(S.sn_parent[s]) > 0) zero_tasks(S.sn_parent[s]);
-            }
-            push(fac, L_ZERO, off, 0);
-            // assembly of the children's contribution blocks into big parents: one launch, the CTA that
-            // owns a range of destination columns also zero-fills its part of the parent's block.
-            // In phase A a top parent receives this rank's subtree contributions here as well.
-            off = (int64_t)tasks.size();
-            for (int t = 0; t < cnt; ++t) {
-                int s = sn[t];
-                if (SMALL(s) || NC(s) == 0) continue;                 // small parents pull their children
-                if (!(IN(s) || (ph == 0 && S.owner[s] == -1))) continue;
-                std::vector<int> kids;
-                for (int u = S.child_ptr[s]; u < S.child_ptr[s + 1]; ++u) {
-                    const int c = S.child_idx[u];
-                    if (IN(c) && !S.direct[c] && R(c) > 0) kids.push_back(c);
-                }
-                if (kids.empty()) continue;
-                const bool zero = IN(s) && R(s) > 0 && !S.iface[s];
-                const int64_t f = K(s) + R(s);
-                for (int64_t pb0 = 0; pb0 < f; pb0 += ASM_COLS) {
-                    const int64_t moff = (int64_t)h->asm_meta.size();
-                    int np = 0;
-                    for (int c : kids) {            // first column of c whose parent position is >= pb0
-                        const int* rb = S.rel.data() + S.rows_ptr[c];
-                        const int* re = S.rel.data() + S.rows_ptr[c + 1];
-                        const int* it = std::lower_bound(rb, re, (int)pb0);
-                        if (it == re || *it >= pb0 + ASM_COLS) continue;       // nothing of c lands in this range
-                        h->asm_meta.push_back(c); h->asm_meta.push_back((int)(it - rb));
-                        ++np;
-                    }
-                    if (np == 0 && !zero) continue;
-                    tasks.push_back(make_int4(s, (int)pb0, (int)moff, (zero ? 1 : 0) | (np << 8)));
-                }
-            }
-            push(fac, L_EXTEND, off, 0);
+            int64_t off;
             // small fronts by shared-memory class
             const int classes[5] = {32, 40, 48, 64, front_small_limit()};
             int lo = 0;
@@ -265,54 +222,107 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
                 push(fac, L_SMALL, off, classes[ci]);
                 lo = classes[ci];
             }
-            // big fronts: left-looking panel steps (one launch per 32 pivot columns), then Schur update
-            int max_blk = 0;
-            for (int t = 0; t < cnt; ++t) if (IN(sn[t]) && !SMALL(sn[t])) max_blk = std::max(max_blk, (K(sn[t]) + NB - 1) / NB);
-            for (int g = 0; g < max_blk; ++g) {
-                // rows per CTA: 128 when that already gives the machine enough CTAs, else 32
-                int rows = PANEL_ROWS;
-                for (int attempt = 0; attempt < 2; ++attempt) {
-                    off = (int64_t)tasks.size();
-                    const int64_t nc0 = ncounters;
-                    for (int t = 0; t < cnt; ++t) {
-                        int s = sn[t];
-                        if (!IN(s) || SMALL(s)) continue;
-                        const int k = K(s), nblk = (k + NB - 1) / NB;
-                        if (g >= nblk) continue;
-                        const int64_t r = R(s), f = k + r;
-                        const int j1 = std::min(k, (g + 1) * NB);
-                        int tl = (int)((f - j1 + rows - 1) / rows);      // rows below the diagonal block
-                        const int tt = (int)((r + rows - 1) / rows);     // rows of U12'
-                        const int ti = (k - j1 + rows - 1) / rows;       // columns right of it
-                        if (tl + tt + ti == 0) tl = 1;                   // someone has to factor D_gg
-                        const int total = tl + tt + ti;
-                        const int cidx = (int)ncounters++;
-                        for (int i = 0; i < tl; ++i) tasks.push_back(make_int4(s, g | (0 << 4) | (total << 8), i, cidx));
-                        for (int i = 0; i < tt; ++i) tasks.push_back(make_int4(s, g | (1 << 4) | (total << 8), i, cidx));
-                        for (int i = 0; i < ti; ++i) tasks.push_back(make_int4(s, g | (2 << 4) | (total << 8), i, cidx));
-                    }
-                    if (attempt == 0 && (int64_t)tasks.size() - off < 120 && (int64_t)tasks.size() > off) {
-                        tasks.resize(off); ncounters = nc0; rows = PANEL_ROWS_TOP;     // redo with small CTAs
-                        continue;
-                    }
-                    break;
+            // Big fronts in two independent groups, each on its own lane: pivot blocks of at most 64 columns (one or
+            // two panel steps, then their Schur update) do not wait for the 3- and 4-step fronts of the level.
+            auto NARROW = [&](int s) { return K(s) <= 2 * NB; };
+            for (int grp = 0; grp < 2; ++grp) {
+                big_lane = grp == 1 ? 3 : 0;
+                // Zero the contribution blocks that receive '+=' contributions.  Extend-add children add
+                // at this level; a direct child adds one level earlier, so its parent is zeroed there.
+                // Interface blocks are zero-filled once, before phase A, and arrive here all-reduced.
+                off = (int64_t)tasks.size();
+                auto zero_tasks = [&](int s) {
+                    int64_t tiles = (R(s) * R(s) + ZERO_TILE - 1) / ZERO_TILE;
+                    for (int64_t i = 0; i < tiles; ++i) tasks.push_back(make_int4(s, (int)i, 0, 0));
+                };
+                for (int t = 0; t < cnt; ++t) {
+                    int s = sn[t];
+                    if (!IN(s) || NARROW(s) != (grp == 1)) continue;
+                    if (S.direct[s] && !S.cb_assigned[S.sn_parent[s]] && R(S.sn_parent[s]) > 0) zero_tasks(S.sn_parent[s]);
                 }
-                push(fac, L_PANEL, off, g | (rows << 8));
-            }
-            off = (int64_t)tasks.size();
-            for (int t = 0; t < cnt; ++t) {
-                int s = sn[t];
-                int64_t r = R(s);
-                if (!IN(s) || SMALL(s)) continue;
-                int nt = (int)((r + GEMM_TILE - 1) / GEMM_TILE);
-                for (int j = 0; j < nt; ++j)
-                    for (int i = 0; i < nt; ++i) {
-                        int flags = (NC(s) > 0 ? 1 : 0) | (S.direct[s] ? 2 : 0) |
-                                    (S.direct[s] && S.cb_assigned[S.sn_parent[s]] ? 4 : 0);
-                        tasks.push_back(make_int4(s, i, j, flags));
+                push(fac, L_ZERO, off, 0);
+                // assembly of the children's contribution blocks into big parents: one launch, the CTA that
+                // owns a range of destination columns also zero-fills its part of the parent's block.
+                // In phase A a top parent receives this rank's subtree contributions here as well.
+                off = (int64_t)tasks.size();
+                for (int t = 0; t < cnt; ++t) {
+                    int s = sn[t];
+                    if (SMALL(s) || NC(s) == 0 || NARROW(s) != (grp == 1)) continue;   // small parents pull their children
+                    if (!(IN(s) || (ph == 0 && S.owner[s] == -1))) continue;
+                    std::vector<int> kids;
+                    for (int u = S.child_ptr[s]; u < S.child_ptr[s + 1]; ++u) {
+                        const int c = S.child_idx[u];
+                        if (IN(c) && !S.direct[c] && R(c) > 0) kids.push_back(c);
                     }
+                    if (kids.empty()) continue;
+                    const bool zero = IN(s) && R(s) > 0 && !S.iface[s];
+                    const int64_t f = K(s) + R(s);
+                    for (int64_t pb0 = 0; pb0 < f; pb0 += ASM_COLS) {
+                        const int64_t moff = (int64_t)h->asm_meta.size();
+                        int np = 0;
+                        for (int c : kids) {            // first column of c whose parent position is >= pb0
+                            const int* rb = S.rel.data() + S.rows_ptr[c];
+                            const int* re = S.rel.data() + S.rows_ptr[c + 1];
+                            const int* it = std::lower_bound(rb, re, (int)pb0);
+                            if (it == re || *it >= pb0 + ASM_COLS) continue;       // nothing of c lands in this range
+                            h->asm_meta.push_back(c); h->asm_meta.push_back((int)(it - rb));
+                            ++np;
+                        }
+                        if (np == 0 && !zero) continue;
+                        tasks.push_back(make_int4(s, (int)pb0, (int)moff, (zero ? 1 : 0) | (np << 8)));
+                    }
+                }
+                push(fac, L_EXTEND, off, 0);
+                // big fronts: left-looking panel steps (one launch per 32 pivot columns), then Schur update
+                int max_blk = 0;
+                for (int t = 0; t < cnt; ++t) if (IN(sn[t]) && !SMALL(sn[t]) && NARROW(sn[t]) == (grp == 1)) max_blk = std::max(max_blk, (K(sn[t]) + NB - 1) / NB);
+                for (int g = 0; g < max_blk; ++g) {
+                    // rows per CTA: 128 when that already gives the machine enough CTAs, else 32
+                    int rows = PANEL_ROWS;
+                    for (int attempt = 0; attempt < 2; ++attempt) {
+                        off = (int64_t)tasks.size();
+                        const int64_t nc0 = ncounters;
+                        for (int t = 0; t < cnt; ++t) {
+                            int s = sn[t];
+                            if (!IN(s) || SMALL(s) || NARROW(s) != (grp == 1)) continue;
+                            const int k = K(s), nblk = (k + NB - 1) / NB;
+                            if (g >= nblk) continue;
+                            const int64_t r = R(s), f = k + r;
+                            const int j1 = std::min(k, (g + 1) * NB);
+                            int tl = (int)((f - j1 + rows - 1) / rows);      // rows below the diagonal block
+                            const int tt = (int)((r + rows - 1) / rows);     // rows of U12'
+                            const int ti = (k - j1 + rows - 1) / rows;       // columns right of it
+                            if (tl + tt + ti == 0) tl = 1;                   // someone has to factor D_gg
+                            const int total = tl + tt + ti;
+                            const int cidx = (int)ncounters++;
+                            for (int i = 0; i < tl; ++i) tasks.push_back(make_int4(s, g | (0 << 4) | (total << 8), i, cidx));
+                            for (int i = 0; i < tt; ++i) tasks.push_back(make_int4(s, g | (1 << 4) | (total << 8), i, cidx));
+                            for (int i = 0; i < ti; ++i) tasks.push_back(make_int4(s, g | (2 << 4) | (total << 8), i, cidx));
+                        }
+                        if (attempt == 0 && (int64_t)tasks.size() - off < 120 && (int64_t)tasks.size() > off) {
+                            tasks.resize(off); ncounters = nc0; rows = PANEL_ROWS_TOP;     // redo with small CTAs
+                            continue;
+                        }
+                        break;
+                    }
+                    push(fac, L_PANEL, off, g | (rows << 8));
+                }
+                off = (int64_t)tasks.size();
+                for (int t = 0; t < cnt; ++t) {
+                    int s = sn[t];
+                    int64_t r = R(s);
+                    if (!IN(s) || SMALL(s) || NARROW(s) != (grp == 1)) continue;
+                    int nt = (int)((r + GEMM_TILE - 1) / GEMM_TILE);
+                    for (int j = 0; j < nt; ++j)
+                        for (int i = 0; i < nt; ++i) {
+                            int flags = (NC(s) > 0 ? 1 : 0) | (S.direct[s] ? 2 : 0) |
+                                        (S.direct[s] && S.cb_assigned[S.sn_parent[s]] ? 4 : 0);
+                            tasks.push_back(make_int4(s, i, j, flags));
+                        }
+                }
+                push(fac, L_GEMM, off, 0);
             }
-            push(fac, L_GEMM, off, 0);
+            big_lane = 0;
             // forward solve level: warp-per-front kernel for the small fronts; narrow (k <= 32) and
             // wide big fronts go to separate launches because the kernel stages the whole pivot block
             // in shared memory (8 KB vs up to 129 KB)
@@ -375,7 +385,7 @@ int ensure_uploaded(smslu_handle_t h) {
     CU(kernels_init());
     if (h->have_user_stream) { h->stream = h->user_stream; h->own_stream = false; }
     else CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < NLANES - 1; ++a) {
         CU(cudaStreamCreateWithFlags(&h->aux_stream[a], cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&h->ev_join[a], cudaEventDisableTiming));
     }
@@ -571,9 +581,9 @@ int run_schedule(smslu_handle_t h, const std::vector<Launch>& sched, const doubl
     int rc;
     for (size_t i = 0; i < sched.size();) {
         size_t j = i;
-        bool used[NLANES] = {false, false, false};
+        bool used[NLANES] = {false, false, false, false};
         while (j < sched.size() && sched[j].level == sched[i].level) { used[sched[j].lane] = true; ++j; }
-        const int nused = (int)used[0] + (int)used[1] + (int)used[2];
+        const int nused = (int)used[0] + (int)used[1] + (int)used[2] + (int)used[3];
         const bool fork = nused > 1 && !h->profile && h->aux_stream[0];
         auto lane_stream = [&](int lane) { return (fork && lane > 0) ? h->aux_stream[lane - 1] : h->stream; };
         if (fork) {
@@ -1090,7 +1100,7 @@ int smslu_destroy(smslu_handle_t h) {
         for (cudaEvent_t e : h->pev) cudaEventDestroy(e);
         if (h->h_flag) cudaFreeHost(h->h_flag);
         if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < NLANES - 1; ++a) {
             if (h->aux_stream[a]) { cudaStreamSynchronize(h->aux_stream[a]); cudaStreamDestroy(h->aux_stream[a]); }
             if (h->ev_join[a]) cudaEventDestroy(h->ev_join[a]);
         }
