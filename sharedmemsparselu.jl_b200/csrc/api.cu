@@ -194,7 +194,8 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
         // small fronts: factor classes up to 40 rows on lane 1, the wider ones on lane 2; solves on lane 1;
         // big fronts of the factorization: lane 0 (wide pivot blocks) or lane 3 (at most 64 pivot columns)
         const int lane = kind == L_SMALL ? (fmax <= 40 ? 1 : 2) : ((kind == L_FWD_SMALL || kind == L_BWD_SMALL) ? 1 :
-                         ((kind == L_ZERO || kind == L_EXTEND || kind == L_PANEL || kind == L_GEMM) ? big_lane : 0));
+                         ((kind == L_ZERO || kind == L_EXTEND || kind == L_PANEL || kind == L_GEMM) ? big_lane :
+                          ((kind == L_FWD || kind == L_BWD) && fmax <= NB ? 3 : 0)));     // solves: narrow big fronts on lane 3
         if (nt > 0) v.push_back(Launch{kind, off, nt, fmax, cur_level, lane});
     };
     for (int ph = 0; ph < 2; ++ph) {
