@@ -92,6 +92,8 @@ struct smslu_handle_s {
     cudaStream_t stream = nullptr;
     cudaStream_t aux_stream[NLANES - 1] = {nullptr, nullptr, nullptr};   // lanes 1..3 of a level
     cudaEvent_t ev_fork = nullptr, ev_join[NLANES - 1] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_scatter = nullptr;        // big fronts' panels zero-filled and scattered into
+    bool scatter_pending = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     std::vector<void*> dev_allocs;
     DevCtx cx{};
@@ -391,6 +393,7 @@ int ensure_uploaded(smslu_handle_t h) {
         CU(cudaEventCreateWithFlags(&h->ev_join[a], cudaEventDisableTiming));
     }
     CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_scatter, cudaEventDisableTiming));
     CU(cudaMallocHost((void**)&h->h_flag, sizeof(int)));
     CU(cudaEventCreate(&h->ev0)); CU(cudaEventCreate(&h->ev1));
     CU(cudaEventCreate(&h->ev2)); CU(cudaEventCreate(&h->ev3));
@@ -585,6 +588,10 @@ int run_schedule(smslu_handle_t h, const std::vector<Launch>& sched, const doubl
         bool used[NLANES] = {false, false, false, false};
         while (j < sched.size() && sched[j].level == sched[i].level) { used[sched[j].lane] = true; ++j; }
         const int nused = (int)used[0] + (int)used[1] + (int)used[2] + (int)used[3];
+        if (h->scatter_pending && (used[0] || used[NLANES - 1])) {      // first level with a big front: its panels must be ready
+            CU(cudaStreamWaitEvent(h->stream, h->ev_scatter, 0));
+            h->scatter_pending = false;
+        }
         const bool fork = nused > 1 && !h->profile && h->aux_stream[0];
         auto lane_stream = [&](int lane) { return (fork && lane > 0) ? h->aux_stream[lane - 1] : h->stream; };
         if (fork) {
@@ -622,15 +629,25 @@ int enqueue_refactor(smslu_handle_t h, const double* av, bool rs_given) {
     if ((rc = prof_begin(h, SMSLU_K_SCATTER))) return rc;
     CU(cudaMemsetAsync(h->cx.flag, 0x7f, sizeof(int), h->stream));   // 0x7f7f7f7f = clean
     CU(cudaMemsetAsync(h->cx.counters, 0, sizeof(int) * std::max<int64_t>(h->ncounters, 1), h->stream));
-    if (S.lu_top_size > 0) CU(cudaMemsetAsync(h->cx.lu, 0, sizeof(double) * S.lu_top_size, h->stream));
+    // The zero-fill and scatter of the big fronts' panels only matter from the first level that has a big front:
+    // they run on the big-front lane's stream while the main stream starts on the small-front levels.
+    cudaStream_t zs = h->stream;
+    if (!h->profile && h->aux_stream[NLANES - 2]) {
+        zs = h->aux_stream[NLANES - 2];
+        CU(cudaEventRecord(h->ev_fork, h->stream));
+        CU(cudaStreamWaitEvent(zs, h->ev_fork, 0));
+    }
+    if (S.lu_top_size > 0) CU(cudaMemsetAsync(h->cx.lu, 0, sizeof(double) * S.lu_top_size, zs));
     if (S.lu_big_end[h->rank] > S.lu_big_begin[h->rank])
         CU(cudaMemsetAsync(h->cx.lu + S.lu_big_begin[h->rank], 0,
-                           sizeof(double) * (S.lu_big_end[h->rank] - S.lu_big_begin[h->rank]), h->stream));
-    if (S.cb_iface_size > 0) CU(cudaMemsetAsync(h->cx.cb, 0, sizeof(double) * S.cb_iface_size, h->stream));
-    launch_scatter(h->stream, h->nnz_big, h->d_big_dst, h->d_big_row, h->d_big_src, h->d_Rs, av, h->cx.lu);
+                           sizeof(double) * (S.lu_big_end[h->rank] - S.lu_big_begin[h->rank]), zs));
+    if (S.cb_iface_size > 0) CU(cudaMemsetAsync(h->cx.cb, 0, sizeof(double) * S.cb_iface_size, zs));
+    launch_scatter(zs, h->nnz_big, h->d_big_dst, h->d_big_row, h->d_big_src, h->d_Rs, av, h->cx.lu);
+    if (zs != h->stream) { CU(cudaEventRecord(h->ev_scatter, zs)); h->scatter_pending = true; }
     h->cur_av = av;
     if ((rc = prof_end(h))) return rc;
     if ((rc = run_schedule(h, h->fac, nullptr, nullptr))) return rc;
+    if (h->scatter_pending) { CU(cudaStreamWaitEvent(h->stream, h->ev_scatter, 0)); h->scatter_pending = false; }
     if (h->nranks > 1) {
         // sum the subtrees' contributions to the top of the tree over NVLink, then factor the top
         if ((rc = prof_begin(h, SMSLU_K_ALLREDUCE))) return rc;
@@ -1106,6 +1123,7 @@ int smslu_destroy(smslu_handle_t h) {
             if (h->ev_join[a]) cudaEventDestroy(h->ev_join[a]);
         }
         if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+        if (h->ev_scatter) cudaEventDestroy(h->ev_scatter);
     }
     delete h;
     return 0;
