@@ -8,6 +8,7 @@
 #include <chrono>
 #include <climits>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -227,7 +228,13 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
             }
             // Big fronts in two independent groups, each on its own lane: pivot blocks of at most 64 columns (one or
             // two panel steps, then their Schur update) do not wait for the 3- and 4-step fronts of the level.
-            auto NARROW = [&](int s) { return K(s) <= 2 * NB; };
+            // (Only where the level's big fronts do not fill the machine anyway: with thousands of Schur-update tiles the
+            // two groups would just compete, and the split costs extra launches.)
+            int64_t level_tiles = 0;
+            for (int t = 0; t < cnt; ++t)
+                if (IN(sn[t]) && !SMALL(sn[t])) { const int64_t nt = (R(sn[t]) + GEMM_TILE - 1) / GEMM_TILE; level_tiles += nt * nt; }
+            const bool split = level_tiles <= 4096;
+            auto NARROW = [&](int s) { return split && K(s) <= 2 * NB; };
             for (int grp = 0; grp < 2; ++grp) {
                 big_lane = grp == 1 ? 3 : 0;
                 // Zero the contribution blocks that receive '+=' contributions.  Extend-add children add
@@ -388,8 +395,9 @@ int ensure_uploaded(smslu_handle_t h) {
     CU(kernels_init());
     if (h->have_user_stream) { h->stream = h->user_stream; h->own_stream = false; }
     else CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    const bool lanes = !(getenv("SMSLU_NO_LANES") && atoi(getenv("SMSLU_NO_LANES")) != 0);   // debugging aid: one stream only
     for (int a = 0; a < NLANES - 1; ++a) {
-        CU(cudaStreamCreateWithFlags(&h->aux_stream[a], cudaStreamNonBlocking));
+        if (lanes) CU(cudaStreamCreateWithFlags(&h->aux_stream[a], cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&h->ev_join[a], cudaEventDisableTiming));
     }
     CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));

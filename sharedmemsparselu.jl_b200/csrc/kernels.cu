@@ -2,6 +2,7 @@
 #include "kernels.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace smslu {
 
@@ -1188,7 +1189,7 @@ static size_t panel_smem(int j0, int rows) {
     return sizeof(double) * ((2 * (size_t)j0 + rows) * CLD + (rows == PANEL_ROWS_TOP ? (size_t)rows * (KW + 4) : 0));
 }
 
-// launch with programmatic stream serialization (see pdl_trigger / pdl_wait)
+// launch with programmatic stream serialization (see pdl_trigger / pdl_wait) when the grid is small
 template <class... KArgs, class... Args>
 static void launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg = {};
@@ -1196,7 +1197,10 @@ static void launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem,
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    static const bool pdl = !(getenv("SMSLU_NO_PDL") && atoi(getenv("SMSLU_NO_PDL")) != 0);   // debugging aid
+    // only where latency matters: early-launched CTAs of a big dependent grid sit on SM resources while the
+    // predecessor's tail is still running (measured: +13 % on a 3D 96^3 refactorization)
+    cfg.attrs = attr; cfg.numAttrs = (pdl && grid <= 4 * 148) ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
