@@ -43,6 +43,21 @@ CASES = {
 }
 
 
+def unsym_random(W, n, per_row, seed):
+    """Structurally unsymmetric random pattern (the symbolic analysis works on A+A'), strictly diagonally dominant."""
+    u = W.splitmix64(seed, 2 * n * per_row)
+    rows = np.repeat(np.arange(n), per_row)
+    cols = np.minimum((u[:n * per_row] * n).astype(np.int64), n - 1)
+    vals = u[n * per_row:] - 0.5
+    A = sp.csr_matrix((vals, (rows, cols)), shape=(n, n))
+    A.sum_duplicates()
+    A = A - sp.diags(A.diagonal())
+    A = A + sp.diags(np.asarray(abs(A).sum(axis=1)).ravel() + 1.0)
+    A = sp.csc_matrix(A); A.sort_indices()
+    A.indptr = A.indptr.astype(np.int64); A.indices = A.indices.astype(np.int64)
+    return A
+
+
 @pytest.mark.parametrize("name", list(CASES))
 def test_factor_and_solve_match_oracle(smslu, O, W, name):
     A, kw = CASES[name](W)
@@ -83,6 +98,30 @@ def test_factor_and_solve_match_oracle(smslu, O, W, name):
     smslu.ldiv_(x, F, b2)
     assert isapprox(x, ref.solve(b2), TOL if n < 5000 else 1e-11)
     smslu.cleanup_ParallelSparseLU_(F)
+
+
+@pytest.mark.parametrize("n,per_row,kw", [(400, 6, {}), (1500, 9, dict(max_width=64)), (3000, 4, dict(relax=False))])
+def test_structurally_unsymmetric_pattern(smslu, O, W, n, per_row, kw):
+    """The symbolic analysis works on pattern(A + A'), so for a structurally unsymmetric A the stored factors are a
+    superset of the oracle's exact (Gilbert-Peierls) structure, padded with explicit zeros: same values where the oracle
+    has entries, zero elsewhere, same contract L*U == (Rs .* A)[p,q] (src:307), same solves."""
+    A = unsym_random(W, n, per_row, seed=7 + n)
+    assert abs(abs(A) > 0).astype(np.int8).T.tocsc().nnz == A.nnz and ((abs(A) > 0) != (abs(A.T) > 0)).nnz > 0
+    F = smslu.ParallelSparseLU(A, **kw)
+    ref = O.OracleLU(A, p=F.p, q=F.q, Rs=F.Rs)
+    L, U = F.L, F.U
+    B = (sp.diags(F.Rs) @ A).tocsr()[F.p][:, F.q]
+    assert abs(L @ U - B).max() < 1e-13 * max(1.0, abs(B).max())
+    assert abs(L - ref.L).max() < 1e-12 and abs(U - ref.U).max() < 1e-12 * abs(ref.U).max()
+    assert L.nnz >= ref.L.nnz and U.nnz >= ref.U.nnz
+    b = W.rhs(n, 3)
+    x = np.empty(n); smslu.ldiv_(x, F, b)
+    assert isapprox(x, ref.solve(b), TOL)
+    y = b.copy(); smslu.lsolve_(F, y)
+    assert isapprox(y, ref.lsolve(b), TOL)
+    y = b.copy(); smslu.rsolve_(F, y)
+    assert isapprox(y, ref.usolve(b), DENSE_TOL)
+    F.close()
 
 
 @pytest.mark.parametrize("name", ["lap2d_37x23", "lap3d_12", "fe_50_shifted", "lap2d_200"])
