@@ -46,6 +46,11 @@ __device__ __forceinline__ Front load_front(const DevCtx& cx, int s) {
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Warp index as a provably warp-uniform value (a shuffle from lane 0): branches on it are uniform branches, so the
+// compiler does not wrap every shuffle inside a warp-role branch into WARPSYNC.COLLECTIVE / ENDCOLLECTIVE + moves
+// (that wrapping tripled the instruction count of the 32 x 32 register LU).
+__device__ __forceinline__ int uniform_warp_id() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 __device__ __forceinline__ bool bad_pivot(double p) { return !(fabs(p) > 0.0) || !isfinite(p); }
 
 constexpr int SMALL_F_MAX = 96;   // largest front handled by the shared-memory kernels (with k <= NB)
@@ -416,7 +421,7 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
     pdl_wait();
     const int g = tk.y & 15, kind = (tk.y >> 4) & 15, total = tk.y >> 8;
     const int k = F.k, j0 = g * NB, w = (k - j0 < NB) ? k - j0 : NB, j1 = j0 + w;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, fr = lane >> 2, fc = lane & 3;
+    const int tid = threadIdx.x, lane = tid & 31, warp = uniform_warp_id(), fr = lane >> 2, fc = lane & 3;
     TRACE(1);
     double* Uc = dsm;                               // Uc[m * CLD + c] = U[m, j0 + c],  m < j0
     double* Lc = dsm + j0 * CLD;                    // Lc[m * CLD + i] = L[j0 + i, m],  m < j0
@@ -774,7 +779,7 @@ __device__ __forceinline__ void diag_load_upper(double (&buf)[NB], const Front& 
 // Threads t >= KW only take part in the barriers.
 template <int RB>
 __device__ __forceinline__ void diag_solve_lower(const Front& F, double (&y)[RB], double* ys, int tid) {
-    const int lane = tid & 31, warp = tid >> 5, nblk = (F.k + NB - 1) / NB;
+    const int lane = tid & 31, warp = uniform_warp_id(), nblk = (F.k + NB - 1) / NB;
     double cur[NB], nxt[NB];
     if (tid < KW) diag_load_lower(cur, F, tid, 0, lane, warp);
     for (int g = 0; g < nblk; ++g) {
@@ -802,7 +807,7 @@ __device__ __forceinline__ void diag_solve_lower(const Front& F, double (&y)[RB]
 // x <- U11^{-1} v (upper, d = 1 / u_tt).  xs: shared, KW * RB doubles; the solution is left there.
 template <int RB>
 __device__ __forceinline__ void diag_solve_upper(const Front& F, double (&v)[RB], double d, double* xs, int tid) {
-    const int lane = tid & 31, warp = tid >> 5, nblk = (F.k + NB - 1) / NB;
+    const int lane = tid & 31, warp = uniform_warp_id(), nblk = (F.k + NB - 1) / NB;
     double cur[NB], nxt[NB];
     if (tid < KW) diag_load_upper(cur, F, tid, nblk - 1, lane, warp);
     for (int g = nblk - 1; g >= 0; --g) {
@@ -945,7 +950,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_bwd(DevCtx cx, const int4* __
     const int s = tk.x, ntiles = tk.z;
     const Front F = load_front(cx, s);
     pdl_wait();
-    const int k = F.k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k = F.k, tid = threadIdx.x, lane = tid & 31, warp = uniform_warp_id();
     const int64_t lo = (int64_t)tk.y * BWD_ROWS;
     const int cnt = (int)(F.r - lo < BWD_ROWS ? F.r - lo : BWD_ROWS);
     const int* __restrict__ rows = cx.rows + cx.rows_ptr[s] + lo;
@@ -1063,7 +1068,7 @@ template <int FPC, int RB>
 __global__ void __launch_bounds__(32 * FPC) k_small_fwd(DevCtx cx, const int4* __restrict__ tasks, int ntasks,
                                                         const double* __restrict__ win, double* __restrict__ zout) {
     __shared__ double vs[FPC][SMALL_F_MAX * RB];
-    const int grp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = uniform_warp_id(), lane = threadIdx.x & 31;
     const int ti = blockIdx.x * FPC + grp;
     if (ti >= ntasks) return;
     pdl_trigger();
@@ -1121,7 +1126,7 @@ template <int FPC, int RB>
 __global__ void __launch_bounds__(32 * FPC) k_small_bwd(DevCtx cx, const int4* __restrict__ tasks, int ntasks,
                                                         double* __restrict__ x) {
     __shared__ double xs[FPC][SMALL_F_MAX * RB];
-    const int grp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = uniform_warp_id(), lane = threadIdx.x & 31;
     const int ti = blockIdx.x * FPC + grp;
     if (ti >= ntasks) return;
     pdl_trigger();
