@@ -463,72 +463,74 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
     }
     __syncthreads();
     TRACE(2);
-    // ---- U: left-looking update, pieces of 8 rows x 16 columns (2 DMMA tiles) round-robin over the warps
+    // ---- U: left-looking update on the FP64 tensor pipe, in pieces of 8 rows x 16 columns (2 DMMA tiles).
+    // The diagonal block goes first (one piece per warp); then warp 0 factors it (phase L) WHILE the other seven
+    // warps update the row block, which does not depend on the factorization.
     const double* cf = kind == 0 ? Uc : Lc;
-    constexpr int NPIECE = (ROWS / 8 + 4) * 2;      // pieces of 8 rows x 16 columns (2 DMMA tiles)
-    for (int pc = warp; pc < NPIECE; pc += PANEL_THREADS / 32) {
-        const int st = pc >> 1, ch = (pc & 1) * 16;
+    constexpr int NW = PANEL_THREADS / 32, ROW_PIECES = (ROWS / 8) * 2;
+    auto row_piece = [&](int st, int ch) {
         double acc[2][2];
-        if (st < ROWS / 8) {                        // a piece of the row block
-            if (STAGE_ROWS) {
-                const double* __restrict__ ar = As + (st * 8 + fr) * ALD;
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int c = ch + 8 * j + 2 * fc + e;
-                        acc[j][e] = c < w ? ar[j0 + c] : 0.0;
-                    }
-                for (int m0 = 0; m0 < j0; m0 += 4) {
-                    const double a = -ar[m0 + fc];
-                    const double* __restrict__ cm = cf + (m0 + fc) * CLD + ch + fr;
-                    dmma884(acc[0][0], acc[0][1], a, cm[0]);
-                    dmma884(acc[1][0], acc[1][1], a, cm[8]);
-                }
-            } else {
-            double* fb; bool fa;
-            row_ptr((int64_t)tk.z * ROWS + st * 8 + fr, fb, fa);
+        if (STAGE_ROWS) {
+            const double* __restrict__ ar = As + (st * 8 + fr) * ALD;
 #pragma unroll
             for (int j = 0; j < 2; ++j)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int c = ch + 8 * j + 2 * fc + e;
-                    acc[j][e] = (fa && c < w) ? fb[(int64_t)(j0 + c) * stride] : 0.0;
+                    acc[j][e] = c < w ? ar[j0 + c] : 0.0;
                 }
-            if (j0 > 0) {
-                double an = fa ? -fb[(int64_t)fc * stride] : 0.0;
-                double an2 = (fa && j0 > 4) ? -fb[(int64_t)(4 + fc) * stride] : 0.0;
-                for (int m0 = 0; m0 < j0; m0 += 4) {
-                    const double a = an;
-                    an = an2;
-                    if (m0 + 8 < j0) an2 = fa ? -fb[(int64_t)(m0 + 8 + fc) * stride] : 0.0;
-                    const double* __restrict__ cm = cf + (m0 + fc) * CLD + ch + fr;
-                    dmma884(acc[0][0], acc[0][1], a, cm[0]);
-                    dmma884(acc[1][0], acc[1][1], a, cm[8]);
-                }
-            }
-            }
-            double* xs = Xs + (st * 8 + fr) * CLD + ch + 2 * fc;
-#pragma unroll
-            for (int j = 0; j < 2; ++j) *reinterpret_cast<double2*>(xs + 8 * j) = make_double2(acc[j][0], acc[j][1]);
-        } else if (j0 > 0) {                        // a piece of the diagonal block: D -= L[g, 0:j0] U[0:j0, g]
-            const int i0 = (st - ROWS / 8) * 8;
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const double2 v = *reinterpret_cast<const double2*>(&D[i0 + fr][ch + 8 * j + 2 * fc]);
-                acc[j][0] = v.x; acc[j][1] = v.y;
-            }
             for (int m0 = 0; m0 < j0; m0 += 4) {
-                const double a = -Lc[(m0 + fc) * CLD + i0 + fr];
-                const double* __restrict__ cm = Uc + (m0 + fc) * CLD + ch + fr;
+                const double a = -ar[m0 + fc];
+                const double* __restrict__ cm = cf + (m0 + fc) * CLD + ch + fr;
                 dmma884(acc[0][0], acc[0][1], a, cm[0]);
                 dmma884(acc[1][0], acc[1][1], a, cm[8]);
             }
+        } else {
+        double* fb; bool fa;
+        row_ptr((int64_t)tk.z * ROWS + st * 8 + fr, fb, fa);
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
-                *reinterpret_cast<double2*>(&D[i0 + fr][ch + 8 * j + 2 * fc]) = make_double2(acc[j][0], acc[j][1]);
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = ch + 8 * j + 2 * fc + e;
+                acc[j][e] = (fa && c < w) ? fb[(int64_t)(j0 + c) * stride] : 0.0;
+            }
+        if (j0 > 0) {
+            double an = fa ? -fb[(int64_t)fc * stride] : 0.0;
+            double an2 = (fa && j0 > 4) ? -fb[(int64_t)(4 + fc) * stride] : 0.0;
+            for (int m0 = 0; m0 < j0; m0 += 4) {
+                const double a = an;
+                an = an2;
+                if (m0 + 8 < j0) an2 = fa ? -fb[(int64_t)(m0 + 8 + fc) * stride] : 0.0;
+                const double* __restrict__ cm = cf + (m0 + fc) * CLD + ch + fr;
+                dmma884(acc[0][0], acc[0][1], a, cm[0]);
+                dmma884(acc[1][0], acc[1][1], a, cm[8]);
+            }
         }
-    }
+        }
+        double* xs = Xs + (st * 8 + fr) * CLD + ch + 2 * fc;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) *reinterpret_cast<double2*>(xs + 8 * j) = make_double2(acc[j][0], acc[j][1]);
+    };
+    auto diag_piece = [&](int i0, int ch) {      // D -= L[g, 0:j0] U[0:j0, g]
+        double acc[2][2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const double2 v = *reinterpret_cast<const double2*>(&D[i0 + fr][ch + 8 * j + 2 * fc]);
+            acc[j][0] = v.x; acc[j][1] = v.y;
+        }
+        for (int m0 = 0; m0 < j0; m0 += 4) {
+            const double a = -Lc[(m0 + fc) * CLD + i0 + fr];
+            const double* __restrict__ cm = Uc + (m0 + fc) * CLD + ch + fr;
+            dmma884(acc[0][0], acc[0][1], a, cm[0]);
+            dmma884(acc[1][0], acc[1][1], a, cm[8]);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            *reinterpret_cast<double2*>(&D[i0 + fr][ch + 8 * j + 2 * fc]) = make_double2(acc[j][0], acc[j][1]);
+    };
+    if (j0 > 0) diag_piece((warp >> 1) * 8, (warp & 1) * 16);       // 8 pieces, 8 warps
+    static_assert(NW == 8, "one diagonal piece per warp");
     __syncthreads();
     TRACE(3);
     double x[NB];
@@ -564,6 +566,8 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
 #pragma unroll
             for (int p = 0; p < NB; ++p) W[p][lane] = x[p];
         }
+    } else {
+        for (int pc = warp - 1; pc < ROW_PIECES; pc += NW - 1) row_piece(pc >> 1, (pc & 1) * 16);
     }
     TRACE(4);
     __syncthreads();
