@@ -8,10 +8,12 @@ A = W.laplacian_2d(1024)
 n = A.shape[0]
 F = smslu.ParallelSparseLU(A)
 b = W.rhs(n, 47); x = np.empty(n)
-for rep in range(2):
-    smslu.rsolve_(F, b.copy())
+for rep in range(3):
+    smslu.ldiv_(x, F, b)
     t = np.zeros(32, np.int64)
     _capi.lib().smslu_debug_trace(t.ctypes.data)
     r = t[16:24]
-    print("k_bwd CTA0:", [int(r[i] - r[0]) for i in range(5)])
+    print("k_bwd (last 1-CTA launch) load|wait|gather|gemv|..|diag:", [int(r[i] - r[0]) for i in range(6)])
+    r = t[24:32]
+    print("k_fwd (last 1-CTA launch) load|wait|gather..|diag|gemv:", [int(r[i] - r[0]) for i in range(5)])
 F.close()

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsmslu.so")
+LIB_PATH = os.environ.get("SMSLU_LIB") or os.path.join(HERE, "libsmslu.so")   # SMSLU_LIB: A/B testing of builds
 
 OK, E_DIM, E_PIVOT, E_PATTERN, E_ARG, E_CUDA, E_OOM, E_INTERNAL, E_NCCL = 0, -1, -2, -3, -4, -5, -6, -7, -8
 ORD = {"auto": 0, "natural": 1, "given": 2, "nd_graph": 3, "nd_grid": 4}

@@ -106,6 +106,8 @@ struct smslu_handle_s {
     int *d_p = nullptr, *d_q = nullptr;
     double *d_Rs = nullptr, *d_aval = nullptr, *d_w = nullptr, *d_z = nullptr, *d_xb = nullptr;
     int4* d_tasks = nullptr;
+    int2* d_inv_tasks = nullptr;        // (front, 32-column block) pairs of k_diag_inverse
+    int n_inv_tasks = 0;
     std::vector<int> asm_meta;                       // (child, first column) pairs of the assembly tasks
     std::vector<Launch> fac, fwd, bwd;               // this rank's supernodes (everything when nranks == 1)
     std::vector<Launch> fac_top, fwd_top, bwd_top;   // top of the tree, replicated on every rank
@@ -523,6 +525,21 @@ int ensure_uploaded(smslu_handle_t h) {
     int* d_asm_meta;
     if ((rc = dev_upload(h, &d_asm_meta, h->asm_meta))) return rc;
     h->cx.asm_meta = d_asm_meta;
+    int* d_Doff; double* d_dblk;
+    {   // inverted diagonal blocks of the big fronts this rank factors (its own and the replicated top)
+        std::vector<int> Doff(S.nsn, 0);
+        std::vector<int2> inv_tasks;
+        for (int s2 = 0; s2 < S.nsn; ++s2) {
+            if (S.small[s2] || !(S.owner[s2] == h->rank || S.owner[s2] == -1)) continue;
+            Doff[s2] = (int)inv_tasks.size();
+            const int k2 = S.sn_start[s2 + 1] - S.sn_start[s2];
+            for (int g = 0; g * NB < k2; ++g) inv_tasks.push_back(make_int2(s2, g));
+        }
+        h->n_inv_tasks = (int)inv_tasks.size();
+        if ((rc = dev_upload(h, &d_Doff, Doff))) return rc;
+        if ((rc = dev_upload(h, &h->d_inv_tasks, inv_tasks))) return rc;
+        if ((rc = dev_alloc(h, &d_dblk, (size_t)std::max<size_t>(inv_tasks.size(), 1) * NB * NB))) return rc;
+    }
     double* d_bpart; int* d_counters2;
     if ((rc = dev_alloc(h, &d_counters, (size_t)h->ncounters))) return rc;
     if ((rc = dev_alloc(h, &d_bpart, (size_t)h->bpart_slots * KMAX * RB_MAX))) return rc;
@@ -534,6 +551,7 @@ int ensure_uploaded(smslu_handle_t h) {
     cx.child_ptr = d_child_ptr; cx.child_idx = d_child_idx;
     cx.lu = d_lu; cx.cb = d_cb; cx.upd = d_upd; cx.counters = d_counters; cx.flag = d_flag;
     cx.bpart = d_bpart; cx.counters2 = d_counters2; cx.dinv = d_dinv;
+    cx.Doff = d_Doff; cx.dblk = d_dblk;
     cx.a_ptr = d_a_ptr; cx.a_src = d_a_src; cx.a_row = d_a_row; cx.a_pos = d_a_pos;
     CU(cudaDeviceSynchronize());
     h->uploaded = true;
@@ -667,6 +685,10 @@ int enqueue_refactor(smslu_handle_t h, const double* av, bool rs_given) {
         if ((rc = run_schedule(h, h->fac_top, nullptr, nullptr))) return rc;
         NCCLCHK(nccl_api().AllReduce(h->cx.flag, h->cx.flag, 1, ncclInt, ncclMin, h->comm, h->stream));
     }
+    // the solves apply the 32 x 32 diagonal blocks of the big fronts through their inverses
+    if ((rc = prof_begin(h, SMSLU_K_PANEL))) return rc;
+    launch_diag_inverse(h->stream, h->cx, h->d_inv_tasks, h->n_inv_tasks);
+    if ((rc = prof_end(h))) return rc;
     CU(cudaMemcpyAsync(h->h_flag, h->cx.flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     h->pending_refactor = true;
     return 0;

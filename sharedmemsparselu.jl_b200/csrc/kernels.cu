@@ -45,6 +45,18 @@ __device__ __forceinline__ Front load_front(const DevCtx& cx, int s) {
 // successor's prologue overlaps the predecessor's tail.
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Pull a rows x cols column-major block (leading dimension ld) towards L2 ahead of its use: one prefetch per
+// 128 bytes of every column (the block's start need not be line-aligned, hence the clamped extra probe).
+// The factors are never written during a solve, so this is issued before griddepcontrol.wait.
+__device__ __forceinline__ void prefetch_block_l2(const double* base, int rows, int cols, int64_t ld, int tid, int nthreads) {
+    if (rows <= 0) return;
+    const int per = (rows + 15) / 16 + 1;
+    for (int e = tid; e < cols * per; e += nthreads) {
+        const int c = e / per, l = e - c * per;
+        const int off = l * 16 < rows ? l * 16 : rows - 1;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (int64_t)c * ld + off));
+    }
+}
 
 // Warp index as a provably warp-uniform value (a shuffle from lane 0): branches on it are uniform branches, so the
 // compiler does not wrap every shuffle inside a warp-role branch into WARPSYNC.COLLECTIVE / ENDCOLLECTIVE + moves
@@ -736,6 +748,55 @@ __global__ void __launch_bounds__(256) k_gemm_cb(DevCtx cx, const int4* __restri
         }
 }
 
+// ------------------------------------------------------------------ inverses of the diagonal blocks
+// After the factorization, one warp per 32 x 32 diagonal block D_gg = L_gg U_gg of a big front's pivot block:
+// dblk[block] (32 x 32, column-major) holds L_gg^{-1} below the diagonal (its unit diagonal is implicit) and
+// U_gg^{-1} on and above it.  The solve kernels then apply a diagonal block as ONE 32-term product per row
+// (independent shuffles) instead of a 32-step dependent substitution chain -- the chain was 3.3 k cycles per
+// block, four blocks per 128-column front, on the critical path of every solve launch.
+// Lane c computes column c of both inverses by column-oriented substitution; the coefficients are read as
+// shared-memory broadcasts, all updates of one step are independent.  A partial block is padded with the identity.
+// task: x = supernode, y = block g.
+constexpr int INV_WARPS = 4;
+__global__ void __launch_bounds__(32 * INV_WARPS) k_diag_inverse(DevCtx cx, const int2* __restrict__ tasks, int ntasks) {
+    __shared__ double Bs[INV_WARPS][NB][NB + 1];
+    __shared__ double rds[INV_WARPS][NB];
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const int ti = blockIdx.x * INV_WARPS + wl;
+    if (ti >= ntasks) return;
+    const int2 tk = tasks[ti];
+    const Front F = load_front(cx, tk.x);
+    const int j0 = tk.y * NB, w = (F.k - j0 < NB) ? F.k - j0 : NB;
+    double (*B)[NB + 1] = Bs[wl];
+    {
+        const double* __restrict__ src = F.P + (j0 + lane) + (int64_t)j0 * F.f;
+#pragma unroll 8
+        for (int c = 0; c < NB; ++c) B[lane][c] = (lane < w && c < w) ? src[(int64_t)c * F.f] : (lane == c ? 1.0 : 0.0);
+        rds[wl][lane] = lane < w ? cx.dinv[F.c0 + j0 + lane] : 1.0;
+    }
+    __syncwarp();
+    double x[NB], y[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) { x[i] = i == lane ? 1.0 : 0.0; y[i] = x[i]; }
+#pragma unroll
+    for (int j = 0; j < NB - 1; ++j)                 // L x = e_lane
+#pragma unroll
+        for (int i = j + 1; i < NB; ++i) x[i] -= B[i][j] * x[j];
+#pragma unroll
+    for (int j = NB - 1; j >= 0; --j) {              // U y = e_lane
+        y[j] *= rds[wl][j];
+#pragma unroll
+        for (int i = 0; i < j; ++i) y[i] -= B[i][j] * y[j];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < NB; ++i) B[i][lane] = i > lane ? x[i] : y[i];
+    __syncwarp();
+    double* __restrict__ dst = cx.dblk + ((int64_t)cx.Doff[tk.x] + tk.y) * (NB * NB);
+#pragma unroll 8
+    for (int c = 0; c < NB; ++c) dst[lane + NB * c] = B[lane][c];
+}
+
 // ------------------------------------------------------------------ solves
 // All solve kernels are templated on RB, the number of right-hand sides swept together (1, 4 or 8): the
 // work vectors are interleaved (entry i of right-hand side q at [i * RB + q]), so the factor entries are
@@ -767,34 +828,48 @@ __global__ void k_unpermute(int n, const int* __restrict__ qv, const double* __r
 // Warp g owns the rows of diagonal block g: it runs the 32-step substitution with shuffles only (the
 // coefficients that do not apply are loaded as zeros, so the loop has no predicates); the warps on the far
 // side of the block then apply the block's solution values, published in shared memory, to their rows.
-__device__ __forceinline__ void diag_load_lower(double (&buf)[NB], const Front& F, int t, int g, int lane, int warp) {
+__device__ __forceinline__ void diag_load_lower(double (&buf)[NB], const Front& F, const double* __restrict__ inv,
+                                                int t, int g, int lane, int warp) {
     const int j0 = g * NB;
+    if (warp == g) {                                   // the block's own rows: row `lane` of L_gg^{-1}
 #pragma unroll
-    for (int c = 0; c < NB; ++c)
-        buf[c] = (t < F.k && j0 + c < F.k && (warp > g || (warp == g && c < lane))) ? F.P[t + (int64_t)(j0 + c) * F.f] : 0.0;
+        for (int c = 0; c < NB; ++c) buf[c] = c < lane ? inv[g * (NB * NB) + lane + NB * c] : 0.0;
+    } else {
+#pragma unroll
+        for (int c = 0; c < NB; ++c)
+            buf[c] = (t < F.k && j0 + c < F.k && warp > g) ? F.P[t + (int64_t)(j0 + c) * F.f] : 0.0;
+    }
 }
-__device__ __forceinline__ void diag_load_upper(double (&buf)[NB], const Front& F, int t, int g, int lane, int warp) {
+__device__ __forceinline__ void diag_load_upper(double (&buf)[NB], const Front& F, const double* __restrict__ inv,
+                                                int t, int g, int lane, int warp) {
     const int j0 = g * NB;
+    if (warp == g) {                                   // row `lane` of U_gg^{-1}
 #pragma unroll
-    for (int c = 0; c < NB; ++c)
-        buf[c] = (t < F.k && j0 + c < F.k && (warp < g || (warp == g && c > lane))) ? F.P[t + (int64_t)(j0 + c) * F.f] : 0.0;
+        for (int c = 0; c < NB; ++c) buf[c] = c >= lane ? inv[g * (NB * NB) + lane + NB * c] : 0.0;
+    } else {
+#pragma unroll
+        for (int c = 0; c < NB; ++c)
+            buf[c] = (t < F.k && j0 + c < F.k && warp < g) ? F.P[t + (int64_t)(j0 + c) * F.f] : 0.0;
+    }
 }
 // y <- L11^{-1} y (unit lower).  ys: shared, KW * RB doubles; the solution is left there.
-// Threads t >= KW only take part in the barriers.
+// inv: the front's inverted diagonal blocks (k_diag_inverse).  Threads t >= KW only take part in the barriers.
 template <int RB>
-__device__ __forceinline__ void diag_solve_lower(const Front& F, double (&y)[RB], double* ys, int tid) {
+__device__ __forceinline__ void diag_solve_lower(const Front& F, const double* __restrict__ inv, double (&y)[RB], double* ys, int tid) {
     const int lane = tid & 31, warp = uniform_warp_id(), nblk = (F.k + NB - 1) / NB;
     double cur[NB], nxt[NB];
-    if (tid < KW) diag_load_lower(cur, F, tid, 0, lane, warp);
+    if (tid < KW) diag_load_lower(cur, F, inv, tid, 0, lane, warp);
     for (int g = 0; g < nblk; ++g) {
-        if (tid < KW && g + 1 < nblk) diag_load_lower(nxt, F, tid, g + 1, lane, warp);
+        if (tid < KW && g + 1 < nblk) diag_load_lower(nxt, F, inv, tid, g + 1, lane, warp);
         if (warp == g) {
 #pragma unroll
-            for (int j = 0; j < NB; ++j)
+            for (int q = 0; q < RB; ++q) {
+                double a[4] = {y[q], 0.0, 0.0, 0.0};             // y_i + sum_{j<i} (L^{-1})_ij y_j, fixed order
 #pragma unroll
-                for (int q = 0; q < RB; ++q) y[q] -= cur[j] * __shfl_sync(0xffffffffu, y[q], j);
-#pragma unroll
-            for (int q = 0; q < RB; ++q) ys[tid * RB + q] = y[q];
+                for (int j = 0; j < NB; ++j) a[j & 3] += cur[j] * __shfl_sync(0xffffffffu, y[q], j);
+                y[q] = (a[0] + a[1]) + (a[2] + a[3]);
+                ys[tid * RB + q] = y[q];
+            }
         }
         __syncthreads();
         if (tid < KW && warp > g) {
@@ -808,24 +883,23 @@ __device__ __forceinline__ void diag_solve_lower(const Front& F, double (&y)[RB]
         for (int c = 0; c < NB; ++c) cur[c] = nxt[c];
     }
 }
-// x <- U11^{-1} v (upper, d = 1 / u_tt).  xs: shared, KW * RB doubles; the solution is left there.
+// x <- U11^{-1} v (upper).  xs: shared, KW * RB doubles; the solution is left there.
 template <int RB>
-__device__ __forceinline__ void diag_solve_upper(const Front& F, double (&v)[RB], double d, double* xs, int tid) {
+__device__ __forceinline__ void diag_solve_upper(const Front& F, const double* __restrict__ inv, double (&v)[RB], double* xs, int tid) {
     const int lane = tid & 31, warp = uniform_warp_id(), nblk = (F.k + NB - 1) / NB;
     double cur[NB], nxt[NB];
-    if (tid < KW) diag_load_upper(cur, F, tid, nblk - 1, lane, warp);
+    if (tid < KW) diag_load_upper(cur, F, inv, tid, nblk - 1, lane, warp);
     for (int g = nblk - 1; g >= 0; --g) {
-        if (tid < KW && g > 0) diag_load_upper(nxt, F, tid, g - 1, lane, warp);
+        if (tid < KW && g > 0) diag_load_upper(nxt, F, inv, tid, g - 1, lane, warp);
         if (warp == g) {
 #pragma unroll
-            for (int j = NB - 1; j >= 0; --j)
+            for (int q = 0; q < RB; ++q) {
+                double a[4] = {0.0, 0.0, 0.0, 0.0};              // sum_{j>=i} (U^{-1})_ij v_j, fixed order
 #pragma unroll
-                for (int q = 0; q < RB; ++q) {
-                    const double xj = __shfl_sync(0xffffffffu, v[q] * d, j);
-                    v[q] = lane == j ? xj : v[q] - cur[j] * xj;
-                }
-#pragma unroll
-            for (int q = 0; q < RB; ++q) xs[tid * RB + q] = v[q];
+                for (int j = 0; j < NB; ++j) a[j & 3] += cur[j] * __shfl_sync(0xffffffffu, v[q], j);
+                v[q] = (a[0] + a[1]) + (a[2] + a[3]);
+                xs[tid * RB + q] = v[q];
+            }
         }
         __syncthreads();
         if (tid < KW && warp < g) {
@@ -856,9 +930,15 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_fwd(DevCtx cx, const int4* __
     int4 tk = tasks[blockIdx.x];
     const int s = tk.x;
     const Front F = load_front(cx, s);
-    pdl_wait();
     const int k = F.k, tid = threadIdx.x, kp = ((k + NB - 1) / NB) * NB;
     const int64_t lo = (int64_t)tk.y * FWD_ROWS;            // first update row of this tile
+    const double* __restrict__ inv = cx.dblk + (int64_t)cx.Doff[s] * (NB * NB);
+    prefetch_block_l2(inv, NB, kp, NB, tid, SOLVE_THREADS);
+    prefetch_block_l2(F.P, k, k, F.f, tid, SOLVE_THREADS);
+    prefetch_block_l2(F.P + k + lo, (int)(F.r - lo < FWD_ROWS ? F.r - lo : FWD_ROWS), k, F.f, tid, SOLVE_THREADS);
+    TRACE2(8);
+    pdl_wait();
+    TRACE2(9);
     for (int e = tid; e < KW * RB; e += SOLVE_THREADS) ys[e] = e < k * RB ? win[(int64_t)F.c0 * RB + e] : 0.0;
     for (int e = tid; e < FWD_ROWS * RB; e += SOLVE_THREADS) acc[e] = 0.0;
     __syncthreads();
@@ -896,8 +976,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_fwd(DevCtx cx, const int4* __
 #pragma unroll
         for (int q = 0; q < RB; ++q) y[q] = tid < k ? ys[tid * RB + q] : 0.0;
         __syncthreads();                                     // everybody has read its entries of ys
-        diag_solve_lower<RB>(F, y, ys, tid);
+        TRACE2(10);
+        diag_solve_lower<RB>(F, inv, y, ys, tid);
         __syncthreads();
+        TRACE2(11);
     }
     if (tk.y == 0) for (int e = tid; e < k * RB; e += SOLVE_THREADS) zout[(int64_t)F.c0 * RB + e] = ys[e];
     {   // rows of L21: thread (row, quarter) sums kp/4 columns
@@ -910,6 +992,16 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_fwd(DevCtx cx, const int4* __
             const double* __restrict__ src = F.P + F.k + row + (int64_t)(qt * kq) * F.f;
             const int jn = (k - qt * kq < kq) ? k - qt * kq : kq;     // may be <= 0 for the last quarters
             int j = 0;
+            if (jn == NB) {                                  // k = 128: the thread's 32 entries in flight at once
+                double l[NB];
+#pragma unroll
+                for (int u = 0; u < NB; ++u) l[u] = src[(int64_t)u * F.f];
+#pragma unroll
+                for (int u = 0; u < NB; ++u)
+#pragma unroll
+                    for (int q = 0; q < RB; ++q) v[q] += l[u] * ys[(qt * kq + u) * RB + q];
+                j = NB;
+            }
             for (; j + 8 <= jn; j += 8) {
                 double l[8];
 #pragma unroll
@@ -935,6 +1027,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_fwd(DevCtx cx, const int4* __
                 cx.upd[(cx.rows_ptr[s] + row) * RB + q] = acc[e] - (((red[0][e] + red[1][e]) + red[2][e]) + red[3][e]);
             }
         }
+        TRACE2(12);
     }
 }
 
@@ -953,10 +1046,16 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_bwd(DevCtx cx, const int4* __
     int4 tk = tasks[blockIdx.x];
     const int s = tk.x, ntiles = tk.z;
     const Front F = load_front(cx, s);
-    pdl_wait();
     const int k = F.k, tid = threadIdx.x, lane = tid & 31, warp = uniform_warp_id();
     const int64_t lo = (int64_t)tk.y * BWD_ROWS;
     const int cnt = (int)(F.r - lo < BWD_ROWS ? F.r - lo : BWD_ROWS);
+    const double* __restrict__ inv = cx.dblk + (int64_t)cx.Doff[s] * (NB * NB);
+    prefetch_block_l2(F.T + lo, cnt, k, F.r, tid, SOLVE_THREADS);
+    prefetch_block_l2(inv, NB, ((k + NB - 1) / NB) * NB, NB, tid, SOLVE_THREADS);
+    prefetch_block_l2(F.P, k, k, F.f, tid, SOLVE_THREADS);
+    TRACE2(0);
+    pdl_wait();
+    TRACE2(1);
     const int* __restrict__ rows = cx.rows + cx.rows_ptr[s] + lo;
     {
         const int64_t xr = tid < cnt ? (int64_t)rows[tid] * RB : 0;     // BWD_ROWS == SOLVE_THREADS
@@ -964,6 +1063,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_bwd(DevCtx cx, const int4* __
         for (int q = 0; q < RB; ++q) xs[tid * RB + q] = tid < cnt ? x[xr + q] : 0.0;
     }
     __syncthreads();
+    TRACE2(2);
     for (int i0 = warp * 4; i0 < k; i0 += (SOLVE_THREADS / 32) * 4) {
         double v[4][RB];
 #pragma unroll
@@ -995,6 +1095,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_bwd(DevCtx cx, const int4* __
             }
     }
     __syncthreads();
+    TRACE2(3);
     if (ntiles > 1) {
         double* slot = cx.bpart + (int64_t)tk.w * KW * RB;
         for (int e = tid; e < k * RB; e += SOLVE_THREADS) slot[(int64_t)tk.y * KW * RB + e] = part[e];
@@ -1019,10 +1120,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_bwd(DevCtx cx, const int4* __
         const int64_t xc = (int64_t)(F.c0 + tid) * RB;
 #pragma unroll
         for (int q = 0; q < RB; ++q) v0[q] = tid < k ? x[xc + q] - part[tid * RB + q] : 0.0;     // right-hand side of U11 x = ...
-        const double d = tid < k ? cx.dinv[F.c0 + tid] : 0.0;
         __syncthreads();                                     // everybody has read its entries of part
-        diag_solve_upper<RB>(F, v0, d, part, tid);           // the solution is published in part
+        TRACE2(4);
+        diag_solve_upper<RB>(F, inv, v0, part, tid);         // the solution is published in part
         __syncthreads();
+        TRACE2(5);
     }
     for (int e = tid; e < k * RB; e += SOLVE_THREADS) x[(int64_t)F.c0 * RB + e] = part[e];
 }
@@ -1226,6 +1328,9 @@ cudaError_t kernels_init() {
     return cudaSuccess;
 }
 
+void launch_diag_inverse(cudaStream_t st, const DevCtx& cx, const int2* tasks, int ntasks) {
+    if (ntasks > 0) k_diag_inverse<<<(ntasks + INV_WARPS - 1) / INV_WARPS, 32 * INV_WARPS, 0, st>>>(cx, tasks, ntasks);
+}
 void launch_rowscale(cudaStream_t st, int n, const int64_t* rowptr, const int64_t* rowidx, const double* av, double* Rs) {
     k_rowscale<<<(n + 255) / 256, 256, 0, st>>>(n, rowptr, rowidx, av, Rs);
 }

@@ -48,6 +48,8 @@ struct DevCtx {
     int* counters2;     // one per supernode, used by the backward-solve kernel
     int* flag;          // first bad pivot column (atomicMin), INT_MAX when clean
     double* dinv;       // 1 / u_jj by permuted column, written by the factor kernels
+    const int* Doff;    // big fronts: index of the front's first 32x32 block in dblk
+    double* dblk;       // inverses of the 32x32 diagonal blocks of the big fronts' pivot blocks (k_diag_inverse)
     // entries of A grouped by the small front that pulls them (k_small_factor)
     const int* a_ptr;   // nsn+1 (empty range for big fronts)
     const int* a_src;   // index into the caller's nzval
@@ -62,6 +64,7 @@ void launch_rowscale(cudaStream_t st, int n, const int64_t* rowptr, const int64_
 void launch_scatter(cudaStream_t st, int64_t nnz, const int64_t* dst, const int* arow, const int* asrc,
                     const double* Rs, const double* av, double* lu);
 void launch_zero_cb(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks);
+void launch_diag_inverse(cudaStream_t st, const DevCtx& cx, const int2* tasks, int ntasks);
 void launch_assemble(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks);
 void launch_front_small(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int fmax,
                         const double* av, const double* Rs);
