@@ -62,6 +62,8 @@ enum LaunchKind { L_ZERO = SMSLU_K_ZERO, L_EXTEND = SMSLU_K_EXTEND, L_SMALL = SM
 
 constexpr int NLANES = 4;
 
+constexpr int FWD_WIDE_TILES = 148;   // 64-row forward tiles of a level beyond which 256-row tiles are used
+
 struct Launch {
     int kind;
     int64_t off;
@@ -200,7 +202,7 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
         // big fronts of the factorization: lane 0 (wide pivot blocks) or lane 3 (at most 64 pivot columns)
         const int lane = kind == L_SMALL ? (fmax <= 40 ? 1 : 2) : ((kind == L_FWD_SMALL || kind == L_BWD_SMALL) ? 1 :
                          ((kind == L_ZERO || kind == L_EXTEND || kind == L_PANEL || kind == L_GEMM) ? big_lane :
-                          ((kind == L_FWD || kind == L_BWD) && fmax <= NB ? 3 : 0)));     // solves: narrow big fronts on lane 3
+                          ((kind == L_FWD || kind == L_BWD) && (fmax & 255) <= NB ? 3 : 0)));     // solves: narrow big fronts on lane 3
         if (nt > 0) v.push_back(Launch{kind, off, nt, fmax, cur_level, lane});
     };
     for (int ph = 0; ph < 2; ++ph) {
@@ -342,16 +344,25 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
             for (int t = 0; t < cnt; ++t) if (IN(sn[t]) && SMALL(sn[t])) tasks.push_back(make_int4(sn[t], 0, 0, 0));
             push(fwd, L_FWD_SMALL, off, 0);
             for (int cls = 0; cls < 2; ++cls) {
+                // 64-row tiles where the level is a few fronts (latency); 256-row tiles where the 64-row tiles
+                // would not be resident at once anyway (every tile repeats the pivot-block solve)
+                int64_t tiles64 = 0;
+                for (int t = 0; t < cnt; ++t) {
+                    int s = sn[t];
+                    if (!IN(s) || SMALL(s) || (K(s) > NB) != (cls == 1)) continue;
+                    tiles64 += std::max<int64_t>(1, (R(s) + FWD_ROWS - 1) / FWD_ROWS);
+                }
+                const int rows = tiles64 > FWD_WIDE_TILES ? FWD_ROWS_WIDE : FWD_ROWS;
                 off = (int64_t)tasks.size();
                 int kmax = 0;
                 for (int t = 0; t < cnt; ++t) {
                     int s = sn[t];
                     if (!IN(s) || SMALL(s) || (K(s) > NB) != (cls == 1)) continue;
                     kmax = std::max(kmax, K(s));
-                    int nt = (int)std::max<int64_t>(1, (R(s) + FWD_ROWS - 1) / FWD_ROWS);
+                    int nt = (int)std::max<int64_t>(1, (R(s) + rows - 1) / rows);
                     for (int i = 0; i < nt; ++i) tasks.push_back(make_int4(s, i, 0, 0));
                 }
-                push(fwd, L_FWD, off, kmax);
+                push(fwd, L_FWD, off, kmax | (rows << 8));
             }
         }
         for (int l = S.nlevels - 1; l >= 0; --l) {
@@ -598,7 +609,7 @@ int launch_one(smslu_handle_t h, cudaStream_t st, const Launch& L, const double*
         case L_BWD_SMALL: launch_small_bwd(st, h->cx, tk, L.ntasks, zx, rb); break;
         case L_PANEL: launch_panel(st, h->cx, tk, L.ntasks, L.fmax & 255, L.fmax >> 8); break;
         case L_GEMM: launch_gemm_cb(st, h->cx, tk, L.ntasks); break;
-        case L_FWD: launch_fwd(st, h->cx, tk, L.ntasks, win, zx, rb); break;
+        case L_FWD: launch_fwd(st, h->cx, tk, L.ntasks, L.fmax >> 8, win, zx, rb); break;
         case L_BWD: launch_bwd(st, h->cx, tk, L.ntasks, zx, rb); break;
     }
     return 0;

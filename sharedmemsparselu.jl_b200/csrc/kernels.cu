@@ -874,10 +874,17 @@ __device__ __forceinline__ void diag_solve_lower(const Front& F, const double* _
         __syncthreads();
         if (tid < KW && warp > g) {
             const double* __restrict__ yb = ys + g * NB * RB;
+            if (RB == 1) {                                   // four short dependent chains instead of one
+                double a[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-            for (int c = 0; c < NB; ++c)
+                for (int c = 0; c < NB; ++c) a[c & 3] += cur[c] * yb[c * RB];
+                y[0] -= (a[0] + a[1]) + (a[2] + a[3]);
+            } else {                                         // RB independent chains already
 #pragma unroll
-                for (int q = 0; q < RB; ++q) y[q] -= cur[c] * yb[c * RB + q];
+                for (int c = 0; c < NB; ++c)
+#pragma unroll
+                    for (int q = 0; q < RB; ++q) y[q] -= cur[c] * yb[c * RB + q];
+            }
         }
 #pragma unroll
         for (int c = 0; c < NB; ++c) cur[c] = nxt[c];
@@ -904,10 +911,17 @@ __device__ __forceinline__ void diag_solve_upper(const Front& F, const double* _
         __syncthreads();
         if (tid < KW && warp < g) {
             const double* __restrict__ xb = xs + g * NB * RB;
+            if (RB == 1) {                                   // four short dependent chains instead of one
+                double a[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-            for (int c = 0; c < NB; ++c)
+                for (int c = 0; c < NB; ++c) a[c & 3] += cur[c] * xb[c * RB];
+                v[0] -= (a[0] + a[1]) + (a[2] + a[3]);
+            } else {                                         // RB independent chains already
 #pragma unroll
-                for (int q = 0; q < RB; ++q) v[q] -= cur[c] * xb[c * RB + q];
+                for (int c = 0; c < NB; ++c)
+#pragma unroll
+                    for (int q = 0; q < RB; ++q) v[q] -= cur[c] * xb[c * RB + q];
+            }
         }
 #pragma unroll
         for (int c = 0; c < NB; ++c) cur[c] = nxt[c];
@@ -920,27 +934,28 @@ __device__ __forceinline__ void diag_solve_upper(const Front& F, const double* _
 // so the summation order is fixed.  L11 is applied by diag_solve_lower (coefficients straight from
 // global memory into registers).  The tile's FWD_ROWS rows of L21 are reduced by 4 threads per row
 // (k/4 columns each, combined in a fixed order).
-template <int RB>
+template <int RB, int ROWS>
 __global__ void __launch_bounds__(SOLVE_THREADS) k_fwd(DevCtx cx, const int4* __restrict__ tasks,
                                                        const double* __restrict__ win, double* __restrict__ zout) {
     __shared__ double ys[KW * RB];
-    __shared__ double acc[FWD_ROWS * RB];
-    __shared__ double red[4][FWD_ROWS * RB];
+    constexpr int NQ = SOLVE_THREADS / ROWS;                 // threads per row in the L21 product (4 or 1)
+    __shared__ double acc[ROWS * RB];
+    __shared__ double red[NQ > 1 ? 4 : 1][NQ > 1 ? ROWS * RB : 1];
     pdl_trigger();
     int4 tk = tasks[blockIdx.x];
     const int s = tk.x;
     const Front F = load_front(cx, s);
     const int k = F.k, tid = threadIdx.x, kp = ((k + NB - 1) / NB) * NB;
-    const int64_t lo = (int64_t)tk.y * FWD_ROWS;            // first update row of this tile
+    const int64_t lo = (int64_t)tk.y * ROWS;            // first update row of this tile
     const double* __restrict__ inv = cx.dblk + (int64_t)cx.Doff[s] * (NB * NB);
     prefetch_block_l2(inv, NB, kp, NB, tid, SOLVE_THREADS);
     prefetch_block_l2(F.P, k, k, F.f, tid, SOLVE_THREADS);
-    prefetch_block_l2(F.P + k + lo, (int)(F.r - lo < FWD_ROWS ? F.r - lo : FWD_ROWS), k, F.f, tid, SOLVE_THREADS);
+    prefetch_block_l2(F.P + k + lo, (int)(F.r - lo < ROWS ? F.r - lo : ROWS), k, F.f, tid, SOLVE_THREADS);
     TRACE2(8);
     pdl_wait();
     TRACE2(9);
     for (int e = tid; e < KW * RB; e += SOLVE_THREADS) ys[e] = e < k * RB ? win[(int64_t)F.c0 * RB + e] : 0.0;
-    for (int e = tid; e < FWD_ROWS * RB; e += SOLVE_THREADS) acc[e] = 0.0;
+    for (int e = tid; e < ROWS * RB; e += SOLVE_THREADS) acc[e] = 0.0;
     __syncthreads();
     for (int ci = cx.child_ptr[s]; ci < cx.child_ptr[s + 1]; ++ci) {
         const int c = cx.child_idx[ci];
@@ -963,7 +978,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_fwd(DevCtx cx, const int4* __
                 if (ra[u] < k) {
 #pragma unroll
                     for (int q = 0; q < RB; ++q) ys[ra[u] * RB + q] += uv[u][q];
-                } else if (ra[u] - k >= lo && ra[u] - k < lo + FWD_ROWS) {
+                } else if (ra[u] - k >= lo && ra[u] - k < lo + ROWS) {
 #pragma unroll
                     for (int q = 0; q < RB; ++q) acc[(ra[u] - k - lo) * RB + q] += uv[u][q];
                 }
@@ -982,50 +997,64 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_fwd(DevCtx cx, const int4* __
         TRACE2(11);
     }
     if (tk.y == 0) for (int e = tid; e < k * RB; e += SOLVE_THREADS) zout[(int64_t)F.c0 * RB + e] = ys[e];
-    {   // rows of L21: thread (row, quarter) sums kp/4 columns
-        const int rloc = tid & (FWD_ROWS - 1), qt = tid / FWD_ROWS, kq = kp / 4;
+    {   // rows of L21: the kp columns are summed in four quarters, combined in a fixed order; with ROWS = 64 the
+        // quarters of a row belong to four threads, with ROWS = 256 one thread takes them one after the other
+        const int rloc = tid & (ROWS - 1), kq = kp / 4;
         const int64_t row = lo + rloc;
-        double v[RB];
+        double vq[4 / NQ][RB];
 #pragma unroll
-        for (int q = 0; q < RB; ++q) v[q] = 0.0;
-        if (row < F.r) {
-            const double* __restrict__ src = F.P + F.k + row + (int64_t)(qt * kq) * F.f;
-            const int jn = (k - qt * kq < kq) ? k - qt * kq : kq;     // may be <= 0 for the last quarters
-            int j = 0;
-            if (jn == NB) {                                  // k = 128: the thread's 32 entries in flight at once
-                double l[NB];
+        for (int h = 0; h < 4 / NQ; ++h) {
+            const int qt = NQ > 1 ? tid / ROWS : h;
+            double (&v)[RB] = vq[h];
 #pragma unroll
-                for (int u = 0; u < NB; ++u) l[u] = src[(int64_t)u * F.f];
+            for (int q = 0; q < RB; ++q) v[q] = 0.0;
+            if (row < F.r) {
+                const double* __restrict__ src = F.P + F.k + row + (int64_t)(qt * kq) * F.f;
+                const int jn = (k - qt * kq < kq) ? k - qt * kq : kq;     // may be <= 0 for the last quarters
+                int j = 0;
+                if (jn == NB) {                                  // k = 128: the thread's 32 entries in flight at once
+                    double l[NB];
 #pragma unroll
-                for (int u = 0; u < NB; ++u)
+                    for (int u = 0; u < NB; ++u) l[u] = src[(int64_t)u * F.f];
 #pragma unroll
-                    for (int q = 0; q < RB; ++q) v[q] += l[u] * ys[(qt * kq + u) * RB + q];
-                j = NB;
-            }
-            for (; j + 8 <= jn; j += 8) {
-                double l[8];
+                    for (int u = 0; u < NB; ++u)
 #pragma unroll
-                for (int u = 0; u < 8; ++u) l[u] = src[(int64_t)(j + u) * F.f];
+                        for (int q = 0; q < RB; ++q) v[q] += l[u] * ys[(qt * kq + u) * RB + q];
+                    j = NB;
+                }
+                for (; j + 8 <= jn; j += 8) {
+                    double l[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u)
+                    for (int u = 0; u < 8; ++u) l[u] = src[(int64_t)(j + u) * F.f];
 #pragma unroll
-                    for (int q = 0; q < RB; ++q) v[q] += l[u] * ys[(qt * kq + j + u) * RB + q];
-            }
-            for (; j < jn; ++j) {
-                const double l = src[(int64_t)j * F.f];
+                    for (int u = 0; u < 8; ++u)
 #pragma unroll
-                for (int q = 0; q < RB; ++q) v[q] += l * ys[(qt * kq + j) * RB + q];
+                        for (int q = 0; q < RB; ++q) v[q] += l[u] * ys[(qt * kq + j + u) * RB + q];
+                }
+                for (; j < jn; ++j) {
+                    const double l = src[(int64_t)j * F.f];
+#pragma unroll
+                    for (int q = 0; q < RB; ++q) v[q] += l * ys[(qt * kq + j) * RB + q];
+                }
             }
         }
+        if (NQ > 1) {
+            const int qt = tid / ROWS;
 #pragma unroll
-        for (int q = 0; q < RB; ++q) red[qt][rloc * RB + q] = v[q];
-        __syncthreads();
-        if (qt == 0 && row < F.r) {
+            for (int q = 0; q < RB; ++q) red[qt][rloc * RB + q] = vq[0][q];
+            __syncthreads();
+            if (qt == 0 && row < F.r) {
 #pragma unroll
-            for (int q = 0; q < RB; ++q) {
-                const int e = rloc * RB + q;
-                cx.upd[(cx.rows_ptr[s] + row) * RB + q] = acc[e] - (((red[0][e] + red[1][e]) + red[2][e]) + red[3][e]);
+                for (int q = 0; q < RB; ++q) {
+                    const int e = rloc * RB + q;
+                    cx.upd[(cx.rows_ptr[s] + row) * RB + q] = acc[e] - (((red[0][e] + red[1][e]) + red[2][e]) + red[3][e]);
+                }
             }
+        } else if (row < F.r) {
+#pragma unroll
+            for (int q = 0; q < RB; ++q)
+                cx.upd[(cx.rows_ptr[s] + row) * RB + q] =
+                    acc[rloc * RB + q] - (((vq[0][q] + vq[(4 / NQ) > 1 ? 1 : 0][q]) + vq[(4 / NQ) > 2 ? 2 : 0][q]) + vq[(4 / NQ) > 3 ? 3 : 0][q]);
         }
         TRACE2(12);
     }
@@ -1064,15 +1093,18 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_bwd(DevCtx cx, const int4* __
     }
     __syncthreads();
     TRACE2(2);
-    for (int i0 = warp * 4; i0 < k; i0 += (SOLVE_THREADS / 32) * 4) {
-        double v[4][RB];
+    // a warp takes BU columns at a time (8 for a single right-hand side: 64 loads per lane in flight; 4 when
+    // RB > 1, where the accumulators need the registers)
+    constexpr int BU = RB == 1 ? 8 : 4;
+    for (int i0 = warp * BU; i0 < k; i0 += (SOLVE_THREADS / 32) * BU) {
+        double v[BU][RB];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < BU; ++u)
 #pragma unroll
             for (int q = 0; q < RB; ++q) v[u][q] = 0.0;
-        double t[4][BWD_ROWS / 32];
+        double t[BU][BWD_ROWS / 32];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < BU; ++u) {
             const double* __restrict__ col = F.T + (int64_t)(i0 + u) * F.r + lo;
 #pragma unroll
             for (int a = 0; a < BWD_ROWS / 32; ++a) t[u][a] = (i0 + u < k && lane + 32 * a < cnt) ? col[lane + 32 * a] : 0.0;
@@ -1083,10 +1115,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_bwd(DevCtx cx, const int4* __
             for (int q = 0; q < RB; ++q) {
                 const double xv = xs[(lane + 32 * a) * RB + q];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) v[u][q] += t[u][a] * xv;
+                for (int u = 0; u < BU; ++u) v[u][q] += t[u][a] * xv;
             }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < BU; ++u)
 #pragma unroll
             for (int q = 0; q < RB; ++q) {
 #pragma unroll
@@ -1409,11 +1441,17 @@ void launch_unpermute(cudaStream_t st, int n, const int* q, const double* w, dou
     RB_DISPATCH(rb, CALL);
 #undef CALL
 }
-void launch_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const double* win, double* zout, int rb) {
+void launch_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int rows, const double* win, double* zout, int rb) {
     if (ntasks <= 0) return;
-#define CALL(R) launch_pdl(k_fwd<R>, ntasks, SOLVE_THREADS, 0, st, cx, tasks, win, zout)
-    RB_DISPATCH(rb, CALL);
+    if (rows == FWD_ROWS) {
+#define CALL(R) launch_pdl(k_fwd<R, FWD_ROWS>, ntasks, SOLVE_THREADS, 0, st, cx, tasks, win, zout)
+        RB_DISPATCH(rb, CALL);
 #undef CALL
+    } else {
+#define CALL(R) launch_pdl(k_fwd<R, FWD_ROWS_WIDE>, ntasks, SOLVE_THREADS, 0, st, cx, tasks, win, zout)
+        RB_DISPATCH(rb, CALL);
+#undef CALL
+    }
 }
 void launch_bwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, double* x, int rb) {
     if (ntasks <= 0) return;

@@ -23,7 +23,8 @@ constexpr int PANEL_ROWS = 128;   // rows of L21 / U12' handled by one panel CTA
 constexpr int PANEL_ROWS_TOP = 32; // ... near the top of the tree, where one CTA's latency is what matters
 constexpr int GEMM_TILE = 64;
 constexpr int SOLVE_THREADS = 256;
-constexpr int FWD_ROWS = 64;      // update rows per forward CTA (4 threads per row)
+constexpr int FWD_ROWS = 64;      // update rows per forward CTA (4 threads per row) ...
+constexpr int FWD_ROWS_WIDE = 256; // ... or one thread per row on levels with many tiles (every CTA repeats the pivot-block solve)
 constexpr int BWD_ROWS = 256;     // rows of U12' per backward CTA
 constexpr int ZERO_TILE = 8192;
 constexpr int RB_MAX = 8;         // most right-hand sides swept together by the solve kernels
@@ -82,7 +83,7 @@ int debug_read_trace(long long* out);   // 0 unless built with SMSLU_TRACE
 // ---- solves
 void launch_permute_scale(cudaStream_t st, int n, const int* p, const double* Rs, const double* b, int64_t ldb, double* w, int rb, int nv);
 void launch_unpermute(cudaStream_t st, int n, const int* q, const double* w, double* x, int64_t ldx, int rb, int nv);
-void launch_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const double* win, double* zout, int rb);
+void launch_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int rows, const double* win, double* zout, int rb);
 void launch_bwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, double* x, int rb);
 
 }  // namespace smslu
