@@ -854,13 +854,14 @@ __device__ __forceinline__ void diag_load_upper(double (&buf)[NB], const Front& 
 }
 // y <- L11^{-1} y (unit lower).  ys: shared, KW * RB doubles; the solution is left there.
 // inv: the front's inverted diagonal blocks (k_diag_inverse).  Threads t >= KW only take part in the barriers.
-template <int RB>
+template <int RB, bool AHEAD = true>
 __device__ __forceinline__ void diag_solve_lower(const Front& F, const double* __restrict__ inv, double (&y)[RB], double* ys, int tid) {
     const int lane = tid & 31, warp = uniform_warp_id(), nblk = (F.k + NB - 1) / NB;
     double cur[NB], nxt[NB];
-    if (tid < KW) diag_load_lower(cur, F, inv, tid, 0, lane, warp);
+    if (AHEAD && tid < KW) diag_load_lower(cur, F, inv, tid, 0, lane, warp);
     for (int g = 0; g < nblk; ++g) {
-        if (tid < KW && g + 1 < nblk) diag_load_lower(nxt, F, inv, tid, g + 1, lane, warp);
+        if constexpr (AHEAD) { if (tid < KW && g + 1 < nblk) diag_load_lower(nxt, F, inv, tid, g + 1, lane, warp); }
+        else if (tid < KW) diag_load_lower(cur, F, inv, tid, g, lane, warp);      // throughput variant: half the registers
         if (warp == g) {
 #pragma unroll
             for (int q = 0; q < RB; ++q) {
@@ -886,8 +887,10 @@ __device__ __forceinline__ void diag_solve_lower(const Front& F, const double* _
                     for (int q = 0; q < RB; ++q) y[q] -= cur[c] * yb[c * RB + q];
             }
         }
+        if constexpr (AHEAD) {
 #pragma unroll
-        for (int c = 0; c < NB; ++c) cur[c] = nxt[c];
+            for (int c = 0; c < NB; ++c) cur[c] = nxt[c];
+        }
     }
 }
 // x <- U11^{-1} v (upper).  xs: shared, KW * RB doubles; the solution is left there.
@@ -935,7 +938,7 @@ __device__ __forceinline__ void diag_solve_upper(const Front& F, const double* _
 // global memory into registers).  The tile's FWD_ROWS rows of L21 are reduced by 4 threads per row
 // (k/4 columns each, combined in a fixed order).
 template <int RB, int ROWS>
-__global__ void __launch_bounds__(SOLVE_THREADS) k_fwd(DevCtx cx, const int4* __restrict__ tasks,
+__global__ void __launch_bounds__(SOLVE_THREADS, (ROWS == FWD_ROWS_WIDE && RB == 1) ? 2 : 1) k_fwd(DevCtx cx, const int4* __restrict__ tasks,
                                                        const double* __restrict__ win, double* __restrict__ zout) {
     __shared__ double ys[KW * RB];
     constexpr int NQ = SOLVE_THREADS / ROWS;                 // threads per row in the L21 product (4 or 1)
@@ -992,7 +995,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_fwd(DevCtx cx, const int4* __
         for (int q = 0; q < RB; ++q) y[q] = tid < k ? ys[tid * RB + q] : 0.0;
         __syncthreads();                                     // everybody has read its entries of ys
         TRACE2(10);
-        diag_solve_lower<RB>(F, inv, y, ys, tid);
+        diag_solve_lower<RB, !(ROWS == FWD_ROWS_WIDE && RB == 1)>(F, inv, y, ys, tid);
         __syncthreads();
         TRACE2(11);
     }
