@@ -894,13 +894,14 @@ __device__ __forceinline__ void diag_solve_lower(const Front& F, const double* _
     }
 }
 // x <- U11^{-1} v (upper).  xs: shared, KW * RB doubles; the solution is left there.
-template <int RB>
+template <int RB, bool AHEAD = true>
 __device__ __forceinline__ void diag_solve_upper(const Front& F, const double* __restrict__ inv, double (&v)[RB], double* xs, int tid) {
     const int lane = tid & 31, warp = uniform_warp_id(), nblk = (F.k + NB - 1) / NB;
     double cur[NB], nxt[NB];
-    if (tid < KW) diag_load_upper(cur, F, inv, tid, nblk - 1, lane, warp);
+    if (AHEAD && tid < KW) diag_load_upper(cur, F, inv, tid, nblk - 1, lane, warp);
     for (int g = nblk - 1; g >= 0; --g) {
-        if (tid < KW && g > 0) diag_load_upper(nxt, F, inv, tid, g - 1, lane, warp);
+        if constexpr (AHEAD) { if (tid < KW && g > 0) diag_load_upper(nxt, F, inv, tid, g - 1, lane, warp); }
+        else if (tid < KW) diag_load_upper(cur, F, inv, tid, g, lane, warp);
         if (warp == g) {
 #pragma unroll
             for (int q = 0; q < RB; ++q) {
@@ -926,8 +927,10 @@ __device__ __forceinline__ void diag_solve_upper(const Front& F, const double* _
                     for (int q = 0; q < RB; ++q) v[q] -= cur[c] * xb[c * RB + q];
             }
         }
+        if constexpr (AHEAD) {
 #pragma unroll
-        for (int c = 0; c < NB; ++c) cur[c] = nxt[c];
+            for (int c = 0; c < NB; ++c) cur[c] = nxt[c];
+        }
     }
 }
 
@@ -1069,8 +1072,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (ROWS == FWD_ROWS_WIDE && RB ==
 // so 32 loads per lane are in flight); with several tiles the partial k-vectors go to scratch and
 // the CTA that arrives last adds them in tile order (fixed summation order, nobody waits) and
 // finishes the back substitution (diag_solve_upper: coefficients straight from global memory into registers).
-template <int RB>
-__global__ void __launch_bounds__(SOLVE_THREADS) k_bwd(DevCtx cx, const int4* __restrict__ tasks, double* __restrict__ x) {
+template <int RB, bool WIDE>
+__global__ void __launch_bounds__(SOLVE_THREADS, (WIDE && RB == 1) ? 2 : 1) k_bwd(DevCtx cx, const int4* __restrict__ tasks, double* __restrict__ x) {
     __shared__ double xs[BWD_ROWS * RB];
     __shared__ double part[KW * RB];
     __shared__ int s_last;
@@ -1097,8 +1100,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_bwd(DevCtx cx, const int4* __
     __syncthreads();
     TRACE2(2);
     // a warp takes BU columns at a time (8 for a single right-hand side: 64 loads per lane in flight; 4 when
-    // RB > 1, where the accumulators need the registers)
-    constexpr int BU = RB == 1 ? 8 : 4;
+    // RB > 1, where the accumulators need the registers, and in the two-CTAs-per-SM variant of the bulk levels)
+    constexpr int BU = (RB == 1 && !WIDE) ? 8 : 4;
     for (int i0 = warp * BU; i0 < k; i0 += (SOLVE_THREADS / 32) * BU) {
         double v[BU][RB];
 #pragma unroll
@@ -1157,7 +1160,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_bwd(DevCtx cx, const int4* __
         for (int q = 0; q < RB; ++q) v0[q] = tid < k ? x[xc + q] - part[tid * RB + q] : 0.0;     // right-hand side of U11 x = ...
         __syncthreads();                                     // everybody has read its entries of part
         TRACE2(4);
-        diag_solve_upper<RB>(F, inv, v0, part, tid);         // the solution is published in part
+        diag_solve_upper<RB, !(WIDE && RB == 1)>(F, inv, v0, part, tid);         // the solution is published in part
         __syncthreads();
         TRACE2(5);
     }
@@ -1458,9 +1461,15 @@ void launch_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks
 }
 void launch_bwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, double* x, int rb) {
     if (ntasks <= 0) return;
-#define CALL(R) launch_pdl(k_bwd<R>, ntasks, SOLVE_THREADS, 0, st, cx, tasks, x)
-    RB_DISPATCH(rb, CALL);
+    if (ntasks <= BWD_WIDE_TILES) {
+#define CALL(R) launch_pdl(k_bwd<R, false>, ntasks, SOLVE_THREADS, 0, st, cx, tasks, x)
+        RB_DISPATCH(rb, CALL);
 #undef CALL
+    } else {                                                 // throughput variant: two CTAs per SM
+#define CALL(R) launch_pdl(k_bwd<R, true>, ntasks, SOLVE_THREADS, 0, st, cx, tasks, x)
+        RB_DISPATCH(rb, CALL);
+#undef CALL
+    }
 }
 
 }  // namespace smslu
