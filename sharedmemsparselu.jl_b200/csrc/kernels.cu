@@ -168,6 +168,33 @@ __global__ void __launch_bounds__(256) k_assemble(DevCtx cx, const int4* __restr
     }
 }
 
+// Pull the front's entries of Rs .* A into its shared-memory image, four entries per thread in flight (the index
+// loads and the two dependent gathers are latency, not bandwidth).  BEFORE: the loads of the first batch are issued
+// ahead of the caller's zero-fill barrier through the two-phase interface below.
+struct PulledEntries {
+    int pos[4];
+    double val[4];
+};
+__device__ __forceinline__ void pull_entries_load(const DevCtx& cx, int e, int e1, int nt, const double* __restrict__ av,
+                                                  const double* __restrict__ Rs, PulledEntries& b) {
+    int row[4], src[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int ee = e + u * nt;
+        const bool ok = ee < e1;
+        b.pos[u] = ok ? cx.a_pos[ee] : -1;
+        row[u] = ok ? cx.a_row[ee] : 0;
+        src[u] = ok ? cx.a_src[ee] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) b.val[u] = b.pos[u] >= 0 ? Rs[row[u]] * av[src[u]] : 0.0;
+}
+__device__ __forceinline__ void pull_entries_store(const PulledEntries& b, double* Fs, int ld) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        if (b.pos[u] >= 0) Fs[(b.pos[u] & 0xffff) * ld + (b.pos[u] >> 16)] = b.val[u];
+}
+
 // ------------------------------------------------------------------ fused small front
 // A front with k <= 32 pivots and f <= SMALL_F_MAX rows is assembled, factored and stored by one
 // group of RW*CH threads entirely in shared memory ("pull" assembly):
@@ -203,13 +230,17 @@ __global__ void __launch_bounds__(RW * CH * FPC) k_small_factor(DevCtx cx, const
     double* Fs = sm + (size_t)grp * small_group_doubles(fmax);
     double* rd = Fs + (size_t)fmax * small_ld(fmax);
     {
+        const int e0 = cx.a_ptr[s] + tid, e1 = cx.a_ptr[s + 1];
+        PulledEntries pe;
+        pull_entries_load(cx, e0, e1, NT, av, Rs, pe);        // in flight across the zero-fill
         double2* z = reinterpret_cast<double2*>(Fs);
         for (int e = tid; e < f * ld / 2; e += NT) z[e] = make_double2(0.0, 0.0);
-    }
-    sync();
-    for (int e = cx.a_ptr[s] + tid; e < cx.a_ptr[s + 1]; e += NT) {
-        const int pos = cx.a_pos[e];
-        Fs[(pos & 0xffff) * ld + (pos >> 16)] = Rs[cx.a_row[e]] * av[cx.a_src[e]];
+        sync();
+        pull_entries_store(pe, Fs, ld);
+        for (int e = e0 + 4 * NT; e < e1; e += 4 * NT) {
+            pull_entries_load(cx, e, e1, NT, av, Rs, pe);
+            pull_entries_store(pe, Fs, ld);
+        }
     }
     sync();
     for (int ci = cx.child_ptr[s]; ci < cx.child_ptr[s + 1]; ++ci) {
@@ -309,13 +340,17 @@ __global__ void __launch_bounds__(((NC + 31) / 32) * 32 * FPC) k_small_factor_re
     double* strip = Fs + NC * ld;                     // strip[2][SL]: row j (NC values), 1/u_jj at [NC]
     double* rd = strip + 2 * SL;
     {
+        const int e0 = cx.a_ptr[s] + tid, e1 = cx.a_ptr[s + 1];
+        PulledEntries pe;
+        pull_entries_load(cx, e0, e1, NT, av, Rs, pe);        // in flight across the zero-fill
         double2* z = reinterpret_cast<double2*>(Fs);
         for (int e = tid; e < f * ld / 2; e += NT) z[e] = make_double2(0.0, 0.0);
-    }
-    sync();
-    for (int e = cx.a_ptr[s] + tid; e < cx.a_ptr[s + 1]; e += NT) {
-        const int pos = cx.a_pos[e];
-        Fs[(pos & 0xffff) * ld + (pos >> 16)] = Rs[cx.a_row[e]] * av[cx.a_src[e]];
+        sync();
+        pull_entries_store(pe, Fs, ld);
+        for (int e = e0 + 4 * NT; e < e1; e += 4 * NT) {
+            pull_entries_load(cx, e, e1, NT, av, Rs, pe);
+            pull_entries_store(pe, Fs, ld);
+        }
     }
     sync();
     for (int ci = cx.child_ptr[s]; ci < cx.child_ptr[s + 1]; ++ci) {
@@ -324,9 +359,16 @@ __global__ void __launch_bounds__(((NC + 31) / 32) * 32 * FPC) k_small_factor_re
         const int* __restrict__ rel = cx.rel + cx.rows_ptr[c];
         const double* __restrict__ Cc = cx.cb + cx.CBoff[c];
         const int pa = tid < rc ? rel[tid] * ld : 0;              // rc <= f <= NC <= NT
-        for (int b = 0; b < rc; ++b) {
-            const int pb = rel[b];
-            if (tid < rc) Fs[pa + pb] += Cc[tid + b * rc];
+        for (int b0 = 0; b0 < rc; b0 += 8) {                      // eight columns of the child's block in flight
+            double cv[8]; int pb[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const bool ok = tid < rc && b0 + u < rc;
+                pb[u] = ok ? rel[b0 + u] : -1;
+                cv[u] = ok ? Cc[tid + (b0 + u) * rc] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) if (pb[u] >= 0) Fs[pa + pb[u]] += cv[u];
         }
         sync();
     }
