@@ -1,0 +1,22 @@
+"""Device time of refactor-only and solve-only loops (lanes on), 2D 1024^2."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, numpy as np, smslu
+from sharedmemsparselu_jl_b200 import workloads as W
+grid = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+A = W.laplacian_2d(grid); n = A.shape[0]
+F = smslu.ParallelSparseLU(A)
+st = torch.cuda.current_stream(); F.set_stream(st)
+v = torch.from_numpy(A.data.copy()).cuda(); b = torch.from_numpy(W.rhs(n, 47)).cuda(); x = torch.empty_like(b)
+def timed(fn, reps=20):
+    for _ in range(5): fn()
+    F.sync(); torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(reps): fn()
+    e1.record(st); F.sync(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+print("refactor only : %.3f ms" % timed(lambda: F.refactor_async(v)))
+print("solve only    : %.3f ms" % timed(lambda: F.solve_async(x, b)))
+print("refactor+solve: %.3f ms" % timed(lambda: (F.refactor_async(v), F.solve_async(x, b))))
+F.close()

@@ -126,6 +126,10 @@ struct smslu_handle_s {
     cudaStream_t user_stream = nullptr;
     bool have_user_stream = false;
     bool profile = false;
+    // SMSLU_LEVEL_TIMES=1 (debug): an event on the main stream at every level boundary, printed by smslu_sync
+    bool level_times = getenv("SMSLU_LEVEL_TIMES") != nullptr;
+    struct LevelMark { cudaEvent_t ev; int level; int nlaunch; int ntasks; const void* sched; };
+    std::vector<LevelMark> lvl_marks;
     std::vector<cudaEvent_t> pev;          // event pool for per-launch profiling
     std::vector<int> pev_kind;             // kind of the launch between pev[2i], pev[2i+1]
     size_t pev_used = 0;
@@ -586,6 +590,18 @@ int prof_end(smslu_handle_t h) {
     return 0;
 }
 int prof_collect(smslu_handle_t h) {   // stream must be synchronized
+    if (!h->lvl_marks.empty()) {
+        for (size_t i = 0; i + 1 < h->lvl_marks.size(); ++i) {
+            const auto& m = h->lvl_marks[i];
+            if (!m.sched) continue;
+            float ms = 0;
+            cudaEventElapsedTime(&ms, m.ev, h->lvl_marks[i + 1].ev);
+            const char* nm = m.sched == &h->fac ? "fac" : m.sched == &h->fwd ? "fwd" : m.sched == &h->bwd ? "bwd" : "top";
+            fprintf(stderr, "[smslu level] %s level %3d launches %2d tasks %7d  %8.1f us\n", nm, m.level, m.nlaunch, m.ntasks, 1e3 * ms);
+        }
+        for (auto& m : h->lvl_marks) cudaEventDestroy(m.ev);
+        h->lvl_marks.clear();
+    }
     if (!h->profile) return 0;
     for (size_t i = 0; i + 1 < h->pev_used; i += 2) {
         float ms = 0;
@@ -629,6 +645,14 @@ int run_schedule(smslu_handle_t h, const std::vector<Launch>& sched, const doubl
             CU(cudaStreamWaitEvent(h->stream, h->ev_scatter, 0));
             h->scatter_pending = false;
         }
+        if (h->level_times) {
+            smslu_handle_s::LevelMark m;
+            CU(cudaEventCreate(&m.ev));
+            CU(cudaEventRecord(m.ev, h->stream));
+            m.level = sched[i].level; m.nlaunch = (int)(j - i); m.ntasks = 0; m.sched = &sched;
+            for (size_t t = i; t < j; ++t) m.ntasks += sched[t].ntasks;
+            h->lvl_marks.push_back(m);
+        }
         const bool fork = nused > 1 && !h->profile && h->aux_stream[0];
         auto lane_stream = [&](int lane) { return (fork && lane > 0) ? h->aux_stream[lane - 1] : h->stream; };
         if (fork) {
@@ -649,6 +673,13 @@ int run_schedule(smslu_handle_t h, const std::vector<Launch>& sched, const doubl
                 }
         }
         i = j;
+    }
+    if (h->level_times) {
+        smslu_handle_s::LevelMark m;
+        CU(cudaEventCreate(&m.ev));
+        CU(cudaEventRecord(m.ev, h->stream));
+        m.level = -1; m.nlaunch = 0; m.ntasks = 0; m.sched = nullptr;
+        h->lvl_marks.push_back(m);
     }
     CU(cudaGetLastError());
     return 0;
