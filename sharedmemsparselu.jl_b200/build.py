@@ -34,6 +34,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     tmp = LIB + ".%d.tmp" % os.getpid()
     trace = ["-DSMSLU_TRACE"] if os.environ.get("SMSLU_TRACE") == "1" else []
+    if trace and os.environ.get("SMSLU_TRACE_ROWS"):
+        trace.append("-DSMSLU_TRACE_ROWS=" + os.environ["SMSLU_TRACE_ROWS"])
     cmd = [nvcc()] + NVCC_FLAGS + trace + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + \
           [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     subprocess.check_call(cmd)

@@ -62,6 +62,8 @@ enum LaunchKind { L_ZERO = SMSLU_K_ZERO, L_EXTEND = SMSLU_K_EXTEND, L_SMALL = SM
 
 constexpr int NLANES = 4;
 
+constexpr int PANEL_GROUP_CTAS = 296;  // panel launches aim at about this many CTAs (2 per SM) ...
+constexpr int PANEL_GROUP_MAX = 16;    // ... by giving one CTA up to this many 128-row tiles of its front
 constexpr int FWD_WIDE_TILES = 148;   // 64-row forward tiles of a level beyond which 256-row tiles are used
 
 struct Launch {
@@ -263,6 +265,7 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
                 // owns a range of destination columns also zero-fills its part of the parent's block.
                 // In phase A a top parent receives this rank's subtree contributions here as well.
                 off = (int64_t)tasks.size();
+                int64_t asm_fmax = 0;                  // rows of the largest parent assembled in this launch
                 for (int t = 0; t < cnt; ++t) {
                     int s = sn[t];
                     if (SMALL(s) || NC(s) == 0 || NARROW(s) != (grp == 1)) continue;   // small parents pull their children
@@ -275,6 +278,7 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
                     if (kids.empty()) continue;
                     const bool zero = IN(s) && R(s) > 0 && !S.iface[s];
                     const int64_t f = K(s) + R(s);
+                    asm_fmax = std::max<int64_t>(asm_fmax, f);
                     for (int64_t pb0 = 0; pb0 < f; pb0 += ASM_COLS) {
                         const int64_t moff = (int64_t)h->asm_meta.size();
                         int np = 0;
@@ -290,38 +294,46 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
                         tasks.push_back(make_int4(s, (int)pb0, (int)moff, (zero ? 1 : 0) | (np << 8)));
                     }
                 }
-                push(fac, L_EXTEND, off, 0);
+                push(fac, L_EXTEND, off, (int)std::min<int64_t>(asm_fmax, 1 << 30));
                 // big fronts: left-looking panel steps (one launch per 32 pivot columns), then Schur update
                 int max_blk = 0;
                 for (int t = 0; t < cnt; ++t) if (IN(sn[t]) && !SMALL(sn[t]) && NARROW(sn[t]) == (grp == 1)) max_blk = std::max(max_blk, (K(sn[t]) + NB - 1) / NB);
                 for (int g = 0; g < max_blk; ++g) {
-                    // rows per CTA: 128 when that already gives the machine enough CTAs, else 32
+                    // rows per tile: 128 when that already gives the machine enough CTAs, else 32.  On bulk levels a CTA
+                    // takes up to `group` consecutive tiles of its front (one staging and one factorization of D_gg
+                    // for all of them): group = tiles of the launch / (2 CTAs x 148 SMs).
                     int rows = PANEL_ROWS;
-                    for (int attempt = 0; attempt < 2; ++attempt) {
-                        off = (int64_t)tasks.size();
-                        const int64_t nc0 = ncounters;
-                        for (int t = 0; t < cnt; ++t) {
-                            int s = sn[t];
-                            if (!IN(s) || SMALL(s) || NARROW(s) != (grp == 1)) continue;
-                            const int k = K(s), nblk = (k + NB - 1) / NB;
-                            if (g >= nblk) continue;
-                            const int64_t r = R(s), f = k + r;
-                            const int j1 = std::min(k, (g + 1) * NB);
-                            int tl = (int)((f - j1 + rows - 1) / rows);      // rows below the diagonal block
-                            const int tt = (int)((r + rows - 1) / rows);     // rows of U12'
-                            const int ti = (k - j1 + rows - 1) / rows;       // columns right of it
-                            if (tl + tt + ti == 0) tl = 1;                   // someone has to factor D_gg
-                            const int total = tl + tt + ti;
-                            const int cidx = (int)ncounters++;
-                            for (int i = 0; i < tl; ++i) tasks.push_back(make_int4(s, g | (0 << 4) | (total << 8), i, cidx));
-                            for (int i = 0; i < tt; ++i) tasks.push_back(make_int4(s, g | (1 << 4) | (total << 8), i, cidx));
-                            for (int i = 0; i < ti; ++i) tasks.push_back(make_int4(s, g | (2 << 4) | (total << 8), i, cidx));
+                    auto tiles_of = [&](int s, int rws, int& tl, int& tt, int& ti) {
+                        const int k = K(s);
+                        const int64_t r = R(s), f = k + r;
+                        const int j1 = std::min(k, (g + 1) * NB);
+                        tl = (int)((f - j1 + rws - 1) / rws);            // rows below the diagonal block
+                        tt = (int)((r + rws - 1) / rws);                 // rows of U12'
+                        ti = (k - j1 + rws - 1) / rws;                   // columns right of it
+                    };
+                    auto in_step = [&](int s) {
+                        return IN(s) && !SMALL(s) && NARROW(s) == (grp == 1) && g < (K(s) + NB - 1) / NB;
+                    };
+                    int64_t tiles_total = 0;
+                    for (int t = 0; t < cnt; ++t) {
+                        if (!in_step(sn[t])) continue;
+                        int tl, tt, ti; tiles_of(sn[t], rows, tl, tt, ti);
+                        tiles_total += std::max(1, tl + tt + ti);
+                    }
+                    if (tiles_total > 0 && tiles_total < 120) rows = PANEL_ROWS_TOP;     // few tiles: small CTAs
+                    const int group = rows == PANEL_ROWS ? (int)std::min<int64_t>(PANEL_GROUP_MAX, std::max<int64_t>(1, tiles_total / PANEL_GROUP_CTAS)) : 1;
+                    off = (int64_t)tasks.size();
+                    for (int t = 0; t < cnt; ++t) {
+                        int s = sn[t];
+                        if (!in_step(s)) continue;
+                        int tl, tt, ti; tiles_of(s, rows, tl, tt, ti);
+                        const int ntile = std::max(1, tl + tt + ti);         // someone has to factor D_gg
+                        const int nctas = (ntile + group - 1) / group;
+                        const int cidx = (int)ncounters++;
+                        for (int c = 0; c < nctas; ++c) {                    // even split of the tiles over the CTAs
+                            const int t0 = (int)((int64_t)ntile * c / nctas), t1 = (int)((int64_t)ntile * (c + 1) / nctas);
+                            tasks.push_back(make_int4(s, g | ((t1 - t0) << 4) | (nctas << 16), t0, cidx));
                         }
-                        if (attempt == 0 && (int64_t)tasks.size() - off < 120 && (int64_t)tasks.size() > off) {
-                            tasks.resize(off); ncounters = nc0; rows = PANEL_ROWS_TOP;     // redo with small CTAs
-                            continue;
-                        }
-                        break;
                     }
                     push(fac, L_PANEL, off, g | (rows << 8));
                 }
@@ -619,7 +631,7 @@ int launch_one(smslu_handle_t h, cudaStream_t st, const Launch& L, const double*
     const int4* tk = h->d_tasks + L.off;
     switch (L.kind) {
         case L_ZERO: launch_zero_cb(st, h->cx, tk, L.ntasks); break;
-        case L_EXTEND: launch_assemble(st, h->cx, tk, L.ntasks); break;
+        case L_EXTEND: launch_assemble(st, h->cx, tk, L.ntasks, L.fmax); break;
         case L_SMALL: launch_front_small(st, h->cx, tk, L.ntasks, L.fmax, h->cur_av, h->d_Rs); break;
         case L_FWD_SMALL: launch_small_fwd(st, h->cx, tk, L.ntasks, win, zx, rb); break;
         case L_BWD_SMALL: launch_small_bwd(st, h->cx, tk, L.ntasks, zx, rb); break;

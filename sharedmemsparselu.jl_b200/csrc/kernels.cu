@@ -13,9 +13,15 @@ __device__ long long g_trace[32];
 #define TRACE(i) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && ((threadIdx.x >> 5) == 0 || (threadIdx.x >> 5) == 4)) \
         g_trace[(i) + ((threadIdx.x >> 5) == 4 ? 8 : 0)] = clock64(); } while (0)
 #define TRACE2(i) do { if (blockIdx.x == 0 && threadIdx.x == 0 && gridDim.x == 1) g_trace[16 + (i)] = clock64(); } while (0)
+// panel kernel: SMSLU_TRACE_ROWS selects the variant that records (default: the 32-row latency variant)
+#ifndef SMSLU_TRACE_ROWS
+#define SMSLU_TRACE_ROWS 32
+#endif
+#define TRACEP(i) do { if (ROWS == SMSLU_TRACE_ROWS) TRACE(i); } while (0)
 #else
 #define TRACE(i) do {} while (0)
 #define TRACE2(i) do {} while (0)
+#define TRACEP(i) do {} while (0)
 #endif
 
 namespace {
@@ -165,6 +171,75 @@ __global__ void __launch_bounds__(256) k_assemble(DevCtx cx, const int4* __restr
             }
         }
         __syncthreads();
+    }
+}
+
+// Same task format, for parents with at most ASM_SMEM_ROWS rows (every level but the top few): the CTA's
+// destination columns are accumulated in shared memory -- loaded once (zeros for the part of the contribution
+// block that would have been zero-filled), the children added in the same ascending order (so the result is
+// bitwise the same as k_assemble's), written back once.  The per-child work has no dependent global round trip
+// left (k_assemble: rel -> old value -> store, per child, 69 % of its cycles on the long scoreboard) and the
+// parent is read and written once instead of once per child.
+// dynamic shared memory: ASM_COLS * (rows of the largest parent of the launch) doubles.
+__global__ void __launch_bounds__(256) k_assemble_smem(DevCtx cx, const int4* __restrict__ tasks) {
+    extern __shared__ __align__(16) double cols[];         // cols[c * f + pa]
+    const int4 tk = tasks[blockIdx.x];
+    const int s = tk.x, pb0 = tk.y, nch = tk.w >> 8;
+    pdl_trigger();
+    const int* __restrict__ meta = cx.asm_meta + tk.z;
+    const Front F = load_front(cx, s);
+    pdl_wait();
+    const int k = F.k, f = (int)F.f, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pb1 = pb0 + ASM_COLS < f ? pb0 + ASM_COLS : f;
+    const bool zero = tk.w & 1;
+    // address of front entry (pa, pb): P(:, pb) for pb < k; else row pb-k of U12' when pa < k, column pb-k of C
+    auto entry = [&](int pa, int pb) -> double* {
+        return pb < k ? F.P + pa + (int64_t)pb * F.f
+                      : (pa < k ? F.T + (pb - k) + (int64_t)pa * F.r : F.C + (pa - k) + (int64_t)(pb - k) * F.r);
+    };
+    const int total = (pb1 - pb0) * f;
+    for (int e0 = tid; e0 < total; e0 += 4 * 256) {              // four loads per thread in flight
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + 256 * u;
+            v[u] = 0.0;
+            if (e < total) {
+                const int c = e / f, pa = e - c * f, pb = pb0 + c;
+                if (!(zero && pb >= k && pa >= k)) v[u] = *entry(pa, pb);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (e0 + 256 * u < total) cols[e0 + 256 * u] = v[u];
+    }
+    __syncthreads();
+    for (int q = 0; q < nch; ++q) {
+        const int c = meta[2 * q], lo = meta[2 * q + 1];
+        const int rc = (int)(cx.rows_ptr[c + 1] - cx.rows_ptr[c]);
+        const int* __restrict__ rel = cx.rel + cx.rows_ptr[c];
+        const double* __restrict__ Cc = cx.cb + cx.CBoff[c];
+        for (int b = lo + warp; b < rc; b += 8) {
+            const int pb = rel[b];
+            if (pb >= pb1) break;
+            const double* __restrict__ src = Cc + (int64_t)b * rc;
+            double* col = cols + (pb - pb0) * f;
+            for (int a0 = lane; a0 < rc; a0 += 256) {           // eight entries per lane in flight
+                int pa[8]; double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int a = a0 + 32 * u;
+                    pa[u] = a < rc ? rel[a] : -1;
+                    v[u] = a < rc ? src[a] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) if (pa[u] >= 0) col[pa[u]] += v[u];
+            }
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < total; e += 256) {
+        const int c = e / f, pa = e - c * f;
+        *entry(pa, pb0 + c) = cols[e];
     }
 }
 
@@ -465,18 +540,34 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 template <int ROWS>
 __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* __restrict__ tasks) {
     extern __shared__ __align__(16) double dsm[];
-    __shared__ __align__(16) double D[NB][CLD];     // diagonal block, D[i][c]
-    __shared__ __align__(16) double W[NB][CLD];     // W[p][c] = U[p][c] (kind 0) or L[c][p] (kinds 1, 2)
+    // DW[0] = W: W[p][c] = U[p][c], the factored block as the kind-0 tiles read it.
+    // DW[1] = D: the raw diagonal block D[i][c]; once warp 0 holds it in registers, D[p][c] = L[c][p] for kinds 1, 2.
+    __shared__ __align__(16) double DW[2][NB][CLD];
+    double (*const W)[CLD] = DW[0];
+    double (*const D)[CLD] = DW[1];
     __shared__ double rd[NB];
-    TRACE(0);
+    TRACEP(0);
     pdl_trigger();
     int4 tk = tasks[blockIdx.x];
     const Front F = load_front(cx, tk.x);
     pdl_wait();
-    const int g = tk.y & 15, kind = (tk.y >> 4) & 15, total = tk.y >> 8;
+    const int g = tk.y & 15, ngroup = (tk.y >> 4) & 4095, total = tk.y >> 16;
     const int k = F.k, j0 = g * NB, w = (k - j0 < NB) ? k - j0 : NB, j1 = j0 + w;
     const int tid = threadIdx.x, lane = tid & 31, warp = uniform_warp_id(), fr = lane >> 2, fc = lane & 3;
-    TRACE(1);
+    // The step's tiles in canonical order: kind 0 (rows below the diagonal block), kind 1 (rows of U12'), kind 2
+    // (columns right of the diagonal block).  This CTA takes tiles [tk.z, tk.z + ngroup).
+    const int nt0 = (int)((F.f - j1 + ROWS - 1) / ROWS), nt1 = (int)((F.r + ROWS - 1) / ROWS);
+    int kind, tile;
+    int64_t stride;
+    const double* cf;
+    auto set_tile = [&](int t) {
+        kind = t < nt0 ? 0 : (t < nt0 + nt1 ? 1 : 2);
+        if (nt0 + nt1 + (k - j1 + ROWS - 1) / ROWS == 0) kind = 0;      // the lone CTA that only factors D_gg
+        tile = kind == 0 ? t : (kind == 1 ? t - nt0 : t - nt0 - nt1);
+        stride = kind == 0 ? F.f : (kind == 1 ? F.r : 1);
+    };
+    set_tile(tk.z);
+    TRACEP(1);
     double* Uc = dsm;                               // Uc[m * CLD + c] = U[m, j0 + c],  m < j0
     double* Lc = dsm + j0 * CLD;                    // Lc[m * CLD + i] = L[j0 + i, m],  m < j0
     double* Xs = dsm + 2 * j0 * CLD;                // Xs[row][CLD]: updated rows, one per thread in phase T
@@ -486,7 +577,6 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
     constexpr bool STAGE_ROWS = ROWS == PANEL_ROWS_TOP;
     constexpr int ALD = KW + 4;
     double* As = Xs + ROWS * CLD;
-    const int64_t stride = kind == 0 ? F.f : (kind == 1 ? F.r : 1);
     auto row_ptr = [&](int64_t idx, double*& b, bool& act) {
         if (kind == 0) { act = j1 + idx < F.f; b = F.P + j1 + idx; }
         else if (kind == 1) { act = idx < F.r; b = F.T + idx; }
@@ -498,7 +588,7 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
         constexpr int NW = PANEL_THREADS / 32;
         if (STAGE_ROWS) {
             double* rb; bool ra;
-            row_ptr((int64_t)tk.z * ROWS + lane, rb, ra);
+            row_ptr((int64_t)tile * ROWS + lane, rb, ra);
             for (int m = warp; m < j1; m += NW) cp_async8(As + lane * ALD + m, ra ? rb + (int64_t)m * stride : Pg, ra);
         }
         {
@@ -516,11 +606,11 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
         cp_async_wait_all();
     }
     __syncthreads();
-    TRACE(2);
+    TRACEP(2);
     // ---- U: left-looking update on the FP64 tensor pipe, in pieces of 8 rows x 16 columns (2 DMMA tiles).
     // The diagonal block goes first (one piece per warp); then warp 0 factors it (phase L) WHILE the other seven
     // warps update the row block, which does not depend on the factorization.
-    const double* cf = kind == 0 ? Uc : Lc;
+    cf = kind == 0 ? Uc : Lc;
     constexpr int NW = PANEL_THREADS / 32, ROW_PIECES = (ROWS / 8) * 2;
     auto row_piece = [&](int st, int ch) {
         double acc[2][2];
@@ -541,7 +631,7 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
             }
         } else {
         double* fb; bool fa;
-        row_ptr((int64_t)tk.z * ROWS + st * 8 + fr, fb, fa);
+        row_ptr((int64_t)tile * ROWS + st * 8 + fr, fb, fa);
 #pragma unroll
         for (int j = 0; j < 2; ++j)
 #pragma unroll
@@ -586,7 +676,7 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
     if (j0 > 0) diag_piece((warp >> 1) * 8, (warp & 1) * 16);       // 8 pieces, 8 warps
     static_assert(NW == 8, "one diagonal piece per warp");
     __syncthreads();
-    TRACE(3);
+    TRACEP(3);
     double x[NB];
     // ---- L: warp 0 factors the diagonal block
     if (warp == 0) {
@@ -613,19 +703,24 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
         }
         rd[lane] = myr;
         if (lane == 0 && bad < w) atomicMin(cx.flag, F.c0 + j0 + bad);
-        if (kind == 0) {                           // W[p][c] = U[p][c]: lane p stores its row
+        // publish the factors in the form(s) this CTA's tiles need: rows of U for kind 0 (in W), columns of L for
+        // kinds 1 and 2 (in D, whose raw contents only this warp still needed)
+        const bool need_u = kind == 0, need_l = kind != 0 || (int)tk.z + ngroup > nt0;
+        __syncwarp();
+        if (need_l) {                              // D[p][c] = L[c][p]: lane c stores column c
+#pragma unroll
+            for (int p = 0; p < NB; ++p) D[p][lane] = x[p];
+        }
+        if (need_u) {                              // W[p][c] = U[p][c]: lane p stores its row
 #pragma unroll
             for (int c2 = 0; c2 < NB / 2; ++c2) *reinterpret_cast<double2*>(&W[lane][2 * c2]) = make_double2(x[2 * c2], x[2 * c2 + 1]);
-        } else {                                   // W[p][c] = L[c][p]: lane c stores column c
-#pragma unroll
-            for (int p = 0; p < NB; ++p) W[p][lane] = x[p];
         }
     } else {
         for (int pc = warp - 1; pc < ROW_PIECES; pc += NW - 1) row_piece(pc >> 1, (pc & 1) * 16);
     }
-    TRACE(4);
+    TRACEP(4);
     __syncthreads();
-    TRACE(5);
+    TRACEP(5);
     if (warp == 0) {
         // this CTA's reads of the raw diagonal block completed in phase S; the CTA that arrives last
         // stores the factors (column by column: lanes = rows) and the reciprocal pivots
@@ -646,31 +741,43 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
     // ---- T: thread = row; warp 0 is busy storing the block, so the rows start at warp 1 when ROWS < 224
     constexpr int T0 = ROWS <= PANEL_THREADS - 32 ? 32 : 0;
     const int row = tid - T0;
-    if (row < 0 || row >= ROWS) return;
-    double* base; bool active;
-    row_ptr((int64_t)tk.z * ROWS + row, base, active);
-    if (!active) return;
+    for (int t = tk.z;;) {
+        if (row >= 0 && row < ROWS) {
+            double* base; bool active;
+            row_ptr((int64_t)tile * ROWS + row, base, active);
+            if (active) {
 #pragma unroll
-    for (int c2 = 0; c2 < NB / 2; ++c2) {
-        const double2 v = *reinterpret_cast<const double2*>(Xs + row * CLD + 2 * c2);
-        x[2 * c2] = v.x; x[2 * c2 + 1] = v.y;
-    }
+                for (int c2 = 0; c2 < NB / 2; ++c2) {
+                    const double2 v = *reinterpret_cast<const double2*>(Xs + row * CLD + 2 * c2);
+                    x[2 * c2] = v.x; x[2 * c2 + 1] = v.y;
+                }
+                const double (*Wk)[CLD] = DW[kind == 0 ? 0 : 1];
 #pragma unroll
-    for (int p = 0; p < NB; ++p) {
-        if (p >= w) break;
-        const double xp = kind == 0 ? x[p] * rd[p] : x[p];
-        x[p] = xp;
-        const double2* __restrict__ wr = reinterpret_cast<const double2*>(&W[p][0]);
+                for (int p = 0; p < NB; ++p) {
+                    if (p >= w) break;
+                    const double xp = kind == 0 ? x[p] * rd[p] : x[p];
+                    x[p] = xp;
+                    const double2* __restrict__ wr = reinterpret_cast<const double2*>(&Wk[p][0]);
 #pragma unroll
-        for (int c2 = (p + 1) / 2; c2 < NB / 2; ++c2) {
-            const double2 wv = wr[c2];
-            if (2 * c2 > p) x[2 * c2] -= xp * wv.x;
-            x[2 * c2 + 1] -= xp * wv.y;
+                    for (int c2 = (p + 1) / 2; c2 < NB / 2; ++c2) {
+                        const double2 wv = wr[c2];
+                        if (2 * c2 > p) x[2 * c2] -= xp * wv.x;
+                        x[2 * c2 + 1] -= xp * wv.y;
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < NB; ++c) if (c < w) base[(int64_t)(j0 + c) * stride] = x[c];
+            }
         }
+        TRACEP(6);
+        // ---- further tiles of this CTA's group (bulk levels): same coefficient blocks, same factored D_gg
+        if (STAGE_ROWS || ++t >= (int)tk.z + ngroup) break;    // the latency variant has one tile per CTA
+        __syncthreads();                           // phase T has consumed Xs
+        set_tile(t);
+        cf = kind == 0 ? Uc : Lc;
+        for (int pc = warp; pc < ROW_PIECES; pc += NW) row_piece(pc >> 1, (pc & 1) * 16);
+        __syncthreads();
     }
-    TRACE(6);
-#pragma unroll
-    for (int c = 0; c < NB; ++c) if (c < w) base[(int64_t)(j0 + c) * stride] = x[c];
 }
 
 // ------------------------------------------------------------------ Schur update of the CB
@@ -1405,6 +1512,8 @@ cudaError_t kernels_init() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_panel<PANEL_ROWS_TOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem(KW - NB, PANEL_ROWS_TOP));
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_assemble_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ASM_COLS * ASM_SMEM_ROWS));
+    if (e != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -1424,8 +1533,10 @@ void launch_scatter(cudaStream_t st, int64_t nnz, const int64_t* dst, const int*
 void launch_zero_cb(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks) {
     if (ntasks > 0) launch_pdl(k_zero_cb, ntasks, 256, 0, st, cx, tasks);
 }
-void launch_assemble(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks) {
-    if (ntasks > 0) launch_pdl(k_assemble, ntasks, 256, 0, st, cx, tasks);
+void launch_assemble(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int fmax) {
+    if (ntasks <= 0) return;
+    if (fmax > 0 && fmax <= ASM_SMEM_ROWS) launch_pdl(k_assemble_smem, ntasks, 256, sizeof(double) * ASM_COLS * fmax, st, cx, tasks);
+    else launch_pdl(k_assemble, ntasks, 256, 0, st, cx, tasks);
 }
 template <int RW, int CH, int FPC>
 static void launch_small_class(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int fmax,

@@ -30,6 +30,7 @@ constexpr int BWD_ROWS = 256;     // rows of U12' per backward CTA
 constexpr int ZERO_TILE = 8192;
 constexpr int RB_MAX = 8;         // most right-hand sides swept together by the solve kernels
 constexpr int ASM_COLS = 8;       // destination columns of a parent front per assembly CTA
+constexpr int ASM_SMEM_ROWS = 1536; // parents up to this many rows are assembled through shared memory (96 KB per CTA at most)
 
 struct DevCtx {
     const int* sn_start;
@@ -67,7 +68,7 @@ void launch_scatter(cudaStream_t st, int64_t nnz, const int64_t* dst, const int*
                     const double* Rs, const double* av, double* lu);
 void launch_zero_cb(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks);
 void launch_diag_inverse(cudaStream_t st, const DevCtx& cx, const int2* tasks, int ntasks);
-void launch_assemble(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks);
+void launch_assemble(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int fmax);
 void launch_front_small(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int fmax,
                         const double* av, const double* Rs);
 // rb = right-hand sides swept together (1, 4 or 8); vectors are interleaved [i * rb + q]
