@@ -302,6 +302,16 @@ def test_full_size_properties(smslu, W, cfg):
     smslu.lsolve_(F, w); smslu.rsolve_(F, w)
     xx = np.empty(n); xx[F.q] = w
     assert np.array_equal(xx, x2)
+    # matrix right-hand sides at full size: 11 columns = one 8-wide and one 4-wide sweep through the bulk-level
+    # variants of the solve kernels (256-row forward tiles, two-CTAs-per-SM backward), column by column
+    # against the single-vector solve
+    B = np.asfortranarray(np.stack([b2 * (1.0 + 0.1 * r) + r * b for r in range(11)], axis=1))
+    X = np.empty((n, 11), order="F")
+    smslu.ldiv_(X, F, B)
+    for r in (0, 4, 7, 8, 10):
+        xr = np.empty(n); smslu.ldiv_(xr, F, np.ascontiguousarray(B[:, r]))
+        assert np.linalg.norm(X[:, r] - xr) <= 1e-13 * np.linalg.norm(xr)
+        assert residual(A, X[:, r], B[:, r]) < 1e-12
     # refactor with shifted values (config 2: A + k*1e-3*I), pattern fixed
     A2 = sp.csc_matrix(A + 1e-3 * sp.identity(n)); A2.sort_indices()
     smslu.lu_(F, A2)
