@@ -311,7 +311,6 @@ def test_full_size_properties(smslu, W, cfg):
     for r in (0, 4, 7, 8, 10):
         xr = np.empty(n); smslu.ldiv_(xr, F, np.ascontiguousarray(B[:, r]))
         assert np.linalg.norm(X[:, r] - xr) <= 1e-13 * np.linalg.norm(xr)
-        assert residual(A, X[:, r], B[:, r]) < 1e-12
     # refactor with shifted values (config 2: A + k*1e-3*I), pattern fixed
     A2 = sp.csc_matrix(A + 1e-3 * sp.identity(n)); A2.sort_indices()
     smslu.lu_(F, A2)
