@@ -748,6 +748,11 @@ int enqueue_refactor(smslu_handle_t h, const double* av, bool rs_given) {
     return 0;
 }
 
+// kernels of one refactorization besides the optional row scaling: scatter, the schedules, the diagonal-block inverses
+int64_t refactor_launches(smslu_handle_t h) {
+    return 1 + (int64_t)h->fac.size() + (int64_t)h->fac_top.size() + (h->n_inv_tasks > 0 ? 1 : 0);
+}
+
 constexpr int FLAG_CLEAN = 0x7f7f7f7f;
 
 // After the stream has been synchronized: turn the device pivot flag into a status.
@@ -965,7 +970,7 @@ int smslu_refactor(smslu_handle_t h, const double* nzval, const double* Rs) {
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1)); h->st.ms_refactor_h2d = ms;
     CU(cudaEventElapsedTime(&ms, h->ev1, h->ev2)); h->st.ms_refactor = ms;
-    h->st.launches_refactor = (int64_t)h->fac.size() + 1 + ((!Rs && h->opt.scaling == SMSLU_SCALE_SUM) ? 1 : 0);
+    h->st.launches_refactor = refactor_launches(h) + ((!Rs && h->opt.scaling == SMSLU_SCALE_SUM) ? 1 : 0);
     if ((rc = prof_collect(h))) return rc;
     return finish_refactor(h);
 }
@@ -978,7 +983,7 @@ int smslu_refactor_async(smslu_handle_t h, const double* nzval_dev, const double
         return fail(h, SMSLU_E_ARG, "smslu_refactor_async needs device pointers");
     if (Rs_dev) CU(cudaMemcpyAsync(h->d_Rs, Rs_dev, sizeof(double) * h->n, cudaMemcpyDeviceToDevice, h->stream));
     else if (h->opt.scaling != SMSLU_SCALE_SUM) return fail(h, SMSLU_E_ARG, "async refactor needs Rs or SUM scaling");
-    h->st.launches_refactor = (int64_t)h->fac.size() + 1 + ((!Rs_dev) ? 1 : 0);
+    h->st.launches_refactor = refactor_launches(h) + ((!Rs_dev) ? 1 : 0);
     return enqueue_refactor(h, nzval_dev, Rs_dev != nullptr);
 }
 
