@@ -2,6 +2,10 @@
 #include "symbolic.hpp"
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -113,8 +117,15 @@ void nd_grid(const int dims[3], int leaf, std::vector<int>& order) {
 // rooted level structure started at a pseudo-peripheral vertex, chosen near the median.
 class GraphND {
   public:
-    GraphND(const Graph& G, const SymOptions& o) : G_(G), opt_(o), region_(G.n, -1), level_(G.n, -1) {}
+    GraphND(const Graph& G, const SymOptions& o) : G_(G), opt_(o), region_(G.n), level_(G.n, -1) {
+        for (int v = 0; v < G.n; ++v) region_[v].store(-1, std::memory_order_relaxed);
+    }
 
+    struct Item { std::vector<int> verts; int64_t pos; };
+
+    // The two sides of a separator are independent subproblems (disjoint vertices, disjoint ranges of `order`),
+    // and an item's result does not depend on when it is processed: a few worker threads share the open
+    // subdomains.  The ordering is bit-for-bit the sequential one.
     void run(std::vector<int>& order) {
         const int n = G_.n;
         order.assign(n, -1);
@@ -126,93 +137,139 @@ class GraphND {
         if (normal.empty()) { std::iota(order.begin(), order.end(), 0); return; }
         int64_t pos_dense = (int64_t)normal.size();
         for (int v : dense) order[pos_dense++] = v;   // region_ stays -1 => invisible to BFS
-        struct Item { std::vector<int> verts; int64_t pos; };
         std::vector<Item> st;
         st.push_back(Item{std::move(normal), 0});
-        int next_region = 0;
-        std::vector<int> queue;
+        int nthreads = (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+        if (n < 100000) nthreads = 1;
+        if (nthreads > 1) {
+            // shared stack of large open subdomains; a worker keeps one side of every split for itself and hands
+            // the other one over while it is still large
+            constexpr size_t SHARE_MIN = 8192;
+            std::mutex mu;
+            std::condition_variable cv;
+            int active = 0;
+            auto worker = [&]() {
+                std::vector<Item> mine;
+                for (;;) {
+                    {
+                        std::unique_lock<std::mutex> lk(mu);
+                        cv.wait(lk, [&] { return !st.empty() || active == 0; });
+                        if (st.empty()) { cv.notify_all(); return; }
+                        mine.push_back(std::move(st.back()));
+                        st.pop_back();
+                        ++active;
+                    }
+                    while (!mine.empty()) {
+                        Item it = std::move(mine.back());
+                        mine.pop_back();
+                        process(std::move(it), mine, order);
+                        while (mine.size() > 1 && mine.back().verts.size() >= SHARE_MIN) {
+                            std::lock_guard<std::mutex> lk(mu);
+                            st.push_back(std::move(mine.back()));
+                            mine.pop_back();
+                            cv.notify_one();
+                        }
+                    }
+                    {
+                        std::lock_guard<std::mutex> lk(mu);
+                        --active;
+                        if (active == 0 && st.empty()) cv.notify_all();
+                    }
+                }
+            };
+            std::vector<std::thread> pool;
+            for (int t = 1; t < nthreads; ++t) pool.emplace_back(worker);
+            worker();
+            for (auto& th : pool) th.join();
+            return;
+        }
         while (!st.empty()) {
             Item it = std::move(st.back());
             st.pop_back();
-            const int rid = next_region++;
-            for (int v : it.verts) region_[v] = rid;
-            // ---- connected components
-            std::vector<std::vector<int>> comps;
-            for (int v : it.verts) level_[v] = -1;
-            for (int v : it.verts) {
-                if (level_[v] != -1) continue;
-                comps.emplace_back();
-                bfs(v, rid, comps.back());
-            }
-            if (comps.size() > 1) {
-                int64_t pos = it.pos;
-                for (auto& c : comps) {
-                    int64_t sz = (int64_t)c.size();
-                    st.push_back(Item{std::move(c), pos});
-                    pos += sz;
-                }
-                continue;
-            }
-            std::vector<int>& comp = comps[0];
-            const int m = (int)comp.size();
-            if (m <= opt_.nd_leaf) {   // leaf: Cuthill-McKee style order from a peripheral vertex
-                int root = pseudo_peripheral(comp, rid);
-                std::vector<int> ord;
-                for (int v : comp) level_[v] = -1;
-                bfs(root, rid, ord);
-                for (int k = 0; k < m; ++k) order[it.pos + k] = ord[k];
-                continue;
-            }
-            int root = pseudo_peripheral(comp, rid);
-            std::vector<int> ord;
-            for (int v : comp) level_[v] = -1;
-            bfs(root, rid, ord);
-            int nlev = level_[ord.back()] + 1;
-            if (nlev < 3) {   // clique-like: no useful separator
-                for (int k = 0; k < m; ++k) order[it.pos + k] = ord[k];
-                continue;
-            }
-            std::vector<int> lcount(nlev, 0);
-            for (int v : ord) ++lcount[level_[v]];
-            // candidate separator levels: both sides keep >= 25% of the vertices; among those the
-            // narrowest level wins (penalised by imbalance).  Fallback: the median level.
-            int best = -1, median = -1; double best_score = 1e300; int64_t cum = 0;
-            for (int l = 0; l < nlev; ++l) {
-                int64_t before = cum; cum += lcount[l];
-                if (median < 0 && 2 * cum >= m) median = l;
-                if (l == 0 || l == nlev - 1) continue;
-                double fb = (double)before / m, fa = (double)(m - cum) / m;
-                if (fb < 0.25 || fa < 0.25) continue;
-                double score = (double)lcount[l] * (1.0 + std::fabs(fb - fa));
-                if (score < best_score) { best_score = score; best = l; }
-            }
-            if (best < 0) best = std::min(std::max(median, 1), nlev - 2);
-            std::vector<int> A, B, Sv;
-            for (int v : ord) {
-                int l = level_[v];
-                if (l < best) A.push_back(v);
-                else if (l > best) B.push_back(v);
-                else {
-                    bool touches_after = false;
-                    for (int64_t t = G_.xadj[v]; t < G_.xadj[v + 1] && !touches_after; ++t) {
-                        int u = G_.adj[t];
-                        if (region_[u] == rid && level_[u] == best + 1) touches_after = true;
-                    }
-                    (touches_after ? Sv : A).push_back(v);
-                }
-            }
-            if (Sv.empty() || A.empty() || B.empty()) {
-                for (int k = 0; k < m; ++k) order[it.pos + k] = ord[k];
-                continue;
-            }
-            int64_t pa = it.pos, pb = pa + (int64_t)A.size(), ps = pb + (int64_t)B.size();
-            for (size_t k = 0; k < Sv.size(); ++k) { order[ps + (int64_t)k] = Sv[k]; region_[Sv[k]] = -2; }
-            st.push_back(Item{std::move(A), pa});
-            st.push_back(Item{std::move(B), pb});
+            process(std::move(it), st, order);
         }
     }
 
   private:
+    // One step of the recursion: order a leaf, or split `it` and push the two sides onto st.
+    void process(Item it, std::vector<Item>& st, std::vector<int>& order) {
+        const int rid = next_region_.fetch_add(1);
+        for (int v : it.verts) region_[v].store(rid, std::memory_order_relaxed);
+        // ---- connected components
+        std::vector<std::vector<int>> comps;
+        for (int v : it.verts) level_[v] = -1;
+        for (int v : it.verts) {
+            if (level_[v] != -1) continue;
+            comps.emplace_back();
+            bfs(v, rid, comps.back());
+        }
+        if (comps.size() > 1) {
+            int64_t pos = it.pos;
+            for (auto& c : comps) {
+                int64_t sz = (int64_t)c.size();
+                st.push_back(Item{std::move(c), pos});
+                pos += sz;
+            }
+            return;
+        }
+        std::vector<int>& comp = comps[0];
+        const int m = (int)comp.size();
+        if (m <= opt_.nd_leaf) {   // leaf: Cuthill-McKee style order from a peripheral vertex
+            int root = pseudo_peripheral(comp, rid);
+            std::vector<int> ord;
+            for (int v : comp) level_[v] = -1;
+            bfs(root, rid, ord);
+            for (int k = 0; k < m; ++k) order[it.pos + k] = ord[k];
+            return;
+        }
+        int root = pseudo_peripheral(comp, rid);
+        std::vector<int> ord;
+        for (int v : comp) level_[v] = -1;
+        bfs(root, rid, ord);
+        int nlev = level_[ord.back()] + 1;
+        if (nlev < 3) {   // clique-like: no useful separator
+            for (int k = 0; k < m; ++k) order[it.pos + k] = ord[k];
+            return;
+        }
+        std::vector<int> lcount(nlev, 0);
+        for (int v : ord) ++lcount[level_[v]];
+        // candidate separator levels: both sides keep >= 25% of the vertices; among those the
+        // narrowest level wins (penalised by imbalance).  Fallback: the median level.
+        int best = -1, median = -1; double best_score = 1e300; int64_t cum = 0;
+        for (int l = 0; l < nlev; ++l) {
+            int64_t before = cum; cum += lcount[l];
+            if (median < 0 && 2 * cum >= m) median = l;
+            if (l == 0 || l == nlev - 1) continue;
+            double fb = (double)before / m, fa = (double)(m - cum) / m;
+            if (fb < 0.25 || fa < 0.25) continue;
+            double score = (double)lcount[l] * (1.0 + std::fabs(fb - fa));
+            if (score < best_score) { best_score = score; best = l; }
+        }
+        if (best < 0) best = std::min(std::max(median, 1), nlev - 2);
+        std::vector<int> A, B, Sv;
+        for (int v : ord) {
+            int l = level_[v];
+            if (l < best) A.push_back(v);
+            else if (l > best) B.push_back(v);
+            else {
+                bool touches_after = false;
+                for (int64_t t = G_.xadj[v]; t < G_.xadj[v + 1] && !touches_after; ++t) {
+                    int u = G_.adj[t];
+                    if (region_[u].load(std::memory_order_relaxed) == rid && level_[u] == best + 1) touches_after = true;
+                }
+                (touches_after ? Sv : A).push_back(v);
+            }
+        }
+        if (Sv.empty() || A.empty() || B.empty()) {
+            for (int k = 0; k < m; ++k) order[it.pos + k] = ord[k];
+            return;
+        }
+        int64_t pa = it.pos, pb = pa + (int64_t)A.size(), ps = pb + (int64_t)B.size();
+        for (size_t k = 0; k < Sv.size(); ++k) { order[ps + (int64_t)k] = Sv[k]; region_[Sv[k]].store(-2, std::memory_order_relaxed); }
+        st.push_back(Item{std::move(A), pa});
+        st.push_back(Item{std::move(B), pb});
+    }
+
     // BFS inside region rid from root over vertices with level_ == -1; appends visit order.
     void bfs(int root, int rid, std::vector<int>& out) {
         size_t head = out.size();
@@ -222,7 +279,7 @@ class GraphND {
             int v = out[head++];
             for (int64_t t = G_.xadj[v]; t < G_.xadj[v + 1]; ++t) {
                 int u = G_.adj[t];
-                if (region_[u] != rid || level_[u] != -1) continue;
+                if (region_[u].load(std::memory_order_relaxed) != rid || level_[u] != -1) continue;
                 level_[u] = level_[v] + 1;
                 out.push_back(u);
             }
@@ -256,7 +313,9 @@ class GraphND {
     }
     const Graph& G_;
     const SymOptions& opt_;
-    std::vector<int> region_, level_;
+    std::vector<std::atomic<int>> region_;   // other threads' regions are read (never matched) while they change
+    std::vector<int> level_;
+    std::atomic<int> next_region_{0};
 };
 
 // ------------------------------------------------------------------ elimination tree etc.
