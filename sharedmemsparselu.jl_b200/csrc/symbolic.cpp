@@ -3,6 +3,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -452,6 +455,17 @@ inline int64_t align2(int64_t x) { return (x + 1) & ~(int64_t)1; }
 
 int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const int* q_in,
             const SymOptions& opt, Symbolic& S, std::string& err) {
+    // SMSLU_ANALYZE_TIMES=1 (debug): wall time of every numbered step below on stderr
+    const bool step_times = getenv("SMSLU_ANALYZE_TIMES") != nullptr;
+    const char* step_name = nullptr;
+    auto step_clock = std::chrono::steady_clock::now();
+    auto step_mark = [&](const char* nm) {
+        if (!step_times) return;
+        const auto t = std::chrono::steady_clock::now();
+        if (step_name) fprintf(stderr, "[smslu analyze] %-36s %9.1f ms\n", step_name, std::chrono::duration<double, std::milli>(t - step_clock).count());
+        step_name = nm; step_clock = t;
+    };
+
     S = Symbolic();
     S.n = n;
     if (n <= 0) { err = "matrix must have at least one row"; return SMSLU_E_DIM; }
@@ -461,6 +475,7 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
         for (int64_t t = Ap[c]; t < Ap[c + 1]; ++t)
             if (Ai[t] < 0 || Ai[t] >= n) { err = "row index out of range"; return SMSLU_E_PATTERN; }
     }
+    step_mark("1 initial ordering");
     // ---------------------------------------------------------------- 1. initial ordering
     std::vector<int> p0(n), q0(n);
     int ordering = opt.ordering;
@@ -497,6 +512,7 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
         q0 = p0;
     } else { err = "unknown ordering"; return SMSLU_E_ARG; }
 
+    step_mark("2 etree + postorder");
     // ---------------------------------------------------------------- 2. etree + postorder
     std::vector<int> rinv(n), cinv(n);
     for (int k = 0; k < n; ++k) { rinv[p0[k]] = k; cinv[q0[k]] = k; }
@@ -515,6 +531,7 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
     for (int k = 0; k < n; ++k) { rinv[S.p[k]] = k; cinv[S.q[k]] = k; }
     const std::vector<int>& parent = S.parent;
 
+    step_mark("3 column counts");
     // ---------------------------------------------------------------- 3. column counts
     column_counts(G, parent, S.colcount);
     const std::vector<int>& cc = S.colcount;
@@ -526,6 +543,7 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
         S.flops_exact += c * (2.0 * c + 1.0);
     }
 
+    step_mark("4 supernodes");
     // ---------------------------------------------------------------- 4. supernodes
     std::vector<int> fs_start;   // fundamental (maximal) supernodes
     const int W = std::max(1, opt.max_width);
@@ -590,6 +608,7 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
     S.max_children = 0;
     for (int s = 0; s < nsn; ++s) S.max_children = std::max(S.max_children, S.child_ptr[s + 1] - S.child_ptr[s]);
 
+    step_mark("5 supernodal row structure");
     // ---------------------------------------------------------------- 5. supernodal row structure
     S.rows_ptr.assign(nsn + 1, 0);
     S.rows.clear();
@@ -621,6 +640,7 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
             S.rows_ptr[s + 1] = (int64_t)S.rows.size();
         }
     }
+    step_mark("6 child -> parent index maps");
     // ---------------------------------------------------------------- 6. child -> parent index maps
     S.rel.assign(S.rows.size(), -1);
     for (int c = 0; c < nsn; ++c) {
@@ -639,6 +659,7 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
             S.rel[t] = pk + (int)(u - S.rows_ptr[s]);
         }
     }
+    step_mark("7 levels");
     // ---------------------------------------------------------------- 7. levels
     S.sn_level.assign(nsn, 0);
     S.nlevels = 0;
@@ -654,6 +675,7 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
         std::vector<int> w(S.level_ptr.begin(), S.level_ptr.end() - 1);
         for (int s = 0; s < nsn; ++s) S.level_sn[w[S.sn_level[s]]++] = s;
     }
+    step_mark("7b partition over GPUs");
     // ---------------------------------------------------------------- 7b. partition over GPUs
     // owner[s] = rank that factors supernode s, or -1 for the "top" of the tree, which every rank
     // factors redundantly after the contributions of the subtrees have been summed (all-reduce).
@@ -714,6 +736,7 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
         for (int s = 0; s < nsn; ++s)
             if (S.owner[s] >= 0 && S.sn_parent[s] != -1 && S.owner[S.sn_parent[s]] == -1) S.iface[S.sn_parent[s]] = 1;
     }
+    step_mark("8 storage plan");
     // ---------------------------------------------------------------- 8. storage plan
     S.Loff.resize(nsn);
     S.Uoff.resize(nsn);
@@ -805,6 +828,7 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
         }
         S.cb_size = ioff + arena.top();
     }
+    step_mark("9 A -> factor scatter map");
     // ---------------------------------------------------------------- 9. A -> factor scatter map
     S.a_dst.resize(S.annz);
     S.a_sn.resize(S.annz);
@@ -837,6 +861,7 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
             }
         }
     }
+    step_mark("end");
     return 0;
 }
 
