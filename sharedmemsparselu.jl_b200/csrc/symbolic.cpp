@@ -25,6 +25,32 @@ struct Graph {
     std::vector<int> adj;   // sorted, unique, no self loops
 };
 
+// Run fn(i0, i1) over [0, n) cut into ranges of about equal weight (prefix[i] = weight of the rows before i), on a few
+// host threads when the total weight makes that worthwhile.  The ranges are disjoint, so any fn that only writes what
+// belongs to its own rows gives the sequential result.
+// Host threads of the analysis: min(16, cores), or SMSLU_HOST_THREADS (the results do not depend on it).
+int host_threads() {
+    if (const char* e = getenv("SMSLU_HOST_THREADS")) return std::max(1, std::min(64, atoi(e)));
+    return (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+}
+
+template <class F>
+void parallel_rows(int n, const std::vector<int64_t>& prefix, F fn) {
+    const int64_t total = prefix[n];
+    int nthreads = host_threads();
+    if (total < (int64_t)2000000 || n < 1024) nthreads = 1;
+    if (nthreads == 1) { fn(0, n); return; }
+    std::vector<int> cut(nthreads + 1, n);
+    cut[0] = 0;
+    for (int t = 1; t < nthreads; ++t)
+        cut[t] = (int)(std::lower_bound(prefix.begin(), prefix.begin() + n, total * t / nthreads) - prefix.begin());
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nthreads; ++t)
+        if (cut[t + 1] > cut[t]) pool.emplace_back(fn, cut[t], cut[t + 1]);
+    if (cut[1] > cut[0]) fn(cut[0], cut[1]);
+    for (auto& th : pool) th.join();
+}
+
 // Graph of pattern(B + B') for B = A[p,q]; rinv/cinv map original row/col -> permuted index.
 Graph build_sym_graph(int n, const int64_t* Ap, const int64_t* Ai, const int* rinv, const int* cinv) {
     Graph G;
@@ -47,17 +73,20 @@ Graph build_sym_graph(int n, const int64_t* Ap, const int64_t* Ai, const int* ri
             tmp[w[i]++] = j;
             tmp[w[j]++] = i;
         }
+    // sort + unique every row inside its own slot (rows are independent), then compact
     G.xadj.assign(n + 1, 0);
-    int64_t out = 0;
-    for (int i = 0; i < n; ++i) {
-        std::sort(tmp.begin() + cnt[i], tmp.begin() + cnt[i + 1]);
-        int64_t b = out;
-        for (int64_t t = cnt[i]; t < cnt[i + 1]; ++t)
-            if (out == b || tmp[out - 1] != tmp[t]) tmp[out++] = tmp[t];
-        G.xadj[i + 1] = out;
-    }
-    tmp.resize(out);
-    G.adj.swap(tmp);
+    parallel_rows(n, cnt, [&](int i0, int i1) {
+        for (int i = i0; i < i1; ++i) {
+            std::sort(tmp.begin() + cnt[i], tmp.begin() + cnt[i + 1]);
+            G.xadj[i + 1] = std::unique(tmp.begin() + cnt[i], tmp.begin() + cnt[i + 1]) - (tmp.begin() + cnt[i]);
+        }
+    });
+    for (int i = 0; i < n; ++i) G.xadj[i + 1] += G.xadj[i];
+    G.adj.resize(G.xadj[n]);
+    parallel_rows(n, cnt, [&](int i0, int i1) {
+        for (int i = i0; i < i1; ++i)
+            std::copy(tmp.begin() + cnt[i], tmp.begin() + cnt[i] + (G.xadj[i + 1] - G.xadj[i]), G.adj.begin() + G.xadj[i]);
+    });
     return G;
 }
 
@@ -71,12 +100,14 @@ Graph relabel(const Graph& G, const std::vector<int>& perm) {
     H.xadj.assign(n + 1, 0);
     for (int k = 0; k < n; ++k) H.xadj[k + 1] = H.xadj[k] + (G.xadj[perm[k] + 1] - G.xadj[perm[k]]);
     H.adj.resize(G.adj.size());
-    for (int k = 0; k < n; ++k) {
-        int v = perm[k];
-        int64_t o = H.xadj[k];
-        for (int64_t t = G.xadj[v]; t < G.xadj[v + 1]; ++t) H.adj[o++] = inv[G.adj[t]];
-        std::sort(H.adj.begin() + H.xadj[k], H.adj.begin() + H.xadj[k + 1]);
-    }
+    parallel_rows(n, H.xadj, [&](int k0, int k1) {
+        for (int k = k0; k < k1; ++k) {
+            int v = perm[k];
+            int64_t o = H.xadj[k];
+            for (int64_t t = G.xadj[v]; t < G.xadj[v + 1]; ++t) H.adj[o++] = inv[G.adj[t]];
+            std::sort(H.adj.begin() + H.xadj[k], H.adj.begin() + H.xadj[k + 1]);
+        }
+    });
     return H;
 }
 
@@ -142,7 +173,7 @@ class GraphND {
         for (int v : dense) order[pos_dense++] = v;   // region_ stays -1 => invisible to BFS
         std::vector<Item> st;
         st.push_back(Item{std::move(normal), 0});
-        int nthreads = (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+        int nthreads = host_threads();
         if (n < 100000) nthreads = 1;
         if (nthreads > 1) {
             // shared stack of large open subdomains; a worker keeps one side of every split for itself and hands
@@ -833,7 +864,10 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
     S.a_dst.resize(S.annz);
     S.a_sn.resize(S.annz);
     S.a_loc.resize(S.annz);
-    for (int c = 0; c < n; ++c) {
+    std::atomic<int> outside{0};          // 1: entry outside the L structure, 2: outside the U structure
+    const std::vector<int64_t> col_prefix(Ap, Ap + n + 1);
+    parallel_rows(n, col_prefix, [&](int cbeg, int cend) {     // every entry writes only its own slots
+    for (int c = cbeg; c < cend; ++c) {
         const int j = cinv[c];
         for (int64_t t = Ap[c]; t < Ap[c + 1]; ++t) {
             const int i = rinv[Ai[t]];
@@ -846,7 +880,7 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
                 if (i <= last) lr = i - c0;
                 else {
                     const int* it = std::lower_bound(rb, rb + r, i);
-                    if (it == rb + r || *it != i) { err = "internal: A entry outside L structure"; return SMSLU_E_INTERNAL; }
+                    if (it == rb + r || *it != i) { outside.store(1); return; }
                     lr = k + (it - rb);
                 }
                 S.a_dst[t] = S.Loff[s] + (int64_t)(j - c0) * f + lr;
@@ -854,12 +888,17 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
                 S.a_loc[t] = f < 65536 ? (int)(lr | ((int64_t)(j - c0) << 16)) : 0;
             } else {           // row in the pivot block, column beyond: U panel (stored transposed)
                 const int* it = std::lower_bound(rb, rb + r, j);
-                if (it == rb + r || *it != j) { err = "internal: A entry outside U structure"; return SMSLU_E_INTERNAL; }
+                if (it == rb + r || *it != j) { outside.store(2); return; }
                 S.a_dst[t] = S.Uoff[s] + (int64_t)(i - c0) * r + (it - rb);
                 S.a_sn[t] = s;
                 S.a_loc[t] = f < 65536 ? (int)((i - c0) | ((k + (it - rb)) << 16)) : 0;
             }
         }
+    }
+    });
+    if (outside.load()) {
+        err = outside.load() == 1 ? "internal: A entry outside L structure" : "internal: A entry outside U structure";
+        return SMSLU_E_INTERNAL;
     }
     step_mark("end");
     return 0;
