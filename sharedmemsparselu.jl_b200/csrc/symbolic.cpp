@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <condition_variable>
 #include <mutex>
+#include <system_error>
 #include <thread>
 #include <cmath>
 #include <cstring>
@@ -45,9 +46,14 @@ void parallel_rows(int n, const std::vector<int64_t>& prefix, F fn) {
     for (int t = 1; t < nthreads; ++t)
         cut[t] = (int)(std::lower_bound(prefix.begin(), prefix.begin() + n, total * t / nthreads) - prefix.begin());
     std::vector<std::thread> pool;
-    for (int t = 1; t < nthreads; ++t)
-        if (cut[t + 1] > cut[t]) pool.emplace_back(fn, cut[t], cut[t + 1]);
+    int started = 1;                       // ranges [1, started) run on their own threads
+    try {
+        for (; started < nthreads; ++started)
+            if (cut[started + 1] > cut[started]) pool.emplace_back(fn, cut[started], cut[started + 1]);
+    } catch (const std::system_error&) {}  // no more threads to be had: the rest runs here
     if (cut[1] > cut[0]) fn(cut[0], cut[1]);
+    for (int t = started; t < nthreads; ++t)
+        if (cut[t + 1] > cut[t]) fn(cut[t], cut[t + 1]);
     for (auto& th : pool) th.join();
 }
 
@@ -212,7 +218,9 @@ class GraphND {
                 }
             };
             std::vector<std::thread> pool;
-            for (int t = 1; t < nthreads; ++t) pool.emplace_back(worker);
+            try {
+                for (int t = 1; t < nthreads; ++t) pool.emplace_back(worker);
+            } catch (const std::system_error&) {}      // fewer workers, same result
             worker();
             for (auto& th : pool) th.join();
             return;
