@@ -127,3 +127,25 @@ def test_block_border_components_and_dense_rows(hostexec, O, W):
     assert np.array_equal(r["Li"], F.Li)
     assert relerr(r["Lx"], F.Lx) < 1e-11
     assert np.allclose(A @ r["x"], r["b"], rtol=1e-11, atol=1e-11)
+
+
+def test_analysis_does_not_depend_on_host_threads(smslu, W, monkeypatch):
+    """The ordering, the graph construction and the scatter map run on several host threads above a size
+    threshold (n >= 100 000, >= 2e6 entries); the layout must be identical for any thread count."""
+    from sharedmemsparselu_jl_b200 import _SymbolicOnly
+    A = W.laplacian_2d(720)                      # n = 518 400, 2.6e6 entries: every threaded path is taken
+    outs = []
+    for nthreads in ("1", "6", "3"):
+        monkeypatch.setenv("SMSLU_HOST_THREADS", nthreads)
+        F = _SymbolicOnly(A)
+        sym = F.symbolic()
+        st = F.stats()
+        outs.append((F.p.copy(), F.q.copy(), sym, {k: st[k] for k in ("n_supernodes", "n_levels", "nnz_l_exact",
+                                                                      "lu_pool_doubles", "cb_pool_doubles", "flops_exact")}))
+        F.close()
+    p0, q0, sym0, st0 = outs[0]
+    for p, q, sym, st in outs[1:]:
+        assert np.array_equal(p, p0) and np.array_equal(q, q0)
+        assert st == st0
+        for k in sym0:
+            assert np.array_equal(sym[k], sym0[k]), k
