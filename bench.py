@@ -2,20 +2,25 @@
 """bench.py -- LU refactorize+solve per second (Laplacian, Float64) on N B200s.
 
 One "step" = one numeric refactorization (`lu!`, new values, fixed pattern) followed by one
-`ldiv!` with a fresh right-hand side, through libsmslu.so.  N=1 workload = BASELINE.json
-configs[1]: 2D 5-point Laplacian 1024x1024 (n = 1 048 576), refactor input k = A + k*1e-3*I,
-b from splitmix64(47+k).
+`ldiv!` with a fresh right-hand side, through libsmslu.so.  Default workload at EVERY N = the
+north-star target, BASELINE.json configs[2]: 3D 7-point Laplacian 128^3 (n = 2 097 152), refactor
+input k = A + k*1e-3*I, b from splitmix64(47+k).  `--config lap2d_1024` gives configs[1] (the r01 line),
+`--config lap3d_96` the matrix of configs[4].
 
   value      : steps/s with nzval, b, x resident in HBM (stream-ordered calls, CUDA events on the
                launching stream, max over ranks)
   e2e        : same metric through the synchronous host API with pinned HOST buffers: H2D of nzval
                and b and D2H of x inside the timed region
   roofline   : the dominant kernel of the step (per-launch CUDA-event timing inside the library)
-  cpu_baseline / --impl reference : the CPU oracle port (oracle/ref_lu.c) on a bounded sample
+  parity     : x of the last timed step against an INDEPENDENT full-size solver (fast Poisson solver:
+               DST-I diagonalisation of the Dirichlet Laplacian), at every N -- so the multi-GPU path
+               carries a checker result, not only a residual
+  cpu_baseline / --impl reference : the CPU port of the path (oracle/ref_mf.cpp: multifrontal LU with the
+               same ordering, BLAS-3 fronts, all host cores) on a bounded sample of the same stencil.
+               The reference itself (Julia + UMFPACK) cannot run here.  The reference arm never loads
+               libsmslu.so.
 
-N>1 (torchrun): ONE factorization partitioned over the GPUs (strong scaling): every rank factors the
-subtrees it owns, the contributions to the top of the elimination tree (the coupling Schur complement)
-are summed with ncclAllReduce inside libsmslu.so, the top is factored by every rank.  `--replicas`
+N>1 (torchrun): ONE factorization partitioned over the GPUs (strong scaling).  `--replicas`
 runs one independent factorization per GPU instead (weak scaling).
 """
 import argparse
@@ -109,10 +114,45 @@ def measure_fp64_peak(torch):
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12
 
 
-def workload(grid):
-    from sharedmemsparselu_jl_b200 import workloads as W
-    A = W.laplacian_2d(grid)
-    return A, W
+CONFIGS = {
+    # name: (kind, edge, BASELINE.json config it is, reference-arm sample edge)
+    "lap3d_128": ("lap3d", 128, "BASELINE configs[2] = north-star target", 72),
+    "lap3d_96": ("lap3d", 96, "matrix of BASELINE configs[4]", 64),
+    "lap2d_1024": ("lap2d", 1024, "BASELINE configs[1]", 1024),
+}
+
+
+def load_workloads():
+    """workloads.py loaded by path: the reference arm must not import the product package (that would map
+    libsmslu.so into the process)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_smslu_workloads", os.path.join(ROOT, "sharedmemsparselu.jl_b200", "workloads.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def make_matrix(W, kind, edge):
+    return W.laplacian_3d(edge) if kind == "lap3d" else W.laplacian_2d(edge)
+
+
+def workload_string(cfg):
+    kind, edge, which, _ = CONFIGS[cfg]
+    if kind == "lap3d":
+        return "3D 7-point Laplacian %d^3 (n=%d) refactorize+solve, %s" % (edge, edge ** 3, which)
+    return "2D 5-point Laplacian %dx%d (n=%d) refactorize+solve, %s" % (edge, edge, edge * edge, which)
+
+
+def poisson_solve(kind, edge, shift, b):
+    """Independent full-size checker: the Dirichlet Laplacian (diag 2d, off-diagonals -1) is diagonalised
+    exactly by the type-I discrete sine transform; x = S^-1 (S b / (lambda_i + lambda_j (+ lambda_k) + shift))."""
+    import numpy as np
+    import scipy.fft as sfft
+    d = 3 if kind == "lap3d" else 2
+    lam1 = 2.0 - 2.0 * np.cos(np.arange(1, edge + 1) * np.pi / (edge + 1))
+    lam = lam1.reshape(-1, 1, 1) + lam1.reshape(1, -1, 1) + lam1.reshape(1, 1, -1) if d == 3 else lam1.reshape(-1, 1) + lam1.reshape(1, -1)
+    B = sfft.dstn(np.asarray(b, dtype=np.float64).reshape((edge,) * d), type=1, norm="ortho")
+    return sfft.idstn(B / (lam + shift), type=1, norm="ortho").reshape(-1)
 
 
 def algorithmic_work(F, A):
@@ -157,90 +197,104 @@ def algorithmic_work(F, A):
     return work, st
 
 
-def cpu_oracle_sample(sample_grid, full_flops):
-    """Oracle port timed on a smaller grid of the same stencil, scaled by the flop ratio."""
-    import numpy as np
-    import smslu
-    from sharedmemsparselu_jl_b200 import _SymbolicOnly, workloads as W
+def cpu_port_setup(cfg, sample_edge):
+    """The CPU port (oracle/ref_mf.cpp) analysed on the bounded sample; for an extrapolating sample also the exact
+    flop / nnz(L) counts of the FULL workload (host analysis only, nothing is factored at full size on the CPU)."""
     from oracle import oracle as O
-    As = W.laplacian_2d(sample_grid)
-    ns = As.shape[0]
-    S = _SymbolicOnly(As)                       # same ordering code as the GPU path (host only)
-    p, q = S.p.copy(), S.q.copy()
-    fl = S.stats()["flops_exact"]
-    S.close()
-    Rs = O.row_scale_sum(As)
-    t0 = time.perf_counter()
-    Fo = O.OracleLU(As, p=p, q=q, Rs=Rs)
-    t1 = time.perf_counter()
-    x = Fo.solve(W.rhs(ns, 47))
-    t2 = time.perf_counter()
-    scale = full_flops / fl
-    t_full = (t1 - t0) * scale + (t2 - t1) * scale ** 0.5
-    return {"value": 1.0 / t_full, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": "oracle/ref_lu.c left-looking LU + CSC solves on a %dx%d grid of the same stencil with the "
-                      "GPU path's ordering (%.2f s factor, %.3f s solve), factor time scaled by the flop ratio %.1f"
-                      % (sample_grid, sample_grid, t1 - t0, t2 - t1, scale),
-            "sample_seconds": t2 - t0}
+    W = load_workloads()
+    kind, edge, _, _ = CONFIGS[cfg]
+    As = make_matrix(W, kind, sample_edge)
+    Fs = O.RefMF(As)
+    if sample_edge == edge:
+        full = {"flops": Fs.flops, "nnzL": Fs.info["nnzL"]}
+    else:
+        Ff = O.RefMF(make_matrix(W, kind, edge))
+        full = {"flops": Ff.flops, "nnzL": Ff.info["nnzL"]}
+        Ff.close()
+    return W, As, Fs, full
 
 
-def superlu_standin(A, W):
-    """SciPy SuperLU (sequential) on the FULL workload: stand-in for the UMFPACK the reference calls
-    (src:74, 247 -- not installed here), with the ordering closest to UMFPACK's symmetric strategy."""
-    import scipy.sparse.linalg as spla
-    t0 = time.perf_counter()
-    lu = spla.splu(A, permc_spec="MMD_AT_PLUS_A", diag_pivot_thresh=0.0, options=dict(SymmetricMode=True))
-    t1 = time.perf_counter()
-    lu.solve(W.rhs(A.shape[0], 47))
-    t2 = time.perf_counter()
-    return {"value": 1.0 / (t2 - t0), "unit": UNIT, "cores": 1, "factor_s": t1 - t0, "solve_s": t2 - t1}
+def cpu_port_step(W, As, Fs, k):
+    """One refactorize+solve of the sample on the host cores; returns (refactor s, solve s, residual)."""
+    import numpy as np
+    n = As.shape[0]
+    vals = As.data.copy()
+    vals[np.flatnonzero(As.indices == np.repeat(np.arange(n), np.diff(As.indptr)))] += k * 1e-3
+    bad = Fs.lu_(vals)
+    b = W.rhs(n, 47 + k)
+    x = Fs.ldiv(b)
+    if bad != -1:
+        raise RuntimeError("CPU port met a bad pivot")
+    tf, ts = Fs.times()
+    Ak = As.copy(); Ak.data = vals
+    return tf, ts, float(np.linalg.norm(Ak @ x - b) / np.linalg.norm(b))
 
 
-def cpu_baseline(A, W, sample_grid, full_flops, with_oracle=True):
-    """CPU figure reported beside the GPU number.  The reference's factorization is UMFPACK's, which cannot
-    run here; two CPU implementations of the same path are timed on the host cores and the FASTER one is the
-    reported value (so the GPU/CPU ratio is not flattered by a slow baseline):
-      * SciPy SuperLU, full workload, 1 thread (library stand-in for UMFPACK);
-      * the oracle port oracle/ref_lu.c (Gilbert-Peierls, 1 thread) on a bounded sample, extrapolated."""
-    sl = superlu_standin(A, W)
-    out = {"value": sl["value"], "unit": UNIT, "cores": 1, "kind": "port",
-           "sample": "full workload (n=%d): scipy.sparse.linalg.splu(MMD_AT_PLUS_A, diagonal pivots) %.2f s + solve %.3f s, "
-                     "1 thread -- SuperLU standing in for the UMFPACK the reference calls (src:74, src:247; not installed here)"
-                     % (A.shape[0], sl["factor_s"], sl["solve_s"]),
-           "sample_seconds": sl["factor_s"] + sl["solve_s"]}
-    if with_oracle:
-        oc = cpu_oracle_sample(sample_grid, full_flops)
-        out["oracle_port"] = {"value": oc["value"], "sample": oc["sample"], "sample_seconds": oc["sample_seconds"]}
-        if oc["value"] > out["value"]:
-            out.update(value=oc["value"], sample=oc["sample"], sample_seconds=oc["sample_seconds"])
+def cpu_port_summary(cfg, sample_edge, Fs, full, tf, ts, nsteps):
+    kind, edge, _, _ = CONFIGS[cfg]
+    sf, sn = full["flops"] / Fs.flops, full["nnzL"] / float(Fs.info["nnzL"])
+    t_full = tf * sf + ts * sn
+    dim = "%d^3" % sample_edge if kind == "lap3d" else "%dx%d" % (sample_edge, sample_edge)
+    if sample_edge == edge:
+        sample = "the full workload, %d timed steps: refactor %.3f s + solve %.3f s per step" % (nsteps, tf, ts)
+    else:
+        sample = ("same stencil on a %s grid (n=%d), %d timed steps: refactor %.3f s + solve %.3f s per step; extrapolated to the "
+                  "full workload by the exact flop ratio %.1f (refactor) and nnz(L) ratio %.1f (solve) of the two analyses"
+                  % (dim, Fs.n, nsteps, tf, ts, sf, sn))
+    return {"value": 1.0 / t_full, "unit": UNIT, "cores": Fs.info["threads"], "kind": "port",
+            "what": "oracle/ref_mf.cpp: CPU multifrontal LU, static pivots, same nested-dissection ordering as the GPU path, "
+                    "BLAS-3 fronts (SciPy's OpenBLAS), OpenMP over fronts + threaded BLAS; numeric refactorization + solve only "
+                    "(analysis reused, as in lu!). A port, not the reference: Julia + UMFPACK are not installed here",
+            "sample": sample, "sample_seconds_per_step": tf + ts, "extrapolated_seconds_per_step": t_full,
+            "cpu_GFLOPs": Fs.flops / tf / 1e9}
+
+
+def cpu_baseline(cfg, sample_edge, nsteps=2):
+    W, As, Fs, full = cpu_port_setup(cfg, sample_edge)
+    cpu_port_step(W, As, Fs, 0)                                     # warm-up (page faults of the factor storage)
+    tfs, tss = [], []
+    for k in range(nsteps):
+        tf, ts, _ = cpu_port_step(W, As, Fs, k + 1)
+        tfs.append(tf); tss.append(ts)
+    out = cpu_port_summary(cfg, sample_edge, Fs, full, sum(tfs) / nsteps, sum(tss) / nsteps, nsteps)
+    Fs.close()
     return out
 
 
 # ----------------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
-    """--impl reference: the CPU port of the path (the reference is Julia+UMFPACK and cannot run
-    here: no oracle/_ref), on the host cores, bounded sample per step."""
+    """--impl reference: the reference's path on the host cores.  The reference itself (pure Julia calling UMFPACK)
+    cannot be built or run here (no oracle/_ref), so this arm times the oracle's CPU port on a bounded sample of the
+    workload, `warmup` untimed and `steps` timed sample steps.  It does not import the product package."""
     if rank != 0:
         return
-    import __graft_entry__ as ge
-    ge.build()
-    from sharedmemsparselu_jl_b200 import _SymbolicOnly
-    A, W = workload(args.grid)
-    S = _SymbolicOnly(A)
-    full_flops = S.stats()["flops_exact"]
-    S.close()
-    vals = []
-    nrun = max(1, min(args.steps, 3))                       # each run is a bounded sample (about 6-25 s of CPU work)
-    for i in range(nrun):
-        vals.append(cpu_baseline(A, W, args.sample_grid, full_flops, with_oracle=(i == 0)))
-    best = max(v["value"] for v in vals)
-    cb = dict(vals[0]); cb["value"] = best
-    out = {"impl": "reference", "metric": METRIC, "value": best, "unit": UNIT, "n_gpus": args.gpus,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / best, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "2D 5-point Laplacian %dx%d refactorize+solve (BASELINE configs[1])" % (args.grid, args.grid)},
-           "cpu_baseline": cb,
-           "e2e": {"value": best, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    from oracle import oracle as O
+    O.build_mf()
+    cfg = args.config
+    sample_edge = args.ref_size or CONFIGS[cfg][3]
+    t0 = time.perf_counter()
+    W, As, Fs, full = cpu_port_setup(cfg, sample_edge)
+    t_setup = time.perf_counter() - t0
+    for k in range(max(args.warmup, 1)):
+        cpu_port_step(W, As, Fs, k)
+    tfs, tss, res = [], [], 0.0
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        tf, ts, res = cpu_port_step(W, As, Fs, k)
+        tfs.append(tf); tss.append(ts)
+    wall = time.perf_counter() - t0
+    cb = cpu_port_summary(cfg, sample_edge, Fs, full, sum(tfs) / len(tfs), sum(tss) / len(tss), args.steps)
+    Fs.close()
+    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup,
+           # what this run actually timed per step (a sample step); the metric's value is per FULL-workload step
+           "ms_per_step": 1e3 * wall / args.steps,
+           "ms_per_step_full_workload_extrapolated": 1e3 * cb["extrapolated_seconds_per_step"],
+           "higher_is_better": True, "scaling": "strong" if (world > 1 and not args.replicas) else "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": workload_string(cfg)},
+           "cpu_baseline": cb, "setup_s": t_setup, "residual_sample": res,
+           "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
 
@@ -262,7 +316,10 @@ def run_ours(args, rank, world, local_rank):
     if dist:
         dist.barrier()
     import smslu
-    A, W = workload(args.grid)
+    from sharedmemsparselu_jl_b200 import workloads as W
+    cfg = args.config
+    kind, edge, _, ref_edge = CONFIGS[cfg]
+    A = make_matrix(W, kind, edge)
     n, nnz = A.shape[0], A.nnz
     K, Wu = args.steps, args.warmup
     NV = 4                                                 # distinct value sets cycled through the steps
@@ -315,6 +372,15 @@ def run_ours(args, rank, world, local_rank):
     Ak = sp.csc_matrix(A + ((K - 1) % NV) * 1e-3 * sp.identity(n))
     bk = W.rhs(n, 47 + (K - 1) % NV)
     residual = float(np.linalg.norm(Ak @ xk - bk) / np.linalg.norm(bk))
+    # independent full-size checker (every rank has the full x; rank 0 reports)
+    parity = None
+    if rank == 0:
+        xp = poisson_solve(kind, edge, ((K - 1) % NV) * 1e-3, bk)
+        parity = {"checker": "fast Poisson solver (DST-I diagonalisation of the Dirichlet Laplacian, scipy.fft), full size, "
+                             "independent of libsmslu.so and of the oracle",
+                  "x_relerr": float(np.linalg.norm(xk - xp) / np.linalg.norm(xp)),
+                  "x_max_abs_err": float(np.max(np.abs(xk - xp))),
+                  "checker_residual": float(np.linalg.norm(Ak @ xp - bk) / np.linalg.norm(bk))}
 
     # ---- end-to-end leg: synchronous host API, pinned host buffers ----------------------------
     vals_h = []
@@ -354,7 +420,7 @@ def run_ours(args, rank, world, local_rank):
     streamed_ms = None
     if not dist:
         try:
-            def _timed(fn, reps=5):
+            def _timed(fn, reps=3):
                 fn(0); F.sync(); torch.cuda.synchronize()
                 ea = torch.cuda.Event(enable_timing=True); eb = torch.cuda.Event(enable_timing=True)
                 ea.record(stream)
@@ -383,7 +449,7 @@ def run_ours(args, rank, world, local_rank):
     value = jobs * K / (ms_dev * 1e-3)
     e2e_value = jobs * K / (ms_e2e * 1e-3)
     step_ms_prof = sum(ms_kernel.values())
-    dom = max((k for k in ms_kernel if k in work), key=lambda k: ms_kernel[k])
+    dom = max((k for k in ms_kernel if k in work and k != "allreduce"), key=lambda k: ms_kernel[k])
     kinds = {}
     for kname, w in work.items():
         ms = ms_kernel.get(kname, 0.0)
@@ -429,7 +495,7 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak" if jobs == world else "strong",
         "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "2D 5-point Laplacian %dx%d (n=%d, nnz=%d) refactorize+solve, BASELINE configs[1]" % (args.grid, args.grid, n, nnz),
+        "config": {"workload": workload_string(cfg), "nnz_A": int(nnz),
                    "values": "A + k*1e-3*I, %d value sets cycled; b = splitmix64(47+k)" % NV,
                    "ordering": "nd_graph", "nnz_L": int(st0["nnz_l_exact"]), "flops_refactor": st0["flops_exact"],
                    "cache": "factor storage %.0f MB per step exceeds the 126 MB L2 (no explicit flush)" % (8e-6 * st0["lu_pool_doubles"]),
@@ -449,11 +515,11 @@ def run_ours(args, rank, world, local_rank):
                    "refactor_TFLOPs": st0["flops_exact"] / (refac_ms * 1e-3) / 1e12,
                    "solve_GBs": solve_bytes / (solve_ms * 1e-3) / 1e9, "solve_frac_hbm": solve_bytes / (solve_ms * 1e-3) / 1e9 / hbm_gbs},
         "phases_streamed": phases_streamed,
-        "residual": residual, "setup_s": t_setup,
+        "residual": residual, "parity": parity, "parity_x_relerr": parity["x_relerr"], "setup_s": t_setup,
         "host_overhead": {"wall_ms_per_step_kernel_leg": wall_dev * 1e3 / K},
     }
     if not args.no_cpu:
-        out["cpu_baseline"] = cpu_baseline(A, W, args.sample_grid, st0["flops_exact"], with_oracle=args.oracle_sample)
+        out["cpu_baseline"] = cpu_baseline(cfg, args.ref_size or ref_edge, nsteps=2)
     F.close()
     print(json.dumps(out), flush=True)
     if dist:
@@ -466,10 +532,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--grid", type=int, default=1024, help="2D grid edge (default: BASELINE configs[1])")
-    ap.add_argument("--sample-grid", type=int, default=320, help="grid edge of the oracle port's bounded sample")
+    ap.add_argument("--config", default="lap3d_128", choices=sorted(CONFIGS), help="workload (default: the north-star target, BASELINE configs[2])")
+    ap.add_argument("--ref-size", type=int, default=0, help="grid edge of the CPU port's bounded sample (default: per config)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--oracle-sample", action="store_true", help="cpu_baseline: also time the oracle port on the bounded sample grid")
     ap.add_argument("--replicas", action="store_true", help="N>1: independent factorization per GPU instead of one partitioned factorization")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

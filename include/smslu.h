@@ -36,6 +36,10 @@ extern "C" {
 #define SMSLU_E_OOM (-6)
 #define SMSLU_E_INTERNAL (-7)
 #define SMSLU_E_NCCL (-8)
+#define SMSLU_E_REPIVOT (-9)  /* the factorization finished, but a multiplier |l_ij| exceeded 1/pivot_tol: the static pivot
+                                 order fails UMFPACK's threshold test for these values.  The reference's lu! would re-pivot
+                                 (src:245-279, pattern may change: src:252-273); here the caller re-analyses with fresh
+                                 (p, q) -- both host mirrors do that automatically.  The factors stay usable.          */
 
 #define SMSLU_ORD_AUTO 0      /* ND_GRID when the grid hint matches n, else ND_GRAPH              */
 #define SMSLU_ORD_NATURAL 1
@@ -56,10 +60,13 @@ typedef struct smslu_options {
     int32_t max_width;       /* pivot-block width of a front (<= 128); wider supernodes are chained */
     int32_t scaling;         /* SMSLU_SCALE_*, used when smslu_refactor gets Rs == NULL        */
     int32_t device;          /* CUDA device ordinal; -1 = current device                       */
-    int32_t use_graph;       /* reserved (ignored): launch cost is hidden behind the kernels   */
+    int32_t reserved0;       /* unused (keeps the layout of version 1.0)                        */
     int32_t nranks;          /* GPUs (= processes) the elimination tree is partitioned over; 0/1 = one GPU */
     int32_t rank;            /* this process' rank in [0, nranks)                                */
-    int32_t reserved[6];
+    double pivot_tol;        /* threshold test of the static pivots: SMSLU_E_REPIVOT when some |l_ij| > 1/pivot_tol, i.e.
+                                |u_jj| < pivot_tol * max_i |a_ij| in column j.  0 = default 1e-3 (UMFPACK's tolerance for
+                                diagonal pivots in its symmetric strategy); negative = no test                       */
+    int32_t reserved[4];
 } smslu_options_t;
 
 typedef struct smslu_stats {
@@ -81,7 +88,8 @@ typedef struct smslu_stats {
     int64_t n_local_supernodes;         /*   supernodes owned by this rank                                */
     int64_t allreduce_doubles_refactor; /*   doubles summed across ranks per refactorization / per solve  */
     int64_t allreduce_doubles_solve;
-    int64_t reserved[4];
+    int64_t threshold_col;              /* first permuted column of a front whose multipliers failed the threshold test, or -1 */
+    int64_t reserved[3];
 } smslu_stats_t;
 
 /* kernel kinds for ms_kernel / launches_kernel */

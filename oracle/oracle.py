@@ -219,3 +219,144 @@ class RefChunks:
             self.close()
         except Exception:
             pass
+
+
+# ----------------------------------------------------------------------------------------------
+# Threaded CPU multifrontal port (oracle/ref_mf.cpp): the CPU side of bench.py's comparison.
+_MF_LIB = os.path.join(_HERE, "_build", "libref_mf.so")
+_MF_SRC = [os.path.join(_HERE, "ref_mf.cpp"),
+           os.path.join(os.path.dirname(_HERE), "sharedmemsparselu.jl_b200", "csrc", "symbolic.cpp")]
+_MF_HDR = [os.path.join(os.path.dirname(_HERE), "sharedmemsparselu.jl_b200", "csrc", "symbolic.hpp")]
+
+
+# OpenMP threads that spin after a parallel region starve the BLAS threads of the next call (measured: 13x slower)
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+
+
+def build_mf(force: bool = False) -> str:
+    """g++ -fopenmp: ref_mf.cpp + the host-only analysis source csrc/symbolic.cpp (no kernels, no libsmslu.so)."""
+    stale = force or not os.path.exists(_MF_LIB) or any(
+        os.path.getmtime(s) > os.path.getmtime(_MF_LIB) for s in _MF_SRC + _MF_HDR)
+    if stale:
+        os.makedirs(os.path.dirname(_MF_LIB), exist_ok=True)
+        tmp = _MF_LIB + ".%d.tmp" % os.getpid()
+        subprocess.check_call(["g++", "-O3", "-fopenmp", "-pthread", "-fPIC", "-std=c++17", "-shared",
+                               "-o", tmp] + _MF_SRC)
+        os.replace(tmp, _MF_LIB)
+    return _MF_LIB
+
+
+_mf = None
+
+
+def _blas_ptr(name):
+    """Address of SciPy's bundled OpenBLAS routine (scipy.linalg.cython_blas capsule)."""
+    import scipy.linalg.cython_blas as cb
+    cap = cb.__pyx_capi__[name]
+    C.pythonapi.PyCapsule_GetName.restype = C.c_char_p
+    C.pythonapi.PyCapsule_GetName.argtypes = [C.py_object]
+    C.pythonapi.PyCapsule_GetPointer.restype = C.c_void_p
+    C.pythonapi.PyCapsule_GetPointer.argtypes = [C.py_object, C.c_char_p]
+    return C.pythonapi.PyCapsule_GetPointer(cap, C.pythonapi.PyCapsule_GetName(cap))
+
+
+def _blas_set_threads_ptr():
+    """openblas_set_num_threads of the OpenBLAS behind scipy.linalg (so that the fronts handled one per
+    OpenMP thread call BLAS on the calling thread only); None if it cannot be found."""
+    try:
+        import scipy.linalg  # noqa: F401  (loads the library)
+        from threadpoolctl import threadpool_info
+        for info in threadpool_info():
+            if info.get("internal_api") != "openblas" or "scipy.libs" not in info.get("filepath", ""):
+                continue
+            L = C.CDLL(info["filepath"])
+            for nm in ("scipy_openblas_set_num_threads", "openblas_set_num_threads"):
+                if hasattr(L, nm):
+                    return C.cast(getattr(L, nm), C.c_void_p)
+    except Exception:
+        pass
+    return None
+
+
+def mf_lib():
+    global _mf
+    if _mf is None:
+        L = C.CDLL(build_mf())
+        L.mf_create.restype = C.c_void_p
+        L.mf_create.argtypes = [C.c_longlong, _i64p, _i64p, C.c_int, C.c_void_p, C.c_int]
+        L.mf_set_blas.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mf_free.argtypes = [C.c_void_p]
+        L.mf_info.argtypes = [C.c_void_p, _i64p, _f64p]
+        L.mf_perm.argtypes = [C.c_void_p, _i64p, _i64p]
+        L.mf_factor.restype = C.c_longlong
+        L.mf_factor.argtypes = [C.c_void_p, _f64p, C.c_void_p, _f64p]
+        L.mf_solve.argtypes = [C.c_void_p, _f64p, _f64p]
+        L.mf_times.argtypes = [C.c_void_p, _f64p]
+        L.mf_get_factors.argtypes = [C.c_void_p, _i64p, _i64p, _f64p, _i64p, _i64p, _f64p, _f64p]
+        _mf = L
+    return _mf
+
+
+class RefMF:
+    """CPU multifrontal LU (static diagonal pivots under the same nested-dissection ordering and
+    supernodes as the GPU path, BLAS-3 fronts, all host cores).  ``lu_(Ax)`` = numeric
+    refactorization with the analysis reused (reference src:245-279), ``ldiv(b)`` = src:286-342."""
+
+    def __init__(self, A, grid=None, threads=0, blas=True):
+        n, Ap, Ai, Ax = _csc(A)
+        self.n, self._Ap, self._Ai = n, Ap, Ai
+        g = None if grid is None else np.array(list(grid) + [1] * (3 - len(grid)), dtype=np.int32)
+        self._h = mf_lib().mf_create(n, Ap, Ai, 0, None if g is None else g.ctypes.data_as(C.c_void_p), int(threads))
+        if not self._h:
+            raise RuntimeError("mf_create failed")
+        if blas:
+            mf_lib().mf_set_blas(self._h, _blas_ptr("dgemm"), _blas_ptr("dtrsm"), _blas_set_threads_ptr())
+        info = np.zeros(8, np.int64); fl = np.zeros(1)
+        mf_lib().mf_info(self._h, info, fl)
+        self.info = dict(zip(("n", "nsn", "nlevels", "nnzL", "lu_size", "threads", "big_fronts", "max_front"), map(int, info)))
+        self.flops = float(fl[0])
+        self.growth = 0.0
+
+    def lu_(self, Ax, Rs=None):
+        Ax = np.ascontiguousarray(Ax, np.float64)
+        rs = None if Rs is None else np.ascontiguousarray(Rs, np.float64)
+        g = np.zeros(1)
+        bad = mf_lib().mf_factor(self._h, Ax, None if rs is None else rs.ctypes.data_as(C.c_void_p), g)
+        self.growth = float(g[0])
+        return int(bad)
+
+    def ldiv(self, b):
+        b = np.ascontiguousarray(b, np.float64)
+        x = np.empty(self.n)
+        mf_lib().mf_solve(self._h, b, x)
+        return x
+
+    def times(self):
+        t = np.zeros(2)
+        mf_lib().mf_times(self._h, t)
+        return float(t[0]), float(t[1])
+
+    def perm(self):
+        p = np.zeros(self.n, np.int64); q = np.zeros(self.n, np.int64)
+        mf_lib().mf_perm(self._h, p, q)
+        return p, q
+
+    def factors(self):
+        import scipy.sparse as sp
+        n, nl = self.n, self.info["nnzL"]
+        Lp = np.zeros(n + 1, np.int64); Li = np.zeros(nl, np.int64); Lx = np.zeros(nl)
+        Up = np.zeros(n + 1, np.int64); Ui = np.zeros(nl, np.int64); Ux = np.zeros(nl)
+        Rs = np.zeros(n)
+        mf_lib().mf_get_factors(self._h, Lp, Li, Lx, Up, Ui, Ux, Rs)
+        return sp.csc_matrix((Lx, Li, Lp), shape=(n, n)), sp.csc_matrix((Ux, Ui, Up), shape=(n, n)), Rs
+
+    def close(self):
+        if self._h:
+            mf_lib().mf_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

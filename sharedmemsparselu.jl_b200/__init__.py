@@ -18,11 +18,11 @@ import ctypes as C
 import numpy as np
 
 from . import _capi
-from ._capi import DimensionMismatch, SingularException, SmsluError  # noqa: F401
+from ._capi import DimensionMismatch, PivotThresholdError, SingularException, SmsluError  # noqa: F401
 
 __all__ = ["ParallelSparseLU", "lu_", "ldiv_", "lsolve_", "rsolve_", "cleanup_ParallelSparseLU_",
-           "allocate_shared", "pinned_empty", "comm_unique_id", "DimensionMismatch", "SingularException",
-           "SmsluError"]
+           "allocate_shared", "pinned_empty", "comm_unique_id", "host_pivots", "DimensionMismatch", "SingularException",
+           "PivotThresholdError", "SmsluError"]
 
 
 def comm_unique_id() -> bytes:
@@ -33,6 +33,23 @@ def comm_unique_id() -> bytes:
     if rc != 0:
         raise _capi.SmsluError(rc, "smslu_comm_unique_id failed")
     return buf.raw
+
+
+def host_pivots(A, pivot_tol=1.0e-3):
+    """Host pivot search: (p, q, Rs) with a threshold-pivoted L*U == (Rs .* A)[p, q].
+
+    What the Julia shim gets from UMFPACK's ``lu(A)`` (src:74) -- ordering, threshold partial pivoting with
+    a preference for the diagonal, row scaling Rs = 1/sum_j|a_ij| -- comes here from SciPy's SuperLU (UMFPACK is
+    not installed): COLAMD column ordering, diagonal preferred when it passes ``pivot_tol``.  Only the
+    permutations are used; every factor entry is then computed on the GPU under that static pivot order."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    A = sp.csc_matrix(A)
+    rs = np.asarray(abs(A).sum(axis=1)).ravel()
+    Rs = np.where(rs > 0, 1.0 / np.where(rs > 0, rs, 1.0), 1.0)
+    B = sp.csc_matrix(sp.diags(Rs) @ A)
+    lu = spla.splu(B, permc_spec="COLAMD", diag_pivot_thresh=float(pivot_tol), options=dict(Equil=False))
+    return np.argsort(lu.perm_r).astype(np.int64), np.argsort(lu.perm_c).astype(np.int64), Rs
 
 
 def _ptr(a):
@@ -110,14 +127,50 @@ class ParallelSparseLU:
     ``A`` / ``b`` and receives the full ``x``; ``F.L`` / ``F.U`` hold this rank's share of the values.
     """
 
-    def __init__(self, A, chunk_size=None, *, ordering="auto", grid=None, p=None, q=None, Rs=None,
+    def __init__(self, A, chunk_size=None, *, pivots="auto", ordering="auto", grid=None, p=None, q=None, Rs=None,
                  scaling="sum", nd_leaf=None, relax=True, max_width=None, device=None,
-                 nranks=1, rank=0, comm_id=None):
+                 nranks=1, rank=0, comm_id=None, pivot_tol=None):
         import scipy.sparse as sp
         if not sp.isspmatrix_csc(A):
             raise TypeError("A must be a scipy.sparse.csc_matrix (SparseMatrixCSC)")
         if A.shape[0] != A.shape[1]:
             raise DimensionMismatch(_capi.E_DIM, "matrix is not square")
+        if pivots not in ("auto", "native", "host"):
+            raise ValueError("pivots must be 'auto', 'native' or 'host'")
+        # pivots: "native" = the library's nested-dissection ordering with diagonal pivots, never re-pivoted (a failed
+        # threshold test raises PivotThresholdError); "host" = pivot search on the host (host_pivots) at construction and
+        # again whenever lu_ fails the threshold test; "auto" = native first, host pivots when the test fails.
+        self._pivots = pivots if (p is None and nranks == 1) else "native"
+        self._ctor = dict(ordering=ordering, grid=grid, scaling=scaling, nd_leaf=nd_leaf, relax=relax, max_width=max_width,
+                          device=device, nranks=nranks, rank=rank, comm_id=comm_id, pivot_tol=pivot_tol)
+        self._h = None
+        if self._pivots == "host":
+            p, q, Rs = host_pivots(A, 1.0e-3 if pivot_tol in (None, 0) else abs(pivot_tol))
+        try:
+            self._setup(A, chunk_size, p, q, Rs)
+        except (PivotThresholdError, SingularException):
+            if self._pivots != "auto":
+                raise
+            self._repivot(A)
+
+    def _repivot(self, A):
+        """The static pivot order failed for these values: fresh host pivot search, re-analysis, refactorization
+        (the reference's lu! lets UMFPACK re-pivot and re-chunks when the pattern of L/U changed, src:252-273)."""
+        import scipy.sparse as sp
+        A = sp.csc_matrix((A.data, self._rowval, self._colptr), shape=(self.n, self.n)) if not hasattr(A, "indptr") else A
+        tol = self._ctor["pivot_tol"]
+        try:
+            p, q, Rs = host_pivots(A, 1.0e-3 if tol in (None, 0) else abs(tol))
+        except RuntimeError as exc:              # SuperLU: "Factor is exactly singular"
+            raise SingularException(_capi.E_PIVOT, "host pivot search: %s" % exc) from None
+        self.close()
+        self._pivots = "host"
+        self._setup(A, self.chunk_size, p, q, Rs)
+
+    def _setup(self, A, chunk_size, p, q, Rs):
+        ordering, grid, scaling, nd_leaf, relax, max_width, device, nranks, rank, comm_id, pivot_tol = (
+            self._ctor[k] for k in ("ordering", "grid", "scaling", "nd_leaf", "relax", "max_width", "device", "nranks",
+                                    "rank", "comm_id", "pivot_tol"))
         L = _capi.lib()
         self.chunk_size = 8 if chunk_size is None else chunk_size   # kept, unused
         self.m = self.n = int(A.shape[0])
@@ -143,6 +196,8 @@ class ParallelSparseLU:
         if device is not None:
             opts.device = int(device)
         opts.nranks, opts.rank = int(nranks), int(rank)
+        if pivot_tol is not None:
+            opts.pivot_tol = float(pivot_tol)
         self.nranks, self.rank = int(nranks), int(rank)
         self._h = C.c_void_p()
         rc = L.smslu_create(C.byref(self._h), self.n, _ptr(self._colptr), _ptr(self._rowval), 0, C.byref(opts))
@@ -155,7 +210,13 @@ class ParallelSparseLU:
             _capi.check(self._h, L.smslu_comm_init(self._h, C.c_char_p(bytes(comm_id)), len(comm_id)))
         self._Rs_given = None if Rs is None else np.ascontiguousarray(Rs, dtype=np.float64)
         self._cache = {}
+        self._constructed = False
         self._numeric(A)
+        self._constructed = True
+        # lu!(F, A) with new values: the row scaling is recomputed from them (UMFPACK's lu! does the same), unless the
+        # caller fixed the whole contract (p, q, Rs) explicitly
+        if self._pivots == "host":
+            self._Rs_given = None
 
     # -- numeric (re)factorization -------------------------------------------------------------
     def _numeric(self, A):
@@ -171,7 +232,14 @@ class ParallelSparseLU:
         else:           # raw nzval (numpy / pinned / torch CUDA tensor), same pattern
             vals = _check_f64(A, "nzval")
         self._cache = {}
-        _capi.check(self._h, _capi.lib().smslu_refactor(self._h, _ptr(vals), _ptr(self._Rs_given)))
+        try:
+            _capi.check(self._h, _capi.lib().smslu_refactor(self._h, _ptr(vals), _ptr(self._Rs_given)))
+        except (PivotThresholdError, SingularException):
+            # constructor: handled there.  lu!(F, A) with values that break the current pivots: re-pivot on the host
+            if self._pivots == "native" or not getattr(self, "_constructed", False) or hasattr(vals, "data_ptr"):
+                raise
+            import scipy.sparse as sp
+            self._repivot(sp.csc_matrix((np.asarray(vals), self._rowval, self._colptr), shape=(self.n, self.n)))
 
     # -- fields ----------------------------------------------------------------------------------
     def _factors(self):

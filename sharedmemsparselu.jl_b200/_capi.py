@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SMSLU_LIB") or os.path.join(HERE, "libsmslu.so")   # SMSLU_LIB: A/B testing of builds
 
-OK, E_DIM, E_PIVOT, E_PATTERN, E_ARG, E_CUDA, E_OOM, E_INTERNAL, E_NCCL = 0, -1, -2, -3, -4, -5, -6, -7, -8
+OK, E_DIM, E_PIVOT, E_PATTERN, E_ARG, E_CUDA, E_OOM, E_INTERNAL, E_NCCL, E_REPIVOT = 0, -1, -2, -3, -4, -5, -6, -7, -8, -9
 ORD = {"auto": 0, "natural": 1, "given": 2, "nd_graph": 3, "nd_grid": 4}
 SCALE = {"none": 0, "sum": 1}
 
@@ -28,8 +28,8 @@ KERNEL_KINDS = ["rowscale", "scatter", "zero_cb", "extend_add", "front_small", "
 class Options(C.Structure):
     _fields_ = [("ordering", C.c_int32), ("grid", C.c_int32 * 3), ("nd_leaf", C.c_int32),
                 ("relax", C.c_int32), ("max_width", C.c_int32), ("scaling", C.c_int32),
-                ("device", C.c_int32), ("use_graph", C.c_int32), ("nranks", C.c_int32), ("rank", C.c_int32),
-                ("reserved", C.c_int32 * 6)]
+                ("device", C.c_int32), ("reserved0", C.c_int32), ("nranks", C.c_int32), ("rank", C.c_int32),
+                ("pivot_tol", C.c_double), ("reserved", C.c_int32 * 4)]
 
 
 class Stats(C.Structure):
@@ -41,8 +41,8 @@ class Stats(C.Structure):
             "ms_refactor_h2d", "ms_solve_h2d", "ms_solve_d2h")] + [(k, C.c_int64) for k in (
                 "launches_refactor", "launches_solve", "n_refactor", "n_solve", "bad_pivot_col")] + [
         ("ms_kernel", C.c_double * 16), ("launches_kernel", C.c_int64 * 16)] + [(k, C.c_int64) for k in (
-            "n_top_supernodes", "n_local_supernodes", "allreduce_doubles_refactor", "allreduce_doubles_solve")] + [
-        ("reserved", C.c_int64 * 4)]
+            "n_top_supernodes", "n_local_supernodes", "allreduce_doubles_refactor", "allreduce_doubles_solve",
+            "threshold_col")] + [("reserved", C.c_int64 * 3)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k not in ("reserved", "ms_kernel", "launches_kernel")}
@@ -63,6 +63,11 @@ class DimensionMismatch(SmsluError, ValueError):
 
 class SingularException(SmsluError, ArithmeticError):
     """SMSLU_E_PIVOT -- zero pivot under the static pivot order."""
+
+
+class PivotThresholdError(SmsluError):
+    """SMSLU_E_REPIVOT -- the factorization finished, but a multiplier exceeded 1/pivot_tol: the static pivot order
+    fails the threshold test for these values (UMFPACK's lu! would re-pivot here, src:245-279)."""
 
 
 _lib = None
@@ -117,4 +122,6 @@ def check(h, rc):
         raise DimensionMismatch(rc, msg)
     if rc == E_PIVOT:
         raise SingularException(rc, msg)
+    if rc == E_REPIVOT:
+        raise PivotThresholdError(rc, msg)
     raise SmsluError(rc, msg)

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <chrono>
 #include <climits>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -108,6 +109,7 @@ struct smslu_handle_s {
     const double* cur_av = nullptr;      // device nzval of the refactorization being enqueued
     int64_t *d_rowptr = nullptr, *d_rowidx = nullptr;
     int *d_p = nullptr, *d_q = nullptr;
+    int* d_post = nullptr;               // ORD_GIVEN with a relabelling postorder: caller position of internal index (else null)
     double *d_Rs = nullptr, *d_aval = nullptr, *d_w = nullptr, *d_z = nullptr, *d_xb = nullptr;
     int4* d_tasks = nullptr;
     int2* d_inv_tasks = nullptr;        // (front, 32-column block) pairs of k_diag_inverse
@@ -431,7 +433,7 @@ int ensure_uploaded(smslu_handle_t h) {
     }
     CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_scatter, cudaEventDisableTiming));
-    CU(cudaMallocHost((void**)&h->h_flag, sizeof(int)));
+    CU(cudaMallocHost((void**)&h->h_flag, 2 * sizeof(int)));
     CU(cudaEventCreate(&h->ev0)); CU(cudaEventCreate(&h->ev1));
     CU(cudaEventCreate(&h->ev2)); CU(cudaEventCreate(&h->ev3));
     const Symbolic& S = h->S;
@@ -488,6 +490,7 @@ int ensure_uploaded(smslu_handle_t h) {
     if ((rc = dev_upload(h, &d_child_idx, child_idx_d))) return rc;
     if ((rc = dev_upload(h, &h->d_p, S.p))) return rc;
     if ((rc = dev_upload(h, &h->d_q, S.q))) return rc;
+    if (!S.post.empty() && (rc = dev_upload(h, &h->d_post, S.post))) return rc;
     {   // row index of every nonzero (for the scaling) and a row-major view of the pattern
         std::vector<int64_t> rowptr(n + 1, 0), rowidx(h->annz);
         for (int64_t t = 0; t < h->annz; ++t) ++rowptr[h->Ai[t] + 1];
@@ -535,7 +538,7 @@ int ensure_uploaded(smslu_handle_t h) {
     if ((rc = dev_alloc(h, &d_lu, (size_t)S.lu_size))) return rc;
     if ((rc = dev_alloc(h, &d_cb, (size_t)S.cb_size))) return rc;
     if ((rc = dev_alloc(h, &d_upd, (size_t)(S.sum_r + h->vupd_len) * RB_MAX))) return rc;
-    if ((rc = dev_alloc(h, &d_flag, 1))) return rc;
+    if ((rc = dev_alloc(h, &d_flag, 2))) return rc;
     if ((rc = dev_alloc(h, &d_dinv, (size_t)n))) return rc;
     if ((rc = dev_alloc(h, &h->d_Rs, (size_t)n))) return rc;
     if ((rc = dev_alloc(h, &h->d_aval, (size_t)h->annz))) return rc;
@@ -579,6 +582,10 @@ int ensure_uploaded(smslu_handle_t h) {
     cx.lu = d_lu; cx.cb = d_cb; cx.upd = d_upd; cx.counters = d_counters; cx.flag = d_flag;
     cx.bpart = d_bpart; cx.counters2 = d_counters2; cx.dinv = d_dinv;
     cx.Doff = d_Doff; cx.dblk = d_dblk;
+    {
+        const double tol = h->opt.pivot_tol == 0.0 ? 1.0e-3 : h->opt.pivot_tol;
+        cx.lmax = tol > 0.0 ? (1.0 + 1.0e-6) / tol : HUGE_VAL;   // a hair above 1/tol: pivots chosen by a host threshold search pass
+    }
     cx.a_ptr = d_a_ptr; cx.a_src = d_a_src; cx.a_row = d_a_row; cx.a_pos = d_a_pos;
     CU(cudaDeviceSynchronize());
     h->uploaded = true;
@@ -707,7 +714,7 @@ int enqueue_refactor(smslu_handle_t h, const double* av, bool rs_given) {
         if ((rc = prof_end(h))) return rc;
     }
     if ((rc = prof_begin(h, SMSLU_K_SCATTER))) return rc;
-    CU(cudaMemsetAsync(h->cx.flag, 0x7f, sizeof(int), h->stream));   // 0x7f7f7f7f = clean
+    CU(cudaMemsetAsync(h->cx.flag, 0x7f, 2 * sizeof(int), h->stream));   // 0x7f7f7f7f = clean
     CU(cudaMemsetAsync(h->cx.counters, 0, sizeof(int) * std::max<int64_t>(h->ncounters, 1), h->stream));
     // The zero-fill and scatter of the big fronts' panels only matter from the first level that has a big front:
     // they run on the big-front lane's stream while the main stream starts on the small-front levels.
@@ -737,13 +744,13 @@ int enqueue_refactor(smslu_handle_t h, const double* av, bool rs_given) {
         NCCLCHK(nccl_api().GroupEnd());
         if ((rc = prof_end(h))) return rc;
         if ((rc = run_schedule(h, h->fac_top, nullptr, nullptr))) return rc;
-        NCCLCHK(nccl_api().AllReduce(h->cx.flag, h->cx.flag, 1, ncclInt, ncclMin, h->comm, h->stream));
+        NCCLCHK(nccl_api().AllReduce(h->cx.flag, h->cx.flag, 2, ncclInt, ncclMin, h->comm, h->stream));
     }
     // the solves apply the 32 x 32 diagonal blocks of the big fronts through their inverses
     if ((rc = prof_begin(h, SMSLU_K_PANEL))) return rc;
     launch_diag_inverse(h->stream, h->cx, h->d_inv_tasks, h->n_inv_tasks);
     if ((rc = prof_end(h))) return rc;
-    CU(cudaMemcpyAsync(h->h_flag, h->cx.flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(h->h_flag, h->cx.flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     h->pending_refactor = true;
     return 0;
 }
@@ -769,6 +776,15 @@ int finish_refactor(smslu_handle_t h) {
     }
     h->st.bad_pivot_col = -1;
     h->factored = true;
+    const int tflag = h->h_flag[1];
+    h->st.threshold_col = tflag != FLAG_CLEAN ? tflag : -1;
+    if (tflag != FLAG_CLEAN) {
+        // the factors are complete and usable, but the static pivots fail the threshold test for these values
+        char buf[240];
+        snprintf(buf, sizeof buf, "a multiplier exceeds 1/pivot_tol = %.3g in the front starting at permuted column %d: the static "
+                 "pivot order fails the threshold test for these values; re-analyse with fresh pivots", h->cx.lmax, tflag);
+        return fail(h, SMSLU_E_REPIVOT, buf);
+    }
     return 0;
 }
 
@@ -844,7 +860,7 @@ int smslu_options_default(smslu_options_t* o) {
     o->max_width = KMAX;
     o->scaling = SMSLU_SCALE_SUM;
     o->device = -1;
-    o->use_graph = 0;
+    o->pivot_tol = 0.0;   // = 1e-3
     return 0;
 }
 
@@ -871,6 +887,7 @@ int smslu_create(smslu_handle_t* hp, int64_t n, const int64_t* colptr, const int
     h->st.n = n;
     h->st.nnz_a = h->annz;
     h->st.bad_pivot_col = -1;
+    h->st.threshold_col = -1;
     *hp = h;
     return 0;
 }
@@ -984,6 +1001,7 @@ int smslu_refactor_async(smslu_handle_t h, const double* nzval_dev, const double
     if (Rs_dev) CU(cudaMemcpyAsync(h->d_Rs, Rs_dev, sizeof(double) * h->n, cudaMemcpyDeviceToDevice, h->stream));
     else if (h->opt.scaling != SMSLU_SCALE_SUM) return fail(h, SMSLU_E_ARG, "async refactor needs Rs or SUM scaling");
     h->st.launches_refactor = refactor_launches(h) + ((!Rs_dev) ? 1 : 0);
+    h->factored = false;                       // valid again once smslu_sync has seen the pivot flags
     return enqueue_refactor(h, nzval_dev, Rs_dev != nullptr);
 }
 
@@ -1041,7 +1059,7 @@ int smslu_solve(smslu_handle_t h, double* x, int64_t nx, const double* b, int64_
     int rc;
     if ((rc = check_vec(h, nx, nrhs, ldx, "x"))) return rc;
     if ((rc = check_vec(h, nb, nrhs, ldb, "b"))) return rc;
-    if (h->pending_refactor && (rc = smslu_sync(h))) return rc;
+    if (h->pending_refactor && (rc = smslu_sync(h)) && rc != SMSLU_E_REPIVOT) return rc;
     if (!h->factored) return fail(h, SMSLU_E_ARG, "no valid factorization (call smslu_refactor)");
     if ((rc = ensure_uploaded(h))) return rc;
     const int n = h->n;
@@ -1082,6 +1100,7 @@ static int tri_solve(smslu_handle_t h, double* x, int64_t nx, int64_t nrhs, int6
     if (!h || !x) return SMSLU_E_ARG;
     int rc;
     if ((rc = check_vec(h, nx, nrhs, ld, "x"))) return rc;
+    if (h->pending_refactor && (rc = smslu_sync(h)) && rc != SMSLU_E_REPIVOT) return rc;
     if (!h->factored) return fail(h, SMSLU_E_ARG, "no valid factorization (call smslu_refactor)");
     if ((rc = ensure_uploaded(h))) return rc;
     const int n = h->n;
@@ -1098,16 +1117,16 @@ static int tri_solve(smslu_handle_t h, double* x, int64_t nx, int64_t nrhs, int6
         }
         // interleave the block (identity permutation, no scaling), sweep, de-interleave
         if (lower) {
-            launch_permute_scale(h->stream, n, nullptr, nullptr, src, lsrc, h->d_w, rb, nv);
+            launch_permute_scale(h->stream, n, h->d_post, nullptr, src, lsrc, h->d_w, rb, nv);
             if ((rc = run_schedule(h, h->fwd, h->d_w, h->d_z, rb))) return rc;
             if (h->nranks > 1 && (rc = enqueue_top_forward(h, rb))) return rc;
         } else {
-            launch_permute_scale(h->stream, n, nullptr, nullptr, src, lsrc, h->d_z, rb, nv);
+            launch_permute_scale(h->stream, n, h->d_post, nullptr, src, lsrc, h->d_z, rb, nv);
             if (h->nranks > 1 && (rc = run_schedule(h, h->bwd_top, nullptr, h->d_z, rb))) return rc;
             if ((rc = run_schedule(h, h->bwd, nullptr, h->d_z, rb))) return rc;
         }
         if (h->nranks > 1 && (rc = enqueue_gather_solution(h, rb))) return rc;
-        launch_unpermute(h->stream, n, nullptr, h->d_z, dev ? xc : h->d_xb, dev ? ld : n, rb, nv);
+        launch_unpermute(h->stream, n, h->d_post, h->d_z, dev ? xc : h->d_xb, dev ? ld : n, rb, nv);
         if (!dev) CU(cudaMemcpy2DAsync(xc, sizeof(double) * ld, h->d_xb, sizeof(double) * n, sizeof(double) * n, nv,
                                        cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
@@ -1131,9 +1150,11 @@ int smslu_get_factors(smslu_handle_t h, int64_t* lp, int64_t* li, double* lx, in
     if (!h || !h->analyzed) return SMSLU_E_ARG;
     if (index_base != 0 && index_base != 1) return SMSLU_E_ARG;
     const Symbolic& S = h->S;
-    if (p) for (int i = 0; i < S.n; ++i) p[i] = S.p[i] + index_base;
-    if (q) for (int i = 0; i < S.n; ++i) q[i] = S.q[i] + index_base;
+    const bool relabel = !S.post.empty();        // ORD_GIVEN: answer in the caller's labelling (see Symbolic::post)
+    if (p) for (int i = 0; i < S.n; ++i) p[i] = (relabel ? S.p_given[i] : S.p[i]) + index_base;
+    if (q) for (int i = 0; i < S.n; ++i) q[i] = (relabel ? S.q_given[i] : S.q[i]) + index_base;
     const bool want_vals = lx || ux || Rs;
+    if (want_vals && h->pending_refactor) { const int rcs = smslu_sync(h); if (rcs && rcs != SMSLU_E_REPIVOT) return rcs; }
     if (want_vals && !h->factored) return fail(h, SMSLU_E_ARG, "no valid factorization (call smslu_refactor)");
     if (Rs) {
         CU(cudaSetDevice(h->device));
@@ -1164,6 +1185,21 @@ int smslu_get_factors(smslu_handle_t h, int64_t* lp, int64_t* li, double* lx, in
                 std::fill(lu.begin() + S.Uoff[s2], lu.begin() + S.Uoff[s2] + r * k, 0.0);
             }
         }
+    }
+    if (relabel) {
+        // the relabelling permutes rows inside the columns, so it needs colptr + rowval next to the values
+        const int64_t nz = S.nnzL_exact;
+        std::vector<int64_t> tlp, tli, tup, tui;
+        if (!lp) { tlp.resize(S.n + 1); lp = tlp.data(); }
+        if (!li) { tli.resize(nz); li = tli.data(); }
+        if (!up) { tup.resize(S.n + 1); up = tup.data(); }
+        if (!ui) { tui.resize(nz); ui = tui.data(); }
+        export_factors(S, h->ex_ptr, h->ex_idx, lu.empty() ? nullptr : lu.data(), index_base, lp, li,
+                       lu.empty() ? nullptr : lx, up, ui, lu.empty() ? nullptr : ux,
+                       col_mine.empty() ? nullptr : col_mine.data());
+        relabel_csc(S.n, S.post.data(), index_base, lp, li, lu.empty() ? nullptr : lx);
+        relabel_csc(S.n, S.post.data(), index_base, up, ui, lu.empty() ? nullptr : ux);
+        return 0;
     }
     export_factors(S, h->ex_ptr, h->ex_idx, lu.empty() ? nullptr : lu.data(), index_base, lp, li,
                    lu.empty() ? nullptr : lx, up, ui, lu.empty() ? nullptr : ux,

@@ -338,9 +338,11 @@ __global__ void __launch_bounds__(RW * CH * FPC) k_small_factor(DevCtx cx, const
     {
         const int i = tid % RW, h = tid / RW, npair = ld >> 1;
         double* myrow = Fs + i * ld;
+        bool big_l = false;                                   // threshold test: some multiplier above 1 / pivot_tol
         for (int j = 0; j < k; ++j) {
             if (i > j && i < f) {
                 const double l = myrow[j] * rd[j];
+                big_l |= fabs(l) > cx.lmax;
                 const double2* __restrict__ prow = reinterpret_cast<const double2*>(Fs + j * ld);
                 double2* __restrict__ mrow = reinterpret_cast<double2*>(myrow);
                 int p = ((j + 1) >> 1) + h;
@@ -368,6 +370,7 @@ __global__ void __launch_bounds__(RW * CH * FPC) k_small_factor(DevCtx cx, const
             }
             sync();
         }
+        if (big_l) atomicMin(cx.flag + 1, F.c0);
     }
     for (int c = wrp; c < k; c += NT / 32) {                  // P: pivot block on top of L21
         const double rc = rd[c];
@@ -448,6 +451,7 @@ __global__ void __launch_bounds__(((NC + 31) / 32) * 32 * FPC) k_small_factor_re
         sync();
     }
     double x[NC];                                     // row `tid` of the front (zero beyond f)
+    bool big_l = false;                               // threshold test: some multiplier above 1 / pivot_tol
 #pragma unroll
     for (int p = 0; p < NC / 2; ++p) {
         const double2 v = tid < f ? *reinterpret_cast<const double2*>(Fs + tid * ld + 2 * p) : make_double2(0.0, 0.0);
@@ -468,6 +472,7 @@ __global__ void __launch_bounds__(((NC + 31) / 32) * 32 * FPC) k_small_factor_re
         }
         sync();
         const double l = tid > j ? x[j] * sj[NC] : 0.0;
+        big_l |= fabs(l) > cx.lmax;
         x[j] = tid > j ? l : x[j];
 #pragma unroll
         for (int p = (j + 1) / 2; p < NC / 2; ++p) {
@@ -476,6 +481,7 @@ __global__ void __launch_bounds__(((NC + 31) / 32) * 32 * FPC) k_small_factor_re
             x[2 * p + 1] -= l * u.y;
         }
     }
+    if (big_l) atomicMin(cx.flag + 1, F.c0);
     // pivot block on top of L21: column c of P, threads = rows (multipliers are already scaled)
     if (tid < f) {
         double* __restrict__ dst = F.P + tid;
@@ -690,6 +696,7 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
         for (int c = 0; c < NB; ++c) x[c] = (lane >= w && c == lane) ? 1.0 : x[c];
         double myr = 0.0;                          // 1 / u_jj of this lane's row
         int bad = NB;                              // first bad pivot (uniform across the warp)
+        bool big_l = false;                        // threshold test: some multiplier above 1 / pivot_tol
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
             const double piv = __shfl_sync(0xffffffffu, x[j], j);
@@ -697,11 +704,13 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
             bad = (bad == NB && bad_pivot(piv)) ? j : bad;
             myr = lane == j ? rinv : myr;
             const double l = lane > j ? x[j] * rinv : 0.0;
+            big_l |= fabs(l) > cx.lmax;
             x[j] = lane > j ? l : x[j];
 #pragma unroll
             for (int c = j + 1; c < NB; ++c) x[c] -= l * __shfl_sync(0xffffffffu, x[c], j);
         }
         rd[lane] = myr;
+        if (big_l && lane < w) atomicMin(cx.flag + 1, F.c0 + j0);
         if (lane == 0 && bad < w) atomicMin(cx.flag, F.c0 + j0 + bad);
         // publish the factors in the form(s) this CTA's tiles need: rows of U for kind 0 (in W), columns of L for
         // kinds 1 and 2 (in D, whose raw contents only this warp still needed)
@@ -752,10 +761,12 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
                     x[2 * c2] = v.x; x[2 * c2 + 1] = v.y;
                 }
                 const double (*Wk)[CLD] = DW[kind == 0 ? 0 : 1];
+                bool big_l = false;
 #pragma unroll
                 for (int p = 0; p < NB; ++p) {
                     if (p >= w) break;
                     const double xp = kind == 0 ? x[p] * rd[p] : x[p];
+                    big_l |= kind == 0 && fabs(xp) > cx.lmax;      // rows of L: multipliers
                     x[p] = xp;
                     const double2* __restrict__ wr = reinterpret_cast<const double2*>(&Wk[p][0]);
 #pragma unroll
@@ -767,6 +778,7 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
                 }
 #pragma unroll
                 for (int c = 0; c < NB; ++c) if (c < w) base[(int64_t)(j0 + c) * stride] = x[c];
+                if (big_l) atomicMin(cx.flag + 1, F.c0 + j0);
             }
         }
         TRACEP(6);

@@ -49,7 +49,9 @@ struct DevCtx {
     double* bpart;      // backward-solve partial sums, KMAX doubles per (supernode, tile)
     int* counters;      // one per (big front, panel step), used by the panel kernel
     int* counters2;     // one per supernode, used by the backward-solve kernel
-    int* flag;          // first bad pivot column (atomicMin), INT_MAX when clean
+    int* flag;          // flag[0]: first bad (zero / non-finite) pivot column, flag[1]: first column of a front with a
+                        // multiplier above lmax (threshold test); atomicMin, 0x7f7f7f7f when clean
+    double lmax;        // 1 / pivot_tol (infinity: no test)
     double* dinv;       // 1 / u_jj by permuted column, written by the factor kernels
     const int* Doff;    // big fronts: index of the front's first 32x32 block in dblk
     double* dblk;       // inverses of the 32x32 diagonal blocks of the big fronts' pivot blocks (k_diag_inverse)

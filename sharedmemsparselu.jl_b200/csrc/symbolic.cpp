@@ -509,10 +509,16 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
     S.n = n;
     if (n <= 0) { err = "matrix must have at least one row"; return SMSLU_E_DIM; }
     S.annz = Ap[n];
-    for (int c = 0; c < n; ++c) {
-        if (Ap[c + 1] < Ap[c]) { err = "colptr is not monotone"; return SMSLU_E_PATTERN; }
-        for (int64_t t = Ap[c]; t < Ap[c + 1]; ++t)
-            if (Ai[t] < 0 || Ai[t] >= n) { err = "row index out of range"; return SMSLU_E_PATTERN; }
+    {
+        std::vector<int> seen(n, -1);     // a duplicate (row, column) would silently lose a value in the scatter
+        for (int c = 0; c < n; ++c) {
+            if (Ap[c + 1] < Ap[c]) { err = "colptr is not monotone"; return SMSLU_E_PATTERN; }
+            for (int64_t t = Ap[c]; t < Ap[c + 1]; ++t) {
+                if (Ai[t] < 0 || Ai[t] >= n) { err = "row index out of range"; return SMSLU_E_PATTERN; }
+                if (seen[Ai[t]] == c) { err = "duplicate (row, column) entry in the pattern: sum duplicates first"; return SMSLU_E_PATTERN; }
+                seen[Ai[t]] = c;
+            }
+        }
     }
     step_mark("1 initial ordering");
     // ---------------------------------------------------------------- 1. initial ordering
@@ -563,6 +569,11 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
     S.q.resize(n);
     std::vector<int> ipost(n);
     for (int k = 0; k < n; ++k) { S.p[k] = p0[post[k]]; S.q[k] = q0[post[k]]; ipost[post[k]] = k; }
+    if (ordering == ORD_GIVEN) {
+        bool ident = true;
+        for (int k = 0; k < n && ident; ++k) ident = post[k] == k;
+        if (!ident) { S.p_given = p0; S.q_given = q0; S.post = post; }
+    }
     Graph G = relabel(G1, post);
     G1 = Graph();
     S.parent.resize(n);
@@ -943,6 +954,29 @@ void exact_structure(const Symbolic& S, const int64_t* Ap, const int64_t* Ai,
 }  // namespace smslu
 
 namespace smslu {
+
+void relabel_csc(int n, const int* post, int64_t base, int64_t* colptr, int64_t* idx, double* val) {
+    const int64_t nnz = colptr[n] - base;
+    std::vector<int64_t> np(n + 1, 0);
+    for (int j = 0; j < n; ++j) np[post[j] + 1] = colptr[j + 1] - colptr[j];
+    for (int c = 0; c < n; ++c) np[c + 1] += np[c];
+    std::vector<int64_t> ti(idx ? nnz : 0);
+    std::vector<double> tv(val ? nnz : 0);
+    std::vector<std::pair<int64_t, double>> col;
+    for (int j = 0; j < n; ++j) {
+        const int64_t lo = colptr[j] - base, cnt = colptr[j + 1] - colptr[j], o = np[post[j]];
+        if (!idx) {            // values only: the order inside the column still follows the relabelled rows, which
+            continue;          // needs the row indices -- callers that want values pass idx too
+        }
+        col.resize(cnt);
+        for (int64_t t = 0; t < cnt; ++t) col[t] = {(int64_t)post[idx[lo + t] - base], val ? val[lo + t] : 0.0};
+        std::sort(col.begin(), col.end(), [](const std::pair<int64_t, double>& a, const std::pair<int64_t, double>& b) { return a.first < b.first; });
+        for (int64_t t = 0; t < cnt; ++t) { ti[o + t] = col[t].first + base; if (val) tv[o + t] = col[t].second; }
+    }
+    if (idx) std::copy(ti.begin(), ti.end(), idx);
+    if (val && idx) std::copy(tv.begin(), tv.end(), val);
+    for (int c = 0; c <= n; ++c) colptr[c] = np[c] + base;
+}
 
 void export_factors(const Symbolic& S, const std::vector<int64_t>& ptr, const std::vector<int>& idx,
                     const double* lu, int64_t base, int64_t* Lp, int64_t* Li, double* Lx,

@@ -36,6 +36,11 @@ struct Symbolic {
     int n = 0;
     int64_t annz = 0;
     std::vector<int> p, q;            // B = (Rs .* A)[p, q], 0-based, postordered
+    // ORD_GIVEN only (empty otherwise): the caller's (p0, q0) and post[k] = position in the caller's order of
+    // internal index k (p[k] = p0[post[k]]).  The postorder is an equivalent reordering (a topological order of
+    // the elimination tree), so L_caller(post[i], post[j]) = L(i, j): the C ABI reports p0, q0 and the factors
+    // in the caller's labelling, and lsolve/rsolve permute their vector through post.
+    std::vector<int> p_given, q_given, post;
     std::vector<int> parent;          // column elimination tree of pattern(B + B')
     std::vector<int> colcount;        // exact |struct(L(:,j))| incl. diagonal
 
@@ -102,5 +107,9 @@ void exact_structure(const Symbolic& S, const int64_t* Ap, const int64_t* Ai,
 void export_factors(const Symbolic& S, const std::vector<int64_t>& ptr, const std::vector<int>& idx,
                     const double* lu, int64_t base, int64_t* Lp, int64_t* Li, double* Lx,
                     int64_t* Up, int64_t* Ui, double* Ux, const char* col_mine = nullptr);
+
+// Relabel a square CSC matrix in place: entry (i, j) moves to (post[i], post[j]); rows sorted inside every column.
+// colptr keeps `base`; any of idx / val may be null (the other is still permuted consistently).
+void relabel_csc(int n, const int* post, int64_t base, int64_t* colptr, int64_t* idx, double* val);
 
 }  // namespace smslu

@@ -15,13 +15,20 @@
 # NOT EXECUTED in the build environment (no Julia toolchain there); the same C entry points are
 # exercised by the Python mirror (sharedmemsparselu.jl_b200/__init__.py) in tests/.
 #
-# Two ways to fix the pivot order:
-#   pivots = :native  (default)  the library's own fill-reducing ordering (nested dissection on
-#                                A+A'), diagonal pivots, UMFPACK-style row scaling Rs = 1/sum|a_ij|.
-#   pivots = :umfpack            `lu(A)` from SparseArrays (UMFPACK, what the reference calls at
-#                                src:74) is run ONCE on the host for its (p, q, Rs); the GPU then
-#                                factors with exactly those pivots, so F.p, F.q, F.Rs are
-#                                bit-identical to the reference's and L, U agree to rounding.
+# Where the pivot order comes from:
+#   pivots = :umfpack (default)  `lu(A)` from SparseArrays (UMFPACK, what the reference calls at
+#                                src:74) is run on the host for its (p, q, Rs); the GPU then
+#                                factors with exactly those pivots, so F.p, F.q, F.Rs are the
+#                                reference's and L, U agree to rounding.  `lu!(F, A)` keeps them while the
+#                                new values pass the threshold test on the GPU (every |l_ij| <= 1/pivot_tol);
+#                                when the test fails (SMSLU_E_REPIVOT) or a pivot is zero, UMFPACK is asked
+#                                again and the object is re-analysed -- the reference's re-pivot /
+#                                re-chunk branch (src:252-273).
+#   pivots = :native             the library's own fill-reducing ordering (nested dissection on
+#                                A+A'), diagonal pivots, UMFPACK-style row scaling Rs = 1/sum|a_ij|:
+#                                for matrices known to need no pivoting (M-matrices, diagonally dominant
+#                                blocks); this is also the ordering the multi-GPU partition needs.  A failed
+#                                threshold test falls back to :umfpack pivots unless `strict=true`.
 module SharedMemSparseLU
 
 export ParallelSparseLU, cleanup_ParallelSparseLU!, allocate_shared, comm_unique_id
@@ -37,8 +44,14 @@ const libsmslu = get(ENV, "SMSLU_LIB", joinpath(@__DIR__, "..", "libsmslu.so"))
 const SMSLU_E_DIM = -1
 const SMSLU_E_PIVOT = -2
 const SMSLU_E_PATTERN = -3
+const SMSLU_E_REPIVOT = -9
 
-# mirror of smslu_options_t (18 Int32)
+"Thrown by `lu!` (strict mode only) when the static pivot order fails the threshold test for the new values."
+struct PivotThresholdError <: Exception
+    msg::String
+end
+
+# mirror of smslu_options_t (12 Int32, one Float64, 4 Int32 = 72 bytes)
 struct SmsluOptions
     ordering::Int32
     grid::NTuple{3,Int32}
@@ -47,10 +60,11 @@ struct SmsluOptions
     max_width::Int32
     scaling::Int32
     device::Int32
-    use_graph::Int32
+    reserved0::Int32
     nranks::Int32
     rank::Int32
-    reserved::NTuple{6,Int32}
+    pivot_tol::Float64
+    reserved::NTuple{4,Int32}
 end
 
 const ORDERINGS = Dict(:auto => 0, :natural => 1, :given => 2, :nd_graph => 3, :nd_grid => 4)
@@ -72,12 +86,13 @@ function check(h::Ptr{Cvoid}, rc::Integer)
     rc == SMSLU_E_DIM && throw(DimensionMismatch(msg))
     rc == SMSLU_E_PIVOT && throw(SingularException(0))
     rc == SMSLU_E_PATTERN && throw(ArgumentError(msg))
+    rc == SMSLU_E_REPIVOT && throw(PivotThresholdError(msg))
     error("smslu error $rc: $msg")
 end
 
 """
-    ParallelSparseLU(A::SparseMatrixCSC{Float64,Int64}, chunk_size=nothing; pivots=:native,
-                     ordering=:auto, grid=nothing, device=-1)
+    ParallelSparseLU(A::SparseMatrixCSC{Float64,Int64}, chunk_size=nothing; pivots=:umfpack,
+                     ordering=:auto, grid=nothing, device=-1, strict=false)
 
 Factorize `A` on the GPU.  `chunk_size` is accepted for compatibility with the reference
 (src:64-72) and ignored: the dense column-chunk layout it sized (src:101-178) does not exist here.
@@ -91,46 +106,85 @@ mutable struct ParallelSparseLU{Tf,Ti}
     chunk_size::Ti
     Rs_given::Union{Vector{Float64},Nothing}
     cache::Dict{Symbol,Any}
+    pivots::Symbol
+    strict::Bool
+    opts::SmsluOptions
+    comm_id::Union{Vector{UInt8},Nothing}
 
     function ParallelSparseLU(A::SparseMatrixCSC{Tf,Ti}, chunk_size=nothing;
-                              pivots::Symbol=:native, ordering::Symbol=:auto,
-                              grid=nothing, device::Integer=-1,
-                              nranks::Integer=1, rank::Integer=0,
+                              pivots::Symbol=:umfpack, ordering::Symbol=:auto,
+                              grid=nothing, device::Integer=-1, strict::Bool=false,
+                              nranks::Integer=1, rank::Integer=0, pivot_tol::Real=0.0,
                               comm_id::Union{Vector{UInt8},Nothing}=nothing) where {Tf<:Float64,Ti<:Int64}
         size(A, 1) == size(A, 2) || throw(DimensionMismatch("matrix is not square: $(size(A))"))
         chunk_size === nothing && (chunk_size = 8)                       # src:67-70
         chunk_size = min(chunk_size, A.n)                                # src:72
+        nranks > 1 && (pivots = :native)                                 # the partition is the top of OUR nested dissection
         o = default_options()
-        p = q = nothing
-        Rs = nothing
-        if pivots === :umfpack
-            F0 = lu(A)                                                   # host UMFPACK, once
-            p, q, Rs = Vector{Int64}(F0.p), Vector{Int64}(F0.q), Vector{Float64}(F0.Rs)
-            ordering = :given
-        end
         g = grid === nothing ? (Int32(0), Int32(0), Int32(0)) :
             (Int32(grid[1]), Int32(length(grid) > 1 ? grid[2] : 1), Int32(length(grid) > 2 ? grid[3] : 1))
         o = SmsluOptions(Int32(ORDERINGS[ordering]), g, o.nd_leaf, o.relax, o.max_width, o.scaling,
-                         Int32(device), o.use_graph, Int32(nranks), Int32(rank), o.reserved)
-        h = Ref{Ptr{Cvoid}}(C_NULL)
-        rc = ccall((:smslu_create, libsmslu), Cint,
-                   (Ptr{Ptr{Cvoid}}, Int64, Ptr{Int64}, Ptr{Int64}, Int32, Ptr{SmsluOptions}),
-                   h, A.n, A.colptr, A.rowval, 1, Ref(o))
-        rc == 0 || error("smslu_create failed with code $rc")
-        F = new{Tf,Ti}(A.m, A.n, h[], copy(A.colptr), copy(A.rowval), chunk_size, Rs, Dict{Symbol,Any}())
+                         Int32(device), Int32(0), Int32(nranks), Int32(rank), Float64(pivot_tol), o.reserved)
+        F = new{Tf,Ti}(A.m, A.n, C_NULL, copy(A.colptr), copy(A.rowval), chunk_size, nothing, Dict{Symbol,Any}(),
+                       pivots, strict, o, comm_id)
         finalizer(cleanup_ParallelSparseLU!, F)
-        check(F.handle, ccall((:smslu_analyze, libsmslu), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}),
-                              F.handle, p === nothing ? C_NULL : p, q === nothing ? C_NULL : q))
-        if nranks > 1
-            # one process (MPI rank) per GPU: every rank analyses the same pattern; the 128-byte id comes from
-            # `comm_unique_id()` on rank 0, e.g.  id = MPI.bcast(rank == 0 ? comm_unique_id() : nothing, 0, comm)
-            comm_id === nothing && throw(ArgumentError("nranks > 1 needs comm_id (see comm_unique_id)"))
-            check(F.handle, ccall((:smslu_comm_init, libsmslu), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int64),
-                                  F.handle, comm_id, length(comm_id)))
+        if pivots === :umfpack
+            build!(F, A, true)
+        else
+            try
+                build!(F, A, false)
+            catch e
+                (e isa PivotThresholdError || e isa SingularException) && !strict || rethrow()
+                build!(F, A, true)                                       # the diagonal pivots fail for this matrix
+            end
         end
-        lu!(F, A)
         return F
     end
+end
+
+# (Re)create the handle: host pivot search with UMFPACK when `umfpack`, analysis, first numeric factorization.
+function build!(F::ParallelSparseLU, A::SparseMatrixCSC, umfpack::Bool)
+    cleanup_ParallelSparseLU!(F)
+    o = getfield(F, :opts)
+    p = q = nothing
+    setfield!(F, :Rs_given, nothing)
+    if umfpack
+        F0 = lu(A)                                                       # host UMFPACK (src:74): ordering + threshold pivoting
+        p, q = Vector{Int64}(F0.p), Vector{Int64}(F0.q)
+        setfield!(F, :Rs_given, Vector{Float64}(F0.Rs))
+        o = SmsluOptions(Int32(ORDERINGS[:given]), o.grid, o.nd_leaf, o.relax, o.max_width, o.scaling,
+                         o.device, o.reserved0, o.nranks, o.rank, o.pivot_tol, o.reserved)
+        setfield!(F, :pivots, :umfpack)
+    end
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:smslu_create, libsmslu), Cint,
+               (Ptr{Ptr{Cvoid}}, Int64, Ptr{Int64}, Ptr{Int64}, Int32, Ptr{SmsluOptions}),
+               h, A.n, A.colptr, A.rowval, 1, Ref(o))
+    rc == 0 || error("smslu_create failed with code $rc")
+    setfield!(F, :handle, h[])
+    check(h[], ccall((:smslu_analyze, libsmslu), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}),
+                     h[], p === nothing ? C_NULL : p, q === nothing ? C_NULL : q))
+    if o.nranks > 1
+        # one process (MPI rank) per GPU: every rank analyses the same pattern; the 128-byte id comes from
+        # `comm_unique_id()` on rank 0, e.g.  id = MPI.bcast(rank == 0 ? comm_unique_id() : nothing, 0, comm)
+        id = getfield(F, :comm_id)
+        id === nothing && throw(ArgumentError("nranks > 1 needs comm_id (see comm_unique_id)"))
+        check(h[], ccall((:smslu_comm_init, libsmslu), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int64), h[], id, length(id)))
+    end
+    refactor!(F, A)
+    # later lu!(F, A) calls recompute the row scaling from the new values on the GPU (same formula as UMFPACK's
+    # default, Rs[i] = 1 / sum_j |a_ij|); the first factorization used UMFPACK's own vector
+    setfield!(F, :Rs_given, nothing)
+    return nothing
+end
+
+function refactor!(F::ParallelSparseLU, A::SparseMatrixCSC)
+    empty!(getfield(F, :cache))
+    Rs = getfield(F, :Rs_given)
+    h = getfield(F, :handle)
+    check(h, ccall((:smslu_refactor, libsmslu), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}),
+                   h, A.nzval, Rs === nothing ? C_NULL : Rs))
+    return nothing
 end
 
 """
@@ -148,19 +202,24 @@ end
 """
     lu!(F::ParallelSparseLU, A::SparseMatrixCSC)
 
-Numeric refactorization with the sparsity pattern `F` was analysed for (reference src:245-279).
-The pivot order is static; a pattern change raises `ArgumentError`, a zero pivot `SingularException`
-(the reference would let UMFPACK re-pivot; rebuild the object in that case).  Returns `nothing`.
+Numeric refactorization with the sparsity pattern `F` was analysed for (reference src:245-279).  The pivot order of
+the previous factorization is kept as long as the new values pass the threshold test on the GPU; when they do not
+(or a pivot is zero) UMFPACK is asked for fresh pivots on the host and `F` is re-analysed, which is what the
+reference's re-pivot / re-chunk branch (src:252-273) amounts to.  With `strict=true` (or on a multi-GPU object) a
+`PivotThresholdError` / `SingularException` is thrown instead.  A pattern change raises `ArgumentError`.  Returns `nothing`.
 """
 function lu!(F::ParallelSparseLU{Tf,Ti}, A::Union{SparseMatrixCSC{Tf,Ti},Nothing}) where {Tf,Ti}
     A === nothing && throw(ArgumentError("lu!(F, nothing) is not supported (nor does the reference's Nothing arm work, src:246-247)"))
     (A.m == F.m && A.n == F.n) || throw(DimensionMismatch("matrix size differs from the factor object"))
     (A.colptr == F.colptr && A.rowval == F.rowval) ||
         throw(ArgumentError("sparsity pattern differs from the analysed one"))
-    empty!(F.cache)
-    Rs = getfield(F, :Rs_given)
-    check(F.handle, ccall((:smslu_refactor, libsmslu), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}),
-                          F.handle, A.nzval, Rs === nothing ? C_NULL : Rs))
+    try
+        refactor!(F, A)
+    catch e
+        (e isa PivotThresholdError || e isa SingularException) || rethrow()
+        (getfield(F, :strict) || getfield(F, :opts).nranks > 1) && rethrow()
+        build!(F, A, true)
+    end
     return nothing
 end
 

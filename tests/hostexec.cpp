@@ -74,8 +74,9 @@ void hx_info(void* hv, int64_t* out, double* flops) {
 }
 
 void hx_perm(void* hv, int64_t* p, int64_t* q) {
-    const Symbolic& S = ((HX*)hv)->S;
-    for (int k = 0; k < S.n; ++k) { p[k] = S.p[k]; q[k] = S.q[k]; }
+    const Symbolic& S = ((HX*)hv)->S;       // ORD_GIVEN: the caller's own p, q (see Symbolic::post)
+    const bool given = !S.post.empty();
+    for (int k = 0; k < S.n; ++k) { p[k] = given ? S.p_given[k] : S.p[k]; q[k] = given ? S.q_given[k] : S.q[k]; }
 }
 
 void hx_owner(void* hv, int64_t* owner) {
@@ -245,7 +246,16 @@ void hx_lsolve_phase(void* hv, double* x, int rank, int phase) {
         }
 }
 
-void hx_lsolve(void* hv, double* x) { hx_lsolve_phase(hv, x, 0, 0); }
+// lsolve! / rsolve! at the boundary work in the caller's labelling: permute through post when the analysis relabelled
+static void with_post(void* hv, double* x, void (*fn)(void*, double*, int, int)) {
+    const Symbolic& S = ((HX*)hv)->S;
+    if (S.post.empty()) { fn(hv, x, 0, 0); return; }
+    std::vector<double> w(S.n);
+    for (int k = 0; k < S.n; ++k) w[k] = x[S.post[k]];
+    fn(hv, w.data(), 0, 0);
+    for (int k = 0; k < S.n; ++k) x[S.post[k]] = w[k];
+}
+void hx_lsolve(void* hv, double* x) { with_post(hv, x, hx_lsolve_phase); }
 
 // Backward substitution, one phase: phase 1 (top) runs first, then phase 0 (the rank's subtrees).
 void hx_rsolve_phase(void* hv, double* x, int rank, int phase) {
@@ -270,7 +280,7 @@ void hx_rsolve_phase(void* hv, double* x, int rank, int phase) {
         }
 }
 
-void hx_rsolve(void* hv, double* x) { hx_rsolve_phase(hv, x, 0, 0); }
+void hx_rsolve(void* hv, double* x) { with_post(hv, x, hx_rsolve_phase); }
 
 // zero the entries of a permuted-space vector this rank is not responsible for
 void hx_mask_owned(void* hv, double* z, int rank) {
@@ -295,8 +305,8 @@ void hx_solve(void* hv, const double* b, double* x) {
     const Symbolic& S = h->S;
     std::vector<double> w(S.n);
     for (int i = 0; i < S.n; ++i) w[i] = h->Rs[S.p[i]] * b[S.p[i]];
-    hx_lsolve(hv, w.data());
-    hx_rsolve(hv, w.data());
+    hx_lsolve_phase(hv, w.data(), 0, 0);
+    hx_rsolve_phase(hv, w.data(), 0, 0);
     for (int i = 0; i < S.n; ++i) x[S.q[i]] = w[i];
 }
 
@@ -306,6 +316,10 @@ void hx_get_factors(void* hv, int64_t* Lp, int64_t* Li, double* Lx, int64_t* Up,
     std::vector<int> idx;
     exact_structure(h->S, h->Ap.data(), h->Ai.data(), ptr, idx);
     export_factors(h->S, ptr, idx, h->lu.data(), 0, Lp, Li, Lx, Up, Ui, Ux);
+    if (!h->S.post.empty()) {
+        relabel_csc(h->S.n, h->S.post.data(), 0, Lp, Li, Lx);
+        relabel_csc(h->S.n, h->S.post.data(), 0, Up, Ui, Ux);
+    }
 }
 
 }  // extern "C"

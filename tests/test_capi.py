@@ -91,3 +91,17 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".jl")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in txt.lower() or f == "__init__.py" and False, os.path.join(dirpath, f)
+
+
+def test_duplicate_entries_are_rejected():
+    """A non-canonical CSC with a repeated (row, column) would silently lose a value in the A -> front scatter."""
+    import ctypes as C
+    import numpy as np
+    from sharedmemsparselu_jl_b200 import _capi
+    L = _capi.lib()
+    colptr = np.array([0, 3, 5], np.int64); rowval = np.array([0, 1, 1, 0, 1], np.int64)     # (1,0) twice
+    h = C.c_void_p()
+    assert L.smslu_create(C.byref(h), 2, colptr.ctypes.data_as(C.c_void_p), rowval.ctypes.data_as(C.c_void_p), 0, None) == 0
+    assert L.smslu_analyze(h, None, None) == _capi.E_PATTERN
+    assert b"duplicate" in L.smslu_last_error(h)
+    L.smslu_destroy(h)

@@ -317,3 +317,178 @@ def test_full_size_properties(smslu, W, cfg):
     smslu.ldiv_(x, F, b)
     assert residual(A2, x, b) < 1e-13
     F.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Pivoting robustness: threshold test on the GPU, re-analysis with fresh host pivots
+
+@pytest.mark.parametrize("n", [1, 2, 5, 8, 33, 100, 200])
+def test_reference_dense_update_testset_default_arguments(smslu, W, n):
+    """The reference's 'dense matrix' testset (test:108-146) with DEFAULT arguments: factorize rand(n,n), solve, new
+    right-hand side, lu! with a NEW random matrix of the same (full) pattern, solve twice more -- each against an
+    independent dense solve at the reference's tolerance (rtol = atol = 1e-10, test:26).  Static diagonal pivots are
+    unstable on these matrices: the threshold test must catch it and the pivots must come from the host search."""
+    A = W.dense_random(n, seed=2000 + n)
+    F = smslu.ParallelSparseLU(A)
+    for rnd, seed in ((0, 7), (0, 8)):
+        b = W.rhs(n, seed)
+        x = np.empty(n); smslu.ldiv_(x, F, b)
+        assert isapprox(x, np.linalg.solve(A.toarray(), b), DENSE_TOL)
+    A2 = W.dense_random(n, seed=3000 + n)
+    assert smslu.lu_(F, A2) is None                                         # test:129-131
+    for seed in (9, 10):
+        b = W.rhs(n, seed)
+        x = np.empty(n); smslu.ldiv_(x, F, b)
+        assert isapprox(x, np.linalg.solve(A2.toarray(), b), DENSE_TOL)     # test:138, 144
+    L, U = F.L, F.U
+    assert abs(L).max() <= 1000.0 * (1 + 1e-6)                              # every multiplier passes the threshold
+    B = (sp.diags(F.Rs) @ A2).tocsr()[F.p][:, F.q]
+    assert abs(L @ U - B).max() < 1e-12 * max(1.0, abs(B).max())            # src:307
+    F.close()
+
+
+def test_threshold_violation_is_reported_not_silent(smslu, W):
+    """New values that break the old pivots: strict ('native') objects return the distinct 'needs re-analysis' error
+    instead of a wrong x; default objects re-pivot like the reference's lu! (src:245-279)."""
+    A = W.laplacian_2d(12)
+    n = A.shape[0]
+    bad = A.copy()
+    d = np.flatnonzero(bad.indices == np.repeat(np.arange(n), np.diff(bad.indptr)))
+    bad.data[d[n // 2]] = 1e-9                                              # a tiny pivot in the middle of the grid
+    b = W.rhs(n, 3)
+    xo = np.linalg.solve(bad.toarray(), b)
+    F = smslu.ParallelSparseLU(A, pivots="native")
+    with pytest.raises(smslu.PivotThresholdError):
+        smslu.lu_(F, bad)
+    assert F.stats()["threshold_col"] >= 0
+    smslu.lu_(F, A)                                                         # the object stays usable with good values
+    assert F.stats()["threshold_col"] == -1
+    x = np.empty(n); smslu.ldiv_(x, F, b)
+    assert residual(A, x, b) < 1e-14
+    F.close()
+    with pytest.raises(smslu.PivotThresholdError):
+        smslu.ParallelSparseLU(bad, pivots="native")
+    G = smslu.ParallelSparseLU(A)                                           # default: re-pivot on the host when needed
+    p_before = G.p.copy()
+    smslu.lu_(G, bad)
+    x = np.empty(n); smslu.ldiv_(x, G, b)
+    assert isapprox(x, xo, 1e-10)
+    assert not np.array_equal(G.p, p_before) or not np.array_equal(G.p, G.q)
+    assert abs(G.L).max() <= 1000.0 * (1 + 1e-6)
+    smslu.lu_(G, A)                                                         # and back: the new pivots still pass on A? either way correct
+    smslu.ldiv_(x, G, b)
+    assert isapprox(x, np.linalg.solve(A.toarray(), b), 1e-10)
+    G.close()
+    H = smslu.ParallelSparseLU(A, pivot_tol=-1.0, pivots="native")          # test switched off: no error (and no guarantee)
+    smslu.lu_(H, bad)
+    H.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Independent factorization at real sizes: SciPy SuperLU forced to the same pivots (F.p, F.q, F.Rs)
+
+def _superlu_same_pivots(A, p, q, Rs):
+    import scipy.sparse.linalg as spla
+    B = sp.csc_matrix((sp.diags(Rs) @ A).tocsr()[p][:, q])
+    lu = spla.splu(B, permc_spec="NATURAL", diag_pivot_thresh=0.0, options=dict(SymmetricMode=True))
+    assert np.array_equal(lu.perm_r, np.arange(A.shape[0])) and np.array_equal(lu.perm_c, np.arange(A.shape[0]))
+    return lu
+
+
+FULL = {
+    "config2_lap2d_1024": lambda W: W.laplacian_2d(1024),                                    # BASELINE configs[1]
+    "config3_lap3d_48": lambda W: W.laplacian_3d(48),
+    "config4_blocks_nel45_x8": lambda W: W.block_border(nblocks=8, nel=45, ngr=5, border=64),  # full-size blocks
+}
+
+
+@pytest.mark.parametrize("cfg", list(FULL))
+def test_full_size_entries_against_superlu_same_pivots(smslu, W, cfg):
+    """L and U entry by entry against an independent LU (SuperLU, same pivot order) at BASELINE sizes."""
+    A = FULL[cfg](W)
+    n = A.shape[0]
+    F = smslu.ParallelSparseLU(A)
+    p, q, Rs = F.p, F.q, F.Rs
+    lu = _superlu_same_pivots(A, p, q, Rs)
+    Ls, Us = sp.csc_matrix(lu.L), sp.csc_matrix(lu.U)
+    Ls.sort_indices(); Us.sort_indices()
+    L, U = F.L, F.U
+    # SuperLU's supernodes may store explicit zeros / drop nothing: compare on the union through sparse differences
+    dl, du = abs(L - Ls), abs(U - Us)
+    assert dl.max() < 1e-12 * max(1.0, abs(Ls).max()) and du.max() < 1e-12 * abs(Us).max()
+    assert L.nnz == F.stats()["nnz_l_exact"] and (abs(Ls) > 0).nnz <= L.nnz
+    if cfg.startswith("config2") or cfg.startswith("config3"):     # M-matrices: no cancellation -> plain relative error
+        for M, Ms in ((L, Ls), (U, Us)):
+            Ms = Ms.copy(); Ms.eliminate_zeros()                   # SuperLU pads its relaxed supernodes with zeros
+            assert np.array_equal(M.indptr, Ms.indptr) and np.array_equal(M.indices, Ms.indices)   # bit-exact structure
+            assert (abs(M.data - Ms.data) <= 1e-12 * abs(Ms.data)).all()
+    b = W.rhs(n, 11)
+    x = np.empty(n); smslu.ldiv_(x, F, b)
+    w = (Rs * b)[p]
+    xs = np.empty(n); xs[q] = lu.solve(w)
+    assert np.linalg.norm(x - xs) <= 1e-10 * np.linalg.norm(xs)
+    assert residual(A, x, b) <= max(4 * residual(A, xs, b), 1e-15)
+    F.close()
+
+
+def test_many_rhs_against_superlu_config5(smslu, W):
+    """BASELINE config 5 shape: 64 right-hand sides on a 48^3 Laplacian, every column against SuperLU's solve."""
+    A = W.laplacian_3d(48)
+    n, nrhs = A.shape[0], 64
+    F = smslu.ParallelSparseLU(A)
+    lu = _superlu_same_pivots(A, F.p, F.q, F.Rs)
+    B = W.rhs(n, 47, nrhs=nrhs)
+    X = np.empty((n, nrhs), order="F")
+    smslu.ldiv_(X, F, B)
+    Wm = (F.Rs[:, None] * B)[F.p]
+    Xs = np.empty_like(X); Xs[F.q] = lu.solve(np.ascontiguousarray(Wm))
+    err = np.linalg.norm(X - Xs, axis=0) / np.linalg.norm(Xs, axis=0)
+    assert err.max() < 1e-10
+    F.close()
+
+
+def test_north_star_lap3d_128_against_poisson_solver(smslu, W):
+    """The north-star target at FULL size (3D 7-point Laplacian 128^3) on one GPU: refactorize + solve against an
+    independent exact solver (type-I sine transform diagonalises the Dirichlet Laplacian) -- the checker bench.py
+    prints as parity.x_relerr at every N."""
+    import scipy.fft as sfft
+    e = 128
+    A = W.laplacian_3d(e)
+    n = A.shape[0]
+    F = smslu.ParallelSparseLU(A)
+    assert F.stats()["bad_pivot_col"] == -1
+    lam1 = 2.0 - 2.0 * np.cos(np.arange(1, e + 1) * np.pi / (e + 1))
+    lam = lam1.reshape(-1, 1, 1) + lam1.reshape(1, -1, 1) + lam1.reshape(1, 1, -1)
+    for k in (0, 1):
+        vals = A.data.copy()
+        if k:
+            d = np.flatnonzero(A.indices == np.repeat(np.arange(n), np.diff(A.indptr)))
+            vals[d] += 1e-3
+            smslu.lu_(F, vals)                                    # refactorize: A + 1e-3 I, same pattern
+        b = W.rhs(n, 47 + k)
+        x = np.empty(n); smslu.ldiv_(x, F, b)
+        xp = sfft.idstn(sfft.dstn(b.reshape(e, e, e), type=1, norm="ortho") / (lam + k * 1e-3), type=1, norm="ortho").reshape(-1)
+        assert np.linalg.norm(x - xp) <= 1e-10 * np.linalg.norm(xp)
+        Ak = A + k * 1e-3 * sp.identity(n)
+        assert residual(Ak, x, b) < 1e-12
+    F.close()
+
+
+def test_cuda_factors_through_the_reference_chunk_solve_config1(smslu, O, W):
+    """BASELINE configs[0] (100 x 100): the CUDA factors fed to the restated reference solve -- dense column chunks,
+    trsv + gemv per chunk, src:101-243 and src:349-392 -- give the same x as smslu.ldiv_ (and the same lsolve!/rsolve!)."""
+    A = W.laplacian_2d(100)
+    n = A.shape[0]
+    F = smslu.ParallelSparseLU(A)
+    L, U = F.L, F.U
+    assert O.RefChunks.predict_bytes(L, U) < 6e9
+    RC = O.RefChunks(L, U)
+    b = W.rhs(n, 47)
+    x = np.empty(n); smslu.ldiv_(x, F, b)
+    xr = RC.ldiv(F.p, F.q, F.Rs, b)
+    assert isapprox(x, xr, TOL)
+    y = b.copy(); smslu.lsolve_(F, y)
+    assert isapprox(y, RC.lsolve(b), TOL)
+    y = b.copy(); smslu.rsolve_(F, y)
+    assert isapprox(y, RC.rsolve(b), DENSE_TOL)
+    RC.close(); F.close()

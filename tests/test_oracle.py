@@ -130,3 +130,47 @@ def test_splitmix_known_answers(W):
     v = W.splitmix64(0, 2)
     assert v[0] == (0xE220A8397B1DCDAF >> 11) / 2.0**53
     assert v[1] == (0x6E789E6AA1B965F4 >> 11) / 2.0**53
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The threaded CPU multifrontal port (oracle/ref_mf.cpp) that bench.py times as cpu_baseline / --impl reference:
+# pinned against the left-looking oracle entry by entry.
+@pytest.mark.parametrize("case", ["lap2d_30", "lap3d_14", "block_border", "lap3d_24_blas"])
+def test_cpu_multifrontal_port_matches_oracle(O, W, case):
+    A = {"lap2d_30": lambda: W.laplacian_2d(30), "lap3d_14": lambda: W.laplacian_3d(14),
+         "block_border": lambda: W.block_border(nblocks=4, nel=5, ngr=5, border=8),
+         "lap3d_24_blas": lambda: W.laplacian_3d(24)}[case]()
+    n = A.shape[0]
+    F = O.RefMF(A, threads=3)
+    assert F.lu_(A.data) == -1
+    p, q = F.perm()
+    L, U, Rs = F.factors()
+    assert np.array_equal(Rs, O.row_scale_sum(A))
+    ref = O.OracleLU(A, p=p, q=q, Rs=Rs)
+    assert np.array_equal(L.indices, ref.Li) and np.array_equal(U.indices, ref.Ui)
+    assert abs(L - ref.L).max() < 1e-13 and abs(U - ref.U).max() < 1e-13 * abs(ref.U).max()
+    b = W.rhs(n, 47)
+    x = F.ldiv(b)
+    assert np.linalg.norm(x - ref.solve(b)) <= 1e-12 * np.linalg.norm(x)
+    vals = A.data * 1.01                                  # refactorization with the analysis reused
+    assert F.lu_(vals) == -1
+    A2 = A.copy(); A2.data = vals
+    x2 = F.ldiv(b)
+    assert np.linalg.norm(A2 @ x2 - b) <= 1e-13 * np.linalg.norm(b)
+    assert F.growth <= 1.0 + 1e-12                         # diagonally dominant: no multiplier above 1
+    F.close()
+
+
+def test_bench_poisson_checker_is_exact(W):
+    """bench.py's independent full-size checker (DST-I diagonalisation) against a sparse direct solve."""
+    import importlib.util, os, scipy.sparse as sp, scipy.sparse.linalg as spla
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("_bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
+    for kind, e in (("lap3d", 11), ("lap2d", 37)):
+        A = bench.make_matrix(W, kind, e)
+        n = A.shape[0]
+        b = W.rhs(n, 5)
+        x = bench.poisson_solve(kind, e, 2e-3, b)
+        xs = spla.spsolve(sp.csc_matrix(A + 2e-3 * sp.identity(n)), b)
+        assert np.linalg.norm(x - xs) <= 1e-13 * np.linalg.norm(xs)
