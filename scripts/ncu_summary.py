@@ -20,6 +20,10 @@ COLS = [
     ("dram__bytes_read.sum", "dram_read"),
     ("dram__bytes_write.sum", "dram_write"),
     ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram_pct"),
+    ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "gpu_dram_pct"),
+    ("dram__cycles_active.avg.pct_of_peak_sustained_elapsed", "dram_active_pct"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor_pipe_pct"),
+    ("sm__inst_executed_pipe_tensor.sum", "tensor_inst"),
     ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2_pct"),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm_pct"),
     ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "fp64_pipe_pct"),
@@ -36,6 +40,9 @@ def main():
     hi = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
     head, units, data = rows[hi], rows[hi + 1], rows[hi + 2:]
     sel = [(head.index(k), name, k) for k, name in COLS if k in head]
+    # every FP64-tensor (DMMA) counter the capture holds, whatever this ncu version calls them
+    known = {k for k, _ in COLS}
+    sel += [(i, k, k) for i, k in enumerate(head) if "dmma" in k.lower() and k not in known]
     with open(out, "w", newline="") as f:
         w = csv.writer(f)
         w.writerow([name + ("[%s]" % units[i] if units[i] else "") for i, name, _ in sel])

@@ -5,8 +5,12 @@ import numpy as np
 import smslu
 from sharedmemsparselu_jl_b200 import workloads as W
 
-grid = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-A = W.laplacian_2d(grid)
+# usage: <script> [grid]  (2D)   or   <script> lap3d <edge>
+if len(sys.argv) > 2 and sys.argv[1] == "lap3d":
+    grid = int(sys.argv[2]); A = W.laplacian_3d(grid)
+else:
+    grid = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+    A = W.laplacian_2d(grid)
 n = A.shape[0]
 F = smslu.ParallelSparseLU(A)
 b = W.rhs(n, 47); x = np.empty(n)

@@ -32,15 +32,17 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
-    tmp = LIB + ".%d.tmp" % os.getpid()
+    out = os.environ.get("SMSLU_BUILD_OUT") or LIB
+    tmp = out + ".%d.tmp" % os.getpid()
     trace = ["-DSMSLU_TRACE"] if os.environ.get("SMSLU_TRACE") == "1" else []
     if trace and os.environ.get("SMSLU_TRACE_ROWS"):
         trace.append("-DSMSLU_TRACE_ROWS=" + os.environ["SMSLU_TRACE_ROWS"])
+    trace += os.environ.get("SMSLU_NVCC_FLAGS", "").split()          # A/B builds: extra -D switches
     cmd = [nvcc()] + NVCC_FLAGS + trace + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + \
           [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     subprocess.check_call(cmd)
-    os.replace(tmp, LIB)
-    return LIB
+    os.replace(tmp, out)
+    return out
 
 
 if __name__ == "__main__":

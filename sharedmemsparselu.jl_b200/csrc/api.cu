@@ -30,6 +30,7 @@ struct NcclApi {
     decltype(&ncclCommInitRank) CommInitRank = nullptr;
     decltype(&ncclCommDestroy) CommDestroy = nullptr;
     decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
     decltype(&ncclGroupStart) GroupStart = nullptr;
     decltype(&ncclGroupEnd) GroupEnd = nullptr;
     decltype(&ncclGetErrorString) GetErrorString = nullptr;
@@ -47,10 +48,11 @@ NcclApi& nccl_api() {
             api.CommInitRank = (decltype(api.CommInitRank))dlsym(lib, "ncclCommInitRank");
             api.CommDestroy = (decltype(api.CommDestroy))dlsym(lib, "ncclCommDestroy");
             api.AllReduce = (decltype(api.AllReduce))dlsym(lib, "ncclAllReduce");
+            api.AllGather = (decltype(api.AllGather))dlsym(lib, "ncclAllGather");
             api.GroupStart = (decltype(api.GroupStart))dlsym(lib, "ncclGroupStart");
             api.GroupEnd = (decltype(api.GroupEnd))dlsym(lib, "ncclGroupEnd");
             api.GetErrorString = (decltype(api.GetErrorString))dlsym(lib, "ncclGetErrorString");
-            api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GroupStart &&
+            api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.AllGather && api.GroupStart &&
                      api.GroupEnd && api.GetErrorString;
         }
     }
@@ -59,7 +61,9 @@ NcclApi& nccl_api() {
 
 enum LaunchKind { L_ZERO = SMSLU_K_ZERO, L_EXTEND = SMSLU_K_EXTEND, L_SMALL = SMSLU_K_SMALL, L_PANEL = SMSLU_K_PANEL,
                   L_GEMM = SMSLU_K_GEMM, L_FWD = SMSLU_K_FWD, L_BWD = SMSLU_K_BWD,
-                  L_FWD_SMALL = SMSLU_K_FWD_SMALL, L_BWD_SMALL = SMSLU_K_BWD_SMALL };
+                  L_FWD_SMALL = SMSLU_K_FWD_SMALL, L_BWD_SMALL = SMSLU_K_BWD_SMALL,
+                  // partitioned top (timed as SMSLU_K_ALLREDUCE = "exchange"): publish panels to the peers, signal, wait
+                  L_REPL = 100, L_SIGNAL = 101, L_WAIT = 102 };
 
 constexpr int NLANES = 4;
 
@@ -124,6 +128,16 @@ struct smslu_handle_s {
     int nvtasks = 0;
     int64_t vupd_off = 0, vupd_len = 0;  // region of cx.upd holding the virtual children's vectors
     int* d_colowner = nullptr;           // owner of every permuted column (-1 = top)
+    // distributed top of the tree: peers' pools mapped through CUDA IPC, cross-GPU flags, per-level publish lists
+    int* d_xflags = nullptr;             // [sync point * nranks + source rank] = epoch of the last signal
+    int64_t* d_segs = nullptr;           // (offset, length) pairs of the panels this rank publishes
+    int* d_wait_slots = nullptr;
+    int4* d_trow_tasks = nullptr;        // runs of U12' rows this rank owns (published at the end of a refactorization)
+    int n_trow_tasks = 0;
+    int epoch = 0;
+    int* d_barrier = nullptr;            // one int, all-reduced as a barrier between the phases
+    std::vector<void*> ipc_opened;
+    int64_t peer_bytes_refactor = 0;     // bytes this rank stores into peer memory per refactorization
     int64_t bpart_slots = 0, ncounters = 0;
 
     bool own_stream = true;
@@ -225,6 +239,7 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
             const int* sn = S.level_sn.data() + S.level_ptr[l];
             const int cnt = S.level_ptr[l + 1] - S.level_ptr[l];
             int64_t off;
+            if (ph == 0) {                          // (the top's factorization schedule: build_top_fac)
             // small fronts by shared-memory class
             const int classes[5] = {32, 40, 48, 64, front_small_limit()};
             int lo = 0;
@@ -271,7 +286,7 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
                 for (int t = 0; t < cnt; ++t) {
                     int s = sn[t];
                     if (SMALL(s) || NC(s) == 0 || NARROW(s) != (grp == 1)) continue;   // small parents pull their children
-                    if (!(IN(s) || (ph == 0 && S.owner[s] == -1))) continue;
+                    if (!IN(s)) continue;       // (a top parent pulls the subtree roots' blocks in the top phase)
                     std::vector<int> kids;
                     for (int u = S.child_ptr[s]; u < S.child_ptr[s + 1]; ++u) {
                         const int c = S.child_idx[u];
@@ -348,13 +363,16 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
                     for (int j = 0; j < nt; ++j)
                         for (int i = 0; i < nt; ++i) {
                             int flags = (NC(s) > 0 ? 1 : 0) | (S.direct[s] ? 2 : 0) |
-                                        (S.direct[s] && S.cb_assigned[S.sn_parent[s]] ? 4 : 0);
+                                        (S.direct[s] && S.cb_assigned[S.sn_parent[s]] ? 4 : 0) |
+                                        (S.xroot[s] ? 8 : 0) |      // subtree root: columns go to their owners' pools
+                                        (S.direct[s] && r == K(S.sn_parent[s]) + R(S.sn_parent[s]) ? 32 : 0);   // chain link: identity map
                             tasks.push_back(make_int4(s, i, j, flags));
                         }
                 }
                 push(fac, L_GEMM, off, 0);
             }
             big_lane = 0;
+            }
             // forward solve level: warp-per-front kernel for the small fronts; narrow (k <= 32) and
             // wide big fronts go to separate launches because the kernel stages the whole pivot block
             // in shared memory (8 KB vs up to 129 KB)
@@ -406,6 +424,200 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
     }
     h->bpart_slots = slots;
     h->ncounters = ncounters;
+}
+
+// Map every peer's factor pool, contribution pool and flag array into this process (CUDA IPC over NVLink): the handles
+// travel through one ncclAllGather.  Offsets into the pools are the same on every rank (same deterministic analysis).
+int map_peers(smslu_handle_t h) {
+    if (h->nranks > MAX_RANKS) return fail(h, SMSLU_E_ARG, "at most 8 ranks (one NVSwitch box)");
+    struct Handles { cudaIpcMemHandle_t lu, cb, fl; };
+    Handles mine;
+    CU(cudaIpcGetMemHandle(&mine.lu, h->cx.lu));
+    CU(cudaIpcGetMemHandle(&mine.cb, h->cx.cb));
+    CU(cudaIpcGetMemHandle(&mine.fl, h->d_xflags));
+    char* d_all = nullptr;
+    int rc;
+    if ((rc = dev_alloc(h, &d_all, sizeof(Handles) * (size_t)h->nranks))) return rc;
+    CU(cudaMemcpy(d_all + sizeof(Handles) * h->rank, &mine, sizeof(Handles), cudaMemcpyHostToDevice));
+    NCCLCHK(nccl_api().AllGather(d_all + sizeof(Handles) * h->rank, d_all, sizeof(Handles), ncclChar, h->comm, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    std::vector<Handles> all(h->nranks);
+    CU(cudaMemcpy(all.data(), d_all, sizeof(Handles) * (size_t)h->nranks, cudaMemcpyDeviceToHost));
+    for (int g = 0; g < h->nranks; ++g) {
+        if (g == h->rank) continue;
+        void *plu = nullptr, *pcb = nullptr, *pfl = nullptr;
+        CU(cudaIpcOpenMemHandle(&plu, all[g].lu, cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle(&pcb, all[g].cb, cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle(&pfl, all[g].fl, cudaIpcMemLazyEnablePeerAccess));
+        h->ipc_opened.push_back(plu); h->ipc_opened.push_back(pcb); h->ipc_opened.push_back(pfl);
+        h->cx.lu_peer[g] = (double*)plu; h->cx.cb_peer[g] = (double*)pcb; h->cx.xflag_peer[g] = (int*)pfl;
+    }
+    return 0;
+}
+
+// Factorization schedule of the distributed top (nranks > 1), one entry list walked in order on the main stream.
+// Per level:  zero-fill / assembly (destination columns this rank owns)  ->  panel owner: the pivot block and L21 of its
+// fronts (k_panel mode 1), published to every peer's pool, signal  ->  wait for the other owners of the level  ->
+// rows of U12' this rank owns (k_panel mode 2)  ->  Schur update of the columns this rank owns.
+void build_top_fac(smslu_handle_t h, std::vector<int4>& tasks, std::vector<int64_t>& segs, std::vector<int>& wait_slots,
+                   std::vector<int4>& trow_tasks, int64_t& ncounters) {
+    const Symbolic& S = h->S;
+    const int rank = h->rank, NR = h->nranks;
+    auto K = [&](int s) { return S.sn_start[s + 1] - S.sn_start[s]; };
+    auto R = [&](int s) { return (int64_t)(S.rows_ptr[s + 1] - S.rows_ptr[s]); };
+    auto NC = [&](int s) { return S.child_ptr[s + 1] - S.child_ptr[s]; };
+    auto ROWOWN = [&](int s, int64_t a) { return S.col_owner[S.rows[S.rows_ptr[s] + a]]; };
+    // owner of destination column pb of front s (pivot columns: the panel owner)
+    auto DSTOWN = [&](int s, int64_t pb) { return pb < K(s) ? S.top_owner[s] : ROWOWN(s, pb - K(s)); };
+    std::vector<Launch>& fac = h->fac_top;
+    fac.clear();
+    int sync_id = 0;
+    int64_t peer_doubles = 0;
+    auto push = [&](int kind, int64_t off, int nt, int fmax, int level) {
+        if (nt > 0) fac.push_back(Launch{kind, off, nt, fmax, level, 0});
+    };
+    for (int l = 0; l < S.nlevels; ++l) {
+        std::vector<int> top;
+        for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) if (S.owner[S.level_sn[t]] == -1) top.push_back(S.level_sn[t]);
+        if (top.empty()) continue;
+        // zero-fill of the parents that direct children of this level add into (whole blocks: local memory)
+        int64_t off = (int64_t)tasks.size();
+        for (int s : top)
+            if (S.direct[s] && !S.cb_assigned[S.sn_parent[s]] && R(S.sn_parent[s]) > 0) {
+                const int ps = S.sn_parent[s];
+                const int64_t tiles = (R(ps) * R(ps) + ZERO_TILE - 1) / ZERO_TILE;
+                for (int64_t i = 0; i < tiles; ++i) tasks.push_back(make_int4(ps, (int)i, 0, 0));
+            }
+        push(L_ZERO, off, (int)((int64_t)tasks.size() - off), 0, l);
+        // assembly: every non-direct child (top fronts and the subtree roots, whose columns arrived in this rank's
+        // exchange slots), destination columns this rank owns, tasks cut where the owner changes
+        off = (int64_t)tasks.size();
+        int64_t asm_fmax = 0;
+        for (int s : top) {
+            if (NC(s) == 0) continue;
+            std::vector<int> kids;
+            for (int u = S.child_ptr[s]; u < S.child_ptr[s + 1]; ++u) {
+                const int c = S.child_idx[u];
+                if (!S.direct[c] && R(c) > 0) kids.push_back(c);
+            }
+            if (kids.empty()) continue;
+            const bool zero = R(s) > 0;
+            const int64_t f = K(s) + R(s);
+            for (int64_t pb0 = 0; pb0 < f;) {
+                const int own = DSTOWN(s, pb0);
+                int64_t pb1 = pb0 + 1;
+                while (pb1 < f && pb1 < pb0 + ASM_COLS && DSTOWN(s, pb1) == own) ++pb1;
+                if (own == rank) {
+                    const int64_t moff = (int64_t)h->asm_meta.size();
+                    int np = 0;
+                    for (int c : kids) {
+                        const int* rb = S.rel.data() + S.rows_ptr[c];
+                        const int* re = S.rel.data() + S.rows_ptr[c + 1];
+                        const int* it = std::lower_bound(rb, re, (int)pb0);
+                        if (it == re || *it >= pb1) continue;
+                        h->asm_meta.push_back(c); h->asm_meta.push_back((int)(it - rb));
+                        ++np;
+                    }
+                    if (np > 0 || zero) {
+                        tasks.push_back(make_int4(s, (int)pb0, (int)moff, (zero ? 1 : 0) | ((int)(pb1 - pb0) << 4) | (np << 8)));
+                        asm_fmax = std::max<int64_t>(asm_fmax, f);
+                    }
+                }
+                pb0 = pb1;
+            }
+        }
+        push(L_EXTEND, off, (int)((int64_t)tasks.size() - off), (int)std::min<int64_t>(asm_fmax, 1 << 30), l);
+        // panel owner's pass: pivot block and L21 (tiles of kinds 0 and 2), one launch per 32 pivot columns
+        int max_blk = 0;
+        bool own_any = false;
+        std::vector<int> other_owners;
+        for (int s : top) {
+            max_blk = std::max(max_blk, (K(s) + NB - 1) / NB);
+            if (S.top_owner[s] == rank) own_any = true;
+            else if (std::find(other_owners.begin(), other_owners.end(), S.top_owner[s]) == other_owners.end()) other_owners.push_back(S.top_owner[s]);
+        }
+        for (int pass = 1; pass <= 2; ++pass) {
+            for (int g = 0; g < max_blk; ++g) {
+                // tiles of the launch decide the tile height, as in the one-GPU schedule
+                auto ntiles = [&](int s, int rws) -> int {
+                    const int k = K(s);
+                    const int64_t r = R(s), f = k + r;
+                    const int j1 = std::min(k, (g + 1) * NB);
+                    if (pass == 1) return (int)((f - j1 + rws - 1) / rws) + (k - j1 + rws - 1) / rws;
+                    return (int)((r + rws - 1) / rws);
+                };
+                int64_t tiles_total = 0;
+                for (int s : top) {
+                    if (g >= (K(s) + NB - 1) / NB) continue;
+                    if (pass == 1 && S.top_owner[s] != rank) continue;
+                    tiles_total += std::max(1, ntiles(s, PANEL_ROWS));
+                }
+                const int rows = (tiles_total > 0 && tiles_total < 120) ? PANEL_ROWS_TOP : PANEL_ROWS;
+                off = (int64_t)tasks.size();
+                for (int s : top) {
+                    if (g >= (K(s) + NB - 1) / NB) continue;
+                    if (pass == 1) {
+                        if (S.top_owner[s] != rank) continue;
+                        const int nt = std::max(1, ntiles(s, rows));         // someone has to factor D_gg
+                        const int cidx = (int)ncounters++;
+                        for (int t = 0; t < nt; ++t)
+                            tasks.push_back(make_int4(s, (int)(g | (1 << 4) | (nt << 16) | (1u << 30)), t, cidx));
+                    } else {
+                        const int nt = ntiles(s, rows);
+                        for (int t = 0; t < nt; ++t) {
+                            bool mine = false;
+                            for (int64_t a = (int64_t)t * rows; a < std::min<int64_t>(R(s), (int64_t)(t + 1) * rows) && !mine; ++a) mine = ROWOWN(s, a) == rank;
+                            if (mine) tasks.push_back(make_int4(s, (int)(g | (1 << 4) | (1 << 16) | (2u << 30)), t, 0));
+                        }
+                    }
+                }
+                push(L_PANEL, off, (int)((int64_t)tasks.size() - off), g | (rows << 8), l);
+            }
+            if (pass == 1) {
+                // publish the finished panels P_s (pivot block on top of L21), then tell the peers; wait for the others
+                const int64_t s0 = (int64_t)segs.size() / 2;
+                for (int s : top)
+                    if (S.top_owner[s] == rank) {
+                        const int64_t len = ((K(s) + R(s)) * K(s) + 1) & ~(int64_t)1;
+                        segs.push_back(S.Loff[s]); segs.push_back(len);
+                        peer_doubles += len * (NR - 1);
+                    }
+                push(L_REPL, s0, (int)((int64_t)segs.size() / 2 - s0), 0, l);
+                if (own_any) fac.push_back(Launch{L_SIGNAL, (int64_t)sync_id * NR + rank, 1, 0, l, 0});
+                const int64_t w0 = (int64_t)wait_slots.size();
+                for (int o : other_owners) wait_slots.push_back(sync_id * NR + o);
+                push(L_WAIT, w0, (int)other_owners.size(), 0, l);
+                ++sync_id;
+            }
+        }
+        // Schur update of the columns this rank owns
+        off = (int64_t)tasks.size();
+        for (int s : top) {
+            const int64_t r = R(s);
+            const int nt = (int)((r + GEMM_TILE - 1) / GEMM_TILE);
+            const int flags = (NC(s) > 0 ? 1 : 0) | (S.direct[s] ? 2 : 0) | (S.direct[s] && S.cb_assigned[S.sn_parent[s]] ? 4 : 0) | 16 |
+                              (S.direct[s] && r == K(S.sn_parent[s]) + R(S.sn_parent[s]) ? 32 : 0);
+            for (int j = 0; j < nt; ++j) {
+                bool mine = false;
+                for (int64_t b = (int64_t)j * GEMM_TILE; b < std::min<int64_t>(r, (int64_t)(j + 1) * GEMM_TILE) && !mine; ++b) mine = ROWOWN(s, b) == rank;
+                if (!mine) continue;
+                for (int i = 0; i < nt; ++i) tasks.push_back(make_int4(s, i, j, flags));
+            }
+        }
+        push(L_GEMM, off, (int)((int64_t)tasks.size() - off), 0, l);
+        // rows of U12' this rank owns, published to the peers at the end of the refactorization (the solves read all of T_s)
+        for (int s : top) {
+            const int64_t r = R(s);
+            for (int64_t a = 0; a < r;) {
+                int64_t b = a + 1;
+                const int own = ROWOWN(s, a);
+                while (b < r && b < a + 256 && ROWOWN(s, b) == own) ++b;
+                if (own == rank) { trow_tasks.push_back(make_int4(s, (int)a, (int)(b - a), 0)); peer_doubles += (b - a) * K(s) * (NR - 1); }
+                a = b;
+            }
+        }
+    }
+    h->peer_bytes_refactor = 8 * peer_doubles;
 }
 
 int ensure_uploaded(smslu_handle_t h) {
@@ -478,6 +690,12 @@ int ensure_uploaded(smslu_handle_t h) {
         for (int j = 0; j < n; ++j) colowner[j] = S.owner[S.col2sn[j]];
         if ((rc = dev_upload(h, &h->d_colowner, colowner))) return rc;
     }
+    signed char* d_rowown;
+    {   // owner of the global column behind every entry of `rows` (the virtual children's rows: none)
+        std::vector<signed char> rowown(rows_d.size(), (signed char)-1);
+        for (int64_t t = 0; t < S.sum_r; ++t) rowown[t] = (signed char)S.col_owner[S.rows[t]];
+        if ((rc = dev_upload(h, &d_rowown, rowown))) return rc;
+    }
     if ((rc = dev_upload(h, &d_sn_start, S.sn_start))) return rc;
     if ((rc = dev_upload(h, &d_rows_ptr, rows_ptr_d))) return rc;
     if ((rc = dev_upload(h, &d_rows, rows_d))) return rc;
@@ -505,9 +723,23 @@ int ensure_uploaded(smslu_handle_t h) {
     {   // entries of A grouped by the small front that pulls them; the big fronts' entries follow
         const int nsn = S.nsn;
         if (h->annz > INT_MAX) return fail(h, SMSLU_E_ARG, "more than 2^31-1 nonzeros");
-        // this rank assembles the entries of its own fronts; rank 0 also those of the top fronts
+        // this rank assembles the entries of its own fronts and, in the top fronts, the entries of the columns it owns
+        // (pivot columns of a top front: its panel owner; an entry of U12 in global column j: the owner of column j)
         auto small = [&](int s) { return S.small[s] != 0 && S.owner[s] == h->rank; };
-        auto mine = [&](int s) { return S.owner[s] == h->rank || (S.owner[s] == -1 && h->rank == 0); };
+        std::vector<int> cinv;
+        if (S.nranks > 1) { cinv.resize(n); for (int k2 = 0; k2 < n; ++k2) cinv[S.q[k2]] = k2; }
+        std::vector<char> top_mine;               // per nonzero, only filled for entries of top fronts
+        if (S.nranks > 1) {
+            top_mine.assign(h->annz, 0);
+            for (int c = 0; c < n; ++c)
+                for (int64_t t = h->Ap[c]; t < h->Ap[c + 1]; ++t) {
+                    const int s = S.a_sn[t];
+                    if (S.owner[s] != -1) continue;
+                    const int jj = cinv[c];
+                    top_mine[t] = (jj < S.sn_start[s + 1] ? S.top_owner[s] : S.col_owner[jj]) == h->rank;
+                }
+        }
+        auto mine = [&](int s, int64_t t) { return S.owner[s] == h->rank || (S.owner[s] == -1 && top_mine[t]); };
         std::vector<int> a_ptr(nsn + 1, 0);
         for (int64_t t = 0; t < h->annz; ++t) if (small(S.a_sn[t])) ++a_ptr[S.a_sn[t] + 1];
         for (int s = 0; s < nsn; ++s) a_ptr[s + 1] += a_ptr[s];
@@ -519,7 +751,7 @@ int ensure_uploaded(smslu_handle_t h) {
             const int s = S.a_sn[t];
             int64_t o;
             if (small(s)) { o = w[s]++; a_pos[o] = S.a_loc[t]; }
-            else if (mine(s)) { o = nsmall + nb; dst_big[nb++] = S.a_dst[t]; }
+            else if (mine(s, t)) { o = nsmall + nb; dst_big[nb++] = S.a_dst[t]; }
             else continue;
             a_src[o] = (int)t;
             a_row[o] = (int)h->Ai[t];
@@ -551,6 +783,21 @@ int ensure_uploaded(smslu_handle_t h) {
     }
     std::vector<int4> tasks;
     build_schedules(h, tasks);
+    if (S.nranks > 1) {
+        std::vector<int64_t> segs;
+        std::vector<int> wait_slots;
+        std::vector<int4> trow;
+        build_top_fac(h, tasks, segs, wait_slots, trow, h->ncounters);
+        h->n_trow_tasks = (int)trow.size();
+        if ((rc = dev_upload(h, &h->d_segs, segs))) return rc;
+        if ((rc = dev_upload(h, &h->d_wait_slots, wait_slots))) return rc;
+        if ((rc = dev_upload(h, &h->d_trow_tasks, trow))) return rc;
+        if ((rc = dev_alloc(h, &h->d_xflags, (size_t)(S.nlevels + 1) * MAX_RANKS))) return rc;
+        CU(cudaMemset(h->d_xflags, 0, sizeof(int) * (size_t)(S.nlevels + 1) * MAX_RANKS));
+        if ((rc = dev_alloc(h, &h->d_barrier, 1))) return rc;
+        CU(cudaMemset(h->d_barrier, 0, sizeof(int)));
+        h->st.allreduce_doubles_refactor = h->peer_bytes_refactor / 8;
+    }
     if ((rc = dev_upload(h, &h->d_tasks, tasks))) return rc;
     int* d_asm_meta;
     if ((rc = dev_upload(h, &d_asm_meta, h->asm_meta))) return rc;
@@ -587,7 +834,11 @@ int ensure_uploaded(smslu_handle_t h) {
         cx.lmax = tol > 0.0 ? (1.0 + 1.0e-6) / tol : HUGE_VAL;   // a hair above 1/tol: pivots chosen by a host threshold search pass
     }
     cx.a_ptr = d_a_ptr; cx.a_src = d_a_src; cx.a_row = d_a_row; cx.a_pos = d_a_pos;
+    cx.rowown = d_rowown; cx.rank = h->rank; cx.nranks = h->nranks;
+    for (int g = 0; g < MAX_RANKS; ++g) { cx.cb_peer[g] = nullptr; cx.lu_peer[g] = nullptr; cx.xflag_peer[g] = nullptr; }
+    cx.cb_peer[h->rank] = d_cb; cx.lu_peer[h->rank] = d_lu; cx.xflag_peer[h->rank] = h->d_xflags;
     CU(cudaDeviceSynchronize());
+    if (S.nranks > 1 && (rc = map_peers(h))) return rc;
     h->uploaded = true;
     h->st.ms_upload = now_ms() - t0;
     return 0;
@@ -635,7 +886,7 @@ int prof_collect(smslu_handle_t h) {   // stream must be synchronized
 }
 
 int launch_one(smslu_handle_t h, cudaStream_t st, const Launch& L, const double* win, double* zx, int rb) {
-    const int4* tk = h->d_tasks + L.off;
+    const int4* tk = h->d_tasks + (L.kind < L_REPL ? L.off : 0);
     switch (L.kind) {
         case L_ZERO: launch_zero_cb(st, h->cx, tk, L.ntasks); break;
         case L_EXTEND: launch_assemble(st, h->cx, tk, L.ntasks, L.fmax); break;
@@ -646,6 +897,9 @@ int launch_one(smslu_handle_t h, cudaStream_t st, const Launch& L, const double*
         case L_GEMM: launch_gemm_cb(st, h->cx, tk, L.ntasks); break;
         case L_FWD: launch_fwd(st, h->cx, tk, L.ntasks, L.fmax >> 8, win, zx, rb); break;
         case L_BWD: launch_bwd(st, h->cx, tk, L.ntasks, zx, rb); break;
+        case L_REPL: launch_replicate(st, h->cx, h->d_segs + 2 * L.off, L.ntasks); break;
+        case L_SIGNAL: launch_signal(st, h->cx, (int)L.off, h->epoch); break;
+        case L_WAIT: launch_wait(st, h->cx, h->d_wait_slots + L.off, L.ntasks, h->epoch); break;
     }
     return 0;
 }
@@ -680,7 +934,7 @@ int run_schedule(smslu_handle_t h, const std::vector<Launch>& sched, const doubl
         }
         for (size_t t = i; t < j; ++t) {
             const Launch& L = sched[t];
-            if ((rc = prof_begin(h, L.kind))) return rc;
+            if ((rc = prof_begin(h, L.kind >= L_REPL ? SMSLU_K_ALLREDUCE : L.kind))) return rc;
             launch_one(h, lane_stream(L.lane), L, win, zx, rb);
             if ((rc = prof_end(h))) return rc;
         }
@@ -728,7 +982,6 @@ int enqueue_refactor(smslu_handle_t h, const double* av, bool rs_given) {
     if (S.lu_big_end[h->rank] > S.lu_big_begin[h->rank])
         CU(cudaMemsetAsync(h->cx.lu + S.lu_big_begin[h->rank], 0,
                            sizeof(double) * (S.lu_big_end[h->rank] - S.lu_big_begin[h->rank]), zs));
-    if (S.cb_iface_size > 0) CU(cudaMemsetAsync(h->cx.cb, 0, sizeof(double) * S.cb_iface_size, zs));
     launch_scatter(zs, h->nnz_big, h->d_big_dst, h->d_big_row, h->d_big_src, h->d_Rs, av, h->cx.lu);
     if (zs != h->stream) { CU(cudaEventRecord(h->ev_scatter, zs)); h->scatter_pending = true; }
     h->cur_av = av;
@@ -736,15 +989,19 @@ int enqueue_refactor(smslu_handle_t h, const double* av, bool rs_given) {
     if ((rc = run_schedule(h, h->fac, nullptr, nullptr))) return rc;
     if (h->scatter_pending) { CU(cudaStreamWaitEvent(h->stream, h->ev_scatter, 0)); h->scatter_pending = false; }
     if (h->nranks > 1) {
-        // sum the subtrees' contributions to the top of the tree over NVLink, then factor the top
+        // The subtree roots' Schur updates have stored their blocks column by column into the owners' pools.  Barrier
+        // (every rank is past its subtrees, and past the solves that read the previous factors), then the distributed
+        // top: per level the panel owners publish their panels into every pool and signal; Schur updates by column owner.
         if ((rc = prof_begin(h, SMSLU_K_ALLREDUCE))) return rc;
-        NCCLCHK(nccl_api().GroupStart());
-        if (S.lu_top_size > 0) NCCLCHK(nccl_api().AllReduce(h->cx.lu, h->cx.lu, (size_t)S.lu_top_size, ncclDouble, ncclSum, h->comm, h->stream));
-        if (S.cb_iface_size > 0) NCCLCHK(nccl_api().AllReduce(h->cx.cb, h->cx.cb, (size_t)S.cb_iface_size, ncclDouble, ncclSum, h->comm, h->stream));
-        NCCLCHK(nccl_api().GroupEnd());
+        NCCLCHK(nccl_api().AllReduce(h->d_barrier, h->d_barrier, 1, ncclInt, ncclMax, h->comm, h->stream));
         if ((rc = prof_end(h))) return rc;
+        ++h->epoch;
         if ((rc = run_schedule(h, h->fac_top, nullptr, nullptr))) return rc;
+        if ((rc = prof_begin(h, SMSLU_K_ALLREDUCE))) return rc;
+        launch_replicate_rows(h->stream, h->cx, h->d_trow_tasks, h->n_trow_tasks);     // U12' rows to every pool (for the solves)
+        // pivot flags of all ranks; also the barrier behind which every pool holds the complete top factors
         NCCLCHK(nccl_api().AllReduce(h->cx.flag, h->cx.flag, 2, ncclInt, ncclMin, h->comm, h->stream));
+        if ((rc = prof_end(h))) return rc;
     }
     // the solves apply the 32 x 32 diagonal blocks of the big fronts through their inverses
     if ((rc = prof_begin(h, SMSLU_K_PANEL))) return rc;
@@ -934,7 +1191,7 @@ int smslu_analyze(smslu_handle_t h, const int64_t* p, const int64_t* q) {
     int64_t vlen = 0;
     for (int s2 = 0; s2 < S.nsn; ++s2)
         if (S.iface[s2]) vlen += (S.sn_start[s2 + 1] - S.sn_start[s2]) + (S.rows_ptr[s2 + 1] - S.rows_ptr[s2]);
-    st.allreduce_doubles_refactor = h->nranks > 1 ? S.lu_top_size + S.cb_iface_size : 0;
+    st.allreduce_doubles_refactor = 0;     // set at upload: doubles this rank stores into peer pools per refactorization
     st.allreduce_doubles_solve = h->nranks > 1 ? vlen + S.n : 0;
     st.ms_analyze = now_ms() - t0;
     return 0;
@@ -1235,6 +1492,7 @@ int smslu_destroy(smslu_handle_t h) {
     if (h->uploaded || h->stream) {
         cudaSetDevice(h->device);
         if (h->stream) cudaStreamSynchronize(h->stream);
+        for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
         for (void* p : h->dev_allocs) cudaFree(p);
         if (h->ev0) cudaEventDestroy(h->ev0);
         if (h->ev1) cudaEventDestroy(h->ev1);

@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(256) k_assemble(DevCtx cx, const int4* __restr
     const Front F = load_front(cx, s);
     pdl_wait();
     const int k = F.k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int pb1 = pb0 + ASM_COLS < (int)F.f ? pb0 + ASM_COLS : (int)F.f;
+    const int wdt = (tk.w >> 4) & 15 ? (tk.w >> 4) & 15 : ASM_COLS;     // narrower where the columns' owner changes
+    const int pb1 = pb0 + wdt < (int)F.f ? pb0 + wdt : (int)F.f;
     if (tk.w & 1) {
         const int c_lo = pb0 > k ? pb0 - k : 0, c_hi = pb1 - k;      // contribution-block columns owned here
         if (c_hi > c_lo) {
@@ -190,7 +191,8 @@ __global__ void __launch_bounds__(256) k_assemble_smem(DevCtx cx, const int4* __
     const Front F = load_front(cx, s);
     pdl_wait();
     const int k = F.k, f = (int)F.f, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int pb1 = pb0 + ASM_COLS < f ? pb0 + ASM_COLS : f;
+    const int wdt = (tk.w >> 4) & 15 ? (tk.w >> 4) & 15 : ASM_COLS;
+    const int pb1 = pb0 + wdt < f ? pb0 + wdt : f;
     const bool zero = tk.w & 1;
     // address of front entry (pa, pb): P(:, pb) for pb < k; else row pb-k of U12' when pa < k, column pb-k of C
     auto entry = [&](int pa, int pb) -> double* {
@@ -557,7 +559,11 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
     int4 tk = tasks[blockIdx.x];
     const Front F = load_front(cx, tk.x);
     pdl_wait();
-    const int g = tk.y & 15, ngroup = (tk.y >> 4) & 4095, total = tk.y >> 16;
+    const int g = tk.y & 15, ngroup = (tk.y >> 4) & 4095, total = (tk.y >> 16) & 0x3fff;
+    // mode 0: all three kinds of tiles (one GPU).  Partitioned top front: mode 1 = the panel owner's pass, kinds 0 and 2
+    // (the pivot block and L21); mode 2 = every rank's pass over the rows of U12' it owns (kind 1), with the diagonal
+    // block already factored in P (replicated by the owner).
+    const int mode = (int)((unsigned)tk.y >> 30);
     const int k = F.k, j0 = g * NB, w = (k - j0 < NB) ? k - j0 : NB, j1 = j0 + w;
     const int tid = threadIdx.x, lane = tid & 31, warp = uniform_warp_id(), fr = lane >> 2, fc = lane & 3;
     // The step's tiles in canonical order: kind 0 (rows below the diagonal block), kind 1 (rows of U12'), kind 2
@@ -567,9 +573,13 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
     int64_t stride;
     const double* cf;
     auto set_tile = [&](int t) {
-        kind = t < nt0 ? 0 : (t < nt0 + nt1 ? 1 : 2);
-        if (nt0 + nt1 + (k - j1 + ROWS - 1) / ROWS == 0) kind = 0;      // the lone CTA that only factors D_gg
-        tile = kind == 0 ? t : (kind == 1 ? t - nt0 : t - nt0 - nt1);
+        if (mode == 1) { kind = t < nt0 ? 0 : 2; tile = kind == 0 ? t : t - nt0; }
+        else if (mode == 2) { kind = 1; tile = t; }
+        else {
+            kind = t < nt0 ? 0 : (t < nt0 + nt1 ? 1 : 2);
+            if (nt0 + nt1 + (k - j1 + ROWS - 1) / ROWS == 0) kind = 0;      // the lone CTA that only factors D_gg
+            tile = kind == 0 ? t : (kind == 1 ? t - nt0 : t - nt0 - nt1);
+        }
         stride = kind == 0 ? F.f : (kind == 1 ? F.r : 1);
     };
     set_tile(tk.z);
@@ -583,9 +593,10 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
     constexpr bool STAGE_ROWS = ROWS == PANEL_ROWS_TOP;
     constexpr int ALD = KW + 4;
     double* As = Xs + ROWS * CLD;
+    const signed char* __restrict__ rown = cx.rowown + cx.rows_ptr[tk.x];
     auto row_ptr = [&](int64_t idx, double*& b, bool& act) {
         if (kind == 0) { act = j1 + idx < F.f; b = F.P + j1 + idx; }
-        else if (kind == 1) { act = idx < F.r; b = F.T + idx; }
+        else if (kind == 1) { act = idx < F.r && (mode != 2 || rown[idx] == cx.rank); b = F.T + idx; }
         else { act = j1 + idx < k; b = F.P + (j1 + idx) * F.f; }
     };
     // ---- S: stage D_gg and the coefficient blocks
@@ -679,7 +690,7 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
         for (int j = 0; j < 2; ++j)
             *reinterpret_cast<double2*>(&D[i0 + fr][ch + 8 * j + 2 * fc]) = make_double2(acc[j][0], acc[j][1]);
     };
-    if (j0 > 0) diag_piece((warp >> 1) * 8, (warp & 1) * 16);       // 8 pieces, 8 warps
+    if (j0 > 0 && mode != 2) diag_piece((warp >> 1) * 8, (warp & 1) * 16);       // 8 pieces, 8 warps
     static_assert(NW == 8, "one diagonal piece per warp");
     __syncthreads();
     TRACEP(3);
@@ -697,6 +708,7 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
         double myr = 0.0;                          // 1 / u_jj of this lane's row
         int bad = NB;                              // first bad pivot (uniform across the warp)
         bool big_l = false;                        // threshold test: some multiplier above 1 / pivot_tol
+        if (mode != 2) {
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
             const double piv = __shfl_sync(0xffffffffu, x[j], j);
@@ -708,6 +720,7 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
             x[j] = lane > j ? l : x[j];
 #pragma unroll
             for (int c = j + 1; c < NB; ++c) x[c] -= l * __shfl_sync(0xffffffffu, x[c], j);
+        }
         }
         rd[lane] = myr;
         if (big_l && lane < w) atomicMin(cx.flag + 1, F.c0 + j0);
@@ -730,7 +743,7 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
     TRACEP(4);
     __syncthreads();
     TRACEP(5);
-    if (warp == 0) {
+    if (warp == 0 && mode != 2) {
         // this CTA's reads of the raw diagonal block completed in phase S; the CTA that arrives last
         // stores the factors (column by column: lanes = rows) and the reciprocal pivots
         int last = 0;
@@ -804,7 +817,10 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
 //   without bit1 V overwrites C in place.
 constexpr int GEMM_LDS = GEMM_TILE + 4;   // row stride = 4 (mod 16) doubles: fragment loads are conflict-free
 
-__global__ void __launch_bounds__(256) k_gemm_cb(DevCtx cx, const int4* __restrict__ tasks) {
+#ifndef GEMM_MINB
+#define GEMM_MINB 2
+#endif
+__global__ void __launch_bounds__(256, GEMM_MINB) k_gemm_cb(DevCtx cx, const int4* __restrict__ tasks) {
     extern __shared__ __align__(16) double gsm[];         // 2 stages x (As[NB][GEMM_LDS] | Bs[NB][GEMM_LDS])
     pdl_trigger();
     int4 tk = tasks[blockIdx.x];
@@ -815,36 +831,72 @@ __global__ void __launch_bounds__(256) k_gemm_cb(DevCtx cx, const int4* __restri
     const double* __restrict__ A = F.P + F.k;
     const double* __restrict__ B = F.T;
     const bool beta = tk.w & 1, direct = tk.w & 2, assign = tk.w & 4;
+    // partitioned factorization: bit3 = this front is a subtree root below the cut: column b of V goes to the rank that
+    // owns global column rows[b], into that rank's copy of the block (peer memory over NVLink, or this rank's own);
+    // bit4 = this front is in the distributed top: only the columns this rank owns are updated
+    const bool xchg = tk.w & 8, mine_only = tk.w & 16;
+    const signed char* __restrict__ rown = cx.rowown + cx.rows_ptr[tk.x];
     // warp tile: 32 rows x 16 columns = 4 x 2 DMMA tiles; 8 warps cover 64 x 64
     const int wm = (warp & 1) * 32, wn = (warp >> 1) * 16;
     const int fr = lane >> 2, fc = lane & 3;            // fragment row / k (A), n / k (B), row / column pair (C)
-    // stage one K chunk (32 columns of L21, 32 rows of U12) with cp.async; rows beyond the block are zero-filled
+    // bit5 = the child's row list IS the parent's front (a link of a chain of fronts cut out of one wide separator):
+    // entry (row, col) of V lands at front position (row, col) of the parent, no index map needed
+    const bool ident = tk.w & 32;
+    // interior tile: all 64 x 64 entries exist, no bounds checks in the prologue / epilogue
+    const bool full = m0 + GEMM_TILE <= F.r && n0 + GEMM_TILE <= F.r;
+    // stage one K chunk (32 columns of L21, 32 rows of U12) with cp.async; rows beyond the block are zero-filled.
+    // Thread (a, p0) copies element a of columns p0, p0 + 4, ... of the chunk: running pointers, no index arithmetic.
+    const int sa = tid & (GEMM_TILE - 1), sp0 = tid >> 6;
+    const bool oka = m0 + sa < F.r, okb = n0 + sa < F.r;
+    const double* __restrict__ Ath = A + (oka ? m0 + sa : 0) + (int64_t)sp0 * F.f;
+    const double* __restrict__ Bth = B + (okb ? n0 + sa : 0) + (int64_t)sp0 * F.r;
+    const int64_t astep = 4 * F.f, bstep = 4 * F.r;
     auto stage = [&](int kc, int buf) {
-        double* As = gsm + buf * (2 * NB * GEMM_LDS);
-        double* Bs = As + NB * GEMM_LDS;
-        const int kw = (k - kc < NB) ? k - kc : NB;
-        const int a = tid & (GEMM_TILE - 1);
-        const int64_t ra = m0 + a, rb = n0 + a;
-        const bool oka = ra < F.r, okb = rb < F.r;
-        for (int p = tid >> 6; p < NB; p += 4) {
-            const bool in = p < kw;
-            cp_async8(As + p * GEMM_LDS + a, A + ((in && oka) ? ra + (int64_t)(kc + p) * F.f : 0), in && oka);
-            cp_async8(Bs + p * GEMM_LDS + a, B + ((in && okb) ? rb + (int64_t)(kc + p) * F.r : 0), in && okb);
+        double* as = gsm + buf * (2 * NB * GEMM_LDS) + sp0 * GEMM_LDS + sa;
+        double* bs = as + NB * GEMM_LDS;
+        const double* __restrict__ ap = Ath + (int64_t)kc * F.f;
+        const double* __restrict__ bp = Bth + (int64_t)kc * F.r;
+        if (kc + NB <= k) {
+#pragma unroll
+            for (int u = 0; u < NB / 4; ++u, ap += astep, bp += bstep) {
+                cp_async8(as + u * 4 * GEMM_LDS, ap, oka);
+                cp_async8(bs + u * 4 * GEMM_LDS, bp, okb);
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < NB / 4; ++u, ap += astep, bp += bstep) {
+                const bool in = kc + sp0 + 4 * u < k;
+                cp_async8(as + u * 4 * GEMM_LDS, in ? ap : A, in && oka);
+                cp_async8(bs + u * 4 * GEMM_LDS, in ? bp : B, in && okb);
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     stage(0, 0);
     double acc[4][2][2];
     // the C loads are in flight while the operand tiles arrive
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
+    if (beta && full) {
+        const double* __restrict__ c0 = F.C + (m0 + wm + fr) + (n0 + wn + 2 * fc) * F.r;
 #pragma unroll
         for (int j = 0; j < 2; ++j)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int64_t row = m0 + wm + 8 * i + fr, col = n0 + wn + 8 * j + 2 * fc + e;
-                acc[i][j][e] = (beta && row < F.r && col < F.r) ? F.C[row + col * F.r] : 0.0;
+                const double* __restrict__ cc = c0 + (8 * j + e) * F.r;
+                const bool on = !mine_only || rown[n0 + wn + 8 * j + 2 * fc + e] == cx.rank;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[i][j][e] = on ? cc[8 * i] : 0.0;
             }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int64_t row = m0 + wm + 8 * i + fr, col = n0 + wn + 8 * j + 2 * fc + e;
+                    acc[i][j][e] = (beta && row < F.r && col < F.r && (!mine_only || rown[col] == cx.rank)) ? F.C[row + col * F.r] : 0.0;
+                }
+    }
     int buf = 0;
     for (int kc = 0; kc < k; kc += NB, buf ^= 1) {
         if (kc + NB < k) {
@@ -873,31 +925,70 @@ __global__ void __launch_bounds__(256) k_gemm_cb(DevCtx cx, const int4* __restri
         __syncthreads();                                 // the stage is refilled two iterations from now
     }
     if (!direct) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
+        const int64_t coff = F.C - cx.cb;
+        if (full && !xchg) {
+            double* __restrict__ c0 = F.C + (m0 + wm + fr) + (n0 + wn + 2 * fc) * F.r;
 #pragma unroll
             for (int j = 0; j < 2; ++j)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const int64_t row = m0 + wm + 8 * i + fr, col = n0 + wn + 8 * j + 2 * fc + e;
-                    if (row < F.r && col < F.r) F.C[row + col * F.r] = acc[i][j][e];
+                    if (mine_only && rown[n0 + wn + 8 * j + 2 * fc + e] != cx.rank) continue;
+                    double* __restrict__ cc = c0 + (8 * j + e) * F.r;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) cc[8 * i] = acc[i][j][e];
                 }
+            return;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int64_t col = n0 + wn + 8 * j + 2 * fc + e;
+                if (col >= F.r) continue;
+                double* __restrict__ dst = F.C;
+                if (xchg) dst = cx.cb_peer[rown[col]] + coff;            // the column's owner (maybe this rank)
+                else if (mine_only && rown[col] != cx.rank) continue;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int64_t row = m0 + wm + 8 * i + fr;
+                    if (row < F.r) dst[row + col * F.r] = acc[i][j][e];
+                }
+            }
         return;
     }
     const Front Q = load_front(cx, cx.sn_parent[tk.x]);
+    if (ident && full && m0 >= Q.k && n0 >= Q.k) {
+        // link of a chain, tile inside the parent's contribution block: a shifted copy
+        double* __restrict__ d0 = Q.C + (m0 - Q.k + wm + fr) + (n0 - Q.k + wn + 2 * fc) * Q.r;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                if (mine_only && rown[n0 + wn + 8 * j + 2 * fc + e] != cx.rank) continue;
+                double* __restrict__ dd = d0 + (8 * j + e) * Q.r;
+                if (assign) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) dd[8 * i] = acc[i][j][e];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) dd[8 * i] += acc[i][j][e];
+                }
+            }
+        return;
+    }
     const int* __restrict__ rel = cx.rel + cx.rows_ptr[tk.x];
 #pragma unroll
     for (int j = 0; j < 2; ++j)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int64_t col = n0 + wn + 8 * j + 2 * fc + e;
-            if (col >= F.r) continue;
-            const int64_t pb = rel[col];
+            if (col >= F.r || (mine_only && rown[col] != cx.rank)) continue;
+            const int64_t pb = ident ? col : rel[col];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int64_t row = m0 + wm + 8 * i + fr;
                 if (row >= F.r) continue;
-                const int64_t pa = rel[row];
+                const int64_t pa = ident ? row : rel[row];
                 const double v = acc[i][j][e];
                 if (pb < Q.k) Q.P[pa + pb * Q.f] += v;
                 else if (pa < Q.k) Q.T[(pb - Q.k) + pa * Q.r] += v;
@@ -933,7 +1024,7 @@ __global__ void __launch_bounds__(32 * INV_WARPS) k_diag_inverse(DevCtx cx, cons
         const double* __restrict__ src = F.P + (j0 + lane) + (int64_t)j0 * F.f;
 #pragma unroll 8
         for (int c = 0; c < NB; ++c) B[lane][c] = (lane < w && c < w) ? src[(int64_t)c * F.f] : (lane == c ? 1.0 : 0.0);
-        rds[wl][lane] = lane < w ? cx.dinv[F.c0 + j0 + lane] : 1.0;
+        rds[wl][lane] = lane < w ? 1.0 / src[(int64_t)lane * F.f] : 1.0;     // = dinv (same division as in the factor kernels)
     }
     __syncwarp();
     double x[NB], y[NB];
@@ -1364,6 +1455,62 @@ __global__ void k_mask_owned(int n, const int* __restrict__ colowner, int rank, 
     }
 }
 
+// ------------------------------------------------------------------ partitioned top: replication and sync
+// Copy segments [off, off + len) (doubles, both even) of this rank's factor pool to the same offsets of every
+// peer's pool: the panel owner publishes P_s (pivot block + L21) of a top front.  One read, nranks - 1 remote
+// writes over NVLink, 16 bytes per lane.  segs: (off, len) pairs; blockIdx.y = segment.
+__global__ void __launch_bounds__(256) k_replicate(DevCtx cx, const int64_t* __restrict__ segs) {
+    const int64_t off = segs[2 * blockIdx.y], len2 = segs[2 * blockIdx.y + 1] >> 1;
+    const double2* __restrict__ src = reinterpret_cast<const double2*>(cx.lu + off);
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < len2; i += (int64_t)gridDim.x * 256) {
+        const double2 v = src[i];
+        for (int g = 0; g < cx.nranks; ++g)
+            if (g != cx.rank) reinterpret_cast<double2*>(cx.lu_peer[g] + off)[i] = v;
+    }
+}
+// Rows of U12' (T_s, r x k, column-major) this rank owns and computed, to every peer: the solves read the whole of T_s
+// on every rank.  task: x = supernode, y = first row, z = number of rows (a run with one owner), one CTA per task.
+__global__ void __launch_bounds__(256) k_replicate_rows(DevCtx cx, const int4* __restrict__ tasks) {
+    const int4 tk = tasks[blockIdx.x];
+    const int s = tk.x, k = cx.sn_start[s + 1] - cx.sn_start[s];
+    const int64_t r = cx.rows_ptr[s + 1] - cx.rows_ptr[s], off = cx.Uoff[s] + tk.y;
+    for (int e = threadIdx.x; e < tk.z * k; e += 256) {
+        const int c = e / tk.z, a = e - c * tk.z;
+        const int64_t o = off + a + (int64_t)c * r;
+        const double v = cx.lu[o];
+        for (int g = 0; g < cx.nranks; ++g)
+            if (g != cx.rank) cx.lu_peer[g][o] = v;
+    }
+}
+// Cross-GPU signalling (each rank drives its own GPU, so a waiting kernel never shares a device with its producer):
+// k_signal publishes `epoch` in slot `slot` of every peer's flag array after making this rank's earlier writes visible
+// system-wide; k_wait spins on this rank's own flags.  A wait that lasts longer than ~4 s gives up and raises the
+// pivot flag to -3, so that a lost peer shows up as an error instead of a hang.
+__global__ void k_signal(DevCtx cx, int slot, int epoch) {
+    __threadfence_system();
+    const int g = threadIdx.x;
+    if (g < cx.nranks && g != cx.rank) {
+        int* f = cx.xflag_peer[g] + slot;
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
+    }
+}
+__global__ void k_wait(DevCtx cx, const int* __restrict__ slots, int nslots, int epoch) {
+    const int i = threadIdx.x;
+    if (i < nslots) {
+        const int* f = cx.xflag_peer[cx.rank] + slots[i];
+        const long long t0 = clock64();
+        for (;;) {
+            int v;
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if (v >= epoch) break;
+            if (clock64() - t0 > 8000000000LL) { atomicMin(cx.flag, -3); break; }
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+}
+
 // ------------------------------------------------------------------ solves, small fronts
 // One warp per front (k <= 32, f <= SMALL_F_MAX), FPC fronts per CTA, no block-wide barriers.
 // Forward: v = [w[cols]; 0] + children's update vectors (gathered through rel, child by child),
@@ -1569,6 +1716,16 @@ void launch_front_small(cudaStream_t st, const DevCtx& cx, const int4* tasks, in
     else if (fmax <= 64)
         launch_pdl(k_small_factor_reg<64, 1>, ntasks, 64, sizeof(double) * reg_group_doubles(64), st, cx, tasks, ntasks, av, Rs);
     else launch_small_class<96, 3, 1>(st, cx, tasks, ntasks, fmax, av, Rs);
+}
+void launch_replicate(cudaStream_t st, const DevCtx& cx, const int64_t* segs, int nsegs) {
+    if (nsegs > 0) k_replicate<<<dim3(148, nsegs), 256, 0, st>>>(cx, segs);
+}
+void launch_replicate_rows(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks) {
+    if (ntasks > 0) k_replicate_rows<<<ntasks, 256, 0, st>>>(cx, tasks);
+}
+void launch_signal(cudaStream_t st, const DevCtx& cx, int slot, int epoch) { k_signal<<<1, 32, 0, st>>>(cx, slot, epoch); }
+void launch_wait(cudaStream_t st, const DevCtx& cx, const int* slots, int nslots, int epoch) {
+    if (nslots > 0) k_wait<<<1, 32, 0, st>>>(cx, slots, nslots, epoch);
 }
 #define RB_DISPATCH(rb, CALL) do { if ((rb) == 1) { CALL(1); } else if ((rb) == 4) { CALL(4); } else { CALL(8); } } while (0)
 void launch_vgather(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const int* vlist, int rb) {

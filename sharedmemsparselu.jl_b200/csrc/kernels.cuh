@@ -30,6 +30,7 @@ constexpr int BWD_ROWS = 256;     // rows of U12' per backward CTA
 constexpr int ZERO_TILE = 8192;
 constexpr int RB_MAX = 8;         // most right-hand sides swept together by the solve kernels
 constexpr int ASM_COLS = 8;       // destination columns of a parent front per assembly CTA
+constexpr int MAX_RANKS = 8;      // GPUs of one NVSwitch box
 constexpr int ASM_SMEM_ROWS = 1536; // parents up to this many rows are assembled through shared memory (96 KB per CTA at most)
 
 struct DevCtx {
@@ -62,6 +63,14 @@ struct DevCtx {
     const int* a_pos;   // row | col << 16 inside the front
     // assembly kernel: per task, the (child, first column in range) pairs it pulls
     const int* asm_meta;
+    // partition over several GPUs (one process each), see DESIGN.md "Multi-GPU": owner of the global column behind
+    // every entry of `rows` (-1: not a top column); this rank; the ranks' contribution / factor pools and sync flags
+    // mapped into this process (CUDA IPC; own pool at index `rank`)
+    const signed char* rowown;
+    int rank, nranks;
+    double* cb_peer[MAX_RANKS];
+    double* lu_peer[MAX_RANKS];
+    int* xflag_peer[MAX_RANKS];
 };
 
 // ---- refactorization
@@ -74,6 +83,13 @@ void launch_assemble(cudaStream_t st, const DevCtx& cx, const int4* tasks, int n
 void launch_front_small(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int fmax,
                         const double* av, const double* Rs);
 // rb = right-hand sides swept together (1, 4 or 8); vectors are interleaved [i * rb + q]
+// ---- partitioned top of the tree (nranks > 1)
+// copy factor-pool segments (tasks: x = offset / 2, y = length / 2 in double2 units ... as int64 pairs) to every peer
+void launch_replicate(cudaStream_t st, const DevCtx& cx, const int64_t* segs, int nsegs);
+// rows of U12' this rank owns, of the top fronts listed in tasks (x = supernode, y = first row, z = rows), to every peer
+void launch_replicate_rows(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks);
+void launch_signal(cudaStream_t st, const DevCtx& cx, int slot, int epoch);
+void launch_wait(cudaStream_t st, const DevCtx& cx, const int* slots, int nslots, int epoch);
 void launch_vgather(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const int* vlist, int rb);
 void launch_mask_owned(cudaStream_t st, int n, const int* colowner, int rank, double* z, int rb);
 void launch_small_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const double* win, double* zout, int rb);

@@ -762,7 +762,7 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
         std::vector<int> q, best_q;
         std::vector<char> is_top(nsn, 0), best_top;
         for (int s = 0; s < nsn; ++s) if (S.sn_parent[s] == -1) q.push_back(s);
-        double top_w = 0.0, best_cost = top_w + lpt(q, nullptr);
+        double top_w = 0.0, best_cost = 1e300;      // at least the roots go to the top
         best_q = q; best_top = is_top;
         for (int it = 0; it < 96 * NR && !q.empty(); ++it) {
             int hi = -1;
@@ -774,7 +774,9 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
             is_top[s] = 1;
             top_w += wself[s];
             for (int u = S.child_ptr[s]; u < S.child_ptr[s + 1]; ++u) q.push_back(S.child_idx[u]);
-            const double cost = top_w + lpt(q, nullptr);
+            // the top is shared by the ranks (column-distributed Schur updates; panels and the chain of dependent
+            // steps are not): count it at 60 % parallel efficiency
+            const double cost = top_w / (0.6 * NR) + lpt(q, nullptr);
             if (cost < best_cost) { best_cost = cost; best_q = q; best_top = is_top; }
         }
         std::vector<int> assign;
@@ -785,6 +787,19 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
             if (S.owner[s] == -2) S.owner[s] = S.owner[S.sn_parent[s]];
         for (int s = 0; s < nsn; ++s)
             if (S.owner[s] >= 0 && S.sn_parent[s] != -1 && S.owner[S.sn_parent[s]] == -1) S.iface[S.sn_parent[s]] = 1;
+    }
+    S.top_owner.assign(nsn, -1);
+    S.col_owner.assign(n, -1);
+    S.xroot.assign(nsn, 0);
+    if (NR > 1) {
+        int t = 0;                                // consecutive fronts of a chain go to consecutive ranks
+        for (int s = 0; s < nsn; ++s) {
+            if (S.owner[s] != -1) continue;
+            S.top_owner[s] = t++ % NR;
+            for (int j = S.sn_start[s]; j < S.sn_start[s + 1]; ++j) S.col_owner[j] = S.top_owner[s];
+        }
+        for (int s = 0; s < nsn; ++s)
+            S.xroot[s] = S.owner[s] >= 0 && S.sn_parent[s] != -1 && S.owner[S.sn_parent[s]] == -1;
     }
     step_mark("8 storage plan");
     // ---------------------------------------------------------------- 8. storage plan
@@ -797,7 +812,8 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
     S.small.assign(nsn, 0);
     for (int s = 0; s < nsn; ++s) {
         const int64_t k = S.sn_start[s + 1] - S.sn_start[s], r = S.rows_ptr[s + 1] - S.rows_ptr[s];
-        S.small[s] = S.owner[s] >= 0 && k <= opt.small_k_max && k + r <= opt.small_front_max;
+        // (a subtree root hands its contribution block to other ranks from the Schur-update kernel: never "small")
+        S.small[s] = S.owner[s] >= 0 && !S.xroot[s] && k <= opt.small_k_max && k + r <= opt.small_front_max;
     }
     auto is_small = [&](int s) { return S.small[s] != 0; };
     // Pool order: top fronts (summed across ranks in one all-reduce), then per rank its big fronts
@@ -842,18 +858,20 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
         if (rc - inside == rs) S.cb_assigned[s] = 1;
     }
     {
-        // contribution blocks of the interface fronts (top fronts with children below the cut) live in a
-        // permanent, contiguous region at the start of the pool: they are zero-filled at the start of a
-        // refactorization, receive the subtrees' contributions and are all-reduced in one call.
+        // Exchange slots: the contribution block of every subtree root lives in a permanent region at the start of
+        // the pool, at the same offset on every rank.  Its owner's Schur update writes column b of the block into
+        // the slot of the rank that owns global column rows[b] (its own memory or a peer's, over NVLink); the top
+        // fronts' assembly then reads its own columns locally.
         int64_t ioff = 0;
         std::vector<char> have(nsn, 0);
         for (int s = 0; s < nsn; ++s)
-            if (S.iface[s]) {
+            if (S.xroot[s]) {
                 int64_t r = S.rows_ptr[s + 1] - S.rows_ptr[s];
                 S.CBoff[s] = ioff; ioff += align2(r * r);
                 have[s] = 1;
             }
-        S.cb_iface_size = ioff;
+        S.cb_xchg_size = ioff;
+        S.cb_iface_size = 0;
         Arena arena;
         auto need = [&](int s) {
             if (have[s]) return;
@@ -870,7 +888,7 @@ int analyze(int n, const int64_t* Ap, const int64_t* Ai, const int* p_in, const 
                 int s = S.level_sn[t];
                 for (int u = S.child_ptr[s]; u < S.child_ptr[s + 1]; ++u) {
                     int c = S.child_idx[u];
-                    if (S.iface[c]) continue;
+                    if (S.xroot[c]) continue;
                     int64_t r = S.rows_ptr[c + 1] - S.rows_ptr[c];
                     arena.release(S.CBoff[c] - ioff, align2(r * r));
                 }

@@ -69,8 +69,18 @@ struct Symbolic {
     int64_t lu_big_size = 0;          // [0, lu_big_size) holds the top and big fronts, the small ones follow
     // partition over nranks GPUs (nranks == 1: everything is owned by rank 0, no top set)
     int nranks = 1;
-    std::vector<int> owner;           // rank that factors the supernode; -1 = top of the tree (replicated)
+    std::vector<int> owner;           // rank that factors the supernode; -1 = top of the tree (distributed by columns)
     std::vector<char> iface;          // top front that receives contributions from below the cut
+    // Top of the tree, distributed: every top supernode has a panel owner (it factors the pivot block and L21 and
+    // replicates them); every top COLUMN j belongs to the panel owner of its supernode, and that rank holds / updates
+    // column j of every trailing matrix it appears in (rows of U12', columns of contribution blocks).  A child's
+    // contribution-block column and the parent entry it is added to have the same global column, hence the same owner:
+    // extend-add inside the top needs no communication.
+    std::vector<int> top_owner;       // per supernode: panel owner of a top supernode, else -1
+    std::vector<int> col_owner;       // per permuted column: owner of a top column, else -1
+    std::vector<char> xroot;          // subtree root (owner >= 0, parent in the top): its contribution block is
+                                      // delivered column by column to the column owners (slots [0, cb_xchg_size))
+    int64_t cb_xchg_size = 0;
     std::vector<char> small;          // handled by the shared-memory kernels (never a top front)
     int64_t lu_top_size = 0;          // [0, lu_top_size): panels of the top fronts (all-reduced)
     std::vector<int64_t> lu_big_begin, lu_big_end;   // per rank: its big fronts' panels

@@ -86,6 +86,13 @@ class HostExec:
         L.hx_buffer.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_longlong)]
         L.hx_factor_phase.restype = C.c_longlong
         L.hx_factor_phase.argtypes = [C.c_void_p, f64p, C.c_void_p, C.c_int, C.c_int]
+        L.hx_top_levels.restype = C.c_int
+        L.hx_top_levels.argtypes = [C.c_void_p, i64p]
+        L.hx_top_segments.restype = C.c_int
+        L.hx_top_segments.argtypes = [C.c_void_p, C.c_int, C.c_int, i64p]
+        L.hx_top_panels.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.hx_top_update.restype = C.c_longlong
+        L.hx_top_update.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.hx_lsolve_phase.argtypes = [C.c_void_p, f64p, C.c_int, C.c_int]
         L.hx_rsolve_phase.argtypes = [C.c_void_p, f64p, C.c_int, C.c_int]
         L.hx_mask_owned.argtypes = [C.c_void_p, f64p, C.c_int]
@@ -180,11 +187,27 @@ class PartitionedWalk:
     def factor(self, Ax, Rs):
         Ax = np.ascontiguousarray(Ax, np.float64); Rs = np.ascontiguousarray(Rs, np.float64)
         self.L.hx_factor_phase(self.h, Ax, Rs.ctypes.data_as(C.c_void_p), self.rank, 0)
-        if self.nranks > 1:
-            self.allreduce(self._view(0, self.info["lu_top_size"]))      # panels of the top fronts
-            self.allreduce(self._view(1, self.info["cb_iface_size"]))    # interface contribution blocks
-            return int(self.L.hx_factor_phase(self.h, Ax, Rs.ctypes.data_as(C.c_void_p), self.rank, 1))
-        return 0
+        if self.nranks == 1:
+            return 0
+        # exchange 1: the subtree roots' contribution blocks reach the column owners (the GPU path stores every column
+        # straight into its owner's pool; here every rank's slots are zero except the producer's, so a sum delivers them)
+        self.allreduce(self._view(1, self.info["cb_iface_size"]))
+        lv = np.zeros(self.info["nlevels"], np.int64)
+        nl = self.L.hx_top_levels(self.h, lv)
+        segs = np.zeros(2 * self.info["nsn"] + 2, np.int64)
+        lu = self._view(0, self.info["lu_size"])
+        bad = -1
+        for l in lv[:nl]:
+            self.L.hx_top_panels(self.h, self.rank, int(l))
+            # exchange 2 (per level): the panel owners publish P_s (non-owners hold zeros there)
+            for i in range(self.L.hx_top_segments(self.h, int(l), 0, segs)):
+                self.allreduce(lu[segs[2 * i]:segs[2 * i] + segs[2 * i + 1]])
+            bad = int(self.L.hx_top_update(self.h, self.rank, int(l)))
+        # exchange 3: every rank publishes the rows of U12' it owns (zeros elsewhere) -- the solves read all of T_s
+        for l in lv[:nl]:
+            for i in range(self.L.hx_top_segments(self.h, int(l), 1, segs)):
+                self.allreduce(lu[segs[2 * i]:segs[2 * i] + segs[2 * i + 1]])
+        return bad
 
     def solve(self, b):
         n = self.n

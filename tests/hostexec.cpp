@@ -59,7 +59,7 @@ void* hx_create(int64_t n, const int64_t* Ap, const int64_t* Ai, int ordering, c
 void hx_free(void* hv) { delete (HX*)hv; }
 
 // info: n, nsn, nlevels, lu_size, cb_size, nnzL_exact, nnzL_stored, sum_r, max_front, max_k, max_children,
-//       nranks, lu_top_size, cb_iface_size, vbuf length, number of top supernodes
+//       nranks, lu_top_size, cb_xchg_size (exchange slots of the subtree roots), vbuf length, number of top supernodes
 void hx_info(void* hv, int64_t* out, double* flops) {
     HX* h = (HX*)hv;
     const Symbolic& S = h->S;
@@ -67,7 +67,7 @@ void hx_info(void* hv, int64_t* out, double* flops) {
     for (int s = 0; s < S.nsn; ++s) ntop += S.owner[s] == -1;
     int64_t v[] = {S.n, S.nsn, S.nlevels, S.lu_size, S.cb_size, S.nnzL_exact, S.nnzL_stored,
                    S.sum_r, S.max_front, S.max_k, S.max_children,
-                   S.nranks, S.lu_top_size, S.cb_iface_size, (int64_t)h->vbuf.size(), ntop};
+                   S.nranks, S.lu_top_size, S.cb_xchg_size, (int64_t)h->vbuf.size(), ntop};
     memcpy(out, v, sizeof(v));
     flops[0] = S.flops_exact;
     flops[1] = S.flops_stored;
@@ -110,19 +110,27 @@ int64_t hx_factor_phase(void* hv, const double* Ax, const double* Rs, int rank, 
         h->cb.assign(S.cb_size, 0.0);
         h->zeroed.assign(S.nsn, 0);
         h->bad = -1;
+        std::vector<int> cinv(n);
+        for (int k2 = 0; k2 < n; ++k2) cinv[S.q[k2]] = k2;
         for (int c = 0; c < n; ++c)
             for (int64_t t = h->Ap[c]; t < h->Ap[c + 1]; ++t) {
-                const int o = S.owner[S.a_sn[t]];
-                if (o == rank || (o == -1 && rank == 0)) h->lu[S.a_dst[t]] += h->Rs[h->Ai[t]] * Ax[t];
+                const int s = S.a_sn[t], o = S.owner[s];
+                bool mine = o == rank;
+                if (o == -1) {   // top front: pivot columns belong to the panel owner, an entry of U12 to its column's owner
+                    const int jj = cinv[c];
+                    mine = (jj < S.sn_start[s + 1] ? S.top_owner[s] : S.col_owner[jj]) == rank;
+                }
+                if (mine) h->lu[S.a_dst[t]] += h->Rs[h->Ai[t]] * Ax[t];
             }
     }
+    if (phase == 1) return h->bad;      // the distributed top is walked level by level: hx_top_panels / hx_top_update
     int64_t& bad = h->bad;
     std::vector<char>& zeroed = h->zeroed;
     for (int l = 0; l < S.nlevels; ++l)
         for (int u = S.level_ptr[l]; u < S.level_ptr[l + 1]; ++u) {
             const int s = S.level_sn[u];
             const bool own = S.owner[s] == mine;
-            if (!own && !(phase == 0 && S.owner[s] == -1)) continue;
+            if (!own) continue;        // (a top parent pulls the subtree roots' blocks in hx_top_panels)
             const int c0 = S.sn_start[s];
             const int64_t k = S.sn_start[s + 1] - c0, r = S.rows_ptr[s + 1] - S.rows_ptr[s], f = k + r;
             double* P = h->lu.data() + S.Loff[s];
@@ -196,6 +204,132 @@ int64_t hx_factor_phase(void* hv, const double* Ax, const double* Rs, int rank, 
             }
         }
     return bad;
+}
+
+// ---- the distributed top of the tree (nranks > 1), mirroring the GPU schedule (api.cu: build_top_fac) -------------
+// levels that hold top fronts
+int hx_top_levels(void* hv, int64_t* out) {
+    const Symbolic& S = ((HX*)hv)->S;
+    int n = 0;
+    for (int l = 0; l < S.nlevels; ++l) {
+        bool any = false;
+        for (int u = S.level_ptr[l]; u < S.level_ptr[l + 1]; ++u) any |= S.owner[S.level_sn[u]] == -1;
+        if (any) out[n++] = l;
+    }
+    return n;
+}
+// (offset, length) of the panels P_s of the level's top fronts (kind 0) or of their U12' blocks T_s (kind 1)
+int hx_top_segments(void* hv, int level, int kind, int64_t* out) {
+    const Symbolic& S = ((HX*)hv)->S;
+    int n = 0;
+    for (int u = S.level_ptr[level]; u < S.level_ptr[level + 1]; ++u) {
+        const int s = S.level_sn[u];
+        if (S.owner[s] != -1) continue;
+        const int64_t k = S.sn_start[s + 1] - S.sn_start[s], r = S.rows_ptr[s + 1] - S.rows_ptr[s];
+        out[2 * n] = kind == 0 ? S.Loff[s] : S.Uoff[s];
+        out[2 * n + 1] = kind == 0 ? (k + r) * k : r * k;
+        ++n;
+    }
+    return n;
+}
+// Step 1 of a level: assembly of the destination columns this rank owns (children: top fronts and subtree roots, whose
+// blocks the caller has delivered), then the panel owner factors the pivot block and L21 of its fronts.
+void hx_top_panels(void* hv, int rank, int level) {
+    HX* h = (HX*)hv;
+    const Symbolic& S = h->S;
+    for (int u = S.level_ptr[level]; u < S.level_ptr[level + 1]; ++u) {
+        const int s = S.level_sn[u];
+        if (S.owner[s] != -1) continue;
+        const int c0 = S.sn_start[s];
+        const int64_t k = S.sn_start[s + 1] - c0, r = S.rows_ptr[s + 1] - S.rows_ptr[s], f = k + r;
+        double* P = h->lu.data() + S.Loff[s];
+        double* T = h->lu.data() + S.Uoff[s];
+        double* C = h->cb.data() + S.CBoff[s];
+        const int* rows = S.rows.data() + S.rows_ptr[s];
+        auto dstown = [&](int64_t pb) { return pb < k ? S.top_owner[s] : S.col_owner[rows[pb - k]]; };
+        const bool has_children = S.child_ptr[s + 1] > S.child_ptr[s];
+        if (has_children && !S.cb_assigned[s] && !h->zeroed[s]) { for (int64_t e = 0; e < r * r; ++e) C[e] = 0.0; h->zeroed[s] = 1; }
+        for (int ci = S.child_ptr[s]; ci < S.child_ptr[s + 1]; ++ci) {
+            const int c = S.child_idx[ci];
+            if (S.direct[c]) continue;
+            const int64_t rc = S.rows_ptr[c + 1] - S.rows_ptr[c];
+            const int* rel = S.rel.data() + S.rows_ptr[c];
+            const double* Cc = h->cb.data() + S.CBoff[c];
+            for (int64_t b = 0; b < rc; ++b) {
+                const int64_t rb = rel[b];
+                if (dstown(rb) != rank) continue;
+                for (int64_t a = 0; a < rc; ++a) {
+                    const double v = Cc[a + b * rc];
+                    const int64_t ra = rel[a];
+                    if (rb < k) P[ra + rb * f] += v;
+                    else if (ra < k) T[(rb - k) + ra * r] += v;
+                    else C[(ra - k) + (rb - k) * r] += v;
+                }
+            }
+        }
+        if (S.top_owner[s] != rank) continue;
+        for (int64_t j = 0; j < k; ++j) {
+            const double piv = P[j + j * f];
+            if (!(std::fabs(piv) > 0.0) || !std::isfinite(piv)) { if (h->bad < 0) h->bad = c0 + j; }
+            for (int64_t i = j + 1; i < f; ++i) P[i + j * f] /= piv;
+            for (int64_t c = j + 1; c < k; ++c) {
+                const double ujc = P[j + c * f];
+                for (int64_t i = j + 1; i < f; ++i) P[i + c * f] -= P[i + j * f] * ujc;
+            }
+        }
+    }
+}
+// Step 2 (after the caller has made the level's panels known to every rank): the rows of U12' and the columns of the
+// Schur update this rank owns; a direct child hands its columns straight to the parent.
+int64_t hx_top_update(void* hv, int rank, int level) {
+    HX* h = (HX*)hv;
+    const Symbolic& S = h->S;
+    for (int u = S.level_ptr[level]; u < S.level_ptr[level + 1]; ++u) {
+        const int s = S.level_sn[u];
+        if (S.owner[s] != -1) continue;
+        const int64_t k = S.sn_start[s + 1] - S.sn_start[s], r = S.rows_ptr[s + 1] - S.rows_ptr[s], f = k + r;
+        const double* P = h->lu.data() + S.Loff[s];
+        double* T = h->lu.data() + S.Uoff[s];
+        double* C = h->cb.data() + S.CBoff[s];
+        const int* rows = S.rows.data() + S.rows_ptr[s];
+        const bool has_children = S.child_ptr[s + 1] > S.child_ptr[s];
+        std::vector<char> mine(r);
+        for (int64_t a = 0; a < r; ++a) mine[a] = S.col_owner[rows[a]] == rank;
+        for (int64_t j = 0; j < k; ++j)
+            for (int64_t a = 0; a < r; ++a) {
+                if (!mine[a]) continue;
+                const double uja = T[a + j * r];
+                for (int64_t i = j + 1; i < k; ++i) T[a + i * r] -= P[i + j * f] * uja;
+            }
+        if (!has_children) for (int64_t e = 0; e < r * r; ++e) C[e] = 0.0;
+        for (int64_t p = 0; p < k; ++p)
+            for (int64_t b = 0; b < r; ++b) {
+                if (!mine[b]) continue;
+                const double upb = T[b + p * r];
+                for (int64_t a = 0; a < r; ++a) C[a + b * r] -= P[(k + a) + p * f] * upb;
+            }
+        if (S.direct[s]) {
+            const int ps = S.sn_parent[s];
+            const int64_t pk = S.sn_start[ps + 1] - S.sn_start[ps], pr = S.rows_ptr[ps + 1] - S.rows_ptr[ps], pf = pk + pr;
+            double* PP = h->lu.data() + S.Loff[ps];
+            double* PT = h->lu.data() + S.Uoff[ps];
+            double* PC = h->cb.data() + S.CBoff[ps];
+            if (!S.cb_assigned[ps] && !h->zeroed[ps]) { for (int64_t e = 0; e < pr * pr; ++e) PC[e] = 0.0; h->zeroed[ps] = 1; }
+            const int* rel = S.rel.data() + S.rows_ptr[s];
+            for (int64_t b = 0; b < r; ++b) {
+                if (!mine[b]) continue;
+                for (int64_t a = 0; a < r; ++a) {
+                    const double v = C[a + b * r];
+                    const int64_t ra = rel[a], rb = rel[b];
+                    if (rb < pk) PP[ra + rb * pf] += v;
+                    else if (ra < pk) PT[(rb - pk) + ra * pr] += v;
+                    else if (S.cb_assigned[ps]) PC[(ra - pk) + (rb - pk) * pr] = v;
+                    else PC[(ra - pk) + (rb - pk) * pr] += v;
+                }
+            }
+        }
+    }
+    return h->bad;
 }
 
 int64_t hx_factor(void* hv, const double* Ax, const double* Rs) { return hx_factor_phase(hv, Ax, Rs, 0, 0); }
