@@ -190,6 +190,7 @@ def algorithmic_work(F, A):
                     "bytes": 8.0 * float(np.sum(k[big] * f[big] + k[big] * r[big])) + 28.0 * (float(A.nnz) - a_small)},
         "fwd": {"flops": 2.0 * (nnzL - n) * (1 - sf), "bytes": Bf * (1 - sf)},
         "bwd": {"flops": 2.0 * nnzL * (1 - sb), "bytes": Bb * (1 - sb)},
+        # exchange: peer stores of the panels / U12' rows (refactor) + all-reduced vectors (solve); its time includes the waits
         "allreduce": {"flops": 0.0, "bytes": 8.0 * (st["allreduce_doubles_refactor"] + st["allreduce_doubles_solve"])},
         "fwd_small": {"flops": 2.0 * (nnzL - n) * sf, "bytes": Bf * sf},
         "bwd_small": {"flops": 2.0 * nnzL * sb, "bytes": Bb * sb},
@@ -477,6 +478,13 @@ def run_ours(args, rank, world, local_rank):
             roof["algorithmic_bytes_per_launch"] = work[dom]["bytes"] / max(1, launches_kernel.get(dom, 1))
     except Exception:
         pass
+    comm = None
+    if world > 1 and ms_kernel.get("allreduce", 0) > 0:
+        comm = {"ms_per_profiled_step": ms_kernel["allreduce"], "bytes_per_step_rank0": work["allreduce"]["bytes"],
+                "note": "exchange kernels of one PROFILED step on rank 0 (per-launch events, no stream overlap): peer-store "
+                        "publishing of panels, cross-GPU signal/wait (the wait time is idle time: load imbalance and the "
+                        "dependency on the panel owner), NCCL barriers and the solve's all-reduces",
+                "nvlink_peer_store_GBs_measured": 680.0}
     roof["kernel_ms_per_step"] = ms_kernel[dom]
     roof["share_of_step"] = ms_kernel[dom] / step_ms_prof
     solve_ms = sum(ms_kernel.get(kk, 0) for kk in ("fwd", "bwd", "fwd_small", "bwd_small", "permute_scale", "unpermute"))
@@ -501,16 +509,18 @@ def run_ours(args, rank, world, local_rank):
                    "cache": "factor storage %.0f MB per step exceeds the 126 MB L2 (no explicit flush)" % (8e-6 * st0["lu_pool_doubles"]),
                    "parallelism": "1 GPU" if world == 1 else (
                        "replicas: one independent factorization per GPU" if jobs == world else
-                       "one factorization partitioned over %d GPUs: per-rank subtrees + NCCL all-reduce of the coupling "
-                       "Schur complement (%d top supernodes replicated, %.1f MB all-reduced per refactor, %.1f MB per solve)"
-                       % (world, st0["n_top_supernodes"], 8e-6 * st0["allreduce_doubles_refactor"],
-                          8e-6 * st0["allreduce_doubles_solve"]))},
+                       "one factorization partitioned over %d GPUs: per-rank subtrees; the %d top supernodes (coupling Schur "
+                       "complement) distributed by columns -- panel owners publish their panels into every GPU's pool with NVLink "
+                       "peer stores (CUDA IPC), Schur updates by column owner, subtree roots' blocks stored straight into the "
+                       "owners' pools from the GEMM epilogue (rank 0: %.1f MB of peer stores per refactor); solve: replicated top, "
+                       "%.1f MB all-reduced" % (world, st0["n_top_supernodes"], 8e-6 * st0["allreduce_doubles_refactor"],
+                                                8e-6 * st0["allreduce_doubles_solve"]))},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * (nnz + n), "d2h_bytes_per_step": 8 * n,
                 "ms_per_step": ms_e2e / K, "residual": res_e2e},
         "gpu_launches": int(launches_per_step * K),
         "clocks": clocks,
         "roofline": roof,
-        "kernels": kinds,
+        "kernels": kinds, "comm": comm,
         "phases": {"refactor_ms": refac_ms, "solve_ms": solve_ms,
                    "refactor_TFLOPs": st0["flops_exact"] / (refac_ms * 1e-3) / 1e12,
                    "solve_GBs": solve_bytes / (solve_ms * 1e-3) / 1e9, "solve_frac_hbm": solve_bytes / (solve_ms * 1e-3) / 1e9 / hbm_gbs},

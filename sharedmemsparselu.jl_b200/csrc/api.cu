@@ -382,13 +382,14 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
             for (int cls = 0; cls < 2; ++cls) {
                 // 64-row tiles where the level is a few fronts (latency); 256-row tiles where the 64-row tiles
                 // would not be resident at once anyway (every tile repeats the pivot-block solve)
-                int64_t tiles64 = 0;
+                int64_t tiles64 = 0, tiles128 = 0;
                 for (int t = 0; t < cnt; ++t) {
                     int s = sn[t];
                     if (!IN(s) || SMALL(s) || (K(s) > NB) != (cls == 1)) continue;
                     tiles64 += std::max<int64_t>(1, (R(s) + FWD_ROWS - 1) / FWD_ROWS);
+                    tiles128 += std::max<int64_t>(1, (R(s) + FWD_ROWS_MID - 1) / FWD_ROWS_MID);
                 }
-                const int rows = tiles64 > FWD_WIDE_TILES ? FWD_ROWS_WIDE : FWD_ROWS;
+                const int rows = tiles64 <= FWD_WIDE_TILES ? FWD_ROWS : (tiles128 <= 2 * FWD_WIDE_TILES ? FWD_ROWS_MID : FWD_ROWS_WIDE);
                 off = (int64_t)tasks.size();
                 int kmax = 0;
                 for (int t = 0; t < cnt; ++t) {
@@ -410,13 +411,23 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
             for (int cls = 0; cls < 2; ++cls) {
                 int64_t off = (int64_t)tasks.size();
                 int kmax = 0;
+                // few row tiles on the level: split the pivot columns of every tile over 2 or 4 CTAs
+                int64_t lvl_tiles = 0;
+                for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) {
+                    int s = S.level_sn[t];
+                    if (!IN(s) || SMALL(s) || (K(s) > NB) != (cls == 1)) continue;
+                    lvl_tiles += std::max<int64_t>(1, (R(s) + BWD_ROWS - 1) / BWD_ROWS);
+                }
+                const int want = cls == 0 ? 1 : (lvl_tiles <= 37 ? 4 : (lvl_tiles <= 148 ? 2 : 1));
                 for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) {
                     int s = S.level_sn[t];
                     if (!IN(s) || SMALL(s) || (K(s) > NB) != (cls == 1)) continue;
                     kmax = std::max(kmax, K(s));
                     int nt = (int)std::max<int64_t>(1, (R(s) + BWD_ROWS - 1) / BWD_ROWS);
-                    for (int i = 0; i < nt; ++i) tasks.push_back(make_int4(s, i, nt, (int)slots));
-                    if (nt > 1) slots += nt;
+                    const int nsp = (R(s) > 0 && K(s) >= 16 * want) ? want : 1;
+                    for (int i = 0; i < nt; ++i)
+                        for (int cp = 0; cp < nsp; ++cp) tasks.push_back(make_int4(s, i | (cp << 24) | (nsp << 28), nt, (int)slots));
+                    if (nt * nsp > 1) slots += nt;
                 }
                 push(bwd, L_BWD, off, kmax);
             }
@@ -455,10 +466,16 @@ int map_peers(smslu_handle_t h) {
     return 0;
 }
 
-// Factorization schedule of the distributed top (nranks > 1), one entry list walked in order on the main stream.
-// Per level:  zero-fill / assembly (destination columns this rank owns)  ->  panel owner: the pivot block and L21 of its
-// fronts (k_panel mode 1), published to every peer's pool, signal  ->  wait for the other owners of the level  ->
-// rows of U12' this rank owns (k_panel mode 2)  ->  Schur update of the columns this rank owns.
+// Factorization schedule of the distributed top (nranks > 1).  Per level l two groups of launches (run_schedule forks /
+// joins the lanes of a group):
+//   group 2l  : zero-fill / assembly (destination columns this rank owns); panel owner's pass over the fronts it did not
+//               already factor ahead (k_panel mode 1: pivot block and L21), published to every peer's pool, signal;
+//               wait for the other owners of the level; rows of U12' this rank owns (k_panel mode 2); the Schur-update
+//               tiles that feed the pivot columns of a parent this rank owns (look-ahead part)
+//   group 2l+1: lane 0: the rest of the Schur update (columns this rank owns);
+//               lane 1 (high-priority stream): LOOK-AHEAD -- the panels of the next level's fronts this rank owns whose
+//               only input is that look-ahead part (links of a chain), published and signalled while every rank is
+//               still inside the current Schur update.
 void build_top_fac(smslu_handle_t h, std::vector<int4>& tasks, std::vector<int64_t>& segs, std::vector<int>& wait_slots,
                    std::vector<int4>& trow_tasks, int64_t& ncounters) {
     const Symbolic& S = h->S;
@@ -471,15 +488,64 @@ void build_top_fac(smslu_handle_t h, std::vector<int4>& tasks, std::vector<int64
     auto DSTOWN = [&](int s, int64_t pb) { return pb < K(s) ? S.top_owner[s] : ROWOWN(s, pb - K(s)); };
     std::vector<Launch>& fac = h->fac_top;
     fac.clear();
-    int sync_id = 0;
+    std::vector<int> slot_of(S.nsn, -1);          // sync slot of a top front = its ordinal among the top fronts
+    { int t = 0; for (int s = 0; s < S.nsn; ++s) if (S.owner[s] == -1) slot_of[s] = t++; }
+    std::vector<char> ahead(S.nsn, 0);            // panel already factored and published by the look-ahead lane
+    const bool lookahead = !(getenv("SMSLU_NO_LOOKAHEAD") && atoi(getenv("SMSLU_NO_LOOKAHEAD")) != 0);
     int64_t peer_doubles = 0;
-    auto push = [&](int kind, int64_t off, int nt, int fmax, int level) {
-        if (nt > 0) fac.push_back(Launch{kind, off, nt, fmax, level, 0});
+    auto push = [&](int kind, int64_t off, int nt, int fmax, int group, int lane) {
+        if (nt > 0) fac.push_back(Launch{kind, off, nt, fmax, group, lane});
+    };
+    // the panel owner's pass (pass 1: tiles of kinds 0 and 2 of the fronts in `list` this rank owns) or every rank's pass
+    // over the rows of U12' it owns (pass 2), one launch per 32 pivot columns; then, for pass 1, publish + signal
+    auto panel_pass = [&](const std::vector<int>& list, int pass, int group, int lane) {
+        int max_blk = 0;
+        for (int s : list) max_blk = std::max(max_blk, (K(s) + NB - 1) / NB);
+        for (int g = 0; g < max_blk; ++g) {
+            auto ntiles = [&](int s, int rws) -> int {
+                const int k = K(s);
+                const int64_t r = R(s), f = k + r;
+                const int j1 = std::min(k, (g + 1) * NB);
+                if (pass == 1) return (int)((f - j1 + rws - 1) / rws) + (k - j1 + rws - 1) / rws;
+                return (int)((r + rws - 1) / rws);
+            };
+            int64_t tiles_total = 0;
+            for (int s : list) if (g < (K(s) + NB - 1) / NB) tiles_total += std::max(1, ntiles(s, PANEL_ROWS));
+            const int rows = (tiles_total > 0 && tiles_total < 120) ? PANEL_ROWS_TOP : PANEL_ROWS;
+            const int64_t off = (int64_t)tasks.size();
+            for (int s : list) {
+                if (g >= (K(s) + NB - 1) / NB) continue;
+                if (pass == 1) {
+                    const int nt = std::max(1, ntiles(s, rows));         // someone has to factor D_gg
+                    const int cidx = (int)ncounters++;
+                    for (int t = 0; t < nt; ++t) tasks.push_back(make_int4(s, (int)(g | (1 << 4) | (nt << 16) | (1u << 30)), t, cidx));
+                } else {
+                    const int nt = ntiles(s, rows);
+                    for (int t = 0; t < nt; ++t) {
+                        bool mine = false;
+                        for (int64_t a = (int64_t)t * rows; a < std::min<int64_t>(R(s), (int64_t)(t + 1) * rows) && !mine; ++a) mine = ROWOWN(s, a) == rank;
+                        if (mine) tasks.push_back(make_int4(s, (int)(g | (1 << 4) | (1 << 16) | (2u << 30)), t, 0));
+                    }
+                }
+            }
+            push(L_PANEL, off, (int)((int64_t)tasks.size() - off), g | (rows << 8), group, lane);
+        }
+        if (pass == 1 && !list.empty()) {
+            const int64_t s0 = (int64_t)segs.size() / 2;
+            for (int s : list) {
+                const int64_t len = ((K(s) + R(s)) * K(s) + 1) & ~(int64_t)1;
+                segs.push_back(S.Loff[s]); segs.push_back(len);
+                peer_doubles += len * (NR - 1);
+            }
+            push(L_REPL, s0, (int)list.size(), 0, group, lane);
+            for (int s : list) fac.push_back(Launch{L_SIGNAL, (int64_t)slot_of[s], 1, 0, group, lane});
+        }
     };
     for (int l = 0; l < S.nlevels; ++l) {
         std::vector<int> top;
         for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) if (S.owner[S.level_sn[t]] == -1) top.push_back(S.level_sn[t]);
         if (top.empty()) continue;
+        const int gA = 2 * l, gB = 2 * l + 1;
         // zero-fill of the parents that direct children of this level add into (whole blocks: local memory)
         int64_t off = (int64_t)tasks.size();
         for (int s : top)
@@ -488,7 +554,7 @@ void build_top_fac(smslu_handle_t h, std::vector<int4>& tasks, std::vector<int64
                 const int64_t tiles = (R(ps) * R(ps) + ZERO_TILE - 1) / ZERO_TILE;
                 for (int64_t i = 0; i < tiles; ++i) tasks.push_back(make_int4(ps, (int)i, 0, 0));
             }
-        push(L_ZERO, off, (int)((int64_t)tasks.size() - off), 0, l);
+        push(L_ZERO, off, (int)((int64_t)tasks.size() - off), 0, gA, 0);
         // assembly: every non-direct child (top fronts and the subtree roots, whose columns arrived in this rank's
         // exchange slots), destination columns this rank owns, tasks cut where the owner changes
         off = (int64_t)tasks.size();
@@ -526,85 +592,45 @@ void build_top_fac(smslu_handle_t h, std::vector<int4>& tasks, std::vector<int64
                 pb0 = pb1;
             }
         }
-        push(L_EXTEND, off, (int)((int64_t)tasks.size() - off), (int)std::min<int64_t>(asm_fmax, 1 << 30), l);
-        // panel owner's pass: pivot block and L21 (tiles of kinds 0 and 2), one launch per 32 pivot columns
-        int max_blk = 0;
-        bool own_any = false;
-        std::vector<int> other_owners;
+        push(L_EXTEND, off, (int)((int64_t)tasks.size() - off), (int)std::min<int64_t>(asm_fmax, 1 << 30), gA, 0);
+        // panels of the fronts this rank owns and has not factored ahead; then wait for everybody else's
+        std::vector<int> mine_now;
+        const int64_t w0 = (int64_t)wait_slots.size();
         for (int s : top) {
-            max_blk = std::max(max_blk, (K(s) + NB - 1) / NB);
-            if (S.top_owner[s] == rank) own_any = true;
-            else if (std::find(other_owners.begin(), other_owners.end(), S.top_owner[s]) == other_owners.end()) other_owners.push_back(S.top_owner[s]);
+            if (S.top_owner[s] == rank) { if (!ahead[s]) mine_now.push_back(s); }
+            else wait_slots.push_back(slot_of[s]);
         }
-        for (int pass = 1; pass <= 2; ++pass) {
-            for (int g = 0; g < max_blk; ++g) {
-                // tiles of the launch decide the tile height, as in the one-GPU schedule
-                auto ntiles = [&](int s, int rws) -> int {
-                    const int k = K(s);
-                    const int64_t r = R(s), f = k + r;
-                    const int j1 = std::min(k, (g + 1) * NB);
-                    if (pass == 1) return (int)((f - j1 + rws - 1) / rws) + (k - j1 + rws - 1) / rws;
-                    return (int)((r + rws - 1) / rws);
-                };
-                int64_t tiles_total = 0;
-                for (int s : top) {
-                    if (g >= (K(s) + NB - 1) / NB) continue;
-                    if (pass == 1 && S.top_owner[s] != rank) continue;
-                    tiles_total += std::max(1, ntiles(s, PANEL_ROWS));
+        panel_pass(mine_now, 1, gA, 0);
+        push(L_WAIT, w0, (int)((int64_t)wait_slots.size() - w0), 0, gA, 0);
+        panel_pass(top, 2, gA, 0);
+        // Schur update of the columns this rank owns: first the tile columns that feed the pivot columns of a parent this
+        // rank owns (then that parent's panel runs ahead on lane 1), the rest beside it on lane 0
+        std::vector<int> next_mine;
+        for (int part = 0; part < 2; ++part) {
+            off = (int64_t)tasks.size();
+            for (int s : top) {
+                const int64_t r = R(s);
+                const int nt = (int)((r + GEMM_TILE - 1) / GEMM_TILE);
+                const int ps = S.sn_parent[s];
+                int ja = 0;                              // tile columns [0, ja) feed the parent's pivot columns
+                if (lookahead && S.direct[s] && ps != -1 && S.owner[ps] == -1 && S.top_owner[ps] == rank) {
+                    int64_t nb = 0;
+                    while (nb < r && S.rel[S.rows_ptr[s] + nb] < K(ps)) ++nb;
+                    ja = (int)((nb + GEMM_TILE - 1) / GEMM_TILE);
+                    if (part == 0) { next_mine.push_back(ps); ahead[ps] = 1; }
                 }
-                const int rows = (tiles_total > 0 && tiles_total < 120) ? PANEL_ROWS_TOP : PANEL_ROWS;
-                off = (int64_t)tasks.size();
-                for (int s : top) {
-                    if (g >= (K(s) + NB - 1) / NB) continue;
-                    if (pass == 1) {
-                        if (S.top_owner[s] != rank) continue;
-                        const int nt = std::max(1, ntiles(s, rows));         // someone has to factor D_gg
-                        const int cidx = (int)ncounters++;
-                        for (int t = 0; t < nt; ++t)
-                            tasks.push_back(make_int4(s, (int)(g | (1 << 4) | (nt << 16) | (1u << 30)), t, cidx));
-                    } else {
-                        const int nt = ntiles(s, rows);
-                        for (int t = 0; t < nt; ++t) {
-                            bool mine = false;
-                            for (int64_t a = (int64_t)t * rows; a < std::min<int64_t>(R(s), (int64_t)(t + 1) * rows) && !mine; ++a) mine = ROWOWN(s, a) == rank;
-                            if (mine) tasks.push_back(make_int4(s, (int)(g | (1 << 4) | (1 << 16) | (2u << 30)), t, 0));
-                        }
-                    }
+                const int flags = (NC(s) > 0 ? 1 : 0) | (S.direct[s] ? 2 : 0) | (S.direct[s] && S.cb_assigned[ps] ? 4 : 0) | 16 |
+                                  (S.direct[s] && r == K(ps) + R(ps) ? 32 : 0);
+                for (int j = part == 0 ? 0 : ja; j < (part == 0 ? ja : nt); ++j) {
+                    bool mine = false;
+                    for (int64_t b = (int64_t)j * GEMM_TILE; b < std::min<int64_t>(r, (int64_t)(j + 1) * GEMM_TILE) && !mine; ++b) mine = ROWOWN(s, b) == rank;
+                    if (!mine) continue;
+                    for (int i = 0; i < nt; ++i) tasks.push_back(make_int4(s, i, j, flags));
                 }
-                push(L_PANEL, off, (int)((int64_t)tasks.size() - off), g | (rows << 8), l);
             }
-            if (pass == 1) {
-                // publish the finished panels P_s (pivot block on top of L21), then tell the peers; wait for the others
-                const int64_t s0 = (int64_t)segs.size() / 2;
-                for (int s : top)
-                    if (S.top_owner[s] == rank) {
-                        const int64_t len = ((K(s) + R(s)) * K(s) + 1) & ~(int64_t)1;
-                        segs.push_back(S.Loff[s]); segs.push_back(len);
-                        peer_doubles += len * (NR - 1);
-                    }
-                push(L_REPL, s0, (int)((int64_t)segs.size() / 2 - s0), 0, l);
-                if (own_any) fac.push_back(Launch{L_SIGNAL, (int64_t)sync_id * NR + rank, 1, 0, l, 0});
-                const int64_t w0 = (int64_t)wait_slots.size();
-                for (int o : other_owners) wait_slots.push_back(sync_id * NR + o);
-                push(L_WAIT, w0, (int)other_owners.size(), 0, l);
-                ++sync_id;
-            }
+            push(L_GEMM, off, (int)((int64_t)tasks.size() - off), 0, part == 0 ? gA : gB, 0);
         }
-        // Schur update of the columns this rank owns
-        off = (int64_t)tasks.size();
-        for (int s : top) {
-            const int64_t r = R(s);
-            const int nt = (int)((r + GEMM_TILE - 1) / GEMM_TILE);
-            const int flags = (NC(s) > 0 ? 1 : 0) | (S.direct[s] ? 2 : 0) | (S.direct[s] && S.cb_assigned[S.sn_parent[s]] ? 4 : 0) | 16 |
-                              (S.direct[s] && r == K(S.sn_parent[s]) + R(S.sn_parent[s]) ? 32 : 0);
-            for (int j = 0; j < nt; ++j) {
-                bool mine = false;
-                for (int64_t b = (int64_t)j * GEMM_TILE; b < std::min<int64_t>(r, (int64_t)(j + 1) * GEMM_TILE) && !mine; ++b) mine = ROWOWN(s, b) == rank;
-                if (!mine) continue;
-                for (int i = 0; i < nt; ++i) tasks.push_back(make_int4(s, i, j, flags));
-            }
-        }
-        push(L_GEMM, off, (int)((int64_t)tasks.size() - off), 0, l);
+        panel_pass(next_mine, 1, gB, 1);
         // rows of U12' this rank owns, published to the peers at the end of the refactorization (the solves read all of T_s)
         for (int s : top) {
             const int64_t r = R(s);
@@ -640,7 +666,11 @@ int ensure_uploaded(smslu_handle_t h) {
     else CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     const bool lanes = !(getenv("SMSLU_NO_LANES") && atoi(getenv("SMSLU_NO_LANES")) != 0);   // debugging aid: one stream only
     for (int a = 0; a < NLANES - 1; ++a) {
-        if (lanes) CU(cudaStreamCreateWithFlags(&h->aux_stream[a], cudaStreamNonBlocking));
+        if (lanes) {       // lane 1 carries the look-ahead panels of the distributed top: ahead of the queued Schur-update CTAs
+            int plo = 0, phi = 0;
+            CU(cudaDeviceGetStreamPriorityRange(&plo, &phi));
+            CU(cudaStreamCreateWithPriority(&h->aux_stream[a], cudaStreamNonBlocking, a == 0 ? phi : plo));
+        }
         CU(cudaEventCreateWithFlags(&h->ev_join[a], cudaEventDisableTiming));
     }
     CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
@@ -792,8 +822,8 @@ int ensure_uploaded(smslu_handle_t h) {
         if ((rc = dev_upload(h, &h->d_segs, segs))) return rc;
         if ((rc = dev_upload(h, &h->d_wait_slots, wait_slots))) return rc;
         if ((rc = dev_upload(h, &h->d_trow_tasks, trow))) return rc;
-        if ((rc = dev_alloc(h, &h->d_xflags, (size_t)(S.nlevels + 1) * MAX_RANKS))) return rc;
-        CU(cudaMemset(h->d_xflags, 0, sizeof(int) * (size_t)(S.nlevels + 1) * MAX_RANKS));
+        if ((rc = dev_alloc(h, &h->d_xflags, (size_t)S.nsn + 1))) return rc;
+        CU(cudaMemset(h->d_xflags, 0, sizeof(int) * ((size_t)S.nsn + 1)));
         if ((rc = dev_alloc(h, &h->d_barrier, 1))) return rc;
         CU(cudaMemset(h->d_barrier, 0, sizeof(int)));
         h->st.allreduce_doubles_refactor = h->peer_bytes_refactor / 8;

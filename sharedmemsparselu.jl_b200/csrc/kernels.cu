@@ -1196,7 +1196,8 @@ template <int RB, int ROWS>
 __global__ void __launch_bounds__(SOLVE_THREADS, (ROWS == FWD_ROWS_WIDE && RB == 1) ? 2 : 1) k_fwd(DevCtx cx, const int4* __restrict__ tasks,
                                                        const double* __restrict__ win, double* __restrict__ zout) {
     __shared__ double ys[KW * RB];
-    constexpr int NQ = SOLVE_THREADS / ROWS;                 // threads per row in the L21 product (4 or 1)
+    constexpr int NQ = SOLVE_THREADS / ROWS;                 // threads per row in the L21 product (4, 2 or 1)
+    constexpr int QPT = 4 / NQ;                              // quarters of the pivot columns per thread
     __shared__ double acc[ROWS * RB];
     __shared__ double red[NQ > 1 ? 4 : 1][NQ > 1 ? ROWS * RB : 1];
     pdl_trigger();
@@ -1212,10 +1213,24 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (ROWS == FWD_ROWS_WIDE && RB ==
     TRACE2(8);
     pdl_wait();
     TRACE2(9);
+    // A single child whose row list is exactly this front (a link of a chain cut out of one wide separator, or the
+    // virtual child of an interface front): rel is the identity, so the child's update vector is read in place --
+    // pivot rows first, then this tile's rows -- instead of every tile scanning all of it.
+    const int ch0 = cx.child_ptr[s], nch = cx.child_ptr[s + 1] - ch0;
+    const int c_id = nch == 1 ? cx.child_idx[ch0] : -1;
+    const bool ident = nch == 1 && cx.rows_ptr[c_id + 1] - cx.rows_ptr[c_id] == F.f;
+    if (ident) {
+        const double* __restrict__ uc = cx.upd + cx.rows_ptr[c_id] * RB;
+        for (int e = tid; e < KW * RB; e += SOLVE_THREADS) ys[e] = e < k * RB ? win[(int64_t)F.c0 * RB + e] + uc[e] : 0.0;
+        const int64_t nrow = F.r - lo < ROWS ? F.r - lo : ROWS;
+        for (int e = tid; e < ROWS * RB; e += SOLVE_THREADS) acc[e] = e < nrow * RB ? uc[(k + lo) * RB + e] : 0.0;
+        __syncthreads();
+    } else {
     for (int e = tid; e < KW * RB; e += SOLVE_THREADS) ys[e] = e < k * RB ? win[(int64_t)F.c0 * RB + e] : 0.0;
     for (int e = tid; e < ROWS * RB; e += SOLVE_THREADS) acc[e] = 0.0;
     __syncthreads();
-    for (int ci = cx.child_ptr[s]; ci < cx.child_ptr[s + 1]; ++ci) {
+    }
+    for (int ci = ch0; ci < (ident ? ch0 : ch0 + nch); ++ci) {
         const int c = cx.child_idx[ci];
         const int64_t rc = cx.rows_ptr[c + 1] - cx.rows_ptr[c];
         const int* __restrict__ rel = cx.rel + cx.rows_ptr[c];
@@ -1259,10 +1274,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (ROWS == FWD_ROWS_WIDE && RB ==
         // quarters of a row belong to four threads, with ROWS = 256 one thread takes them one after the other
         const int rloc = tid & (ROWS - 1), kq = kp / 4;
         const int64_t row = lo + rloc;
-        double vq[4 / NQ][RB];
+        double vq[QPT][RB];
 #pragma unroll
-        for (int h = 0; h < 4 / NQ; ++h) {
-            const int qt = NQ > 1 ? tid / ROWS : h;
+        for (int h = 0; h < QPT; ++h) {
+            const int qt = (tid / ROWS) * QPT + h;
             double (&v)[RB] = vq[h];
 #pragma unroll
             for (int q = 0; q < RB; ++q) v[q] = 0.0;
@@ -1299,7 +1314,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (ROWS == FWD_ROWS_WIDE && RB ==
         if (NQ > 1) {
             const int qt = tid / ROWS;
 #pragma unroll
-            for (int q = 0; q < RB; ++q) red[qt][rloc * RB + q] = vq[0][q];
+            for (int h = 0; h < QPT; ++h)
+#pragma unroll
+                for (int q = 0; q < RB; ++q) red[qt * QPT + h][rloc * RB + q] = vq[h][q];
             __syncthreads();
             if (qt == 0 && row < F.r) {
 #pragma unroll
@@ -1312,7 +1329,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (ROWS == FWD_ROWS_WIDE && RB ==
 #pragma unroll
             for (int q = 0; q < RB; ++q)
                 cx.upd[(cx.rows_ptr[s] + row) * RB + q] =
-                    acc[rloc * RB + q] - (((vq[0][q] + vq[(4 / NQ) > 1 ? 1 : 0][q]) + vq[(4 / NQ) > 2 ? 2 : 0][q]) + vq[(4 / NQ) > 3 ? 3 : 0][q]);
+                    acc[rloc * RB + q] - (((vq[0][q] + vq[QPT > 1 ? 1 : 0][q]) + vq[QPT > 2 ? 2 : 0][q]) + vq[QPT > 3 ? 3 : 0][q]);
         }
         TRACE2(12);
     }
@@ -1331,10 +1348,13 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (WIDE && RB == 1) ? 2 : 1) k_bw
     __shared__ int s_last;
     pdl_trigger();
     int4 tk = tasks[blockIdx.x];
-    const int s = tk.x, ntiles = tk.z;
+    // tk.y = row tile | column part << 24 | column parts << 28: on levels with few row tiles the k pivot columns of a tile
+    // are split over 2 or 4 CTAs (each reads its columns of the tile of U12'; the partial sums are independent)
+    const int s = tk.x, ntiles = tk.z, rtile = tk.y & 0xffffff, cpart = (tk.y >> 24) & 15, nsp = (tk.y >> 28) ? (tk.y >> 28) : 1;
     const Front F = load_front(cx, s);
     const int k = F.k, tid = threadIdx.x, lane = tid & 31, warp = uniform_warp_id();
-    const int64_t lo = (int64_t)tk.y * BWD_ROWS;
+    const int kper = (((k + nsp - 1) / nsp) + 7) & ~7, c_lo = cpart * kper, c_hi = c_lo + kper < k ? c_lo + kper : k;
+    const int64_t lo = (int64_t)rtile * BWD_ROWS;
     const int cnt = (int)(F.r - lo < BWD_ROWS ? F.r - lo : BWD_ROWS);
     const double* __restrict__ inv = cx.dblk + (int64_t)cx.Doff[s] * (NB * NB);
     prefetch_block_l2(F.T + lo, cnt, k, F.r, tid, SOLVE_THREADS);
@@ -1354,7 +1374,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (WIDE && RB == 1) ? 2 : 1) k_bw
     // a warp takes BU columns at a time (8 for a single right-hand side: 64 loads per lane in flight; 4 when
     // RB > 1, where the accumulators need the registers, and in the two-CTAs-per-SM variant of the bulk levels)
     constexpr int BU = (RB == 1 && !WIDE) ? 8 : 4;
-    for (int i0 = warp * BU; i0 < k; i0 += (SOLVE_THREADS / 32) * BU) {
+    for (int i0 = c_lo + warp * BU; i0 < c_hi; i0 += (SOLVE_THREADS / 32) * BU) {
         double v[BU][RB];
 #pragma unroll
         for (int u = 0; u < BU; ++u)
@@ -1365,7 +1385,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (WIDE && RB == 1) ? 2 : 1) k_bw
         for (int u = 0; u < BU; ++u) {
             const double* __restrict__ col = F.T + (int64_t)(i0 + u) * F.r + lo;
 #pragma unroll
-            for (int a = 0; a < BWD_ROWS / 32; ++a) t[u][a] = (i0 + u < k && lane + 32 * a < cnt) ? col[lane + 32 * a] : 0.0;
+            for (int a = 0; a < BWD_ROWS / 32; ++a) t[u][a] = (i0 + u < c_hi && lane + 32 * a < cnt) ? col[lane + 32 * a] : 0.0;
         }
 #pragma unroll
         for (int a = 0; a < BWD_ROWS / 32; ++a)
@@ -1381,19 +1401,19 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (WIDE && RB == 1) ? 2 : 1) k_bw
             for (int q = 0; q < RB; ++q) {
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) v[u][q] += __shfl_xor_sync(0xffffffffu, v[u][q], o);
-                if (lane == 0 && i0 + u < k) part[(i0 + u) * RB + q] = v[u][q];
+                if (lane == 0 && i0 + u < c_hi) part[(i0 + u) * RB + q] = v[u][q];
             }
     }
     __syncthreads();
     TRACE2(3);
-    if (ntiles > 1) {
+    if (ntiles * nsp > 1) {
         double* slot = cx.bpart + (int64_t)tk.w * KW * RB;
-        for (int e = tid; e < k * RB; e += SOLVE_THREADS) slot[(int64_t)tk.y * KW * RB + e] = part[e];
+        for (int e = c_lo * RB + tid; e < c_hi * RB; e += SOLVE_THREADS) slot[(int64_t)rtile * KW * RB + e] = part[e];
         __threadfence();
         __syncthreads();
         if (tid == 0) {
             int old = atomicAdd(cx.counters2 + s, 1);
-            s_last = ((old + 1) % ntiles) == 0;
+            s_last = ((old + 1) % (ntiles * nsp)) == 0;
         }
         __syncthreads();
         if (!s_last) return;
@@ -1773,6 +1793,10 @@ void launch_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks
     if (ntasks <= 0) return;
     if (rows == FWD_ROWS) {
 #define CALL(R) launch_pdl(k_fwd<R, FWD_ROWS>, ntasks, SOLVE_THREADS, 0, st, cx, tasks, win, zout)
+        RB_DISPATCH(rb, CALL);
+#undef CALL
+    } else if (rows == FWD_ROWS_MID) {
+#define CALL(R) launch_pdl(k_fwd<R, FWD_ROWS_MID>, ntasks, SOLVE_THREADS, 0, st, cx, tasks, win, zout)
         RB_DISPATCH(rb, CALL);
 #undef CALL
     } else {

@@ -25,6 +25,7 @@ constexpr int GEMM_TILE = 64;
 constexpr int SOLVE_THREADS = 256;
 constexpr int FWD_ROWS = 64;      // update rows per forward CTA (4 threads per row) ...
 constexpr int BWD_WIDE_TILES = 148; // backward launches with more tiles than this use the two-CTAs-per-SM variant
+constexpr int FWD_ROWS_MID = 128;  // ... two threads per row where 64-row tiles would be more than one wave but 256-row tiles leave SMs idle
 constexpr int FWD_ROWS_WIDE = 256; // ... or one thread per row on levels with many tiles (every CTA repeats the pivot-block solve)
 constexpr int BWD_ROWS = 256;     // rows of U12' per backward CTA
 constexpr int ZERO_TILE = 8192;
