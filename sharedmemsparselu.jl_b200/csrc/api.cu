@@ -63,7 +63,9 @@ enum LaunchKind { L_ZERO = SMSLU_K_ZERO, L_EXTEND = SMSLU_K_EXTEND, L_SMALL = SM
                   L_GEMM = SMSLU_K_GEMM, L_FWD = SMSLU_K_FWD, L_BWD = SMSLU_K_BWD,
                   L_FWD_SMALL = SMSLU_K_FWD_SMALL, L_BWD_SMALL = SMSLU_K_BWD_SMALL,
                   // partitioned top (timed as SMSLU_K_ALLREDUCE = "exchange"): publish panels to the peers, signal, wait
-                  L_REPL = 100, L_SIGNAL = 101, L_WAIT = 102 };
+                  L_REPL = 100, L_SIGNAL = 101, L_WAIT = 102,
+                  // persistent chain solves (single right-hand side)
+                  L_FWD_CHAIN = 103, L_BWD_RECT = 104, L_BWD_CHAIN = 105 };
 
 constexpr int NLANES = 4;
 
@@ -121,6 +123,11 @@ struct smslu_handle_s {
     std::vector<int> asm_meta;                       // (child, first column) pairs of the assembly tasks
     std::vector<Launch> fac, fwd, bwd;               // this rank's supernodes (everything when nranks == 1)
     std::vector<Launch> fac_top, fwd_top, bwd_top;   // top of the tree, replicated on every rank
+    // single right-hand side: the same sweeps with every set of parallel chains of fronts in one persistent kernel
+    std::vector<Launch> fwd1, bwd1, fwd_top1, bwd_top1;
+    int* d_chain_desc = nullptr;
+    int solve_epoch = 0;
+    int64_t chain_part_vecs = 0;
     int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
     int4* d_vtasks = nullptr;            // interface fronts: x = front, y = virtual child, z..w = range in d_vlist
@@ -437,6 +444,158 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
     h->ncounters = ncounters;
 }
 
+// Chains of fronts (links of at most KW pivot columns cut out of one wide separator; each link the only child of the
+// next, its row list exactly the next link's front) are solved by persistent kernels when there is one right-hand side:
+// find the sets of level-aligned parallel chains in a sweep's schedule, build their descriptors, and derive the chain
+// variants of the forward / backward schedules (the per-level launches of the chains' wide fronts are dropped).
+struct ChainSet { int l0, l1; std::vector<std::vector<int>> chains; };
+
+void build_chain_schedules(smslu_handle_t h, std::vector<int4>& tasks, const std::vector<int>& dchild_ptr,
+                           const std::vector<int>& dchild_idx, std::vector<int>& desc, std::vector<int>& links,
+                           std::vector<int>& boffs) {
+    const Symbolic& S = h->S;
+    auto K = [&](int s) { return S.sn_start[s + 1] - S.sn_start[s]; };
+    auto R = [&](int s) { return (int64_t)(S.rows_ptr[s + 1] - S.rows_ptr[s]); };
+    const bool enabled = !(getenv("SMSLU_NO_CHAINS") && atoi(getenv("SMSLU_NO_CHAINS")) != 0);
+    for (int ph = 0; ph < 2; ++ph) {
+        const std::vector<Launch>& fwd = ph == 0 ? h->fwd : h->fwd_top;
+        const std::vector<Launch>& bwd = ph == 0 ? h->bwd : h->bwd_top;
+        std::vector<Launch>& fwd1 = ph == 0 ? h->fwd1 : h->fwd_top1;
+        std::vector<Launch>& bwd1 = ph == 0 ? h->bwd1 : h->bwd_top1;
+        const int mine = ph == 0 ? h->rank : -1;
+        auto WIDE = [&](int s) { return S.owner[s] == mine && !S.small[s] && K(s) > NB; };
+        // wide fronts per level
+        std::vector<std::vector<int>> C(S.nlevels);
+        for (int l = 0; l < S.nlevels; ++l)
+            for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) if (WIDE(S.level_sn[t])) C[l].push_back(S.level_sn[t]);
+        // the wide front below s when s continues a chain: its only device child, whose row list is s's front
+        auto below = [&](int s) -> int {
+            if (dchild_ptr[s + 1] - dchild_ptr[s] != 1) return -1;
+            const int c = dchild_idx[dchild_ptr[s]];
+            if (c >= S.nsn || !WIDE(c) || R(c) != K(s) + R(s)) return -1;
+            return c;
+        };
+        std::vector<ChainSet> sets;
+        for (int l = 0; enabled && l < S.nlevels;) {
+            if (C[l].empty()) { ++l; continue; }
+            int l1 = l;
+            while (l1 + 1 < S.nlevels && C[l1 + 1].size() == C[l].size()) {
+                bool ok = true;
+                std::vector<int> seen;
+                for (int s : C[l1 + 1]) {
+                    const int c = below(s);
+                    if (c < 0 || S.sn_level[c] != l1 || std::find(seen.begin(), seen.end(), c) != seen.end()) { ok = false; break; }
+                    seen.push_back(c);
+                }
+                if (!ok) break;
+                ++l1;
+            }
+            if (l1 - l + 1 >= 4 && C[l].size() <= 32) {
+                ChainSet cs; cs.l0 = l; cs.l1 = l1;
+                for (int top : C[l1]) {                    // follow every chain down from its top link
+                    std::vector<int> ch(1, top);
+                    for (int lv = l1; lv > l; --lv) ch.push_back(below(ch.back()));
+                    std::reverse(ch.begin(), ch.end());
+                    cs.chains.push_back(ch);
+                }
+                // CTAs in proportion to the chains' blocks; every CTA may own at most CHAIN_MAXOWN of them
+                std::vector<int> nb(cs.chains.size());
+                int64_t tot = 0;
+                for (size_t q = 0; q < cs.chains.size(); ++q) {
+                    const int last = cs.chains[q].back();
+                    nb[q] = (int)cs.chains[q].size() + (int)((R(last) + KW - 1) / KW);
+                    tot += nb[q];
+                }
+                bool fits = true;
+                int used = 0;
+                std::vector<int> nct(cs.chains.size());
+                for (size_t q = 0; q < cs.chains.size(); ++q) {
+                    nct[q] = std::max<int>(1, (int)((int64_t)CHAIN_CTAS * nb[q] / tot));
+                    used += nct[q];
+                    if (nb[q] > CHAIN_MAXOWN * nct[q]) fits = false;
+                }
+                if (fits && used <= CHAIN_CTAS) sets.push_back(cs);
+            }
+            l = l1 + 1;
+        }
+        // descriptors + the backward sweep's tasks for the rows above the chains
+        struct SetDev { int desc0, nch, nctas; int64_t rect_off; int rect_n; };
+        std::vector<SetDev> dev(sets.size());
+        for (size_t si = 0; si < sets.size(); ++si) {
+            const ChainSet& cs = sets[si];
+            std::vector<int> nb(cs.chains.size());
+            int64_t tot = 0;
+            for (size_t q = 0; q < cs.chains.size(); ++q) { nb[q] = (int)cs.chains[q].size() + (int)((R(cs.chains[q].back()) + KW - 1) / KW); tot += nb[q]; }
+            dev[si].desc0 = (int)desc.size() / CHAIN_DESC; dev[si].nch = (int)cs.chains.size();
+            dev[si].rect_off = (int64_t)tasks.size();
+            int cta0 = 0;
+            int64_t part0 = 0;
+            for (size_t q = 0; q < cs.chains.size(); ++q) {
+                const std::vector<int>& ch = cs.chains[q];
+                const int m = (int)ch.size(), last = ch.back();
+                const int64_t ra = R(last);
+                const int ntile = (int)((ra + BWD_ROWS - 1) / BWD_ROWS);
+                const int nct = std::max<int>(1, (int)((int64_t)CHAIN_CTAS * nb[q] / tot));
+                const int d8[CHAIN_DESC] = {(int)links.size(), m, (int)boffs.size(), nb[q], cta0, nct, (int)part0, ntile};
+                desc.insert(desc.end(), d8, d8 + CHAIN_DESC);
+                int o = 0;
+                for (int s : ch) { links.push_back(s); boffs.push_back(o); o += K(s); }
+                for (int64_t a = 0; a < ra; a += KW) boffs.push_back(o + (int)a);
+                boffs.push_back(o + (int)ra);
+                for (int j = 0; j < m; ++j)                 // rows above the chain are the last `ra` rows of every link's row list
+                    for (int tl = 0; tl < ntile; ++tl) {
+                        const int64_t first = R(ch[j]) - ra + (int64_t)tl * BWD_ROWS;
+                        tasks.push_back(make_int4(ch[j], (int)first, (int)std::min<int64_t>(BWD_ROWS, ra - (int64_t)tl * BWD_ROWS), (int)(part0 + (int64_t)j * ntile + tl)));
+                    }
+                part0 += (int64_t)m * ntile;
+                cta0 += nct;
+            }
+            dev[si].nctas = cta0;
+            dev[si].rect_n = (int)((int64_t)tasks.size() - dev[si].rect_off);
+            h->chain_part_vecs = std::max(h->chain_part_vecs, part0);
+        }
+        auto in_set = [&](int level) -> int {
+            for (size_t si = 0; si < sets.size(); ++si) if (level >= sets[si].l0 && level <= sets[si].l1) return (int)si;
+            return -1;
+        };
+        // forward: ascending levels; the chain kernel of a set goes in front of the first launch at or above its bottom level
+        fwd1.clear();
+        {
+            size_t next = 0;
+            auto emit_upto = [&](int level) {
+                while (next < sets.size() && sets[next].l0 <= level) {
+                    fwd1.push_back(Launch{L_FWD_CHAIN, dev[next].desc0, dev[next].nch, dev[next].nctas, sets[next].l0, 0});
+                    ++next;
+                }
+            };
+            for (const Launch& L : fwd) {
+                emit_upto(L.level);
+                if (L.kind == L_FWD && (L.fmax & 255) > NB && in_set(L.level) >= 0) continue;
+                fwd1.push_back(L);
+            }
+            emit_upto(S.nlevels);
+        }
+        // backward: descending levels; rows above the chains first (one launch), then the chain kernel
+        bwd1.clear();
+        {
+            int next = (int)sets.size() - 1;
+            auto emit_downto = [&](int level) {
+                while (next >= 0 && sets[next].l1 >= level) {
+                    if (dev[next].rect_n > 0) bwd1.push_back(Launch{L_BWD_RECT, dev[next].rect_off, dev[next].rect_n, 0, sets[next].l1, 0});
+                    bwd1.push_back(Launch{L_BWD_CHAIN, dev[next].desc0, dev[next].nch, dev[next].nctas, sets[next].l1, 0});
+                    --next;
+                }
+            };
+            for (const Launch& L : bwd) {
+                emit_downto(L.level);
+                if (L.kind == L_BWD && L.fmax > NB && in_set(L.level) >= 0) continue;
+                bwd1.push_back(L);
+            }
+            emit_downto(-1);
+        }
+    }
+}
+
 // Map every peer's factor pool, contribution pool and flag array into this process (CUDA IPC over NVLink): the handles
 // travel through one ncclAllGather.  Offsets into the pools are the same on every rank (same deterministic analysis).
 int map_peers(smslu_handle_t h) {
@@ -612,20 +771,25 @@ void build_top_fac(smslu_handle_t h, std::vector<int4>& tasks, std::vector<int64
                 const int64_t r = R(s);
                 const int nt = (int)((r + GEMM_TILE - 1) / GEMM_TILE);
                 const int ps = S.sn_parent[s];
-                int ja = 0;                              // tile columns [0, ja) feed the parent's pivot columns
+                int64_t nb = 0;                          // columns [0, nb) feed the pivot columns of a parent this rank owns
                 if (lookahead && S.direct[s] && ps != -1 && S.owner[ps] == -1 && S.top_owner[ps] == rank) {
-                    int64_t nb = 0;
                     while (nb < r && S.rel[S.rows_ptr[s] + nb] < K(ps)) ++nb;
-                    ja = (int)((nb + GEMM_TILE - 1) / GEMM_TILE);
                     if (part == 0) { next_mine.push_back(ps); ahead[ps] = 1; }
                 }
                 const int flags = (NC(s) > 0 ? 1 : 0) | (S.direct[s] ? 2 : 0) | (S.direct[s] && S.cb_assigned[ps] ? 4 : 0) | 16 |
-                                  (S.direct[s] && r == K(ps) + R(ps) ? 32 : 0);
-                for (int j = part == 0 ? 0 : ja; j < (part == 0 ? ja : nt); ++j) {
-                    bool mine = false;
-                    for (int64_t b = (int64_t)j * GEMM_TILE; b < std::min<int64_t>(r, (int64_t)(j + 1) * GEMM_TILE) && !mine; ++b) mine = ROWOWN(s, b) == rank;
-                    if (!mine) continue;
-                    for (int i = 0; i < nt; ++i) tasks.push_back(make_int4(s, i, j, flags));
+                                  (S.direct[s] && r == K(ps) + R(ps) ? 32 : 0) | 64;
+                // column tiles restart at every change of owner (and at nb): runs of columns this rank owns, cut into <= 64
+                for (int64_t b0 = part == 0 ? 0 : nb; b0 < (part == 0 ? nb : r);) {
+                    const int own = ROWOWN(s, b0);
+                    const int64_t lim = part == 0 ? nb : r;
+                    int64_t b1 = b0 + 1;
+                    while (b1 < lim && ROWOWN(s, b1) == own) ++b1;
+                    if (own == rank)
+                        for (int64_t c0 = b0; c0 < b1; c0 += GEMM_TILE) {
+                            const int w = (int)std::min<int64_t>(GEMM_TILE, b1 - c0);
+                            for (int i = 0; i < nt; ++i) tasks.push_back(make_int4(s, i, (int)c0, flags | (w << 8)));
+                        }
+                    b0 = b1;
                 }
             }
             push(L_GEMM, off, (int)((int64_t)tasks.size() - off), 0, part == 0 ? gA : gB, 0);
@@ -828,6 +992,18 @@ int ensure_uploaded(smslu_handle_t h) {
         CU(cudaMemset(h->d_barrier, 0, sizeof(int)));
         h->st.allreduce_doubles_refactor = h->peer_bytes_refactor / 8;
     }
+    int *d_chain_links, *d_chain_boff, *d_chain_flags;
+    double* d_chain_part;
+    {
+        std::vector<int> cdesc, clinks, cboff;
+        build_chain_schedules(h, tasks, child_ptr_d, child_idx_d, cdesc, clinks, cboff);
+        if ((rc = dev_upload(h, &h->d_chain_desc, cdesc))) return rc;
+        if ((rc = dev_upload(h, &d_chain_links, clinks))) return rc;
+        if ((rc = dev_upload(h, &d_chain_boff, cboff))) return rc;
+        if ((rc = dev_alloc(h, &d_chain_flags, (size_t)2 * S.nsn))) return rc;
+        CU(cudaMemset(d_chain_flags, 0, sizeof(int) * 2 * (size_t)std::max(S.nsn, 1)));
+        if ((rc = dev_alloc(h, &d_chain_part, (size_t)h->chain_part_vecs * KW))) return rc;
+    }
     if ((rc = dev_upload(h, &h->d_tasks, tasks))) return rc;
     int* d_asm_meta;
     if ((rc = dev_upload(h, &d_asm_meta, h->asm_meta))) return rc;
@@ -864,6 +1040,8 @@ int ensure_uploaded(smslu_handle_t h) {
         cx.lmax = tol > 0.0 ? (1.0 + 1.0e-6) / tol : HUGE_VAL;   // a hair above 1/tol: pivots chosen by a host threshold search pass
     }
     cx.a_ptr = d_a_ptr; cx.a_src = d_a_src; cx.a_row = d_a_row; cx.a_pos = d_a_pos;
+    cx.chain_links = d_chain_links; cx.chain_boff = d_chain_boff; cx.chain_flags = d_chain_flags; cx.chain_nsn = S.nsn;
+    cx.chain_part = d_chain_part;
     cx.rowown = d_rowown; cx.rank = h->rank; cx.nranks = h->nranks;
     for (int g = 0; g < MAX_RANKS; ++g) { cx.cb_peer[g] = nullptr; cx.lu_peer[g] = nullptr; cx.xflag_peer[g] = nullptr; }
     cx.cb_peer[h->rank] = d_cb; cx.lu_peer[h->rank] = d_lu; cx.xflag_peer[h->rank] = h->d_xflags;
@@ -930,6 +1108,13 @@ int launch_one(smslu_handle_t h, cudaStream_t st, const Launch& L, const double*
         case L_REPL: launch_replicate(st, h->cx, h->d_segs + 2 * L.off, L.ntasks); break;
         case L_SIGNAL: launch_signal(st, h->cx, (int)L.off, h->epoch); break;
         case L_WAIT: launch_wait(st, h->cx, h->d_wait_slots + L.off, L.ntasks, h->epoch); break;
+        case L_FWD_CHAIN:
+            if (launch_fwd_chain(st, h->cx, h->d_chain_desc + L.off * CHAIN_DESC, L.ntasks, L.fmax, win, zx, ++h->solve_epoch) != cudaSuccess) return -1;
+            break;
+        case L_BWD_RECT: launch_bwd_rect(st, h->cx, h->d_tasks + L.off, L.ntasks, zx); break;
+        case L_BWD_CHAIN:
+            if (launch_bwd_chain(st, h->cx, h->d_chain_desc + L.off * CHAIN_DESC, L.ntasks, L.fmax, zx, ++h->solve_epoch) != cudaSuccess) return -1;
+            break;
     }
     return 0;
 }
@@ -964,8 +1149,8 @@ int run_schedule(smslu_handle_t h, const std::vector<Launch>& sched, const doubl
         }
         for (size_t t = i; t < j; ++t) {
             const Launch& L = sched[t];
-            if ((rc = prof_begin(h, L.kind >= L_REPL ? SMSLU_K_ALLREDUCE : L.kind))) return rc;
-            launch_one(h, lane_stream(L.lane), L, win, zx, rb);
+            if ((rc = prof_begin(h, L.kind == L_FWD_CHAIN ? SMSLU_K_FWD : (L.kind >= L_BWD_RECT ? SMSLU_K_BWD : (L.kind >= L_REPL ? SMSLU_K_ALLREDUCE : L.kind))))) return rc;
+            if (launch_one(h, lane_stream(L.lane), L, win, zx, rb) != 0) return fail(h, SMSLU_E_CUDA, std::string("cooperative launch of a chain kernel failed: ") + cudaGetErrorString(cudaGetLastError()));
             if ((rc = prof_end(h))) return rc;
         }
         if (fork) {
@@ -1084,7 +1269,7 @@ int enqueue_top_forward(smslu_handle_t h, int rb) {
     if (h->vupd_len > 0)
         NCCLCHK(nccl_api().AllReduce(h->cx.upd + h->vupd_off * rb, h->cx.upd + h->vupd_off * rb, (size_t)h->vupd_len * rb, ncclDouble, ncclSum, h->comm, h->stream));
     if ((rc = prof_end(h))) return rc;
-    return run_schedule(h, h->fwd_top, h->d_w, h->d_z, rb);
+    return run_schedule(h, rb == 1 ? h->fwd_top1 : h->fwd_top, h->d_w, h->d_z, rb);
 }
 
 // Every rank holds the solution on its own columns and on the top columns; zero the rest (rank 0
@@ -1103,12 +1288,12 @@ int enqueue_solve(smslu_handle_t h, double* xdev, int64_t ldx, const double* bde
     if ((rc = prof_begin(h, SMSLU_K_PERMUTE))) return rc;
     launch_permute_scale(h->stream, h->n, h->d_p, h->d_Rs, bdev, ldb, h->d_w, rb, nv);
     if ((rc = prof_end(h))) return rc;
-    if ((rc = run_schedule(h, h->fwd, h->d_w, h->d_z, rb))) return rc;
+    if ((rc = run_schedule(h, rb == 1 ? h->fwd1 : h->fwd, h->d_w, h->d_z, rb))) return rc;
     if (h->nranks > 1) {
         if ((rc = enqueue_top_forward(h, rb))) return rc;
-        if ((rc = run_schedule(h, h->bwd_top, nullptr, h->d_z, rb))) return rc;
+        if ((rc = run_schedule(h, rb == 1 ? h->bwd_top1 : h->bwd_top, nullptr, h->d_z, rb))) return rc;
     }
-    if ((rc = run_schedule(h, h->bwd, nullptr, h->d_z, rb))) return rc;
+    if ((rc = run_schedule(h, rb == 1 ? h->bwd1 : h->bwd, nullptr, h->d_z, rb))) return rc;
     if (h->nranks > 1 && (rc = enqueue_gather_solution(h, rb))) return rc;
     if ((rc = prof_begin(h, SMSLU_K_UNPERMUTE))) return rc;
     launch_unpermute(h->stream, h->n, h->d_q, h->d_z, xdev, ldx, rb, nv);
@@ -1298,7 +1483,7 @@ int smslu_solve_async(smslu_handle_t h, double* x_dev, const double* b_dev) {
     if (!h->factored && !h->pending_refactor) return fail(h, SMSLU_E_ARG, "no valid factorization (call smslu_refactor)");
     if (!is_device_ptr(x_dev) || !is_device_ptr(b_dev)) return fail(h, SMSLU_E_ARG, "smslu_solve_async needs device pointers");
     CU(cudaSetDevice(h->device));
-    h->st.launches_solve = (int64_t)h->fwd.size() + (int64_t)h->bwd.size() + 2;
+    h->st.launches_solve = (int64_t)h->fwd1.size() + (int64_t)h->bwd1.size() + (int64_t)h->fwd_top1.size() + (int64_t)h->bwd_top1.size() + 2;
     return enqueue_solve(h, x_dev, h->n, b_dev, h->n, 1, 1);
 }
 
@@ -1378,7 +1563,8 @@ int smslu_solve(smslu_handle_t h, double* x, int64_t nx, const double* b, int64_
         c += nv; ++nsweeps;
     }
     h->st.ms_solve_h2d = h2d; h->st.ms_solve = dev; h->st.ms_solve_d2h = d2h;
-    h->st.launches_solve = nsweeps * ((int64_t)h->fwd.size() + (int64_t)h->bwd.size() + 2);
+    h->st.launches_solve = nrhs == 1 ? (int64_t)h->fwd1.size() + (int64_t)h->bwd1.size() + (int64_t)h->fwd_top1.size() + (int64_t)h->bwd_top1.size() + 2
+                                      : nsweeps * ((int64_t)h->fwd.size() + (int64_t)h->bwd.size() + (int64_t)h->fwd_top.size() + (int64_t)h->bwd_top.size() + 2);
     h->st.n_solve++;
     return prof_collect(h);
 }
@@ -1405,12 +1591,12 @@ static int tri_solve(smslu_handle_t h, double* x, int64_t nx, int64_t nrhs, int6
         // interleave the block (identity permutation, no scaling), sweep, de-interleave
         if (lower) {
             launch_permute_scale(h->stream, n, h->d_post, nullptr, src, lsrc, h->d_w, rb, nv);
-            if ((rc = run_schedule(h, h->fwd, h->d_w, h->d_z, rb))) return rc;
+            if ((rc = run_schedule(h, rb == 1 ? h->fwd1 : h->fwd, h->d_w, h->d_z, rb))) return rc;
             if (h->nranks > 1 && (rc = enqueue_top_forward(h, rb))) return rc;
         } else {
             launch_permute_scale(h->stream, n, h->d_post, nullptr, src, lsrc, h->d_z, rb, nv);
-            if (h->nranks > 1 && (rc = run_schedule(h, h->bwd_top, nullptr, h->d_z, rb))) return rc;
-            if ((rc = run_schedule(h, h->bwd, nullptr, h->d_z, rb))) return rc;
+            if (h->nranks > 1 && (rc = run_schedule(h, rb == 1 ? h->bwd_top1 : h->bwd_top, nullptr, h->d_z, rb))) return rc;
+            if ((rc = run_schedule(h, rb == 1 ? h->bwd1 : h->bwd, nullptr, h->d_z, rb))) return rc;
         }
         if (h->nranks > 1 && (rc = enqueue_gather_solution(h, rb))) return rc;
         launch_unpermute(h->stream, n, h->d_post, h->d_z, dev ? xc : h->d_xb, dev ? ld : n, rb, nv);

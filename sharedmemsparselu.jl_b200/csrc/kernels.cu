@@ -820,17 +820,29 @@ constexpr int GEMM_LDS = GEMM_TILE + 4;   // row stride = 4 (mod 16) doubles: fr
 #ifndef GEMM_MINB
 #define GEMM_MINB 2
 #endif
-__global__ void __launch_bounds__(256, GEMM_MINB) k_gemm_cb(DevCtx cx, const int4* __restrict__ tasks) {
+#ifndef GEMM_AHEAD
+#define GEMM_AHEAD 296          // tiles ahead whose contribution-block tile is pulled into L2 (0 = off): two waves of CTAs
+#endif
+__global__ void __launch_bounds__(256, GEMM_MINB) k_gemm_cb(DevCtx cx, const int4* __restrict__ tasks, int ntasks) {
     extern __shared__ __align__(16) double gsm[];         // 2 stages x (As[NB][GEMM_LDS] | Bs[NB][GEMM_LDS])
     pdl_trigger();
     int4 tk = tasks[blockIdx.x];
     const Front F = load_front(cx, tk.x);
     pdl_wait();
     const int k = F.k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t m0 = (int64_t)tk.y * GEMM_TILE, n0 = (int64_t)tk.z * GEMM_TILE;
+    // tile columns: tk.z = tile index; or (flag bit6, distributed top) tk.z = first column and bits 8..14 of the flags =
+    // width (<= 64): the tiling restarts wherever the column owner changes, so no tile is computed by two ranks
+    const bool colrun = tk.w & 64;
+    const int64_t m0 = (int64_t)tk.y * GEMM_TILE, n0 = colrun ? (int64_t)tk.z : (int64_t)tk.z * GEMM_TILE;
+    const int64_t ncend = colrun ? n0 + ((tk.w >> 8) & 127) : F.r;            // columns [n0, ncend) exist (ncend <= F.r)
     const double* __restrict__ A = F.P + F.k;
     const double* __restrict__ B = F.T;
     const bool beta = tk.w & 1, direct = tk.w & 2, assign = tk.w & 4;
+#ifdef GEMM_EARLY_PARENT
+    // the parent's geometry (direct epilogue) is requested now: two dependent round trips less at the end of the tile
+    Front Q = F;
+    if (direct) Q = load_front(cx, cx.sn_parent[tk.x]);
+#endif
     // partitioned factorization: bit3 = this front is a subtree root below the cut: column b of V goes to the rank that
     // owns global column rows[b], into that rank's copy of the block (peer memory over NVLink, or this rank's own);
     // bit4 = this front is in the distributed top: only the columns this rank owns are updated
@@ -843,11 +855,11 @@ __global__ void __launch_bounds__(256, GEMM_MINB) k_gemm_cb(DevCtx cx, const int
     // entry (row, col) of V lands at front position (row, col) of the parent, no index map needed
     const bool ident = tk.w & 32;
     // interior tile: all 64 x 64 entries exist, no bounds checks in the prologue / epilogue
-    const bool full = m0 + GEMM_TILE <= F.r && n0 + GEMM_TILE <= F.r;
+    const bool full = m0 + GEMM_TILE <= F.r && n0 + GEMM_TILE <= ncend;
     // stage one K chunk (32 columns of L21, 32 rows of U12) with cp.async; rows beyond the block are zero-filled.
     // Thread (a, p0) copies element a of columns p0, p0 + 4, ... of the chunk: running pointers, no index arithmetic.
     const int sa = tid & (GEMM_TILE - 1), sp0 = tid >> 6;
-    const bool oka = m0 + sa < F.r, okb = n0 + sa < F.r;
+    const bool oka = m0 + sa < F.r, okb = n0 + sa < ncend;
     const double* __restrict__ Ath = A + (oka ? m0 + sa : 0) + (int64_t)sp0 * F.f;
     const double* __restrict__ Bth = B + (okb ? n0 + sa : 0) + (int64_t)sp0 * F.r;
     const int64_t astep = 4 * F.f, bstep = 4 * F.r;
@@ -873,6 +885,18 @@ __global__ void __launch_bounds__(256, GEMM_MINB) k_gemm_cb(DevCtx cx, const int
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     stage(0, 0);
+#if GEMM_AHEAD > 0
+    // The tile that will run on this SM about two CTA generations from now reads its 64 x 64 piece of C from HBM
+    // (the trailing matrix is far larger than L2): pull it towards L2 now, so that its prologue sees an L2 hit.
+    // One 128-byte line per thread (64 columns x 4 lines); only when that tile belongs to the same front.
+    if (beta && (int)blockIdx.x + GEMM_AHEAD < ntasks) {
+        const int4 t2 = tasks[blockIdx.x + GEMM_AHEAD];
+        if (t2.x == tk.x) {
+            const int64_t pm = (int64_t)t2.y * GEMM_TILE + (tid & 3) * 16, pn = ((t2.w & 64) ? (int64_t)t2.z : (int64_t)t2.z * GEMM_TILE) + (tid >> 2);
+            if (pm < F.r && pn < F.r) asm volatile("prefetch.global.L2 [%0];" ::"l"(F.C + pm + pn * F.r));
+        }
+    }
+#endif
     double acc[4][2][2];
     // the C loads are in flight while the operand tiles arrive
     if (beta && full) {
@@ -894,7 +918,7 @@ __global__ void __launch_bounds__(256, GEMM_MINB) k_gemm_cb(DevCtx cx, const int
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int64_t row = m0 + wm + 8 * i + fr, col = n0 + wn + 8 * j + 2 * fc + e;
-                    acc[i][j][e] = (beta && row < F.r && col < F.r && (!mine_only || rown[col] == cx.rank)) ? F.C[row + col * F.r] : 0.0;
+                    acc[i][j][e] = (beta && row < F.r && col < ncend && (!mine_only || rown[col] == cx.rank)) ? F.C[row + col * F.r] : 0.0;
                 }
     }
     int buf = 0;
@@ -944,7 +968,7 @@ __global__ void __launch_bounds__(256, GEMM_MINB) k_gemm_cb(DevCtx cx, const int
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int64_t col = n0 + wn + 8 * j + 2 * fc + e;
-                if (col >= F.r) continue;
+                if (col >= ncend) continue;
                 double* __restrict__ dst = F.C;
                 if (xchg) dst = cx.cb_peer[rown[col]] + coff;            // the column's owner (maybe this rank)
                 else if (mine_only && rown[col] != cx.rank) continue;
@@ -956,7 +980,9 @@ __global__ void __launch_bounds__(256, GEMM_MINB) k_gemm_cb(DevCtx cx, const int
             }
         return;
     }
+#ifndef GEMM_EARLY_PARENT
     const Front Q = load_front(cx, cx.sn_parent[tk.x]);
+#endif
     if (ident && full && m0 >= Q.k && n0 >= Q.k) {
         // link of a chain, tile inside the parent's contribution block: a shifted copy
         double* __restrict__ d0 = Q.C + (m0 - Q.k + wm + fr) + (n0 - Q.k + wn + 2 * fc) * Q.r;
@@ -982,7 +1008,7 @@ __global__ void __launch_bounds__(256, GEMM_MINB) k_gemm_cb(DevCtx cx, const int
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int64_t col = n0 + wn + 8 * j + 2 * fc + e;
-            if (col >= F.r || (mine_only && rown[col] != cx.rank)) continue;
+            if (col >= ncend || (mine_only && rown[col] != cx.rank)) continue;
             const int64_t pb = ident ? col : rel[col];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -1193,7 +1219,7 @@ __device__ __forceinline__ void diag_solve_upper(const Front& F, const double* _
 // global memory into registers).  The tile's FWD_ROWS rows of L21 are reduced by 4 threads per row
 // (k/4 columns each, combined in a fixed order).
 template <int RB, int ROWS>
-__global__ void __launch_bounds__(SOLVE_THREADS, (ROWS == FWD_ROWS_WIDE && RB == 1) ? 2 : 1) k_fwd(DevCtx cx, const int4* __restrict__ tasks,
+__global__ void __launch_bounds__(SOLVE_THREADS, (ROWS >= FWD_ROWS_MID && RB == 1) ? 2 : 1) k_fwd(DevCtx cx, const int4* __restrict__ tasks,
                                                        const double* __restrict__ win, double* __restrict__ zout) {
     __shared__ double ys[KW * RB];
     constexpr int NQ = SOLVE_THREADS / ROWS;                 // threads per row in the L21 product (4, 2 or 1)
@@ -1265,7 +1291,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (ROWS == FWD_ROWS_WIDE && RB ==
         for (int q = 0; q < RB; ++q) y[q] = tid < k ? ys[tid * RB + q] : 0.0;
         __syncthreads();                                     // everybody has read its entries of ys
         TRACE2(10);
-        diag_solve_lower<RB, !(ROWS == FWD_ROWS_WIDE && RB == 1)>(F, inv, y, ys, tid);
+        diag_solve_lower<RB, !(ROWS >= FWD_ROWS_MID && RB == 1)>(F, inv, y, ys, tid);
         __syncthreads();
         TRACE2(11);
     }
@@ -1439,6 +1465,267 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (WIDE && RB == 1) ? 2 : 1) k_bw
     for (int e = tid; e < k * RB; e += SOLVE_THREADS) x[(int64_t)F.c0 * RB + e] = part[e];
 }
 
+// ------------------------------------------------------------------ persistent chain solves
+// A wide separator is stored as a chain of fronts (links) of at most KW pivot columns, each the only child of the next and
+// its row list exactly the next link's front.  Level by level that is one launch per link and sweep -- hundreds of dependent
+// launches of ~10-20 us for a 3D problem, an order of magnitude off the HBM time.  Here one persistent kernel runs a whole
+// set of parallel chains (all CTAs co-resident: cooperative launch, one per SM): the chain's row space is cut into blocks
+// (the pivot rows of link j = block j; the rows above the chain in blocks of 128) that are OWNED by CTAs round-robin.
+// Forward, link j:  the owner of block j solves y_j = L11^-1 v_j and publishes it (solution vector + release flag);
+// every CTA acquires it and applies v_B -= L21_j[B, :] y_j to the blocks B > j it owns, block j + 1 first -- its owner
+// then solves and publishes y_{j+1} before touching its other blocks (look-ahead), so the dependent chain per link is
+// flag -> one 128 x 128 product -> pivot solve, while the streaming of L21 trails behind on the other CTAs.
+// Waits are bounded (~2 s): a lost producer raises the error flag instead of hanging the device.
+__device__ __forceinline__ void chain_publish(int* flag, int epoch) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ void chain_wait(const DevCtx& cx, const int* flag, int epoch) {
+    if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        for (;;) {
+            int v;
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            if (v >= epoch) break;
+            if (clock64() - t0 > 4000000000LL) { atomicMin(cx.flag, -4); break; }
+        }
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ const int* chain_of_cta(const int* __restrict__ chains, int nchains) {
+    const int* d = chains;
+    for (int q = 0; q < nchains; ++q, d += CHAIN_DESC)
+        if ((int)blockIdx.x >= d[4] && (int)blockIdx.x < d[4] + d[5]) return d;
+    return nullptr;
+}
+
+__global__ void __launch_bounds__(SOLVE_THREADS, 1) k_fwd_chain(DevCtx cx, const int* __restrict__ chains, int nchains,
+                                                                const double* __restrict__ win, double* __restrict__ zout, int epoch) {
+    __shared__ double vown[CHAIN_MAXOWN][KW];
+    __shared__ double ysA[KW], ysB[KW], red[KW];
+    const int* d = chain_of_cta(chains, nchains);
+    if (!d) return;
+    const int* __restrict__ links = cx.chain_links + d[0];
+    const int m = d[1], nblocks = d[3], c = (int)blockIdx.x - d[4], G = d[5];
+    const int* __restrict__ boff = cx.chain_boff + d[2];
+    const int tid = threadIdx.x, t = tid & (KW - 1), hf = tid >> 7;
+    int* flags = cx.chain_flags;
+    // ---- right-hand side on the pivot blocks, zero above the chain
+    for (int i = 0; c + i * G < nblocks; ++i) {
+        const int b = c + i * G, nb = boff[b + 1] - boff[b];
+        if (tid < KW) vown[i][tid] = (b < m && tid < nb) ? win[cx.sn_start[links[b]] + tid] : 0.0;
+    }
+    __syncthreads();
+    // ---- the bottom link's children (any number, any index map), child by child in ascending order
+    {
+        const int s0 = links[0];
+        for (int ci = cx.child_ptr[s0]; ci < cx.child_ptr[s0 + 1]; ++ci) {
+            const int ch = cx.child_idx[ci];
+            const int64_t rc = cx.rows_ptr[ch + 1] - cx.rows_ptr[ch];
+            const int* __restrict__ rel = cx.rel + cx.rows_ptr[ch];
+            const double* __restrict__ uc = cx.upd + cx.rows_ptr[ch];
+            for (int64_t a = tid; a < rc; a += SOLVE_THREADS) {
+                const int pos = rel[a];
+                for (int i = 0; c + i * G < nblocks; ++i) {
+                    const int b = c + i * G;
+                    if (pos >= boff[b] && pos < boff[b + 1]) { vown[i][pos - boff[b]] += uc[a]; break; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // pivot solve of link j from the block this CTA owns; the solution is left in ys and published
+    auto solve = [&](int j, double* ys) {
+        const int s = links[j];
+        const Front F = load_front(cx, s);
+        const double* __restrict__ inv = cx.dblk + (int64_t)cx.Doff[s] * (NB * NB);
+        double y[1];
+        y[0] = tid < F.k ? vown[j / G][tid] : 0.0;
+        __syncthreads();
+        diag_solve_lower<1, true>(F, inv, y, ys, tid);
+        __syncthreads();
+        if (tid < F.k) zout[F.c0 + tid] = ys[tid];
+        chain_publish(flags + s, epoch);
+    };
+    bool ahead = false;                       // y_j already solved (and sitting in ysB) by the look-ahead of step j - 1
+    for (int j = 0; j < m; ++j) {
+        const int s = links[j];
+        const Front F = load_front(cx, s);
+        if (j % G == c) {
+            if (ahead) { if (tid < KW) ysA[tid] = ysB[tid]; __syncthreads(); }
+            else solve(j, ysA);
+        } else {
+            chain_wait(cx, flags + s, epoch);
+            if (tid < KW) ysA[tid] = tid < F.k ? __ldcg(zout + F.c0 + tid) : 0.0;
+            __syncthreads();
+        }
+        ahead = false;
+        // blocks B > j this CTA owns, block j + 1 first
+        const int first = j + 1;
+        for (int pass = 0; pass < 2; ++pass)
+            for (int i = 0; c + i * G < nblocks; ++i) {
+                const int b = c + i * G;
+                if (b <= j || (pass == 0) != (b == first)) continue;
+                const int nb = boff[b + 1] - boff[b];
+                // rows of block b inside P_j: below the pivot block, offset by the chain rows between
+                const double* __restrict__ src = F.P + F.k + (boff[b] - boff[j + 1]) + t + (int64_t)(hf * (KW / 2)) * F.f;
+                const int jn = F.k - hf * (KW / 2) < KW / 2 ? F.k - hf * (KW / 2) : KW / 2;      // columns of this half
+                double a4[4] = {0.0, 0.0, 0.0, 0.0};
+                if (t < nb) {
+                    const double* __restrict__ yh = ysA + hf * (KW / 2);
+                    int u0 = 0;
+                    for (; u0 + 32 <= jn; u0 += 32) {
+                        double l[32];
+#pragma unroll
+                        for (int u = 0; u < 32; ++u) l[u] = src[(int64_t)(u0 + u) * F.f];
+#pragma unroll
+                        for (int u = 0; u < 32; ++u) a4[u & 3] += l[u] * yh[u0 + u];
+                    }
+                    for (; u0 < jn; ++u0) a4[u0 & 3] += src[(int64_t)u0 * F.f] * yh[u0];
+                }
+                const double part = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+                if (hf == 1) red[t] = part;
+                __syncthreads();
+                if (hf == 0 && t < nb) vown[i][t] -= part + red[t];
+                __syncthreads();
+                if (pass == 0 && first < m) { solve(first, ysB); ahead = true; }
+            }
+    }
+    // ---- what is left on the rows above the chain is the top link's update vector
+    {
+        const int sl = links[m - 1];
+        double* __restrict__ us = cx.upd + cx.rows_ptr[sl];
+        for (int i = 0; c + i * G < nblocks; ++i) {
+            const int b = c + i * G;
+            if (b < m) continue;
+            const int nb = boff[b + 1] - boff[b];
+            if (tid < nb) us[boff[b] - boff[m] + tid] = vown[i][tid];
+        }
+    }
+}
+
+// Backward, rows above the chain: partial products  part[link][tile][c] = sum_{a in tile} U12'_link[a, c] x[rows[a]]  for every
+// link of every chain of the set at once (x above the chain is final: no dependencies).  task: x = link, y = first row of the
+// tile inside T_link, z = rows, w = slot (KW-vector) of the result.
+__global__ void __launch_bounds__(SOLVE_THREADS, 2) k_bwd_rect(DevCtx cx, const int4* __restrict__ tasks, const double* __restrict__ x) {
+    __shared__ double xs[BWD_ROWS];
+    const int4 tk = tasks[blockIdx.x];
+    const Front F = load_front(cx, tk.x);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, cnt = tk.z;
+    const int* __restrict__ rows = cx.rows + cx.rows_ptr[tk.x] + tk.y;
+    xs[tid] = tid < cnt ? x[rows[tid]] : 0.0;
+    __syncthreads();
+    double* __restrict__ out = cx.chain_part + (int64_t)tk.w * KW;
+    constexpr int BU = 4;
+    for (int i0 = warp * BU; i0 < F.k; i0 += (SOLVE_THREADS / 32) * BU) {
+        double tv[BU][BWD_ROWS / 32], v[BU];
+#pragma unroll
+        for (int u = 0; u < BU; ++u) {
+            const double* __restrict__ col = F.T + (int64_t)(i0 + u) * F.r + tk.y;
+#pragma unroll
+            for (int a = 0; a < BWD_ROWS / 32; ++a) tv[u][a] = (i0 + u < F.k && lane + 32 * a < cnt) ? col[lane + 32 * a] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < BU; ++u) {
+            v[u] = 0.0;
+#pragma unroll
+            for (int a = 0; a < BWD_ROWS / 32; ++a) v[u] += tv[u][a] * xs[lane + 32 * a];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[u] += __shfl_xor_sync(0xffffffffu, v[u], o);
+            if (lane == 0 && i0 + u < F.k) out[i0 + u] = v[u];
+        }
+    }
+}
+
+// Backward chain: link i = m-1 .. 0.  The owner of link i solves x_i = U11^-1 (pending_i) and publishes it; every CTA
+// applies  pending_j -= U[j-block, i-block] x_i  to the links j < i it owns (the block is rows [o_i - o_{j+1}, +k_i) of T_j),
+// link i - 1 first, whose owner then solves and publishes x_{i-1} before its other links (look-ahead).
+__global__ void __launch_bounds__(SOLVE_THREADS, 1) k_bwd_chain(DevCtx cx, const int* __restrict__ chains, int nchains,
+                                                                double* __restrict__ x, int epoch) {
+    __shared__ double pend[CHAIN_MAXOWN][KW];
+    __shared__ double xsA[KW], xsB[KW];
+    const int* d = chain_of_cta(chains, nchains);
+    if (!d) return;
+    const int* __restrict__ links = cx.chain_links + d[0];
+    const int m = d[1], c = (int)blockIdx.x - d[4], G = d[5], ntile = d[7];
+    const int* __restrict__ boff = cx.chain_boff + d[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int* flags = cx.chain_flags + cx.chain_nsn;
+    // link j is owned by CTA (m - 1 - j) % G, slot (m - 1 - j) / G
+    auto owner = [&](int j) { return (m - 1 - j) % G; };
+    auto slot = [&](int j) { return (m - 1 - j) / G; };
+    // ---- pending right-hand sides: forward solution minus the (tile-ordered) products with the rows above the chain
+    for (int j = m - 1 - c; j >= 0; j -= G) {
+        const int s = links[j], k = cx.sn_start[s + 1] - cx.sn_start[s];
+        if (tid < KW) {
+            double v = tid < k ? x[cx.sn_start[s] + tid] : 0.0;
+            const double* __restrict__ pp = cx.chain_part + ((int64_t)d[6] + (int64_t)j * ntile) * KW + tid;
+            for (int tl = 0; tl < ntile; ++tl) v -= (tid < k ? pp[(int64_t)tl * KW] : 0.0);
+            pend[slot(j)][tid] = v;
+        }
+    }
+    __syncthreads();
+    auto solve = [&](int i, double* xs) {
+        const int s = links[i];
+        const Front F = load_front(cx, s);
+        const double* __restrict__ inv = cx.dblk + (int64_t)cx.Doff[s] * (NB * NB);
+        double v[1];
+        v[0] = tid < F.k ? pend[slot(i)][tid] : 0.0;
+        __syncthreads();
+        diag_solve_upper<1, true>(F, inv, v, xs, tid);
+        __syncthreads();
+        if (tid < F.k) x[F.c0 + tid] = xs[tid];
+        chain_publish(flags + s, epoch);
+    };
+    bool ahead = false;
+    for (int i = m - 1; i >= 0; --i) {
+        const int s = links[i], ki = cx.sn_start[s + 1] - cx.sn_start[s];
+        if (owner(i) == c) {
+            if (ahead) { if (tid < KW) xsA[tid] = xsB[tid]; __syncthreads(); }
+            else solve(i, xsA);
+        } else {
+            chain_wait(cx, flags + s, epoch);
+            if (tid < KW) xsA[tid] = tid < ki ? __ldcg(x + cx.sn_start[s] + tid) : 0.0;
+            __syncthreads();
+        }
+        ahead = false;
+        const int first = i - 1;
+        for (int pass = 0; pass < 2; ++pass)
+            for (int j = m - 1 - c; j >= 0; j -= G) {
+                if (j >= i || (pass == 0) != (j == first)) continue;
+                const Front F = load_front(cx, links[j]);
+                // rows of link i's pivots inside T_j (r_j x k_j): a warp takes columns c0 = warp, warp + 8, ...; lanes = rows
+                const double* __restrict__ blk = F.T + (boff[i] - boff[j + 1]);
+                double xv[KW / 32];
+#pragma unroll
+                for (int a = 0; a < KW / 32; ++a) xv[a] = xsA[lane + 32 * a];        // zero beyond k_i
+                for (int c0 = warp; c0 < F.k; c0 += 4 * (SOLVE_THREADS / 32)) {
+                    double v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int cc = c0 + u * (SOLVE_THREADS / 32);
+                        const double* __restrict__ col = blk + (int64_t)cc * F.r;
+                        v[u] = 0.0;
+                        if (cc < F.k) {
+#pragma unroll
+                            for (int a = 0; a < KW / 32; ++a) v[u] += (lane + 32 * a < ki ? col[lane + 32 * a] : 0.0) * xv[a];
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) v[u] += __shfl_xor_sync(0xffffffffu, v[u], o);
+                        const int cc = c0 + u * (SOLVE_THREADS / 32);
+                        if (lane == 0 && cc < F.k) pend[slot(j)][cc] -= v[u];
+                    }
+                }
+                __syncthreads();
+                if (pass == 0 && first >= 0) { solve(first, xsB); ahead = true; }
+            }
+    }
+}
+
 // ------------------------------------------------------------------ partitioned solves
 // One CTA per interface front: sum the update vectors of this rank's subtree roots below it into the
 // front's virtual child (rel = identity), root by root in ascending order.
@@ -1515,8 +1802,7 @@ __global__ void k_signal(DevCtx cx, int slot, int epoch) {
     }
 }
 __global__ void k_wait(DevCtx cx, const int* __restrict__ slots, int nslots, int epoch) {
-    const int i = threadIdx.x;
-    if (i < nslots) {
+    for (int i = threadIdx.x; i < nslots; i += blockDim.x) {
         const int* f = cx.xflag_peer[cx.rank] + slots[i];
         const long long t0 = clock64();
         for (;;) {
@@ -1777,7 +2063,21 @@ void launch_panel(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntas
     else launch_pdl(k_panel<PANEL_ROWS_TOP>, ntasks, PANEL_THREADS, panel_smem(g * NB, PANEL_ROWS_TOP), st, cx, tasks);
 }
 void launch_gemm_cb(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks) {
-    if (ntasks > 0) launch_pdl(k_gemm_cb, ntasks, 256, gemm_smem(), st, cx, tasks);
+    if (ntasks > 0) launch_pdl(k_gemm_cb, ntasks, 256, gemm_smem(), st, cx, tasks, ntasks);
+}
+template <class... KArgs>
+static cudaError_t launch_coop(void (*kern)(KArgs...), int grid, int block, cudaStream_t st, KArgs... args) {
+    void* argv[] = {(void*)&args...};
+    return cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(block), argv, 0, st);
+}
+cudaError_t launch_fwd_chain(cudaStream_t st, const DevCtx& cx, const int* chains, int nchains, int nctas, const double* win, double* zout, int epoch) {
+    return launch_coop(k_fwd_chain, nctas, SOLVE_THREADS, st, cx, chains, nchains, win, zout, epoch);
+}
+void launch_bwd_rect(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const double* x) {
+    if (ntasks > 0) k_bwd_rect<<<ntasks, SOLVE_THREADS, 0, st>>>(cx, tasks, x);
+}
+cudaError_t launch_bwd_chain(cudaStream_t st, const DevCtx& cx, const int* chains, int nchains, int nctas, double* x, int epoch) {
+    return launch_coop(k_bwd_chain, nctas, SOLVE_THREADS, st, cx, chains, nchains, x, epoch);
 }
 void launch_permute_scale(cudaStream_t st, int n, const int* p, const double* Rs, const double* b, int64_t ldb, double* w, int rb, int nv) {
 #define CALL(R) k_permute_scale<R><<<(n + 255) / 256, 256, 0, st>>>(n, p, Rs, b, ldb, w, nv)

@@ -32,6 +32,9 @@ constexpr int ZERO_TILE = 8192;
 constexpr int RB_MAX = 8;         // most right-hand sides swept together by the solve kernels
 constexpr int ASM_COLS = 8;       // destination columns of a parent front per assembly CTA
 constexpr int MAX_RANKS = 8;      // GPUs of one NVSwitch box
+constexpr int CHAIN_MAXOWN = 8;   // blocks (forward) / links (backward) of a chain one CTA of the persistent solve kernels may own
+constexpr int CHAIN_DESC = 8;     // ints per chain descriptor: links_off, m, boff_off, nblocks, cta0, nctas, part_off (in KW-vectors), tiles above
+constexpr int CHAIN_CTAS = 148;   // one CTA per SM, all co-resident (cooperative launch)
 constexpr int ASM_SMEM_ROWS = 1536; // parents up to this many rows are assembled through shared memory (96 KB per CTA at most)
 
 struct DevCtx {
@@ -67,6 +70,12 @@ struct DevCtx {
     // partition over several GPUs (one process each), see DESIGN.md "Multi-GPU": owner of the global column behind
     // every entry of `rows` (-1: not a top column); this rank; the ranks' contribution / factor pools and sync flags
     // mapped into this process (CUDA IPC; own pool at index `rank`)
+    // chains of fronts cut out of one wide separator, solved by one persistent kernel per sweep (k_fwd_chain / k_bwd_chain)
+    const int* chain_links;   // supernodes of every chain, bottom link first
+    const int* chain_boff;    // per chain: row offsets of its blocks (pivot blocks of the links, then 128-row blocks of the rows above the chain)
+    int* chain_flags;         // [2 * chain_nsn]: epoch at which link s published its part of the solution (forward | backward)
+    int chain_nsn;
+    double* chain_part;       // backward: partial products of the rows above the chain, [link][row tile][KW]
     const signed char* rowown;
     int rank, nranks;
     double* cb_peer[MAX_RANKS];
@@ -97,6 +106,7 @@ void launch_small_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int 
 void launch_small_bwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, double* x, int rb);
 void launch_panel(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int g, int rows);
 void launch_gemm_cb(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks);
+void launch_gemm_strip(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks);   // y = first row tile | tiles << 16
 int front_small_limit();   // largest front the fused shared-memory kernel takes
 cudaError_t kernels_init();
 int debug_read_trace(long long* out);   // 0 unless built with SMSLU_TRACE
@@ -106,5 +116,9 @@ void launch_permute_scale(cudaStream_t st, int n, const int* p, const double* Rs
 void launch_unpermute(cudaStream_t st, int n, const int* q, const double* w, double* x, int64_t ldx, int rb, int nv);
 void launch_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int rows, const double* win, double* zout, int rb);
 void launch_bwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, double* x, int rb);
+// persistent chain kernels (single right-hand side): descriptors of `nchains` chains, `nctas` CTAs in total
+cudaError_t launch_fwd_chain(cudaStream_t st, const DevCtx& cx, const int* chains, int nchains, int nctas, const double* win, double* zout, int epoch);
+void launch_bwd_rect(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const double* x);
+cudaError_t launch_bwd_chain(cudaStream_t st, const DevCtx& cx, const int* chains, int nchains, int nctas, double* x, int epoch);
 
 }  // namespace smslu
