@@ -473,9 +473,14 @@ def run_ours(args, rank, world, local_rank):
     try:   # DRAM traffic of that kernel from the committed ncu --set full capture (mean over the captured launches)
         tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["kernels"].get(dom)
         if tr:
-            roof["traffic"] = tr["dram_bytes_per_launch_mean"]
-            roof["traffic_source"] = "profiles/%s: mean dram read+write bytes over %d captured launches" % (tr["capture"], len(tr["launches"]))
             roof["algorithmic_bytes_per_launch"] = work[dom]["bytes"] / max(1, launches_kernel.get(dom, 1))
+            if "traffic_over_algorithmic" in tr:      # launches of very different sizes: scale the captured launches' ratio
+                roof["traffic"] = tr["traffic_over_algorithmic"] * roof["algorithmic_bytes_per_launch"]
+                roof["traffic_source"] = ("profiles/%s: dram read+write bytes / algorithmic bytes = %.3f over %d captured launches, "
+                                          "times this run's algorithmic bytes per launch" % (tr["capture"], tr["traffic_over_algorithmic"], len(tr["launches"])))
+            else:
+                roof["traffic"] = tr["dram_bytes_per_launch_mean"]
+                roof["traffic_source"] = "profiles/%s: mean dram read+write bytes over %d captured launches" % (tr["capture"], len(tr["launches"]))
     except Exception:
         pass
     comm = None

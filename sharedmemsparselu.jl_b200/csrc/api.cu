@@ -68,6 +68,8 @@ enum LaunchKind { L_ZERO = SMSLU_K_ZERO, L_EXTEND = SMSLU_K_EXTEND, L_SMALL = SM
                   L_FWD_CHAIN = 103, L_BWD_RECT = 104, L_BWD_CHAIN = 105 };
 
 constexpr int NLANES = 4;
+constexpr int GEMM_STRIP_DEFAULT = 1;
+constexpr bool CHAINS_DEFAULT = false;
 
 constexpr int PANEL_GROUP_CTAS = 296;  // panel launches aim at about this many CTAs (2 per SM) ...
 constexpr int PANEL_GROUP_MAX = 16;    // ... by giving one CTA up to this many 128-row tiles of its front
@@ -225,6 +227,8 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
     auto SMALL = [&](int s) { return S.small[s] != 0; };
     int64_t ncounters = 0, slots = 0;
     int cur_level = 0, big_lane = 0;
+    // Schur-update CTAs walk strips of this many row tiles of one tile column (k_gemm_strip); 1 = one tile per CTA (k_gemm_cb)
+    const int gemm_strip = getenv("SMSLU_GEMM_STRIP") ? std::max(1, atoi(getenv("SMSLU_GEMM_STRIP"))) : GEMM_STRIP_DEFAULT;
     auto push = [&](std::vector<Launch>& v, int kind, int64_t off, int fmax) {
         int nt = (int)((int64_t)tasks.size() - off);
         // small fronts: factor classes up to 40 rows on lane 1, the wider ones on lane 2; solves on lane 1;
@@ -367,16 +371,14 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
                     int64_t r = R(s);
                     if (!IN(s) || SMALL(s) || NARROW(s) != (grp == 1)) continue;
                     int nt = (int)((r + GEMM_TILE - 1) / GEMM_TILE);
+                    const int flags = (NC(s) > 0 ? 1 : 0) | (S.direct[s] ? 2 : 0) |
+                                      (S.direct[s] && S.cb_assigned[S.sn_parent[s]] ? 4 : 0) |
+                                      (S.xroot[s] ? 8 : 0) |      // subtree root: columns go to their owners' pools
+                                      (S.direct[s] && r == K(S.sn_parent[s]) + R(S.sn_parent[s]) ? 32 : 0);   // chain link: identity map
                     for (int j = 0; j < nt; ++j)
-                        for (int i = 0; i < nt; ++i) {
-                            int flags = (NC(s) > 0 ? 1 : 0) | (S.direct[s] ? 2 : 0) |
-                                        (S.direct[s] && S.cb_assigned[S.sn_parent[s]] ? 4 : 0) |
-                                        (S.xroot[s] ? 8 : 0) |      // subtree root: columns go to their owners' pools
-                                        (S.direct[s] && r == K(S.sn_parent[s]) + R(S.sn_parent[s]) ? 32 : 0);   // chain link: identity map
-                            tasks.push_back(make_int4(s, i, j, flags));
-                        }
+                        for (int i = 0; i < nt; i += gemm_strip) tasks.push_back(make_int4(s, gemm_strip > 1 ? (i | (std::min(gemm_strip, nt - i) << 16)) : i, j, flags));
                 }
-                push(fac, L_GEMM, off, 0);
+                push(fac, L_GEMM, off, gemm_strip > 1 ? 1 : 0);
             }
             big_lane = 0;
             }
@@ -456,7 +458,9 @@ void build_chain_schedules(smslu_handle_t h, std::vector<int4>& tasks, const std
     const Symbolic& S = h->S;
     auto K = [&](int s) { return S.sn_start[s + 1] - S.sn_start[s]; };
     auto R = [&](int s) { return (int64_t)(S.rows_ptr[s + 1] - S.rows_ptr[s]); };
-    const bool enabled = !(getenv("SMSLU_NO_CHAINS") && atoi(getenv("SMSLU_NO_CHAINS")) != 0);
+    // default off until validated on the GPU in this round: SMSLU_CHAINS=1 switches the persistent chain kernels on
+    const bool enabled = CHAINS_DEFAULT ? !(getenv("SMSLU_NO_CHAINS") && atoi(getenv("SMSLU_NO_CHAINS")) != 0)
+                                        : (getenv("SMSLU_CHAINS") && atoi(getenv("SMSLU_CHAINS")) != 0);
     for (int ph = 0; ph < 2; ++ph) {
         const std::vector<Launch>& fwd = ph == 0 ? h->fwd : h->fwd_top;
         const std::vector<Launch>& bwd = ph == 0 ? h->bwd : h->bwd_top;
@@ -1102,7 +1106,7 @@ int launch_one(smslu_handle_t h, cudaStream_t st, const Launch& L, const double*
         case L_FWD_SMALL: launch_small_fwd(st, h->cx, tk, L.ntasks, win, zx, rb); break;
         case L_BWD_SMALL: launch_small_bwd(st, h->cx, tk, L.ntasks, zx, rb); break;
         case L_PANEL: launch_panel(st, h->cx, tk, L.ntasks, L.fmax & 255, L.fmax >> 8); break;
-        case L_GEMM: launch_gemm_cb(st, h->cx, tk, L.ntasks); break;
+        case L_GEMM: if (L.fmax == 1) launch_gemm_strip(st, h->cx, tk, L.ntasks); else launch_gemm_cb(st, h->cx, tk, L.ntasks); break;
         case L_FWD: launch_fwd(st, h->cx, tk, L.ntasks, L.fmax >> 8, win, zx, rb); break;
         case L_BWD: launch_bwd(st, h->cx, tk, L.ntasks, zx, rb); break;
         case L_REPL: launch_replicate(st, h->cx, h->d_segs + 2 * L.off, L.ntasks); break;
@@ -1239,6 +1243,11 @@ int finish_refactor(smslu_handle_t h) {
     h->pending_refactor = false;
     h->st.n_refactor++;
     const int flag = *h->h_flag;
+    if (flag == -3 || flag == -4) {          // a bounded device-side wait gave up (k_wait: a peer GPU; chain_wait: a CTA of the same kernel)
+        h->factored = false;
+        return fail(h, SMSLU_E_INTERNAL, flag == -3 ? "timed out waiting for a panel from a peer GPU (a rank died or fell out of step)"
+                                                    : "a chain solve kernel timed out waiting for another CTA");
+    }
     if (flag != FLAG_CLEAN) {
         h->factored = false;
         h->st.bad_pivot_col = flag;
@@ -1561,6 +1570,11 @@ int smslu_solve(smslu_handle_t h, double* x, int64_t nx, const double* b, int64_
         CU(cudaEventElapsedTime(&ms, h->ev1, h->ev2)); dev += ms;
         CU(cudaEventElapsedTime(&ms, h->ev2, h->ev3)); d2h += ms;
         c += nv; ++nsweeps;
+    }
+    {   // the persistent chain kernels report a timed-out wait through the pivot flag word
+        int f0 = 0;
+        CU(cudaMemcpy(&f0, h->cx.flag, sizeof(int), cudaMemcpyDeviceToHost));
+        if (f0 == -4) return fail(h, SMSLU_E_INTERNAL, "a chain solve kernel timed out waiting for another CTA");
     }
     h->st.ms_solve_h2d = h2d; h->st.ms_solve = dev; h->st.ms_solve_d2h = d2h;
     h->st.launches_solve = nrhs == 1 ? (int64_t)h->fwd1.size() + (int64_t)h->bwd1.size() + (int64_t)h->fwd_top1.size() + (int64_t)h->bwd_top1.size() + 2

@@ -1026,6 +1026,193 @@ __global__ void __launch_bounds__(256, GEMM_MINB) k_gemm_cb(DevCtx cx, const int
         }
 }
 
+// Strip variant of k_gemm_cb: one CTA walks `ni` consecutive row tiles of ONE tile column.  The 64 x k piece of U12
+// stays in shared memory for the whole strip (half the operand traffic and copy instructions), the front's geometry is
+// read once, and the cp.async pipeline of the L21 chunks never drains: chunk 0 of the next tile is in flight under the
+// last chunk and the epilogue of the current one.  task: y = first row tile | tiles << 16; everything else as k_gemm_cb.
+__global__ void __launch_bounds__(256, 2) k_gemm_strip(DevCtx cx, const int4* __restrict__ tasks) {
+    extern __shared__ __align__(16) double gsm[];         // Bs[KW][GEMM_LDS] | 2 stages x As[NB][GEMM_LDS]
+    pdl_trigger();
+    const int4 tk = tasks[blockIdx.x];
+    const Front F = load_front(cx, tk.x);
+    const bool beta = tk.w & 1, direct = tk.w & 2, assign = tk.w & 4, xchg = tk.w & 8, mine_only = tk.w & 16, ident = tk.w & 32, colrun = tk.w & 64;
+    Front Q = F;
+    if (direct) Q = load_front(cx, cx.sn_parent[tk.x]);   // static geometry: requested before the dependency wait
+    pdl_wait();
+    const int k = F.k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ni = (tk.y >> 16) > 0 ? (tk.y >> 16) : 1;
+    const int64_t m0s = (int64_t)(tk.y & 0xffff) * GEMM_TILE, n0 = colrun ? (int64_t)tk.z : (int64_t)tk.z * GEMM_TILE;
+    const int64_t ncend = colrun ? n0 + ((tk.w >> 8) & 127) : F.r;
+    const double* __restrict__ A = F.P + F.k;
+    const double* __restrict__ B = F.T;
+    const signed char* __restrict__ rown = cx.rowown + cx.rows_ptr[tk.x];
+    const int wm = (warp & 1) * 32, wn = (warp >> 1) * 16, fr = lane >> 2, fc = lane & 3;
+    const int sa = tid & (GEMM_TILE - 1), sp0 = tid >> 6;
+    const bool okb = n0 + sa < ncend;
+    double* const Bs_all = gsm;
+    double* const As_all = gsm + KW * GEMM_LDS;
+    const int nchunk = (k + NB - 1) / NB;
+    {   // the strip's piece of U12 (k x 64), once
+        const double* __restrict__ bp = B + (okb ? n0 + sa : 0) + (int64_t)sp0 * F.r;
+        double* bs = Bs_all + sp0 * GEMM_LDS + sa;
+        for (int p = sp0; p < nchunk * NB; p += 4, bp += 4 * F.r, bs += 4 * GEMM_LDS) cp_async8(bs, p < k ? bp : B, p < k && okb);
+    }
+    const double* __restrict__ Acol = A + (int64_t)sp0 * F.f;
+    const int64_t astep = 4 * F.f;
+    auto stage = [&](int q) {              // chunk q of the strip: tile q / nchunk, columns [32 (q % nchunk), +32) of L21
+        const int ti = q / nchunk, kc = (q - ti * nchunk) * NB;
+        const int64_t mrow = m0s + (int64_t)ti * GEMM_TILE + sa;
+        const bool oka = mrow < F.r;
+        double* as = As_all + (q & 1) * (NB * GEMM_LDS) + sp0 * GEMM_LDS + sa;
+        const double* __restrict__ ap = Acol + (oka ? mrow : 0) + (int64_t)kc * F.f;
+#pragma unroll
+        for (int u = 0; u < NB / 4; ++u, ap += astep) {
+            const bool in = kc + sp0 + 4 * u < k;
+            cp_async8(as + u * 4 * GEMM_LDS, in ? ap : A, in && oka);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage(0);
+    double acc[4][2][2];
+    const int total = ni * nchunk;
+    int64_t m0 = m0s;
+    bool full = false;
+    for (int q = 0; q < total; ++q) {
+        const int ti = q / nchunk, c = q - ti * nchunk;
+        if (c == 0) {
+            m0 = m0s + (int64_t)ti * GEMM_TILE;
+            full = m0 + GEMM_TILE <= F.r && n0 + GEMM_TILE <= ncend;
+            // the next tile's piece of C towards L2; this tile's piece into the accumulators (in flight while the operands arrive)
+            if (beta && ti + 1 < ni) {
+                const int64_t pm = m0 + GEMM_TILE + (tid & 3) * 16, pn = n0 + (tid >> 2);
+                if (pm < F.r && pn < ncend) asm volatile("prefetch.global.L2 [%0];" ::"l"(F.C + pm + pn * F.r));
+            }
+            if (beta && full) {
+                const double* __restrict__ c0 = F.C + (m0 + wm + fr) + (n0 + wn + 2 * fc) * F.r;
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const double* __restrict__ cc = c0 + (8 * j + e) * F.r;
+                        const bool on = !mine_only || rown[n0 + wn + 8 * j + 2 * fc + e] == cx.rank;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc[i][j][e] = on ? cc[8 * i] : 0.0;
+                    }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int64_t row = m0 + wm + 8 * i + fr, col = n0 + wn + 8 * j + 2 * fc + e;
+                            acc[i][j][e] = (beta && row < F.r && col < ncend && (!mine_only || rown[col] == cx.rank)) ? F.C[row + col * F.r] : 0.0;
+                        }
+            }
+        }
+        if (q + 1 < total) {
+            stage(q + 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        {
+            const double* As = As_all + (q & 1) * (NB * GEMM_LDS);
+            const double* Bs = Bs_all + c * NB * GEMM_LDS;
+            const int kw = (k - c * NB < NB) ? k - c * NB : NB;
+            const int ksteps = (kw + 3) >> 2;
+            for (int ks = 0; ks < ksteps; ++ks) {
+                const int p = 4 * ks + fc;
+                double a[4], b[2];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = -As[p * GEMM_LDS + wm + 8 * i + fr];      // C - L21 U12
+#pragma unroll
+                for (int j = 0; j < 2; ++j) b[j] = Bs[p * GEMM_LDS + wn + 8 * j + fr];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            }
+        }
+        __syncthreads();                                 // the stage is refilled by the next iteration's copy
+        if (c != nchunk - 1) continue;
+        // ---- epilogue of tile ti (as in k_gemm_cb)
+        if (!direct) {
+            const int64_t coff = F.C - cx.cb;
+            if (full && !xchg) {
+                double* __restrict__ c0 = F.C + (m0 + wm + fr) + (n0 + wn + 2 * fc) * F.r;
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        if (mine_only && rown[n0 + wn + 8 * j + 2 * fc + e] != cx.rank) continue;
+                        double* __restrict__ cc = c0 + (8 * j + e) * F.r;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) cc[8 * i] = acc[i][j][e];
+                    }
+                continue;
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int64_t col = n0 + wn + 8 * j + 2 * fc + e;
+                    if (col >= ncend) continue;
+                    double* __restrict__ dst = F.C;
+                    if (xchg) dst = cx.cb_peer[rown[col]] + coff;
+                    else if (mine_only && rown[col] != cx.rank) continue;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int64_t row = m0 + wm + 8 * i + fr;
+                        if (row < F.r) dst[row + col * F.r] = acc[i][j][e];
+                    }
+                }
+            continue;
+        }
+        if (ident && full && m0 >= Q.k && n0 >= Q.k) {
+            double* __restrict__ d0 = Q.C + (m0 - Q.k + wm + fr) + (n0 - Q.k + wn + 2 * fc) * Q.r;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    if (mine_only && rown[n0 + wn + 8 * j + 2 * fc + e] != cx.rank) continue;
+                    double* __restrict__ dd = d0 + (8 * j + e) * Q.r;
+                    if (assign) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) dd[8 * i] = acc[i][j][e];
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) dd[8 * i] += acc[i][j][e];
+                    }
+                }
+            continue;
+        }
+        const int* __restrict__ rel = cx.rel + cx.rows_ptr[tk.x];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int64_t col = n0 + wn + 8 * j + 2 * fc + e;
+                if (col >= ncend || (mine_only && rown[col] != cx.rank)) continue;
+                const int64_t pb = ident ? col : rel[col];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int64_t row = m0 + wm + 8 * i + fr;
+                    if (row >= F.r) continue;
+                    const int64_t pa = ident ? row : rel[row];
+                    const double v = acc[i][j][e];
+                    if (pb < Q.k) Q.P[pa + pb * Q.f] += v;
+                    else if (pa < Q.k) Q.T[(pb - Q.k) + pa * Q.r] += v;
+                    else {
+                        double* d = Q.C + (pa - Q.k) + (pb - Q.k) * Q.r;
+                        *d = assign ? v : *d + v;
+                    }
+                }
+            }
+    }
+}
+
 // ------------------------------------------------------------------ inverses of the diagonal blocks
 // After the factorization, one warp per 32 x 32 diagonal block D_gg = L_gg U_gg of a big front's pivot block:
 // dblk[block] (32 x 32, column-major) holds L_gg^{-1} below the diagonal (its unit diagonal is implicit) and
@@ -1488,6 +1675,8 @@ __device__ __forceinline__ void chain_wait(const DevCtx& cx, const int* flag, in
             int v;
             asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
             if (v >= epoch) break;
+            // a producer that never shows up: raise the error flag once; every later wait sees it and gives up at once
+            if (*(volatile int*)cx.flag == -4) break;
             if (clock64() - t0 > 4000000000LL) { atomicMin(cx.flag, -4); break; }
         }
     }
@@ -1948,6 +2137,7 @@ int debug_read_trace(long long* out) {
 constexpr int SMALL_FPC32 = 4;     // fronts per CTA in the one-warp class of k_small_factor
 
 static size_t gemm_smem() { return sizeof(double) * 2 * 2 * NB * GEMM_LDS; }
+static size_t gemm_strip_smem() { return sizeof(double) * (KW + 2 * NB) * GEMM_LDS; }
 static size_t panel_smem(int j0, int rows) {
     return sizeof(double) * ((2 * (size_t)j0 + rows) * CLD + (rows == PANEL_ROWS_TOP ? (size_t)rows * (KW + 4) : 0));
 }
@@ -1972,6 +2162,8 @@ cudaError_t kernels_init() {
                                          (int)(sizeof(double) * small_group_doubles(96)));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_gemm_cb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_gemm_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_strip_smem());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_panel<PANEL_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem(KW - NB, PANEL_ROWS));
     if (e != cudaSuccess) return e;
@@ -2064,6 +2256,9 @@ void launch_panel(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntas
 }
 void launch_gemm_cb(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks) {
     if (ntasks > 0) launch_pdl(k_gemm_cb, ntasks, 256, gemm_smem(), st, cx, tasks, ntasks);
+}
+void launch_gemm_strip(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks) {
+    if (ntasks > 0) launch_pdl(k_gemm_strip, ntasks, 256, gemm_strip_smem(), st, cx, tasks);
 }
 template <class... KArgs>
 static cudaError_t launch_coop(void (*kern)(KArgs...), int grid, int block, cudaStream_t st, KArgs... args) {
