@@ -494,7 +494,7 @@ void build_chain_schedules(smslu_handle_t h, std::vector<int4>& tasks, const std
                 if (!ok) break;
                 ++l1;
             }
-            if (l1 - l + 1 >= 4 && C[l].size() <= 32) {
+            if (l1 - l + 1 >= 4 && l1 - l + 1 <= KW && C[l].size() <= 32) {        // (the kernels keep per-link geometry of <= KW links in shared memory)
                 ChainSet cs; cs.l0 = l; cs.l1 = l1;
                 for (int top : C[l1]) {                    // follow every chain down from its top link
                     std::vector<int> ch(1, top);

@@ -1631,10 +1631,21 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (WIDE && RB == 1) ? 2 : 1) k_bw
         __syncthreads();
         if (!s_last) return;
         __threadfence();
+        // tile-ordered sum of the partial vectors: eight loads in flight per thread (the chain of dependent L2 round
+        // trips was the longest piece of a level with many tiles), four running sums combined in a fixed order
         for (int e = tid; e < k * RB; e += SOLVE_THREADS) {
-            double v = 0.0;
-            for (int t = 0; t < ntiles; ++t) v += __ldcg(slot + (int64_t)t * KW * RB + e);
-            part[e] = v;
+            double a4[4] = {0.0, 0.0, 0.0, 0.0};
+            const double* __restrict__ sp = slot + e;
+            int t = 0;
+            for (; t + 8 <= ntiles; t += 8) {
+                double l[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) l[u] = __ldcg(sp + (int64_t)(t + u) * KW * RB);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) a4[u & 3] += l[u];
+            }
+            for (; t < ntiles; ++t) a4[t & 3] += __ldcg(sp + (int64_t)t * KW * RB);
+            part[e] = (a4[0] + a4[1]) + (a4[2] + a4[3]);
         }
         __syncthreads();
     }
@@ -1671,13 +1682,15 @@ __device__ __forceinline__ void chain_publish(int* flag, int epoch) {
 __device__ __forceinline__ void chain_wait(const DevCtx& cx, const int* flag, int epoch) {
     if (threadIdx.x == 0) {
         const long long t0 = clock64();
-        for (;;) {
+        for (int it = 0;; ++it) {
             int v;
             asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
             if (v >= epoch) break;
-            // a producer that never shows up: raise the error flag once; every later wait sees it and gives up at once
-            if (*(volatile int*)cx.flag == -4) break;
-            if (clock64() - t0 > 4000000000LL) { atomicMin(cx.flag, -4); break; }
+            if ((it & 63) == 63) {
+                // a producer that never shows up: raise the error flag once; every later wait sees it and gives up at once
+                if (*(volatile int*)cx.flag == -4) break;
+                if (clock64() - t0 > 4000000000LL) { atomicMin(cx.flag, -4); break; }
+            }
         }
     }
     __syncthreads();
@@ -1700,6 +1713,21 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_fwd_chain(DevCtx cx, const
     const int* __restrict__ boff = cx.chain_boff + d[2];
     const int tid = threadIdx.x, t = tid & (KW - 1), hf = tid >> 7;
     int* flags = cx.chain_flags;
+    // geometry of every link, once (the per-link loop then has no dependent metadata loads on its critical path)
+    __shared__ int lk_s[KW], lk_k[KW], lk_c0[KW];
+    __shared__ int64_t lk_f[KW];
+    __shared__ const double* lk_P[KW];
+    __shared__ const double* lk_inv[KW];
+    for (int j = tid; j < m; j += SOLVE_THREADS) {
+        const int s = links[j];
+        lk_s[j] = s; lk_c0[j] = cx.sn_start[s]; lk_k[j] = cx.sn_start[s + 1] - cx.sn_start[s];
+        lk_f[j] = lk_k[j] + (cx.rows_ptr[s + 1] - cx.rows_ptr[s]);
+        lk_P[j] = cx.lu + cx.Loff[s];
+        lk_inv[j] = cx.dblk + (int64_t)cx.Doff[s] * (NB * NB);
+    }
+    int last_own = -1;
+    for (int i = 0; c + i * G < nblocks; ++i) last_own = c + i * G;
+    __syncthreads();
     // ---- right-hand side on the pivot blocks, zero above the chain
     for (int i = 0; c + i * G < nblocks; ++i) {
         const int b = c + i * G, nb = boff[b + 1] - boff[b];
@@ -1726,21 +1754,21 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_fwd_chain(DevCtx cx, const
     }
     // pivot solve of link j from the block this CTA owns; the solution is left in ys and published
     auto solve = [&](int j, double* ys) {
-        const int s = links[j];
-        const Front F = load_front(cx, s);
-        const double* __restrict__ inv = cx.dblk + (int64_t)cx.Doff[s] * (NB * NB);
+        Front F;
+        F.c0 = lk_c0[j]; F.k = lk_k[j]; F.f = lk_f[j]; F.r = F.f - F.k; F.P = const_cast<double*>(lk_P[j]); F.T = nullptr; F.C = nullptr;
+        const double* __restrict__ inv = lk_inv[j];
         double y[1];
         y[0] = tid < F.k ? vown[j / G][tid] : 0.0;
         __syncthreads();
         diag_solve_lower<1, true>(F, inv, y, ys, tid);
         __syncthreads();
         if (tid < F.k) zout[F.c0 + tid] = ys[tid];
-        chain_publish(flags + s, epoch);
+        chain_publish(flags + lk_s[j], epoch);
     };
     bool ahead = false;                       // y_j already solved (and sitting in ysB) by the look-ahead of step j - 1
-    for (int j = 0; j < m; ++j) {
-        const int s = links[j];
-        const Front F = load_front(cx, s);
+    for (int j = 0; j < m && j <= last_own; ++j) {         // (a CTA whose blocks are all behind the chain's front is done)
+        const int s = lk_s[j];
+        struct { int k, c0; int64_t f; const double* P; } F = {lk_k[j], lk_c0[j], lk_f[j], lk_P[j]};
         if (j % G == c) {
             if (ahead) { if (tid < KW) ysA[tid] = ysB[tid]; __syncthreads(); }
             else solve(j, ysA);
