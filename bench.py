@@ -34,6 +34,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_emit = print
 METRIC = "lu_refactorize_plus_solve_per_sec"
 UNIT = "refactor+solve/s"
 
@@ -296,7 +297,7 @@ def run_reference(args, rank, world):
            "config": {"workload": workload_string(cfg)},
            "cpu_baseline": cb, "setup_s": t_setup, "residual_sample": res,
            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out), flush=True)
+    _emit(json.dumps(out))
 
 
 def run_ours(args, rank, world, local_rank):
@@ -459,17 +460,21 @@ def run_ours(args, rank, world, local_rank):
         kinds[kname] = {"ms": round(ms, 4), "launches": int(launches_kernel.get(kname, 0)),
                         "share": round(ms / step_ms_prof, 4),
                         "GB/s": round(w["bytes"] / (ms * 1e-3) / 1e9, 1),
-                        "frac_hbm": round(w["bytes"] / (ms * 1e-3) / 1e9 / hbm_gbs, 4),
+                        "frac_hbm": round(w["bytes"] / (ms * 1e-3) / 1e9 / hbm_gbs / (1 if jobs == world else world), 4),
                         "TFLOP/s": round(w["flops"] / (ms * 1e-3) / 1e12, 3)}
+    # partitioned run: `work` counts the whole factorization, the kernel time is rank 0's share of it -> the achieved figure
+    # is the aggregate over the GPUs (as if every rank took as long as rank 0) and is held against N times the one-GPU peak
+    ngp = 1 if jobs == world else world
+    agg = "" if ngp == 1 else "; aggregate over %d GPUs against %d x the one-GPU peak (whole-job work / rank 0's kernel time)" % (ngp, ngp)
     if dom == "gemm_cb":   # FP64 contraction: bound by the FP64 pipe (DFMA/DMMA), not bf16 tensor peak
         ach = work[dom]["flops"] / (ms_kernel[dom] * 1e-3) / 1e12
-        roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": ach / fp64_peak, "traffic": None,
-                "peak_source": "FP64 DGEMM (torch.matmul f64 6144^3) measured in this run; MEASURED_PEAKS.json has no FP64 entry"}
+        roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": fp64_peak * ngp, "unit": "TFLOP/s",
+                "frac": ach / (fp64_peak * ngp), "traffic": None,
+                "peak_source": "FP64 DGEMM (torch.matmul f64 6144^3) measured in this run; MEASURED_PEAKS.json has no FP64 entry" + agg}
     else:
         ach = work[dom]["bytes"] / (ms_kernel[dom] * 1e-3) / 1e9
-        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_gbs, "unit": "GB/s",
-                "frac": ach / hbm_gbs, "traffic": None, "peak_source": peak_src}
+        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_gbs * ngp, "unit": "GB/s",
+                "frac": ach / (hbm_gbs * ngp), "traffic": None, "peak_source": peak_src + agg}
     try:   # DRAM traffic of that kernel from the committed ncu --set full capture (mean over the captured launches)
         tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["kernels"].get(dom)
         if tr:
@@ -528,7 +533,7 @@ def run_ours(args, rank, world, local_rank):
         "kernels": kinds, "comm": comm,
         "phases": {"refactor_ms": refac_ms, "solve_ms": solve_ms,
                    "refactor_TFLOPs": st0["flops_exact"] / (refac_ms * 1e-3) / 1e12,
-                   "solve_GBs": solve_bytes / (solve_ms * 1e-3) / 1e9, "solve_frac_hbm": solve_bytes / (solve_ms * 1e-3) / 1e9 / hbm_gbs},
+                   "solve_GBs": solve_bytes / (solve_ms * 1e-3) / 1e9, "solve_frac_hbm": solve_bytes / (solve_ms * 1e-3) / 1e9 / hbm_gbs / ngp},
         "phases_streamed": phases_streamed,
         "residual": residual, "parity": parity, "parity_x_relerr": parity["x_relerr"], "setup_s": t_setup,
         "host_overhead": {"wall_ms_per_step_kernel_leg": wall_dev * 1e3 / K},
@@ -536,7 +541,7 @@ def run_ours(args, rank, world, local_rank):
     if not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(cfg, args.ref_size or ref_edge, nsteps=2)
     F.close()
-    print(json.dumps(out), flush=True)
+    _emit(json.dumps(out))
     if dist:
         dist.destroy_process_group()
 
@@ -556,6 +561,14 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # Only the JSON line may reach stdout: libraries print there too (NCCL's version banner when NCCL_DEBUG is set, build
+    # chatter), so fd 1 is pointed at stderr for the run and the line is written to the real stdout.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global _emit
+    def _emit(line):
+        os.write(real_stdout, (line + "\n").encode())
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:

@@ -319,7 +319,8 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
                             ++np;
                         }
                         if (np == 0 && !zero) continue;
-                        tasks.push_back(make_int4(s, (int)pb0, (int)moff, (zero ? 1 : 0) | (np << 8)));
+                        for (int ch = 0; ch * (int64_t)asm_chunk_rows(f) < f; ++ch)          // one task per row chunk of a tall parent
+                            tasks.push_back(make_int4(s, (int)pb0 | (ch << 20), (int)moff, (zero ? 1 : 0) | (np << 8)));
                     }
                 }
                 push(fac, L_EXTEND, off, (int)std::min<int64_t>(asm_fmax, 1 << 30));
@@ -748,7 +749,8 @@ void build_top_fac(smslu_handle_t h, std::vector<int4>& tasks, std::vector<int64
                         ++np;
                     }
                     if (np > 0 || zero) {
-                        tasks.push_back(make_int4(s, (int)pb0, (int)moff, (zero ? 1 : 0) | ((int)(pb1 - pb0) << 4) | (np << 8)));
+                        for (int ch = 0; ch * (int64_t)asm_chunk_rows(f) < f; ++ch)
+                            tasks.push_back(make_int4(s, (int)pb0 | (ch << 20), (int)moff, (zero ? 1 : 0) | ((int)(pb1 - pb0) << 4) | (np << 8)));
                         asm_fmax = std::max<int64_t>(asm_fmax, f);
                     }
                 }

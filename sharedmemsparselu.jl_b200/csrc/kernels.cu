@@ -175,17 +175,20 @@ __global__ void __launch_bounds__(256) k_assemble(DevCtx cx, const int4* __restr
     }
 }
 
-// Same task format, for parents with at most ASM_SMEM_ROWS rows (every level but the top few): the CTA's
-// destination columns are accumulated in shared memory -- loaded once (zeros for the part of the contribution
-// block that would have been zero-filled), the children added in the same ascending order (so the result is
-// bitwise the same as k_assemble's), written back once.  The per-child work has no dependent global round trip
-// left (k_assemble: rel -> old value -> store, per child, 69 % of its cycles on the long scoreboard) and the
-// parent is read and written once instead of once per child.
-// dynamic shared memory: ASM_COLS * (rows of the largest parent of the launch) doubles.
+// Same task format (y = pb0 | row chunk << 20), the production path: the CTA's destination columns are accumulated in
+// shared memory -- loaded once (zeros for the part of the contribution block that would have been zero-filled), the
+// children added in the same ascending order (so the result is bitwise the same as k_assemble's), written back once.
+// The per-child work has no dependent global round trip left (k_assemble: rel -> old value -> store, per child, 69 % of
+// its cycles on the long scoreboard) and the parent is read and written once instead of once per child.
+// Parents with more than ASM_SMEM_ROWS rows are cut into row chunks of equal size (asm_chunk_rows), one task per
+// (column range, chunk): rel is ascending, so the rows of a child that fall into a chunk are one range, found by two
+// binary searches per child (one thread each, beside the loads of the destination block).
+// dynamic shared memory: ASM_COLS * min(rows of the largest parent of the launch, ASM_SMEM_ROWS) doubles.
 __global__ void __launch_bounds__(256) k_assemble_smem(DevCtx cx, const int4* __restrict__ tasks) {
-    extern __shared__ __align__(16) double cols[];         // cols[c * f + pa]
+    extern __shared__ __align__(16) double cols[];         // cols[c * nr + (pa - ra0)]
+    __shared__ int s_alo[64], s_ahi[64];
     const int4 tk = tasks[blockIdx.x];
-    const int s = tk.x, pb0 = tk.y, nch = tk.w >> 8;
+    const int s = tk.x, pb0 = tk.y & 0xfffff, chunk = (int)((unsigned)tk.y >> 20), nch = tk.w >> 8;
     pdl_trigger();
     const int* __restrict__ meta = cx.asm_meta + tk.z;
     const Front F = load_front(cx, s);
@@ -194,12 +197,14 @@ __global__ void __launch_bounds__(256) k_assemble_smem(DevCtx cx, const int4* __
     const int wdt = (tk.w >> 4) & 15 ? (tk.w >> 4) & 15 : ASM_COLS;
     const int pb1 = pb0 + wdt < f ? pb0 + wdt : f;
     const bool zero = tk.w & 1;
+    const int cr = asm_chunk_rows(f), ra0 = chunk * cr, ra1 = ra0 + cr < f ? ra0 + cr : f, nr = ra1 - ra0;
+    const bool whole = nr == f;
     // address of front entry (pa, pb): P(:, pb) for pb < k; else row pb-k of U12' when pa < k, column pb-k of C
     auto entry = [&](int pa, int pb) -> double* {
         return pb < k ? F.P + pa + (int64_t)pb * F.f
                       : (pa < k ? F.T + (pb - k) + (int64_t)pa * F.r : F.C + (pa - k) + (int64_t)(pb - k) * F.r);
     };
-    const int total = (pb1 - pb0) * f;
+    const int total = (pb1 - pb0) * nr;
     for (int e0 = tid; e0 < total; e0 += 4 * 256) {              // four loads per thread in flight
         double v[4];
 #pragma unroll
@@ -207,40 +212,57 @@ __global__ void __launch_bounds__(256) k_assemble_smem(DevCtx cx, const int4* __
             const int e = e0 + 256 * u;
             v[u] = 0.0;
             if (e < total) {
-                const int c = e / f, pa = e - c * f, pb = pb0 + c;
+                const int c = e / nr, pa = ra0 + e - c * nr, pb = pb0 + c;
                 if (!(zero && pb >= k && pa >= k)) v[u] = *entry(pa, pb);
             }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) if (e0 + 256 * u < total) cols[e0 + 256 * u] = v[u];
     }
-    __syncthreads();
-    for (int q = 0; q < nch; ++q) {
-        const int c = meta[2 * q], lo = meta[2 * q + 1];
-        const int rc = (int)(cx.rows_ptr[c + 1] - cx.rows_ptr[c]);
-        const int* __restrict__ rel = cx.rel + cx.rows_ptr[c];
-        const double* __restrict__ Cc = cx.cb + cx.CBoff[c];
-        for (int b = lo + warp; b < rc; b += 8) {
-            const int pb = rel[b];
-            if (pb >= pb1) break;
-            const double* __restrict__ src = Cc + (int64_t)b * rc;
-            double* col = cols + (pb - pb0) * f;
-            for (int a0 = lane; a0 < rc; a0 += 256) {           // eight entries per lane in flight
-                int pa[8]; double v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int a = a0 + 32 * u;
-                    pa[u] = a < rc ? rel[a] : -1;
-                    v[u] = a < rc ? src[a] : 0.0;
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) if (pa[u] >= 0) col[pa[u]] += v[u];
+    for (int q0 = 0; q0 < nch; q0 += 64) {
+        if (!whole && tid < 128) {                               // rows [alo, ahi) of child q fall into [ra0, ra1)
+            const int q = q0 + (tid & 63);
+            if (q < nch) {
+                const int c = meta[2 * q];
+                const int rc = (int)(cx.rows_ptr[c + 1] - cx.rows_ptr[c]);
+                const int* __restrict__ rel = cx.rel + cx.rows_ptr[c];
+                const int key = tid < 64 ? ra0 : ra1;
+                int lo = 0, hi = rc;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (rel[mid] < key) lo = mid + 1; else hi = mid; }
+                (tid < 64 ? s_alo : s_ahi)[tid & 63] = lo;
             }
         }
         __syncthreads();
+        const int q1 = q0 + 64 < nch ? q0 + 64 : nch;
+        for (int q = q0; q < q1; ++q) {
+            const int c = meta[2 * q], lo = meta[2 * q + 1];
+            const int rc = (int)(cx.rows_ptr[c + 1] - cx.rows_ptr[c]);
+            const int* __restrict__ rel = cx.rel + cx.rows_ptr[c];
+            const double* __restrict__ Cc = cx.cb + cx.CBoff[c];
+            const int alo = whole ? 0 : s_alo[q - q0], ahi = whole ? rc : s_ahi[q - q0];
+            for (int b = lo + warp; b < rc; b += 8) {
+                const int pb = rel[b];
+                if (pb >= pb1) break;
+                const double* __restrict__ src = Cc + (int64_t)b * rc;
+                double* col = cols + (pb - pb0) * nr - ra0;
+                for (int a0 = alo + lane; a0 < ahi; a0 += 256) {           // eight entries per lane in flight
+                    int pa[8]; double v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int a = a0 + 32 * u;
+                        pa[u] = a < ahi ? rel[a] : -1;
+                        v[u] = a < ahi ? src[a] : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) if (pa[u] >= 0) col[pa[u]] += v[u];
+                }
+            }
+            __syncthreads();
+        }
     }
+    if (nch == 0) __syncthreads();
     for (int e = tid; e < total; e += 256) {
-        const int c = e / f, pa = e - c * f;
+        const int c = e / nr, pa = ra0 + e - c * nr;
         *entry(pa, pb0 + c) = cols[e];
     }
 }
@@ -545,8 +567,11 @@ __device__ __forceinline__ void cp_async8(double* dst_smem, const double* src, b
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+#ifndef PANEL_MINB
+#define PANEL_MINB 2          // CTAs per SM of the streaming (128-row) variant: <= 128 registers
+#endif
 template <int ROWS>
-__global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* __restrict__ tasks) {
+__global__ void __launch_bounds__(PANEL_THREADS, PANEL_MINB) k_panel(DevCtx cx, const int4* __restrict__ tasks) {
     extern __shared__ __align__(16) double dsm[];
     // DW[0] = W: W[p][c] = U[p][c], the factored block as the kind-0 tiles read it.
     // DW[1] = D: the raw diagonal block D[i][c]; once warp 0 holds it in registers, D[p][c] = L[c][p] for kinds 1, 2.
@@ -572,17 +597,37 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
     int kind, tile;
     int64_t stride;
     const double* cf;
-    auto set_tile = [&](int t) {
-        if (mode == 1) { kind = t < nt0 ? 0 : 2; tile = kind == 0 ? t : t - nt0; }
-        else if (mode == 2) { kind = 1; tile = t; }
+    auto tile_of = [&](int t, int& kd, int& tl) {
+        if (mode == 1) { kd = t < nt0 ? 0 : 2; tl = kd == 0 ? t : t - nt0; }
+        else if (mode == 2) { kd = 1; tl = t; }
         else {
-            kind = t < nt0 ? 0 : (t < nt0 + nt1 ? 1 : 2);
-            if (nt0 + nt1 + (k - j1 + ROWS - 1) / ROWS == 0) kind = 0;      // the lone CTA that only factors D_gg
-            tile = kind == 0 ? t : (kind == 1 ? t - nt0 : t - nt0 - nt1);
+            kd = t < nt0 ? 0 : (t < nt0 + nt1 ? 1 : 2);
+            if (nt0 + nt1 + (k - j1 + ROWS - 1) / ROWS == 0) kd = 0;        // the lone CTA that only factors D_gg
+            tl = kd == 0 ? t : (kd == 1 ? t - nt0 : t - nt0 - nt1);
         }
+    };
+    auto set_tile = [&](int t) {
+        tile_of(t, kind, tile);
         stride = kind == 0 ? F.f : (kind == 1 ? F.r : 1);
     };
+    // pull the rows of tile t (columns [0, j1) of the row strip: ROWS * 8 bytes = 8 or 9 lines per column) towards L2
+    // while the CTA works on the tile before it
+    auto prefetch_tile = [&](int t) {
+        if (ROWS == PANEL_ROWS_TOP || t >= (int)tk.z + ngroup) return;
+        int kd, tl;
+        tile_of(t, kd, tl);
+        if (kd == 2) return;
+        const int64_t r0 = (int64_t)tl * ROWS, ld = kd == 0 ? F.f : F.r;
+        const int64_t nrows = (kd == 0 ? F.f - j1 : F.r) - r0;
+        const double* __restrict__ base = (kd == 0 ? F.P + j1 : F.T) + r0;
+        for (int l = threadIdx.x; l < j1 * 9; l += PANEL_THREADS) {
+            const int col = l / 9;
+            const int64_t ro = (l - col * 9) * 16;
+            if (ro < nrows && ro < ROWS + 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (int64_t)col * ld + ro));
+        }
+    };
     set_tile(tk.z);
+    prefetch_tile((int)tk.z + 1);
     TRACEP(1);
     double* Uc = dsm;                               // Uc[m * CLD + c] = U[m, j0 + c],  m < j0
     double* Lc = dsm + j0 * CLD;                    // Lc[m * CLD + i] = L[j0 + i, m],  m < j0
@@ -628,7 +673,7 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
     // The diagonal block goes first (one piece per warp); then warp 0 factors it (phase L) WHILE the other seven
     // warps update the row block, which does not depend on the factorization.
     cf = kind == 0 ? Uc : Lc;
-    constexpr int NW = PANEL_THREADS / 32, ROW_PIECES = (ROWS / 8) * 2;
+    constexpr int NW = PANEL_THREADS / 32, ROW_PIECES = STAGE_ROWS ? (ROWS / 8) * 2 : ROWS / 8;   // 8 x 16 (staged) or 8 x 32 pieces
     auto row_piece = [&](int st, int ch) {
         double acc[2][2];
         if (STAGE_ROWS) {
@@ -647,27 +692,46 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
                 dmma884(acc[1][0], acc[1][1], a, cm[8]);
             }
         } else {
+        // Streaming variant: one piece = 8 rows x all 32 columns (four DMMA tiles share every A fragment).  The A
+        // fragments come straight from global memory in batches of eight k-steps (32 columns of the row strip), the
+        // next batch requested before the current one is consumed: 8-16 loads in flight per lane instead of 2.
         double* fb; bool fa;
         row_ptr((int64_t)tile * ROWS + st * 8 + fr, fb, fa);
+        double ac[4][2];
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
+        for (int j = 0; j < 4; ++j)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int c = ch + 8 * j + 2 * fc + e;
-                acc[j][e] = (fa && c < w) ? fb[(int64_t)(j0 + c) * stride] : 0.0;
+                const int c = 8 * j + 2 * fc + e;
+                ac[j][e] = (fa && c < w) ? fb[(int64_t)(j0 + c) * stride] : 0.0;
             }
         if (j0 > 0) {
-            double an = fa ? -fb[(int64_t)fc * stride] : 0.0;
-            double an2 = (fa && j0 > 4) ? -fb[(int64_t)(4 + fc) * stride] : 0.0;
-            for (int m0 = 0; m0 < j0; m0 += 4) {
-                const double a = an;
-                an = an2;
-                if (m0 + 8 < j0) an2 = fa ? -fb[(int64_t)(m0 + 8 + fc) * stride] : 0.0;
-                const double* __restrict__ cm = cf + (m0 + fc) * CLD + ch + fr;
-                dmma884(acc[0][0], acc[0][1], a, cm[0]);
-                dmma884(acc[1][0], acc[1][1], a, cm[8]);
+            double av[8], aw[8];
+            const double* __restrict__ fp = fb + (int64_t)fc * stride;
+            const int64_t st4 = 4 * stride;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) av[u] = fa ? fp[u * st4] : 0.0;
+            for (int mb = 0; mb < j0; mb += NB) {
+                fp += 8 * st4;
+                if (mb + NB < j0) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) aw[u] = fa ? fp[u * st4] : 0.0;
+                }
+                const double* __restrict__ cm = cf + (mb + fc) * CLD + fr;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const double a = -av[u];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma884(ac[j][0], ac[j][1], a, cm[u * 4 * CLD + 8 * j]);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) av[u] = aw[u];
             }
         }
+        double* xs = Xs + (st * 8 + fr) * CLD + 2 * fc;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<double2*>(xs + 8 * j) = make_double2(ac[j][0], ac[j][1]);
+        return;
         }
         double* xs = Xs + (st * 8 + fr) * CLD + ch + 2 * fc;
 #pragma unroll
@@ -738,7 +802,7 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
             for (int c2 = 0; c2 < NB / 2; ++c2) *reinterpret_cast<double2*>(&W[lane][2 * c2]) = make_double2(x[2 * c2], x[2 * c2 + 1]);
         }
     } else {
-        for (int pc = warp - 1; pc < ROW_PIECES; pc += NW - 1) row_piece(pc >> 1, (pc & 1) * 16);
+        for (int pc = warp - 1; pc < ROW_PIECES; pc += NW - 1) row_piece(STAGE_ROWS ? pc >> 1 : pc, STAGE_ROWS ? (pc & 1) * 16 : 0);
     }
     TRACEP(4);
     __syncthreads();
@@ -799,8 +863,9 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
         if (STAGE_ROWS || ++t >= (int)tk.z + ngroup) break;    // the latency variant has one tile per CTA
         __syncthreads();                           // phase T has consumed Xs
         set_tile(t);
+        prefetch_tile(t + 1);
         cf = kind == 0 ? Uc : Lc;
-        for (int pc = warp; pc < ROW_PIECES; pc += NW) row_piece(pc >> 1, (pc & 1) * 16);
+        for (int pc = warp; pc < ROW_PIECES; pc += NW) row_piece(pc, 0);      // (only the streaming variant has groups)
         __syncthreads();
     }
 }
@@ -818,15 +883,28 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(DevCtx cx, const int4* 
 constexpr int GEMM_LDS = GEMM_TILE + 4;   // row stride = 4 (mod 16) doubles: fragment loads are conflict-free
 
 #ifndef GEMM_MINB
-#define GEMM_MINB 2
+#define GEMM_MINB 4             // CTAs per SM (<= 64 registers): measured 2 -> 944 ms, 3 -> 886 ms, 4 (16-column chunks) -> 822 ms of Schur updates at 128^3
+#endif
+#ifndef GEMM_KC
+#define GEMM_KC 16              // pivot columns per staged operand chunk of k_gemm_cb (2 stages = 34 KB per CTA: four CTAs per SM)
+#endif
+constexpr int GKC = GEMM_KC;
+#ifndef GEMM_STAGES
+#define GEMM_STAGES 2           // cp.async stages of the operand chunks (3: one barrier per chunk instead of two)
 #endif
 #ifndef GEMM_AHEAD
-#define GEMM_AHEAD 296          // tiles ahead whose contribution-block tile is pulled into L2 (0 = off): two waves of CTAs
+#define GEMM_AHEAD 592          // tiles ahead whose contribution-block tile is pulled into L2 (0 = off): one wave of CTAs (4 per SM)
 #endif
 __global__ void __launch_bounds__(256, GEMM_MINB) k_gemm_cb(DevCtx cx, const int4* __restrict__ tasks, int ntasks) {
-    extern __shared__ __align__(16) double gsm[];         // 2 stages x (As[NB][GEMM_LDS] | Bs[NB][GEMM_LDS])
+    extern __shared__ __align__(16) double gsm[];         // 2 stages x (As[GKC][GEMM_LDS] | Bs[GKC][GEMM_LDS])
     pdl_trigger();
     int4 tk = tasks[blockIdx.x];
+#if GEMM_AHEAD > 0
+    // the task two waves ahead (its C tile is pulled towards L2 below): requested together with this CTA's own task, so the
+    // round trip is not on the tile's critical path
+    int4 t2 = make_int4(-1, 0, 0, 0);
+    if ((int)blockIdx.x + GEMM_AHEAD < ntasks) t2 = tasks[blockIdx.x + GEMM_AHEAD];
+#endif
     const Front F = load_front(cx, tk.x);
     pdl_wait();
     const int k = F.k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -864,19 +942,19 @@ __global__ void __launch_bounds__(256, GEMM_MINB) k_gemm_cb(DevCtx cx, const int
     const double* __restrict__ Bth = B + (okb ? n0 + sa : 0) + (int64_t)sp0 * F.r;
     const int64_t astep = 4 * F.f, bstep = 4 * F.r;
     auto stage = [&](int kc, int buf) {
-        double* as = gsm + buf * (2 * NB * GEMM_LDS) + sp0 * GEMM_LDS + sa;
-        double* bs = as + NB * GEMM_LDS;
+        double* as = gsm + buf * (2 * GKC * GEMM_LDS) + sp0 * GEMM_LDS + sa;
+        double* bs = as + GKC * GEMM_LDS;
         const double* __restrict__ ap = Ath + (int64_t)kc * F.f;
         const double* __restrict__ bp = Bth + (int64_t)kc * F.r;
-        if (kc + NB <= k) {
+        if (kc + GKC <= k) {
 #pragma unroll
-            for (int u = 0; u < NB / 4; ++u, ap += astep, bp += bstep) {
+            for (int u = 0; u < GKC / 4; ++u, ap += astep, bp += bstep) {
                 cp_async8(as + u * 4 * GEMM_LDS, ap, oka);
                 cp_async8(bs + u * 4 * GEMM_LDS, bp, okb);
             }
         } else {
 #pragma unroll
-            for (int u = 0; u < NB / 4; ++u, ap += astep, bp += bstep) {
+            for (int u = 0; u < GKC / 4; ++u, ap += astep, bp += bstep) {
                 const bool in = kc + sp0 + 4 * u < k;
                 cp_async8(as + u * 4 * GEMM_LDS, in ? ap : A, in && oka);
                 cp_async8(bs + u * 4 * GEMM_LDS, in ? bp : B, in && okb);
@@ -884,20 +962,9 @@ __global__ void __launch_bounds__(256, GEMM_MINB) k_gemm_cb(DevCtx cx, const int
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    stage(0, 0);
-#if GEMM_AHEAD > 0
-    // The tile that will run on this SM about two CTA generations from now reads its 64 x 64 piece of C from HBM
-    // (the trailing matrix is far larger than L2): pull it towards L2 now, so that its prologue sees an L2 hit.
-    // One 128-byte line per thread (64 columns x 4 lines); only when that tile belongs to the same front.
-    if (beta && (int)blockIdx.x + GEMM_AHEAD < ntasks) {
-        const int4 t2 = tasks[blockIdx.x + GEMM_AHEAD];
-        if (t2.x == tk.x) {
-            const int64_t pm = (int64_t)t2.y * GEMM_TILE + (tid & 3) * 16, pn = ((t2.w & 64) ? (int64_t)t2.z : (int64_t)t2.z * GEMM_TILE) + (tid >> 2);
-            if (pm < F.r && pn < F.r) asm volatile("prefetch.global.L2 [%0];" ::"l"(F.C + pm + pn * F.r));
-        }
-    }
-#endif
     double acc[4][2][2];
+#ifdef GEMM_C_FIRST
+    // the C tile comes from HBM, the operand chunks from L2: request C first
     // the C loads are in flight while the operand tiles arrive
     if (beta && full) {
         const double* __restrict__ c0 = F.C + (m0 + wm + fr) + (n0 + wn + 2 * fc) * F.r;
@@ -921,18 +988,79 @@ __global__ void __launch_bounds__(256, GEMM_MINB) k_gemm_cb(DevCtx cx, const int
                     acc[i][j][e] = (beta && row < F.r && col < ncend && (!mine_only || rown[col] == cx.rank)) ? F.C[row + col * F.r] : 0.0;
                 }
     }
+    stage(0, 0);
+#if GEMM_AHEAD > 0
+    // The tile that will run on this SM about two CTA generations from now reads its 64 x 64 piece of C from HBM
+    // (the trailing matrix is far larger than L2): pull it towards L2 now, so that its prologue sees an L2 hit.
+    // One 128-byte line per thread (64 columns x 4 lines); only when that tile belongs to the same front.
+    if (beta) {
+        if (t2.x == tk.x) {
+            const int64_t pm = (int64_t)t2.y * GEMM_TILE + (tid & 3) * 16, pn = ((t2.w & 64) ? (int64_t)t2.z : (int64_t)t2.z * GEMM_TILE) + (tid >> 2);
+            if (pm < F.r && pn < F.r) asm volatile("prefetch.global.L2 [%0];" ::"l"(F.C + pm + pn * F.r));
+        }
+    }
+#endif
+#else
+    stage(0, 0);
+#if GEMM_AHEAD > 0
+    // The tile that will run on this SM about two CTA generations from now reads its 64 x 64 piece of C from HBM
+    // (the trailing matrix is far larger than L2): pull it towards L2 now, so that its prologue sees an L2 hit.
+    // One 128-byte line per thread (64 columns x 4 lines); only when that tile belongs to the same front.
+    if (beta) {
+        if (t2.x == tk.x) {
+            const int64_t pm = (int64_t)t2.y * GEMM_TILE + (tid & 3) * 16, pn = ((t2.w & 64) ? (int64_t)t2.z : (int64_t)t2.z * GEMM_TILE) + (tid >> 2);
+            if (pm < F.r && pn < F.r) asm volatile("prefetch.global.L2 [%0];" ::"l"(F.C + pm + pn * F.r));
+        }
+    }
+#endif
+    // the C loads are in flight while the operand tiles arrive
+    if (beta && full) {
+        const double* __restrict__ c0 = F.C + (m0 + wm + fr) + (n0 + wn + 2 * fc) * F.r;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const double* __restrict__ cc = c0 + (8 * j + e) * F.r;
+                const bool on = !mine_only || rown[n0 + wn + 8 * j + 2 * fc + e] == cx.rank;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[i][j][e] = on ? cc[8 * i] : 0.0;
+            }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int64_t row = m0 + wm + 8 * i + fr, col = n0 + wn + 8 * j + 2 * fc + e;
+                    acc[i][j][e] = (beta && row < F.r && col < ncend && (!mine_only || rown[col] == cx.rank)) ? F.C[row + col * F.r] : 0.0;
+                }
+    }
+#endif
     int buf = 0;
-    for (int kc = 0; kc < k; kc += NB, buf ^= 1) {
-        if (kc + NB < k) {
-            stage(kc + NB, buf ^ 1);                     // next chunk into the other stage
+#if GEMM_STAGES == 3
+    // three stages, one barrier per chunk: chunk kc + 2 GKC is requested right after the barrier that also tells every
+    // warp is done with chunk kc - GKC (whose stage it overwrites), so a chunk has two chunks of MMA time to arrive
+    if (GKC < k) stage(GKC, 1);
+    for (int kc = 0; kc < k; kc += GKC, buf = buf == 2 ? 0 : buf + 1) {
+        if (kc + GKC < k) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        if (kc + 2 * GKC < k) stage(kc + 2 * GKC, buf == 0 ? 2 : buf - 1);
+        const double* As = gsm + buf * (2 * GKC * GEMM_LDS);
+#else
+    for (int kc = 0; kc < k; kc += GKC, buf ^= 1) {
+        if (kc + GKC < k) {
+            stage(kc + GKC, buf ^ 1);                     // next chunk into the other stage
             asm volatile("cp.async.wait_group 1;" ::: "memory");
         } else {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
-        const double* As = gsm + buf * (2 * NB * GEMM_LDS);
-        const double* Bs = As + NB * GEMM_LDS;
-        const int kw = (k - kc < NB) ? k - kc : NB;
+        const double* As = gsm + buf * (2 * GKC * GEMM_LDS);
+#endif
+        const double* Bs = As + GKC * GEMM_LDS;
+        const int kw = (k - kc < GKC) ? k - kc : GKC;
         const int ksteps = (kw + 3) >> 2;
         for (int ks = 0; ks < ksteps; ++ks) {
             const int p = 4 * ks + fc;
@@ -946,7 +1074,9 @@ __global__ void __launch_bounds__(256, GEMM_MINB) k_gemm_cb(DevCtx cx, const int
 #pragma unroll
                 for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
+#if GEMM_STAGES != 3
         __syncthreads();                                 // the stage is refilled two iterations from now
+#endif
     }
     if (!direct) {
         const int64_t coff = F.C - cx.cb;
@@ -2164,7 +2294,7 @@ int debug_read_trace(long long* out) {
 
 constexpr int SMALL_FPC32 = 4;     // fronts per CTA in the one-warp class of k_small_factor
 
-static size_t gemm_smem() { return sizeof(double) * 2 * 2 * NB * GEMM_LDS; }
+static size_t gemm_smem() { return sizeof(double) * GEMM_STAGES * 2 * GKC * GEMM_LDS; }
 static size_t gemm_strip_smem() { return sizeof(double) * (KW + 2 * NB) * GEMM_LDS; }
 static size_t panel_smem(int j0, int rows) {
     return sizeof(double) * ((2 * (size_t)j0 + rows) * CLD + (rows == PANEL_ROWS_TOP ? (size_t)rows * (KW + 4) : 0));
@@ -2220,8 +2350,8 @@ void launch_zero_cb(cudaStream_t st, const DevCtx& cx, const int4* tasks, int nt
 }
 void launch_assemble(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int fmax) {
     if (ntasks <= 0) return;
-    if (fmax > 0 && fmax <= ASM_SMEM_ROWS) launch_pdl(k_assemble_smem, ntasks, 256, sizeof(double) * ASM_COLS * fmax, st, cx, tasks);
-    else launch_pdl(k_assemble, ntasks, 256, 0, st, cx, tasks);
+    if (fmax > 0) launch_pdl(k_assemble_smem, ntasks, 256, sizeof(double) * ASM_COLS * (fmax < ASM_SMEM_ROWS ? fmax : ASM_SMEM_ROWS), st, cx, tasks);
+    else launch_pdl(k_assemble, ntasks, 256, 0, st, cx, tasks);       // (never: every assembly launch knows its largest parent)
 }
 template <int RW, int CH, int FPC>
 static void launch_small_class(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int fmax,

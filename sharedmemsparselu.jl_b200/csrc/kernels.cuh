@@ -35,7 +35,16 @@ constexpr int MAX_RANKS = 8;      // GPUs of one NVSwitch box
 constexpr int CHAIN_MAXOWN = 8;   // blocks (forward) / links (backward) of a chain one CTA of the persistent solve kernels may own
 constexpr int CHAIN_DESC = 8;     // ints per chain descriptor: links_off, m, boff_off, nblocks, cta0, nctas, part_off (in KW-vectors), tiles above
 constexpr int CHAIN_CTAS = 148;   // one CTA per SM, all co-resident (cooperative launch)
-constexpr int ASM_SMEM_ROWS = 1536; // parents up to this many rows are assembled through shared memory (96 KB per CTA at most)
+#ifndef SMSLU_ASM_ROWS
+#define SMSLU_ASM_ROWS 512
+#endif
+constexpr int ASM_SMEM_ROWS = SMSLU_ASM_ROWS; // rows of a parent front one assembly CTA holds in shared memory (96 KB per CTA at most; a multiple of 16)
+// rows per chunk / chunks of a parent with f rows (taller parents are cut into equal row chunks, one assembly task each)
+__host__ __device__ inline int asm_chunks(int64_t f) { return (int)((f + ASM_SMEM_ROWS - 1) / ASM_SMEM_ROWS); }
+__host__ __device__ inline int asm_chunk_rows(int64_t f) {
+    const int nc = asm_chunks(f);
+    return nc <= 1 ? (int)f : (int)((((f + nc - 1) / nc) + 15) & ~(int64_t)15);
+}
 
 struct DevCtx {
     const int* sn_start;
