@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 evidence, call A (ONE GPU): tests, smoke, bench lines, launch list, ncu --set full captures (summarised on the box).
-T=round2
+T=${1:-round2b}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,memory.total --format=csv,noheader
 ( timeout 1200 python -m pytest tests -m gpu -x -q --durations=8 > gpurun_out/${T}_pytest_gpu.log 2>&1; echo "pytest rc=$?" ); tail -12 gpurun_out/${T}_pytest_gpu.log
@@ -11,10 +11,10 @@ nvidia-smi --query-gpu=name,clocks.max.sm,memory.total --format=csv,noheader
 python scripts/launch_list.py gpurun_out/${T}_launches_one_step_128.csv totals > gpurun_out/${T}_launch_totals.txt 2>&1; cat gpurun_out/${T}_launch_totals.txt
 : > gpurun_out/${T}_ncu_stalls.txt
 i=0
-for spec in "k_gemm:2:332" "k_fwd<:2:20" "k_bwd<:2:20" "k_assemble:1:119" "k_panel:2:1500" "k_small_factor:1:20"; do
+for spec in "k_gemm_cb:2:332" "k_fwd:2:450" "k_bwd:2:450" "k_assemble_smem:2:120" "k_panel:2:1500" "k_small_factor_reg:1:20"; do
   IFS=: read KRE CNT SKIP <<< "$spec"
-  NAME=$(echo $KRE | tr -d '<')
-  timeout 400 ncu --set full --clock-control none --import-source on -k regex:$KRE -s $SKIP -c $CNT -o gpurun_out/${T}_prof_$i -f python scripts/one_step.py lap3d 128 > gpurun_out/${T}_ncu_full_$i.log 2>&1
+  NAME=$KRE
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:^$KRE\$ -s $SKIP -c $CNT -o gpurun_out/${T}_prof_$i -f python scripts/one_step.py lap3d 128 > gpurun_out/${T}_ncu_full_$i.log 2>&1
   echo "capture $i ($KRE) rc=$?"
   python scripts/ncu_summary.py gpurun_out/${T}_prof_$i.ncu-rep gpurun_out/${T}_ncu_full_${NAME}_$i.csv
   python scripts/ncu_stalls.py gpurun_out/${T}_prof_$i.ncu-rep >> gpurun_out/${T}_ncu_stalls.txt

@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256) k_assemble(DevCtx cx, const int4* __restr
 // (column range, chunk): rel is ascending, so the rows of a child that fall into a chunk are one range, found by two
 // binary searches per child (one thread each, beside the loads of the destination block).
 // dynamic shared memory: ASM_COLS * min(rows of the largest parent of the launch, ASM_SMEM_ROWS) doubles.
-__global__ void __launch_bounds__(256) k_assemble_smem(DevCtx cx, const int4* __restrict__ tasks) {
+__global__ void __launch_bounds__(256, 5) k_assemble_smem(DevCtx cx, const int4* __restrict__ tasks) {
     extern __shared__ __align__(16) double cols[];         // cols[c * nr + (pa - ra0)]
     __shared__ int s_alo[64], s_ahi[64];
     const int4 tk = tasks[blockIdx.x];
@@ -199,25 +199,21 @@ __global__ void __launch_bounds__(256) k_assemble_smem(DevCtx cx, const int4* __
     const bool zero = tk.w & 1;
     const int cr = asm_chunk_rows(f), ra0 = chunk * cr, ra1 = ra0 + cr < f ? ra0 + cr : f, nr = ra1 - ra0;
     const bool whole = nr == f;
-    // address of front entry (pa, pb): P(:, pb) for pb < k; else row pb-k of U12' when pa < k, column pb-k of C
-    auto entry = [&](int pa, int pb) -> double* {
-        return pb < k ? F.P + pa + (int64_t)pb * F.f
-                      : (pa < k ? F.T + (pb - k) + (int64_t)pa * F.r : F.C + (pa - k) + (int64_t)(pb - k) * F.r);
-    };
-    const int total = (pb1 - pb0) * nr;
-    for (int e0 = tid; e0 < total; e0 += 4 * 256) {              // four loads per thread in flight
-        double v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int e = e0 + 256 * u;
-            v[u] = 0.0;
-            if (e < total) {
-                const int c = e / nr, pa = ra0 + e - c * nr, pb = pb0 + c;
-                if (!(zero && pb >= k && pa >= k)) v[u] = *entry(pa, pb);
-            }
+    // destination block -> shared memory, column by column (no index division): column pb of the front is one contiguous
+    // run of P (pb < k), or k strided entries of U12' followed by a contiguous run of the contribution block
+    const int ncol = pb1 - pb0;
+    for (int c = 0; c < ncol; ++c) {
+        const int pb = pb0 + c;
+        double* __restrict__ dst = cols + c * nr - ra0;
+        if (pb < k) {
+            const double* __restrict__ src = F.P + (int64_t)pb * F.f;
+            for (int pa = ra0 + tid; pa < ra1; pa += 256) dst[pa] = src[pa];
+        } else {
+            const double* __restrict__ srcT = F.T + (pb - k);
+            const double* __restrict__ srcC = F.C + (int64_t)(pb - k) * F.r - k;
+            for (int pa = ra0 + tid; pa < ra1; pa += 256)
+                dst[pa] = pa < k ? srcT[(int64_t)pa * F.r] : (zero ? 0.0 : srcC[pa]);
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) if (e0 + 256 * u < total) cols[e0 + 256 * u] = v[u];
     }
     for (int q0 = 0; q0 < nch; q0 += 64) {
         if (!whole && tid < 128) {                               // rows [alo, ahi) of child q fall into [ra0, ra1)
@@ -261,9 +257,20 @@ __global__ void __launch_bounds__(256) k_assemble_smem(DevCtx cx, const int4* __
         }
     }
     if (nch == 0) __syncthreads();
-    for (int e = tid; e < total; e += 256) {
-        const int c = e / nr, pa = ra0 + e - c * nr;
-        *entry(pa, pb0 + c) = cols[e];
+    for (int c = 0; c < ncol; ++c) {
+        const int pb = pb0 + c;
+        const double* __restrict__ src = cols + c * nr - ra0;
+        if (pb < k) {
+            double* __restrict__ dst = F.P + (int64_t)pb * F.f;
+            for (int pa = ra0 + tid; pa < ra1; pa += 256) dst[pa] = src[pa];
+        } else {
+            double* __restrict__ dstT = F.T + (pb - k);
+            double* __restrict__ dstC = F.C + (int64_t)(pb - k) * F.r - k;
+            for (int pa = ra0 + tid; pa < ra1; pa += 256) {
+                if (pa < k) dstT[(int64_t)pa * F.r] = src[pa];
+                else dstC[pa] = src[pa];
+            }
+        }
     }
 }
 
