@@ -70,6 +70,7 @@ enum LaunchKind { L_ZERO = SMSLU_K_ZERO, L_EXTEND = SMSLU_K_EXTEND, L_SMALL = SM
 constexpr int NLANES = 4;
 constexpr int GEMM_STRIP_DEFAULT = 1;
 constexpr bool CHAINS_DEFAULT = false;
+constexpr int CHAIN_MAXC_DEFAULT = 32;
 
 constexpr int PANEL_GROUP_CTAS = 296;  // panel launches aim at about this many CTAs (2 per SM) ...
 constexpr int PANEL_GROUP_MAX = 16;    // ... by giving one CTA up to this many 128-row tiles of its front
@@ -462,6 +463,8 @@ void build_chain_schedules(smslu_handle_t h, std::vector<int4>& tasks, const std
     // default off until validated on the GPU in this round: SMSLU_CHAINS=1 switches the persistent chain kernels on
     const bool enabled = CHAINS_DEFAULT ? !(getenv("SMSLU_NO_CHAINS") && atoi(getenv("SMSLU_NO_CHAINS")) != 0)
                                         : (getenv("SMSLU_CHAINS") && atoi(getenv("SMSLU_CHAINS")) != 0);
+    // only sets of at most this many parallel chains (1 = the separators that stand alone on their levels: the top of the tree)
+    const int max_chains = getenv("SMSLU_CHAIN_MAXC") ? std::max(1, std::min(32, atoi(getenv("SMSLU_CHAIN_MAXC")))) : CHAIN_MAXC_DEFAULT;
     for (int ph = 0; ph < 2; ++ph) {
         const std::vector<Launch>& fwd = ph == 0 ? h->fwd : h->fwd_top;
         const std::vector<Launch>& bwd = ph == 0 ? h->bwd : h->bwd_top;
@@ -495,7 +498,7 @@ void build_chain_schedules(smslu_handle_t h, std::vector<int4>& tasks, const std
                 if (!ok) break;
                 ++l1;
             }
-            if (l1 - l + 1 >= 4 && l1 - l + 1 <= KW && C[l].size() <= 32) {        // (the kernels keep per-link geometry of <= KW links in shared memory)
+            if (l1 - l + 1 >= 4 && l1 - l + 1 <= KW && (int)C[l].size() <= max_chains) {        // (the kernels keep per-link geometry of <= KW links in shared memory)
                 ChainSet cs; cs.l0 = l; cs.l1 = l1;
                 for (int top : C[l1]) {                    // follow every chain down from its top link
                     std::vector<int> ch(1, top);

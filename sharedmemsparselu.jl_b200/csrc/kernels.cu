@@ -184,7 +184,10 @@ __global__ void __launch_bounds__(256) k_assemble(DevCtx cx, const int4* __restr
 // (column range, chunk): rel is ascending, so the rows of a child that fall into a chunk are one range, found by two
 // binary searches per child (one thread each, beside the loads of the destination block).
 // dynamic shared memory: ASM_COLS * min(rows of the largest parent of the launch, ASM_SMEM_ROWS) doubles.
-__global__ void __launch_bounds__(256, 5) k_assemble_smem(DevCtx cx, const int4* __restrict__ tasks) {
+#ifndef ASM_MINB
+#define ASM_MINB 5
+#endif
+__global__ void __launch_bounds__(256, ASM_MINB) k_assemble_smem(DevCtx cx, const int4* __restrict__ tasks) {
     extern __shared__ __align__(16) double cols[];         // cols[c * nr + (pa - ra0)]
     __shared__ int s_alo[64], s_ahi[64];
     const int4 tk = tasks[blockIdx.x];
