@@ -65,7 +65,9 @@ enum LaunchKind { L_ZERO = SMSLU_K_ZERO, L_EXTEND = SMSLU_K_EXTEND, L_SMALL = SM
                   // partitioned top (timed as SMSLU_K_ALLREDUCE = "exchange"): publish panels to the peers, signal, wait
                   L_REPL = 100, L_SIGNAL = 101, L_WAIT = 102,
                   // persistent chain solves (single right-hand side)
-                  L_FWD_CHAIN = 103, L_BWD_RECT = 104, L_BWD_CHAIN = 105 };
+                  L_FWD_CHAIN = 103, L_BWD_RECT = 104, L_BWD_CHAIN = 105,
+                  // 32 right-hand sides per sweep on the FP64 tensor pipe (big fronts)
+                  L_FWD32 = 106, L_BWD32 = 107 };
 
 constexpr int NLANES = 4;
 constexpr int GEMM_STRIP_DEFAULT = 1;
@@ -128,6 +130,13 @@ struct smslu_handle_s {
     std::vector<Launch> fac_top, fwd_top, bwd_top;   // top of the tree, replicated on every rank
     // single right-hand side: the same sweeps with every set of parallel chains of fronts in one persistent kernel
     std::vector<Launch> fwd1, bwd1, fwd_top1, bwd_top1;
+    // 32-wide sweeps (one GPU): the small fronts' launches of fwd / bwd + k_fwd32 / k_bwd32 for every big front;
+    // their work vectors are allocated by the first solve with that many right-hand sides (ensure_wide)
+    std::vector<Launch> fwd32, bwd32;
+    int64_t bpart32_slots = 0;
+    double *d_w32 = nullptr, *d_z32 = nullptr, *d_xb32 = nullptr;
+    bool have_wide = false, wide_failed = false;
+    DevCtx cx32{};
     int* d_chain_desc = nullptr;
     int solve_epoch = 0;
     int64_t chain_part_vecs = 0;
@@ -446,6 +455,45 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
     }
     h->bpart_slots = slots;
     h->ncounters = ncounters;
+    // 32-wide sweeps (one GPU only): small fronts as in fwd / bwd, every big front through the tensor-pipe kernels
+    h->fwd32.clear(); h->bwd32.clear(); h->bpart32_slots = 0;
+    if (h->nranks == 1) {
+        for (int l = 0; l < S.nlevels; ++l) {
+            cur_level = l;
+            int64_t off = (int64_t)tasks.size();
+            for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) if (SMALL(S.level_sn[t])) tasks.push_back(make_int4(S.level_sn[t], 0, 0, 0));
+            push(h->fwd32, L_FWD_SMALL, off, 0);
+            off = (int64_t)tasks.size();
+            int64_t wide_tiles = 0;
+            for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t)
+                if (!SMALL(S.level_sn[t])) wide_tiles += std::max<int64_t>(1, (R(S.level_sn[t]) + RB_WIDE_ROWS - 1) / RB_WIDE_ROWS);
+            const int trows = wide_tiles < 74 ? RB_WIDE_ROWS_TOP : RB_WIDE_ROWS;      // few tiles: spread the level over more SMs (one wave of 64-row tiles)
+            for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) {
+                const int s = S.level_sn[t];
+                if (SMALL(s)) continue;
+                const int nt = (int)std::max<int64_t>(1, (R(s) + trows - 1) / trows);
+                for (int i = 0; i < nt; ++i) tasks.push_back(make_int4(s, i, 0, 0));
+            }
+            if ((int64_t)tasks.size() > off) h->fwd32.push_back(Launch{L_FWD32, off, (int)((int64_t)tasks.size() - off), trows, l, 0});
+        }
+        int64_t slots32 = 0;
+        for (int l = S.nlevels - 1; l >= 0; --l) {
+            cur_level = l;
+            int64_t off = (int64_t)tasks.size();
+            for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) if (SMALL(S.level_sn[t])) tasks.push_back(make_int4(S.level_sn[t], 0, 0, 0));
+            push(h->bwd32, L_BWD_SMALL, off, 0);
+            off = (int64_t)tasks.size();
+            for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; ++t) {
+                const int s = S.level_sn[t];
+                if (SMALL(s)) continue;
+                const int nt = (int)std::max<int64_t>(1, (R(s) + RB_WIDE_ROWS - 1) / RB_WIDE_ROWS);
+                for (int i = 0; i < nt; ++i) tasks.push_back(make_int4(s, i, nt, (int)slots32));
+                if (nt > 1) slots32 += nt;
+            }
+            if ((int64_t)tasks.size() > off) h->bwd32.push_back(Launch{L_BWD32, off, (int)((int64_t)tasks.size() - off), 0, l, 0});
+        }
+        h->bpart32_slots = slots32;
+    }
 }
 
 // Chains of fronts (links of at most KW pivot columns cut out of one wide separator; each link the only child of the
@@ -1103,13 +1151,16 @@ int prof_collect(smslu_handle_t h) {   // stream must be synchronized
 }
 
 int launch_one(smslu_handle_t h, cudaStream_t st, const Launch& L, const double* win, double* zx, int rb) {
-    const int4* tk = h->d_tasks + (L.kind < L_REPL ? L.off : 0);
+    const int4* tk = h->d_tasks + ((L.kind < L_REPL || L.kind >= L_FWD32) ? L.off : 0);
+    const DevCtx& cxv = rb == RB_WIDE ? h->cx32 : h->cx;      // the wide sweeps have their own update vectors / scratch
     switch (L.kind) {
         case L_ZERO: launch_zero_cb(st, h->cx, tk, L.ntasks); break;
         case L_EXTEND: launch_assemble(st, h->cx, tk, L.ntasks, L.fmax); break;
         case L_SMALL: launch_front_small(st, h->cx, tk, L.ntasks, L.fmax, h->cur_av, h->d_Rs); break;
-        case L_FWD_SMALL: launch_small_fwd(st, h->cx, tk, L.ntasks, win, zx, rb); break;
-        case L_BWD_SMALL: launch_small_bwd(st, h->cx, tk, L.ntasks, zx, rb); break;
+        case L_FWD_SMALL: launch_small_fwd(st, cxv, tk, L.ntasks, win, zx, rb); break;
+        case L_BWD_SMALL: launch_small_bwd(st, cxv, tk, L.ntasks, zx, rb); break;
+        case L_FWD32: launch_fwd32(st, cxv, tk, L.ntasks, L.fmax, win, zx); break;
+        case L_BWD32: launch_bwd32(st, cxv, tk, L.ntasks, zx); break;
         case L_PANEL: launch_panel(st, h->cx, tk, L.ntasks, L.fmax & 255, L.fmax >> 8); break;
         case L_GEMM: if (L.fmax == 1) launch_gemm_strip(st, h->cx, tk, L.ntasks); else launch_gemm_cb(st, h->cx, tk, L.ntasks); break;
         case L_FWD: launch_fwd(st, h->cx, tk, L.ntasks, L.fmax >> 8, win, zx, rb); break;
@@ -1158,7 +1209,7 @@ int run_schedule(smslu_handle_t h, const std::vector<Launch>& sched, const doubl
         }
         for (size_t t = i; t < j; ++t) {
             const Launch& L = sched[t];
-            if ((rc = prof_begin(h, L.kind == L_FWD_CHAIN ? SMSLU_K_FWD : (L.kind >= L_BWD_RECT ? SMSLU_K_BWD : (L.kind >= L_REPL ? SMSLU_K_ALLREDUCE : L.kind))))) return rc;
+            if ((rc = prof_begin(h, (L.kind == L_FWD_CHAIN || L.kind == L_FWD32) ? SMSLU_K_FWD : (L.kind >= L_BWD_RECT ? SMSLU_K_BWD : (L.kind >= L_REPL ? SMSLU_K_ALLREDUCE : L.kind))))) return rc;
             if (launch_one(h, lane_stream(L.lane), L, win, zx, rb) != 0) return fail(h, SMSLU_E_CUDA, std::string("cooperative launch of a chain kernel failed: ") + cudaGetErrorString(cudaGetLastError()));
             if ((rc = prof_end(h))) return rc;
         }
@@ -1300,6 +1351,15 @@ int enqueue_gather_solution(smslu_handle_t h, int rb) {
 int enqueue_solve(smslu_handle_t h, double* xdev, int64_t ldx, const double* bdev, int64_t ldb, int rb, int nv) {
     int rc;
     if ((rc = prof_begin(h, SMSLU_K_PERMUTE))) return rc;
+    if (rb == RB_WIDE) {                 // one GPU: forward and backward sweeps of 32 right-hand sides
+        launch_permute_scale(h->stream, h->n, h->d_p, h->d_Rs, bdev, ldb, h->d_w32, rb, nv);
+        if ((rc = prof_end(h))) return rc;
+        if ((rc = run_schedule(h, h->fwd32, h->d_w32, h->d_z32, rb))) return rc;
+        if ((rc = run_schedule(h, h->bwd32, nullptr, h->d_z32, rb))) return rc;
+        if ((rc = prof_begin(h, SMSLU_K_UNPERMUTE))) return rc;
+        launch_unpermute(h->stream, h->n, h->d_q, h->d_z32, xdev, ldx, rb, nv);
+        return prof_end(h);
+    }
     launch_permute_scale(h->stream, h->n, h->d_p, h->d_Rs, bdev, ldb, h->d_w, rb, nv);
     if ((rc = prof_end(h))) return rc;
     if ((rc = run_schedule(h, rb == 1 ? h->fwd1 : h->fwd, h->d_w, h->d_z, rb))) return rc;
@@ -1315,7 +1375,35 @@ int enqueue_solve(smslu_handle_t h, double* xdev, int64_t ldx, const double* bde
     return 0;
 }
 
-// slots of the next sweep: a partly filled sweep of 4 or 8 beats several narrower ones
+// Work vectors of the 32-wide sweeps, allocated by the first solve that has enough right-hand sides for one (one GPU only).
+// If the device cannot hold them the solve quietly stays with the 8-wide sweeps.
+bool ensure_wide(smslu_handle_t h) {
+    if (h->have_wide) return true;
+    if (h->wide_failed || h->nranks > 1 || h->fwd32.empty()) return false;
+    if (getenv("SMSLU_NO_WIDE") && atoi(getenv("SMSLU_NO_WIDE")) != 0) { h->wide_failed = true; return false; }
+    const Symbolic& S = h->S;
+    const size_t n = (size_t)h->n;
+    double *w = nullptr, *z = nullptr, *xb = nullptr, *upd = nullptr, *bp = nullptr;
+    int* cnt = nullptr;
+    auto grab = [&](void** p, size_t bytes) {
+        if (cudaMalloc(p, std::max<size_t>(bytes, 8)) != cudaSuccess) { cudaGetLastError(); *p = nullptr; return false; }
+        h->dev_allocs.push_back(*p);
+        return true;
+    };
+    const bool ok = grab((void**)&w, sizeof(double) * n * RB_WIDE) && grab((void**)&z, sizeof(double) * n * RB_WIDE) &&
+                    grab((void**)&xb, sizeof(double) * n * RB_WIDE) && grab((void**)&upd, sizeof(double) * (size_t)S.sum_r * RB_WIDE) &&
+                    grab((void**)&bp, sizeof(double) * (size_t)h->bpart32_slots * KMAX * RB_WIDE) && grab((void**)&cnt, sizeof(int) * (size_t)std::max(S.nsn, 1));
+    if (!ok || cudaMemset(cnt, 0, sizeof(int) * (size_t)std::max(S.nsn, 1)) != cudaSuccess) { cudaGetLastError(); h->wide_failed = true; return false; }
+    h->d_w32 = w; h->d_z32 = z; h->d_xb32 = xb;
+    h->cx32 = h->cx;
+    h->cx32.upd = upd; h->cx32.bpart = bp; h->cx32.counters2 = cnt;
+    h->have_wide = true;
+    return true;
+}
+
+// slots of the next sweep: a partly filled sweep of 4 or 8 beats several narrower ones; from WIDE_MIN right-hand sides on a
+// 32-wide sweep on the tensor pipe (one GPU) beats two or more 8-wide ones
+constexpr int WIDE_MIN = 9;
 inline int chunk_rb(int64_t left) { return left >= 5 ? 8 : (left >= 2 ? 4 : 1); }
 
 }  // namespace
@@ -1553,21 +1641,22 @@ int smslu_solve(smslu_handle_t h, double* x, int64_t nx, const double* b, int64_
     float h2d = 0, dev = 0, d2h = 0, ms;
     int64_t nsweeps = 0;
     for (int64_t c = 0; c < nrhs;) {
-        const int rb = chunk_rb(nrhs - c);               // 8, 4 or 1 slots per sweep
+        const int rb = (nrhs - c >= WIDE_MIN && ensure_wide(h)) ? RB_WIDE : chunk_rb(nrhs - c);     // 32, 8, 4 or 1 slots per sweep
         const int nv = (int)std::min<int64_t>(rb, nrhs - c);
+        double* const stage = rb == RB_WIDE ? h->d_xb32 : h->d_xb;      // host columns pass through this device block
         const double* bc = b + c * ldb;
         double* xc = x + c * ldx;
         int64_t lb = ldb, lx = ldx;
         CU(cudaEventRecord(h->ev0, h->stream));
         if (!bdev) {                                     // host columns -> contiguous device block, ld = n
-            CU(cudaMemcpy2DAsync(h->d_xb, sizeof(double) * n, bc, sizeof(double) * ldb, sizeof(double) * n, nv,
+            CU(cudaMemcpy2DAsync(stage, sizeof(double) * n, bc, sizeof(double) * ldb, sizeof(double) * n, nv,
                                  cudaMemcpyHostToDevice, h->stream));
-            bc = h->d_xb; lb = n;
+            bc = stage; lb = n;
         }
         CU(cudaEventRecord(h->ev1, h->stream));
-        if ((rc = enqueue_solve(h, xdev ? xc : h->d_xb, xdev ? lx : n, bc, lb, rb, nv))) return rc;
+        if ((rc = enqueue_solve(h, xdev ? xc : stage, xdev ? lx : n, bc, lb, rb, nv))) return rc;
         CU(cudaEventRecord(h->ev2, h->stream));
-        if (!xdev) CU(cudaMemcpy2DAsync(xc, sizeof(double) * ldx, h->d_xb, sizeof(double) * n, sizeof(double) * n, nv,
+        if (!xdev) CU(cudaMemcpy2DAsync(xc, sizeof(double) * ldx, stage, sizeof(double) * n, sizeof(double) * n, nv,
                                         cudaMemcpyDeviceToHost, h->stream));
         CU(cudaEventRecord(h->ev3, h->stream));
         CU(cudaStreamSynchronize(h->stream));
@@ -1598,14 +1687,25 @@ static int tri_solve(smslu_handle_t h, double* x, int64_t nx, int64_t nrhs, int6
     const int n = h->n;
     const bool dev = is_device_ptr(x);
     for (int64_t c = 0; c < nrhs;) {
-        const int rb = chunk_rb(nrhs - c);
+        const int rb = (nrhs - c >= WIDE_MIN && ensure_wide(h)) ? RB_WIDE : chunk_rb(nrhs - c);
         const int nv = (int)std::min<int64_t>(rb, nrhs - c);
+        double* const stage = rb == RB_WIDE ? h->d_xb32 : h->d_xb;
         double* xc = x + c * ld;
         const double* src = xc; int64_t lsrc = ld;
         if (!dev) {
-            CU(cudaMemcpy2DAsync(h->d_xb, sizeof(double) * n, xc, sizeof(double) * ld, sizeof(double) * n, nv,
+            CU(cudaMemcpy2DAsync(stage, sizeof(double) * n, xc, sizeof(double) * ld, sizeof(double) * n, nv,
                                  cudaMemcpyHostToDevice, h->stream));
-            src = h->d_xb; lsrc = n;
+            src = stage; lsrc = n;
+        }
+        if (rb == RB_WIDE) {                 // one GPU, 32 slots: the same sweep on the tensor-pipe kernels
+            launch_permute_scale(h->stream, n, h->d_post, nullptr, src, lsrc, lower ? h->d_w32 : h->d_z32, rb, nv);
+            if ((rc = run_schedule(h, lower ? h->fwd32 : h->bwd32, lower ? h->d_w32 : nullptr, h->d_z32, rb))) return rc;
+            launch_unpermute(h->stream, n, h->d_post, h->d_z32, dev ? xc : stage, dev ? ld : n, rb, nv);
+            if (!dev) CU(cudaMemcpy2DAsync(xc, sizeof(double) * ld, stage, sizeof(double) * n, sizeof(double) * n, nv,
+                                           cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+            c += nv;
+            continue;
         }
         // interleave the block (identity permutation, no scaling), sweep, de-interleave
         if (lower) {

@@ -1803,6 +1803,340 @@ __global__ void __launch_bounds__(SOLVE_THREADS, (WIDE && RB == 1) ? 2 : 1) k_bw
     for (int e = tid; e < k * RB; e += SOLVE_THREADS) x[(int64_t)F.c0 * RB + e] = part[e];
 }
 
+// ------------------------------------------------------------------ many right-hand sides: 32-wide sweeps on the FP64 tensor pipe
+// With MR = 32 right-hand sides swept together the big-front solves are dense contractions (the ridge is at
+// ~37 right-hand sides): upd = gathered - L21 * Y and part = U12 * X run as DMMA (m8n8k4) products whose A fragments
+// (the factor entries) come straight from global memory -- every factor entry is read once per 32 right-hand sides --
+// and whose B fragments (the right-hand sides) sit in shared memory.  The k x k pivot block is applied 32 columns at a
+// time: the inverted diagonal blocks of k_diag_inverse as one 32 x 32 x 32 product, the off-diagonal blocks as further
+// products.  Vectors are interleaved [i * 32 + q] like the narrower sweeps.  The small fronts run the 8-wide warp-per-front
+// kernels on the four slices of the 32 slots (k_small_fwd / k_small_bwd with LDV = 32).
+constexpr int MR = 32;             // right-hand sides per sweep
+constexpr int MLD = MR + 4;        // shared-memory row stride: 4 (mod 16) doubles, so B fragment loads are conflict-free
+constexpr int MROWS = 256;         // rows of L21 / U12' per CTA (eight warps x 32 rows, or 256 contraction rows backward)
+
+// One warp's share of a 32 x 32 (block) = A (32 x 32, element functor) * B (32 x 32 rows of a shared [..][MLD] array):
+// warp w computes tile row i = w >> 1 and the tile columns jb, jb + 1 (jb = 2 (w & 1)); k-steps [ks0, ks1).
+template <class FA>
+__device__ __forceinline__ void block32_mma(double (&acc)[2][2], FA getA, const double* __restrict__ Bs, int i, int jb,
+                                            int fr, int fc, int ks0, int ks1) {
+    double a[8];
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) a[ks] = (ks >= ks0 && ks < ks1) ? getA(8 * i + fr, 4 * ks + fc) : 0.0;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+        if (ks < ks0 || ks >= ks1) continue;
+        const double* __restrict__ bp = Bs + (4 * ks + fc) * MLD + fr;
+        dmma884(acc[0][0], acc[0][1], a[ks], bp[8 * jb]);
+        dmma884(acc[1][0], acc[1][1], a[ks], bp[8 * jb + 8]);
+    }
+}
+__device__ __forceinline__ void block32_load(double (&acc)[2][2], const double* __restrict__ Cs, int i, int jb, int fr, int fc) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const double2 v = *reinterpret_cast<const double2*>(Cs + (8 * i + fr) * MLD + 8 * (jb + j) + 2 * fc);
+        acc[j][0] = v.x; acc[j][1] = v.y;
+    }
+}
+__device__ __forceinline__ void block32_store(const double (&acc)[2][2], double* __restrict__ Cs, int i, int jb, int fr, int fc) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+        *reinterpret_cast<double2*>(Cs + (8 * i + fr) * MLD + 8 * (jb + j) + 2 * fc) = make_double2(acc[j][0], acc[j][1]);
+}
+// ys (KW x MLD, rows >= k zero) <- L11^{-1} ys (unit lower) or U11^{-1} ys (upper); all 256 threads, ends with a barrier.
+template <bool LOWER>
+__device__ __forceinline__ void pivot_solve32(const Front& F, const double* __restrict__ inv, double* ys) {
+    const int lane = threadIdx.x & 31, w = uniform_warp_id(), fr = lane >> 2, fc = lane & 3;
+    const int i = w >> 1, jb = 2 * (w & 1), k = F.k, nblk = (k + NB - 1) / NB;
+    const double* __restrict__ P = F.P;
+    const int64_t f = F.f;
+    for (int gg = 0; gg < nblk; ++gg) {
+        const int g = LOWER ? gg : nblk - 1 - gg;
+        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        const double* __restrict__ ib = inv + (int64_t)g * (NB * NB);
+        if (LOWER) block32_mma(acc, [&](int m, int c) { return m > c ? ib[m + NB * c] : (m == c ? 1.0 : 0.0); }, ys + g * NB * MLD, i, jb, fr, fc, 0, 2 * (i + 1));
+        else block32_mma(acc, [&](int m, int c) { return m <= c ? ib[m + NB * c] : 0.0; }, ys + g * NB * MLD, i, jb, fr, fc, 2 * i, 8);
+        __syncthreads();                                     // every warp has read the block's right-hand sides
+        block32_store(acc, ys + g * NB * MLD, i, jb, fr, fc);
+        __syncthreads();
+        // the other blocks on the far side: V_h -= L_hg Y_g (h > g) / V_h -= U_hg X_g (h < g)
+        for (int h = LOWER ? g + 1 : 0; LOWER ? h < nblk : h < g; ++h) {
+            double c2[2][2];
+            block32_load(c2, ys + h * NB * MLD, i, jb, fr, fc);
+            block32_mma(c2, [&](int m, int c) {
+                            const int row = h * NB + m, col = g * NB + c;
+                            return (row < k && col < k) ? -P[row + (int64_t)col * f] : 0.0;
+                        }, ys + g * NB * MLD, i, jb, fr, fc, 0, 8);
+            block32_store(c2, ys + h * NB * MLD, i, jb, fr, fc);
+        }
+        __syncthreads();
+    }
+}
+
+// Forward substitution of one level, 32 right-hand sides.  task: x = supernode, y = row tile (TR = 8 WR rows of L21:
+// 256 where a level has many tiles, 64 near the top of the tree, where the few fronts of a level are spread over more SMs).
+// dynamic shared memory: ys[KW][MLD] | accs[TR][MLD].
+template <int WR>
+__global__ void __launch_bounds__(SOLVE_THREADS, 2) k_fwd32(DevCtx cx, const int4* __restrict__ tasks,
+                                                            const double* __restrict__ win, double* __restrict__ zout) {
+    constexpr int TR = 8 * WR, NI = WR / 8;
+    extern __shared__ __align__(16) double msm[];
+    double* ys = msm;
+    double* accs = msm + KW * MLD;
+    __shared__ int s_piv[64], s_lo[64], s_hi[64];
+    pdl_trigger();
+    const int4 tk = tasks[blockIdx.x];
+    const int s = tk.x;
+    const Front F = load_front(cx, s);
+    const int k = F.k, tid = threadIdx.x, lane = tid & 31, w = uniform_warp_id(), fr = lane >> 2, fc = lane & 3;
+    const int64_t lo = (int64_t)tk.y * TR;
+    const int nrow = (int)(F.r - lo < TR ? (F.r - lo > 0 ? F.r - lo : 0) : TR);
+    const double* __restrict__ inv = cx.dblk + (int64_t)cx.Doff[s] * (NB * NB);
+    // the factors are constant during a solve: pull this CTA's share towards L2 before waiting for the level below
+    prefetch_block_l2(inv, NB, ((k + NB - 1) / NB) * NB, NB, tid, SOLVE_THREADS);
+    prefetch_block_l2(F.P, k, k, F.f, tid, SOLVE_THREADS);
+    prefetch_block_l2(F.P + k + lo, nrow, k, F.f, tid, SOLVE_THREADS);
+    pdl_wait();
+    const int ch0 = cx.child_ptr[s], nch = cx.child_ptr[s + 1] - ch0;
+    const int c_id = nch == 1 ? cx.child_idx[ch0] : -1;
+    const bool ident = nch == 1 && cx.rows_ptr[c_id + 1] - cx.rows_ptr[c_id] == F.f;
+    // ---- gather: ys = w[cols] (+ children), accs = children's contributions to this tile's rows; a warp per row
+    if (ident) {
+        const double* __restrict__ uc = cx.upd + cx.rows_ptr[c_id] * MR;
+#pragma unroll 8
+        for (int a = w; a < KW; a += 8) ys[a * MLD + lane] = a < k ? win[(int64_t)(F.c0 + a) * MR + lane] + uc[(int64_t)a * MR + lane] : 0.0;
+#pragma unroll 8
+        for (int a = w; a < TR; a += 8) accs[a * MLD + lane] = a < nrow ? uc[(int64_t)(k + lo + a) * MR + lane] : 0.0;
+        __syncthreads();
+    } else {
+#pragma unroll 8
+        for (int a = w; a < KW; a += 8) ys[a * MLD + lane] = a < k ? win[(int64_t)(F.c0 + a) * MR + lane] : 0.0;
+        for (int a = w; a < TR; a += 8) accs[a * MLD + lane] = 0.0;
+        for (int q0 = 0; q0 < nch; q0 += 64) {
+            // rel is ascending: rows [0, piv) of child q land in the pivot rows, rows [lo_q, hi_q) in this tile
+            if (tid < 192) {
+                const int q = q0 + (tid & 63), what = tid >> 6;
+                if (q < nch) {
+                    const int c = cx.child_idx[ch0 + q];
+                    const int rc = (int)(cx.rows_ptr[c + 1] - cx.rows_ptr[c]);
+                    const int* __restrict__ rel = cx.rel + cx.rows_ptr[c];
+                    const int64_t key = what == 0 ? k : (what == 1 ? k + lo : k + lo + TR);
+                    int a0 = 0, a1 = rc;
+                    while (a0 < a1) { const int mid = (a0 + a1) >> 1; if (rel[mid] < key) a0 = mid + 1; else a1 = mid; }
+                    (what == 0 ? s_piv : (what == 1 ? s_lo : s_hi))[tid & 63] = a0;
+                }
+            }
+            __syncthreads();
+            const int q1 = q0 + 64 < nch ? q0 + 64 : nch;
+            for (int q = q0; q < q1; ++q) {
+                const int c = cx.child_idx[ch0 + q];
+                const int* __restrict__ rel = cx.rel + cx.rows_ptr[c];
+                const double* __restrict__ uc = cx.upd + cx.rows_ptr[c] * MR;
+                const int piv = s_piv[q - q0], tlo = s_lo[q - q0], thi = s_hi[q - q0];
+                // a warp takes 32 consecutive rows of the child at a time: their positions in one coalesced load, handed
+                // round by shuffle; the 32 row loads are independent (eight in flight)
+                for (int a0 = 32 * w; a0 < piv; a0 += 256) {
+                    const int rl = a0 + lane < piv ? rel[a0 + lane] : 0;
+                    const int cntr = piv - a0 < 32 ? piv - a0 : 32;
+                    for (int j0 = 0; j0 < cntr; j0 += 8) {
+                        double v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) v[u] = j0 + u < cntr ? uc[(int64_t)(a0 + j0 + u) * MR + lane] : 0.0;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int ra = __shfl_sync(0xffffffffu, rl, (j0 + u) & 31);
+                            if (j0 + u < cntr) ys[ra * MLD + lane] += v[u];
+                        }
+                    }
+                }
+                for (int a0 = tlo + 32 * w; a0 < thi; a0 += 256) {
+                    const int rl = a0 + lane < thi ? rel[a0 + lane] - k - (int)lo : 0;
+                    const int cntr = thi - a0 < 32 ? thi - a0 : 32;
+                    for (int j0 = 0; j0 < cntr; j0 += 8) {
+                        double v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) v[u] = j0 + u < cntr ? uc[(int64_t)(a0 + j0 + u) * MR + lane] : 0.0;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int ra = __shfl_sync(0xffffffffu, rl, (j0 + u) & 31);
+                            if (j0 + u < cntr) accs[ra * MLD + lane] += v[u];
+                        }
+                    }
+                }
+                __syncthreads();                               // children are added one after the other: fixed order
+            }
+        }
+        if (nch == 0) __syncthreads();
+    }
+    // ---- pivot block
+    pivot_solve32<true>(F, inv, ys);
+    if (tk.y == 0)
+        for (int a = w; a < k; a += 8) zout[(int64_t)(F.c0 + a) * MR + lane] = ys[a * MLD + lane];
+    if (nrow == 0) return;
+    // ---- upd = accs - L21 Y: warp w owns rows [WR w, WR w + WR) of the tile, NI x 4 DMMA tiles
+    double acc[NI][4][2];
+#pragma unroll
+    for (int i = 0; i < NI; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double2 v = *reinterpret_cast<const double2*>(accs + (WR * w + 8 * i + fr) * MLD + 8 * j + 2 * fc);
+            acc[i][j][0] = v.x; acc[i][j][1] = v.y;
+        }
+    if (WR * w < nrow) {
+        const double* __restrict__ Lp = F.P + k + lo + WR * w + fr;
+        bool ok[NI];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) ok[i] = WR * w + 8 * i + fr < nrow;
+        const int ksteps = (k + 3) >> 2;
+        for (int ks0 = 0; ks0 < ksteps; ks0 += 4) {
+            double a[4][NI];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int col = 4 * (ks0 + u) + fc;
+#pragma unroll
+                for (int i = 0; i < NI; ++i) a[u][i] = (ok[i] && col < k) ? -Lp[8 * i + (int64_t)col * F.f] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (ks0 + u >= ksteps) continue;
+                const double* __restrict__ bp = ys + (4 * (ks0 + u) + fc) * MLD + fr;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double b = bp[8 * j];
+#pragma unroll
+                    for (int i = 0; i < NI; ++i) dmma884(acc[i][j][0], acc[i][j][1], a[u][i], b);
+                }
+            }
+        }
+        double* __restrict__ up = cx.upd + (cx.rows_ptr[s] + lo + WR * w + fr) * MR + 2 * fc;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            if (!ok[i]) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<double2*>(up + (int64_t)(8 * i) * MR + 8 * j) = make_double2(acc[i][j][0], acc[i][j][1]);
+        }
+    }
+}
+
+// Backward substitution of one level, 32 right-hand sides.  task: x = supernode, y = row tile of U12' (MROWS rows),
+// z = tiles of this supernode, w = slot of its partial sums in cx.bpart (KW * MR doubles per tile).
+// dynamic shared memory: xs[MROWS][MLD] (reused as the pivot block's right-hand sides) | ps[KW][MLD].
+__global__ void __launch_bounds__(SOLVE_THREADS, 2) k_bwd32(DevCtx cx, const int4* __restrict__ tasks, double* __restrict__ x) {
+    extern __shared__ __align__(16) double msm[];
+    double* xs = msm;
+    double* ps = msm + MROWS * MLD;
+    __shared__ int s_last;
+    pdl_trigger();
+    const int4 tk = tasks[blockIdx.x];
+    const int s = tk.x, rtile = tk.y, ntiles = tk.z;
+    const Front F = load_front(cx, s);
+    const int k = F.k, tid = threadIdx.x, lane = tid & 31, w = uniform_warp_id(), fr = lane >> 2, fc = lane & 3;
+    const int64_t lo = (int64_t)rtile * MROWS;
+    const int cnt = (int)(F.r - lo < MROWS ? (F.r - lo > 0 ? F.r - lo : 0) : MROWS);
+    const double* __restrict__ inv = cx.dblk + (int64_t)cx.Doff[s] * (NB * NB);
+    const int* __restrict__ rows = cx.rows + cx.rows_ptr[s] + lo;
+    prefetch_block_l2(F.T + lo, cnt, k, F.r, tid, SOLVE_THREADS);
+    prefetch_block_l2(inv, NB, ((k + NB - 1) / NB) * NB, NB, tid, SOLVE_THREADS);
+    prefetch_block_l2(F.P, k, k, F.f, tid, SOLVE_THREADS);
+    const int rl = 32 * w + lane < cnt ? rows[32 * w + lane] : 0;      // warp w gathers rows [32 w, 32 w + 32) of the tile
+    pdl_wait();
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+        const int ri = __shfl_sync(0xffffffffu, rl, j);
+        xs[(32 * w + j) * MLD + lane] = 32 * w + j < cnt ? x[(int64_t)ri * MR + lane] : 0.0;
+    }
+    __syncthreads();
+    // part (k x 32) = U12 (k x rows) X (rows x 32): warp w owns pivot columns [16 w, 16 w + 16), 2 x 4 DMMA tiles
+    double acc[2][4][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    if (16 * w < k && cnt > 0) {
+        const double* __restrict__ Tp = F.T + lo + fc;
+        const bool ok0 = 16 * w + fr < k, ok1 = 16 * w + 8 + fr < k;
+        const int64_t c0o = (int64_t)(16 * w + fr) * F.r, c1o = (int64_t)(16 * w + 8 + fr) * F.r;
+        const int ksteps = (cnt + 3) >> 2;
+        for (int ks0 = 0; ks0 < ksteps; ks0 += 8) {
+            double a[8][2];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int rr = 4 * (ks0 + u) + fc;
+                a[u][0] = (ok0 && rr < cnt) ? Tp[4 * (ks0 + u) + c0o] : 0.0;
+                a[u][1] = (ok1 && rr < cnt) ? Tp[4 * (ks0 + u) + c1o] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (ks0 + u >= ksteps) continue;
+                const double* __restrict__ bp = xs + (4 * (ks0 + u) + fc) * MLD + fr;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double b = bp[8 * j];
+                    dmma884(acc[0][j][0], acc[0][j][1], a[u][0], b);
+                    dmma884(acc[1][j][0], acc[1][j][1], a[u][1], b);
+                }
+            }
+        }
+    }
+    // partial products -> ps (one tile) or the front's scratch slot (several tiles: the last arriver adds them in tile order)
+    double* slot = cx.bpart + ((int64_t)tk.w + rtile) * (KW * MR);
+    {
+        double* __restrict__ dst = ntiles > 1 ? slot : ps;
+        const int ld = ntiles > 1 ? MR : MLD;
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<double2*>(dst + (16 * w + 8 * i + fr) * ld + 8 * j + 2 * fc) = make_double2(acc[i][j][0], acc[i][j][1]);
+    }
+    if (ntiles > 1) {
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const int old = atomicAdd(cx.counters2 + s, 1);
+            s_last = ((old + 1) % ntiles) == 0;
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        // tile-ordered sums: thread t owns elements t, t + 256, ... (16 of them); two tiles = 32 loads in flight per thread
+        const double* __restrict__ base = cx.bpart + (int64_t)tk.w * (KW * MR) + tid;
+        constexpr int NE = KW * MR / SOLVE_THREADS;
+        double sum[NE];
+#pragma unroll
+        for (int u = 0; u < NE; ++u) sum[u] = 0.0;
+        int t = 0;
+        for (; t + 2 <= ntiles; t += 2) {
+            double l0[NE], l1[NE];
+#pragma unroll
+            for (int u = 0; u < NE; ++u) {
+                l0[u] = __ldcg(base + (int64_t)t * (KW * MR) + u * SOLVE_THREADS);
+                l1[u] = __ldcg(base + (int64_t)(t + 1) * (KW * MR) + u * SOLVE_THREADS);
+            }
+#pragma unroll
+            for (int u = 0; u < NE; ++u) sum[u] = (sum[u] + l0[u]) + l1[u];
+        }
+        if (t < ntiles) {
+#pragma unroll
+            for (int u = 0; u < NE; ++u) sum[u] += __ldcg(base + (int64_t)t * (KW * MR) + u * SOLVE_THREADS);
+        }
+#pragma unroll
+        for (int u = 0; u < NE; ++u) {
+            const int e = tid + u * SOLVE_THREADS;
+            ps[(e >> 5) * MLD + (e & 31)] = sum[u];
+        }
+    }
+    __syncthreads();
+    // right-hand side of U11 X = x[cols] - part, in xs (reused); then the pivot block
+    double* ys = xs;
+#pragma unroll 8
+    for (int a = w; a < KW; a += 8) ys[a * MLD + lane] = a < k ? x[(int64_t)(F.c0 + a) * MR + lane] - ps[a * MLD + lane] : 0.0;
+    __syncthreads();
+    pivot_solve32<false>(F, inv, ys);
+    for (int a = w; a < k; a += 8) x[(int64_t)(F.c0 + a) * MR + lane] = ys[a * MLD + lane];
+}
+
 // ------------------------------------------------------------------ persistent chain solves
 // A wide separator is stored as a chain of fronts (links) of at most KW pivot columns, each the only child of the next and
 // its row list exactly the next link's front.  Level by level that is one launch per link and sweep -- hundreds of dependent
@@ -2179,7 +2513,9 @@ __global__ void k_wait(DevCtx cx, const int* __restrict__ slots, int nslots, int
 // Forward: v = [w[cols]; 0] + children's update vectors (gathered through rel, child by child),
 // then column-oriented substitution: for j < k: y_j = v_j (broadcast by shuffle), v_i -= L_ij y_j
 // for all i > j -- rows of L11 and of L21 alike, each column of P read once, coalesced.
-template <int FPC, int RB>
+// LDV = slots of the interleaved work vectors (RB, or 32 when the sweep is one of the four 8-wide slices of a
+// 32-wide sweep: blockIdx.y picks the slice)
+template <int FPC, int RB, int LDV = RB>
 __global__ void __launch_bounds__(32 * FPC) k_small_fwd(DevCtx cx, const int4* __restrict__ tasks, int ntasks,
                                                         const double* __restrict__ win, double* __restrict__ zout) {
     __shared__ double vs[FPC][SMALL_F_MAX * RB];
@@ -2190,19 +2526,19 @@ __global__ void __launch_bounds__(32 * FPC) k_small_fwd(DevCtx cx, const int4* _
     const int s = tasks[ti].x;
     const Front F = load_front(cx, s);
     pdl_wait();
-    const int k = F.k, f = (int)F.f;
+    const int k = F.k, f = (int)F.f, q0 = LDV == RB ? 0 : (int)blockIdx.y * RB;
     double* v = vs[grp];
-    for (int e = lane; e < f * RB; e += 32) v[e] = e < k * RB ? win[(int64_t)F.c0 * RB + e] : 0.0;
+    for (int e = lane; e < f * RB; e += 32) v[e] = e < k * RB ? win[(int64_t)(F.c0 + e / RB) * LDV + q0 + (e % RB)] : 0.0;
     __syncwarp();
     for (int ci = cx.child_ptr[s]; ci < cx.child_ptr[s + 1]; ++ci) {
         const int c = cx.child_idx[ci];
         const int rc = (int)(cx.rows_ptr[c + 1] - cx.rows_ptr[c]);
         const int* __restrict__ rel = cx.rel + cx.rows_ptr[c];
-        const double* __restrict__ uc = cx.upd + cx.rows_ptr[c] * RB;
+        const double* __restrict__ uc = cx.upd + cx.rows_ptr[c] * LDV + q0;
         for (int a = lane; a < rc; a += 32) {
             const int ra = rel[a] * RB;
 #pragma unroll
-            for (int q = 0; q < RB; ++q) v[ra + q] += uc[(int64_t)a * RB + q];
+            for (int q = 0; q < RB; ++q) v[ra + q] += uc[(int64_t)a * LDV + q];
         }
         __syncwarp();
     }
@@ -2224,20 +2560,20 @@ __global__ void __launch_bounds__(32 * FPC) k_small_fwd(DevCtx cx, const int4* _
             v0[q] -= l0 * yj; v1[q] -= l1 * yj; v2[q] -= l2 * yj;
         }
     }
-    double* __restrict__ us = cx.upd + (cx.rows_ptr[s] - k) * RB;
+    double* __restrict__ us = cx.upd + (cx.rows_ptr[s] - k) * LDV + q0;
 #pragma unroll
     for (int q = 0; q < RB; ++q) {
-        if (lane < k) zout[(int64_t)(F.c0 + lane) * RB + q] = v0[q];
-        if (h0 && lane >= k) us[lane * RB + q] = v0[q];
-        if (h1) us[(lane + 32) * RB + q] = v1[q];                  // k <= 32 <= lane + 32
-        if (h2) us[(lane + 64) * RB + q] = v2[q];
+        if (lane < k) zout[(int64_t)(F.c0 + lane) * LDV + q0 + q] = v0[q];
+        if (h0 && lane >= k) us[lane * LDV + q] = v0[q];
+        if (h1) us[(lane + 32) * LDV + q] = v1[q];                  // k <= 32 <= lane + 32
+        if (h2) us[(lane + 64) * LDV + q] = v2[q];
     }
 }
 
 // Backward: lane c owns pivot row c.  t_c = sum_b U12[c][b] x[rows[b]] is a plain loop over b (the
 // r x k block is a few KB and stays in L1, so the strided reads cost nothing in HBM traffic and no
 // reduction is needed); then column-oriented back substitution with U11 and the stored 1/u_jj.
-template <int FPC, int RB>
+template <int FPC, int RB, int LDV = RB>
 __global__ void __launch_bounds__(32 * FPC) k_small_bwd(DevCtx cx, const int4* __restrict__ tasks, int ntasks,
                                                         double* __restrict__ x) {
     __shared__ double xs[FPC][SMALL_F_MAX * RB];
@@ -2248,11 +2584,11 @@ __global__ void __launch_bounds__(32 * FPC) k_small_bwd(DevCtx cx, const int4* _
     const int s = tasks[ti].x;
     const Front F = load_front(cx, s);
     pdl_wait();
-    const int k = F.k, r = (int)F.r, f = (int)F.f;
+    const int k = F.k, r = (int)F.r, f = (int)F.f, q0 = LDV == RB ? 0 : (int)blockIdx.y * RB;
     double* xr = xs[grp];
     const int* __restrict__ rows = cx.rows + cx.rows_ptr[s];
     for (int b = lane; b < r; b += 32) {
-        const int64_t xo = (int64_t)rows[b] * RB;
+        const int64_t xo = (int64_t)rows[b] * LDV + q0;
 #pragma unroll
         for (int q = 0; q < RB; ++q) xr[b * RB + q] = x[xo + q];
     }
@@ -2271,7 +2607,7 @@ __global__ void __launch_bounds__(32 * FPC) k_small_bwd(DevCtx cx, const int4* _
         }
     }
 #pragma unroll
-    for (int q = 0; q < RB; ++q) v[q] = act ? x[(int64_t)(F.c0 + lane) * RB + q] - v[q] : 0.0;
+    for (int q = 0; q < RB; ++q) v[q] = act ? x[(int64_t)(F.c0 + lane) * LDV + q0 + q] - v[q] : 0.0;
     const double d = act ? cx.dinv[F.c0 + lane] : 0.0;
     const double* __restrict__ col = F.P + lane + (int64_t)(k - 1) * f;
 #pragma unroll 4
@@ -2285,7 +2621,7 @@ __global__ void __launch_bounds__(32 * FPC) k_small_bwd(DevCtx cx, const int4* _
     }
     if (act) {
 #pragma unroll
-        for (int q = 0; q < RB; ++q) x[(int64_t)(F.c0 + lane) * RB + q] = v[q];
+        for (int q = 0; q < RB; ++q) x[(int64_t)(F.c0 + lane) * LDV + q0 + q] = v[q];
     }
 }
 
@@ -2330,6 +2666,12 @@ cudaError_t kernels_init() {
                                          (int)(sizeof(double) * small_group_doubles(96)));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_gemm_cb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_fwd32<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (KW + MROWS) * MLD));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_fwd32<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (KW + RB_WIDE_ROWS_TOP) * MLD));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_bwd32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (KW + MROWS) * MLD));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_gemm_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_strip_smem());
     if (e != cudaSuccess) return e;
@@ -2407,12 +2749,14 @@ void launch_mask_owned(cudaStream_t st, int n, const int* colowner, int rank, do
 }
 void launch_small_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const double* win, double* zout, int rb) {
     if (ntasks <= 0) return;
+    if (rb == MR) { k_small_fwd<2, 8, MR><<<dim3((ntasks + 1) / 2, MR / 8), 64, 0, st>>>(cx, tasks, ntasks, win, zout); return; }
     if (rb == 1) launch_pdl(k_small_fwd<8, 1>, (ntasks + 7) / 8, 256, 0, st, cx, tasks, ntasks, win, zout);
     else if (rb == 4) launch_pdl(k_small_fwd<4, 4>, (ntasks + 3) / 4, 128, 0, st, cx, tasks, ntasks, win, zout);
     else launch_pdl(k_small_fwd<2, 8>, (ntasks + 1) / 2, 64, 0, st, cx, tasks, ntasks, win, zout);
 }
 void launch_small_bwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, double* x, int rb) {
     if (ntasks <= 0) return;
+    if (rb == MR) { k_small_bwd<2, 8, MR><<<dim3((ntasks + 1) / 2, MR / 8), 64, 0, st>>>(cx, tasks, ntasks, x); return; }
     if (rb == 1) launch_pdl(k_small_bwd<8, 1>, (ntasks + 7) / 8, 256, 0, st, cx, tasks, ntasks, x);
     else if (rb == 4) launch_pdl(k_small_bwd<4, 4>, (ntasks + 3) / 4, 128, 0, st, cx, tasks, ntasks, x);
     else launch_pdl(k_small_bwd<2, 8>, (ntasks + 1) / 2, 64, 0, st, cx, tasks, ntasks, x);
@@ -2444,11 +2788,13 @@ cudaError_t launch_bwd_chain(cudaStream_t st, const DevCtx& cx, const int* chain
 }
 void launch_permute_scale(cudaStream_t st, int n, const int* p, const double* Rs, const double* b, int64_t ldb, double* w, int rb, int nv) {
 #define CALL(R) k_permute_scale<R><<<(n + 255) / 256, 256, 0, st>>>(n, p, Rs, b, ldb, w, nv)
+    if (rb == MR) { CALL(MR); return; }
     RB_DISPATCH(rb, CALL);
 #undef CALL
 }
 void launch_unpermute(cudaStream_t st, int n, const int* q, const double* w, double* x, int64_t ldx, int rb, int nv) {
 #define CALL(R) k_unpermute<R><<<(n + 255) / 256, 256, 0, st>>>(n, q, w, x, ldx, nv)
+    if (rb == MR) { CALL(MR); return; }
     RB_DISPATCH(rb, CALL);
 #undef CALL
 }
@@ -2467,6 +2813,15 @@ void launch_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks
         RB_DISPATCH(rb, CALL);
 #undef CALL
     }
+}
+static size_t mrhs_smem() { return sizeof(double) * (KW + MROWS) * MLD; }
+void launch_fwd32(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int rows, const double* win, double* zout) {
+    if (ntasks <= 0) return;
+    if (rows == RB_WIDE_ROWS) launch_pdl(k_fwd32<32>, ntasks, SOLVE_THREADS, mrhs_smem(), st, cx, tasks, win, zout);
+    else launch_pdl(k_fwd32<8>, ntasks, SOLVE_THREADS, sizeof(double) * (KW + RB_WIDE_ROWS_TOP) * MLD, st, cx, tasks, win, zout);
+}
+void launch_bwd32(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, double* x) {
+    if (ntasks > 0) launch_pdl(k_bwd32, ntasks, SOLVE_THREADS, mrhs_smem(), st, cx, tasks, x);
 }
 void launch_bwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, double* x, int rb) {
     if (ntasks <= 0) return;

@@ -29,7 +29,10 @@ constexpr int FWD_ROWS_MID = 128;  // ... two threads per row where 64-row tiles
 constexpr int FWD_ROWS_WIDE = 256; // ... or one thread per row on levels with many tiles (every CTA repeats the pivot-block solve)
 constexpr int BWD_ROWS = 256;     // rows of U12' per backward CTA
 constexpr int ZERO_TILE = 8192;
-constexpr int RB_MAX = 8;         // most right-hand sides swept together by the solve kernels
+constexpr int RB_MAX = 8;         // most right-hand sides swept together by the FMA solve kernels
+constexpr int RB_WIDE = 32;       // right-hand sides of a sweep of the tensor-pipe solve kernels (k_fwd32 / k_bwd32)
+constexpr int RB_WIDE_ROWS = 256; // rows of L21 / U12' per CTA of those kernels ...
+constexpr int RB_WIDE_ROWS_TOP = 64; // ... forward, on levels with few tiles
 constexpr int ASM_COLS = 8;       // destination columns of a parent front per assembly CTA
 constexpr int MAX_RANKS = 8;      // GPUs of one NVSwitch box
 constexpr int CHAIN_MAXOWN = 8;   // blocks (forward) / links (backward) of a chain one CTA of the persistent solve kernels may own
@@ -125,6 +128,10 @@ void launch_permute_scale(cudaStream_t st, int n, const int* p, const double* Rs
 void launch_unpermute(cudaStream_t st, int n, const int* q, const double* w, double* x, int64_t ldx, int rb, int nv);
 void launch_fwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int rows, const double* win, double* zout, int rb);
 void launch_bwd(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, double* x, int rb);
+// 32 right-hand sides per sweep on the FP64 tensor pipe (tasks: x = supernode, y = row tile of RB_WIDE_ROWS rows; backward also
+// z = tiles of the supernode, w = first slot of its partial sums)
+void launch_fwd32(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, int rows, const double* win, double* zout);
+void launch_bwd32(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, double* x);
 // persistent chain kernels (single right-hand side): descriptors of `nchains` chains, `nctas` CTAs in total
 cudaError_t launch_fwd_chain(cudaStream_t st, const DevCtx& cx, const int* chains, int nchains, int nctas, const double* win, double* zout, int epoch);
 void launch_bwd_rect(cudaStream_t st, const DevCtx& cx, const int4* tasks, int ntasks, const double* x);
