@@ -11,7 +11,7 @@ nvidia-smi --query-gpu=name,clocks.max.sm,memory.total --format=csv,noheader
 python scripts/launch_list.py gpurun_out/${T}_launches_one_step_128.csv totals > gpurun_out/${T}_launch_totals.txt 2>&1; cat gpurun_out/${T}_launch_totals.txt
 : > gpurun_out/${T}_ncu_stalls.txt
 i=0
-for spec in "k_gemm_cb:2:332" "k_fwd:2:450" "k_bwd:2:450" "k_assemble_smem:2:120" "k_panel:2:1500" "k_small_factor_reg:1:20"; do
+for spec in "k_gemm_cb:2:332" "k_fwd:3:30" "k_bwd:3:280" "k_assemble_smem:2:120" "k_panel:2:1500" "k_small_factor_reg:1:20"; do
   IFS=: read KRE CNT SKIP <<< "$spec"
   NAME=$KRE
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:^$KRE\$ -s $SKIP -c $CNT -o gpurun_out/${T}_prof_$i -f python scripts/one_step.py lap3d 128 > gpurun_out/${T}_ncu_full_$i.log 2>&1
@@ -22,4 +22,5 @@ for spec in "k_gemm_cb:2:332" "k_fwd:2:450" "k_bwd:2:450" "k_assemble_smem:2:120
   i=$((i+1))
 done
 ( timeout 400 python bench.py --config lap2d_1024 --steps 20 --warmup 5 --no-cpu > gpurun_out/${T}_bench_lap2d_1024_n1.json 2> gpurun_out/${T}_bench_lap2d_n1.err; echo "bench lap2d rc=$?" )
+( timeout 400 python scripts/rhs_sweep.py 96 2>&1 | grep -v Warn > gpurun_out/${T}_rhs_sweep_96.txt; echo "rhs sweep rc=$?" ); cat gpurun_out/${T}_rhs_sweep_96.txt
 du -sh gpurun_out

@@ -20,7 +20,7 @@ def col(head, name):
 
 
 out = {"what": "dram__bytes_read.sum + dram__bytes_write.sum per launch from ncu --set full captures of scripts/one_step.py lap3d 128 "
-               "(profiles/round2b_ncu_full_*.csv), cold caches", "kernels": {}}
+               "(profiles/round2_final_ncu_full_*.csv), cold caches", "kernels": {}}
 for spec in sys.argv[1:]:
     parts = spec.split(":")
     path, kind = parts[0], parts[1]
