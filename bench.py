@@ -538,9 +538,19 @@ def run_ours(args, rank, world, local_rank):
         "residual": residual, "parity": parity, "parity_x_relerr": parity["x_relerr"], "setup_s": t_setup,
         "host_overhead": {"wall_ms_per_step_kernel_leg": wall_dev * 1e3 / K},
     }
-    if not args.no_cpu:
-        out["cpu_baseline"] = cpu_baseline(cfg, args.ref_size or ref_edge, nsteps=2)
     F.close()
+    if not args.no_cpu:
+        # the CPU leg runs in a fresh process (the reference arm's own code path): inside this one torch / CUDA have
+        # already set up their thread pools and the port's OpenMP + BLAS threads ran 2.6x slower than on their own
+        cb = None
+        try:
+            env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "OMP_NUM_THREADS")}
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--config", cfg, "--steps", "2",
+                                "--warmup", "1", "--ref-size", str(args.ref_size or ref_edge)], env=env, capture_output=True, text=True, timeout=900)
+            cb = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])["cpu_baseline"]
+        except Exception as exc:
+            sys.stderr.write("cpu_baseline in a fresh process failed (%s); timing it in-process\n" % exc)
+        out["cpu_baseline"] = cb if cb is not None else cpu_baseline(cfg, args.ref_size or ref_edge, nsteps=2)
     _emit(json.dumps(out))
     if dist:
         dist.destroy_process_group()
@@ -570,6 +580,10 @@ def main():
     def _emit(line):
         os.write(real_stdout, (line + "\n").encode())
     if args.impl == "reference":
+        # torchrun exports OMP_NUM_THREADS=1 for every rank; the CPU arm runs on rank 0 alone and is meant to use all host
+        # cores, so that default is dropped before OpenMP / OpenBLAS are loaded (they read it at load time)
+        if world > 1:
+            os.environ.pop("OMP_NUM_THREADS", None)
         run_reference(args, rank, world)
     else:
         run_ours(args, rank, world, local_rank)
