@@ -185,6 +185,13 @@ int fail(smslu_handle_t h, int code, const std::string& msg) {
     return code;
 }
 
+// Every entry point that touches the device selects the handle's GPU; the caller's current device is put back on return.
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); } }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 #define CU(call)                                                                                  \
     do {                                                                                          \
         cudaError_t e_ = (call);                                                                  \
@@ -1524,6 +1531,7 @@ int smslu_comm_unique_id(void* id, int64_t nbytes) {
 }
 
 int smslu_comm_init(smslu_handle_t h, const void* id, int64_t nbytes) {
+    DeviceGuard device_guard_;
     if (!h || !id || nbytes < (int64_t)sizeof(ncclUniqueId)) return SMSLU_E_ARG;
     if (h->nranks <= 1) return 0;
     if (h->comm) return fail(h, SMSLU_E_ARG, "communicator already initialised");
@@ -1538,6 +1546,7 @@ int smslu_comm_init(smslu_handle_t h, const void* id, int64_t nbytes) {
 }
 
 int smslu_refactor(smslu_handle_t h, const double* nzval, const double* Rs) {
+    DeviceGuard device_guard_;
     if (!h || !nzval) return SMSLU_E_ARG;
     int rc = ensure_uploaded(h);
     if (rc) return rc;
@@ -1567,6 +1576,7 @@ int smslu_refactor(smslu_handle_t h, const double* nzval, const double* Rs) {
 }
 
 int smslu_refactor_async(smslu_handle_t h, const double* nzval_dev, const double* Rs_dev) {
+    DeviceGuard device_guard_;
     if (!h || !nzval_dev) return SMSLU_E_ARG;
     int rc = ensure_uploaded(h);
     if (rc) return rc;
@@ -1580,6 +1590,7 @@ int smslu_refactor_async(smslu_handle_t h, const double* nzval_dev, const double
 }
 
 int smslu_solve_async(smslu_handle_t h, double* x_dev, const double* b_dev) {
+    DeviceGuard device_guard_;
     if (!h || !x_dev || !b_dev) return SMSLU_E_ARG;
     if (!h->uploaded) return fail(h, SMSLU_E_ARG, "no factorization has been enqueued");
     if (!h->factored && !h->pending_refactor) return fail(h, SMSLU_E_ARG, "no valid factorization (call smslu_refactor)");
@@ -1590,6 +1601,7 @@ int smslu_solve_async(smslu_handle_t h, double* x_dev, const double* b_dev) {
 }
 
 int smslu_sync(smslu_handle_t h) {
+    DeviceGuard device_guard_;
     if (!h) return SMSLU_E_ARG;
     if (!h->uploaded) return 0;
     CU(cudaSetDevice(h->device));
@@ -1629,6 +1641,7 @@ static int check_vec(smslu_handle_t h, int64_t len, int64_t nrhs, int64_t ld, co
 
 int smslu_solve(smslu_handle_t h, double* x, int64_t nx, const double* b, int64_t nb,
                 int64_t nrhs, int64_t ldx, int64_t ldb) {
+    DeviceGuard device_guard_;
     if (!h || !x || !b) return SMSLU_E_ARG;
     int rc;
     if ((rc = check_vec(h, nx, nrhs, ldx, "x"))) return rc;
@@ -1678,6 +1691,7 @@ int smslu_solve(smslu_handle_t h, double* x, int64_t nx, const double* b, int64_
 }
 
 static int tri_solve(smslu_handle_t h, double* x, int64_t nx, int64_t nrhs, int64_t ld, bool lower) {
+    DeviceGuard device_guard_;
     if (!h || !x) return SMSLU_E_ARG;
     int rc;
     if ((rc = check_vec(h, nx, nrhs, ld, "x"))) return rc;
@@ -1739,6 +1753,7 @@ int smslu_get_nnz(smslu_handle_t h, int64_t* nnz_l, int64_t* nnz_u) {
 
 int smslu_get_factors(smslu_handle_t h, int64_t* lp, int64_t* li, double* lx, int64_t* up, int64_t* ui,
                       double* ux, int64_t* p, int64_t* q, double* Rs, int32_t index_base) {
+    DeviceGuard device_guard_;
     if (!h || !h->analyzed) return SMSLU_E_ARG;
     if (index_base != 0 && index_base != 1) return SMSLU_E_ARG;
     const Symbolic& S = h->S;
@@ -1822,6 +1837,7 @@ int smslu_get_symbolic(smslu_handle_t h, int64_t* sn_start, int64_t* rows_ptr, i
 }
 
 int smslu_destroy(smslu_handle_t h) {
+    DeviceGuard device_guard_;
     if (!h) return 0;
     if (h->comm) { cudaSetDevice(h->device); nccl_api().CommDestroy(h->comm); h->comm = nullptr; }
     if (h->uploaded || h->stream) {

@@ -269,6 +269,53 @@ def test_multiple_rhs(smslu, O, W, case, nrhs):
     F.close()
 
 
+@pytest.mark.parametrize("n,nrhs", [(200, 33), (131, 12), (40, 70)])
+def test_wide_sweeps_on_dense_matrices_with_given_pivots(smslu, O, W, n, nrhs):
+    """The 32-wide tensor-pipe sweeps on the reference's dense fixture family (rand(n,n), partial pivoting handed in as
+    GIVEN pivots => relabelled internally, chains of 128-column fronts with few rows): ldiv!/lsolve!/rsolve! of a block of
+    right-hand sides against dense solves, at the reference's dense tolerance (test:25-26)."""
+    A = W.dense_random(n, seed=2000 + n)
+    piv = O.OracleLU(A, Rs=O.row_scale_sum(A), diag_tol=2.0)
+    F = smslu.ParallelSparseLU(A, p=piv.p, q=piv.q, Rs=piv.Rs)
+    B = W.rhs(n, 11, nrhs=nrhs)
+    X = np.empty((n, nrhs), order="F")
+    smslu.ldiv_(X, F, B)
+    Xref = np.linalg.solve(A.toarray(), B)
+    assert np.linalg.norm(X - Xref) <= DENSE_TOL * 10 * np.linalg.norm(Xref)
+    L, U = F.L.toarray(), F.U.toarray()
+    Y = B.copy(order="F"); smslu.lsolve_(F, Y)
+    assert np.linalg.norm(Y - np.linalg.solve(L, B)) <= DENSE_TOL * np.linalg.norm(Y)
+    Y = B.copy(order="F"); smslu.rsolve_(F, Y)
+    Yref = np.linalg.solve(U, B)
+    assert np.linalg.norm(Y - Yref) <= DENSE_TOL * 10 * np.linalg.norm(Yref)
+    F.close()
+
+
+def test_wide_sweeps_device_resident_blocks(smslu, W):
+    """Device-resident blocks of right-hand sides (ld = n) through the wide sweeps, twice (the partial-sum scratch and
+    arrival counters of the backward kernel are reused), bitwise equal run to run and equal to the host-buffer call."""
+    import torch
+    A = W.laplacian_3d(16)
+    n, nrhs = A.shape[0], 45
+    F = smslu.ParallelSparseLU(A)
+    B = W.rhs(n, 5, nrhs=nrhs)
+    Xh = np.empty((n, nrhs), order="F"); smslu.ldiv_(Xh, F, B)
+    Bd = torch.from_numpy(np.ascontiguousarray(B.T)).cuda()          # (nrhs, n) row-major == (n, nrhs) column-major
+    Xd = torch.empty_like(Bd)
+    from sharedmemsparselu_jl_b200 import _capi
+    import ctypes as C
+    outs = []
+    for rep in range(2):
+        _capi.check(F._h, _capi.lib().smslu_solve(F._h, C.c_void_p(Xd.data_ptr()), n, C.c_void_p(Bd.data_ptr()), n, nrhs, n, n))
+        torch.cuda.synchronize()
+        outs.append(Xd.cpu().numpy().T.copy())
+    assert np.array_equal(outs[0], outs[1])
+    assert np.array_equal(outs[0], Xh)
+    for r in (0, 31, 32, 44):
+        assert residual(A, outs[0][:, r], B[:, r]) < 1e-12
+    F.close()
+
+
 def test_bitwise_reproducible(smslu, W):
     A = W.laplacian_2d(150)
     n = A.shape[0]
