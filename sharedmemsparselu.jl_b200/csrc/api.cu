@@ -874,8 +874,43 @@ void build_top_fac(smslu_handle_t h, std::vector<int4>& tasks, std::vector<int64
     h->peer_bytes_refactor = 8 * peer_doubles;
 }
 
+// Everything the handle owns on the device: streams, events, allocations, peer mappings.  Used by smslu_destroy and when an
+// upload fails half way (so that a retry starts from a clean handle instead of leaking the first attempt's objects).
+void release_device_state(smslu_handle_t h) {
+    if (!(h->uploaded || h->stream || !h->dev_allocs.empty())) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+    h->ipc_opened.clear();
+    for (void* p : h->dev_allocs) cudaFree(p);
+    h->dev_allocs.clear();
+    cudaEvent_t* evs[] = {&h->ev0, &h->ev1, &h->ev2, &h->ev3, &h->ev_fork, &h->ev_scatter};
+    for (cudaEvent_t* e : evs) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
+    for (cudaEvent_t e : h->pev) cudaEventDestroy(e);
+    h->pev.clear(); h->pev_kind.clear(); h->pev_used = 0;
+    for (auto& m : h->lvl_marks) cudaEventDestroy(m.ev);
+    h->lvl_marks.clear();
+    if (h->h_flag) { cudaFreeHost(h->h_flag); h->h_flag = nullptr; }
+    if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
+    h->stream = nullptr;
+    for (int a = 0; a < NLANES - 1; ++a) {
+        if (h->aux_stream[a]) { cudaStreamSynchronize(h->aux_stream[a]); cudaStreamDestroy(h->aux_stream[a]); h->aux_stream[a] = nullptr; }
+        if (h->ev_join[a]) { cudaEventDestroy(h->ev_join[a]); h->ev_join[a] = nullptr; }
+    }
+    h->uploaded = false; h->factored = false; h->have_wide = false; h->wide_failed = false; h->scatter_pending = false;
+    h->cx = DevCtx{}; h->cx32 = DevCtx{};
+    cudaGetLastError();
+}
+
+int upload_impl(smslu_handle_t h);
 int ensure_uploaded(smslu_handle_t h) {
     if (h->uploaded) { CU(cudaSetDevice(h->device)); return 0; }
+    const int rc = upload_impl(h);
+    if (rc) { const std::string msg = h->err; release_device_state(h); h->err = msg; }
+    return rc;
+}
+
+int upload_impl(smslu_handle_t h) {
     if (!h->analyzed) return fail(h, SMSLU_E_ARG, "smslu_analyze has not been called");
     if (h->nranks > 1 && !h->comm) return fail(h, SMSLU_E_ARG, "partitioned handle: call smslu_comm_init on every rank first");
     double t0 = now_ms();
@@ -1840,25 +1875,7 @@ int smslu_destroy(smslu_handle_t h) {
     DeviceGuard device_guard_;
     if (!h) return 0;
     if (h->comm) { cudaSetDevice(h->device); nccl_api().CommDestroy(h->comm); h->comm = nullptr; }
-    if (h->uploaded || h->stream) {
-        cudaSetDevice(h->device);
-        if (h->stream) cudaStreamSynchronize(h->stream);
-        for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
-        for (void* p : h->dev_allocs) cudaFree(p);
-        if (h->ev0) cudaEventDestroy(h->ev0);
-        if (h->ev1) cudaEventDestroy(h->ev1);
-        if (h->ev2) cudaEventDestroy(h->ev2);
-        if (h->ev3) cudaEventDestroy(h->ev3);
-        for (cudaEvent_t e : h->pev) cudaEventDestroy(e);
-        if (h->h_flag) cudaFreeHost(h->h_flag);
-        if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
-        for (int a = 0; a < NLANES - 1; ++a) {
-            if (h->aux_stream[a]) { cudaStreamSynchronize(h->aux_stream[a]); cudaStreamDestroy(h->aux_stream[a]); }
-            if (h->ev_join[a]) cudaEventDestroy(h->ev_join[a]);
-        }
-        if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-        if (h->ev_scatter) cudaEventDestroy(h->ev_scatter);
-    }
+    release_device_state(h);
     delete h;
     return 0;
 }
