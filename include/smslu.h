@@ -127,7 +127,8 @@ int smslu_analyze(smslu_handle_t h, const int64_t* p, const int64_t* q);
 int smslu_refactor(smslu_handle_t h, const double* nzval, const double* Rs);
 
 /* `ldiv!(x, F, b)` (src:286-342): x = A \ b; b is not modified.  nrhs = 1 is the reference
- * signature; nrhs > 1 solves column-major blocks with leading dimensions ldx, ldb.
+ * signature; nrhs > 1 solves column-major blocks with leading dimensions ldx, ldb (BASELINE config 5):
+ * 32 columns per sweep on the FP64 tensor pipe while at least 9 are left (one GPU), then 8 / 4 / 1.
  * nx / nb are the lengths of x and b per column (checked against n: SMSLU_E_DIM, src:288-290). */
 int smslu_solve(smslu_handle_t h, double* x, int64_t nx, const double* b, int64_t nb,
                 int64_t nrhs, int64_t ldx, int64_t ldb);
