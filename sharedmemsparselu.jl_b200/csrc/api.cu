@@ -76,6 +76,7 @@ constexpr int CHAIN_MAXC_DEFAULT = 32;
 
 constexpr int PANEL_GROUP_CTAS = 296;  // panel launches aim at about this many CTAs (2 per SM) ...
 constexpr int PANEL_GROUP_MAX = 16;    // ... by giving one CTA up to this many 128-row tiles of its front
+constexpr int PANEL_FIT_MAX = 40;      // ... or up to this many where that makes the launch fit one wave of resident CTAs
 constexpr int FWD_WIDE_TILES = 148;   // 64-row forward tiles of a level beyond which 256-row tiles are used
 
 struct Launch {
@@ -245,6 +246,7 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
     int64_t ncounters = 0, slots = 0;
     int cur_level = 0, big_lane = 0;
     // Schur-update CTAs walk strips of this many row tiles of one tile column (k_gemm_strip); 1 = one tile per CTA (k_gemm_cb)
+    const bool panel_fit = !(getenv("SMSLU_PANEL_FIT") && atoi(getenv("SMSLU_PANEL_FIT")) == 0);   // debugging aid / A-B switch
     const int gemm_strip = getenv("SMSLU_GEMM_STRIP") ? std::max(1, atoi(getenv("SMSLU_GEMM_STRIP"))) : GEMM_STRIP_DEFAULT;
     auto push = [&](std::vector<Launch>& v, int kind, int64_t off, int fmax) {
         int nt = (int)((int64_t)tasks.size() - off);
@@ -367,7 +369,21 @@ void build_schedules(smslu_handle_t h, std::vector<int4>& tasks) {
                         tiles_total += std::max(1, tl + tt + ti);
                     }
                     if (tiles_total > 0 && tiles_total < 120) rows = PANEL_ROWS_TOP;     // few tiles: small CTAs
-                    const int group = rows == PANEL_ROWS ? (int)std::min<int64_t>(PANEL_GROUP_MAX, std::max<int64_t>(1, tiles_total / PANEL_GROUP_CTAS)) : 1;
+                    int group = rows == PANEL_ROWS ? (int)std::min<int64_t>(PANEL_GROUP_MAX, std::max<int64_t>(1, tiles_total / PANEL_GROUP_CTAS)) : 1;
+                    if (panel_fit && rows == PANEL_ROWS && tiles_total > PANEL_GROUP_CTAS) {
+                        // the per-front rounding (ceil(tiles / group) CTAs each) pushes a launch past the 2 x 148 resident CTAs and
+                        // the stragglers cost a second round: widen the groups until the launch fits one wave
+                        auto total_ctas = [&](int gsz) {
+                            int64_t tot = 0;
+                            for (int t = 0; t < cnt; ++t) {
+                                if (!in_step(sn[t])) continue;
+                                int tl, tt, ti; tiles_of(sn[t], rows, tl, tt, ti);
+                                tot += (std::max(1, tl + tt + ti) + gsz - 1) / gsz;
+                            }
+                            return tot;
+                        };
+                        while (group < PANEL_FIT_MAX && total_ctas(group) > PANEL_GROUP_CTAS) ++group;
+                    }
                     off = (int64_t)tasks.size();
                     for (int t = 0; t < cnt; ++t) {
                         int s = sn[t];
