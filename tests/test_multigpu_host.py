@@ -1,4 +1,4 @@
-"""CPU, world_size 2 and 4 over gloo: the host-side logic of the multi-GPU path -- partition of the
+"""CPU, world_size 2, 4 and 8 over gloo: the host-side logic of the multi-GPU path -- partition of the
 elimination tree into per-rank subtrees + a replicated top, the three exchange points (top panels +
 interface contribution blocks, forward-solve interface vectors, solution gather) -- walked by
 tests/hostexec.cpp over exactly the layout the CUDA kernels consume."""
@@ -12,7 +12,7 @@ import pytest
 from conftest import ROOT
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_partitioned_walk_over_gloo(world, hostexec, O):
     port = 29600 + world + (os.getpid() % 200)
     procs = []
